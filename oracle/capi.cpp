@@ -1,0 +1,166 @@
+// TEST INFRASTRUCTURE ONLY -- C entry points of the CPU oracle for ctypes (tests/, smoke(), bench.py cpu_baseline).
+#include <cstring>
+#include <memory>
+#include <thread>
+#include <vector>
+
+#include "env.h"
+
+using namespace orc;
+
+struct OrcBatch {
+    Scene scene;
+    std::vector<std::unique_ptr<Env>> envs;
+    std::string err;
+};
+
+static thread_local std::string g_err;
+
+extern "C" {
+
+const char* orc_last_error() { return g_err.c_str(); }
+
+// mode: 0 = policy evaluation (cScenarioPoliEval), 1 = exploration (cScenarioExpMACE)
+OrcBatch* orc_create(const char* pack_path, int num_envs, int mode, const uint64_t* terrain_seeds, uint64_t rng_seed) {
+    try {
+        auto* b = new OrcBatch();
+        b->scene.load(pack_path);
+        for (int i = 0; i < num_envs; ++i) {
+            b->envs.emplace_back(new Env());
+            b->envs.back()->init(&b->scene, i, mode != 0, terrain_seeds ? terrain_seeds[i] : (uint64_t)(1 + i), rng_seed);
+        }
+        return b;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return nullptr;
+    }
+}
+void orc_destroy(OrcBatch* b) { delete b; }
+
+int orc_num_dof(OrcBatch* b) { return b->scene.ndof; }
+int orc_num_joints(OrcBatch* b) { return b->scene.nj; }
+int orc_state_size(OrcBatch* b) { return kNumGroundSamples + 4 * b->scene.nj - 1; }
+
+void orc_set_phys(OrcBatch* b, const double* p7) {
+    PhysParams& pp = b->scene.phys;
+    pp.kn = p7[0]; pp.dn = p7[1]; pp.mu = p7[2]; pp.v_eps = p7[3]; pp.contact_tol = p7[4]; pp.k_lim = p7[5]; pp.d_lim = p7[6];
+}
+void orc_set_explore(OrcBatch* b, int enable, double rate, double temp, double base_rate) {
+    for (auto& e : b->envs) { e->enable_exp = enable != 0; e->exp_rate = rate; e->exp_temp = temp; e->exp_base_rate = base_rate; }
+}
+
+// outer update for all envs, optionally multi-threaded (thread-per-env-slice like cOptScenarioPoliEval::Run)
+void orc_update(OrcBatch* b, double dt, int num_threads) {
+    int n = (int)b->envs.size();
+    if (num_threads <= 1) { for (auto& e : b->envs) e->update(dt); return; }
+    std::vector<std::thread> th;
+    for (int t = 0; t < num_threads; ++t)
+        th.emplace_back([=]() { for (int i = t; i < n; i += num_threads) b->envs[i]->update(dt); });
+    for (auto& t : th) t.join();
+}
+void orc_env_step(OrcBatch* b, int env, double h) { b->envs[env]->env_step(h); }
+void orc_reset(OrcBatch* b, int env) { b->envs[env]->reset(); }
+
+void orc_get_state(OrcBatch* b, int env, double* q, double* qd, double* tau_held, uint8_t* contact) {
+    Env& e = *b->envs[env];
+    int nd = b->scene.ndof, nj = b->scene.nj;
+    if (q) std::memcpy(q, e.q, 8 * nd);
+    if (qd) std::memcpy(qd, e.qd, 8 * nd);
+    if (tau_held) std::memcpy(tau_held, e.tau_held, 8 * nd);
+    if (contact) for (int j = 0; j < nj; ++j) contact[j] = e.contact[j] ? 1 : 0;
+}
+void orc_set_state(OrcBatch* b, int env, const double* q, const double* qd, const double* tau_held, const uint8_t* contact) {
+    Env& e = *b->envs[env];
+    int nd = b->scene.ndof, nj = b->scene.nj;
+    if (q) std::memcpy(e.q, q, 8 * nd);
+    if (qd) std::memcpy(e.qd, qd, 8 * nd);
+    if (tau_held) std::memcpy(e.tau_held, tau_held, 8 * nd);
+    if (contact) for (int j = 0; j < nj; ++j) e.contact[j] = contact[j] != 0;
+    e.update_kin();
+}
+// controller block: [state, phase, first_cycle, cur_cycle_time, prev_cycle_time, cur_stumble, prev_stumble,
+//  prev_com(2), prev_dist(2), action_id, params[30], pd_target[nj], fall(5: dist_counter, contact_counter, sum,
+//  prev_check(2)), fail_fall_dist, exp_critic, exp_actor, cycle_count]
+int orc_get_ctrl(OrcBatch* b, int env, double* out) {
+    Env& e = *b->envs[env];
+    int k = 0;
+    out[k++] = e.state; out[k++] = e.phase; out[k++] = e.first_cycle; out[k++] = e.cur_cycle_time; out[k++] = e.prev_cycle_time;
+    out[k++] = e.cur_stumble; out[k++] = e.prev_stumble; out[k++] = e.prev_com[0]; out[k++] = e.prev_com[1];
+    out[k++] = e.prev_dist[0]; out[k++] = e.prev_dist[1]; out[k++] = e.cur.id;
+    for (int i = 0; i < kDogParams; ++i) out[k++] = e.cur.params[i];
+    for (int j = 0; j < b->scene.nj; ++j) out[k++] = e.pd_target[j];
+    out[k++] = e.fall_dist_counter; out[k++] = e.fall_contact_counter; out[k++] = e.sum_fall_contact;
+    out[k++] = e.prev_check_pos[0]; out[k++] = e.prev_check_pos[1]; out[k++] = e.fail_fall_dist;
+    out[k++] = e.exp_critic; out[k++] = e.exp_actor; out[k++] = e.cycle_count;
+    return k;
+}
+void orc_get_last_tau(OrcBatch* b, int env, double* tau) { std::memcpy(tau, b->envs[env]->last_tau, 8 * b->scene.ndof); }
+void orc_get_poli_state(OrcBatch* b, int env, double* s) {
+    Env& e = *b->envs[env];
+    std::memcpy(s, e.poli_state.data(), 8 * e.poli_state.size());
+}
+void orc_get_net_out(OrcBatch* b, int env, double* y) { std::memcpy(y, b->envs[env]->last_net_out, 8 * b->scene.net.n_out); }
+int orc_get_terrain(OrcBatch* b, int env, int seg, float* data, int cap, double* min_x, int* flip) {
+    Env& e = *b->envs[env];
+    const auto& s = e.ground.seg[seg];
+    int n = (int)s.data.size();
+    for (int i = 0; i < n && i < cap; ++i) data[i] = s.data[i];
+    *min_x = s.min_x;
+    *flip = e.ground.flip ? 1 : 0;
+    return n;
+}
+double orc_sample_height(OrcBatch* b, int env, double x) { return b->envs[env]->ground.sample(x); }
+
+// component probes
+void orc_rbd(OrcBatch* b, int env, double* M, double* C) {
+    Env& e = *b->envs[env];
+    int nd = b->scene.ndof;
+    double pose[kMaxDof];
+    e.build_pose(pose);
+    e.ctrl_model.update(pose, e.qd);
+    for (int a = 0; a < nd; ++a) { for (int c = 0; c < nd; ++c) M[a * nd + c] = e.ctrl_model.M[a][c]; C[a] = e.ctrl_model.C[a]; }
+}
+void orc_forward_dynamics(OrcBatch* b, int env, const double* tau, double dt, double* qdd) {
+    b->envs[env]->forward_dynamics(tau, dt, qdd, false);
+}
+void orc_net_eval(OrcBatch* b, const double* x, double* y) { b->scene.net.eval(x, y); }
+void orc_com(OrcBatch* b, int env, double* com, double* com_vel) {
+    Env& e = *b->envs[env];
+    e.update_kin();
+    e.calc_com(com, com_vel);
+}
+
+// tuples: rows of [reward | s(S) | a(A) | s'(S)] doubles, flags, env ids; drained by orc_reset_tuples
+int orc_num_tuples(OrcBatch* b) { int n = 0; for (auto& e : b->envs) n += (int)e->tuples.size(); return n; }
+int orc_get_tuples(OrcBatch* b, double* rows, uint32_t* flags, int32_t* env_id, int cap) {
+    int S = orc_state_size(b), A = 1 + kDogOptParams, n = 0;
+    for (auto& e : b->envs)
+        for (auto& t : e->tuples) {
+            if (n >= cap) return n;
+            double* r = rows + (size_t)n * (1 + S + A + S);
+            r[0] = t.reward;
+            std::memcpy(r + 1, t.s_beg.data(), 8 * S);
+            std::memcpy(r + 1 + S, t.action.data(), 8 * A);
+            std::memcpy(r + 1 + S + A, t.s_end.data(), 8 * S);
+            flags[n] = t.flags;
+            env_id[n] = e->env_id;
+            ++n;
+        }
+    return n;
+}
+void orc_reset_tuples(OrcBatch* b) { for (auto& e : b->envs) e->tuples.clear(); }
+
+void orc_eval_stats(OrcBatch* b, int64_t* cycles, int64_t* episodes, double* avg_dist, int64_t* steps) {
+    int64_t c = 0, ep = 0, st = 0;
+    double sum = 0;
+    for (auto& e : b->envs) { c += e->cycle_count; ep += e->episode_count; sum += e->avg_dist * e->episode_count; st += e->total_steps; }
+    *cycles = c; *episodes = ep; *avg_dist = ep ? sum / ep : 0; *steps = st;
+}
+int orc_dist_log(OrcBatch* b, int env, double* out, int cap) {
+    auto& l = b->envs[env]->dist_log;
+    int n = (int)l.size();
+    for (int i = 0; i < n && i < cap; ++i) out[i] = l[i];
+    return n;
+}
+
+}  // extern "C"
