@@ -1,0 +1,61 @@
+// deepterrainrl_b200 -- reader for `.trlpack` scene files (named f64 / i32 arrays; written by tools/pack_scene.py
+// from the reference's arg file + JSON assets + Caffe HDF5 weights).
+// Layout: "TRLPACK1", u32 record count, then {u32 name_len, name, u32 dtype (0 f64 | 1 i32), u64 count, payload}.
+#pragma once
+#include <cstdint>
+#include <fstream>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+namespace trl {
+
+class ScenePack {
+public:
+    bool load(const std::string& path, std::string* err) {
+        std::ifstream in(path, std::ios::binary);
+        if (!in) { if (err) *err = "cannot open scene pack: " + path; return false; }
+        char magic[8];
+        in.read(magic, 8);
+        if (!in || std::string(magic, 8) != "TRLPACK1") { if (err) *err = "not a TRLPACK1 file: " + path; return false; }
+        uint32_t count = 0;
+        in.read(reinterpret_cast<char*>(&count), 4);
+        for (uint32_t r = 0; r < count && in; ++r) {
+            uint32_t len = 0, dtype = 0;
+            uint64_t n = 0;
+            in.read(reinterpret_cast<char*>(&len), 4);
+            std::string name(len, ' ');
+            in.read(&name[0], len);
+            in.read(reinterpret_cast<char*>(&dtype), 4);
+            in.read(reinterpret_cast<char*>(&n), 8);
+            if (dtype == 1) {
+                std::vector<int32_t>& v = ints_[name];
+                v.resize(n);
+                in.read(reinterpret_cast<char*>(v.data()), (std::streamsize)(n * 4));
+            } else {
+                std::vector<double>& v = reals_[name];
+                v.resize(n);
+                in.read(reinterpret_cast<char*>(v.data()), (std::streamsize)(n * 8));
+            }
+        }
+        if (!in) { if (err) *err = "truncated scene pack: " + path; return false; }
+        return true;
+    }
+    const std::vector<double>& f64(const std::string& name) const {
+        static const std::vector<double> empty;
+        auto it = reals_.find(name);
+        return it == reals_.end() ? empty : it->second;
+    }
+    const std::vector<int32_t>& i32(const std::string& name) const {
+        static const std::vector<int32_t> empty;
+        auto it = ints_.find(name);
+        return it == ints_.end() ? empty : it->second;
+    }
+    bool has(const std::string& name) const { return reals_.count(name) || ints_.count(name); }
+
+private:
+    std::unordered_map<std::string, std::vector<double>> reals_;
+    std::unordered_map<std::string, std::vector<int32_t>> ints_;
+};
+
+}  // namespace trl

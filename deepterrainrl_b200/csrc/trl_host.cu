@@ -1,0 +1,570 @@
+// deepterrainrl_b200 -- host runtime behind the C ABI (include/terrainrl_b200.h).
+// Owns device memory (plain cudaMalloc; no torch in the boundary), the CUDA stream, the captured CUDA graph of one
+// outer update (21 step launches + 20 decision launches) and the pinned staging buffers for tuple / statistics reads.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/terrainrl_b200.h"
+#include "scene_pack.h"
+#include "trl_types.h"
+
+namespace trl {
+cudaError_t upload_model(const ModelConst& mc);
+size_t step_smem_bytes();
+cudaError_t configure_step_kernels();
+void launch_step(const Buffers& B, double h, int flags, cudaStream_t st);
+void launch_reset(const Buffers& B, const uint64_t* seeds, const int* env_ids, int count, int reseed, cudaStream_t st);
+size_t decide_smem_bytes();
+cudaError_t configure_decide_kernel();
+void launch_decide(const Buffers& B, const NetWeights& W, const ExpSettings& ex, int* done_count, int grid, cudaStream_t st);
+}  // namespace trl
+
+using namespace trl;
+
+static thread_local std::string g_err;
+static int fail(const std::string& msg) { g_err = msg; return 1; }
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess) return fail(std::string(#call) + ": " + cudaGetErrorString(e__)); \
+    } while (0)
+
+static const char* kNetLayers[13] = {"terr_conv0", "terr_conv1", "terr_conv2", "terr_ip0", "ip0", "val_ip0", "val_ip1",
+                                     "a0_ip0", "a0_ip1", "a1_ip0", "a1_ip1", "a2_ip0", "a2_ip1"};
+
+struct trl_handle {
+    int device = 0, n = 0, mode = 0;
+    ScenePack scene;
+    ModelConst mc;
+    ExpSettings ex;
+    Buffers B;
+    NetWeights W;
+    std::vector<double*> net_blobs;      // 26 + 4 device arrays
+    std::vector<int64_t> net_counts;
+    int* done_count = nullptr;
+    cudaStream_t stream = nullptr;
+    int decide_grid = 296;
+    int num_update_steps = 20;
+    int64_t launches = 0;
+    std::map<long long, cudaGraphExec_t> graphs;   // keyed by the bit pattern of dt
+    bool use_graph = true;
+    // host staging
+    std::vector<double> h_tuples;
+    std::vector<float> h_tuples_f32;
+    std::vector<uint32_t> h_tuple_flags;
+    std::vector<int32_t> h_tuple_env;
+    std::vector<double> h_dist;
+    std::vector<int32_t> h_dist_env;
+    std::vector<void*> allocs;
+};
+
+template <typename T>
+static cudaError_t dalloc(trl_handle* h, T** p, size_t count) {
+    cudaError_t e = cudaMalloc((void**)p, count * sizeof(T));
+    if (e == cudaSuccess) { h->allocs.push_back(*p); e = cudaMemset(*p, 0, count * sizeof(T)); }
+    return e;
+}
+
+static int fill_model(trl_handle* h, uint64_t rng_seed) {
+    const ScenePack& s = h->scene;
+    ModelConst& m = h->mc;
+    std::memset(&m, 0, sizeof(m));
+    const auto& mi = s.i32("meta_i32");
+    const auto& mf = s.f64("meta_f64");
+    int char_type = mi[0], ctrl = mi[1];
+    m.nj = mi[8]; m.ndof = mi[9];
+    if (char_type != 1 || m.nj != 21 || m.ndof != 23) return fail("only the dog / goat skeleton (21 joints, 23 dof) is supported in this build");
+    h->num_update_steps = mi[2];
+    m.num_sim_substeps = mi[3];
+    m.has_init_x = mi[4]; m.init_x = mf[2];
+    m.terrain_type = mi[5];
+    int n_sets = mi[6];
+    m.has_net = mi[7];
+    m.n_ctrl = mi[10]; m.n_actions = mi[11]; m.default_action = mi[12]; m.grav_comp = mi[13]; m.virt_forces = mi[14];
+    if (m.n_ctrl > kMaxCtrlSets || m.n_actions > kMaxActions) return fail("too many controller sets / actions");
+    m.is_mace = (ctrl == 3 || ctrl == 4) ? 1 : 0;
+    m.target_vel_x = (ctrl == 4) ? 2.0 : 4.0;   // sim/GoatControllerMACE.cpp:11-14, sim/DogController.cpp:625-628
+    m.gx = mf[0]; m.gy = mf[1];
+    m.exp_mode = h->mode == TRL_MODE_EXPLORE;
+    m.rng_seed = rng_seed;
+    const auto& J = s.f64("joints");
+    const auto& Bd = s.f64("bodies");
+    const auto& P = s.f64("pd");
+    int off = 0;
+    m.total_mass = 0;
+    for (int j = 0; j < m.nj; ++j) {
+        const double* r = &J[7 * j];
+        int type = (int)r[0];
+        m.parent[j] = (int)r[1];
+        if ((j == 0) != (m.parent[j] < 0) || (j == 0 && type != 1) || (j > 0 && type != 0)) return fail("unsupported joint layout");
+        m.attach_x[j] = r[2]; m.attach_y[j] = r[3];
+        m.lim_lo[j] = r[5]; m.lim_hi[j] = r[6];
+        m.has_limit[j] = (j > 0 && r[5] <= r[6]) ? 1 : 0;
+        m.dof[j] = off;
+        off += (j == 0) ? 3 : 1;
+        const double* b = &Bd[9 * j];
+        if ((int)b[0] != 0) return fail("only box bodies are supported");
+        m.mass[j] = b[1]; m.body_ax[j] = b[2]; m.body_ay[j] = b[3]; m.body_theta[j] = b[5];
+        m.body_cos[j] = std::cos(b[5]); m.body_sin[j] = std::sin(b[5]);
+        m.half_x[j] = 0.5 * b[6]; m.half_y[j] = 0.5 * b[7];
+        // planar inertia about the joint origin: box about its COM + parallel-axis shift (sim/RBDUtil.cpp:562-583,614-623)
+        m.izz_o[j] = b[1] / 12.0 * (b[6] * b[6] + b[7] * b[7]) + b[1] * (b[2] * b[2] + b[3] * b[3]);
+        m.total_mass += b[1];
+        // tail parts carry collision group "none" (sim/SimDog.cpp:7,21-24)
+        m.collidable[j] = (j >= 9 && j <= 12) ? 0 : 1;
+        const double* p = &P[6 * j];
+        m.kp[j] = (j == 0) ? 0.0 : p[0]; m.kd[j] = (j == 0) ? 0.0 : p[1];
+        m.torque_lim[j] = p[2]; m.target_theta0[j] = p[3]; m.target_vel[j] = p[4]; m.world_pd[j] = p[5] != 0;
+    }
+    const auto& C = s.f64("ctrl_params");
+    for (int c = 0; c < m.n_ctrl; ++c)
+        for (int k = 0; k < kNumParams; ++k) m.ctrl_params[c][k] = C[c * kNumParams + k];
+    const auto& A = s.f64("actions");
+    for (int a = 0; a < m.n_actions; ++a) {
+        m.act_idx0[a] = (int)A[4 * a]; m.act_idx1[a] = (int)A[4 * a + 1]; m.act_blend[a] = A[4 * a + 2]; m.act_cyclic[a] = A[4 * a + 3] != 0;
+    }
+    const auto& p0 = s.f64("pose0");
+    const auto& v0 = s.f64("vel0");
+    for (int k = 0; k < m.ndof; ++k) { m.pose0[k] = p0[k]; m.vel0[k] = v0[k]; }
+    // cScenarioSimChar::SetTerrainParamsLerp (scenarios/ScenarioSimChar.cpp:255-272)
+    const auto& tp = s.f64("terrain_params");
+    const auto& td = s.f64("terrain_default_params");
+    if (n_sets == 0) for (int i = 0; i < kTerrainParams; ++i) m.terrain_params[i] = td[i];
+    else {
+        double lerp = std::min(std::max(mf[3], 0.0), n_sets - 1.0);
+        int i0 = (int)lerp, i1 = std::min(i0 + 1, n_sets - 1);
+        lerp -= i0;
+        for (int i = 0; i < kTerrainParams; ++i) m.terrain_params[i] = (1 - lerp) * tp[i0 * kTerrainParams + i] + lerp * tp[i1 * kTerrainParams + i];
+    }
+    m.phys = PhysParams{2.0e5, 2.0e3, 0.81, 0.01, 0.00025, 2.0e4, 20.0};
+    h->ex = ExpSettings{h->mode == TRL_MODE_EXPLORE ? 1 : 0, mf[4], mf[5], mf[6], 0.2};
+    if (m.has_net) {
+        const auto& nd = s.i32("net_dims");
+        m.n_in = nd[0]; m.n_char = nd[1]; m.n_out = nd[2]; m.n_frags = nd[3]; m.frag = nd[4];
+        if (m.n_out > kMaxNetOut || m.frag > 32 || m.n_frags > 8 || m.n_char > 96) return fail("unsupported net dimensions");
+        const auto& os = s.f64("net_out_scale");
+        for (int k = 0; k < m.frag; ++k) m.out_scale_actor0[k] = os[m.n_frags + k];
+    }
+    return 0;
+}
+
+static int upload_net(trl_handle* h, const double* const* blobs, const int64_t* counts, const double* const* vecs4, const int64_t* vcounts) {
+    // blobs: 26 (w, b per layer), vecs4: in_off, in_scale, out_off, out_scale
+    if (h->net_blobs.empty()) {
+        h->net_blobs.assign(30, nullptr);
+        h->net_counts.assign(30, 0);
+        for (int i = 0; i < 30; ++i) {
+            int64_t c = i < 26 ? counts[i] : vcounts[i - 26];
+            h->net_counts[i] = c;
+            CK(dalloc(h, &h->net_blobs[i], (size_t)c));
+        }
+    }
+    for (int i = 0; i < 30; ++i) {
+        int64_t c = i < 26 ? counts[i] : vcounts[i - 26];
+        if (c != h->net_counts[i]) return fail("trl_set_weights: blob size mismatch");
+        const double* src = i < 26 ? blobs[i] : vecs4[i - 26];
+        CK(cudaMemcpyAsync(h->net_blobs[i], src, (size_t)c * 8, cudaMemcpyHostToDevice, h->stream));
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    NetWeights& W = h->W;
+    double** b = h->net_blobs.data();
+    W.conv0_w = b[0]; W.conv0_b = b[1]; W.conv1_w = b[2]; W.conv1_b = b[3]; W.conv2_w = b[4]; W.conv2_b = b[5];
+    W.tip0_w = b[6]; W.tip0_b = b[7]; W.ip0_w = b[8]; W.ip0_b = b[9];
+    for (int k = 0; k < 4; ++k) { W.h0_w[k] = b[10 + 4 * k]; W.h0_b[k] = b[11 + 4 * k]; W.h1_w[k] = b[12 + 4 * k]; W.h1_b[k] = b[13 + 4 * k]; }
+    W.in_off = b[26]; W.in_scale = b[27]; W.out_off = b[28]; W.out_scale = b[29];
+    return 0;
+}
+
+static void destroy_graphs(trl_handle* h) {
+    for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second);
+    h->graphs.clear();
+}
+
+static void enqueue_update(trl_handle* h, double dt) {
+    const int ns = h->num_update_steps;
+    const double step = dt / ns;
+    for (int i = 0; i < ns; ++i) {
+        launch_step(h->B, step, i == 0 ? 2 : 3, h->stream);
+        launch_decide(h->B, h->W, h->ex, h->done_count, h->decide_grid, h->stream);
+    }
+    launch_step(h->B, step, 1 | 4, h->stream);
+}
+
+extern "C" {
+
+const char* trl_last_error(void) { return g_err.c_str(); }
+
+trl_handle* trl_create_from_pack(const char* pack_path, int num_envs, int device, int mode, const uint64_t* terrain_seeds,
+                                 uint64_t rng_seed) {
+    auto* h = new trl_handle();
+    auto bail = [&](const std::string& why) -> trl_handle* {
+        if (!why.empty()) g_err = why;
+        trl_destroy(h);
+        return nullptr;
+    };
+    h->device = device; h->n = num_envs; h->mode = mode;
+    if (num_envs <= 0) return bail("num_envs must be positive");
+    std::string err;
+    if (!h->scene.load(pack_path, &err)) return bail(err);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return bail("terrainrl_b200 needs a CUDA device: no GPU visible (the product path has no CPU fallback)");
+    if (cudaSetDevice(device) != cudaSuccess) return bail("cudaSetDevice failed");
+    if (fill_model(h, rng_seed)) return bail("");
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return bail("cudaStreamCreate failed");
+    auto ck = [&](cudaError_t e, const char* what) -> bool {
+        if (e != cudaSuccess) { g_err = std::string(what) + ": " + cudaGetErrorString(e); return false; }
+        return true;
+    };
+    if (!ck(upload_model(h->mc), "upload_model")) return bail("");
+    if (!ck(configure_step_kernels(), "configure_step_kernels")) return bail("");
+    if (!ck(configure_decide_kernel(), "configure_decide_kernel")) return bail("");
+    Buffers& B = h->B;
+    std::memset(&B, 0, sizeof(B));
+    const size_t n = (size_t)num_envs;
+    B.n = num_envs;
+    B.S = kNumGroundSamples + 4 * h->mc.nj - 1;
+    const int A = kNumParams;
+    B.tuple_cap = std::max(4096, num_envs);   // >= one tuple per env per outer update (a cycle lasts >> 20 env-steps)
+    B.dist_cap = std::max(65536, 16 * num_envs);
+    bool ok = ck(dalloc(h, &B.d, (size_t)D_NUM_FIELDS * n), "alloc d") && ck(dalloc(h, &B.i, (size_t)I_NUM_FIELDS * n), "alloc i") &&
+              ck(dalloc(h, &B.terrain, n * 2 * kTerrainCap), "alloc terrain") && ck(dalloc(h, &B.poli_state, n * B.S), "alloc poli") &&
+              ck(dalloc(h, &B.net_out, n * kMaxNetOut), "alloc net_out") && ck(dalloc(h, &B.tuple_sbeg, n * B.S), "alloc sbeg") &&
+              ck(dalloc(h, &B.tuple_action, n * kNumParams), "alloc action") && ck(dalloc(h, &B.com_stash, 2 * n), "alloc com") &&
+              ck(dalloc(h, &B.pending_list, n), "alloc pending") && ck(dalloc(h, &B.pending_count, 1), "alloc pc") &&
+              ck(dalloc(h, &B.tuples, (size_t)B.tuple_cap * (1 + B.S + A + B.S)), "alloc tuples") &&
+              ck(dalloc(h, &B.tuple_flags, (size_t)B.tuple_cap), "alloc tf") && ck(dalloc(h, &B.tuple_env, (size_t)B.tuple_cap), "alloc te") &&
+              ck(dalloc(h, &B.tuple_count, 1), "alloc tc") && ck(dalloc(h, &B.dist_log, (size_t)B.dist_cap), "alloc dl") &&
+              ck(dalloc(h, &B.dist_env, (size_t)B.dist_cap), "alloc de") && ck(dalloc(h, &B.dist_count, 1), "alloc dc") &&
+              ck(dalloc(h, &h->done_count, 1), "alloc done");
+    if (!ok) return bail("");
+    if (h->mc.has_net) {
+        const double* blobs[26];
+        int64_t counts[26];
+        for (int l = 0; l < 13; ++l) {
+            const auto& w = h->scene.f64(std::string("net_") + kNetLayers[l] + "_w");
+            const auto& b = h->scene.f64(std::string("net_") + kNetLayers[l] + "_b");
+            blobs[2 * l] = w.data(); counts[2 * l] = (int64_t)w.size();
+            blobs[2 * l + 1] = b.data(); counts[2 * l + 1] = (int64_t)b.size();
+        }
+        const char* vn[4] = {"net_in_offset", "net_in_scale", "net_out_offset", "net_out_scale"};
+        const double* vecs[4];
+        int64_t vcounts[4];
+        for (int k = 0; k < 4; ++k) { const auto& v = h->scene.f64(vn[k]); vecs[k] = v.data(); vcounts[k] = (int64_t)v.size(); }
+        if (upload_net(h, blobs, counts, vecs, vcounts)) return bail("");
+    } else {
+        std::memset(&h->W, 0, sizeof(h->W));
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) h->decide_grid = 2 * prop.multiProcessorCount;
+    if (trl_seed_terrain(h, terrain_seeds, terrain_seeds ? num_envs : 0)) return bail("");
+    return h;
+}
+
+int trl_destroy(trl_handle* h) {
+    if (!h) return 0;
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    destroy_graphs(h);
+    for (void* p : h->allocs) cudaFree(p);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return 0;
+}
+
+int trl_seed_terrain(trl_handle* h, const uint64_t* seeds, int n) {
+    uint64_t* d_seeds = nullptr;
+    if (seeds) {
+        if (n != h->n) return fail("trl_seed_terrain: need one seed per env");
+        CK(cudaMalloc((void**)&d_seeds, (size_t)n * 8));
+        CK(cudaMemcpyAsync(d_seeds, seeds, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
+    }
+    CK(cudaMemsetAsync(h->B.pending_count, 0, 4, h->stream));
+    launch_reset(h->B, d_seeds, nullptr, h->n, 1, h->stream);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));
+    if (d_seeds) cudaFree(d_seeds);
+    return 0;
+}
+
+int trl_reset(trl_handle* h, const int32_t* env_ids, int n) {
+    int* d_ids = nullptr;
+    int count = h->n;
+    if (env_ids) {
+        count = n;
+        CK(cudaMalloc((void**)&d_ids, (size_t)n * 4));
+        CK(cudaMemcpyAsync(d_ids, env_ids, (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
+    }
+    launch_reset(h->B, nullptr, d_ids, count, 0, h->stream);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));
+    if (d_ids) cudaFree(d_ids);
+    return 0;
+}
+
+int trl_update(trl_handle* h, double dt) {
+    if (!(dt > 0)) return 0;
+    const int nlaunch = 2 * h->num_update_steps + 1;
+    if (h->use_graph) {
+        long long key;
+        std::memcpy(&key, &dt, 8);
+        auto it = h->graphs.find(key);
+        if (it == h->graphs.end()) {
+            cudaGraph_t graph;
+            CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+            enqueue_update(h, dt);
+            CK(cudaStreamEndCapture(h->stream, &graph));
+            cudaGraphExec_t exec;
+            CK(cudaGraphInstantiate(&exec, graph, 0));
+            cudaGraphDestroy(graph);
+            it = h->graphs.emplace(key, exec).first;
+        }
+        CK(cudaGraphLaunch(it->second, h->stream));
+    } else {
+        enqueue_update(h, dt);
+        CK(cudaGetLastError());
+    }
+    h->launches += nlaunch;
+    return 0;
+}
+
+int trl_env_step(trl_handle* h, double step) {
+    launch_step(h->B, step, 2, h->stream);
+    launch_decide(h->B, h->W, h->ex, h->done_count, h->decide_grid, h->stream);
+    launch_step(h->B, step, 1, h->stream);
+    h->launches += 3;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int trl_sync(trl_handle* h) {
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int trl_set_explore(trl_handle* h, int enable, double rate, double temp, double base_rate) {
+    CK(cudaStreamSynchronize(h->stream));
+    h->ex.enable = enable; h->ex.rate = rate; h->ex.temp = temp; h->ex.base_rate = base_rate;
+    destroy_graphs(h);   // kernel parameters are baked into captured graphs
+    return 0;
+}
+
+int trl_set_phys_params(trl_handle* h, const double* p) {
+    CK(cudaStreamSynchronize(h->stream));
+    h->mc.phys = PhysParams{p[0], p[1], p[2], p[3], p[4], p[5], p[6]};
+    CK(upload_model(h->mc));
+    return 0;
+}
+
+int trl_set_weights(trl_handle* h, const double* const* blobs, const int64_t* counts, int nblobs, const double* in_off,
+                    const double* in_scale, const double* out_off, const double* out_scale) {
+    if (nblobs != 26) return fail("trl_set_weights: expected 26 blobs");
+    if (!h->mc.has_net) return fail("trl_set_weights: scene has no policy net");
+    CK(cudaStreamSynchronize(h->stream));
+    const double* vecs[4] = {in_off, in_scale, out_off, out_scale};
+    int64_t vcounts[4] = {h->mc.n_in, h->mc.n_in, h->mc.n_out, h->mc.n_out};
+    if (upload_net(h, blobs, counts, vecs, vcounts)) return 1;
+    for (int k = 0; k < h->mc.frag; ++k) h->mc.out_scale_actor0[k] = out_scale[h->mc.n_frags + k];
+    CK(upload_model(h->mc));
+    return 0;
+}
+
+int trl_sizes(trl_handle* h, int* num_envs, int* state, int* action, int* num_frags, int* frag_size, int* num_dof, int* num_joints) {
+    if (num_envs) *num_envs = h->n;
+    if (state) *state = h->B.S;
+    if (action) *action = kNumParams;
+    if (num_frags) *num_frags = h->mc.n_frags;
+    if (frag_size) *frag_size = kNumParams - 1;
+    if (num_dof) *num_dof = h->mc.ndof;
+    if (num_joints) *num_joints = h->mc.nj;
+    return 0;
+}
+
+static int fetch_tuples(trl_handle* h, int* n_out) {
+    int n = 0;
+    CK(cudaMemcpyAsync(&n, h->B.tuple_count, 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (n > h->B.tuple_cap) n = h->B.tuple_cap;
+    const size_t W = 1 + h->B.S + kNumParams + h->B.S;
+    h->h_tuples.resize((size_t)std::max(n, 1) * W);
+    h->h_tuple_flags.resize(std::max(n, 1));
+    h->h_tuple_env.resize(std::max(n, 1));
+    if (n > 0) {
+        CK(cudaMemcpyAsync(h->h_tuples.data(), h->B.tuples, (size_t)n * W * 8, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(h->h_tuple_flags.data(), h->B.tuple_flags, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(h->h_tuple_env.data(), h->B.tuple_env, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    *n_out = n;
+    return 0;
+}
+
+int trl_num_tuples(trl_handle* h, int* out) {
+    int n = 0;
+    CK(cudaMemcpyAsync(&n, h->B.tuple_count, 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    *out = std::min(n, h->B.tuple_cap);
+    return 0;
+}
+
+int trl_get_tuples_f64(trl_handle* h, const double** rows, const uint32_t** flags, const int32_t** env_id, int* n) {
+    if (fetch_tuples(h, n)) return 1;
+    *rows = h->h_tuples.data(); *flags = h->h_tuple_flags.data(); *env_id = h->h_tuple_env.data();
+    return 0;
+}
+
+int trl_get_tuples(trl_handle* h, const float** rows, const uint32_t** flags, const int32_t** env_id, int* n) {
+    if (fetch_tuples(h, n)) return 1;
+    const size_t W = 1 + h->B.S + kNumParams + h->B.S;
+    h->h_tuples_f32.resize((size_t)std::max(*n, 1) * W);
+    for (size_t k = 0; k < (size_t)*n * W; ++k) h->h_tuples_f32[k] = (float)h->h_tuples[k];
+    *rows = h->h_tuples_f32.data(); *flags = h->h_tuple_flags.data(); *env_id = h->h_tuple_env.data();
+    return 0;
+}
+
+int trl_reset_tuples(trl_handle* h) {
+    CK(cudaMemsetAsync(h->B.tuple_count, 0, 4, h->stream));
+    return 0;
+}
+
+int trl_eval_stats(trl_handle* h, int64_t* cycles, int64_t* episodes, double* avg_dist, int64_t* env_steps) {
+    const size_t n = (size_t)h->n;
+    std::vector<int> cyc(n), eps(n), lo(n), hi(n);
+    std::vector<double> avg(n);
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(cyc.data(), h->B.i + (size_t)I_CYCLE_COUNT * n, n * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(eps.data(), h->B.i + (size_t)I_EPISODE_COUNT * n, n * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(lo.data(), h->B.i + (size_t)I_STEPS_LO * n, n * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(hi.data(), h->B.i + (size_t)I_STEPS_HI * n, n * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(avg.data(), h->B.d + (size_t)D_AVG_DIST * n, n * 8, cudaMemcpyDeviceToHost));
+    int64_t c = 0, e = 0, st = 0;
+    double sum = 0;
+    for (size_t k = 0; k < n; ++k) {
+        c += cyc[k]; e += eps[k]; sum += avg[k] * eps[k];
+        st += ((int64_t)hi[k] << 32) | (uint32_t)lo[k];
+    }
+    if (cycles) *cycles = c;
+    if (episodes) *episodes = e;
+    if (avg_dist) *avg_dist = e ? sum / e : 0.0;
+    if (env_steps) *env_steps = st;
+    return 0;
+}
+
+int trl_dist_log(trl_handle* h, const double** dist, const int32_t** env_id, int* n) {
+    int cnt = 0;
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(&cnt, h->B.dist_count, 4, cudaMemcpyDeviceToHost));
+    cnt = std::min(cnt, h->B.dist_cap);
+    h->h_dist.resize(std::max(cnt, 1));
+    h->h_dist_env.resize(std::max(cnt, 1));
+    if (cnt > 0) {
+        CK(cudaMemcpy(h->h_dist.data(), h->B.dist_log, (size_t)cnt * 8, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(h->h_dist_env.data(), h->B.dist_env, (size_t)cnt * 4, cudaMemcpyDeviceToHost));
+    }
+    *dist = h->h_dist.data(); *env_id = h->h_dist_env.data(); *n = cnt;
+    return 0;
+}
+
+static int copy_plane_d(trl_handle* h, int field, int count, int env, double* out) {
+    // strided gather of `count` consecutive planes for one env
+    return cudaMemcpy2D(out, 8, h->B.d + (size_t)field * h->n + env, (size_t)h->n * 8, 8, count, cudaMemcpyDeviceToHost) != cudaSuccess;
+}
+static int copy_plane_i(trl_handle* h, int field, int count, int env, int* out) {
+    return cudaMemcpy2D(out, 4, h->B.i + (size_t)field * h->n + env, (size_t)h->n * 4, 4, count, cudaMemcpyDeviceToHost) != cudaSuccess;
+}
+
+int trl_get_state(trl_handle* h, int env, double* pose, double* vel, double* held_torque, uint8_t* contact) {
+    if (env < 0 || env >= h->n) return fail("env out of range");
+    CK(cudaStreamSynchronize(h->stream));
+    int nd = h->mc.ndof;
+    if (pose && copy_plane_d(h, D_Q, nd, env, pose)) return fail("copy failed");
+    if (vel && copy_plane_d(h, D_QD, nd, env, vel)) return fail("copy failed");
+    if (held_torque && copy_plane_d(h, D_TAU, nd, env, held_torque)) return fail("copy failed");
+    if (contact) {
+        int mask = 0;
+        if (copy_plane_i(h, I_CONTACT, 1, env, &mask)) return fail("copy failed");
+        for (int j = 0; j < h->mc.nj; ++j) contact[j] = (mask >> j) & 1;
+    }
+    return 0;
+}
+
+int trl_set_state(trl_handle* h, int env, const double* pose, const double* vel, const double* held_torque, const uint8_t* contact) {
+    if (env < 0 || env >= h->n) return fail("env out of range");
+    CK(cudaStreamSynchronize(h->stream));
+    int nd = h->mc.ndof;
+    auto put = [&](int field, const double* src) {
+        return cudaMemcpy2D(h->B.d + (size_t)field * h->n + env, (size_t)h->n * 8, src, 8, 8, nd, cudaMemcpyHostToDevice);
+    };
+    if (pose) CK(put(D_Q, pose));
+    if (vel) CK(put(D_QD, vel));
+    if (held_torque) CK(put(D_TAU, held_torque));
+    if (contact) {
+        int mask = 0;
+        for (int j = 0; j < h->mc.nj; ++j) if (contact[j]) mask |= 1 << j;
+        CK(cudaMemcpy(h->B.i + (size_t)I_CONTACT * h->n + env, &mask, 4, cudaMemcpyHostToDevice));
+    }
+    return 0;
+}
+
+int trl_get_state_all(trl_handle* h, double* pose, double* vel) {
+    CK(cudaStreamSynchronize(h->stream));
+    size_t bytes = (size_t)h->mc.ndof * h->n * 8;
+    if (pose) CK(cudaMemcpy(pose, h->B.d + (size_t)D_Q * h->n, bytes, cudaMemcpyDeviceToHost));
+    if (vel) CK(cudaMemcpy(vel, h->B.d + (size_t)D_QD * h->n, bytes, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int trl_get_ctrl(trl_handle* h, int env, double* out, int cap, int* n_out) {
+    if (env < 0 || env >= h->n) return fail("env out of range");
+    CK(cudaStreamSynchronize(h->stream));
+    std::vector<double> d(D_NUM_FIELDS);
+    std::vector<int> iv(I_NUM_FIELDS);
+    if (copy_plane_d(h, 0, D_NUM_FIELDS, env, d.data()) || copy_plane_i(h, 0, I_NUM_FIELDS, env, iv.data())) return fail("copy failed");
+    std::vector<double> o;
+    o.push_back(iv[I_STATE]); o.push_back(d[D_PHASE]); o.push_back(iv[I_FIRST_CYCLE]); o.push_back(d[D_CUR_CYCLE_T]);
+    o.push_back(d[D_PREV_CYCLE_T]); o.push_back(d[D_CUR_STUMBLE]); o.push_back(d[D_PREV_STUMBLE]); o.push_back(d[D_PREV_COM_X]);
+    o.push_back(d[D_PREV_COM_Y]); o.push_back(d[D_PREV_DIST_X]); o.push_back(d[D_PREV_DIST_Y]); o.push_back(iv[I_ACTION_ID]);
+    for (int k = 0; k < kNumParams; ++k) o.push_back(d[D_PARAMS + k]);
+    for (int j = 0; j < h->mc.nj; ++j) o.push_back(d[D_PD_TARGET + j]);
+    o.push_back(d[D_FALL_DIST_CNT]); o.push_back(d[D_FALL_CONTACT_CNT]); o.push_back(d[D_SUM_FALL]); o.push_back(d[D_PREV_CHECK_X]);
+    o.push_back(d[D_PREV_CHECK_Y]); o.push_back(iv[I_FAIL_FALL_DIST]); o.push_back(iv[I_EXP_FLAGS] & 1); o.push_back((iv[I_EXP_FLAGS] >> 1) & 1);
+    o.push_back(iv[I_CYCLE_COUNT]);
+    int n = (int)std::min<size_t>(o.size(), (size_t)cap);
+    std::memcpy(out, o.data(), (size_t)n * 8);
+    if (n_out) *n_out = n;
+    return 0;
+}
+
+int trl_get_poli_state(trl_handle* h, int env, double* out) {
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(out, h->B.poli_state + (size_t)env * h->B.S, (size_t)h->B.S * 8, cudaMemcpyDeviceToHost));
+    return 0;
+}
+int trl_get_net_out(trl_handle* h, int env, double* out) {
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(out, h->B.net_out + (size_t)env * kMaxNetOut, (size_t)h->mc.n_out * 8, cudaMemcpyDeviceToHost));
+    return 0;
+}
+int trl_get_terrain(trl_handle* h, int env, int seg, float* data, int cap, int* n, double* min_x, int* flip) {
+    CK(cudaStreamSynchronize(h->stream));
+    int sn = 0, fl = 0;
+    double mx = 0;
+    if (copy_plane_i(h, seg == 0 ? I_SEG_N0 : I_SEG_N1, 1, env, &sn) || copy_plane_i(h, I_SEG_FLIP, 1, env, &fl) ||
+        copy_plane_d(h, seg == 0 ? D_SEG_MINX0 : D_SEG_MINX1, 1, env, &mx))
+        return fail("copy failed");
+    int cnt = std::min(sn, cap);
+    if (cnt > 0) CK(cudaMemcpy(data, h->B.terrain + ((size_t)env * 2 + seg) * kTerrainCap, (size_t)cnt * 4, cudaMemcpyDeviceToHost));
+    *n = sn; *min_x = mx; *flip = fl;
+    return 0;
+}
+
+int64_t trl_kernel_launches(trl_handle* h) { return h->launches; }
+
+}  // extern "C"

@@ -1,0 +1,134 @@
+// deepterrainrl_b200 -- batched locomotion rollout engine for B200 (sm_100a).
+// Shared host/device types: model constants (constant memory), SoA state layout in HBM, launch parameters.
+//
+// HBM layout: every per-env scalar lives in a struct-of-arrays plane `plane[field][env]`, so a warp
+// (32 consecutive envs, one env per lane) reads/writes each field as one coalesced 256-byte (f64) or 128-byte (i32)
+// transaction.  Bulk per-env records that are touched by one env at a time (terrain strips, policy state, tuple
+// staging) are env-major rows instead.
+#pragma once
+#include <cstdint>
+
+namespace trl {
+
+constexpr int kMaxJoints = 21;      // dog / goat: 21 joints, raptor: 19
+constexpr int kMaxDof = 23;
+constexpr int kNumParams = 30;      // gait controller parameter vector (sim/DogController.h:14-46)
+constexpr int kNumGroundSamples = 200;
+constexpr int kTerrainCap = 512;    // floats per terrain segment (20 m nominal + overshoot + 2 m pad at 0.1 m)
+constexpr int kTerrainParams = 40;
+constexpr int kMaxActions = 16;
+constexpr int kMaxCtrlSets = 8;
+constexpr int kMaxNetOut = 96;
+constexpr int kWarp = 32;
+
+// ---- f64 SoA planes -------------------------------------------------------------------------------------------
+enum DField : int {
+    D_Q = 0,                               // 23 generalised positions [x, y, th_root, th_1..]
+    D_QD = D_Q + kMaxDof,                  // 23 generalised velocities
+    D_TAU = D_QD + kMaxDof,                // 23 held (clamped) joint torques, applied by the next env-step
+    D_PARAMS = D_TAU + kMaxDof,            // 30 current action parameters
+    D_PD_TARGET = D_PARAMS + kNumParams,   // 21 PD target angles
+    D_PHASE = D_PD_TARGET + kMaxJoints,
+    D_CUR_CYCLE_T, D_PREV_CYCLE_T, D_CUR_STUMBLE, D_PREV_STUMBLE,
+    D_PREV_COM_X, D_PREV_COM_Y, D_PREV_DIST_X, D_PREV_DIST_Y,
+    D_FALL_DIST_CNT, D_FALL_CONTACT_CNT, D_SUM_FALL, D_PREV_CHECK_X, D_PREV_CHECK_Y,
+    D_AVG_DIST, D_POS_START_X,
+    D_SEG_MINX0, D_SEG_MINX1,              // terrain segment origins
+    D_NUM_FIELDS
+};
+
+// ---- i32 SoA planes -------------------------------------------------------------------------------------------
+enum IField : int {
+    I_STATE = 0, I_FIRST_CYCLE, I_ACTION_ID, I_CONTACT, I_FAIL_FALL_DIST,
+    I_EXP_FLAGS,        // bit0 exp_critic, bit1 exp_actor, bit2 off_policy
+    I_CYCLE_COUNT, I_EPISODE_COUNT, I_PENDING, I_CMD,
+    I_SEG_N0, I_SEG_N1, I_SEG_FLIP, I_TERRAIN_RNG,   // minstd_rand0 state of the env's terrain generator
+    I_TUPLE_FLAGS, I_RNG_CTR_LO, I_RNG_CTR_HI, I_STEPS_LO, I_STEPS_HI,
+    I_NUM_FIELDS
+};
+
+struct PhysParams {
+    double kn, dn, mu, v_eps, contact_tol, k_lim, d_lim;
+};
+
+// Model / scene constants, uploaded once into __constant__ memory (uniform across lanes -> constant-cache broadcast).
+struct ModelConst {
+    int nj, ndof;
+    int parent[kMaxJoints];
+    int dof[kMaxJoints];                   // parameter offset of each joint
+    double attach_x[kMaxJoints], attach_y[kMaxJoints];
+    double lim_lo[kMaxJoints], lim_hi[kMaxJoints];
+    int has_limit[kMaxJoints];
+    // bodies
+    double mass[kMaxJoints], body_ax[kMaxJoints], body_ay[kMaxJoints], body_theta[kMaxJoints];
+    double body_cos[kMaxJoints], body_sin[kMaxJoints];
+    double half_x[kMaxJoints], half_y[kMaxJoints];
+    double izz_o[kMaxJoints];              // planar rotational inertia about the joint origin
+    int collidable[kMaxJoints];
+    double total_mass;
+    // PD
+    double kp[kMaxJoints], kd[kMaxJoints], torque_lim[kMaxJoints], target_theta0[kMaxJoints], target_vel[kMaxJoints];
+    int world_pd[kMaxJoints];
+    // gait controller
+    int n_ctrl, n_actions, default_action, grav_comp, virt_forces, is_mace;
+    double ctrl_params[kMaxCtrlSets][kNumParams];
+    int act_idx0[kMaxActions], act_idx1[kMaxActions], act_cyclic[kMaxActions];
+    double act_blend[kMaxActions];
+    double target_vel_x;
+    // initial state
+    double pose0[kMaxDof], vel0[kMaxDof];
+    int has_init_x;
+    double init_x;
+    // terrain
+    int terrain_type;
+    double terrain_params[kTerrainParams];
+    // scenario
+    int num_sim_substeps, exp_mode, has_net;
+    double gx, gy;
+    // net dims
+    int n_in, n_char, n_out, n_frags, frag;
+    double out_scale_actor0[32];           // OutputScale of actor 0 (exploration noise scale)
+    PhysParams phys;
+    uint64_t rng_seed;
+};
+
+// Exploration settings can change between updates (cScenarioExp::SetExpRate/Temp/BaseActionRate).
+struct ExpSettings {
+    int enable;
+    double rate, temp, base_rate, noise;
+};
+
+// Policy network weights (device pointers, f64, Caffe blob order).
+struct NetWeights {
+    const double *conv0_w, *conv0_b, *conv1_w, *conv1_b, *conv2_w, *conv2_b, *tip0_w, *tip0_b, *ip0_w, *ip0_b;
+    const double *h0_w[4], *h0_b[4], *h1_w[4], *h1_b[4];
+    const double *in_off, *in_scale, *out_off, *out_scale;
+};
+
+// Device buffers of one batch of environments.
+struct Buffers {
+    int n;                 // number of envs
+    double* d;             // [D_NUM_FIELDS][n]
+    int* i;                // [I_NUM_FIELDS][n]
+    float* terrain;        // [n][2][kTerrainCap]
+    double* poli_state;    // [n][S]   policy state built at the last decision
+    double* net_out;       // [n][kMaxNetOut]
+    double* tuple_sbeg;    // [n][S]
+    double* tuple_action;  // [n][kNumParams]
+    double* com_stash;     // [2][n]   COM at decision time
+    int* pending_list;     // [n]
+    int* pending_count;    // [1]
+    // outputs
+    double* tuples;        // [tuple_cap][1 + S + A + S]
+    uint32_t* tuple_flags; // [tuple_cap]
+    int* tuple_env;        // [tuple_cap]
+    int* tuple_count;      // [1]
+    int tuple_cap;
+    double* dist_log;      // [dist_cap] episode distances
+    int* dist_env;         // [dist_cap]
+    int* dist_count;       // [1]
+    int dist_cap;
+    int S;                 // policy state size
+};
+
+}  // namespace trl

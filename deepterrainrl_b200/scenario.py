@@ -1,0 +1,237 @@
+"""Host-side mirror of the reference's per-env scenario API over a *batch* of environments.
+
+Method names follow scenarios/ScenarioExp.h:16-40, ScenarioPoliEval.h:13-28 and ScenarioSimChar.h:49-82 so the
+parity tests read like the reference's own call sites (scenarios/ScenarioTrain.cpp:376-410,
+optimizer/scenarios/OptScenarioPoliEval.cpp:170-237).  Everything forwards to the C ABI (include/terrainrl_b200.h).
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_PKG)
+_LIB = None
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
+              "-shared"]
+
+
+def library_path():
+    return os.path.join(_PKG, "lib", "libterrainrl_b200.so")
+
+
+def build_library(force=False, verbose=False):
+    """Compile csrc/*.cu for sm_100a into lib/libterrainrl_b200.so (nvcc cross-compiles without a GPU)."""
+    out = library_path()
+    srcs = [os.path.join(_PKG, "csrc", f) for f in ("trl_step.cu", "trl_host.cu")]
+    deps = [os.path.join(_PKG, "csrc", f) for f in os.listdir(os.path.join(_PKG, "csrc"))]
+    deps.append(os.path.join(_ROOT, "include", "terrainrl_b200.h"))
+    if not force and os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in deps):
+        return out
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + srcs
+    subprocess.run(cmd, check=True)
+    return out
+
+
+EXPORTS = [
+    "trl_create_from_pack", "trl_destroy", "trl_reset", "trl_seed_terrain", "trl_update", "trl_env_step", "trl_sync",
+    "trl_set_explore", "trl_set_phys_params", "trl_set_weights", "trl_sizes", "trl_num_tuples", "trl_get_tuples",
+    "trl_get_tuples_f64", "trl_reset_tuples", "trl_eval_stats", "trl_dist_log", "trl_get_state", "trl_set_state",
+    "trl_get_state_all", "trl_get_ctrl", "trl_get_poli_state", "trl_get_net_out", "trl_get_terrain",
+    "trl_kernel_launches", "trl_last_error",
+]
+
+
+def load_library():
+    """dlopen the CUDA library; raises if it has not been built (no silent fallback)."""
+    global _LIB
+    if _LIB is None:
+        path = library_path()
+        if not os.path.exists(path):
+            raise RuntimeError(f"{path} is missing: run __graft_entry__.build() (nvcc) first; there is no CPU fallback")
+        L = C.CDLL(path)
+        L.trl_create_from_pack.restype = C.c_void_p
+        L.trl_create_from_pack.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_uint64]
+        L.trl_last_error.restype = C.c_char_p
+        L.trl_kernel_launches.restype = C.c_int64
+        L.trl_kernel_launches.argtypes = [C.c_void_p]
+        _LIB = L
+    return _LIB
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class BatchedScenario:
+    """N environments of one scene stepped in lock-step on one GPU (one handle of the C ABI)."""
+
+    MODE = 0
+
+    def __init__(self, pack, num_envs, device=0, terrain_seeds=None, rng_seed=1234):
+        self.L = load_library()
+        seeds = None if terrain_seeds is None else np.ascontiguousarray(terrain_seeds, dtype=np.uint64)
+        h = self.L.trl_create_from_pack(os.fspath(pack).encode(), int(num_envs), int(device), self.MODE, _p(seeds),
+                                        C.c_uint64(rng_seed))
+        if not h:
+            raise RuntimeError("trl_create_from_pack: " + self.L.trl_last_error().decode())
+        self.h = C.c_void_p(h)
+        v = [C.c_int(0) for _ in range(7)]
+        self._ck(self.L.trl_sizes(self.h, *[C.byref(x) for x in v]))
+        self.num_envs, self.state_size, self.action_size, self.num_frags, self.frag_size, self.num_dof, self.num_joints = \
+            [x.value for x in v]
+        self.tuple_width = 1 + self.state_size + self.action_size + self.state_size
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise RuntimeError(self.L.trl_last_error().decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.trl_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- cScenario interface
+    def Update(self, dt=1.0 / 30.0):
+        self._ck(self.L.trl_update(self.h, C.c_double(dt)))
+
+    def Reset(self, env_ids=None):
+        ids = None if env_ids is None else np.ascontiguousarray(env_ids, dtype=np.int32)
+        self._ck(self.L.trl_reset(self.h, _p(ids), 0 if ids is None else ids.size))
+
+    def SetRandSeed(self, seeds):
+        s = np.ascontiguousarray(seeds, dtype=np.uint64)
+        self._ck(self.L.trl_seed_terrain(self.h, _p(s), s.size))
+
+    def Sync(self):
+        self._ck(self.L.trl_sync(self.h))
+
+    def EnvStep(self, h=1.0 / 600.0):
+        self._ck(self.L.trl_env_step(self.h, C.c_double(h)))
+
+    def SetPhysParams(self, p7):
+        a = np.ascontiguousarray(p7, dtype=np.float64)
+        self._ck(self.L.trl_set_phys_params(self.h, _p(a)))
+
+    def SetWeights(self, blobs, in_off, in_scale, out_off, out_scale):
+        blobs = [np.ascontiguousarray(b, dtype=np.float64).ravel() for b in blobs]
+        ptrs = (C.c_void_p * len(blobs))(*[b.ctypes.data for b in blobs])
+        counts = np.array([b.size for b in blobs], dtype=np.int64)
+        vs = [np.ascontiguousarray(v, dtype=np.float64) for v in (in_off, in_scale, out_off, out_scale)]
+        self._ck(self.L.trl_set_weights(self.h, ptrs, _p(counts), len(blobs), *[_p(v) for v in vs]))
+
+    # ---- state probes
+    def GetState(self, env=0):
+        q = np.zeros(self.num_dof); qd = np.zeros(self.num_dof); tau = np.zeros(self.num_dof)
+        c = np.zeros(self.num_joints, np.uint8)
+        self._ck(self.L.trl_get_state(self.h, env, _p(q), _p(qd), _p(tau), _p(c)))
+        return q, qd, tau, c
+
+    def SetState(self, env=0, q=None, qd=None, tau=None, contact=None):
+        f = lambda a, t: None if a is None else np.ascontiguousarray(a, dtype=t)
+        q, qd, tau, contact = f(q, np.float64), f(qd, np.float64), f(tau, np.float64), f(contact, np.uint8)
+        self._ck(self.L.trl_set_state(self.h, env, _p(q), _p(qd), _p(tau), _p(contact)))
+
+    def GetStateAll(self):
+        q = np.zeros((self.num_dof, self.num_envs)); qd = np.zeros((self.num_dof, self.num_envs))
+        self._ck(self.L.trl_get_state_all(self.h, _p(q), _p(qd)))
+        return q, qd
+
+    def GetCtrl(self, env=0):
+        out = np.zeros(128)
+        n = C.c_int(0)
+        self._ck(self.L.trl_get_ctrl(self.h, env, _p(out), 128, C.byref(n)))
+        return out[:n.value]
+
+    def GetPoliState(self, env=0):
+        s = np.zeros(self.state_size)
+        self._ck(self.L.trl_get_poli_state(self.h, env, _p(s)))
+        return s
+
+    def GetNetOut(self, env=0, n=90):
+        y = np.zeros(96)
+        self._ck(self.L.trl_get_net_out(self.h, env, _p(y)))
+        return y[:n]
+
+    def GetTerrain(self, env=0, seg=0, cap=512):
+        d = np.zeros(cap, np.float32)
+        n = C.c_int(0); mx = C.c_double(0); fl = C.c_int(0)
+        self._ck(self.L.trl_get_terrain(self.h, env, seg, _p(d), cap, C.byref(n), C.byref(mx), C.byref(fl)))
+        return d[:min(n.value, cap)].copy(), mx.value, fl.value
+
+    def KernelLaunches(self):
+        return int(self.L.trl_kernel_launches(self.h))
+
+    # ---- cScenarioPoliEval statistics
+    def _stats(self):
+        c = C.c_int64(0); e = C.c_int64(0); a = C.c_double(0); s = C.c_int64(0)
+        self._ck(self.L.trl_eval_stats(self.h, C.byref(c), C.byref(e), C.byref(a), C.byref(s)))
+        return dict(cycles=c.value, episodes=e.value, avg_dist=a.value, steps=s.value)
+
+    def GetNumCycles(self):
+        return self._stats()["cycles"]
+
+    def GetNumEpisodes(self):
+        return self._stats()["episodes"]
+
+    def GetAvgDist(self):
+        return self._stats()["avg_dist"]
+
+    def GetNumEnvSteps(self):
+        return self._stats()["steps"]
+
+    def GetDistLog(self):
+        d = C.c_void_p(); e = C.c_void_p(); n = C.c_int(0)
+        self._ck(self.L.trl_dist_log(self.h, C.byref(d), C.byref(e), C.byref(n)))
+        if n.value == 0:
+            return np.zeros(0), np.zeros(0, np.int32)
+        dist = np.ctypeslib.as_array(C.cast(d, C.POINTER(C.c_double)), (n.value,)).copy()
+        env = np.ctypeslib.as_array(C.cast(e, C.POINTER(C.c_int32)), (n.value,)).copy()
+        return dist, env
+
+
+class ScenarioPoliEval(BatchedScenario):
+    """cScenarioPoliEval over a batch (scenarios/ScenarioPoliEval.h:13-28)."""
+    MODE = 0
+
+
+class ScenarioExpMACE(BatchedScenario):
+    """cScenarioExpMACE over a batch (scenarios/ScenarioExp.h:16-40, ScenarioExpMACE.h)."""
+    MODE = 1
+
+    def EnableExplore(self, enable, rate, temp, base_rate):
+        self._ck(self.L.trl_set_explore(self.h, int(enable), C.c_double(rate), C.c_double(temp), C.c_double(base_rate)))
+
+    def GetNumTuples(self):
+        n = C.c_int(0)
+        self._ck(self.L.trl_num_tuples(self.h, C.byref(n)))
+        return n.value
+
+    def IsTupleBufferFull(self, tuple_buffer_size=32):
+        return self.GetNumTuples() >= tuple_buffer_size
+
+    def GetTuples(self, f64=False):
+        rows = C.c_void_p(); fl = C.c_void_p(); ev = C.c_void_p(); n = C.c_int(0)
+        fn = self.L.trl_get_tuples_f64 if f64 else self.L.trl_get_tuples
+        self._ck(fn(self.h, C.byref(rows), C.byref(fl), C.byref(ev), C.byref(n)))
+        W = self.tuple_width
+        if n.value == 0:
+            return (np.zeros((0, W), np.float64 if f64 else np.float32), np.zeros(0, np.uint32), np.zeros(0, np.int32))
+        ct = C.c_double if f64 else C.c_float
+        r = np.ctypeslib.as_array(C.cast(rows, C.POINTER(ct)), (n.value, W)).copy()
+        f = np.ctypeslib.as_array(C.cast(fl, C.POINTER(C.c_uint32)), (n.value,)).copy()
+        e = np.ctypeslib.as_array(C.cast(ev, C.POINTER(C.c_int32)), (n.value,)).copy()
+        return r, f, e
+
+    def ResetTupleBuffer(self):
+        self._ck(self.L.trl_reset_tuples(self.h))

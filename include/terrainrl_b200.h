@@ -1,0 +1,94 @@
+/* terrainrl_b200 -- C ABI of the B200-native batched rollout engine.
+ *
+ * One handle = one batch of N independent environments stepped in lock-step on one GPU.  Each entry point names
+ * the reference interface it replaces (file:line under the DeepTerrainRL tree); the reference has no FFI layer,
+ * its seam is the C++ virtual scenario API that cScenarioTrain / cOptScenarioPoliEval call on every pooled env
+ * (scenarios/ScenarioTrain.cpp:197-222,376-410; optimizer/scenarios/OptScenarioPoliEval.cpp:135-237).
+ *
+ * Conventions: all functions return 0 on success, non-zero on error (trl_last_error() gives the message; the
+ * reference's printf+assert convention cannot cross an ABI).  A handle is single-writer.  Pointers returned by
+ * the library stay valid until the next call that mutates the same data (documented per function).
+ * Plain C types only: no torch / CUDA types in any signature.
+ */
+#ifndef TERRAINRL_B200_H
+#define TERRAINRL_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct trl_handle trl_handle;
+
+enum { TRL_MODE_POLI_EVAL = 0, TRL_MODE_EXPLORE = 1 };
+
+/* cScenario{PoliEval,ExpMACE}::ParseArgs + Init + SetRandSeed + Reset for N envs
+ * (scenarios/ScenarioSimChar.cpp:80-119, ScenarioPoliEval.cpp:60-108,153-160, ScenarioExp.cpp:29-73).
+ * `pack_path` is a scene pack produced by tools/pack_scene.py from a reference arg file.  terrain_seeds may be NULL
+ * (env i gets seed 1+i).  Returns NULL on failure. */
+trl_handle* trl_create_from_pack(const char* pack_path, int num_envs, int device, int mode,
+                                 const uint64_t* terrain_seeds, uint64_t rng_seed);
+int trl_destroy(trl_handle* h);
+
+/* cScenario::Reset for the listed envs (NULL = all)            scenarios/ScenarioSimChar.cpp:121-132 */
+int trl_reset(trl_handle* h, const int32_t* env_ids, int n);
+/* cScenarioPoliEval::SetRandSeed + Reset for every env         scenarios/ScenarioPoliEval.cpp:153-160 */
+int trl_seed_terrain(trl_handle* h, const uint64_t* seeds, int n);
+
+/* cScenario::Update(dt) for all envs in lock-step: num_update_steps env-steps, then the fall -> reset handling
+ * (scenarios/ScenarioSimChar.cpp:141-182, ScenarioPoliEval.cpp:110-125, ScenarioExp.cpp:83-98).
+ * Asynchronous: enqueued on the handle's stream; trl_sync() or any getter waits. */
+int trl_update(trl_handle* h, double dt);
+/* one iteration of the loop at scenarios/ScenarioSimChar.cpp:162-173 (parity probe; no fall handling) */
+int trl_env_step(trl_handle* h, double step);
+int trl_sync(trl_handle* h);
+
+/* cScenarioExp::{EnableExplore,SetExpRate,SetExpTemp,SetExpBaseActionRate}   scenarios/ScenarioExp.cpp:156-185 */
+int trl_set_explore(trl_handle* h, int enable, double rate, double temp, double base_rate);
+/* engine contact / joint-limit parameters (7 doubles: kn, dn, mu, v_eps, contact_tol, k_lim, d_lim) */
+int trl_set_phys_params(trl_handle* h, const double* p7);
+
+/* cNeuralNet::CopyModel into every env's controller net (learning/NeuralNetLearner.cpp:85-89): 26 blobs in Caffe
+ * order (w, b of terr_conv0..2, terr_ip0, ip0, val_ip0, val_ip1, a{0,1,2}_ip{0,1}) + the four offset/scale vectors. */
+int trl_set_weights(trl_handle* h, const double* const* blobs, const int64_t* counts, int nblobs,
+                    const double* in_off, const double* in_scale, const double* out_off, const double* out_scale);
+
+/* sizes: policy state, action record, MACE fragments           sim/NNController.cpp:49-78, BaseControllerMACE.cpp:36-56 */
+int trl_sizes(trl_handle* h, int* num_envs, int* state, int* action, int* num_frags, int* frag_size, int* num_dof,
+              int* num_joints);
+
+/* cScenarioExp::{IsTupleBufferFull,GetTuples,ResetTupleBuffer} for the whole batch: rows are
+ * [reward | s(S) | a(A) | s'(S)] exactly like cMACETrainer's replay rows (learning/MACETrainer.cpp:515-539);
+ * flags bit0 fail, bit1 expCritic, bit2 expActor (learning/MACETrainer.h:11-17).  The f32 view is what the
+ * trainer stores; the f64 view is what tExpTuple holds.  Pointers valid until trl_reset_tuples / trl_update. */
+int trl_num_tuples(trl_handle* h, int* out);
+int trl_get_tuples(trl_handle* h, const float** rows, const uint32_t** flags, const int32_t** env_id, int* n);
+int trl_get_tuples_f64(trl_handle* h, const double** rows, const uint32_t** flags, const int32_t** env_id, int* n);
+int trl_reset_tuples(trl_handle* h);
+
+/* cScenarioPoliEval::{GetNumCycles,GetNumEpisodes,GetAvgDist,GetDistLog}   scenarios/ScenarioPoliEval.cpp:127-151 */
+int trl_eval_stats(trl_handle* h, int64_t* cycles, int64_t* episodes, double* avg_dist, int64_t* env_steps);
+int trl_dist_log(trl_handle* h, const double** dist, const int32_t** env_id, int* n);
+
+/* cSimCharacter::{BuildPose,BuildVel} / SetPose+SetVel and contact bits for one env (sim/SimCharacter.cpp:166-315) */
+int trl_get_state(trl_handle* h, int env, double* pose, double* vel, double* held_torque, uint8_t* contact);
+int trl_set_state(trl_handle* h, int env, const double* pose, const double* vel, const double* held_torque,
+                  const uint8_t* contact);
+/* bulk SoA views: pose/vel as [num_dof][num_envs] doubles */
+int trl_get_state_all(trl_handle* h, double* pose, double* vel);
+
+/* parity probes (same layouts as the oracle's probes) */
+int trl_get_ctrl(trl_handle* h, int env, double* out, int cap, int* n);
+int trl_get_poli_state(trl_handle* h, int env, double* out);
+int trl_get_net_out(trl_handle* h, int env, double* out);
+int trl_get_terrain(trl_handle* h, int env, int seg, float* data, int cap, int* n, double* min_x, int* flip);
+
+/* number of engine kernels launched since creation (bench.py's gpu_launches claim) */
+int64_t trl_kernel_launches(trl_handle* h);
+
+const char* trl_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,114 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+H = 1.0 / 600.0
+
+
+def _pair(assets, name, n=1, mode=0, seeds=None, rng_seed=1234):
+    from pyoracle import Oracle
+    import deepterrainrl_b200 as trl
+    pack = os.path.join(assets, name)
+    cls = trl.ScenarioExpMACE if mode else trl.ScenarioPoliEval
+    g = cls(pack, n, terrain_seeds=seeds, rng_seed=rng_seed)
+    o = Oracle(pack, n, mode, terrain_seeds=seeds, rng_seed=rng_seed)
+    return g, o
+
+
+def _relerr(a, b):
+    return np.max(np.abs(a - b) / (1.0 + np.abs(b)))
+
+
+def test_reset_state_and_terrain_bit_exact(assets):
+    g, o = _pair(assets, "dog_slopes_mixed.trlpack", n=40)
+    for env in (0, 1, 7, 39):
+        gq, gqd, gt, gc = g.GetState(env)
+        oq, oqd, ot, oc = o.get_state(env)
+        np.testing.assert_array_equal(gq, oq)
+        np.testing.assert_array_equal(gqd, oqd)
+        for seg in (0, 1):
+            gd, gmx, gfl = g.GetTerrain(env, seg)
+            od, omx, ofl = o.terrain(env, seg)
+            assert gd.size == od.size and gfl == ofl
+            assert gmx == omx
+            np.testing.assert_array_equal(gd, od)   # float vertices from the restated libstdc++ RNG: bit-exact
+
+
+def test_flat_dog_300_steps(assets):
+    """BASELINE config 1: dog, flat ground, fixed cyclic action, 300 env-steps; q, qd, contacts, torques per step."""
+    g, o = _pair(assets, "dog_flat.trlpack")
+    worst = 0.0
+    for k in range(300):
+        g.EnvStep(H)
+        o.env_step(0, H)
+        gq, gqd, gt, gc = g.GetState(0)
+        oq, oqd, ot, oc = o.get_state(0)
+        worst = max(worst, _relerr(gq, oq), _relerr(gqd, oqd))
+        assert _relerr(gq, oq) < 1e-6, (k, gq - oq)
+        assert _relerr(gqd, oqd) < 1e-5, (k, gqd - oqd)
+        assert _relerr(gt, ot) < 1e-5, (k, gt - ot)
+        np.testing.assert_array_equal(gc, oc)
+        gctl, octl = g.GetCtrl(0), o.get_ctrl(0)
+        assert gctl[0] == octl[0], (k, "fsm state")
+    print("flat 300 steps worst rel err", worst)
+
+
+def test_slopes_mixed_600_steps_with_policy(assets):
+    """north_star tolerance: per-step state within 1e-4 relative over 600 env-steps from identical seeds."""
+    n = 8
+    g, o = _pair(assets, "dog_slopes_mixed.trlpack", n=n)
+    worst = 0.0
+    for k in range(600):
+        g.EnvStep(H)
+        for e in range(n):
+            o.env_step(e, H)
+        if k % 20 == 19 or k < 5:
+            for e in range(n):
+                gq, gqd, gt, gc = g.GetState(e)
+                oq, oqd, ot, oc = o.get_state(e)
+                worst = max(worst, _relerr(gq, oq), _relerr(gqd, oqd))
+                assert _relerr(gq, oq) < 1e-4, (k, e)
+                assert _relerr(gqd, oqd) < 1e-4, (k, e)
+    # the first decision's network output and policy state
+    np.testing.assert_allclose(g.GetPoliState(0), o.poli_state(0), rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(g.GetNetOut(0), o.net_out(0), rtol=1e-8, atol=1e-8)
+    print("slopes_mixed 600 steps worst rel err", worst)
+
+
+def test_update_loop_stats(assets):
+    """cScenarioPoliEval::Update over 3 s incl. fall handling: cycle / episode counters and env-steps match."""
+    n = 32
+    g, o = _pair(assets, "dog_slopes_mixed.trlpack", n=n)
+    for k in range(90):
+        g.Update(1.0 / 30.0)
+        o.update(1.0 / 30.0, threads=8)
+    gs = g._stats()
+    os_ = o.eval_stats()
+    assert gs["steps"] == os_["steps"] == 90 * 20 * n
+    assert gs["cycles"] == os_["cycles"]
+    assert gs["episodes"] == os_["episodes"]
+    gq, _ = g.GetStateAll()
+    oq = np.stack([o.get_state(e)[0] for e in range(n)], axis=1)
+    assert np.max(np.abs(gq[0] - oq[0])) < 1e-3
+
+
+def test_explore_tuples(assets):
+    n = 16
+    g, o = _pair(assets, "dog_slopes_mixed.trlpack", n=n, mode=1)
+    g.EnableExplore(1, 0.2, 0.025, 0.002)
+    o.set_explore(1, 0.2, 0.025, 0.002)
+    for k in range(60):
+        g.Update(1.0 / 30.0)
+        o.update(1.0 / 30.0, threads=8)
+    gr, gf, ge = g.GetTuples(f64=True)
+    orr, of, oe = o.tuples()
+    assert gr.shape == orr.shape and gr.shape[0] > 0
+    gi = np.lexsort((np.arange(len(ge)), ge))
+    oi = np.lexsort((np.arange(len(oe)), oe))
+    np.testing.assert_array_equal(ge[gi], oe[oi])
+    np.testing.assert_array_equal(gf[gi], of[oi])
+    np.testing.assert_allclose(gr[gi], orr[oi], rtol=1e-5, atol=1e-5)
