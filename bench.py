@@ -1,0 +1,258 @@
+#!/usr/bin/env python
+"""Benchmark: env-steps/sec of the ScenarioPoliEval step loop (dog / slopes_mixed / MACE policy, 4096 envs per GPU).
+
+One "step" = one outer cScenario::Update(1/30 s) over the whole batch = 20 env-steps x 4096 envs (one env-step =
+one iteration of the loop at scenarios/ScenarioSimChar.cpp:162-173 = 1/600 s simulated).  Data is synthetic in the
+contract's sense (procedurally generated terrain from per-env seeds); the character, controller and policy weights
+are the reference's shipped dog / dog_mace3_slopes_mixed assets baked into assets/dog_slopes_mixed.trlpack.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--envs E]
+  python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+Prints ONE JSON line (rank 0).  `value` = whole-job env-steps/s with state resident in HBM, timed with CUDA events on
+the engine's own stream; `e2e` = the same through the public C-ABI calls a user of cOptScenarioPoliEval makes per
+step (Update + statistics read-back to host buffers); `roofline` = algorithmic HBM bytes of the step kernel per
+launch / its measured launch duration vs the measured copy peak; `cpu_baseline` = the CPU oracle timed on this host.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+PACK = os.path.join(ROOT, "assets", "dog_slopes_mixed.trlpack")
+ENV_STEPS_PER_UPDATE = 20
+DT = 1.0 / 30.0
+# per env-step the persistent state must be read and written once (q, qd, held torque, 64-scalar
+# controller block = 133 scalars each way) plus <= 42 terrain vertices read: (133 * 2) * 8 B + 42 * 4 B for f64 state
+ALGO_BYTES_PER_ENV_STEP = 133 * 2 * 8 + 42 * 4
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index=0):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_reference(num_envs, seconds_target, threads):
+    """Times the CPU oracle (restated reference controller + this project's reduced-coordinate physics, f64) with
+    thread-per-env-slice like cOptScenarioPoliEval::Run (optimizer/scenarios/OptScenarioPoliEval.cpp:72-110)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    from pyoracle import Oracle
+    o = Oracle(PACK, num_envs, 0)
+    o.update(DT, threads)   # warm-up
+    t0 = time.perf_counter()
+    updates = 0
+    while time.perf_counter() - t0 < seconds_target:
+        o.update(DT, threads)
+        updates += 1
+    dt = time.perf_counter() - t0
+    steps = updates * ENV_STEPS_PER_UPDATE * num_envs
+    return steps / dt, dt, updates
+
+
+def run_reference_arm(args, rank):
+    cores = os.cpu_count() or 1
+    if rank != 0:
+        return
+    envs = 4 * cores
+    per_step_s = 0.0
+    # warm-up + K steps, each step a bounded sample: `envs` environments advanced by one outer update
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    from pyoracle import Oracle
+    o = Oracle(PACK, envs, 0)
+    for _ in range(args.warmup):
+        o.update(DT, cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        o.update(DT, cores)
+    el = time.perf_counter() - t0
+    per_step_s = el / args.steps
+    value = envs * ENV_STEPS_PER_UPDATE / per_step_s
+    line = {
+        "impl": "reference", "metric": "env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step_s * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "dog/slopes_mixed MACE poli_eval (BASELINE configs[1])", "envs_per_gpu": args.envs},
+        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port",
+                         "sample": f"{envs} envs x {args.steps} outer updates of 20 env-steps, thread-per-env-slice on {cores} threads; "
+                                   "restated CPU oracle (reduced-coordinate physics), not Bullet"},
+        "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--envs", type=int, default=4096, help="environments per GPU")
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import deepterrainrl_b200 as trl
+
+    if world > 1:
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    n = args.envs
+    seeds = np.arange(1 + rank * n, 1 + (rank + 1) * n, dtype=np.uint64)   # SURVEY §8(d) config 4 seeding
+    sc = trl.ScenarioPoliEval(PACK, n, device=local_rank, terrain_seeds=seeds, rng_seed=1234 + rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        sc.Sync()
+
+    # ---- warm-up: W untimed steps (also desynchronises the gait cycles a little)
+    sc.BenchUpdates(max(args.warmup, 3), DT, flush_l2=True)
+    launches0 = sc.KernelLaunches()
+
+    # ---- timed: exactly K steps, device-timed on the engine's stream, max over ranks
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    ms = sc.BenchUpdates(args.steps, DT, flush_l2=True)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = sc.KernelLaunches() - launches0
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    total_env_steps = args.steps * ENV_STEPS_PER_UPDATE * n * world
+    value = total_env_steps / (ms * 1e-3)
+
+    # ---- e2e: the per-step calls of cOptScenarioPoliEval::EvalHelper through the C ABI with host buffers:
+    # Update(1/30), then the counters + all env poses read back to host memory, every step
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        sc.Update(DT)
+        st = sc._stats()
+        q, qd = sc.GetStateAll()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = total_env_steps / e2e_s
+    d2h = n * (4 * 4 + 8) + 2 * sc.num_dof * n * 8
+
+    # ---- roofline of the dominant kernel (step kernel), measured live with per-launch events
+    step_ms, step_l, dec_ms, dec_l = sc.UpdateTimed(DT)
+    peaks, peak_kind = measured_peaks()
+    launch_s = step_ms * 1e-3 / step_l
+    achieved = ALGO_BYTES_PER_ENV_STEP * n / launch_s / 1e9
+    stats = sc._stats()
+
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    cores = os.cpu_count() or 1
+    cpu_envs = 4 * cores
+    cpu_val, cpu_dt, cpu_updates = cpu_reference(cpu_envs, args.cpu_seconds, cores) if world == 1 else (None, 0, 0)
+
+    line = {
+        "metric": "env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "dog/slopes_mixed MACE poli_eval (BASELINE configs[1])", "envs_per_gpu": n,
+                   "env_steps_per_step": ENV_STEPS_PER_UPDATE * n, "sim_substeps": 5, "parallelism": f"env-shard x{world}",
+                   "l2": "flushed between steps (256 MiB memset on the engine stream)",
+                   "timing": "cudaEvent on the engine stream around K graph-launched updates"},
+        "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": d2h,
+                "note": "poli_eval is closed-loop: no per-step host inputs exist; each step reads counters and all poses back"},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_kind": peak_kind,
+                     "kernel": "trl_step_kernel", "launch_ms": launch_s * 1e3,
+                     "algorithmic_bytes_per_env_step": ALGO_BYTES_PER_ENV_STEP,
+                     "step_kernel_share_of_update": step_ms / (step_ms + dec_ms),
+                     "note": "path is FP64-latency bound, not HBM bound (SURVEY §8d): see DESIGN.md"},
+        "sim": {"episodes": stats["episodes"], "cycles": stats["cycles"], "avg_dist_m": stats["avg_dist"]},
+    }
+    if cpu_val is not None:
+        line["cpu_baseline"] = {"value": cpu_val, "unit": "env-steps/s", "cores": cores, "kind": "port",
+                                "sample": f"{cpu_envs} envs x {cpu_updates} outer updates ({cpu_dt:.1f} s) on {cores} threads; "
+                                          "restated CPU oracle (reduced-coordinate physics), not Bullet"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -62,6 +62,7 @@ struct trl_handle {
     std::vector<double> h_dist;
     std::vector<int32_t> h_dist_env;
     std::vector<void*> allocs;
+    void* flush_buf = nullptr;
 };
 
 template <typename T>
@@ -566,5 +567,68 @@ int trl_get_terrain(trl_handle* h, int env, int seg, float* data, int cap, int* 
 }
 
 int64_t trl_kernel_launches(trl_handle* h) { return h->launches; }
+
+// K outer updates timed with CUDA events on the handle's own stream (the stream the kernels are launched on);
+// optionally evicts L2 between updates by writing a 256 MiB scratch buffer.
+int trl_bench_updates(trl_handle* h, double dt, int k, int flush_l2, double* ms_total) {
+    const size_t flush_bytes = (size_t)256 << 20;
+    if (flush_l2 && !h->flush_buf) { CK(cudaMalloc(&h->flush_buf, flush_bytes)); h->allocs.push_back(h->flush_buf); }
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaEventRecord(e0, h->stream));
+    for (int i = 0; i < k; ++i) {
+        if (flush_l2) CK(cudaMemsetAsync(h->flush_buf, i & 0xff, flush_bytes, h->stream));
+        if (trl_update(h, dt)) return 1;
+    }
+    CK(cudaEventRecord(e1, h->stream));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (ms_total) *ms_total = ms;
+    return 0;
+}
+
+// One outer update launched kernel by kernel with an event pair around every launch: returns the summed device time
+// of the step kernel launches and of the decision kernel launches (roofline numerator's denominator).
+int trl_update_timed(trl_handle* h, double dt, double* step_ms, int* step_launches, double* decide_ms, int* decide_launches) {
+    const int ns = h->num_update_steps;
+    const double step = dt / ns;
+    std::vector<cudaEvent_t> ev(2 * (2 * ns + 1));
+    for (auto& e : ev) CK(cudaEventCreate(&e));
+    int k = 0;
+    for (int i = 0; i < ns; ++i) {
+        CK(cudaEventRecord(ev[k++], h->stream));
+        launch_step(h->B, step, i == 0 ? 2 : 3, h->stream);
+        CK(cudaEventRecord(ev[k++], h->stream));
+        CK(cudaEventRecord(ev[k++], h->stream));
+        launch_decide(h->B, h->W, h->ex, h->done_count, h->decide_grid, h->stream);
+        CK(cudaEventRecord(ev[k++], h->stream));
+    }
+    CK(cudaEventRecord(ev[k++], h->stream));
+    launch_step(h->B, step, 1 | 4, h->stream);
+    CK(cudaEventRecord(ev[k++], h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaGetLastError());
+    double sm = 0, dm = 0;
+    int idx = 0;
+    for (int i = 0; i < ns; ++i) {
+        float a = 0, b = 0;
+        CK(cudaEventElapsedTime(&a, ev[idx], ev[idx + 1])); idx += 2;
+        CK(cudaEventElapsedTime(&b, ev[idx], ev[idx + 1])); idx += 2;
+        sm += a; dm += b;
+    }
+    float a = 0;
+    CK(cudaEventElapsedTime(&a, ev[idx], ev[idx + 1]));
+    sm += a;
+    for (auto& e : ev) cudaEventDestroy(e);
+    h->launches += 2 * ns + 1;
+    if (step_ms) *step_ms = sm;
+    if (step_launches) *step_launches = ns + 1;
+    if (decide_ms) *decide_ms = dm;
+    if (decide_launches) *decide_launches = ns;
+    return 0;
+}
 
 }  // extern "C"

@@ -42,7 +42,7 @@ EXPORTS = [
     "trl_set_explore", "trl_set_phys_params", "trl_set_weights", "trl_sizes", "trl_num_tuples", "trl_get_tuples",
     "trl_get_tuples_f64", "trl_reset_tuples", "trl_eval_stats", "trl_dist_log", "trl_get_state", "trl_set_state",
     "trl_get_state_all", "trl_get_ctrl", "trl_get_poli_state", "trl_get_net_out", "trl_get_terrain",
-    "trl_kernel_launches", "trl_last_error",
+    "trl_kernel_launches", "trl_last_error", "trl_bench_updates", "trl_update_timed",
 ]
 
 
@@ -171,6 +171,18 @@ class BatchedScenario:
 
     def KernelLaunches(self):
         return int(self.L.trl_kernel_launches(self.h))
+
+    def BenchUpdates(self, k, dt=1.0 / 30.0, flush_l2=True):
+        """k outer updates, device-timed on the library's stream; returns elapsed milliseconds."""
+        ms = C.c_double(0)
+        self._ck(self.L.trl_bench_updates(self.h, C.c_double(dt), int(k), int(bool(flush_l2)), C.byref(ms)))
+        return ms.value
+
+    def UpdateTimed(self, dt=1.0 / 30.0):
+        """one outer update with per-launch events: (step_ms, step_launches, decide_ms, decide_launches)."""
+        sm = C.c_double(0); dm = C.c_double(0); sl = C.c_int(0); dl = C.c_int(0)
+        self._ck(self.L.trl_update_timed(self.h, C.c_double(dt), C.byref(sm), C.byref(sl), C.byref(dm), C.byref(dl)))
+        return sm.value, sl.value, dm.value, dl.value
 
     # ---- cScenarioPoliEval statistics
     def _stats(self):

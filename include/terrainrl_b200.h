@@ -86,6 +86,11 @@ int trl_get_terrain(trl_handle* h, int env, int seg, float* data, int cap, int* 
 /* number of engine kernels launched since creation (bench.py's gpu_launches claim) */
 int64_t trl_kernel_launches(trl_handle* h);
 
+/* measurement helpers: K outer updates timed with CUDA events on the handle's stream (optional L2 flush between
+ * updates); one update with an event pair around every kernel launch (per-kernel device time for the roofline). */
+int trl_bench_updates(trl_handle* h, double dt, int k, int flush_l2, double* ms_total);
+int trl_update_timed(trl_handle* h, double dt, double* step_ms, int* step_launches, double* decide_ms, int* decide_launches);
+
 const char* trl_last_error(void);
 
 #ifdef __cplusplus
