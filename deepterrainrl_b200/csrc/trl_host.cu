@@ -568,6 +568,19 @@ int trl_get_terrain(trl_handle* h, int env, int seg, float* data, int cap, int* 
 
 int64_t trl_kernel_launches(trl_handle* h) { return h->launches; }
 
+// Raw device views of the tuple block for zero-copy hand-off to a collective (NCCL all-gather of ExpTuple blocks,
+// SURVEY §8e).  Pointers are device addresses on the handle's GPU; the caller must trl_sync() before using them on
+// another stream.
+int trl_device_tuple_block(trl_handle* h, void** rows_f64, void** flags_u32, void** env_i32, void** count_i32, int* cap, int* width) {
+    if (rows_f64) *rows_f64 = h->B.tuples;
+    if (flags_u32) *flags_u32 = h->B.tuple_flags;
+    if (env_i32) *env_i32 = h->B.tuple_env;
+    if (count_i32) *count_i32 = h->B.tuple_count;
+    if (cap) *cap = h->B.tuple_cap;
+    if (width) *width = 1 + h->B.S + kNumParams + h->B.S;
+    return 0;
+}
+
 // K outer updates timed with CUDA events on the handle's own stream (the stream the kernels are launched on);
 // optionally evicts L2 between updates by writing a 256 MiB scratch buffer.
 int trl_bench_updates(trl_handle* h, double dt, int k, int flush_l2, double* ms_total) {

@@ -42,7 +42,7 @@ EXPORTS = [
     "trl_set_explore", "trl_set_phys_params", "trl_set_weights", "trl_sizes", "trl_num_tuples", "trl_get_tuples",
     "trl_get_tuples_f64", "trl_reset_tuples", "trl_eval_stats", "trl_dist_log", "trl_get_state", "trl_set_state",
     "trl_get_state_all", "trl_get_ctrl", "trl_get_poli_state", "trl_get_net_out", "trl_get_terrain",
-    "trl_kernel_launches", "trl_last_error", "trl_bench_updates", "trl_update_timed",
+    "trl_kernel_launches", "trl_last_error", "trl_bench_updates", "trl_update_timed", "trl_device_tuple_block",
 ]
 
 
@@ -247,3 +247,21 @@ class ScenarioExpMACE(BatchedScenario):
 
     def ResetTupleBuffer(self):
         self._ck(self.L.trl_reset_tuples(self.h))
+
+    def DeviceTupleBlock(self):
+        """torch views (zero-copy) of the device tuple block: rows f64 [cap, W], flags i32 [cap], env i32 [cap], count i32 [1]."""
+        import torch
+        ptrs = [C.c_void_p() for _ in range(4)]
+        cap = C.c_int(0); width = C.c_int(0)
+        self._ck(self.L.trl_device_tuple_block(self.h, *[C.byref(p) for p in ptrs], C.byref(cap), C.byref(width)))
+
+        class _Arr:
+            def __init__(self, ptr, shape, typestr):
+                self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 2}
+
+        dev = torch.device("cuda", torch.cuda.current_device())
+        rows = torch.as_tensor(_Arr(ptrs[0].value, (cap.value, width.value), "<f8"), device=dev)
+        flags = torch.as_tensor(_Arr(ptrs[1].value, (cap.value,), "<i4"), device=dev)
+        env = torch.as_tensor(_Arr(ptrs[2].value, (cap.value,), "<i4"), device=dev)
+        count = torch.as_tensor(_Arr(ptrs[3].value, (1,), "<i4"), device=dev)
+        return rows, flags, env, count

@@ -86,6 +86,11 @@ int trl_get_terrain(trl_handle* h, int env, int seg, float* data, int cap, int* 
 /* number of engine kernels launched since creation (bench.py's gpu_launches claim) */
 int64_t trl_kernel_launches(trl_handle* h);
 
+/* device-resident view of the tuple block (rows f64 [cap][width], flags, env ids, count) for zero-copy hand-off to
+ * NCCL; replaces the per-thread `learner->Train(exp->GetTuples())` hand-off (scenarios/ScenarioTrain.cpp:388-395) */
+int trl_device_tuple_block(trl_handle* h, void** rows_f64, void** flags_u32, void** env_i32, void** count_i32,
+                           int* cap, int* width);
+
 /* measurement helpers: K outer updates timed with CUDA events on the handle's stream (optional L2 flush between
  * updates); one update with an event pair around every kernel launch (per-kernel device time for the roofline). */
 int trl_bench_updates(trl_handle* h, double dt, int k, int flush_l2, double* ms_total);

@@ -1,0 +1,71 @@
+"""CPU tests of the boundary: the C-ABI library loads, exports every symbol the header declares, fails loudly without
+a GPU; the asset packs carry the reference's cross-file identities."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+import deepterrainrl_b200 as trl
+from pack_scene import read_pack
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _cuda_available():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def test_library_exports_every_declared_symbol():
+    trl.build_library()
+    L = trl.load_library()
+    hdr = open(os.path.join(ROOT, "include", "terrainrl_b200.h")).read()
+    declared = set(re.findall(r"\b(trl_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 25
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in include/terrainrl_b200.h but not exported"
+    assert declared == set(trl.scenario.EXPORTS)
+
+
+def test_sm100a_cubin_and_no_cpu_fallback(assets):
+    import subprocess
+    out = subprocess.run(["/usr/local/cuda/bin/cuobjdump", "-lelf", trl.library_path()], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+    if not _cuda_available():
+        with pytest.raises(RuntimeError, match="GPU|CUDA"):
+            trl.ScenarioPoliEval(os.path.join(assets, "dog_flat.trlpack"), 4)
+
+
+def test_pack_cross_file_identities(assets):
+    """the scale file's critic offset/scale are (-0.5, 2) (sim/BaseControllerMACE.cpp:108-109) and the
+    actor offsets are minus the optimised parameters of the three gait files (sim/DogControllerMACE.cpp:93-99)."""
+    p = read_pack(os.path.join(assets, "dog_slopes_mixed.trlpack"))
+    off, sc = p["net_out_offset"], p["net_out_scale"]
+    assert np.all(off[:3] == -0.5) and np.all(sc[:3] == 2.0)
+    ctrl = p["ctrl_params"].reshape(-1, 30)
+    for a in range(3):
+        np.testing.assert_allclose(off[3 + 29 * a:3 + 29 * (a + 1)], -ctrl[a % 3][1:], atol=1e-6)
+    dims = p["net_dims"]
+    assert list(dims) == [283, 83, 90, 3, 29]
+    n_params = sum(p[k].size for k in p if k.startswith("net_") and (k.endswith("_w") or k.endswith("_b")))
+    assert n_params == 570474
+    mi = p["meta_i32"]
+    assert mi[2] == 20 and mi[3] == 5 and mi[8] == 21 and mi[9] == 23   # args/dog_slopes_mixed_args.txt:12-13
+    bodies = p["bodies"].reshape(21, 9)
+    assert abs(bodies[:, 1].sum() - 33.67) < 1e-9
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/data"), reason="reference tree not present on this box")
+def test_packs_regenerate_from_reference(assets, tmp_path):
+    from pack_scene import build_pack
+    for arg, name in (("args/sim_dog_args.txt", "dog_flat.trlpack"), ("args/dog_slopes_mixed_args.txt", "dog_slopes_mixed.trlpack"),
+                      ("args/goat_cliffs_args.txt", "goat_cliffs.trlpack")):
+        rec = build_pack(os.path.join("/root/reference", arg), "/root/reference")
+        old = read_pack(os.path.join(assets, name))
+        assert set(rec) == set(old)
+        for k in rec:
+            np.testing.assert_array_equal(np.asarray(rec[k]).ravel(), old[k])
