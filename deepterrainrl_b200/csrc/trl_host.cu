@@ -116,12 +116,49 @@ static int fill_model(trl_handle* h, uint64_t rng_seed) {
         m.half_x[j] = 0.5 * b[6]; m.half_y[j] = 0.5 * b[7];
         // planar inertia about the joint origin: box about its COM + parallel-axis shift (sim/RBDUtil.cpp:562-583,614-623)
         m.izz_o[j] = b[1] / 12.0 * (b[6] * b[6] + b[7] * b[7]) + b[1] * (b[2] * b[2] + b[3] * b[3]);
+        m.izz_c[j] = b[1] / 12.0 * (b[6] * b[6] + b[7] * b[7]);
         m.total_mass += b[1];
         // tail parts carry collision group "none" (sim/SimDog.cpp:7,21-24)
         m.collidable[j] = (j >= 9 && j <= 12) ? 0 : 1;
         const double* p = &P[6 * j];
         m.kp[j] = (j == 0) ? 0.0 : p[0]; m.kd[j] = (j == 0) ? 0.0 : p[1];
         m.torque_lim[j] = p[2]; m.target_theta0[j] = p[3]; m.target_vel[j] = p[4]; m.world_pd[j] = p[5] != 0;
+    }
+    // topology helpers
+    m.max_depth = 0;
+    for (int j = 0; j < m.nj; ++j) {
+        m.depth[j] = (j == 0) ? 0 : m.depth[m.parent[j]] + 1;
+        m.max_depth = std::max(m.max_depth, m.depth[j]);
+        for (int c = 0; c < 3; ++c) m.child[j][c] = -1;
+    }
+    if (m.max_depth >= 12) return fail("kinematic tree too deep");
+    for (int j = 1; j < m.nj; ++j) {
+        int p = m.parent[j], slot = 0;
+        while (slot < 3 && m.child[p][slot] >= 0) ++slot;
+        if (slot == 3) return fail("a link has more than 3 children");
+        m.child[p][slot] = j;
+        m.level_slot[m.depth[j]][slot] = 1;
+    }
+    m.n_corners = 0;
+    for (int j = 0; j < m.nj; ++j) {
+        m.corner_base[j] = -1;
+        if (!m.collidable[j]) continue;
+        m.corner_base[j] = m.n_corners;
+        for (int cn = 0; cn < 4; ++cn) {
+            double bx = (cn & 1) ? m.half_x[j] : -m.half_x[j], by = (cn & 2) ? m.half_y[j] : -m.half_y[j];
+            m.corner_body[m.n_corners] = j;
+            m.corner_lx[m.n_corners] = m.body_ax[j] + m.body_cos[j] * bx - m.body_sin[j] * by;
+            m.corner_ly[m.n_corners] = m.body_ay[j] + m.body_sin[j] * bx + m.body_cos[j] * by;
+            ++m.n_corners;
+        }
+    }
+    {
+        const int toe = 20, finger = 16, torso = 5;
+        m.anc_mask_toe = m.anc_mask_finger = m.vf_mask_toe = m.vf_mask_finger = 0;
+        for (int c = toe; c >= 0; c = m.parent[c]) m.anc_mask_toe |= 1u << c;
+        for (int c = finger; c >= 0; c = m.parent[c]) m.anc_mask_finger |= 1u << c;
+        for (int c = toe; c != 0 && c != torso; c = m.parent[c]) m.vf_mask_toe |= 1u << c;
+        for (int c = finger; c != 0 && c != torso; c = m.parent[c]) m.vf_mask_finger |= 1u << c;
     }
     const auto& C = s.f64("ctrl_params");
     for (int c = 0; c < m.n_ctrl; ++c)

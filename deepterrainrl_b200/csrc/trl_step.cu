@@ -1,26 +1,28 @@
-// deepterrainrl_b200 -- the env-step kernel (sm_100a).
+// deepterrainrl_b200 -- the env-step kernel (sm_100a), warp-per-environment formulation.
 //
-// One environment per warp lane, one warp per CTA, SoA state in HBM (coalesced 256-B plane reads), per-link
-// quantities staged in shared memory transposed [slot][lane] so that a dynamic link index never causes a bank
-// conflict (lane is the fastest-varying index; f64 => two conflict-free wavefronts per access).
+// One environment per WARP: lane j owns link j of the kinematic tree (21 links) and, for the dense solve, row j of
+// the 23x23 system; every tree recursion is level-synchronous over the tree depth (9 for the dog) with the
+// parent <-> child hand-off done by warp shuffles, so per-link quantities live in registers and shared memory only
+// holds the mass matrix.  All spatial quantities are planar 3-vectors expressed in WORLD axes about the root joint's
+// current position O (an inertial frame that instantaneously coincides with the root), which removes every
+// per-link coordinate transform from the recursions: motion (w, vOx, vOy), force (nO, fx, fy), joint axis of a
+// revolute joint at r (relative to O): S = (1, r_y, -r_x).
 //
 // One launch = the *controller half* of env-step k followed by the *physics half* of env-step k+1:
 //
 //   ctrl half  (reference: cSimCharacter::Update -> cDogController::Update, sim/DogController.cpp:229-268)
-//     planar CRBA mass matrix + RNEA bias force        (restates sim/RBDUtil.cpp:4-176 in 3-D planar algebra)
-//     ApplyFeedback, stable-PD solve (LDL^T 23x23), gravity compensation, virtual forces
-//     torque clamp (sim/Joint.cpp:257-264), fall counters (sim/SimCharSoftFall.cpp:74-125)
+//     CRBA mass matrix + RNEA bias force with the reference's Cj (restates sim/RBDUtil.cpp:4-176 in planar algebra)
+//     ApplyFeedback, stable-PD solve (register-resident LDL^T, one row per lane), gravity compensation,
+//     virtual forces, torque clamp (sim/Joint.cpp:257-264), fall counters (sim/SimCharSoftFall.cpp:74-125),
 //     cycle bookkeeping: reward, tuple record, episode statistics (scenarios/ScenarioExp.cpp:209-243)
 //   [end of outer update: fall -> episode reset, scenarios/ScenarioPoliEval.cpp:110-125, ScenarioExp.cpp:83-98]
 //   phys half  (reference: cWorld::Update + cGroundVar2D::Update + the head of the controller update)
-//     num_sim_substeps x planar articulated-body forward dynamics with implicit contact / joint-limit terms
-//     (this project's own physics model -- Bullet is not restatable), semi-implicit Euler
+//     num_sim_substeps x articulated-body forward dynamics with implicit contact / joint-limit terms (this project's
+//     own physics model -- Bullet is not restatable); box corners are evaluated one per lane
 //     contact bits, streaming terrain update, cycle timers, gait FSM (sim/DogController.cpp:805-845)
-//     lanes whose FSM reaches a cycle boundary build the 283-float policy state and enqueue a decision
+//     warps whose FSM reaches a cycle boundary build the 283-float policy state cooperatively and enqueue a decision
 //
-// The decision itself (MACE forward pass + action decode) runs in trl_decide.cu between two launches of this kernel;
-// because the controller half consumes the decided action at the start of the *next* launch, all lanes stay
-// convergent and no tail kernel is needed.
+// The decision itself (MACE forward pass + action decode) runs in trl_decide.cuh between two launches of this kernel.
 #include <cuda_runtime.h>
 
 #include "trl_terrain.cuh"
@@ -30,47 +32,22 @@ namespace trl {
 
 __constant__ ModelConst c_model;
 
-// ------------------------------------------------------------------------------------------------ scratch layout
-// per-lane shared-memory slots (each slot = one f64 per lane)
-enum Slot : int {
-    S_Q = 0,
-    S_QD = S_Q + kMaxDof,
-    S_TAU = S_QD + kMaxDof,
-    S_WC = S_TAU + kMaxDof,          // world cos of joint frame
-    S_WS = S_WC + kMaxJoints,        // world sin
-    S_WX = S_WS + kMaxJoints,        // world origin x
-    S_WY = S_WX + kMaxJoints,
-    S_JVX = S_WY + kMaxJoints,       // world velocity of joint origin
-    S_JVY = S_JVX + kMaxJoints,
-    S_JW = S_JVY + kMaxJoints,       // world angular velocity of link
-    S_JC = S_JW + kMaxJoints,        // cos / sin of each joint angle (child -> parent rotation)
-    S_JS = S_JC + kMaxJoints,
-    S_COMMON_END = S_JS + kMaxJoints,
-    // ---- controller phase
-    C_M = S_COMMON_END,              // lower-triangular mass matrix, 276
-    C_C = C_M + kMaxDof * (kMaxDof + 1) / 2,
-    C_RHS = C_C + kMaxDof,
-    C_ACC = C_RHS + kMaxDof,
-    C_TAUC = C_ACC + kMaxDof,
-    C_UNION = C_TAUC + kMaxDof,      // 189-slot union: {Ic[4][21]} | {LV,LA,LF [3][21] each} | {BASIS[23][4], TG[23]}
-    C_END = C_UNION + 9 * kMaxJoints,
-    // ---- physics phase (aliases the controller region)
-    P_V = S_COMMON_END,              // link velocity (w, vx, vy) in link coords
-    P_CV = P_V + 3 * kMaxJoints,     // velocity-product term (cx, cy)
-    P_IA = P_CV + 2 * kMaxJoints,    // articulated inertia (a, bx, by, cxx, cxy, cyy)
-    P_PA = P_IA + 6 * kMaxJoints,    // articulated bias force (n, fx, fy)
-    P_U = P_PA + 3 * kMaxJoints,
-    P_DINV = P_U + 3 * kMaxJoints,
-    P_UU = P_DINV + kMaxJoints,
-    P_A = P_UU + kMaxJoints,         // link acceleration
-    P_END = P_A + 3 * kMaxJoints,
-    S_NUM = (C_END > P_END ? C_END : P_END)
-};
-static_assert(S_NUM * kWarp * 8 <= 227 * 1024, "per-warp scratch exceeds shared memory");
-
-#define SL(slot) sm[(slot) * kWarp]
+constexpr int kWarpsPerBlock = 4;
+constexpr int kBlockThreads = kWarpsPerBlock * kWarp;
+constexpr unsigned kFull = 0xffffffffu;
+constexpr int kTri = kMaxDof * (kMaxDof + 1) / 2;   // 276
+// per-warp shared scratch (doubles)
+constexpr int X_M = 0;
+constexpr int X_END = X_M + kTri + 4;
 
 __device__ __forceinline__ int tri(int a, int b) { return a * (a + 1) / 2 + b; }  // a >= b
+__device__ __forceinline__ double shf(double v, int src) { return __shfl_sync(kFull, v, src); }
+__device__ __forceinline__ int shfi(int v, int src) { return __shfl_sync(kFull, v, src); }
+__device__ __forceinline__ double warp_sum_all(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
 
 __device__ __forceinline__ double wrap_pi(double a) {
     double s, c;
@@ -112,73 +89,15 @@ struct CounterRng {
     }
 };
 
-// ------------------------------------------------------------------------------------------------ lane context
+// ------------------------------------------------------------------------------------------------ global accessors
 struct Lane {
-    double* sm;          // shared scratch base for this lane
-    int env, n;          // env index, number of envs
-    double* D;           // f64 planes
-    int* I;              // i32 planes
+    double* sm;          // unused by the warp kernel (kept for the decision kernel's scalar helpers)
+    int env, n;
+    double* D;
+    int* I;
     __device__ __forceinline__ double& d(int f) { return D[(size_t)f * n + env]; }
     __device__ __forceinline__ int& i(int f) { return I[(size_t)f * n + env]; }
 };
-
-// forward kinematics of the joint frames: world rotation, origin, origin velocity, angular velocity
-__device__ void fk_world(Lane& L) {
-    double* sm = L.sm;
-    const ModelConst& m = c_model;
-    {
-        double s, c;
-        sincos(SL(S_Q + 2), &s, &c);
-        SL(S_WC) = c; SL(S_WS) = s; SL(S_WX) = SL(S_Q); SL(S_WY) = SL(S_Q + 1);
-        SL(S_JVX) = SL(S_QD); SL(S_JVY) = SL(S_QD + 1); SL(S_JW) = SL(S_QD + 2);
-    }
-    for (int j = 1; j < m.nj; ++j) {
-        int p = m.parent[j], o = m.dof[j];
-        double pc = SL(S_WC + p), ps = SL(S_WS + p);
-        double ax = pc * m.attach_x[j] - ps * m.attach_y[j], ay = ps * m.attach_x[j] + pc * m.attach_y[j];
-        double s, c;
-        sincos(SL(S_Q + o), &s, &c);
-        SL(S_JC + j) = c; SL(S_JS + j) = s;
-        SL(S_WC + j) = pc * c - ps * s;
-        SL(S_WS + j) = ps * c + pc * s;
-        SL(S_WX + j) = SL(S_WX + p) + ax;
-        SL(S_WY + j) = SL(S_WY + p) + ay;
-        double pw = SL(S_JW + p);
-        SL(S_JVX + j) = SL(S_JVX + p) - pw * ay;
-        SL(S_JVY + j) = SL(S_JVY + p) + pw * ax;
-        SL(S_JW + j) = pw + SL(S_QD + o);
-    }
-}
-// body COM world position / velocity of link j
-__device__ __forceinline__ void body_kin(double* sm, int j, double& px, double& py, double& vx, double& vy) {
-    const ModelConst& m = c_model;
-    double c = SL(S_WC + j), s = SL(S_WS + j);
-    double bx = c * m.body_ax[j] - s * m.body_ay[j], by = s * m.body_ax[j] + c * m.body_ay[j];
-    px = SL(S_WX + j) + bx; py = SL(S_WY + j) + by;
-    double w = SL(S_JW + j);
-    vx = SL(S_JVX + j) - w * by; vy = SL(S_JVY + j) + w * bx;
-}
-__device__ void calc_com(double* sm, double& cx, double& cy, double& vx, double& vy) {
-    const ModelConst& m = c_model;
-    cx = cy = vx = vy = 0.0;
-    for (int j = 0; j < m.nj; ++j) {
-        double px, py, bvx, bvy;
-        body_kin(sm, j, px, py, bvx, bvy);
-        cx += m.mass[j] * px; cy += m.mass[j] * py; vx += m.mass[j] * bvx; vy += m.mass[j] * bvy;
-    }
-    double inv = 1.0 / m.total_mass;
-    cx *= inv; cy *= inv; vx *= inv; vy *= inv;
-}
-// bottom-centre of a foot box (cDogController::GetEndEffectorContactPos)
-__device__ __forceinline__ void effector_pos(double* sm, int j, double& ex, double& ey) {
-    const ModelConst& m = c_model;
-    double px, py, vx, vy;
-    body_kin(sm, j, px, py, vx, vy);
-    double c = SL(S_WC + j) * m.body_cos[j] - SL(S_WS + j) * m.body_sin[j];
-    double s = SL(S_WS + j) * m.body_cos[j] + SL(S_WC + j) * m.body_sin[j];
-    double ly = -m.half_y[j];
-    ex = px - s * ly; ey = py + c * ly;
-}
 
 __device__ __forceinline__ bool has_fallen(Lane& L, double root_theta) {
     return L.d(D_SUM_FALL) > 0.25 || L.i(I_FAIL_FALL_DIST) != 0 || fabs(wrap_pi(root_theta)) > 3.14159265358979323846 * 0.8;
@@ -197,309 +116,6 @@ __device__ void set_state_params(Lane& L, int state) {
     L.d(D_PD_TARGET + jAnkle) = L.d(base + spAnkle);
 }
 
-// ================================================================================================ controller half
-// Planar restatement of cRBDModel::Update (CRBA + RNEA with the reference's Cj), the stable-PD solve, gravity
-// compensation and virtual forces.  Writes the clamped torques to S_TAU.
-__device__ void controller_torque(Lane& L, double h, int contact) {
-    double* sm = L.sm;
-    const ModelConst& m = c_model;
-    const int nj = m.nj, nd = m.ndof;
-
-    // pose as the controller sees it: root angle wrapped (axis-angle extraction), hinges as is
-    const double th0 = wrap_pi(SL(S_Q + 2));
-    double s0, c0;
-    sincos(th0, &s0, &c0);
-
-    // ---- CRBA: composite rigid-body inertias (m, hx, hy, I) in link coordinates, accumulated leaf -> root
-    const int IC = C_UNION;
-    for (int j = 0; j < nj; ++j) {
-        SL(IC + 4 * j + 0) = m.mass[j];
-        SL(IC + 4 * j + 1) = m.mass[j] * m.body_ax[j];
-        SL(IC + 4 * j + 2) = m.mass[j] * m.body_ay[j];
-        SL(IC + 4 * j + 3) = m.izz_o[j];
-    }
-    for (int k = 0; k < nd * (nd + 1) / 2; ++k) SL(C_M + k) = 0.0;
-    for (int j = nj - 1; j >= 0; --j) {
-        double mj = SL(IC + 4 * j), hx = SL(IC + 4 * j + 1), hy = SL(IC + 4 * j + 2), Iz = SL(IC + 4 * j + 3);
-        int p = m.parent[j];
-        if (p >= 0) {
-            // shift the composite inertia into the parent's frame: rotate first moment, translate by attach
-            double c = SL(S_JC + j), s = SL(S_JS + j);
-            double hxp = c * hx - s * hy, hyp = s * hx + c * hy;
-            double ax = m.attach_x[j], ay = m.attach_y[j];
-            SL(IC + 4 * p + 0) += mj;
-            SL(IC + 4 * p + 1) += hxp + mj * ax;
-            SL(IC + 4 * p + 2) += hyp + mj * ay;
-            SL(IC + 4 * p + 3) += Iz + 2.0 * (ax * hxp + ay * hyp) + mj * (ax * ax + ay * ay);
-        }
-        if (j > 0) {
-            // F = Ic * S (S = unit rotation): force (n, fx, fy) in link j coords
-            double fn = Iz, fx = -hy, fy = hx;
-            int oj = m.dof[j];
-            SL(C_M + tri(oj, oj)) = fn;
-            int cur = j;
-            while (cur > 0) {
-                double c = SL(S_JC + cur), s = SL(S_JS + cur);
-                double gx = c * fx - s * fy, gy = s * fx + c * fy;
-                fn = fn + m.attach_x[cur] * gy - m.attach_y[cur] * gx;
-                fx = gx; fy = gy;
-                cur = m.parent[cur];
-                if (cur > 0) SL(C_M + tri(oj, m.dof[cur])) = fn;
-                else {
-                    // root columns: S = [Rz(-th)^T e_x, Rz(-th)^T e_y, e_w] in root coords
-                    SL(C_M + tri(oj, 0)) = c0 * fx - s0 * fy;
-                    SL(C_M + tri(oj, 1)) = s0 * fx + c0 * fy;
-                    SL(C_M + tri(oj, 2)) = fn;
-                }
-            }
-        } else {
-            // root block S^T Ic S with S = [(0; c, -s), (0; s, c), (1; 0, 0)]
-            // Ic = [[Iz, -hy, hx], [-hy, m, 0], [hx, 0, m]]
-            double ex0 = c0, ey0 = -s0, ex1 = s0, ey1 = c0;   // linear parts of columns 0, 1 (root coords)
-            SL(C_M + tri(0, 0)) = mj;
-            SL(C_M + tri(1, 0)) = 0.0;
-            SL(C_M + tri(1, 1)) = mj;
-            SL(C_M + tri(2, 0)) = -hy * ex0 + hx * ey0;
-            SL(C_M + tri(2, 1)) = -hy * ex1 + hx * ey1;
-            SL(C_M + tri(2, 2)) = Iz;
-        }
-    }
-
-    // ---- RNEA bias force with qdd = 0, base acceleration -g, and the reference's BuildCjPlanar (cos/cos)
-    const int LV = C_UNION, LA = C_UNION + 3 * kMaxJoints, LF = C_UNION + 6 * kMaxJoints;
-    {
-        double xd = SL(S_QD), yd = SL(S_QD + 1), thd = SL(S_QD + 2);
-        double cb = cos(thd), sb = cb;   // sim/RBDUtil.cpp:821-822
-        double cjx = (-sb * xd + cb * yd) * thd, cjy = (-cb * xd - sb * yd) * thd;
-        // v = S qd (root coords); a = X(-g) + cj
-        SL(LV + 0) = thd; SL(LV + 1) = c0 * xd + s0 * yd; SL(LV + 2) = -s0 * xd + c0 * yd;
-        double gx = -m.gx, gy = -m.gy;
-        SL(LA + 0) = 0.0; SL(LA + 1) = c0 * gx + s0 * gy + cjx; SL(LA + 2) = -s0 * gx + c0 * gy + cjy;
-    }
-    for (int j = 1; j < nj; ++j) {
-        int p = m.parent[j], o = m.dof[j];
-        double c = SL(S_JC + j), s = SL(S_JS + j);
-        double ax = m.attach_x[j], ay = m.attach_y[j], qd = SL(S_QD + o);
-        double pw = SL(LV + 3 * p), pvx = SL(LV + 3 * p + 1) - pw * ay, pvy = SL(LV + 3 * p + 2) + pw * ax;
-        double w = pw + qd, vx = c * pvx + s * pvy, vy = -s * pvx + c * pvy;
-        double pa = SL(LA + 3 * p), pax = SL(LA + 3 * p + 1) - pa * ay, pay = SL(LA + 3 * p + 2) + pa * ax;
-        // crossM(v, vj), vj = (qd, 0, 0): linear part v_lin x (qd z)
-        SL(LV + 3 * j) = w; SL(LV + 3 * j + 1) = vx; SL(LV + 3 * j + 2) = vy;
-        SL(LA + 3 * j) = pa;
-        SL(LA + 3 * j + 1) = c * pax + s * pay + vy * qd;
-        SL(LA + 3 * j + 2) = -s * pax + c * pay - vx * qd;
-    }
-    for (int j = 0; j < nj; ++j) {
-        double mj = m.mass[j], hx = mj * m.body_ax[j], hy = mj * m.body_ay[j], Iz = m.izz_o[j];
-        double w = SL(LV + 3 * j), vx = SL(LV + 3 * j + 1), vy = SL(LV + 3 * j + 2);
-        double aw = SL(LA + 3 * j), ax = SL(LA + 3 * j + 1), ay = SL(LA + 3 * j + 2);
-        double hn = Iz * w - hy * vx + hx * vy, hpx = mj * vx - hy * w, hpy = mj * vy + hx * w;
-        SL(LF + 3 * j) = Iz * aw - hy * ax + hx * ay + (vx * hpy - vy * hpx);
-        SL(LF + 3 * j + 1) = mj * ax - hy * aw - w * hpy;
-        SL(LF + 3 * j + 2) = mj * ay + hx * aw + w * hpx;
-        (void)hn;
-    }
-    for (int j = nj - 1; j >= 1; --j) {
-        int p = m.parent[j], o = m.dof[j];
-        double fn = SL(LF + 3 * j), fx = SL(LF + 3 * j + 1), fy = SL(LF + 3 * j + 2);
-        SL(C_C + o) = fn;
-        double c = SL(S_JC + j), s = SL(S_JS + j);
-        double gx = c * fx - s * fy, gy = s * fx + c * fy;
-        SL(LF + 3 * p) += fn + m.attach_x[j] * gy - m.attach_y[j] * gx;
-        SL(LF + 3 * p + 1) += gx;
-        SL(LF + 3 * p + 2) += gy;
-    }
-    {
-        double fn = SL(LF), fx = SL(LF + 1), fy = SL(LF + 2);
-        SL(C_C + 0) = c0 * fx - s0 * fy;
-        SL(C_C + 1) = s0 * fx + c0 * fy;
-        SL(C_C + 2) = fn;
-    }
-
-    // ---- ApplyFeedback (sim/DogController.cpp:903-945)
-    const int state = L.i(I_STATE);
-    double comx, comy, comvx, comvy;
-    calc_com(sm, comx, comy, comvx, comvy);
-    {
-        double cv = L.d(D_PARAMS + mCv);
-        int base = D_PARAMS + mMiscMax + state * spMax;
-        if (!((contact >> jToe) & 1)) L.d(D_PD_TARGET + jHip) = L.d(base + spHip) + comvx * cv;
-        if (!((contact >> jFinger) & 1)) L.d(D_PD_TARGET + jShoulder) = L.d(base + spShoulder) + comvx * cv;
-    }
-
-    // ---- cImpPDController::CalcControlForces (sim/ImpPDController.cpp:234-278)
-    SL(C_RHS) = -SL(C_C); SL(C_RHS + 1) = -SL(C_C + 1); SL(C_RHS + 2) = -SL(C_C + 2);
-    SL(C_TAUC) = 0.0; SL(C_TAUC + 1) = 0.0; SL(C_TAUC + 2) = 0.0;
-    for (int j = 1; j < nj; ++j) {
-        int o = m.dof[j];
-        double theta = SL(S_Q + o);
-        if (m.world_pd[j]) {
-            // child body's world rotation, wrapped (cPDController::CalcTheta, sim/PDController.cpp:181-198)
-            double c = SL(S_WC + j) * m.body_cos[j] - SL(S_WS + j) * m.body_sin[j];
-            double s = SL(S_WS + j) * m.body_cos[j] + SL(S_WC + j) * m.body_sin[j];
-            double a = acos(fmin(1.0, fmax(-1.0, c)));
-            theta = (s >= 0) ? a : -a;
-        }
-        double qd = SL(S_QD + o);
-        double perr = L.d(D_PD_TARGET + j) - theta, verr = m.target_vel[j] - qd;
-        double t0 = m.kp[j] * (perr - h * qd);
-        SL(C_TAUC + o) = t0 + m.kd[j] * verr;          // tau = Kp(e - h qd) + Kd(ev - h acc): acc term added below
-        SL(C_RHS + o) = t0 + m.kd[j] * verr - SL(C_C + o);
-        SL(C_M + tri(o, o)) += h * m.kd[j];
-    }
-    // in-place LDL^T of the lower triangle, then solve
-    for (int j = 0; j < nd; ++j) {
-        double dj = SL(C_M + tri(j, j));
-        for (int k = 0; k < j; ++k) { double l = SL(C_M + tri(j, k)); dj -= l * l * SL(C_M + tri(k, k)); }
-        SL(C_M + tri(j, j)) = dj;
-        double inv = 1.0 / dj;
-        for (int i = j + 1; i < nd; ++i) {
-            double v = SL(C_M + tri(i, j));
-            for (int k = 0; k < j; ++k) v -= SL(C_M + tri(i, k)) * SL(C_M + tri(j, k)) * SL(C_M + tri(k, k));
-            SL(C_M + tri(i, j)) = v * inv;
-        }
-    }
-    for (int i = 0; i < nd; ++i) {
-        double v = SL(C_RHS + i);
-        for (int k = 0; k < i; ++k) v -= SL(C_M + tri(i, k)) * SL(C_ACC + k);
-        SL(C_ACC + i) = v;
-    }
-    for (int i = 0; i < nd; ++i) SL(C_ACC + i) /= SL(C_M + tri(i, i));
-    for (int i = nd - 1; i >= 0; --i) {
-        double v = SL(C_ACC + i);
-        for (int k = i + 1; k < nd; ++k) v -= SL(C_M + tri(k, i)) * SL(C_ACC + k);
-        SL(C_ACC + i) = v;
-    }
-    for (int j = 1; j < nj; ++j) {
-        int o = m.dof[j];
-        SL(C_TAUC + o) -= m.kd[j] * h * SL(C_ACC + o);
-    }
-
-    // ---- ApplyGravityCompensation (sim/DogController.cpp:947-995, 1120-1175)
-    const bool toe_c = (contact >> jToe) & 1, fin_c = (contact >> jFinger) & 1;
-    if (m.grav_comp && (toe_c || fin_c)) {
-        const int BAS = C_UNION, TG = C_UNION + 4 * kMaxDof;
-        for (int k = 0; k < 4 * nd; ++k) SL(BAS + k) = 0.0;
-        for (int e = 0; e < 2; ++e) {
-            int ej = e == 0 ? jToe : jFinger;
-            if (!((contact >> ej) & 1)) continue;
-            double ex, ey;
-            effector_pos(sm, ej, ex, ey);
-            // column 2e: unit +y force, column 2e+1: unit +x force; entry = J_k^T f = torque of f about joint k
-            for (int cur = ej; cur >= 0; cur = m.parent[cur]) {
-                if (cur > 0) {
-                    int o = m.dof[cur];
-                    double rx = ex - SL(S_WX + cur), ry = ey - SL(S_WY + cur);
-                    SL(BAS + 4 * o + 2 * e) = rx;        // (r x (0,1))
-                    SL(BAS + 4 * o + 2 * e + 1) = -ry;   // (r x (1,0))
-                } else {
-                    double rx = ex - SL(S_WX), ry = ey - SL(S_WY);
-                    SL(BAS + 4 * 0 + 2 * e) = 0.0; SL(BAS + 4 * 0 + 2 * e + 1) = 1.0;
-                    SL(BAS + 4 * 1 + 2 * e) = 1.0; SL(BAS + 4 * 1 + 2 * e + 1) = 0.0;
-                    SL(BAS + 4 * 2 + 2 * e) = rx;  SL(BAS + 4 * 2 + 2 * e + 1) = -ry;
-                }
-            }
-        }
-        // tau_g = -CalcGravityForce: per-link gravity wrench, accumulated towards the root
-        // (generalised force of gravity acting as an acceleration field +g; sim/RBDUtil.cpp:850-895)
-        for (int k = 0; k < nd; ++k) SL(TG + k) = 0.0;
-        {
-            // world-frame accumulation: torque about joint k of the weights of all bodies in its subtree
-            // subtree mass moments via one leaf -> root sweep in world coordinates
-            // reuse RHS slots as temporaries: (msum, mx, my) per link packed in C_RHS is too small -> use LA region
-            const int SUB = C_UNION + 5 * kMaxDof;   // 3 * nj slots (fits: 5*23 + 63 = 178 <= 189)
-            for (int j = 0; j < nj; ++j) {
-                double px, py, vx, vy;
-                body_kin(sm, j, px, py, vx, vy);
-                SL(SUB + 3 * j) = m.mass[j]; SL(SUB + 3 * j + 1) = m.mass[j] * px; SL(SUB + 3 * j + 2) = m.mass[j] * py;
-            }
-            for (int j = nj - 1; j >= 1; --j) {
-                int p = m.parent[j];
-                SL(SUB + 3 * p) += SL(SUB + 3 * j); SL(SUB + 3 * p + 1) += SL(SUB + 3 * j + 1); SL(SUB + 3 * p + 2) += SL(SUB + 3 * j + 2);
-            }
-            // generalised gravity force G_k = sum_subtree (r_com - p_k) x (m g); tau_g = -G
-            for (int j = 1; j < nj; ++j) {
-                double ms = SL(SUB + 3 * j), mx = SL(SUB + 3 * j + 1), my = SL(SUB + 3 * j + 2);
-                double rx = mx - ms * SL(S_WX + j), ry = my - ms * SL(S_WY + j);
-                SL(TG + m.dof[j]) = -(rx * m.gy - ry * m.gx);
-            }
-            double ms = SL(SUB), mx = SL(SUB + 1), my = SL(SUB + 2);
-            double rx = mx - ms * SL(S_WX), ry = my - ms * SL(S_WY);
-            SL(TG + 0) = -(ms * m.gx); SL(TG + 1) = -(ms * m.gy); SL(TG + 2) = -(rx * m.gy - ry * m.gx);
-        }
-        // ridge least squares on the root rows: (A^T A + 1e-4 I) x = A^T b, A = basis[0:3, :], b = tau_g[0:3]
-        double A[4][5];
-        for (int a = 0; a < 4; ++a) {
-            double atb = 0.0;
-            for (int r = 0; r < 3; ++r) atb += SL(BAS + 4 * r + a) * SL(TG + r);
-            for (int b = 0; b < 4; ++b) {
-                double v = 0.0;
-                for (int r = 0; r < 3; ++r) v += SL(BAS + 4 * r + a) * SL(BAS + 4 * r + b);
-                A[a][b] = v;
-            }
-            A[a][a] += 0.0001;
-            A[a][4] = atb;
-        }
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            int piv = c;
-#pragma unroll
-            for (int r = c + 1; r < 4; ++r) if (fabs(A[r][c]) > fabs(A[piv][c])) piv = r;
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                if (r == piv && piv != c) {
-#pragma unroll
-                    for (int k = 0; k < 5; ++k) { double t = A[c][k]; A[c][k] = A[r][k]; A[r][k] = t; }
-                }
-            }
-#pragma unroll
-            for (int r = c + 1; r < 4; ++r) {
-                double f = A[r][c] / A[c][c];
-#pragma unroll
-                for (int k = c; k < 5; ++k) A[r][k] -= f * A[c][k];
-            }
-        }
-        double x[4];
-#pragma unroll
-        for (int r = 3; r >= 0; --r) {
-            double v = A[r][4];
-#pragma unroll
-            for (int k = r + 1; k < 4; ++k) v -= A[r][k] * x[k];
-            x[r] = v / A[r][r];
-        }
-        for (int a = 3; a < nd; ++a) {
-            double tc = SL(BAS + 4 * a) * x[0] + SL(BAS + 4 * a + 1) * x[1] + SL(BAS + 4 * a + 2) * x[2] + SL(BAS + 4 * a + 3) * x[3];
-            SL(C_TAUC + a) += SL(TG + a) - tc;
-        }
-    }
-
-    // ---- ApplyVirtualForces (sim/DogController.cpp:997-1029)
-    if (m.virt_forces) {
-        for (int e = 0; e < 2; ++e) {
-            int ej = e == 0 ? jToe : jFinger;
-            bool valid = (e == 0) ? (state == sBackStance || state == sExtend) : (state == sFrontStance || state == sGather);
-            if (!(valid && ((contact >> ej) & 1))) continue;
-            double fx = -L.d(D_PARAMS + (e == 0 ? mBackForceX : mFrontForceX));
-            double fy = -L.d(D_PARAMS + (e == 0 ? mBackForceY : mFrontForceY));
-            double ex, ey;
-            effector_pos(sm, ej, ex, ey);
-            for (int cur = ej; cur != jRoot && cur != jTorso; cur = m.parent[cur]) {
-                double rx = ex - SL(S_WX + cur), ry = ey - SL(S_WY + cur);
-                SL(C_TAUC + m.dof[cur]) += rx * fy - ry * fx;
-            }
-        }
-    }
-
-    // ---- cJoint::ApplyTorque clamp (sim/Joint.cpp:171-201,257-264)
-    SL(S_TAU) = 0.0; SL(S_TAU + 1) = 0.0; SL(S_TAU + 2) = 0.0;
-    for (int j = 1; j < nj; ++j) {
-        int o = m.dof[j];
-        double t = SL(C_TAUC + o), lim = m.torque_lim[j];
-        if (fabs(t) > lim) t *= lim / fabs(t);
-        SL(S_TAU + o) = t;
-    }
-}
-
 // cDogController::CalcReward (sim/DogController.cpp:594-623)
 __device__ double calc_reward(Lane& L, bool fallen) {
     double vel_r = 0.0, stum_r = 0.0;
@@ -514,36 +130,40 @@ __device__ double calc_reward(Lane& L, bool fallen) {
     return 0.8 * vel_r + 0.2 * stum_r;
 }
 
-// cScenarioExp::NewCycleUpdate (scenarios/ScenarioExp.cpp:209-243): finish the previous tuple, start the next
-__device__ void exp_new_cycle_update(Lane& L, const Buffers& B, bool fallen) {
+// cScenarioExp::NewCycleUpdate (scenarios/ScenarioExp.cpp:209-243): finish the previous tuple, start the next.
+// Cooperative: the row copies are spread over the warp, the scalar bookkeeping is done by lane 0.
+__device__ void exp_new_cycle_update(Lane& L, const Buffers& B, bool fallen, int lane) {
     const int S = B.S, A = 1 + (kNumParams - 1);
     const double* s_end = B.poli_state + (size_t)L.env * S;
     double* s_beg = B.tuple_sbeg + (size_t)L.env * S;
     double* act = B.tuple_action + (size_t)L.env * kNumParams;
-    unsigned flags = (unsigned)L.i(I_TUPLE_FLAGS);
-    flags = fallen ? (flags | 1u) : (flags & ~1u);
-    double reward = calc_reward(L, fallen);
-    if (L.i(I_CYCLE_COUNT) > 1) {
-        int slot = atomicAdd(B.tuple_count, 1);
-        if (slot < B.tuple_cap) {
-            double* row = B.tuples + (size_t)slot * (1 + S + A + S);
-            row[0] = reward;
-            for (int k = 0; k < S; ++k) row[1 + k] = s_beg[k];
-            for (int k = 0; k < A; ++k) row[1 + S + k] = act[k];
-            for (int k = 0; k < S; ++k) row[1 + S + A + k] = s_end[k];
+    int slot = -1;
+    if (lane == 0 && L.i(I_CYCLE_COUNT) > 1) slot = atomicAdd(B.tuple_count, 1);
+    slot = shfi(slot, 0);
+    if (slot >= 0 && slot < B.tuple_cap) {
+        double* row = B.tuples + (size_t)slot * (1 + S + A + S);
+        for (int k = lane; k < S; k += kWarp) { row[1 + k] = s_beg[k]; row[1 + S + A + k] = s_end[k]; }
+        for (int k = lane; k < A; k += kWarp) row[1 + S + k] = act[k];
+        if (lane == 0) {
+            unsigned flags = (unsigned)L.i(I_TUPLE_FLAGS);
+            flags = fallen ? (flags | 1u) : (flags & ~1u);
+            row[0] = calc_reward(L, fallen);
             B.tuple_flags[slot] = flags;
             B.tuple_env[slot] = L.env;
         }
     }
-    for (int k = 0; k < S; ++k) s_beg[k] = s_end[k];
-    act[0] = (double)L.i(I_ACTION_ID);
-    for (int k = 1; k < kNumParams; ++k) act[k] = L.d(D_PARAMS + k);
-    int ef = L.i(I_EXP_FLAGS);
-    unsigned nf = 0;
-    if (ef & 1) nf |= 2u;   // exp critic -> eFlagExpCritic (bit 1)
-    if (ef & 2) nf |= 4u;   // exp actor  -> eFlagExpActor  (bit 2)
-    L.i(I_TUPLE_FLAGS) = (int)nf;
-    L.i(I_CYCLE_COUNT) += 1;
+    __syncwarp();
+    for (int k = lane; k < S; k += kWarp) s_beg[k] = s_end[k];
+    for (int k = lane; k < kNumParams; k += kWarp) act[k] = (k == 0) ? (double)L.i(I_ACTION_ID) : L.d(D_PARAMS + k);
+    if (lane == 0) {
+        int ef = L.i(I_EXP_FLAGS);
+        unsigned nf = 0;
+        if (ef & 1) nf |= 2u;   // exp critic -> eFlagExpCritic (bit 1)
+        if (ef & 2) nf |= 4u;   // exp actor  -> eFlagExpActor  (bit 2)
+        L.i(I_TUPLE_FLAGS) = (int)nf;
+        L.i(I_CYCLE_COUNT) += 1;
+    }
+    __syncwarp();
 }
 
 // cDogController::BlendCtrlParams / BuildBaseAction (+ cDogControllerMACE::AssignFragID); writes params, returns id
@@ -617,311 +237,653 @@ __device__ void store_rng(Lane& L, const CounterRng& r) {
     L.i(I_RNG_CTR_HI) = (int)(uint32_t)(r.ctr >> 32);
 }
 
-// cScenarioSimChar::Reset (+ PoliEval / Exp specifics): scenarios/ScenarioSimChar.cpp:121-132
-__device__ void reset_env(Lane& L, const Buffers& B) {
-    double* sm = L.sm;
+// ================================================================================================ warp context
+// Per-lane constants of link `lane` and the env state held in registers.
+struct LinkC {
+    int act;            // lane < nj
+    int parent, depth, child0, child1, child2;
+    double ax, ay;      // attach point in the parent's joint frame
+    double mass, bax, bay, izz_c;
+    int has_lim;
+    double lim_lo, lim_hi;
+};
+struct Kin {            // world-axes kinematics of link `lane` about O (the root joint position)
+    double phi, cw, sw, rx, ry, w, vx, vy;   // joint frame rotation, joint origin, spatial velocity (w, vO)
+    double cx, cy;                           // body COM
+};
+struct EnvRegs {
+    double q, qd;            // lane j: joint angle / rate of link j (lane 0: root angle)
+    double ox, oy, oxd, oyd; // root translation and its rate (same value in every lane)
+    double tau;              // held joint torque of link j
+};
+
+__device__ __forceinline__ LinkC load_link(int lane) {
     const ModelConst& m = c_model;
-    for (int k = 0; k < m.ndof; ++k) { SL(S_Q + k) = m.pose0[k]; SL(S_QD + k) = m.vel0[k]; SL(S_TAU + k) = 0.0; }
-    L.i(I_CONTACT) = 0;
-    fk_world(L);
-    double comx, comy, cvx, cvy;
-    calc_com(sm, comx, comy, cvx, cvy);
-    CounterRng rng = load_rng(L);
-    // controller reset: default action, FSM state 0, counters zeroed (sim/TerrainRLCharController.cpp:47-58,
-    // sim/DogController.cpp:210-216,640-650)
-    double params[kNumParams];
-    int id = build_base_action(L, rng, m.default_action, params);
-    apply_action(L, id, params, comx, comy);
-    L.i(I_EXP_FLAGS) = 0;
-    L.i(I_FIRST_CYCLE) = 1;
-    L.d(D_PREV_CYCLE_T) = 0.0; L.d(D_CUR_CYCLE_T) = 0.0; L.d(D_PREV_STUMBLE) = 0.0; L.d(D_CUR_STUMBLE) = 0.0;
-    L.d(D_PREV_DIST_X) = 0.0; L.d(D_PREV_DIST_Y) = 0.0;
-    L.d(D_PREV_COM_X) = comx; L.d(D_PREV_COM_Y) = comy;
-    L.i(I_CMD) = -1;
-    L.i(I_PENDING) = 0;
-    // cSimCharSoftFall::Reset
-    L.d(D_FALL_DIST_CNT) = 5.0; L.d(D_PREV_CHECK_X) = SL(S_Q); L.d(D_PREV_CHECK_Y) = SL(S_Q + 1);
-    L.i(I_FAIL_FALL_DIST) = 0; L.d(D_FALL_CONTACT_CNT) = 0.1; L.d(D_SUM_FALL) = 0.0;
-    // ResetGround + InitCharacterPos
-    GroundView g = load_ground(L, B);
-    g.n[0] = g.n[1] = 0; g.flip = 0;
-    g.update(-11.0, 9.0, m.terrain_type, m.terrain_params, 20.0);
-    if (m.has_init_x) SL(S_Q) = m.init_x;
-    SL(S_Q + 1) += g.sample(SL(S_Q));
-    store_ground(L, g);
-    if (m.exp_mode) {
-        L.i(I_CYCLE_COUNT) = 0;
-        L.i(I_CMD) = rng.rand_int(0, m.n_actions);   // cScenarioExp::CommandRandAction
-    } else {
-        L.d(D_POS_START_X) = SL(S_Q);
+    LinkC c;
+    c.act = lane < m.nj;
+    int j = c.act ? lane : 0;
+    c.parent = (c.act && j > 0) ? m.parent[j] : 0;
+    c.depth = c.act ? m.depth[j] : -1;
+    c.child0 = c.act ? m.child[j][0] : -1;
+    c.child1 = c.act ? m.child[j][1] : -1;
+    c.child2 = c.act ? m.child[j][2] : -1;
+    c.ax = m.attach_x[j]; c.ay = m.attach_y[j];
+    c.mass = c.act ? m.mass[j] : 0.0;
+    c.bax = m.body_ax[j]; c.bay = m.body_ay[j];
+    c.izz_c = c.act ? m.izz_c[j] : 0.0;
+    c.has_lim = c.act ? m.has_limit[j] : 0;
+    c.lim_lo = m.lim_lo[j]; c.lim_hi = m.lim_hi[j];
+    return c;
+}
+
+// level-synchronous outward pass: world rotation, joint origin (rel. O) and spatial velocity of every link
+__device__ __forceinline__ Kin kinematics(const LinkC& c, const EnvRegs& e) {
+    const int md = c_model.max_depth;
+    Kin k;
+    double phi = e.q, w = e.qd;
+    for (int l = 1; l <= md; ++l) {
+        double pphi = shf(phi, c.parent), pw = shf(w, c.parent);
+        if (c.depth == l) { phi = pphi + e.q; w = pw + e.qd; }
     }
-    store_rng(L, rng);
+    k.phi = phi; k.w = w;
+    sincos(phi, &k.sw, &k.cw);
+    double rx = 0.0, ry = 0.0, vx = e.oxd, vy = e.oyd;
+    for (int l = 1; l <= md; ++l) {
+        double pcw = shf(k.cw, c.parent), psw = shf(k.sw, c.parent), prx = shf(rx, c.parent), pry = shf(ry, c.parent);
+        double pvx = shf(vx, c.parent), pvy = shf(vy, c.parent);
+        if (c.depth == l) {
+            rx = prx + pcw * c.ax - psw * c.ay;
+            ry = pry + psw * c.ax + pcw * c.ay;
+            vx = pvx + e.qd * ry;      // v_j = v_parent + S_j qd_j,  S_j = (1, r_y, -r_x)
+            vy = pvy - e.qd * rx;
+        }
+    }
+    k.rx = rx; k.ry = ry; k.vx = vx; k.vy = vy;
+    k.cx = rx + k.cw * c.bax - k.sw * c.bay;
+    k.cy = ry + k.sw * c.bax + k.cw * c.bay;
+    return k;
+}
+
+// children -> parent accumulation of NV register values for tree level l (deterministic slot order)
+#define TRL_ACCUM_LEVEL(l, NV, vals)                                                        \
+    do {                                                                                    \
+        _Pragma("unroll") for (int s_ = 0; s_ < 3; ++s_) {                                  \
+            if (!c_model.level_slot[(l)][s_]) continue;                                     \
+            int ch_ = (s_ == 0) ? lc.child0 : ((s_ == 1) ? lc.child1 : lc.child2);          \
+            int src_ = ch_ >= 0 ? ch_ : 0;                                                  \
+            bool take_ = (ch_ >= 0) && (lc.depth == (l)-1);                                 \
+            _Pragma("unroll") for (int v_ = 0; v_ < (NV); ++v_) {                           \
+                double t_ = shf((vals)[v_], src_);                                          \
+                if (take_) (vals)[v_] += t_;                                                \
+            }                                                                               \
+        }                                                                                   \
+    } while (0)
+
+// ================================================================================================ controller half
+// Returns the clamped joint torque of link `lane` (0 for the root and idle lanes).
+__device__ double controller_torque(Lane& L, const LinkC& lc, const EnvRegs& e, const Kin& k, double* xs, int lane,
+                                    double h, int contact) {
+    const ModelConst& m = c_model;
+    const int nj = m.nj, nd = m.ndof, md = m.max_depth;
+    double* M = xs + X_M;
+
+    // ---- body inertia about O in world axes, RNEA accelerations with qdd = 0 and the reference's Cj
+    const double hx = lc.mass * k.cx, hy = lc.mass * k.cy, Io = lc.izz_c + lc.mass * (k.cx * k.cx + k.cy * k.cy);
+    double alx, aly;
+    {
+        // root: a0 = -g + R0 * cj, cj from cRBDUtil::BuildCjPlanar with c = s = cos(theta_dot) (sim/RBDUtil.cpp:821-822)
+        double thd = shf(e.qd, 0), c0 = shf(k.cw, 0), s0 = shf(k.sw, 0);
+        double cb = cos(thd);
+        double cjx = (-cb * e.oxd + cb * e.oyd) * thd, cjy = (-cb * e.oxd - cb * e.oyd) * thd;
+        alx = -m.gx + c0 * cjx - s0 * cjy;
+        aly = -m.gy + s0 * cjx + c0 * cjy;
+    }
+    for (int l = 1; l <= md; ++l) {
+        double pax = shf(alx, lc.parent), pay = shf(aly, lc.parent);
+        if (lc.depth == l) {
+            alx = pax + e.qd * (k.w * k.rx + k.vy);   // a_j = a_parent + v_j x (S_j qd_j)
+            aly = pay + e.qd * (k.w * k.ry - k.vx);
+        }
+    }
+    // vals: composite inertia (Io, hx, hy, m) and subtree force (n, fx, fy)
+    double vals[7];
+    {
+        double hlx = -hy * k.w + lc.mass * k.vx, hly = hx * k.w + lc.mass * k.vy;
+        vals[0] = Io; vals[1] = hx; vals[2] = hy; vals[3] = lc.mass;
+        vals[4] = (-hy * alx + hx * aly) + (k.vx * hly - k.vy * hlx);
+        vals[5] = lc.mass * alx - k.w * hly;
+        vals[6] = lc.mass * aly + k.w * hlx;
+        if (!lc.act) { vals[4] = vals[5] = vals[6] = 0.0; }
+    }
+    for (int l = md; l >= 1; --l) TRL_ACCUM_LEVEL(l, 7, vals);
+    const double s1 = k.ry, s2 = -k.rx;                       // S_j = (1, s1, s2)
+    // bias force C (per link lane; the root's three entries live in lane 0)
+    const double Cj = vals[4] + s1 * vals[5] + s2 * vals[6];
+    const double C0 = shf(vals[5], 0), C1 = shf(vals[6], 0), C2 = shf(vals[4], 0);
+
+    // ---- CRBA: M[i][a] = S_a . (Ic_i S_i) for every ancestor a of i; lower triangle in shared memory
+    for (int t = lane; t < kTri; t += kWarp) M[t] = 0.0;
+    __syncwarp();
+    {
+        const double Fn = vals[0] - vals[2] * s1 + vals[1] * s2;      // Ic = [[I, -hy, hx], [-hy, m, 0], [hx, 0, m]]
+        const double Fx = -vals[2] + vals[3] * s1, Fy = vals[1] + vals[3] * s2;
+        const int dj = lane + 2;
+        bool walking = lc.act && lane > 0;
+        if (walking) M[tri(dj, dj)] = Fn + s1 * Fx + s2 * Fy;
+        int cur = lc.parent;
+        for (int it = 0; it < md; ++it) {
+            double cry = shf(k.ry, cur), crx = shf(k.rx, cur);
+            int cpar = shfi(lc.parent, cur);
+            if (walking) {
+                if (cur > 0) {
+                    M[tri(dj, cur + 2)] = Fn + cry * Fx - crx * Fy;
+                    cur = cpar;
+                } else {
+                    M[tri(dj, 0)] = Fx; M[tri(dj, 1)] = Fy; M[tri(dj, 2)] = Fn;
+                    walking = false;
+                }
+            }
+        }
+        if (lane == 0) {
+            M[tri(0, 0)] = vals[3]; M[tri(1, 1)] = vals[3];
+            M[tri(2, 0)] = -vals[2]; M[tri(2, 1)] = vals[1]; M[tri(2, 2)] = vals[0];
+        }
+    }
+    __syncwarp();
+
+    // ---- ApplyFeedback (sim/DogController.cpp:903-945): COM velocity of the whole character
+    const int state = L.i(I_STATE);
+    {
+        double bvx = lc.mass * (k.vx - k.w * k.cy);
+        double comvx = warp_sum_all(bvx) / m.total_mass;
+        if (lane == 0) {
+            double cv = L.d(D_PARAMS + mCv);
+            int base = D_PARAMS + mMiscMax + state * spMax;
+            if (!((contact >> jToe) & 1)) L.d(D_PD_TARGET + jHip) = L.d(base + spHip) + comvx * cv;
+            if (!((contact >> jFinger) & 1)) L.d(D_PD_TARGET + jShoulder) = L.d(base + spShoulder) + comvx * cv;
+        }
+        __syncwarp();
+    }
+
+    // ---- cImpPDController::CalcControlForces (sim/ImpPDController.cpp:234-278)
+    double tau0 = 0.0, rhs_link = 0.0, kd_link = 0.0;
+    if (lc.act && lane > 0) {
+        double theta = e.q;
+        if (m.world_pd[lane]) {
+            // child body's world rotation, wrapped (cPDController::CalcTheta, sim/PDController.cpp:181-198)
+            double c = k.cw * m.body_cos[lane] - k.sw * m.body_sin[lane];
+            double s = k.sw * m.body_cos[lane] + k.cw * m.body_sin[lane];
+            double a = acos(fmin(1.0, fmax(-1.0, c)));
+            theta = (s >= 0) ? a : -a;
+        }
+        kd_link = m.kd[lane];
+        double perr = L.d(D_PD_TARGET + lane) - theta, verr = m.target_vel[lane] - e.qd;
+        tau0 = m.kp[lane] * (perr - h * e.qd) + kd_link * verr;
+        rhs_link = tau0 - Cj;
+    }
+    // dof-lane view: lane d holds row d of (M + h Kd) and rhs_d
+    double rhs = shf(rhs_link, lane >= 2 ? lane - 2 : 0);
+    double kdd = shf(kd_link, lane >= 2 ? lane - 2 : 0);
+    if (lane == 0) { rhs = -C0; kdd = 0.0; }
+    else if (lane == 1) { rhs = -C1; kdd = 0.0; }
+    else if (lane == 2) { rhs = -C2; kdd = 0.0; }
+    else if (lane >= nd) { rhs = 0.0; kdd = 0.0; }
+    double row[kMaxDof];
+#pragma unroll
+    for (int c = 0; c < kMaxDof; ++c) row[c] = (lane < nd && c <= lane) ? M[tri(lane < nd ? lane : 0, c <= lane ? c : 0)] : 0.0;
+    {
+        double dadd = h * kdd;
+#pragma unroll
+        for (int c = 0; c < kMaxDof; ++c) if (c == lane) row[c] += dadd;
+    }
+    // register-resident LDL^T: pivot broadcast by shuffle, trailing update predicated on lane >= column
+    double diag = 1.0;
+#pragma unroll
+    for (int j = 0; j < kMaxDof; ++j) {
+        double dj = shf(row[j], j);
+        double inv = 1.0 / dj;
+        if (lane == j) diag = dj;
+        double aij = row[j];              // A_ij before scaling (valid for lanes i > j)
+        double lij = aij * inv;
+#pragma unroll
+        for (int c = j + 1; c < kMaxDof; ++c) {
+            double akj = shf(aij, c);     // A_cj held by lane c
+            if (lane >= c) row[c] -= lij * akj;
+        }
+        if (lane > j) row[j] = lij;
+    }
+    // forward substitution L y = rhs, then D, then L^T x = y (L^T read back from shared memory)
+    double y = rhs;
+#pragma unroll
+    for (int c = 0; c < kMaxDof; ++c) {
+        double yc = shf(y, c);
+        if (lane > c) y -= row[c] * yc;
+    }
+    y /= diag;
+#pragma unroll
+    for (int c = 0; c < kMaxDof; ++c) if (lane < nd && c < lane) M[tri(lane, c)] = row[c];
+    __syncwarp();
+    double acc = y;
+    for (int c = nd - 1; c >= 1; --c) {
+        double xc = shf(acc, c);
+        if (lane < c) acc -= M[tri(c, lane)] * xc;
+    }
+    double tau = 0.0;
+    {
+        double acc_link = shf(acc, lane + 2 < kWarp ? lane + 2 : 0);
+        if (lc.act && lane > 0) tau = tau0 - kd_link * h * acc_link;
+    }
+
+    // ---- ApplyGravityCompensation (sim/DogController.cpp:947-995, 1120-1175)
+    const bool toe_c = (contact >> jToe) & 1, fin_c = (contact >> jFinger) & 1;
+    // foot bottom-centre positions (cDogController::GetEndEffectorContactPos), relative to O
+    double ex[2], ey[2];
+    {
+        double bc = k.cw * m.body_cos[lc.act ? lane : 0] - k.sw * m.body_sin[lc.act ? lane : 0];
+        double bs = k.sw * m.body_cos[lc.act ? lane : 0] + k.cw * m.body_sin[lc.act ? lane : 0];
+        double ly = -m.half_y[lc.act ? lane : 0];
+        double px = k.cx - bs * ly, py = k.cy + bc * ly;
+        ex[0] = shf(px, jToe); ey[0] = shf(py, jToe);
+        ex[1] = shf(px, jFinger); ey[1] = shf(py, jFinger);
+    }
+    if (m.grav_comp && (toe_c || fin_c)) {
+        // tau_g = -G,  G_k = (sum_subtree m (c - r_k)) x g   (generalised gravity force, sim/RBDUtil.cpp:850-895)
+        const double ms = vals[3], mhx = vals[1], mhy = vals[2];
+        double tg;
+        if (lane == 0) tg = 0.0;
+        else tg = -((mhx - ms * k.rx) * m.gy - (mhy - ms * k.ry) * m.gx);
+        const double ms0 = shf(ms, 0), mhx0 = shf(mhx, 0), mhy0 = shf(mhy, 0);
+        const double b0 = -(ms0 * m.gx), b1 = -(ms0 * m.gy), b2 = -(mhx0 * m.gy - mhy0 * m.gx);
+        // basis columns [toe +y, toe +x, finger +y, finger +x]; root rows = (Fx, Fy, r x F)
+        double Ar[3][4];
+#pragma unroll
+        for (int e2 = 0; e2 < 2; ++e2) {
+            bool on = e2 == 0 ? toe_c : fin_c;
+            Ar[0][2 * e2] = 0.0;            Ar[0][2 * e2 + 1] = on ? 1.0 : 0.0;
+            Ar[1][2 * e2] = on ? 1.0 : 0.0; Ar[1][2 * e2 + 1] = 0.0;
+            Ar[2][2 * e2] = on ? ex[e2] : 0.0; Ar[2][2 * e2 + 1] = on ? -ey[e2] : 0.0;
+        }
+        double A[4][5];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+#pragma unroll
+            for (int b = 0; b < 4; ++b) A[a][b] = Ar[0][a] * Ar[0][b] + Ar[1][a] * Ar[1][b] + Ar[2][a] * Ar[2][b];
+            A[a][a] += 0.0001;
+            A[a][4] = Ar[0][a] * b0 + Ar[1][a] * b1 + Ar[2][a] * b2;
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            int piv = c;
+#pragma unroll
+            for (int r = c + 1; r < 4; ++r) if (fabs(A[r][c]) > fabs(A[piv][c])) piv = r;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                if (r == piv && piv != c) {
+#pragma unroll
+                    for (int kk = 0; kk < 5; ++kk) { double t = A[c][kk]; A[c][kk] = A[r][kk]; A[r][kk] = t; }
+                }
+            }
+#pragma unroll
+            for (int r = c + 1; r < 4; ++r) {
+                double f = A[r][c] / A[c][c];
+#pragma unroll
+                for (int kk = c; kk < 5; ++kk) A[r][kk] -= f * A[c][kk];
+            }
+        }
+        double x[4];
+#pragma unroll
+        for (int r = 3; r >= 0; --r) {
+            double v = A[r][4];
+#pragma unroll
+            for (int kk = r + 1; kk < 4; ++kk) v -= A[r][kk] * x[kk];
+            x[r] = v / A[r][r];
+        }
+        if (lc.act && lane > 0) {
+            double tc = 0.0;
+            if (toe_c && ((m.anc_mask_toe >> lane) & 1)) { double rx = ex[0] - k.rx, ry = ey[0] - k.ry; tc += rx * x[0] - ry * x[1]; }
+            if (fin_c && ((m.anc_mask_finger >> lane) & 1)) { double rx = ex[1] - k.rx, ry = ey[1] - k.ry; tc += rx * x[2] - ry * x[3]; }
+            tau += tg - tc;
+        }
+    }
+
+    // ---- ApplyVirtualForces (sim/DogController.cpp:997-1029)
+    if (m.virt_forces && lc.act && lane > 0) {
+        if ((state == sBackStance || state == sExtend) && toe_c && ((m.vf_mask_toe >> lane) & 1)) {
+            double fx = -L.d(D_PARAMS + mBackForceX), fy = -L.d(D_PARAMS + mBackForceY);
+            tau += (ex[0] - k.rx) * fy - (ey[0] - k.ry) * fx;
+        }
+        if ((state == sFrontStance || state == sGather) && fin_c && ((m.vf_mask_finger >> lane) & 1)) {
+            double fx = -L.d(D_PARAMS + mFrontForceX), fy = -L.d(D_PARAMS + mFrontForceY);
+            tau += (ex[1] - k.rx) * fy - (ey[1] - k.ry) * fx;
+        }
+    }
+
+    // ---- cJoint::ApplyTorque clamp (sim/Joint.cpp:171-201,257-264)
+    if (lc.act && lane > 0) {
+        double lim = m.torque_lim[lane];
+        if (fabs(tau) > lim) tau *= lim / fabs(tau);
+    } else tau = 0.0;
+    (void)nj;
+    return tau;
 }
 
 // ================================================================================================ physics half
-// One sub-step of planar articulated-body forward dynamics with linearly-implicit contact / joint-limit terms.
-__device__ int physics_substep(Lane& L, const GroundView& g, double dt, bool write_contacts) {
-    double* sm = L.sm;
+// One sub-step of articulated-body forward dynamics with linearly-implicit contact / joint-limit terms.
+// Updates e (q, qd, root translation) in place and returns the contact bitmask (same value in every lane).
+__device__ int physics_substep(const LinkC& lc, EnvRegs& e, const GroundView& g, const double* s_clx, const double* s_cly,
+                               const int* s_cbody, int lane, double dt) {
     const ModelConst& m = c_model;
     const PhysParams& pp = m.phys;
-    const int nj = m.nj;
-    int contact = 0;
+    const int md = m.max_depth;
+    Kin k = kinematics(lc, e);
 
-    // pass 1: kinematics outward (link velocities in link coords, world frames, velocity-product terms, rigid
-    // inertias, bias forces incl. gravity as an external force)
+    // rigid inertia about O, bias force incl. gravity as an external force
+    const double hx = lc.mass * k.cx, hy = lc.mass * k.cy, Io = lc.izz_c + lc.mass * (k.cx * k.cx + k.cy * k.cy);
+    double ia[9];   // articulated inertia (a, bx, by, cxx, cxy, cyy) and bias force (n, fx, fy)
     {
-        double s, c;
-        sincos(SL(S_Q + 2), &s, &c);
-        SL(S_WC) = c; SL(S_WS) = s; SL(S_WX) = SL(S_Q); SL(S_WY) = SL(S_Q + 1);
-        double xd = SL(S_QD), yd = SL(S_QD + 1);
-        SL(P_V) = SL(S_QD + 2); SL(P_V + 1) = c * xd + s * yd; SL(P_V + 2) = -s * xd + c * yd;
+        double hlx = -hy * k.w + lc.mass * k.vx, hly = hx * k.w + lc.mass * k.vy;
+        ia[0] = Io; ia[1] = -hy; ia[2] = hx; ia[3] = lc.mass; ia[4] = 0.0; ia[5] = lc.mass;
+        ia[6] = (k.vx * hly - k.vy * hlx) - (hx * m.gy - hy * m.gx);
+        ia[7] = -k.w * hly - lc.mass * m.gx;
+        ia[8] = k.w * hlx - lc.mass * m.gy;
+        if (!lc.act) { ia[6] = ia[7] = ia[8] = 0.0; }
     }
-    for (int j = 1; j < nj; ++j) {
-        int p = m.parent[j], o = m.dof[j];
-        double s, c;
-        sincos(SL(S_Q + o), &s, &c);
-        SL(S_JC + j) = c; SL(S_JS + j) = s;
-        double pc = SL(S_WC + p), ps = SL(S_WS + p);
-        double ax = m.attach_x[j], ay = m.attach_y[j];
-        SL(S_WC + j) = pc * c - ps * s;
-        SL(S_WS + j) = ps * c + pc * s;
-        SL(S_WX + j) = SL(S_WX + p) + pc * ax - ps * ay;
-        SL(S_WY + j) = SL(S_WY + p) + ps * ax + pc * ay;
-        double qd = SL(S_QD + o);
-        double pw = SL(P_V + 3 * p), pvx = SL(P_V + 3 * p + 1) - pw * ay, pvy = SL(P_V + 3 * p + 2) + pw * ax;
-        double vx = c * pvx + s * pvy, vy = -s * pvx + c * pvy;
-        SL(P_V + 3 * j) = pw + qd; SL(P_V + 3 * j + 1) = vx; SL(P_V + 3 * j + 2) = vy;
-        SL(P_CV + 2 * j) = vy * qd; SL(P_CV + 2 * j + 1) = -vx * qd;
-    }
-    for (int j = 0; j < nj; ++j) {
-        double mj = m.mass[j], hx = mj * m.body_ax[j], hy = mj * m.body_ay[j], Iz = m.izz_o[j];
-        SL(P_IA + 6 * j) = Iz; SL(P_IA + 6 * j + 1) = -hy; SL(P_IA + 6 * j + 2) = hx;
-        SL(P_IA + 6 * j + 3) = mj; SL(P_IA + 6 * j + 4) = 0.0; SL(P_IA + 6 * j + 5) = mj;
-        double w = SL(P_V + 3 * j), vx = SL(P_V + 3 * j + 1), vy = SL(P_V + 3 * j + 2);
-        double hpx = mj * vx - hy * w, hpy = mj * vy + hx * w;
-        // gravity in link coords
-        double wc = SL(S_WC + j), ws = SL(S_WS + j);
-        double glx = wc * m.gx + ws * m.gy, gly = -ws * m.gx + wc * m.gy;
-        SL(P_PA + 3 * j) = (vx * hpy - vy * hpx) - (hx * gly - hy * glx);
-        SL(P_PA + 3 * j + 1) = -w * hpy - mj * glx;
-        SL(P_PA + 3 * j + 2) = w * hpx - mj * gly;
-    }
+    const double cvx = e.qd * (k.w * k.rx + k.vy), cvy = e.qd * (k.w * k.ry - k.vx);   // c_j = v_j x (S_j qd_j)
 
-    // contacts: box corners against the height field
-    for (int j = 0; j < nj; ++j) {
-        if (!m.collidable[j]) continue;
-        double wc = SL(S_WC + j), ws = SL(S_WS + j), wx = SL(S_WX + j), wy = SL(S_WY + j);
-        double w = SL(P_V + 3 * j), vx = SL(P_V + 3 * j + 1), vy = SL(P_V + 3 * j + 2);
-        double bc = m.body_cos[j], bs = m.body_sin[j], hx = m.half_x[j], hy = m.half_y[j];
-#pragma unroll 1
-        for (int cn = 0; cn < 4; ++cn) {
-            double bx = (cn & 1) ? hx : -hx, by = (cn & 2) ? hy : -hy;
-            double lx = m.body_ax[j] + bc * bx - bs * by, ly = m.body_ay[j] + bs * bx + bc * by;   // link coords
-            double px = wx + wc * lx - ws * ly, py = wy + ws * lx + wc * ly;
+    // ---- contacts: one box corner per lane per round against the height field
+    int contact = 0;
+    const int nc = m.n_corners;
+    for (int base = 0; base < nc; base += kWarp) {
+        const int ci = base + lane;
+        const bool valid = ci < nc;
+        const int b = valid ? s_cbody[ci] : 0;
+        const double lx = valid ? s_clx[ci] : 0.0, ly = valid ? s_cly[ci] : 0.0;
+        const double bcw = shf(k.cw, b), bsw = shf(k.sw, b), brx = shf(k.rx, b), bry = shf(k.ry, b);
+        const double bw = shf(k.w, b), bvx = shf(k.vx, b), bvy = shf(k.vy, b);
+        double add[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        bool touching = false;
+        if (valid) {
+            const double rpx = brx + bcw * lx - bsw * ly, rpy = bry + bsw * lx + bcw * ly;   // corner rel. O
             double slope;
-            double hgt = g.sample(px, &slope);
-            double inv = rsqrt(1.0 + slope * slope);
-            double pen = (hgt - py) * inv;
-            if (pen <= -pp.contact_tol) continue;
-            contact |= (1 << j);
-            if (pen <= 0.0) continue;
-            // world normal / tangent -> link coords
-            double nxw = -slope * inv, nyw = inv;
-            double nx = wc * nxw + ws * nyw, ny = -ws * nxw + wc * nyw;   // n_l = R_w^T n_w
-            double tx = ny, ty = -nx;                                       // t_w = (inv, slope inv) -> R^T t_w = (ny, -nx)
-            double pvx = vx - w * ly, pvy = vy + w * lx;                    // point velocity, link coords
-            double vn = pvx * nx + pvy * ny, vt = pvx * tx + pvy * ty;
-            double fn0 = pp.kn * pen - pp.dn * vn;
-            if (fn0 <= 0.0) continue;
-            double cnn = pp.dn + dt * pp.kn;
-            double ctt = pp.mu * fn0 / fmax(fabs(vt), pp.v_eps);
-            double fwx = pp.kn * pen * nx - cnn * vn * nx - ctt * vt * tx;
-            double fwy = pp.kn * pen * ny - cnn * vn * ny - ctt * vt * ty;
-            SL(P_PA + 3 * j) -= lx * fwy - ly * fwx;
-            SL(P_PA + 3 * j + 1) -= fwx;
-            SL(P_PA + 3 * j + 2) -= fwy;
-            double dxx = dt * (cnn * nx * nx + ctt * tx * tx), dxy = dt * (cnn * nx * ny + ctt * tx * ty),
-                   dyy = dt * (cnn * ny * ny + ctt * ty * ty);
-            double kx = -ly, ky = lx;
-            double dkx = dxx * kx + dxy * ky, dky = dxy * kx + dyy * ky;
-            SL(P_IA + 6 * j) += kx * dkx + ky * dky;
-            SL(P_IA + 6 * j + 1) += dkx; SL(P_IA + 6 * j + 2) += dky;
-            SL(P_IA + 6 * j + 3) += dxx; SL(P_IA + 6 * j + 4) += dxy; SL(P_IA + 6 * j + 5) += dyy;
-        }
-    }
-
-    // pass 2: articulated inertias / bias forces inward
-    for (int j = nj - 1; j >= 1; --j) {
-        int p = m.parent[j], o = m.dof[j];
-        double a = SL(P_IA + 6 * j), bx = SL(P_IA + 6 * j + 1), by = SL(P_IA + 6 * j + 2);
-        double cxx = SL(P_IA + 6 * j + 3), cxy = SL(P_IA + 6 * j + 4), cyy = SL(P_IA + 6 * j + 5);
-        double pn = SL(P_PA + 3 * j), pfx = SL(P_PA + 3 * j + 1), pfy = SL(P_PA + 3 * j + 2);
-        double Dj = a, u = SL(S_TAU + o) - pn;
-        if (m.has_limit[j]) {
-            double q = SL(S_Q + o), viol = 0.0;
-            if (q > m.lim_hi[j]) viol = q - m.lim_hi[j];
-            else if (q < m.lim_lo[j]) viol = q - m.lim_lo[j];
-            if (viol != 0.0) {
-                double cl = pp.d_lim + dt * pp.k_lim;
-                u += -pp.k_lim * viol - cl * SL(S_QD + o);
-                Dj += dt * cl;
+            const double hgt = g.sample(e.ox + rpx, &slope);
+            const double inv = rsqrt(1.0 + slope * slope);
+            const double pen = (hgt - (e.oy + rpy)) * inv;
+            if (pen > -pp.contact_tol) {
+                touching = true;
+                if (pen > 0.0) {
+                    const double nx = -slope * inv, ny = inv, tx = inv, ty = slope * inv;
+                    const double pvx = bvx - bw * rpy, pvy = bvy + bw * rpx;
+                    const double vn = pvx * nx + pvy * ny, vt = pvx * tx + pvy * ty;
+                    const double fn0 = pp.kn * pen - pp.dn * vn;
+                    if (fn0 > 0.0) {
+                        const double cnn = pp.dn + dt * pp.kn;
+                        const double ctt = pp.mu * fn0 / fmax(fabs(vt), pp.v_eps);
+                        const double fwx = pp.kn * pen * nx - cnn * vn * nx - ctt * vt * tx;
+                        const double fwy = pp.kn * pen * ny - cnn * vn * ny - ctt * vt * ty;
+                        const double dxx = dt * (cnn * nx * nx + ctt * tx * tx), dxy = dt * (cnn * nx * ny + ctt * tx * ty),
+                                     dyy = dt * (cnn * ny * ny + ctt * ty * ty);
+                        const double kx = -rpy, ky = rpx;
+                        const double dkx = dxx * kx + dxy * ky, dky = dxy * kx + dyy * ky;
+                        add[0] = kx * dkx + ky * dky; add[1] = dkx; add[2] = dky; add[3] = dxx; add[4] = dxy; add[5] = dyy;
+                        add[6] = -(rpx * fwy - rpy * fwx); add[7] = -fwx; add[8] = -fwy;
+                    }
+                }
             }
         }
-        double dinv = 1.0 / Dj;
-        SL(P_U + 3 * j) = a; SL(P_U + 3 * j + 1) = bx; SL(P_U + 3 * j + 2) = by;
-        SL(P_DINV + j) = dinv; SL(P_UU + j) = u;
-        // Ia = IA - U U^T / D
-        double ia = a - a * a * dinv, ibx = bx - a * bx * dinv, iby = by - a * by * dinv;
-        double icxx = cxx - bx * bx * dinv, icxy = cxy - bx * by * dinv, icyy = cyy - by * by * dinv;
-        // pa = pA + Ia c + U u / D,  c = (0, cvx, cvy)
-        double cvx = SL(P_CV + 2 * j), cvy = SL(P_CV + 2 * j + 1), ud = u * dinv;
-        double qn = pn + ibx * cvx + iby * cvy + a * ud;
-        double qx = pfx + icxx * cvx + icxy * cvy + bx * ud;
-        double qy = pfy + icxy * cvx + icyy * cvy + by * ud;
-        // rotate into parent axes
-        double c = SL(S_JC + j), s = SL(S_JS + j);
-        double rbx = c * ibx - s * iby, rby = s * ibx + c * iby;
-        double t1 = c * icxx - s * icxy, t2 = c * icxy - s * icyy, t3 = s * icxx + c * icxy, t4 = s * icxy + c * icyy;
-        double rxx = t1 * c - t2 * s, rxy = t1 * s + t2 * c, ryy = t3 * s + t4 * c;
-        double rfx = c * qx - s * qy, rfy = s * qx + c * qy;
-        // shift by k = (-ay, ax)
-        double kx = -m.attach_y[j], ky = m.attach_x[j];
-        double ckx = rxx * kx + rxy * ky, cky = rxy * kx + ryy * ky;
-        SL(P_IA + 6 * p) += ia + 2.0 * (kx * rbx + ky * rby) + kx * ckx + ky * cky;
-        SL(P_IA + 6 * p + 1) += rbx + ckx; SL(P_IA + 6 * p + 2) += rby + cky;
-        SL(P_IA + 6 * p + 3) += rxx; SL(P_IA + 6 * p + 4) += rxy; SL(P_IA + 6 * p + 5) += ryy;
-        SL(P_PA + 3 * p) += qn + kx * rfx + ky * rfy;
-        SL(P_PA + 3 * p + 1) += rfx; SL(P_PA + 3 * p + 2) += rfy;
+        // the 4 corners of a body sit in 4 consecutive lanes: segmented sum, then the owning link lane fetches it
+        const unsigned tmask = __ballot_sync(kFull, touching);
+#pragma unroll
+        for (int v = 0; v < 9; ++v) {
+            add[v] += __shfl_xor_sync(kFull, add[v], 1);
+            add[v] += __shfl_xor_sync(kFull, add[v], 2);
+        }
+        const int cb = lc.act ? m.corner_base[lane] : -1;
+        const bool mine = cb >= base && cb < base + kWarp;
+        const int src = mine ? cb - base : 0;
+#pragma unroll
+        for (int v = 0; v < 9; ++v) {
+            double t = shf(add[v], src);
+            if (mine) ia[v] += t;
+        }
+        if (mine && ((tmask >> src) & 0xfu)) contact |= 1 << lane;
     }
+    // combine the per-lane contact bits into one mask
+    contact = (int)__ballot_sync(kFull, contact != 0);   // lane index == link index
 
-    // floating base: solve IA_0 a_0 = -pA_0 (symmetric 3x3)
+    // ---- pass 2: articulated inertias / bias forces inward (level-synchronous)
+    const double s1 = k.ry, s2 = -k.rx;
+    double U0 = 0.0, U1 = 0.0, U2 = 0.0, dinv = 0.0, uu = 0.0;
+    for (int l = md; l >= 1; --l) {
+        if (lc.depth == l) {
+            U0 = ia[0] + ia[1] * s1 + ia[2] * s2;
+            U1 = ia[1] + ia[3] * s1 + ia[4] * s2;
+            U2 = ia[2] + ia[4] * s1 + ia[5] * s2;
+            double Dj = U0 + s1 * U1 + s2 * U2;
+            uu = e.tau - (ia[6] + s1 * ia[7] + s2 * ia[8]);
+            if (lc.has_lim) {
+                double viol = 0.0;
+                if (e.q > lc.lim_hi) viol = e.q - lc.lim_hi;
+                else if (e.q < lc.lim_lo) viol = e.q - lc.lim_lo;
+                if (viol != 0.0) {
+                    double cl = pp.d_lim + dt * pp.k_lim;
+                    uu += -pp.k_lim * viol - cl * e.qd;
+                    Dj += dt * cl;
+                }
+            }
+            dinv = 1.0 / Dj;
+            // Ia = IA - U U^T / D ;  pa = pA + Ia c + U u / D
+            double n0 = ia[0] - U0 * U0 * dinv, n1 = ia[1] - U0 * U1 * dinv, n2 = ia[2] - U0 * U2 * dinv;
+            double n3 = ia[3] - U1 * U1 * dinv, n4 = ia[4] - U1 * U2 * dinv, n5 = ia[5] - U2 * U2 * dinv;
+            double ud = uu * dinv;
+            ia[6] += n1 * cvx + n2 * cvy + U0 * ud;
+            ia[7] += n3 * cvx + n4 * cvy + U1 * ud;
+            ia[8] += n4 * cvx + n5 * cvy + U2 * ud;
+            ia[0] = n0; ia[1] = n1; ia[2] = n2; ia[3] = n3; ia[4] = n4; ia[5] = n5;
+        }
+        TRL_ACCUM_LEVEL(l, 9, ia);
+    }
+    // floating base: solve IA_0 a_0 = -pA_0 (symmetric 3x3 LDL^T); every lane computes it from lane 0's values
+    double a0, a1, a2;
     {
-        double a = SL(P_IA), bx = SL(P_IA + 1), by = SL(P_IA + 2), cxx = SL(P_IA + 3), cxy = SL(P_IA + 4), cyy = SL(P_IA + 5);
-        double r0 = -SL(P_PA), r1 = -SL(P_PA + 1), r2 = -SL(P_PA + 2);
-        // LDL^T
+        double a = shf(ia[0], 0), bx = shf(ia[1], 0), by = shf(ia[2], 0), cxx = shf(ia[3], 0), cxy = shf(ia[4], 0), cyy = shf(ia[5], 0);
+        double r0 = -shf(ia[6], 0), r1 = -shf(ia[7], 0), r2 = -shf(ia[8], 0);
         double d0 = a, l10 = bx / d0, l20 = by / d0;
         double d1 = cxx - l10 * l10 * d0, l21 = (cxy - l20 * l10 * d0) / d1;
         double d2 = cyy - l20 * l20 * d0 - l21 * l21 * d1;
         double y0 = r0, y1 = r1 - l10 * y0, y2 = r2 - l20 * y0 - l21 * y1;
-        double z2 = y2 / d2, z1 = y1 / d1 - l21 * z2, z0 = y0 / d0 - l10 * z1 - l20 * z2;
-        SL(P_A) = z0; SL(P_A + 1) = z1; SL(P_A + 2) = z2;
+        a2 = y2 / d2; a1 = y1 / d1 - l21 * a2; a0 = y0 / d0 - l10 * a1 - l20 * a2;
     }
-    // pass 3: accelerations outward, integrate (semi-implicit Euler)
-    for (int j = 1; j < nj; ++j) {
-        int p = m.parent[j], o = m.dof[j];
-        double c = SL(S_JC + j), s = SL(S_JS + j), ax = m.attach_x[j], ay = m.attach_y[j];
-        double pa = SL(P_A + 3 * p), pax = SL(P_A + 3 * p + 1) - pa * ay, pay = SL(P_A + 3 * p + 2) + pa * ax;
-        double aw = pa, alx = c * pax + s * pay + SL(P_CV + 2 * j), aly = -s * pax + c * pay + SL(P_CV + 2 * j + 1);
-        double qdd = (SL(P_UU + j) - (SL(P_U + 3 * j) * aw + SL(P_U + 3 * j + 1) * alx + SL(P_U + 3 * j + 2) * aly)) * SL(P_DINV + j);
-        SL(P_A + 3 * j) = aw + qdd; SL(P_A + 3 * j + 1) = alx; SL(P_A + 3 * j + 2) = aly;
-        double qd = SL(S_QD + o) + dt * qdd;
-        SL(S_QD + o) = qd;
-        SL(S_Q + o) += dt * qd;
+    // pass 3: accelerations outward; each link lane integrates its own joint (semi-implicit Euler)
+    double aw = a0, alx = a1, aly = a2;
+    const double thd0 = shf(e.qd, 0);
+    for (int l = 1; l <= md; ++l) {
+        double paw = shf(aw, lc.parent), pax = shf(alx, lc.parent), pay = shf(aly, lc.parent);
+        if (lc.depth == l) {
+            double bx = pax + cvx, by = pay + cvy;
+            double qdd = (uu - (U0 * paw + U1 * bx + U2 * by)) * dinv;
+            aw = paw + qdd; alx = bx + s1 * qdd; aly = by + s2 * qdd;
+            e.qd += dt * qdd;
+            e.q += dt * e.qd;
+        }
     }
     {
-        // root: classical acceleration of the origin in world axes = R (a_lin + w x v_lin)
-        double c = SL(S_WC), s = SL(S_WS);
-        double w = SL(P_V), vx = SL(P_V + 1), vy = SL(P_V + 2);
-        double alx = SL(P_A + 1) - w * vy, aly = SL(P_A + 2) + w * vx;
-        double xdd = c * alx - s * aly, ydd = s * alx + c * aly, thdd = SL(P_A);
-        double xd = SL(S_QD) + dt * xdd, yd = SL(S_QD + 1) + dt * ydd, thd = SL(S_QD + 2) + dt * thdd;
-        SL(S_QD) = xd; SL(S_QD + 1) = yd; SL(S_QD + 2) = thd;
-        SL(S_Q) += dt * xd; SL(S_Q + 1) += dt * yd; SL(S_Q + 2) += dt * thd;
+        // root: classical acceleration of the origin = spatial acceleration + w x v
+        double xdd = a1 - thd0 * e.oyd, ydd = a2 + thd0 * e.oxd;
+        e.oxd += dt * xdd; e.oyd += dt * ydd;
+        e.ox += dt * e.oxd; e.oy += dt * e.oyd;
+        if (lane == 0) { e.qd += dt * a0; e.q += dt * e.qd; }
     }
     return contact;
 }
 
-// cTerrainRLCharController::ParseGround + BuildPoliState (sim/TerrainRLCharController.cpp:168-285)
-__device__ void build_poli_state(Lane& L, const Buffers& B, const GroundView& g) {
-    double* sm = L.sm;
+// cTerrainRLCharController::ParseGround + BuildPoliState (sim/TerrainRLCharController.cpp:168-285), cooperative
+__device__ void build_poli_state(const LinkC& lc, const EnvRegs& e, const Kin& k, const Buffers& B, const GroundView& g, int env,
+                                 int lane) {
     const ModelConst& m = c_model;
-    double* out = B.poli_state + (size_t)L.env * B.S;
-    double ox = SL(S_Q), oy = g.sample(SL(S_Q));
-    for (int i = 0; i < kNumGroundSamples; ++i) {
+    double* out = B.poli_state + (size_t)env * B.S;
+    const double oy = g.sample(e.ox);
+    for (int i = lane; i < kNumGroundSamples; i += kWarp) {
         double dist = ((10.0 - (-0.5)) * i) / (kNumGroundSamples - 1) + (-0.5);
-        out[i] = g.sample(dist + ox) - oy;
+        out[i] = g.sample(dist + e.ox) - oy;
     }
-    int idx = kNumGroundSamples;
-    out[idx++] = SL(S_Q + 1) - oy;
-    for (int j = 1; j < m.nj; ++j) {
-        double px, py, vx, vy;
-        body_kin(sm, j, px, py, vx, vy);
-        out[idx++] = px - SL(S_Q); out[idx++] = py - SL(S_Q + 1);
+    if (lane == 0) out[kNumGroundSamples] = e.oy - oy;
+    if (lc.act) {
+        if (lane > 0) {
+            out[kNumGroundSamples + 1 + 2 * (lane - 1)] = k.cx;       // body COM relative to the root joint position
+            out[kNumGroundSamples + 1 + 2 * (lane - 1) + 1] = k.cy;
+        }
+        int vo = kNumGroundSamples + 2 * m.nj - 1;
+        out[vo + 2 * lane] = k.vx - k.w * k.cy;                       // body COM velocity
+        out[vo + 2 * lane + 1] = k.vy + k.w * k.cx;
     }
-    for (int j = 0; j < m.nj; ++j) {
-        double px, py, vx, vy;
-        body_kin(sm, j, px, py, vx, vy);
-        out[idx++] = vx; out[idx++] = vy;
+}
+
+// cScenarioSimChar::Reset (+ PoliEval / Exp specifics): scenarios/ScenarioSimChar.cpp:121-132.  Cooperative kinematics,
+// scalar bookkeeping + terrain generation on lane 0.
+__device__ void reset_env(Lane& L, const LinkC& lc, EnvRegs& e, const Buffers& B, int lane) {
+    const ModelConst& m = c_model;
+    e.q = lc.act ? m.pose0[lane == 0 ? 2 : lane + 2] : 0.0;
+    e.qd = lc.act ? m.vel0[lane == 0 ? 2 : lane + 2] : 0.0;
+    e.ox = m.pose0[0]; e.oy = m.pose0[1]; e.oxd = m.vel0[0]; e.oyd = m.vel0[1];
+    e.tau = 0.0;
+    Kin k = kinematics(lc, e);
+    double comx = e.ox + warp_sum_all(lc.mass * k.cx) / m.total_mass;
+    double comy = e.oy + warp_sum_all(lc.mass * k.cy) / m.total_mass;
+    double newx = e.ox, newy = e.oy;
+    if (lane == 0) {
+        L.i(I_CONTACT) = 0;
+        CounterRng rng = load_rng(L);
+        // controller reset: default action, FSM state 0, counters zeroed (sim/TerrainRLCharController.cpp:47-58,
+        // sim/DogController.cpp:210-216,640-650)
+        double params[kNumParams];
+        int id = build_base_action(L, rng, m.default_action, params);
+        apply_action(L, id, params, comx, comy);
+        L.i(I_EXP_FLAGS) = 0;
+        L.i(I_FIRST_CYCLE) = 1;
+        L.d(D_PREV_CYCLE_T) = 0.0; L.d(D_CUR_CYCLE_T) = 0.0; L.d(D_PREV_STUMBLE) = 0.0; L.d(D_CUR_STUMBLE) = 0.0;
+        L.d(D_PREV_DIST_X) = 0.0; L.d(D_PREV_DIST_Y) = 0.0;
+        L.d(D_PREV_COM_X) = comx; L.d(D_PREV_COM_Y) = comy;
+        L.i(I_CMD) = -1;
+        L.i(I_PENDING) = 0;
+        // cSimCharSoftFall::Reset
+        L.d(D_FALL_DIST_CNT) = 5.0; L.d(D_PREV_CHECK_X) = e.ox; L.d(D_PREV_CHECK_Y) = e.oy;
+        L.i(I_FAIL_FALL_DIST) = 0; L.d(D_FALL_CONTACT_CNT) = 0.1; L.d(D_SUM_FALL) = 0.0;
+        // ResetGround + InitCharacterPos
+        GroundView g = load_ground(L, B);
+        g.n[0] = g.n[1] = 0; g.flip = 0;
+        g.update(-11.0, 9.0, m.terrain_type, m.terrain_params, 20.0);
+        if (m.has_init_x) newx = m.init_x;
+        newy = e.oy + g.sample(newx);
+        store_ground(L, g);
+        if (m.exp_mode) {
+            L.i(I_CYCLE_COUNT) = 0;
+            L.i(I_CMD) = rng.rand_int(0, m.n_actions);   // cScenarioExp::CommandRandAction
+        } else {
+            L.d(D_POS_START_X) = newx;
+        }
+        store_rng(L, rng);
+    }
+    __syncwarp();
+    e.ox = shf(newx, 0); e.oy = shf(newy, 0);
+}
+
+__device__ __forceinline__ void load_env(Lane& L, const LinkC& lc, EnvRegs& e, int lane) {
+    const int dq = (lane == 0) ? 2 : lane + 2;
+    e.q = lc.act ? L.d(D_Q + dq) : 0.0;
+    e.qd = lc.act ? L.d(D_QD + dq) : 0.0;
+    e.tau = (lc.act && lane > 0) ? L.d(D_TAU + dq) : 0.0;
+    e.ox = L.d(D_Q); e.oy = L.d(D_Q + 1); e.oxd = L.d(D_QD); e.oyd = L.d(D_QD + 1);
+}
+__device__ __forceinline__ void store_env(Lane& L, const LinkC& lc, const EnvRegs& e, int lane) {
+    const int dq = (lane == 0) ? 2 : lane + 2;
+    if (lc.act) { L.d(D_Q + dq) = e.q; L.d(D_QD + dq) = e.qd; L.d(D_TAU + dq) = (lane > 0) ? e.tau : 0.0; }
+    if (lane == 0) {
+        L.d(D_Q) = e.ox; L.d(D_Q + 1) = e.oy; L.d(D_QD) = e.oxd; L.d(D_QD + 1) = e.oyd;
+        L.d(D_TAU) = 0.0; L.d(D_TAU + 1) = 0.0;
     }
 }
 
 // ================================================================================================ the kernel
 // flags: bit0 do_ctrl (finish env-step k), bit1 do_phys (start env-step k+1), bit2 end of outer update
-__global__ void __launch_bounds__(kWarp, 1)
+__global__ void __launch_bounds__(kBlockThreads)
 trl_step_kernel(Buffers B, double h, int flags) {
-    extern __shared__ double smem[];
-    const int lane = threadIdx.x;
-    const int env = blockIdx.x * kWarp + lane;
-    if (env >= B.n) return;
-    Lane L{smem + lane, env, B.n, B.d, B.i};
-    double* sm = L.sm;
+    __shared__ double s_clx[4 * kMaxJoints], s_cly[4 * kMaxJoints];
+    __shared__ int s_cbody[4 * kMaxJoints];
+    __shared__ double s_x[kWarpsPerBlock * X_END];
     const ModelConst& m = c_model;
-    const int nd = m.ndof;
-
-    for (int k = 0; k < nd; ++k) { SL(S_Q + k) = L.d(D_Q + k); SL(S_QD + k) = L.d(D_QD + k); SL(S_TAU + k) = L.d(D_TAU + k); }
+    for (int t = threadIdx.x; t < m.n_corners; t += kBlockThreads) {
+        s_clx[t] = m.corner_lx[t]; s_cly[t] = m.corner_ly[t]; s_cbody[t] = m.corner_body[t];
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int env = blockIdx.x * kWarpsPerBlock + warp;
+    if (env >= B.n) return;
+    Lane L{nullptr, env, B.n, B.d, B.i};
+    double* xs = s_x + warp * X_END;
+    const LinkC lc = load_link(lane);
+    EnvRegs e;
+    load_env(L, lc, e, lane);
     int contact = L.i(I_CONTACT);
 
     if (flags & 1) {
         // ---------------- controller half of env-step k
-        fk_world(L);
-        controller_torque(L, h, contact);
-        // fall checks (sim/SimCharSoftFall.cpp:74-125)
-        double cnt = L.d(D_FALL_DIST_CNT) - h;
-        if (cnt <= 0.0) {
-            double dx = SL(S_Q) - L.d(D_PREV_CHECK_X), dy = SL(S_Q + 1) - L.d(D_PREV_CHECK_Y);
-            if (dx * dx + dy * dy < 0.25) L.i(I_FAIL_FALL_DIST) = 1;
-            L.d(D_PREV_CHECK_X) = SL(S_Q); L.d(D_PREV_CHECK_Y) = SL(S_Q + 1);
-            cnt = 5.0;
+        Kin k = kinematics(lc, e);
+        e.tau = controller_torque(L, lc, e, k, xs, lane, h, contact);
+        if (lane == 0) {
+            // fall checks (sim/SimCharSoftFall.cpp:74-125)
+            double cnt = L.d(D_FALL_DIST_CNT) - h;
+            if (cnt <= 0.0) {
+                double dx = e.ox - L.d(D_PREV_CHECK_X), dy = e.oy - L.d(D_PREV_CHECK_Y);
+                if (dx * dx + dy * dy < 0.25) L.i(I_FAIL_FALL_DIST) = 1;
+                L.d(D_PREV_CHECK_X) = e.ox; L.d(D_PREV_CHECK_Y) = e.oy;
+                cnt = 5.0;
+            }
+            L.d(D_FALL_DIST_CNT) = cnt;
+            double cc = L.d(D_FALL_CONTACT_CNT) - h;
+            if (cc <= 0.0) {
+                const int fall_mask = (1 << jRoot) | (1 << jSpine0) | (1 << jSpine1) | (1 << jSpine2) | (1 << jSpine3) |
+                                      (1 << jTorso) | (1 << jNeck0) | (1 << jNeck1) | (1 << jHead);
+                double val = (contact & fall_mask) ? 1.0 : 0.0;
+                const double norm = (1.0 + 1.0 / (1.0 - 0.9));
+                L.d(D_SUM_FALL) = val / norm + 0.9 * L.d(D_SUM_FALL);
+                cc = 0.1;
+            }
+            L.d(D_FALL_CONTACT_CNT) = cc;
+            unsigned lo = (unsigned)L.i(I_STEPS_LO) + 1u;
+            L.i(I_STEPS_LO) = (int)lo;
+            if (lo == 0u) L.i(I_STEPS_HI) += 1;
         }
-        L.d(D_FALL_DIST_CNT) = cnt;
-        double cc = L.d(D_FALL_CONTACT_CNT) - h;
-        if (cc <= 0.0) {
-            const int fall_mask = (1 << jRoot) | (1 << jSpine0) | (1 << jSpine1) | (1 << jSpine2) | (1 << jSpine3) |
-                                  (1 << jTorso) | (1 << jNeck0) | (1 << jNeck1) | (1 << jHead);
-            double val = (contact & fall_mask) ? 1.0 : 0.0;
-            const double norm = (1.0 + 1.0 / (1.0 - 0.9));
-            L.d(D_SUM_FALL) = val / norm + 0.9 * L.d(D_SUM_FALL);
-            cc = 0.1;
-        }
-        L.d(D_FALL_CONTACT_CNT) = cc;
+        __syncwarp();
         // PostSubstepUpdate: cycle boundary bookkeeping
-        if (L.i(I_STATE) == 0 && L.d(D_PHASE) == 0.0) {
-            if (m.exp_mode) exp_new_cycle_update(L, B, has_fallen(L, SL(S_Q + 2)));
-            else L.i(I_CYCLE_COUNT) += 1;
+        int nc = 0, fl = 0;
+        if (lane == 0) { nc = (L.i(I_STATE) == 0 && L.d(D_PHASE) == 0.0) ? 1 : 0; fl = has_fallen(L, e.q) ? 1 : 0; }
+        nc = shfi(nc, 0); fl = shfi(fl, 0);
+        if (nc) {
+            if (m.exp_mode) exp_new_cycle_update(L, B, fl != 0, lane);
+            else if (lane == 0) L.i(I_CYCLE_COUNT) += 1;
         }
-        unsigned lo = (unsigned)L.i(I_STEPS_LO) + 1u;
-        L.i(I_STEPS_LO) = (int)lo;
-        if (lo == 0u) L.i(I_STEPS_HI) += 1;
     }
 
     if (flags & 4) {
         // ---------------- end of the outer update: fall -> episode bookkeeping + reset
-        bool fallen = has_fallen(L, SL(S_Q + 2));
-        bool new_cycle = (L.i(I_STATE) == 0 && L.d(D_PHASE) == 0.0);
+        int fallen = 0, new_cycle = 0;
+        if (lane == 0) { fallen = has_fallen(L, e.q) ? 1 : 0; new_cycle = (L.i(I_STATE) == 0 && L.d(D_PHASE) == 0.0) ? 1 : 0; }
+        fallen = shfi(fallen, 0); new_cycle = shfi(new_cycle, 0);
+        bool do_reset = false;
         if (m.exp_mode) {
-            if (!new_cycle && fallen) { exp_new_cycle_update(L, B, true); reset_env(L, B); }
+            if (!new_cycle && fallen) { exp_new_cycle_update(L, B, true, lane); do_reset = true; }
         } else if (fallen) {
-            if (L.i(I_CYCLE_COUNT) >= 1) {
-                double dist = SL(S_Q) - L.d(D_POS_START_X);
+            if (lane == 0 && L.i(I_CYCLE_COUNT) >= 1) {
+                double dist = e.ox - L.d(D_POS_START_X);
                 int ec = L.i(I_EPISODE_COUNT);
                 L.d(D_AVG_DIST) = (ec * L.d(D_AVG_DIST) + dist) / (ec + 1.0);
                 L.i(I_EPISODE_COUNT) = ec + 1;
                 int slot = atomicAdd(B.dist_count, 1);
                 if (slot < B.dist_cap) { B.dist_log[slot] = dist; B.dist_env[slot] = env; }
             }
-            reset_env(L, B);
+            do_reset = true;
         }
-        contact = L.i(I_CONTACT);
+        if (do_reset) { reset_env(L, lc, e, B, lane); contact = 0; }
     }
 
     if (flags & 2) {
@@ -929,62 +891,68 @@ trl_step_kernel(Buffers B, double h, int flags) {
         GroundView g = load_ground(L, B);
         const int ns = m.num_sim_substeps;
         const double dt = h / ns;
-        for (int s = 0; s < ns; ++s) {
-            int cmask = physics_substep(L, g, dt, s == ns - 1);
-            if (s == ns - 1) contact = cmask;
+        for (int s = 0; s < ns; ++s) contact = physics_substep(lc, e, g, s_clx, s_cly, s_cbody, lane, dt);
+        // UpdateGround (scenarios/ScenarioSimChar.cpp:564-572): regenerate a segment when the view window crosses it
+        {
+            int smin = g.seg_id(0), smax = g.seg_id(1);
+            double bmin = e.ox - 2.0, bmax = e.ox + 10.0 + 1.0;
+            bool need = !(bmax < g.seg_max_x(smax) && bmin > g.seg_min_x(smin));
+            if (need) {
+                if (lane == 0) { g.update(bmin, bmax, m.terrain_type, m.terrain_params, 20.0); store_ground(L, g); }
+                __syncwarp();
+                g = load_ground(L, B);
+            }
         }
-        L.i(I_CONTACT) = contact;
-        // UpdateGround (scenarios/ScenarioSimChar.cpp:564-572)
-        if (g.update(SL(S_Q) - 2.0, SL(S_Q) + 10.0 + 1.0, m.terrain_type, m.terrain_params, 20.0)) store_ground(L, g);
-        // head of cDogController::Update: cycle timers, stumble counter, gait FSM
-        L.d(D_CUR_CYCLE_T) += h;
-        const int stumble_mask = ~((1 << jToe) | (1 << jFinger) | (1 << jAnkle) | (1 << jWrist));
-        if (contact & stumble_mask) L.d(D_CUR_STUMBLE) += h;
-        int state = L.i(I_STATE);
-        int first = L.i(I_FIRST_CYCLE);
-        double phase = L.d(D_PHASE) + h / L.d(D_PARAMS + mTransTime);
-        bool advance = first != 0;
-        if ((state == sBackStance || state == sFrontStance) && phase >= 1.0) advance = true;
-        if (state == sExtend && ((contact >> jFinger) & 1)) advance = true;
-        if (state == sGather && ((contact >> jToe) & 1)) advance = true;
-        L.d(D_PHASE) = phase;
-        if (advance) {
-            int ns2 = first ? sBackStance : (state == sGather ? -1 : state + 1);
-            bool end_step = (ns2 < 0) || first;
-            if (end_step) {
-                // cycle boundary: build the policy state and hand the env to the decision kernel
-                fk_world(L);
-                build_poli_state(L, B, g);
-                double comx, comy, cvx, cvy;
-                calc_com(sm, comx, comy, cvx, cvy);
+        // head of cDogController::Update: cycle timers, stumble counter, gait FSM (lane 0)
+        int end_step = 0;
+        if (lane == 0) {
+            L.i(I_CONTACT) = contact;
+            L.d(D_CUR_CYCLE_T) += h;
+            const int stumble_mask = ~((1 << jToe) | (1 << jFinger) | (1 << jAnkle) | (1 << jWrist));
+            if (contact & stumble_mask) L.d(D_CUR_STUMBLE) += h;
+            int state = L.i(I_STATE);
+            int first = L.i(I_FIRST_CYCLE);
+            double phase = L.d(D_PHASE) + h / L.d(D_PARAMS + mTransTime);
+            bool advance = first != 0;
+            if ((state == sBackStance || state == sFrontStance) && phase >= 1.0) advance = true;
+            if (state == sExtend && ((contact >> jFinger) & 1)) advance = true;
+            if (state == sGather && ((contact >> jToe) & 1)) advance = true;
+            L.d(D_PHASE) = phase;
+            if (advance) {
+                int ns2 = first ? sBackStance : (state == sGather ? -1 : state + 1);
+                if ((ns2 < 0) || first) end_step = 1;
+                else { L.i(I_STATE) = ns2; L.d(D_PHASE) = 0.0; set_state_params(L, ns2); }
+            }
+        }
+        end_step = shfi(end_step, 0);
+        if (end_step) {
+            // cycle boundary: build the policy state and hand the env to the decision kernel
+            Kin k = kinematics(lc, e);
+            build_poli_state(lc, e, k, B, g, env, lane);
+            double comx = e.ox + warp_sum_all(lc.mass * k.cx) / m.total_mass;
+            double comy = e.oy + warp_sum_all(lc.mass * k.cy) / m.total_mass;
+            if (lane == 0) {
                 B.com_stash[env] = comx; B.com_stash[B.n + env] = comy;
                 L.i(I_FIRST_CYCLE) = 0;
                 L.i(I_PENDING) = 1;
                 int slot = atomicAdd(B.pending_count, 1);
                 B.pending_list[slot] = env;
-            } else {
-                L.i(I_STATE) = ns2;
-                L.d(D_PHASE) = 0.0;
-                set_state_params(L, ns2);
             }
         }
     }
-
-    for (int k = 0; k < nd; ++k) { L.d(D_Q + k) = SL(S_Q + k); L.d(D_QD + k) = SL(S_QD + k); L.d(D_TAU + k) = SL(S_TAU + k); }
+    store_env(L, lc, e, lane);
 }
 
 // Initial reset of every env (trl_create / trl_reset): seeds the terrain RNG and runs the episode reset.
-__global__ void __launch_bounds__(kWarp, 1)
+__global__ void __launch_bounds__(kBlockThreads)
 trl_reset_kernel(Buffers B, const uint64_t* terrain_seeds, const int* env_ids, int count, int reseed) {
-    extern __shared__ double smem[];
-    const int lane = threadIdx.x;
-    const int idx = blockIdx.x * kWarp + lane;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int idx = blockIdx.x * kWarpsPerBlock + warp;
     if (idx >= count) return;
     const int env = env_ids ? env_ids[idx] : idx;
-    Lane L{smem + lane, env, B.n, B.d, B.i};
-    double* sm = L.sm;
+    Lane L{nullptr, env, B.n, B.d, B.i};
     const ModelConst& m = c_model;
-    if (reseed) {
+    if (reseed && lane == 0) {
         uint64_t seed = terrain_seeds ? terrain_seeds[idx] : (uint64_t)(1 + env);
         L.i(I_TERRAIN_RNG) = (int)TerrainRng::seed_state(seed);
         L.i(I_RNG_CTR_LO) = 0; L.i(I_RNG_CTR_HI) = 0;
@@ -995,25 +963,24 @@ trl_reset_kernel(Buffers B, const uint64_t* terrain_seeds, const int* env_ids, i
         for (int k = 0; k < kNumParams; ++k) L.d(D_PARAMS + k) = 0.0;
         L.d(D_CUR_CYCLE_T) = 0.0; L.d(D_CUR_STUMBLE) = 0.0; L.d(D_PREV_COM_X) = 0.0; L.d(D_PREV_COM_Y) = 0.0;
     }
-    reset_env(L, B);
-    for (int k = 0; k < m.ndof; ++k) { L.d(D_Q + k) = SL(S_Q + k); L.d(D_QD + k) = SL(S_QD + k); L.d(D_TAU + k) = SL(S_TAU + k); }
+    __syncwarp();
+    const LinkC lc = load_link(lane);
+    EnvRegs e;
+    reset_env(L, lc, e, B, lane);
+    store_env(L, lc, e, lane);
 }
 
 // ---- host-side launch helpers (called from trl_host.cu)
 cudaError_t upload_model(const ModelConst& mc) { return cudaMemcpyToSymbol(c_model, &mc, sizeof(ModelConst)); }
-size_t step_smem_bytes() { return (size_t)S_NUM * kWarp * sizeof(double); }
-cudaError_t configure_step_kernels() {
-    cudaError_t e = cudaFuncSetAttribute(trl_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_smem_bytes());
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(trl_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_smem_bytes());
-}
+size_t step_smem_bytes() { return 0; }
+cudaError_t configure_step_kernels() { return cudaSuccess; }
 void launch_step(const Buffers& B, double h, int flags, cudaStream_t st) {
-    int blocks = (B.n + kWarp - 1) / kWarp;
-    trl_step_kernel<<<blocks, kWarp, step_smem_bytes(), st>>>(B, h, flags);
+    int blocks = (B.n + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    trl_step_kernel<<<blocks, kBlockThreads, 0, st>>>(B, h, flags);
 }
 void launch_reset(const Buffers& B, const uint64_t* seeds, const int* env_ids, int count, int reseed, cudaStream_t st) {
-    int blocks = (count + kWarp - 1) / kWarp;
-    trl_reset_kernel<<<blocks, kWarp, step_smem_bytes(), st>>>(B, seeds, env_ids, count, reseed);
+    int blocks = (count + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    trl_reset_kernel<<<blocks, kBlockThreads, 0, st>>>(B, seeds, env_ids, count, reseed);
 }
 
 }  // namespace trl

@@ -64,8 +64,19 @@ struct ModelConst {
     double body_cos[kMaxJoints], body_sin[kMaxJoints];
     double half_x[kMaxJoints], half_y[kMaxJoints];
     double izz_o[kMaxJoints];              // planar rotational inertia about the joint origin
+    double izz_c[kMaxJoints];              // planar rotational inertia about the body COM
     int collidable[kMaxJoints];
     double total_mass;
+    // tree topology helpers for the level-synchronous warp passes
+    int depth[kMaxJoints], max_depth;
+    int child[kMaxJoints][3];              // up to 3 children per link (-1 = none)
+    int level_slot[12][3];                 // level_slot[l][s] != 0: some link at depth l is child slot s of its parent
+    int n_corners;                         // 4 * number of collidable bodies
+    int corner_body[4 * kMaxJoints];
+    double corner_lx[4 * kMaxJoints], corner_ly[4 * kMaxJoints];   // corner position in the link (joint) frame
+    int corner_base[kMaxJoints];           // first corner index of a body (-1 if not collidable)
+    unsigned anc_mask_toe, anc_mask_finger;   // links on the chain effector -> root (inclusive)
+    unsigned vf_mask_toe, vf_mask_finger;     // links that receive the virtual force (chain up to root / torso, exclusive)
     // PD
     double kp[kMaxJoints], kd[kMaxJoints], torque_lim[kMaxJoints], target_theta0[kMaxJoints], target_vel[kMaxJoints];
     int world_pd[kMaxJoints];
