@@ -14,7 +14,7 @@
 
 namespace trl {
 
-constexpr int kDecideThreads = 256;
+constexpr int kDecideThreads = 1024;
 constexpr int kConv0Out = 16, kConv0K = 8, kW0 = 193;
 constexpr int kConv1Out = 32, kConv1K = 4, kW1 = 190;
 constexpr int kConv2Out = 32, kConv2K = 4, kW2 = 187;

@@ -139,6 +139,11 @@ static int fill_model(trl_handle* h, uint64_t rng_seed) {
         m.child[p][slot] = j;
         m.level_slot[m.depth[j]][slot] = 1;
     }
+    if (m.max_depth >= 16) return fail("kinematic tree too deep for the 4-round ancestor jumps");
+    for (int j = 0; j < m.nj; ++j) {
+        m.anc_pow[j][0] = m.parent[j];
+        for (int k = 1; k < 4; ++k) m.anc_pow[j][k] = m.anc_pow[j][k - 1] >= 0 ? m.anc_pow[m.anc_pow[j][k - 1]][k - 1] : -1;
+    }
     m.n_corners = 0;
     for (int j = 0; j < m.nj; ++j) {
         m.corner_base[j] = -1;

@@ -242,6 +242,7 @@ __device__ void store_rng(Lane& L, const CounterRng& r) {
 struct LinkC {
     int act;            // lane < nj
     int parent, depth, child0, child1, child2;
+    int anc1, anc2, anc4, anc8;   // 2^k-th ancestors (-1 = none) for the pointer-jumping prefix sums
     double ax, ay;      // attach point in the parent's joint frame
     double mass, bax, bay, izz_c;
     int has_lim;
@@ -267,6 +268,8 @@ __device__ __forceinline__ LinkC load_link(int lane) {
     c.child0 = c.act ? m.child[j][0] : -1;
     c.child1 = c.act ? m.child[j][1] : -1;
     c.child2 = c.act ? m.child[j][2] : -1;
+    c.anc1 = c.act ? m.anc_pow[j][0] : -1; c.anc2 = c.act ? m.anc_pow[j][1] : -1;
+    c.anc4 = c.act ? m.anc_pow[j][2] : -1; c.anc8 = c.act ? m.anc_pow[j][3] : -1;
     c.ax = m.attach_x[j]; c.ay = m.attach_y[j];
     c.mass = c.act ? m.mass[j] : 0.0;
     c.bax = m.body_ax[j]; c.bay = m.body_ay[j];
@@ -276,28 +279,33 @@ __device__ __forceinline__ LinkC load_link(int lane) {
     return c;
 }
 
-// level-synchronous outward pass: world rotation, joint origin (rel. O) and spatial velocity of every link
+// root-ward prefix sums over the kinematic tree by pointer jumping: after 4 rounds every link holds the sum of its own
+// value and those of all its ancestors (depth <= 15), using the static 2^k-th ancestor table
+#define TRL_TREE_PREFIX2(a, b)                                                                  \
+    do {                                                                                        \
+        _Pragma("unroll") for (int r_ = 0; r_ < 4; ++r_) {                                      \
+            int an_ = (r_ == 0) ? c.anc1 : ((r_ == 1) ? c.anc2 : ((r_ == 2) ? c.anc4 : c.anc8)); \
+            double ta_ = shf((a), an_ >= 0 ? an_ : 0), tb_ = shf((b), an_ >= 0 ? an_ : 0);      \
+            if (an_ >= 0) { (a) += ta_; (b) += tb_; }                                           \
+        }                                                                                       \
+    } while (0)
+
+// outward kinematics: world rotation, joint origin (rel. O) and spatial velocity of every link
 __device__ __forceinline__ Kin kinematics(const LinkC& c, const EnvRegs& e) {
-    const int md = c_model.max_depth;
     Kin k;
     double phi = e.q, w = e.qd;
-    for (int l = 1; l <= md; ++l) {
-        double pphi = shf(phi, c.parent), pw = shf(w, c.parent);
-        if (c.depth == l) { phi = pphi + e.q; w = pw + e.qd; }
-    }
+    TRL_TREE_PREFIX2(phi, w);
     k.phi = phi; k.w = w;
     sincos(phi, &k.sw, &k.cw);
-    double rx = 0.0, ry = 0.0, vx = e.oxd, vy = e.oyd;
-    for (int l = 1; l <= md; ++l) {
-        double pcw = shf(k.cw, c.parent), psw = shf(k.sw, c.parent), prx = shf(rx, c.parent), pry = shf(ry, c.parent);
-        double pvx = shf(vx, c.parent), pvy = shf(vy, c.parent);
-        if (c.depth == l) {
-            rx = prx + pcw * c.ax - psw * c.ay;
-            ry = pry + psw * c.ax + pcw * c.ay;
-            vx = pvx + e.qd * ry;      // v_j = v_parent + S_j qd_j,  S_j = (1, r_y, -r_x)
-            vy = pvy - e.qd * rx;
-        }
-    }
+    // offset of this joint from its parent's joint, in world axes
+    double pcw = shf(k.cw, c.parent), psw = shf(k.sw, c.parent);
+    double rx = 0.0, ry = 0.0;
+    if (c.depth > 0) { rx = pcw * c.ax - psw * c.ay; ry = psw * c.ax + pcw * c.ay; }
+    TRL_TREE_PREFIX2(rx, ry);
+    // v_j = v_root + sum over the chain of S_a qd_a,  S_a = (1, r_ay, -r_ax)
+    double vx = (c.depth > 0) ? e.qd * ry : e.oxd, vy = (c.depth > 0) ? -e.qd * rx : e.oyd;
+    if (c.depth < 0) { vx = 0.0; vy = 0.0; }
+    TRL_TREE_PREFIX2(vx, vy);
     k.rx = rx; k.ry = ry; k.vx = vx; k.vy = vy;
     k.cx = rx + k.cw * c.bax - k.sw * c.bay;
     k.cy = ry + k.sw * c.bax + k.cw * c.bay;
@@ -630,24 +638,23 @@ __device__ int physics_substep(const LinkC& lc, EnvRegs& e, const GroundView& g,
                 }
             }
         }
-        // the 4 corners of a body sit in 4 consecutive lanes: segmented sum, then the owning link lane fetches it
+        // hand the (few) force-producing corners to the lanes that own their bodies, in corner order (deterministic)
         const unsigned tmask = __ballot_sync(kFull, touching);
-#pragma unroll
-        for (int v = 0; v < 9; ++v) {
-            add[v] += __shfl_xor_sync(kFull, add[v], 1);
-            add[v] += __shfl_xor_sync(kFull, add[v], 2);
-        }
+        unsigned fmask = __ballot_sync(kFull, add[3] != 0.0 || add[5] != 0.0);
         const int cb = lc.act ? m.corner_base[lane] : -1;
         const bool mine = cb >= base && cb < base + kWarp;
-        const int src = mine ? cb - base : 0;
+        while (fmask) {
+            const int src = __ffs(fmask) - 1;
+            fmask &= fmask - 1;
+            const bool to_me = mine && (src >= cb - base) && (src < cb - base + 4);
 #pragma unroll
-        for (int v = 0; v < 9; ++v) {
-            double t = shf(add[v], src);
-            if (mine) ia[v] += t;
+            for (int v = 0; v < 9; ++v) {
+                double t = shf(add[v], src);
+                if (to_me) ia[v] += t;
+            }
         }
-        if (mine && ((tmask >> src) & 0xfu)) contact |= 1 << lane;
+        if (mine && ((tmask >> (cb - base)) & 0xfu)) contact |= 1 << lane;
     }
-    // combine the per-lane contact bits into one mask
     contact = (int)__ballot_sync(kFull, contact != 0);   // lane index == link index
 
     // ---- pass 2: articulated inertias / bias forces inward (level-synchronous)
@@ -805,7 +812,7 @@ __device__ __forceinline__ void store_env(Lane& L, const LinkC& lc, const EnvReg
 
 // ================================================================================================ the kernel
 // flags: bit0 do_ctrl (finish env-step k), bit1 do_phys (start env-step k+1), bit2 end of outer update
-__global__ void __launch_bounds__(kBlockThreads)
+__global__ void __launch_bounds__(kBlockThreads, 4)
 trl_step_kernel(Buffers B, double h, int flags) {
     __shared__ double s_clx[4 * kMaxJoints], s_cly[4 * kMaxJoints];
     __shared__ int s_cbody[4 * kMaxJoints];

@@ -70,6 +70,7 @@ struct ModelConst {
     // tree topology helpers for the level-synchronous warp passes
     int depth[kMaxJoints], max_depth;
     int child[kMaxJoints][3];              // up to 3 children per link (-1 = none)
+    int anc_pow[kMaxJoints][4];            // 2^k-th ancestor of each link (k = 0..3), -1 if it does not exist
     int level_slot[12][3];                 // level_slot[l][s] != 0: some link at depth l is child slot s of its parent
     int n_corners;                         // 4 * number of collidable bodies
     int corner_body[4 * kMaxJoints];
