@@ -52,6 +52,43 @@ def gather_tuple_blocks(rows, flags, env_ids, count, env_offset=0, pad_to=64, gr
     return (out_rows.view(world * m, -1)[keep], out_flags.view(-1)[keep], out_env.view(-1)[keep])
 
 
+def gather_tuple_blocks_fixed(rows, flags, env_ids, count, env_offset=0, block_rows=1024, group=None):
+    """Sync-free variant: ONE all-gather of a fixed-shape f32 block per rank, no host round-trip.
+
+    Block layout per rank: [block_rows + 1, W + 2] float32; row 0 carries the rank's tuple count in column 0, rows
+    1.. are [flags, global env id, reward, s, a, s'].  Returns the gathered tensor [world, block_rows + 1, W + 2] on the
+    backend device; `unpack_tuple_blocks` trims it on the consumer side.  Rows beyond block_rows stay queued on the
+    producer (the caller only resets its tuple buffer when count <= block_rows).
+    """
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    W = rows.shape[1]
+    m = min(block_rows, rows.shape[0])
+    blk = torch.zeros((block_rows + 1, W + 2), dtype=torch.float32, device=rows.device)
+    blk[0, 0] = torch.clamp(count[0], max=m).to(torch.float32)
+    blk[1:m + 1, 0] = flags[:m].to(torch.float32)
+    blk[1:m + 1, 1] = (env_ids[:m] + int(env_offset)).to(torch.float32)
+    blk[1:m + 1, 2:] = rows[:m].to(torch.float32)
+    out = torch.empty((world,) + tuple(blk.shape), dtype=torch.float32, device=rows.device)
+    if rows.is_cuda:
+        dist.all_gather_into_tensor(out.view(-1), blk.view(-1), group=group)
+    else:
+        dist.all_gather(list(out.unbind(0)), blk, group=group)
+    return out
+
+
+def unpack_tuple_blocks(gathered):
+    """(rows_f32 [total, W], flags int32, env int32) from the output of gather_tuple_blocks_fixed (syncs)."""
+    import torch
+    rows, flags, env = [], [], []
+    for r in range(gathered.shape[0]):
+        c = int(gathered[r, 0, 0].item())
+        rows.append(gathered[r, 1:c + 1, 2:]); flags.append(gathered[r, 1:c + 1, 0].to(torch.int32))
+        env.append(gathered[r, 1:c + 1, 1].to(torch.int32))
+    return torch.cat(rows), torch.cat(flags), torch.cat(env)
+
+
 def reduce_eval_stats(stats, group=None):
     """Sum (cycles, episodes, steps) and episode-weighted avg_dist over ranks (cOptScenarioPoliEval::OutputResults
     merges per-thread results under a mutex: optimizer/scenarios/OptScenarioPoliEval.cpp:213-237)."""

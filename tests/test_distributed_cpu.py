@@ -17,7 +17,8 @@ def _worker(rank, world, port, pack, out_dir):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from pyoracle import Oracle
-    from deepterrainrl_b200.parallel import gather_tuple_blocks, reduce_eval_stats, shard_seeds
+    from deepterrainrl_b200.parallel import (gather_tuple_blocks, gather_tuple_blocks_fixed, reduce_eval_stats, shard_seeds,
+                                             unpack_tuple_blocks)
     n = 4
     seeds = shard_seeds(rank, n)
     o = Oracle(pack, n, 1, terrain_seeds=seeds, rng_seed=99 + rank)   # the oracle stands in for one rank's engine
@@ -31,6 +32,8 @@ def _worker(rank, world, port, pack, out_dir):
     E = torch.zeros(cap, dtype=torch.int32); E[:len(rows)] = torch.from_numpy(ids)
     cnt = torch.tensor([len(rows)], dtype=torch.int32)
     g_rows, g_flags, g_env = gather_tuple_blocks(R, F, E, cnt, env_offset=rank * n)
+    f_rows, f_flags, f_env = unpack_tuple_blocks(gather_tuple_blocks_fixed(R, F, E, cnt, env_offset=rank * n, block_rows=128))
+    assert torch.equal(f_rows, g_rows) and torch.equal(f_flags, g_flags) and torch.equal(f_env, g_env)
     st = reduce_eval_stats(o.eval_stats())
     np.savez(os.path.join(out_dir, f"r{rank}.npz"), rows=g_rows.numpy(), flags=g_flags.numpy(), env=g_env.numpy(),
              local=rows.astype(np.float32), local_n=len(rows), steps=st["steps"], seeds=seeds)

@@ -1,0 +1,129 @@
+"""More GPU parity cases: goat/cliffs (1 physics sub-step per env-step, gravity compensation off, init x, target 2 m/s),
+set/get state round trip, weight upload, per-env reset, determinism, size-independent properties at the full batch."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+H = 1.0 / 600.0
+
+
+def _relerr(a, b):
+    return np.max(np.abs(a - b) / (1.0 + np.abs(b)))
+
+
+def test_goat_cliffs_parity(assets):
+    from pyoracle import Oracle
+    import deepterrainrl_b200 as trl
+    pack = os.path.join(assets, "goat_cliffs.trlpack")
+    n = 8
+    seeds = (1 + 7919 * np.arange(n)).astype(np.uint64)       # SURVEY §8d config 5 seeding
+    g = trl.ScenarioPoliEval(pack, n, terrain_seeds=seeds)
+    o = Oracle(pack, n, 0, terrain_seeds=seeds)
+    for env in range(n):
+        for seg in (0, 1):
+            gd, gmx, gfl = g.GetTerrain(env, seg)
+            od, omx, ofl = o.terrain(env, seg)
+            np.testing.assert_array_equal(gd, od)
+            assert gmx == omx and gfl == ofl
+    for k in range(30):
+        g.Update(1.0 / 30.0)
+        o.update(1.0 / 30.0, 4)
+        if k % 5 == 4:
+            gq, gqd = g.GetStateAll()
+            for e in range(n):
+                oq, oqd, _, _ = o.get_state(e)
+                assert _relerr(gq[:, e], oq) < 1e-4 and _relerr(gqd[:, e], oqd) < 1e-4, (k, e)
+    assert g._stats()["cycles"] == o.eval_stats()["cycles"]
+    assert g._stats()["episodes"] == o.eval_stats()["episodes"]
+
+
+def test_set_state_roundtrip_and_single_env_reset(assets):
+    import deepterrainrl_b200 as trl
+    pack = os.path.join(assets, "dog_slopes_mixed.trlpack")
+    g = trl.ScenarioPoliEval(pack, 16)
+    q0, qd0, _, _ = g.GetState(3)
+    for _ in range(5):
+        g.Update(1.0 / 30.0)
+    q1, qd1, tau1, c1 = g.GetState(3)
+    assert not np.allclose(q0, q1)
+    other = g.GetState(4)[0].copy()
+    g.Reset([3])
+    q2, qd2, tau2, _ = g.GetState(3)
+    np.testing.assert_array_equal(q2[2:], q0[2:])            # joint angles back to the state file
+    np.testing.assert_array_equal(qd2, qd0)
+    assert np.all(tau2 == 0)
+    np.testing.assert_array_equal(g.GetState(4)[0], other)   # neighbours untouched
+    g.SetState(5, q=q1, qd=qd1, tau=tau1, contact=c1)
+    q3, qd3, tau3, c3 = g.GetState(5)
+    np.testing.assert_array_equal(q3, q1); np.testing.assert_array_equal(qd3, qd1)
+    np.testing.assert_array_equal(tau3, tau1); np.testing.assert_array_equal(c3, c1)
+
+
+def test_determinism_and_weight_upload(assets):
+    from pack_scene import read_pack, NET_LAYERS
+    import deepterrainrl_b200 as trl
+    pack = os.path.join(assets, "dog_slopes_mixed.trlpack")
+    a = trl.ScenarioPoliEval(pack, 64)
+    b = trl.ScenarioPoliEval(pack, 64)
+    p = read_pack(pack)
+    blobs = []
+    for name in NET_LAYERS:
+        blobs += [p["net_" + name + "_w"], p["net_" + name + "_b"]]
+    b.SetWeights(blobs, p["net_in_offset"], p["net_in_scale"], p["net_out_offset"], p["net_out_scale"])  # CopyModel
+    for _ in range(15):
+        a.Update(1.0 / 30.0); b.Update(1.0 / 30.0)
+    qa, qda = a.GetStateAll(); qb, qdb = b.GetStateAll()
+    np.testing.assert_array_equal(qa, qb)                    # bit-identical: deterministic kernels, same weights
+    np.testing.assert_array_equal(qda, qdb)
+    # zeroed actor heads must change behaviour (the upload is really used)
+    blobs2 = [x.copy() for x in blobs]
+    for i in range(14, 26):
+        blobs2[i][:] = 0
+    b.SetWeights(blobs2, p["net_in_offset"], p["net_in_scale"], p["net_out_offset"], p["net_out_scale"])
+    for _ in range(30):
+        a.Update(1.0 / 30.0); b.Update(1.0 / 30.0)
+    assert not np.array_equal(a.GetStateAll()[0], b.GetStateAll()[0])
+
+
+def test_full_batch_properties(assets):
+    """4096 envs (BASELINE configs[1] size): counters add up, no NaNs, env 0..7 identical to a small batch with the
+    same seeds (batch-size independence), dogs make forward progress."""
+    import deepterrainrl_b200 as trl
+    pack = os.path.join(assets, "dog_slopes_mixed.trlpack")
+    n = 4096
+    big = trl.ScenarioPoliEval(pack, n)
+    small = trl.ScenarioPoliEval(pack, 8)
+    for _ in range(30):
+        big.Update(1.0 / 30.0); small.Update(1.0 / 30.0)
+    qb, qdb = big.GetStateAll(); qs, qds = small.GetStateAll()
+    assert np.all(np.isfinite(qb)) and np.all(np.isfinite(qdb))
+    np.testing.assert_array_equal(qb[:, :8], qs)
+    st = big._stats()
+    assert st["steps"] == 30 * 20 * n
+    assert st["cycles"] >= 2 * n
+    d, e = big.GetDistLog()
+    assert d.size == st["episodes"]
+    assert np.median(qb[0]) > 2.5                            # ~4 m/s for 1 s
+
+
+def test_explore_gather_block_views(assets):
+    import torch
+    import deepterrainrl_b200 as trl
+    pack = os.path.join(assets, "dog_slopes_mixed.trlpack")
+    g = trl.ScenarioExpMACE(pack, 256)
+    g.EnableExplore(1, 0.2, 0.025, 0.002)
+    for _ in range(45):
+        g.Update(1.0 / 30.0)
+    g.Sync()
+    rows, flags, env, count = g.DeviceTupleBlock()
+    n = int(count.item())
+    hr, hf, he = g.GetTuples(f64=True)
+    assert n == hr.shape[0] > 0
+    np.testing.assert_array_equal(rows[:n].cpu().numpy(), hr)
+    np.testing.assert_array_equal(flags[:n].cpu().numpy().astype(np.uint32), hf)
+    np.testing.assert_array_equal(env[:n].cpu().numpy(), he)
+    g.ResetTupleBuffer(); g.Sync()
+    assert g.GetNumTuples() == 0
