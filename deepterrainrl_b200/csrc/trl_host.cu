@@ -23,6 +23,8 @@ void launch_reset(const Buffers& B, const uint64_t* seeds, const int* env_ids, i
 size_t decide_smem_bytes();
 cudaError_t configure_decide_kernel();
 void launch_decide(const Buffers& B, const NetWeights& W, const ExpSettings& ex, int* done_count, int grid, cudaStream_t st);
+void launch_stats(const Buffers& B, double* out, cudaStream_t st);
+void launch_terrain(const Buffers& B, double lookahead, cudaStream_t st);
 }  // namespace trl
 
 using namespace trl;
@@ -49,7 +51,7 @@ struct trl_handle {
     std::vector<int64_t> net_counts;
     int* done_count = nullptr;
     cudaStream_t stream = nullptr;
-    int decide_grid = 296;
+    int decide_grid = 288;   // multiple of the 8-CTA cluster size
     int num_update_steps = 20;
     int64_t launches = 0;
     std::map<long long, cudaGraphExec_t> graphs;   // keyed by the bit pattern of dt
@@ -63,6 +65,12 @@ struct trl_handle {
     std::vector<int32_t> h_dist_env;
     std::vector<void*> allocs;
     void* flush_buf = nullptr;
+    // pipelined read-back (trl_snapshot / trl_snapshot_wait)
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t snap_ready = nullptr, snap_copied = nullptr;
+    double* snap_dev = nullptr;      // [2 * ndof * n + 4] device staging (pose planes, vel planes, stats)
+    double* snap_host = nullptr;     // pinned mirror
+    bool snap_pending = false;
 };
 
 template <typename T>
@@ -232,6 +240,7 @@ static void destroy_graphs(trl_handle* h) {
 static void enqueue_update(trl_handle* h, double dt) {
     const int ns = h->num_update_steps;
     const double step = dt / ns;
+    launch_terrain(h->B, 0.5, h->stream);
     for (int i = 0; i < ns; ++i) {
         launch_step(h->B, step, i == 0 ? 2 : 3, h->stream);
         launch_decide(h->B, h->W, h->ex, h->done_count, h->decide_grid, h->stream);
@@ -305,7 +314,7 @@ trl_handle* trl_create_from_pack(const char* pack_path, int num_envs, int device
         std::memset(&h->W, 0, sizeof(h->W));
     }
     cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) h->decide_grid = 2 * prop.multiProcessorCount;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) h->decide_grid = 8 * std::max(1, (2 * prop.multiProcessorCount) / 8);
     if (trl_seed_terrain(h, terrain_seeds, terrain_seeds ? num_envs : 0)) return bail("");
     return h;
 }
@@ -314,6 +323,10 @@ int trl_destroy(trl_handle* h) {
     if (!h) return 0;
     if (h->stream) cudaStreamSynchronize(h->stream);
     destroy_graphs(h);
+    if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
+    if (h->snap_ready) cudaEventDestroy(h->snap_ready);
+    if (h->snap_copied) cudaEventDestroy(h->snap_copied);
+    if (h->snap_host) cudaFreeHost(h->snap_host);
     for (void* p : h->allocs) cudaFree(p);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -354,7 +367,7 @@ int trl_reset(trl_handle* h, const int32_t* env_ids, int n) {
 
 int trl_update(trl_handle* h, double dt) {
     if (!(dt > 0)) return 0;
-    const int nlaunch = 2 * h->num_update_steps + 1;
+    const int nlaunch = 2 * h->num_update_steps + 2;
     if (h->use_graph) {
         long long key;
         std::memcpy(&key, &dt, 8);
@@ -610,6 +623,73 @@ int trl_get_terrain(trl_handle* h, int env, int seg, float* data, int cap, int* 
 
 int64_t trl_kernel_launches(trl_handle* h) { return h->launches; }
 
+// Micro-benchmark of the decision kernel: marks the first `n_pending` envs as pending (their policy state is whatever the
+// last real decision left) and times `iters` launches.  Perturbs those envs' actions: measurement use only.
+int trl_debug_time_decide(trl_handle* h, int n_pending, int iters, double* ms_avg) {
+    if (n_pending > h->n) n_pending = h->n;
+    std::vector<int> ids(n_pending);
+    for (int i = 0; i < n_pending; ++i) ids[i] = i;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    double total = 0;
+    for (int it = 0; it < iters; ++it) {
+        CK(cudaMemcpyAsync(h->B.pending_list, ids.data(), (size_t)n_pending * 4, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->B.pending_count, &n_pending, 4, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaEventRecord(e0, h->stream));
+        launch_decide(h->B, h->W, h->ex, h->done_count, h->decide_grid, h->stream);
+        CK(cudaEventRecord(e1, h->stream));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        total += ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (ms_avg) *ms_avg = total / iters;
+    return 0;
+}
+
+// Pipelined read-back: trl_snapshot() enqueues, behind the work already on the handle's stream, a device-side copy
+// of all pose / velocity planes plus the reduced batch statistics, then moves them to pinned host memory on a second
+// stream; trl_snapshot_wait() blocks on that copy only, so the caller can enqueue the next trl_update() first and
+// read update k's results while update k+1 runs.
+int trl_snapshot(trl_handle* h) {
+    const size_t plane = (size_t)h->mc.ndof * h->n;
+    const size_t total = 2 * plane + 4;
+    if (!h->snap_dev) {
+        CK(cudaMalloc((void**)&h->snap_dev, total * 8)); h->allocs.push_back(h->snap_dev);
+        CK(cudaMallocHost((void**)&h->snap_host, total * 8));
+        CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&h->snap_ready, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->snap_copied, cudaEventDisableTiming));
+    }
+    if (h->snap_pending) CK(cudaEventSynchronize(h->snap_copied));   // previous snapshot must have left the staging area
+    CK(cudaMemcpyAsync(h->snap_dev, h->B.d + (size_t)D_Q * h->n, plane * 8, cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->snap_dev + plane, h->B.d + (size_t)D_QD * h->n, plane * 8, cudaMemcpyDeviceToDevice, h->stream));
+    launch_stats(h->B, h->snap_dev + 2 * plane, h->stream);
+    h->launches += 1;
+    CK(cudaEventRecord(h->snap_ready, h->stream));
+    CK(cudaStreamWaitEvent(h->copy_stream, h->snap_ready, 0));
+    CK(cudaMemcpyAsync(h->snap_host, h->snap_dev, total * 8, cudaMemcpyDeviceToHost, h->copy_stream));
+    CK(cudaEventRecord(h->snap_copied, h->copy_stream));
+    h->snap_pending = true;
+    return 0;
+}
+
+int trl_snapshot_wait(trl_handle* h, double* pose, double* vel, int64_t* cycles, int64_t* episodes, double* avg_dist, int64_t* env_steps) {
+    if (!h->snap_pending) return fail("trl_snapshot_wait: no snapshot in flight");
+    CK(cudaEventSynchronize(h->snap_copied));
+    h->snap_pending = false;
+    const size_t plane = (size_t)h->mc.ndof * h->n;
+    if (pose) std::memcpy(pose, h->snap_host, plane * 8);
+    if (vel) std::memcpy(vel, h->snap_host + plane, plane * 8);
+    const double* st = h->snap_host + 2 * plane;
+    if (cycles) *cycles = (int64_t)st[0];
+    if (episodes) *episodes = (int64_t)st[1];
+    if (env_steps) *env_steps = (int64_t)st[2];
+    if (avg_dist) *avg_dist = st[1] > 0 ? st[3] / st[1] : 0.0;
+    return 0;
+}
+
 // Raw device views of the tuple block for zero-copy hand-off to a collective (NCCL all-gather of ExpTuple blocks,
 // SURVEY §8e).  Pointers are device addresses on the handle's GPU; the caller must trl_sync() before using them on
 // another stream.
@@ -647,12 +727,23 @@ int trl_bench_updates(trl_handle* h, double dt, int k, int flush_l2, double* ms_
 
 // One outer update launched kernel by kernel with an event pair around every launch: returns the summed device time
 // of the step kernel launches and of the decision kernel launches (roofline numerator's denominator).
+static int update_timed_impl(trl_handle* h, double dt, double* step_ms, int* step_launches, double* decide_ms, int* decide_launches,
+                             double* per_step, double* per_decide);
 int trl_update_timed(trl_handle* h, double dt, double* step_ms, int* step_launches, double* decide_ms, int* decide_launches) {
+    return update_timed_impl(h, dt, step_ms, step_launches, decide_ms, decide_launches, nullptr, nullptr);
+}
+// same, also returning every launch's duration: per_step[num_update_steps + 1], per_decide[num_update_steps]
+int trl_update_timed_detail(trl_handle* h, double dt, double* per_step, double* per_decide) {
+    return update_timed_impl(h, dt, nullptr, nullptr, nullptr, nullptr, per_step, per_decide);
+}
+static int update_timed_impl(trl_handle* h, double dt, double* step_ms, int* step_launches, double* decide_ms, int* decide_launches,
+                             double* per_step, double* per_decide) {
     const int ns = h->num_update_steps;
     const double step = dt / ns;
     std::vector<cudaEvent_t> ev(2 * (2 * ns + 1));
     for (auto& e : ev) CK(cudaEventCreate(&e));
     int k = 0;
+    launch_terrain(h->B, 0.5, h->stream);
     for (int i = 0; i < ns; ++i) {
         CK(cudaEventRecord(ev[k++], h->stream));
         launch_step(h->B, step, i == 0 ? 2 : 3, h->stream);
@@ -673,12 +764,15 @@ int trl_update_timed(trl_handle* h, double dt, double* step_ms, int* step_launch
         CK(cudaEventElapsedTime(&a, ev[idx], ev[idx + 1])); idx += 2;
         CK(cudaEventElapsedTime(&b, ev[idx], ev[idx + 1])); idx += 2;
         sm += a; dm += b;
+        if (per_step) per_step[i] = a;
+        if (per_decide) per_decide[i] = b;
     }
     float a = 0;
     CK(cudaEventElapsedTime(&a, ev[idx], ev[idx + 1]));
     sm += a;
+    if (per_step) per_step[ns] = a;
     for (auto& e : ev) cudaEventDestroy(e);
-    h->launches += 2 * ns + 1;
+    h->launches += 2 * ns + 2;
     if (step_ms) *step_ms = sm;
     if (step_launches) *step_launches = ns + 1;
     if (decide_ms) *decide_ms = dm;

@@ -977,6 +977,56 @@ trl_reset_kernel(Buffers B, const uint64_t* terrain_seeds, const int* env_ids, i
     store_env(L, lc, e, lane);
 }
 
+// Terrain look-ahead: regenerates, ahead of the step kernels of the coming outer update, the segment of every env
+// whose view window [x-2, x+11] will cross the end of its terrain during that update (look-ahead 0.5 m >> the distance
+// covered in 1/30 s).  cGroundVar2D::Update's result does not depend on *when* it runs (segment bounds, joint height
+// and the generator stream are functions of the previous segment only, sim/GroundVar2D.cpp:43-91), so the terrain is
+// bit-identical to generating it at the exact step; doing it here keeps the serial generator off the critical path
+// of the 21 step launches (it used to stall one warp for ~90 us per regeneration).
+__global__ void trl_terrain_kernel(Buffers B, double lookahead) {
+    const int env = blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= B.n) return;
+    const ModelConst& m = c_model;
+    Lane L{nullptr, env, B.n, B.d, B.i};
+    const double x = L.d(D_Q);
+    GroundView g = load_ground(L, B);
+    const int smin = g.seg_id(0), smax = g.seg_id(1);
+    const double bmin = x - 2.0, bmax = x + 10.0 + 1.0 + lookahead;
+    if (bmax < g.seg_max_x(smax) && bmin > g.seg_min_x(smin)) return;
+    g.update(bmin, bmax, m.terrain_type, m.terrain_params, 20.0);
+    store_ground(L, g);
+}
+void launch_terrain(const Buffers& B, double lookahead, cudaStream_t st) {
+    trl_terrain_kernel<<<(B.n + 127) / 128, 128, 0, st>>>(B, lookahead);
+}
+
+// Batch statistics (cOptScenarioPoliEval::OutputResults merges the same counters under a mutex): one block reduces
+// cycles / episodes / env-steps / episode-weighted distance into out[4] (doubles).
+__global__ void trl_stats_kernel(Buffers B, double* out) {
+    __shared__ double red[4][32];
+    double c = 0, e = 0, st = 0, ds = 0;
+    for (int env = threadIdx.x; env < B.n; env += blockDim.x) {
+        int ec = B.i[(size_t)I_EPISODE_COUNT * B.n + env];
+        c += B.i[(size_t)I_CYCLE_COUNT * B.n + env];
+        e += ec;
+        st += (double)(((uint64_t)(uint32_t)B.i[(size_t)I_STEPS_HI * B.n + env] << 32) | (uint32_t)B.i[(size_t)I_STEPS_LO * B.n + env]);
+        ds += B.d[(size_t)D_AVG_DIST * B.n + env] * ec;
+    }
+    c = warp_sum_all(c); e = warp_sum_all(e); st = warp_sum_all(st); ds = warp_sum_all(ds);
+    int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { red[0][w] = c; red[1][w] = e; red[2][w] = st; red[3][w] = ds; }
+    __syncthreads();
+    if (w == 0) {
+        int nw = blockDim.x >> 5;
+        for (int k = 0; k < 4; ++k) {
+            double v = l < nw ? red[k][l] : 0.0;
+            v = warp_sum_all(v);
+            if (l == 0) out[k] = v;
+        }
+    }
+}
+void launch_stats(const Buffers& B, double* out, cudaStream_t st) { trl_stats_kernel<<<1, 1024, 0, st>>>(B, out); }
+
 // ---- host-side launch helpers (called from trl_host.cu)
 cudaError_t upload_model(const ModelConst& mc) { return cudaMemcpyToSymbol(c_model, &mc, sizeof(ModelConst)); }
 size_t step_smem_bytes() { return 0; }

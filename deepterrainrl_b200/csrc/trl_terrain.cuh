@@ -18,7 +18,11 @@ namespace trl {
 struct TerrainRng {
     uint32_t x;
     __device__ __forceinline__ uint32_t next() {
-        x = (uint32_t)(((uint64_t)x * 16807ull) % 2147483647ull);
+        // x * 16807 mod (2^31 - 1) by Mersenne folding (exactly the minstd_rand0 recurrence)
+        uint64_t p = (uint64_t)x * 16807ull;
+        uint32_t r = (uint32_t)(p & 0x7fffffffull) + (uint32_t)(p >> 31);
+        if (r >= 2147483647u) r -= 2147483647u;
+        x = r;
         return x;
     }
     __device__ __forceinline__ static uint32_t seed_state(uint64_t s) {

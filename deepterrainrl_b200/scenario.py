@@ -42,7 +42,7 @@ EXPORTS = [
     "trl_set_explore", "trl_set_phys_params", "trl_set_weights", "trl_sizes", "trl_num_tuples", "trl_get_tuples",
     "trl_get_tuples_f64", "trl_reset_tuples", "trl_eval_stats", "trl_dist_log", "trl_get_state", "trl_set_state",
     "trl_get_state_all", "trl_get_ctrl", "trl_get_poli_state", "trl_get_net_out", "trl_get_terrain",
-    "trl_kernel_launches", "trl_last_error", "trl_bench_updates", "trl_update_timed", "trl_device_tuple_block",
+    "trl_kernel_launches", "trl_last_error", "trl_bench_updates", "trl_update_timed", "trl_device_tuple_block", "trl_snapshot", "trl_snapshot_wait", "trl_update_timed_detail", "trl_debug_time_decide",
 ]
 
 
@@ -169,6 +169,16 @@ class BatchedScenario:
         self._ck(self.L.trl_get_terrain(self.h, env, seg, _p(d), cap, C.byref(n), C.byref(mx), C.byref(fl)))
         return d[:min(n.value, cap)].copy(), mx.value, fl.value
 
+    def Snapshot(self):
+        """enqueue a capture of all poses / velocities + batch counters behind the submitted updates"""
+        self._ck(self.L.trl_snapshot(self.h))
+
+    def SnapshotWait(self, pose=None, vel=None):
+        """wait for the last Snapshot(); fills pose / vel ([num_dof, num_envs] float64 arrays) and returns the counters"""
+        c = C.c_int64(0); e = C.c_int64(0); a = C.c_double(0); s = C.c_int64(0)
+        self._ck(self.L.trl_snapshot_wait(self.h, _p(pose), _p(vel), C.byref(c), C.byref(e), C.byref(a), C.byref(s)))
+        return dict(cycles=c.value, episodes=e.value, avg_dist=a.value, steps=s.value)
+
     def KernelLaunches(self):
         return int(self.L.trl_kernel_launches(self.h))
 
@@ -177,6 +187,11 @@ class BatchedScenario:
         ms = C.c_double(0)
         self._ck(self.L.trl_bench_updates(self.h, C.c_double(dt), int(k), int(bool(flush_l2)), C.byref(ms)))
         return ms.value
+
+    def UpdateTimedDetail(self, dt=1.0 / 30.0, num_update_steps=20):
+        ps = np.zeros(num_update_steps + 1); pd = np.zeros(num_update_steps)
+        self._ck(self.L.trl_update_timed_detail(self.h, C.c_double(dt), _p(ps), _p(pd)))
+        return ps, pd
 
     def UpdateTimed(self, dt=1.0 / 30.0):
         """one outer update with per-launch events: (step_ms, step_launches, decide_ms, decide_launches)."""

@@ -86,6 +86,13 @@ int trl_get_terrain(trl_handle* h, int env, int seg, float* data, int cap, int* 
 /* number of engine kernels launched since creation (bench.py's gpu_launches claim) */
 int64_t trl_kernel_launches(trl_handle* h);
 
+/* pipelined read-back of what cOptScenarioPoliEval::EvalHelper reads after every Update (counters; optionally every
+ * env's pose/vel as [num_dof][num_envs] planes): trl_snapshot() enqueues the capture behind the updates already
+ * submitted, trl_snapshot_wait() returns it from pinned host memory -- call trl_update() for the next step in between. */
+int trl_snapshot(trl_handle* h);
+int trl_snapshot_wait(trl_handle* h, double* pose, double* vel, int64_t* cycles, int64_t* episodes, double* avg_dist,
+                      int64_t* env_steps);
+
 /* device-resident view of the tuple block (rows f64 [cap][width], flags, env ids, count) for zero-copy hand-off to
  * NCCL; replaces the per-thread `learner->Train(exp->GetTuples())` hand-off (scenarios/ScenarioTrain.cpp:388-395) */
 int trl_device_tuple_block(trl_handle* h, void** rows_f64, void** flags_u32, void** env_i32, void** count_i32,
@@ -95,6 +102,9 @@ int trl_device_tuple_block(trl_handle* h, void** rows_f64, void** flags_u32, voi
  * updates); one update with an event pair around every kernel launch (per-kernel device time for the roofline). */
 int trl_bench_updates(trl_handle* h, double dt, int k, int flush_l2, double* ms_total);
 int trl_update_timed(trl_handle* h, double dt, double* step_ms, int* step_launches, double* decide_ms, int* decide_launches);
+int trl_update_timed_detail(trl_handle* h, double dt, double* per_step_ms, double* per_decide_ms);
+
+int trl_debug_time_decide(trl_handle* h, int n_pending, int iters, double* ms_avg);
 
 const char* trl_last_error(void);
 
