@@ -40,6 +40,8 @@ void orc_destroy(OrcBatch* b) { delete b; }
 int orc_num_dof(OrcBatch* b) { return b->scene.ndof; }
 int orc_num_joints(OrcBatch* b) { return b->scene.nj; }
 int orc_state_size(OrcBatch* b) { return kNumGroundSamples + 4 * b->scene.nj - 1; }
+int orc_action_size(OrcBatch* b) { return 1 + b->scene.n_opt; }
+int orc_num_params(OrcBatch* b) { return b->scene.n_params; }
 
 void orc_set_phys(OrcBatch* b, const double* p7) {
     PhysParams& pp = b->scene.phys;
@@ -87,11 +89,11 @@ int orc_get_ctrl(OrcBatch* b, int env, double* out) {
     out[k++] = e.state; out[k++] = e.phase; out[k++] = e.first_cycle; out[k++] = e.cur_cycle_time; out[k++] = e.prev_cycle_time;
     out[k++] = e.cur_stumble; out[k++] = e.prev_stumble; out[k++] = e.prev_com[0]; out[k++] = e.prev_com[1];
     out[k++] = e.prev_dist[0]; out[k++] = e.prev_dist[1]; out[k++] = e.cur.id;
-    for (int i = 0; i < kDogParams; ++i) out[k++] = e.cur.params[i];
+    for (int i = 0; i < b->scene.n_params; ++i) out[k++] = e.cur.params[i];
     for (int j = 0; j < b->scene.nj; ++j) out[k++] = e.pd_target[j];
     out[k++] = e.fall_dist_counter; out[k++] = e.fall_contact_counter; out[k++] = e.sum_fall_contact;
     out[k++] = e.prev_check_pos[0]; out[k++] = e.prev_check_pos[1]; out[k++] = e.fail_fall_dist;
-    out[k++] = e.exp_critic; out[k++] = e.exp_actor; out[k++] = e.cycle_count;
+    out[k++] = e.exp_critic; out[k++] = e.exp_actor; out[k++] = e.cycle_count; out[k++] = e.stance;
     return k;
 }
 void orc_get_last_tau(OrcBatch* b, int env, double* tau) { std::memcpy(tau, b->envs[env]->last_tau, 8 * b->scene.ndof); }
@@ -133,7 +135,7 @@ void orc_com(OrcBatch* b, int env, double* com, double* com_vel) {
 // tuples: rows of [reward | s(S) | a(A) | s'(S)] doubles, flags, env ids; drained by orc_reset_tuples
 int orc_num_tuples(OrcBatch* b) { int n = 0; for (auto& e : b->envs) n += (int)e->tuples.size(); return n; }
 int orc_get_tuples(OrcBatch* b, double* rows, uint32_t* flags, int32_t* env_id, int cap) {
-    int S = orc_state_size(b), A = 1 + kDogOptParams, n = 0;
+    int S = orc_state_size(b), A = 1 + b->scene.n_opt, n = 0;
     for (auto& e : b->envs)
         for (auto& t : e->tuples) {
             if (n >= cap) return n;

@@ -59,6 +59,22 @@ enum DogMisc { mTransTime, mCv, mBackForceX, mBackForceY, mFrontForceX, mFrontFo
 enum DogStateParam { spSpineCurve, spShoulder, spElbow, spHip, spKnee, spAnkle, spMax };
 constexpr int kDogParams = mMiscMax + sStateMax * spMax;  // 30
 constexpr int kDogOptParams = kDogParams - 1;             // all but TransTime (sim/DogController.cpp:81-121)
+// raptor (sim/SimRaptor.h:11-33, sim/RaptorController.h:14-47, sim/RaptorController.cpp:11-122)
+enum RaptorJoint {
+    rRoot, rSpine0, rSpine1, rSpine2, rSpine3, rHead, rTail0, rTail1, rTail2, rTail3, rTail4,
+    rRightHip, rRightKnee, rRightAnkle, rRightToe, rLeftHip, rLeftKnee, rLeftAnkle, rLeftToe, rRaptorMax
+};
+enum RaptorState { rsContact, rsDown, rsPassing, rsUp };
+enum RaptorMisc { rmTransTime, rmCv, rmCd, rmForceX, rmForceY, rmMiscMax };
+enum RaptorStateParam { rpRootPitch, rpSpineCurve, rpStanceHip, rpStanceKnee, rpStanceAnkle, rpSwingHip, rpSwingKnee, rpSwingAnkle, rpMax };
+constexpr int kRaptorParams = rmMiscMax + 4 * rpMax;      // 37
+constexpr int kMaxParams = 37;
+static const bool kRaptorOptMask[kRaptorParams] = {
+    false, true, true, false, false,
+    true, false, true, true, true, true, true, true,
+    true, false, true, true, true, true, true, true,
+    false, false, true, true, true, true, true, true,
+    false, false, true, true, true, true, true, true};
 constexpr int kNumGroundSamples = 200;
 enum TupleFlag { fFail = 0, fExpCritic = 1, fExpActor = 2 };  // learning/MACETrainer.h:11-17
 
@@ -104,6 +120,11 @@ struct Scene {
     Net net;
     double target_vel_x = 4.0;
     PhysParams phys;
+    bool is_raptor = false;
+    int n_params = kDogParams, n_opt = kDogOptParams, misc_max = mMiscMax, sp_max = spMax;
+    int opt_idx[kMaxParams];
+    double exp_noise = 0.2;
+    unsigned stumble_mask = 0, fall_mask = 0;   // parts whose contact counts as stumble / fall contact
 
     void load(const std::string& path) {
         Pack p = Pack::load(path);
@@ -118,11 +139,28 @@ struct Scene {
         terrain_params = p.f64("terrain_params"); terrain_default = p.f64("terrain_default_params");
         sk.init(nj, joints.data(), bodies.data());
         if (sk.ndof != ndof) throw std::runtime_error("scene: dof mismatch");
-        if (char_type != 1 || nj != jDogMax) throw std::runtime_error("oracle: only the dog/goat skeleton is implemented");
+        is_raptor = (char_type == 2);
+        if (!((char_type == 1 && nj == jDogMax) || (is_raptor && nj == rRaptorMax)))
+            throw std::runtime_error("oracle: unsupported character");
         if (has_net) net.load(p);
-        target_vel_x = (ctrl == 4) ? 2.0 : 4.0;  // goat_mace (sim/GoatControllerMACE.cpp:11-14)
+        target_vel_x = (ctrl == 4) ? 2.0 : 4.0;  // goat_mace (sim/GoatControllerMACE.cpp:11-14); raptor 4 (sim/RaptorController.cpp:596-600)
+        if (is_raptor) {
+            n_params = kRaptorParams; misc_max = rmMiscMax; sp_max = rpMax; n_opt = 0;
+            for (int i = 0; i < n_params; ++i) if (kRaptorOptMask[i]) opt_idx[n_opt++] = i;
+            exp_noise = 0.15;   // sim/RaptorControllerMACE.cpp:7
+            for (int j = 0; j < nj; ++j) if (j != rRightToe && j != rLeftToe && j != rRightAnkle && j != rLeftAnkle) stumble_mask |= 1u << j;
+            const int fp[6] = {rRoot, rSpine0, rSpine1, rSpine2, rSpine3, rHead};
+            for (int j : fp) fall_mask |= 1u << j;
+        } else {
+            n_opt = 0;
+            for (int i = 1; i < n_params; ++i) opt_idx[n_opt++] = i;
+            for (int j = 0; j < nj; ++j) if (j != jToe && j != jFinger && j != jAnkle && j != jWrist) stumble_mask |= 1u << j;
+            const int fp[9] = {jRoot, jSpine0, jSpine1, jSpine2, jSpine3, jTorso, jNeck0, jNeck1, jHead};
+            for (int j : fp) fall_mask |= 1u << j;
+        }
+        if ((int)ctrl_params.size() != n_ctrl * n_params) throw std::runtime_error("scene: controller parameter size mismatch");
     }
-    bool is_mace() const { return ctrl == 3 || ctrl == 4; }
+    bool is_mace() const { return ctrl == 3 || ctrl == 4 || ctrl == 7; }
     // cScenarioSimChar::SetTerrainParamsLerp (scenarios/ScenarioSimChar.cpp:255-272)
     void terrain_params_lerp(double lerp, double* out) const {
         if (n_terrain_sets == 0) { for (int i = 0; i < pTerrainParamMax; ++i) out[i] = terrain_default[i]; return; }
@@ -140,7 +178,7 @@ struct Tuple {
     std::vector<double> s_beg, action, s_end;
 };
 
-struct Action { int id = -1; double params[kDogParams] = {0}; };
+struct Action { int id = -1; double params[kMaxParams] = {0}; };
 
 struct Env {
     const Scene* sc = nullptr;
@@ -158,6 +196,7 @@ struct Env {
 
     // controller state
     int state = 0;
+    int stance = 0;            // raptor: 0 = right leg is the stance leg (gDefaultStance), 1 = left
     double phase = 0;
     bool first_cycle = true, off_policy = false, exp_critic = false, exp_actor = false;
     Action cur;
@@ -234,26 +273,41 @@ struct Env {
     }
 
     // ------------------------------------------------------------------ controller
-    const double* cur_state_params() const { return cur.params + mMiscMax + state * spMax; }
-    // cDogController::SetStateParams (sim/DogController.cpp:1042-1054)
+    const double* cur_state_params() const { return cur.params + sc->misc_max + state * sc->sp_max; }
+    // raptor leg joints for the current stance (sim/RaptorController.cpp:1489-1536)
+    int r_stance(int k) const { return (stance == 0 ? rRightHip : rLeftHip) + k; }   // k: 0 hip, 1 knee, 2 ankle, 3 toe
+    int r_swing(int k) const { return (stance == 0 ? rLeftHip : rRightHip) + k; }
+    bool r_active_vf(int toe) const {   // cRaptorController::IsActiveVFEffector
+        return toe == r_stance(3) && (state == rsContact || state == rsDown) && contact[toe];
+    }
+    // cDogController::SetStateParams (sim/DogController.cpp:1042-1054); cRaptorController::SetStateParams (:1108-1125)
     void set_state_params() {
         const double* p = cur_state_params();
+        if (sc->is_raptor) {
+            pd_target[r_stance(0)] = p[rpStanceHip]; pd_target[r_stance(1)] = p[rpStanceKnee]; pd_target[r_stance(2)] = p[rpStanceAnkle];
+            pd_target[r_swing(0)] = p[rpSwingHip]; pd_target[r_swing(1)] = p[rpSwingKnee]; pd_target[r_swing(2)] = p[rpSwingAnkle];
+            return;
+        }
         const int spine[5] = {jSpine0, jSpine1, jSpine2, jSpine3, jTorso};
         for (int i = 0; i < 5; ++i) pd_target[spine[i]] = p[spSpineCurve];
         pd_target[jShoulder] = p[spShoulder]; pd_target[jElbow] = p[spElbow]; pd_target[jHip] = p[spHip];
         pd_target[jKnee] = p[spKnee]; pd_target[jAnkle] = p[spAnkle];
     }
     void transition_state(int s, double ph = 0) { state = s; phase = ph; set_state_params(); }
-    static void post_process(double* p) { p[mTransTime] = std::abs(p[mTransTime]); p[mCv] = std::abs(p[mCv]); }
+    void post_process(double* p) const {
+        p[mTransTime] = std::abs(p[mTransTime]); p[mCv] = std::abs(p[mCv]);
+        if (sc->is_raptor) p[rmCd] = std::abs(p[rmCd]);
+    }
     // cDogController::BlendCtrlParams / BuildBaseAction; cDogControllerMACE::AssignFragID
     void build_base_action(int a, Action& out) {
         const double* act = &sc->actions[4 * a];
         int i0 = (int)act[0], i1 = (int)act[1];
         double blend = act[2];
-        for (int k = 0; k < kDogParams; ++k) {
-            double p0 = sc->ctrl_params[i0 * kDogParams + k], p1 = sc->ctrl_params[i1 * kDogParams + k];
+        const int np = sc->n_params;
+        for (int k = 0; k < np; ++k) {
+            double p0 = sc->ctrl_params[i0 * np + k], p1 = sc->ctrl_params[i1 * np + k];
             // ReadParams stores post-processed parameter sets (sim/DogController.cpp:519-520)
-            if (k == mTransTime || k == mCv) { p0 = std::abs(p0); p1 = std::abs(p1); }
+            if (k == mTransTime || k == mCv || (sc->is_raptor && k == rmCd)) { p0 = std::abs(p0); p1 = std::abs(p1); }
             out.params[k] = (1 - blend) * p0 + blend * p1;
         }
         out.id = a;
@@ -293,11 +347,8 @@ struct Env {
         return sum_fall_contact > 0.25 || fail_fall_dist || std::abs(wrap_pi(q[2])) > M_PI * 0.8;
     }
     bool check_contact(int j) const { return contact[j]; }
-    bool has_stumbled() const {
-        for (int j = 0; j < jDogMax; ++j)
-            if (j != jToe && j != jFinger && j != jAnkle && j != jWrist && contact[j]) return true;
-        return false;
-    }
+    unsigned contact_mask() const { unsigned m = 0; for (int j = 0; j < sc->nj; ++j) if (contact[j]) m |= 1u << j; return m; }
+    bool has_stumbled() const { return (contact_mask() & sc->stumble_mask) != 0; }
 
     // cTerrainRLCharController::ParseGround + BuildPoliState (sim/TerrainRLCharController.cpp:168-285)
     void parse_ground_and_build_state() {
@@ -314,14 +365,23 @@ struct Env {
         poli_state[idx++] = q[1] - ground.sample(q[0]);
         for (int i = 1; i < nb; ++i) { poli_state[idx++] = body[i].px - q[0]; poli_state[idx++] = body[i].py - q[1]; }
         for (int i = 0; i < nb; ++i) { poli_state[idx++] = body[i].vx; poli_state[idx++] = body[i].vy; }
+        if (sc->is_raptor && stance != 0) {
+            // cRaptorController::FlipPoliPoseStance: swap the two legs' entries (packed at the end of each block)
+            const int nleg = 4 * 2;
+            int pose_end = kNumGroundSamples + 2 * nb - 1, vel_end = pose_end + 2 * nb;
+            for (int i = 0; i < nleg; ++i) {
+                std::swap(poli_state[pose_end - 1 - i], poli_state[pose_end - nleg - 1 - i]);
+                std::swap(poli_state[vel_end - 1 - i], poli_state[vel_end - nleg - 1 - i]);
+            }
+        }
     }
 
     // cBaseControllerMACE::BuildActorAction (+ cDogController::SetOptParams)
     void build_actor_action(const double* y, int a, Action& out) {
         out.id = a;
-        for (int k = 0; k < kDogParams; ++k) out.params[k] = cur.params[k];
+        for (int k = 0; k < sc->n_params; ++k) out.params[k] = cur.params[k];
         int nf = sc->net.n_frags, fs = sc->net.frag;
-        for (int k = 0; k < fs; ++k) out.params[1 + k] = y[nf + a * fs + k];
+        for (int k = 0; k < fs; ++k) out.params[sc->opt_idx[k]] = y[nf + a * fs + k];
         post_process(out.params);
     }
     // cBaseControllerMACE::DecideActionBoltzmann (sim/BaseControllerMACE.cpp:254-318)
@@ -353,7 +413,7 @@ struct Env {
             if (rn < exp_rate) {  // ApplyExpNoiseAction: N(0, mExpNoise) / OutputScale of actor 0
                 for (int k = 0; k < net.frag; ++k) {
                     double noise = exp_noise * rng.normal();
-                    out.params[1 + k] += noise * (1.0 / net.out_scale[nf + k]);
+                    out.params[sc->opt_idx[k]] += noise * (1.0 / net.out_scale[nf + k]);
                 }
                 exp_actor = true;
             }
@@ -381,6 +441,22 @@ struct Env {
     }
     // cDogController::UpdateState (sim/DogController.cpp:805-845) with the state table (:12-38)
     void update_state(double h) {
+        if (sc->is_raptor) {   // cRaptorController::UpdateState (sim/RaptorController.cpp:804-849), state table :11-37
+            bool advance = first_cycle;
+            phase += h / cur.params[rmTransTime];
+            if (state != rsUp && phase >= 1) advance = true;
+            if (state == rsUp && contact[r_swing(3)]) advance = true;
+            if (advance) {
+                int ns = first_cycle ? rsContact : (state == rsUp ? -1 : state + 1);
+                bool end_step = (ns < 0) || first_cycle;
+                if (end_step) {
+                    if (!first_cycle) { stance = 1 - stance; set_state_params(); }   // FlipStance -> SetStance
+                    update_action();
+                    first_cycle = false;
+                } else transition_state(ns);
+            }
+            return;
+        }
         static const bool trans_time[4] = {true, false, true, false};
         static const int trans_contact[4] = {-1, jFinger, -1, jToe};
         static const int next_state[4] = {sExtend, sFrontStance, sGather, -1};
@@ -418,6 +494,7 @@ struct Env {
         ctrl_model.update(pose, vel);
 
         update_state(h);
+        if (sc->is_raptor) { raptor_controller_tail(h, pose, vel, tau); return; }
 
         // ApplyFeedback (sim/DogController.cpp:903-945)
         {
@@ -517,6 +594,115 @@ struct Env {
             }
         }
     }
+    // cRaptorController::Update after UpdateState (sim/RaptorController.cpp:195-233): UpdateStanceHip,
+    // ApplySwingFeedback, stable-PD with the stance hip switched off while its foot pushes, gravity compensation
+    // (weighted ridge LS, root rows kept), ApplyStanceFeedback, ApplyVirtualForces
+    void raptor_controller_tail(double h, const double* pose, const double* vel, double* tau) {
+        const Skeleton& sk = sc->sk;
+        const int nd = sk.ndof;
+        const int st_hip = r_stance(0), sw_hip = r_swing(0), st_toe = r_stance(3);
+        const bool active_vf = r_active_vf(st_toe);
+        // ApplySwingFeedback (:907-931)
+        {
+            bool first_half = state == rsContact || state == rsDown;
+            double cd = first_half ? 0 : cur.params[rmCd], cv = first_half ? cur.params[rmCv] : 0;
+            double com[2], cvel[2];
+            calc_com(com, cvel);
+            double dth = cd * (com[0] - body[st_toe].px) + cv * cvel[0];
+            pd_target[sw_hip] = cur_state_params()[rpSwingHip] + dth;
+        }
+        // stable PD (stance hip inactive while it is an active virtual-force effector, :899-905)
+        {
+            double kp[kMaxDof] = {0}, kd[kMaxDof] = {0}, kdm[kMaxDof] = {0}, perr[kMaxDof] = {0}, verr[kMaxDof] = {0};
+            for (int j = 1; j < sk.nj; ++j) {
+                int o = sk.offset[j];
+                const double* pdj = &sc->pd[6 * j];
+                bool active = !(j == st_hip && active_vf);
+                kdm[o] = pdj[1];
+                kp[o] = active ? pdj[0] : 0; kd[o] = active ? pdj[1] : 0;
+                bool world = pdj[5] != 0;
+                double theta = world ? wrap_pi(body[j].ang) : pose[o];
+                perr[o] = pd_target[j] - theta;
+                verr[o] = pdj[4] - qd[o];
+            }
+            static thread_local double A[kMaxDof][kMaxDof];
+            double rhs[kMaxDof], acc[kMaxDof];
+            for (int a = 0; a < nd; ++a) {
+                for (int b = 0; b < nd; ++b) A[a][b] = ctrl_model.M[a][b];
+                A[a][a] += h * kdm[a];
+                rhs[a] = kp[a] * (perr[a] - h * vel[a]) + kd[a] * verr[a] - ctrl_model.C[a];
+            }
+            ldlt_solve(nd, A, rhs, acc);
+            for (int a = 0; a < nd; ++a) tau[a] += kp[a] * (perr[a] - h * vel[a]) + kd[a] * (verr[a] - h * acc[a]);
+        }
+        const int eff[2] = {rRightToe, rLeftToe};
+        // ApplyGravityCompensation (:983-1026) + BuildContactBasis (:1168-1230)
+        if (sc->grav_comp) {
+            double basis[kMaxDof][4];
+            for (int a = 0; a < nd; ++a) for (int b = 0; b < 4; ++b) basis[a][b] = 0;
+            bool support = false;
+            for (int e = 0; e < 2; ++e) {
+                if (!r_active_vf(eff[e])) continue;
+                support = true;
+                double p[2];
+                effector_pos(eff[e], p);
+                SpTrans X; X.r = {-p[0], -p[1], 0};
+                SV fb[2] = {apply_F(X, SV{{0, 0, 0}, {0, 1, 0}}), apply_F(X, SV{{0, 0, 0}, {1, 0, 0}})};
+                for (int cur_j = eff[e]; cur_j >= 0; cur_j = sk.parent[cur_j]) {
+                    int o = sk.offset[cur_j];
+                    for (int k = 0; k < sk.size[cur_j]; ++k)
+                        for (int b = 0; b < 2; ++b) basis[o + k][2 * e + b] = dot(ctrl_model.J[o + k], fb[b]);
+                }
+            }
+            if (support) {
+                double tg[kMaxDof];
+                ctrl_model.gravity_force(tg);
+                for (int a = 0; a < nd; ++a) tg[a] = -tg[a];
+                const double W[3] = {0.0001, 0.0001, 1};
+                double AtA[4][4], Atb[4], x[4];
+                for (int a = 0; a < 4; ++a) {
+                    Atb[a] = 0;
+                    for (int r = 0; r < 3; ++r) Atb[a] += basis[r][a] * W[r] * tg[r];
+                    for (int b = 0; b < 4; ++b) {
+                        AtA[a][b] = 0;
+                        for (int r = 0; r < 3; ++r) AtA[a][b] += basis[r][a] * W[r] * basis[r][b];
+                    }
+                    AtA[a][a] += 0.0001;
+                }
+                solve4(AtA, Atb, x);
+                for (int a = 0; a < nd; ++a) {
+                    double tc = 0;
+                    for (int b = 0; b < 4; ++b) tc += basis[a][b] * x[b];
+                    tau[a] += tg[a] - tc;
+                }
+            }
+        }
+        // ApplyStanceFeedback (:933-981)
+        if (active_vf) {
+            double hip_tau = -tau[sk.offset[sw_hip]];
+            const double* pdh = &sc->pd[6 * st_hip];
+            double root_tau = pdh[0] * (cur_state_params()[rpRootPitch] - wrap_pi(q[2])) + pdh[1] * (-qd[2]);
+            hip_tau += -root_tau;
+            tau[sk.offset[st_hip]] += hip_tau;
+        }
+        // ApplyVirtualForces (:1028-1075)
+        if (sc->virt_forces) {
+            for (int e = 0; e < 2; ++e) {
+                int j = eff[e];
+                if (!r_active_vf(j)) continue;
+                double p[2];
+                effector_pos(j, p);
+                SpTrans X; X.r = {-p[0], -p[1], 0};
+                SV f = apply_F(X, SV{{0, 0, 0}, {-cur.params[rmForceX], -cur.params[rmForceY], 0}});
+                for (int cur_j = j; cur_j != rRoot; cur_j = sk.parent[cur_j]) {
+                    int o = sk.offset[cur_j];
+                    double t = dot(ctrl_model.J[o], f);
+                    tau[o] += t;
+                    if (cur_j == st_hip) tau[sk.offset[sw_hip]] += -t;
+                }
+            }
+        }
+    }
     // 4x4 linear solve with partial pivoting (stands in for Eigen householderQr().solve on the SPD A^T A + lambda I)
     static void solve4(double A[4][4], double* b, double* x) {
         double M[4][5];
@@ -546,6 +732,7 @@ struct Env {
             vel_r = std::exp(-0.5 * err * err);
             double avg_st = prev_stumble / prev_cycle_time;
             stum_r = 1.0 / (1 + 10 * avg_st);
+            if (sc->is_raptor && avg_vel < 0) { vel_r = 0; stum_r = 0; }   // sim/RaptorController.cpp:583-587
         }
         return 0.8 * vel_r + 0.2 * stum_r;
     }
@@ -644,6 +831,7 @@ struct Env {
     }
     bool collidable(int j) const {
         // tail parts carry collision group "none" (sim/SimDog.cpp:7,21-24)
+        if (sc->is_raptor) return sc->sk.valid_body(j);   // every raptor part collides (sim/SimRaptor.cpp:4-27)
         return sc->sk.valid_body(j) && !(j >= jTail0 && j <= jTail3);
     }
     void physics_substep(double dt, bool last) {
@@ -665,7 +853,9 @@ struct Env {
         ground.rand.seed((unsigned long)terrain_seed);
         rng.seed(rng_seed, (uint64_t)id);
         for (int j = 0; j < s->nj; ++j) pd_target[j] = s->pd[6 * j + 3];
-        cur_tuple.s_beg.assign(283, 0.0); cur_tuple.s_end.assign(283, 0.0); cur_tuple.action.assign(30, 0.0);
+        const int S = kNumGroundSamples + 4 * s->nj - 1;
+        cur_tuple.s_beg.assign(S, 0.0); cur_tuple.s_end.assign(S, 0.0); cur_tuple.action.assign(1 + s->n_opt, 0.0);
+        exp_noise = s->exp_noise;
         poli_state.assign(kNumGroundSamples + 4 * s->nj - 1, 0.0);
         reset();
     }
@@ -678,7 +868,9 @@ struct Env {
         for (int j = 0; j < sk.nj; ++j) contact[j] = false;
         update_kin();
         // controller Reset: cBaseControllerMACE::Reset, cTerrainRLCharController::Reset, cDogController::Reset
+        // (cRaptorController::Reset additionally restores the default stance, sim/RaptorController.cpp:175-182,663-675)
         exp_critic = false; exp_actor = false;
+        stance = 0;
         Action a;
         build_base_action(sc->default_action, a);
         apply_action(a);
@@ -715,9 +907,9 @@ struct Env {
         cur_tuple.reward = calc_reward();
         if (cycle_count > 1) tuples.push_back(cur_tuple);
         cur_tuple.s_beg = cur_tuple.s_end;
-        cur_tuple.action.assign(1 + kDogOptParams, 0.0);   // RecordPoliAction
+        cur_tuple.action.assign(1 + sc->n_opt, 0.0);   // RecordPoliAction
         cur_tuple.action[0] = cur.id;
-        for (int k = 0; k < kDogOptParams; ++k) cur_tuple.action[1 + k] = cur.params[1 + k];
+        for (int k = 0; k < sc->n_opt; ++k) cur_tuple.action[1 + k] = cur.params[sc->opt_idx[k]];
         cur_tuple.flags = 0;
         if (exp_critic) cur_tuple.flags |= (1u << fExpCritic);
         if (exp_actor) cur_tuple.flags |= (1u << fExpActor);
@@ -751,9 +943,7 @@ struct Env {
         }
         fall_contact_counter -= h;                                            // UpdateFallContactCheck
         if (fall_contact_counter <= 0) {
-            bool hc = false;
-            const int parts[9] = {jRoot, jSpine0, jSpine1, jSpine2, jSpine3, jTorso, jNeck0, jNeck1, jHead};
-            for (int i = 0; i < 9; ++i) hc = hc || contact[parts[i]];
+            bool hc = (contact_mask() & sc->fall_mask) != 0;
             const double norm = (1 + 1 / (1 - 0.9));
             sum_fall_contact = (hc ? 1.0 : 0.0) / norm + 0.9 * sum_fall_contact;
             fall_contact_counter = 0.1;

@@ -51,7 +51,8 @@ class Oracle:
         self.ndof = self.L.orc_num_dof(self.h)
         self.nj = self.L.orc_num_joints(self.h)
         self.S = self.L.orc_state_size(self.h)
-        self.A = 30
+        self.A = self.L.orc_action_size(self.h)
+        self.num_params = self.L.orc_num_params(self.h)
 
     def __del__(self):
         if getattr(self, "h", None):
@@ -86,7 +87,7 @@ class Oracle:
         self.L.orc_set_state(self.h, env, _p(q), _p(qd), _p(tau), _p(contact))
 
     def get_ctrl(self, env=0):
-        out = np.zeros(128)
+        out = np.zeros(160)
         n = self.L.orc_get_ctrl(self.h, env, _p(out))
         return out[:n]
 
