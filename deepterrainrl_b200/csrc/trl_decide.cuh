@@ -288,7 +288,7 @@ trl_decide_kernel(Buffers B, NetWeights W, ExpSettings ex, int* done_count) {
         if (boss) {
             // cDogControllerMACE::UpdateAction: exploration flags cleared, off-policy until decided otherwise
             rng = load_rng(L);
-            for (int k = 0; k < kNumParams; ++k) params[k] = L.d(D_PARAMS + k);
+            for (int k = 0; k < m.n_params; ++k) params[k] = L.d(D_PARAMS + k);
             id = L.i(I_ACTION_ID);
             int cmd = L.i(I_CMD);
             if (cmd >= 0) {
@@ -330,12 +330,13 @@ trl_decide_kernel(Buffers B, NetWeights W, ExpSettings ex, int* done_count) {
                 }
                 // BuildActorAction: actor `a`'s 29 outputs overwrite params[1:30] of the current action
                 id = a;
-                for (int k = 0; k < fs; ++k) params[1 + k] = Y[nf + a * fs + k];
+                for (int k = 0; k < fs; ++k) params[m.opt_idx[k]] = Y[nf + a * fs + k];
                 params[mTransTime] = fabs(params[mTransTime]); params[mCv] = fabs(params[mCv]);
+                if (m.char_type == 2) params[rmCd] = fabs(params[rmCd]);
                 if (ex.enable) {
                     double rn = rng.uniform();
                     if (rn < ex.rate) {              // ApplyExpNoiseAction
-                        for (int k = 0; k < fs; ++k) params[1 + k] += (ex.noise * rng.normal()) * (1.0 / m.out_scale_actor0[k]);
+                        for (int k = 0; k < fs; ++k) params[m.opt_idx[k]] += (ex.noise * rng.normal()) * (1.0 / m.out_scale_actor0[k]);
                         eflags |= 2;
                     }
                     if (a != a_max) eflags |= 1;

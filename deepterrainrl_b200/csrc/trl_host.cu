@@ -88,7 +88,31 @@ static int fill_model(trl_handle* h, uint64_t rng_seed) {
     const auto& mf = s.f64("meta_f64");
     int char_type = mi[0], ctrl = mi[1];
     m.nj = mi[8]; m.ndof = mi[9];
-    if (char_type != 1 || m.nj != 21 || m.ndof != 23) return fail("only the dog / goat skeleton (21 joints, 23 dof) is supported in this build");
+    const bool raptor = char_type == 2;
+    if (!((char_type == 1 && m.nj == 21 && m.ndof == 23) || (raptor && m.nj == 19 && m.ndof == 21)))
+        return fail("unsupported character: expected the dog / goat (21 joints) or raptor (19 joints) skeleton");
+    m.char_type = char_type;
+    {
+        // parameter layout and optimised-parameter mask (sim/DogController.cpp:81-121, sim/RaptorController.cpp:78-122)
+        static const bool raptor_mask[37] = {false, true, true, false, false,
+                                             true, false, true, true, true, true, true, true,
+                                             true, false, true, true, true, true, true, true,
+                                             false, false, true, true, true, true, true, true,
+                                             false, false, true, true, true, true, true, true};
+        m.n_params = raptor ? 37 : 30; m.misc_max = raptor ? 5 : 6; m.sp_max = raptor ? 8 : 6;
+        m.n_opt = 0;
+        for (int i = 0; i < m.n_params; ++i)
+            if (raptor ? raptor_mask[i] : (i != 0)) m.opt_idx[m.n_opt++] = i;
+        m.exp_noise = raptor ? 0.15 : 0.2;
+        m.stumble_mask = 0; m.fall_mask = 0;
+        if (raptor) {
+            for (int j = 0; j < m.nj; ++j) if (j != 14 && j != 18 && j != 13 && j != 17) m.stumble_mask |= 1u << j;
+            for (int j : {0, 1, 2, 3, 4, 5}) m.fall_mask |= 1u << j;
+        } else {
+            for (int j = 0; j < m.nj; ++j) if (j != 20 && j != 16 && j != 19 && j != 15) m.stumble_mask |= 1u << j;
+            for (int j : {0, 1, 2, 3, 4, 5, 6, 7, 8}) m.fall_mask |= 1u << j;
+        }
+    }
     h->num_update_steps = mi[2];
     m.num_sim_substeps = mi[3];
     m.has_init_x = mi[4]; m.init_x = mf[2];
@@ -97,7 +121,7 @@ static int fill_model(trl_handle* h, uint64_t rng_seed) {
     m.has_net = mi[7];
     m.n_ctrl = mi[10]; m.n_actions = mi[11]; m.default_action = mi[12]; m.grav_comp = mi[13]; m.virt_forces = mi[14];
     if (m.n_ctrl > kMaxCtrlSets || m.n_actions > kMaxActions) return fail("too many controller sets / actions");
-    m.is_mace = (ctrl == 3 || ctrl == 4) ? 1 : 0;
+    m.is_mace = (ctrl == 3 || ctrl == 4 || ctrl == 7) ? 1 : 0;
     m.target_vel_x = (ctrl == 4) ? 2.0 : 4.0;   // sim/GoatControllerMACE.cpp:11-14, sim/DogController.cpp:625-628
     m.gx = mf[0]; m.gy = mf[1];
     m.exp_mode = h->mode == TRL_MODE_EXPLORE;
@@ -127,7 +151,7 @@ static int fill_model(trl_handle* h, uint64_t rng_seed) {
         m.izz_c[j] = b[1] / 12.0 * (b[6] * b[6] + b[7] * b[7]);
         m.total_mass += b[1];
         // tail parts carry collision group "none" (sim/SimDog.cpp:7,21-24)
-        m.collidable[j] = (j >= 9 && j <= 12) ? 0 : 1;
+        m.collidable[j] = (!raptor && j >= 9 && j <= 12) ? 0 : 1;   // every raptor part collides (sim/SimRaptor.cpp:4-27)
         const double* p = &P[6 * j];
         m.kp[j] = (j == 0) ? 0.0 : p[0]; m.kd[j] = (j == 0) ? 0.0 : p[1];
         m.torque_lim[j] = p[2]; m.target_theta0[j] = p[3]; m.target_vel[j] = p[4]; m.world_pd[j] = p[5] != 0;
@@ -137,13 +161,13 @@ static int fill_model(trl_handle* h, uint64_t rng_seed) {
     for (int j = 0; j < m.nj; ++j) {
         m.depth[j] = (j == 0) ? 0 : m.depth[m.parent[j]] + 1;
         m.max_depth = std::max(m.max_depth, m.depth[j]);
-        for (int c = 0; c < 3; ++c) m.child[j][c] = -1;
+        for (int c = 0; c < 4; ++c) m.child[j][c] = -1;
     }
     if (m.max_depth >= 12) return fail("kinematic tree too deep");
     for (int j = 1; j < m.nj; ++j) {
         int p = m.parent[j], slot = 0;
-        while (slot < 3 && m.child[p][slot] >= 0) ++slot;
-        if (slot == 3) return fail("a link has more than 3 children");
+        while (slot < 4 && m.child[p][slot] >= 0) ++slot;
+        if (slot == 4) return fail("a link has more than 4 children");
         m.child[p][slot] = j;
         m.level_slot[m.depth[j]][slot] = 1;
     }
@@ -166,7 +190,9 @@ static int fill_model(trl_handle* h, uint64_t rng_seed) {
         }
     }
     {
-        const int toe = 20, finger = 16, torso = 5;
+        // effector 0 / 1: dog toe (back foot) / finger (front foot); raptor right toe / left toe.
+        // dog virtual forces stop at the root / torso (sim/DogController.cpp:1014-1016), raptor's at the root (:1053)
+        const int toe = raptor ? 14 : 20, finger = raptor ? 18 : 16, torso = raptor ? 0 : 5;
         m.anc_mask_toe = m.anc_mask_finger = m.vf_mask_toe = m.vf_mask_finger = 0;
         for (int c = toe; c >= 0; c = m.parent[c]) m.anc_mask_toe |= 1u << c;
         for (int c = finger; c >= 0; c = m.parent[c]) m.anc_mask_finger |= 1u << c;
@@ -175,7 +201,7 @@ static int fill_model(trl_handle* h, uint64_t rng_seed) {
     }
     const auto& C = s.f64("ctrl_params");
     for (int c = 0; c < m.n_ctrl; ++c)
-        for (int k = 0; k < kNumParams; ++k) m.ctrl_params[c][k] = C[c * kNumParams + k];
+        for (int k = 0; k < m.n_params; ++k) m.ctrl_params[c][k] = C[c * m.n_params + k];
     const auto& A = s.f64("actions");
     for (int a = 0; a < m.n_actions; ++a) {
         m.act_idx0[a] = (int)A[4 * a]; m.act_idx1[a] = (int)A[4 * a + 1]; m.act_blend[a] = A[4 * a + 2]; m.act_cyclic[a] = A[4 * a + 3] != 0;
@@ -194,7 +220,7 @@ static int fill_model(trl_handle* h, uint64_t rng_seed) {
         for (int i = 0; i < kTerrainParams; ++i) m.terrain_params[i] = (1 - lerp) * tp[i0 * kTerrainParams + i] + lerp * tp[i1 * kTerrainParams + i];
     }
     m.phys = PhysParams{2.0e5, 2.0e3, 0.81, 0.01, 0.00025, 2.0e4, 20.0};
-    h->ex = ExpSettings{h->mode == TRL_MODE_EXPLORE ? 1 : 0, mf[4], mf[5], mf[6], 0.2};
+    h->ex = ExpSettings{h->mode == TRL_MODE_EXPLORE ? 1 : 0, mf[4], mf[5], mf[6], m.exp_noise};
     if (m.has_net) {
         const auto& nd = s.i32("net_dims");
         m.n_in = nd[0]; m.n_char = nd[1]; m.n_out = nd[2]; m.n_frags = nd[3]; m.frag = nd[4];
@@ -282,7 +308,8 @@ trl_handle* trl_create_from_pack(const char* pack_path, int num_envs, int device
     const size_t n = (size_t)num_envs;
     B.n = num_envs;
     B.S = kNumGroundSamples + 4 * h->mc.nj - 1;
-    const int A = kNumParams;
+    B.A = 1 + h->mc.n_opt;
+    const int A = 1 + h->mc.n_opt;
     B.tuple_cap = std::max(4096, num_envs);   // >= one tuple per env per outer update (a cycle lasts >> 20 env-steps)
     B.dist_cap = std::max(65536, 16 * num_envs);
     bool ok = ck(dalloc(h, &B.d, (size_t)D_NUM_FIELDS * n), "alloc d") && ck(dalloc(h, &B.i, (size_t)I_NUM_FIELDS * n), "alloc i") &&
@@ -435,9 +462,9 @@ int trl_set_weights(trl_handle* h, const double* const* blobs, const int64_t* co
 int trl_sizes(trl_handle* h, int* num_envs, int* state, int* action, int* num_frags, int* frag_size, int* num_dof, int* num_joints) {
     if (num_envs) *num_envs = h->n;
     if (state) *state = h->B.S;
-    if (action) *action = kNumParams;
+    if (action) *action = h->B.A;
     if (num_frags) *num_frags = h->mc.n_frags;
-    if (frag_size) *frag_size = kNumParams - 1;
+    if (frag_size) *frag_size = h->mc.n_opt;
     if (num_dof) *num_dof = h->mc.ndof;
     if (num_joints) *num_joints = h->mc.nj;
     return 0;
@@ -448,7 +475,7 @@ static int fetch_tuples(trl_handle* h, int* n_out) {
     CK(cudaMemcpyAsync(&n, h->B.tuple_count, 4, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     if (n > h->B.tuple_cap) n = h->B.tuple_cap;
-    const size_t W = 1 + h->B.S + kNumParams + h->B.S;
+    const size_t W = 1 + h->B.S + h->B.A + h->B.S;
     h->h_tuples.resize((size_t)std::max(n, 1) * W);
     h->h_tuple_flags.resize(std::max(n, 1));
     h->h_tuple_env.resize(std::max(n, 1));
@@ -478,7 +505,7 @@ int trl_get_tuples_f64(trl_handle* h, const double** rows, const uint32_t** flag
 
 int trl_get_tuples(trl_handle* h, const float** rows, const uint32_t** flags, const int32_t** env_id, int* n) {
     if (fetch_tuples(h, n)) return 1;
-    const size_t W = 1 + h->B.S + kNumParams + h->B.S;
+    const size_t W = 1 + h->B.S + h->B.A + h->B.S;
     h->h_tuples_f32.resize((size_t)std::max(*n, 1) * W);
     for (size_t k = 0; k < (size_t)*n * W; ++k) h->h_tuples_f32[k] = (float)h->h_tuples[k];
     *rows = h->h_tuples_f32.data(); *flags = h->h_tuple_flags.data(); *env_id = h->h_tuple_env.data();
@@ -587,11 +614,11 @@ int trl_get_ctrl(trl_handle* h, int env, double* out, int cap, int* n_out) {
     o.push_back(iv[I_STATE]); o.push_back(d[D_PHASE]); o.push_back(iv[I_FIRST_CYCLE]); o.push_back(d[D_CUR_CYCLE_T]);
     o.push_back(d[D_PREV_CYCLE_T]); o.push_back(d[D_CUR_STUMBLE]); o.push_back(d[D_PREV_STUMBLE]); o.push_back(d[D_PREV_COM_X]);
     o.push_back(d[D_PREV_COM_Y]); o.push_back(d[D_PREV_DIST_X]); o.push_back(d[D_PREV_DIST_Y]); o.push_back(iv[I_ACTION_ID]);
-    for (int k = 0; k < kNumParams; ++k) o.push_back(d[D_PARAMS + k]);
+    for (int k = 0; k < h->mc.n_params; ++k) o.push_back(d[D_PARAMS + k]);
     for (int j = 0; j < h->mc.nj; ++j) o.push_back(d[D_PD_TARGET + j]);
     o.push_back(d[D_FALL_DIST_CNT]); o.push_back(d[D_FALL_CONTACT_CNT]); o.push_back(d[D_SUM_FALL]); o.push_back(d[D_PREV_CHECK_X]);
     o.push_back(d[D_PREV_CHECK_Y]); o.push_back(iv[I_FAIL_FALL_DIST]); o.push_back(iv[I_EXP_FLAGS] & 1); o.push_back((iv[I_EXP_FLAGS] >> 1) & 1);
-    o.push_back(iv[I_CYCLE_COUNT]);
+    o.push_back(iv[I_CYCLE_COUNT]); o.push_back(iv[I_STANCE]);
     int n = (int)std::min<size_t>(o.size(), (size_t)cap);
     std::memcpy(out, o.data(), (size_t)n * 8);
     if (n_out) *n_out = n;
@@ -699,7 +726,7 @@ int trl_device_tuple_block(trl_handle* h, void** rows_f64, void** flags_u32, voi
     if (env_i32) *env_i32 = h->B.tuple_env;
     if (count_i32) *count_i32 = h->B.tuple_count;
     if (cap) *cap = h->B.tuple_cap;
-    if (width) *width = 1 + h->B.S + kNumParams + h->B.S;
+    if (width) *width = 1 + h->B.S + h->B.A + h->B.S;
     return 0;
 }
 

@@ -61,6 +61,14 @@ enum DogJoint {
     jRoot, jSpine0, jSpine1, jSpine2, jSpine3, jTorso, jNeck0, jNeck1, jHead, jTail0, jTail1, jTail2, jTail3,
     jShoulder, jElbow, jWrist, jFinger, jHip, jKnee, jAnkle, jToe
 };
+// raptor joint indices (sim/SimRaptor.h:11-33) and controller layout (sim/RaptorController.h:14-47)
+enum RaptorJoint {
+    rRoot, rSpine0, rSpine1, rSpine2, rSpine3, rHead, rTail0, rTail1, rTail2, rTail3, rTail4,
+    rRightHip, rRightKnee, rRightAnkle, rRightToe, rLeftHip, rLeftKnee, rLeftAnkle, rLeftToe
+};
+enum { rsContact, rsDown, rsPassing, rsUp };
+enum { rmTransTime, rmCv, rmCd, rmForceX, rmForceY };
+enum { rpRootPitch, rpSpineCurve, rpStanceHip, rpStanceKnee, rpStanceAnkle, rpSwingHip, rpSwingKnee, rpSwingAnkle };
 enum { sBackStance, sExtend, sFrontStance, sGather };
 enum { mTransTime, mCv, mBackForceX, mBackForceY, mFrontForceX, mFrontForceY, mMiscMax };
 enum { spSpineCurve, spShoulder, spElbow, spHip, spKnee, spAnkle, spMax };
@@ -103,9 +111,19 @@ __device__ __forceinline__ bool has_fallen(Lane& L, double root_theta) {
     return L.d(D_SUM_FALL) > 0.25 || L.i(I_FAIL_FALL_DIST) != 0 || fabs(wrap_pi(root_theta)) > 3.14159265358979323846 * 0.8;
 }
 
-// cDogController::SetStateParams for the current state (sim/DogController.cpp:1042-1054)
+// cDogController::SetStateParams (sim/DogController.cpp:1042-1054) / cRaptorController::SetStateParams
+// (sim/RaptorController.cpp:1108-1125) for the given state
 __device__ void set_state_params(Lane& L, int state) {
-    int base = D_PARAMS + mMiscMax + state * spMax;
+    const ModelConst& m = c_model;
+    int base = D_PARAMS + m.misc_max + state * m.sp_max;
+    if (m.char_type == 2) {
+        const int st = L.i(I_STANCE) == 0 ? rRightHip : rLeftHip, sw = L.i(I_STANCE) == 0 ? rLeftHip : rRightHip;
+        L.d(D_PD_TARGET + st) = L.d(base + rpStanceHip); L.d(D_PD_TARGET + st + 1) = L.d(base + rpStanceKnee);
+        L.d(D_PD_TARGET + st + 2) = L.d(base + rpStanceAnkle);
+        L.d(D_PD_TARGET + sw) = L.d(base + rpSwingHip); L.d(D_PD_TARGET + sw + 1) = L.d(base + rpSwingKnee);
+        L.d(D_PD_TARGET + sw + 2) = L.d(base + rpSwingAnkle);
+        return;
+    }
     double sc = L.d(base + spSpineCurve);
     L.d(D_PD_TARGET + jSpine0) = sc; L.d(D_PD_TARGET + jSpine1) = sc; L.d(D_PD_TARGET + jSpine2) = sc;
     L.d(D_PD_TARGET + jSpine3) = sc; L.d(D_PD_TARGET + jTorso) = sc;
@@ -126,6 +144,7 @@ __device__ double calc_reward(Lane& L, bool fallen) {
         vel_r = exp(-0.5 * err * err);
         double avg_st = L.d(D_PREV_STUMBLE) / ct;
         stum_r = 1.0 / (1.0 + 10.0 * avg_st);
+        if (c_model.char_type == 2 && avg_vel < 0.0) { vel_r = 0.0; stum_r = 0.0; }   // sim/RaptorController.cpp:583-587
     }
     return 0.8 * vel_r + 0.2 * stum_r;
 }
@@ -133,7 +152,7 @@ __device__ double calc_reward(Lane& L, bool fallen) {
 // cScenarioExp::NewCycleUpdate (scenarios/ScenarioExp.cpp:209-243): finish the previous tuple, start the next.
 // Cooperative: the row copies are spread over the warp, the scalar bookkeeping is done by lane 0.
 __device__ void exp_new_cycle_update(Lane& L, const Buffers& B, bool fallen, int lane) {
-    const int S = B.S, A = 1 + (kNumParams - 1);
+    const int S = B.S, A = B.A;
     const double* s_end = B.poli_state + (size_t)L.env * S;
     double* s_beg = B.tuple_sbeg + (size_t)L.env * S;
     double* act = B.tuple_action + (size_t)L.env * kNumParams;
@@ -154,7 +173,7 @@ __device__ void exp_new_cycle_update(Lane& L, const Buffers& B, bool fallen, int
     }
     __syncwarp();
     for (int k = lane; k < S; k += kWarp) s_beg[k] = s_end[k];
-    for (int k = lane; k < kNumParams; k += kWarp) act[k] = (k == 0) ? (double)L.i(I_ACTION_ID) : L.d(D_PARAMS + k);
+    for (int k = lane; k < A; k += kWarp) act[k] = (k == 0) ? (double)L.i(I_ACTION_ID) : L.d(D_PARAMS + c_model.opt_idx[k - 1]);
     if (lane == 0) {
         int ef = L.i(I_EXP_FLAGS);
         unsigned nf = 0;
@@ -171,9 +190,9 @@ __device__ int build_base_action(Lane& L, CounterRng& rng, int a, double* params
     const ModelConst& m = c_model;
     int i0 = m.act_idx0[a], i1 = m.act_idx1[a];
     double blend = m.act_blend[a];
-    for (int k = 0; k < kNumParams; ++k) {
+    for (int k = 0; k < m.n_params; ++k) {
         double p0 = m.ctrl_params[i0][k], p1 = m.ctrl_params[i1][k];
-        if (k == mTransTime || k == mCv) { p0 = fabs(p0); p1 = fabs(p1); }
+        if (k == mTransTime || k == mCv || (m.char_type == 2 && k == rmCd)) { p0 = fabs(p0); p1 = fabs(p1); }
         params[k] = (1.0 - blend) * p0 + blend * p1;
     }
     int id = a;
@@ -197,9 +216,10 @@ __device__ int build_base_action(Lane& L, CounterRng& rng, int a, double* params
 
 // cTerrainRLCharController::ApplyAction + cDogController::{NewCycleUpdate, ApplyAction}: commit an action
 __device__ void apply_action(Lane& L, int id, const double* params, double comx, double comy) {
-    for (int k = 0; k < kNumParams; ++k) L.d(D_PARAMS + k) = params[k];
+    for (int k = 0; k < c_model.n_params; ++k) L.d(D_PARAMS + k) = params[k];
     L.d(D_PARAMS + mTransTime) = fabs(params[mTransTime]);
     L.d(D_PARAMS + mCv) = fabs(params[mCv]);
+    if (c_model.char_type == 2) L.d(D_PARAMS + rmCd) = fabs(params[rmCd]);
     L.i(I_ACTION_ID) = id;
     L.d(D_PREV_CYCLE_T) = L.d(D_CUR_CYCLE_T); L.d(D_CUR_CYCLE_T) = 0.0;
     L.d(D_PREV_STUMBLE) = L.d(D_CUR_STUMBLE); L.d(D_CUR_STUMBLE) = 0.0;
@@ -241,7 +261,7 @@ __device__ void store_rng(Lane& L, const CounterRng& r) {
 // Per-lane constants of link `lane` and the env state held in registers.
 struct LinkC {
     int act;            // lane < nj
-    int parent, depth, child0, child1, child2;
+    int parent, depth, child0, child1, child2, child3;
     int anc1, anc2, anc4, anc8;   // 2^k-th ancestors (-1 = none) for the pointer-jumping prefix sums
     double ax, ay;      // attach point in the parent's joint frame
     double mass, bax, bay, izz_c;
@@ -268,6 +288,7 @@ __device__ __forceinline__ LinkC load_link(int lane) {
     c.child0 = c.act ? m.child[j][0] : -1;
     c.child1 = c.act ? m.child[j][1] : -1;
     c.child2 = c.act ? m.child[j][2] : -1;
+    c.child3 = c.act ? m.child[j][3] : -1;
     c.anc1 = c.act ? m.anc_pow[j][0] : -1; c.anc2 = c.act ? m.anc_pow[j][1] : -1;
     c.anc4 = c.act ? m.anc_pow[j][2] : -1; c.anc8 = c.act ? m.anc_pow[j][3] : -1;
     c.ax = m.attach_x[j]; c.ay = m.attach_y[j];
@@ -315,9 +336,9 @@ __device__ __forceinline__ Kin kinematics(const LinkC& c, const EnvRegs& e) {
 // children -> parent accumulation of NV register values for tree level l (deterministic slot order)
 #define TRL_ACCUM_LEVEL(l, NV, vals)                                                        \
     do {                                                                                    \
-        _Pragma("unroll") for (int s_ = 0; s_ < 3; ++s_) {                                  \
+        _Pragma("unroll") for (int s_ = 0; s_ < 4; ++s_) {                                  \
             if (!c_model.level_slot[(l)][s_]) continue;                                     \
-            int ch_ = (s_ == 0) ? lc.child0 : ((s_ == 1) ? lc.child1 : lc.child2);          \
+            int ch_ = (s_ == 0) ? lc.child0 : ((s_ == 1) ? lc.child1 : ((s_ == 2) ? lc.child2 : lc.child3)); \
             int src_ = ch_ >= 0 ? ch_ : 0;                                                  \
             bool take_ = (ch_ >= 0) && (lc.depth == (l)-1);                                 \
             _Pragma("unroll") for (int v_ = 0; v_ < (NV); ++v_) {                           \
@@ -399,12 +420,26 @@ __device__ double controller_torque(Lane& L, const LinkC& lc, const EnvRegs& e, 
     }
     __syncwarp();
 
-    // ---- ApplyFeedback (sim/DogController.cpp:903-945): COM velocity of the whole character
+    // ---- ApplyFeedback (sim/DogController.cpp:903-945) / ApplySwingFeedback (sim/RaptorController.cpp:907-931)
     const int state = L.i(I_STATE);
+    const bool raptor = m.char_type == 2;
+    const int stance = raptor ? L.i(I_STANCE) : 0;
+    const int st_hip = stance == 0 ? rRightHip : rLeftHip, sw_hip = stance == 0 ? rLeftHip : rRightHip, st_toe = st_hip + 3;
+    // cRaptorController::IsActiveVFEffector(stance toe): stance foot on the ground during Contact / Down
+    const bool active_vf = raptor && (state == rsContact || state == rsDown) && ((contact >> st_toe) & 1);
     {
         double bvx = lc.mass * (k.vx - k.w * k.cy);
         double comvx = warp_sum_all(bvx) / m.total_mass;
-        if (lane == 0) {
+        if (raptor) {
+            double comx = warp_sum_all(lc.mass * k.cx) / m.total_mass;
+            double toe_x = shf(k.cx, st_toe);
+            if (lane == 0) {
+                bool first_half = state == rsContact || state == rsDown;
+                double cd = first_half ? 0.0 : L.d(D_PARAMS + rmCd), cv = first_half ? L.d(D_PARAMS + rmCv) : 0.0;
+                int base = D_PARAMS + m.misc_max + state * m.sp_max;
+                L.d(D_PD_TARGET + sw_hip) = L.d(base + rpSwingHip) + (cd * (comx - toe_x) + cv * comvx);
+            }
+        } else if (lane == 0) {
             double cv = L.d(D_PARAMS + mCv);
             int base = D_PARAMS + mMiscMax + state * spMax;
             if (!((contact >> jToe) & 1)) L.d(D_PD_TARGET + jHip) = L.d(base + spHip) + comvx * cv;
@@ -413,8 +448,10 @@ __device__ double controller_torque(Lane& L, const LinkC& lc, const EnvRegs& e, 
         __syncwarp();
     }
 
-    // ---- cImpPDController::CalcControlForces (sim/ImpPDController.cpp:234-278)
-    double tau0 = 0.0, rhs_link = 0.0, kd_link = 0.0;
+    // ---- cImpPDController::CalcControlForces (sim/ImpPDController.cpp:234-278); the raptor's stance hip PD is
+    // switched off while its foot is an active virtual-force effector (UpdateStanceHip, sim/RaptorController.cpp:899-905):
+    // zero gains in the torque law, but its Kd stays on the diagonal of the solved system
+    double tau0 = 0.0, rhs_link = 0.0, kd_link = 0.0, kd_eff = 0.0;
     if (lc.act && lane > 0) {
         double theta = e.q;
         if (m.world_pd[lane]) {
@@ -424,9 +461,11 @@ __device__ double controller_torque(Lane& L, const LinkC& lc, const EnvRegs& e, 
             double a = acos(fmin(1.0, fmax(-1.0, c)));
             theta = (s >= 0) ? a : -a;
         }
+        const bool pd_on = !(active_vf && lane == st_hip);
         kd_link = m.kd[lane];
+        kd_eff = pd_on ? kd_link : 0.0;
         double perr = L.d(D_PD_TARGET + lane) - theta, verr = m.target_vel[lane] - e.qd;
-        tau0 = m.kp[lane] * (perr - h * e.qd) + kd_link * verr;
+        tau0 = pd_on ? (m.kp[lane] * (perr - h * e.qd) + kd_link * verr) : 0.0;
         rhs_link = tau0 - Cj;
     }
     // dof-lane view: lane d holds row d of (M + h Kd) and rhs_d
@@ -449,6 +488,7 @@ __device__ double controller_torque(Lane& L, const LinkC& lc, const EnvRegs& e, 
 #pragma unroll
     for (int j = 0; j < kMaxDof; ++j) {
         double dj = shf(row[j], j);
+        if (j >= nd) dj = 1.0;            // padding rows of a smaller character (raptor: 21 dof)
         double inv = 1.0 / dj;
         if (lane == j) diag = dj;
         double aij = row[j];              // A_ij before scaling (valid for lanes i > j)
@@ -479,20 +519,24 @@ __device__ double controller_torque(Lane& L, const LinkC& lc, const EnvRegs& e, 
     double tau = 0.0;
     {
         double acc_link = shf(acc, lane + 2 < kWarp ? lane + 2 : 0);
-        if (lc.act && lane > 0) tau = tau0 - kd_link * h * acc_link;
+        if (lc.act && lane > 0) tau = tau0 - kd_eff * h * acc_link;
     }
 
-    // ---- ApplyGravityCompensation (sim/DogController.cpp:947-995, 1120-1175)
-    const bool toe_c = (contact >> jToe) & 1, fin_c = (contact >> jFinger) & 1;
-    // foot bottom-centre positions (cDogController::GetEndEffectorContactPos), relative to O
+    // ---- ApplyGravityCompensation (sim/DogController.cpp:947-995, 1120-1175; sim/RaptorController.cpp:983-1026)
+    // effector 0 / 1: dog back foot (toe) / front foot (finger); raptor right / left toe.  A dog foot supports when
+    // it touches the ground, a raptor foot only while it is the active virtual-force effector.
+    const int eff0 = raptor ? (int)rRightToe : (int)jToe, eff1 = raptor ? (int)rLeftToe : (int)jFinger;
+    const bool toe_c = raptor ? (active_vf && stance == 0) : (((contact >> jToe) & 1) != 0);
+    const bool fin_c = raptor ? (active_vf && stance == 1) : (((contact >> jFinger) & 1) != 0);
+    // foot bottom-centre positions (GetEndEffectorContactPos), relative to O
     double ex[2], ey[2];
     {
         double bc = k.cw * m.body_cos[lc.act ? lane : 0] - k.sw * m.body_sin[lc.act ? lane : 0];
         double bs = k.sw * m.body_cos[lc.act ? lane : 0] + k.cw * m.body_sin[lc.act ? lane : 0];
         double ly = -m.half_y[lc.act ? lane : 0];
         double px = k.cx - bs * ly, py = k.cy + bc * ly;
-        ex[0] = shf(px, jToe); ey[0] = shf(py, jToe);
-        ex[1] = shf(px, jFinger); ey[1] = shf(py, jFinger);
+        ex[0] = shf(px, eff0); ey[0] = shf(py, eff0);
+        ex[1] = shf(px, eff1); ey[1] = shf(py, eff1);
     }
     if (m.grav_comp && (toe_c || fin_c)) {
         // tau_g = -G,  G_k = (sum_subtree m (c - r_k)) x g   (generalised gravity force, sim/RBDUtil.cpp:850-895)
@@ -502,7 +546,9 @@ __device__ double controller_torque(Lane& L, const LinkC& lc, const EnvRegs& e, 
         else tg = -((mhx - ms * k.rx) * m.gy - (mhy - ms * k.ry) * m.gx);
         const double ms0 = shf(ms, 0), mhx0 = shf(mhx, 0), mhy0 = shf(mhy, 0);
         const double b0 = -(ms0 * m.gx), b1 = -(ms0 * m.gy), b2 = -(mhx0 * m.gy - mhy0 * m.gx);
-        // basis columns [toe +y, toe +x, finger +y, finger +x]; root rows = (Fx, Fy, r x F)
+        // root-row weights of the ridge least squares: identity for the dog, (1e-4, 1e-4, 1) for the raptor
+        const double W0 = raptor ? 0.0001 : 1.0, W1 = raptor ? 0.0001 : 1.0, W2 = 1.0;
+        // basis columns [eff0 +y, eff0 +x, eff1 +y, eff1 +x]; root rows = (Fx, Fy, r x F)
         double Ar[3][4];
 #pragma unroll
         for (int e2 = 0; e2 < 2; ++e2) {
@@ -515,9 +561,9 @@ __device__ double controller_torque(Lane& L, const LinkC& lc, const EnvRegs& e, 
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
 #pragma unroll
-            for (int b = 0; b < 4; ++b) A[a][b] = Ar[0][a] * Ar[0][b] + Ar[1][a] * Ar[1][b] + Ar[2][a] * Ar[2][b];
+            for (int b = 0; b < 4; ++b) A[a][b] = Ar[0][a] * W0 * Ar[0][b] + Ar[1][a] * W1 * Ar[1][b] + Ar[2][a] * W2 * Ar[2][b];
             A[a][a] += 0.0001;
-            A[a][4] = Ar[0][a] * b0 + Ar[1][a] * b1 + Ar[2][a] * b2;
+            A[a][4] = Ar[0][a] * W0 * b0 + Ar[1][a] * W1 * b1 + Ar[2][a] * W2 * b2;
         }
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -554,8 +600,31 @@ __device__ double controller_torque(Lane& L, const LinkC& lc, const EnvRegs& e, 
         }
     }
 
-    // ---- ApplyVirtualForces (sim/DogController.cpp:997-1029)
-    if (m.virt_forces && lc.act && lane > 0) {
+    // ---- ApplyStanceFeedback (sim/RaptorController.cpp:933-981): the stance hip balances the swing hip's torque and
+    // a PD on the root pitch while its foot pushes
+    if (raptor) {
+        const double sw_tau = shf(tau, sw_hip), th0 = shf(e.q, 0), thd0 = shf(e.qd, 0);
+        if (active_vf && lane == st_hip) {
+            int base = D_PARAMS + m.misc_max + state * m.sp_max;
+            double root_tau = m.kp[st_hip] * (L.d(base + rpRootPitch) - wrap_pi(th0)) + m.kd[st_hip] * (-thd0);
+            tau += -sw_tau - root_tau;
+        }
+    }
+
+    // ---- ApplyVirtualForces (sim/DogController.cpp:997-1029; sim/RaptorController.cpp:1028-1075)
+    if (m.virt_forces && raptor) {
+        // only the stance toe can be active; the chain runs up to (excluding) the root and the stance hip's share is
+        // mirrored onto the swing hip
+        const bool on = active_vf;
+        const int e2 = stance;
+        double fx = -L.d(D_PARAMS + rmForceX), fy = -L.d(D_PARAMS + rmForceY);
+        unsigned mask = e2 == 0 ? m.vf_mask_toe : m.vf_mask_finger;
+        double t = 0.0;
+        if (on && lc.act && ((mask >> lane) & 1)) t = (ex[e2] - k.rx) * fy - (ey[e2] - k.ry) * fx;
+        double t_hip = shf(t, st_hip);
+        tau += t;
+        if (on && lane == sw_hip) tau -= t_hip;
+    } else if (m.virt_forces && lc.act && lane > 0) {
         if ((state == sBackStance || state == sExtend) && toe_c && ((m.vf_mask_toe >> lane) & 1)) {
             double fx = -L.d(D_PARAMS + mBackForceX), fy = -L.d(D_PARAMS + mBackForceY);
             tau += (ex[0] - k.rx) * fy - (ey[0] - k.ry) * fx;
@@ -725,7 +794,7 @@ __device__ int physics_substep(const LinkC& lc, EnvRegs& e, const GroundView& g,
 
 // cTerrainRLCharController::ParseGround + BuildPoliState (sim/TerrainRLCharController.cpp:168-285), cooperative
 __device__ void build_poli_state(const LinkC& lc, const EnvRegs& e, const Kin& k, const Buffers& B, const GroundView& g, int env,
-                                 int lane) {
+                                 int lane, int stance) {
     const ModelConst& m = c_model;
     double* out = B.poli_state + (size_t)env * B.S;
     const double oy = g.sample(e.ox);
@@ -735,13 +804,17 @@ __device__ void build_poli_state(const LinkC& lc, const EnvRegs& e, const Kin& k
     }
     if (lane == 0) out[kNumGroundSamples] = e.oy - oy;
     if (lc.act) {
+        // raptor: when the left leg is the stance leg the two legs' entries are swapped
+        // (cRaptorController::FlipPoliPoseStance, sim/RaptorController.cpp:1414-1432,1469-1487)
+        int slot = lane;
+        if (m.char_type == 2 && stance != 0 && lane >= rRightHip) slot = lane < rLeftHip ? lane + 4 : lane - 4;
         if (lane > 0) {
-            out[kNumGroundSamples + 1 + 2 * (lane - 1)] = k.cx;       // body COM relative to the root joint position
-            out[kNumGroundSamples + 1 + 2 * (lane - 1) + 1] = k.cy;
+            out[kNumGroundSamples + 1 + 2 * (slot - 1)] = k.cx;       // body COM relative to the root joint position
+            out[kNumGroundSamples + 1 + 2 * (slot - 1) + 1] = k.cy;
         }
         int vo = kNumGroundSamples + 2 * m.nj - 1;
-        out[vo + 2 * lane] = k.vx - k.w * k.cy;                       // body COM velocity
-        out[vo + 2 * lane + 1] = k.vy + k.w * k.cx;
+        out[vo + 2 * slot] = k.vx - k.w * k.cy;                       // body COM velocity
+        out[vo + 2 * slot + 1] = k.vy + k.w * k.cx;
     }
 }
 
@@ -763,6 +836,7 @@ __device__ void reset_env(Lane& L, const LinkC& lc, EnvRegs& e, const Buffers& B
         // controller reset: default action, FSM state 0, counters zeroed (sim/TerrainRLCharController.cpp:47-58,
         // sim/DogController.cpp:210-216,640-650)
         double params[kNumParams];
+        L.i(I_STANCE) = 0;   // cRaptorController::Reset -> SetStance(gDefaultStance)
         int id = build_base_action(L, rng, m.default_action, params);
         apply_action(L, id, params, comx, comy);
         L.i(I_EXP_FLAGS) = 0;
@@ -848,9 +922,7 @@ trl_step_kernel(Buffers B, double h, int flags) {
             L.d(D_FALL_DIST_CNT) = cnt;
             double cc = L.d(D_FALL_CONTACT_CNT) - h;
             if (cc <= 0.0) {
-                const int fall_mask = (1 << jRoot) | (1 << jSpine0) | (1 << jSpine1) | (1 << jSpine2) | (1 << jSpine3) |
-                                      (1 << jTorso) | (1 << jNeck0) | (1 << jNeck1) | (1 << jHead);
-                double val = (contact & fall_mask) ? 1.0 : 0.0;
+                double val = ((unsigned)contact & m.fall_mask) ? 1.0 : 0.0;
                 const double norm = (1.0 + 1.0 / (1.0 - 0.9));
                 L.d(D_SUM_FALL) = val / norm + 0.9 * L.d(D_SUM_FALL);
                 cc = 0.1;
@@ -915,27 +987,39 @@ trl_step_kernel(Buffers B, double h, int flags) {
         if (lane == 0) {
             L.i(I_CONTACT) = contact;
             L.d(D_CUR_CYCLE_T) += h;
-            const int stumble_mask = ~((1 << jToe) | (1 << jFinger) | (1 << jAnkle) | (1 << jWrist));
-            if (contact & stumble_mask) L.d(D_CUR_STUMBLE) += h;
+            if ((unsigned)contact & m.stumble_mask) L.d(D_CUR_STUMBLE) += h;
             int state = L.i(I_STATE);
             int first = L.i(I_FIRST_CYCLE);
             double phase = L.d(D_PHASE) + h / L.d(D_PARAMS + mTransTime);
             bool advance = first != 0;
-            if ((state == sBackStance || state == sFrontStance) && phase >= 1.0) advance = true;
-            if (state == sExtend && ((contact >> jFinger) & 1)) advance = true;
-            if (state == sGather && ((contact >> jToe) & 1)) advance = true;
+            int ns2;
+            if (m.char_type == 2) {
+                // cRaptorController::UpdateState (sim/RaptorController.cpp:804-849): Contact, Down, Passing are timed,
+                // Up ends when the swing toe touches down; the stance flips at the end of every cycle but the first
+                const int sw_toe = (L.i(I_STANCE) == 0 ? rLeftHip : rRightHip) + 3;
+                if (state != rsUp && phase >= 1.0) advance = true;
+                if (state == rsUp && ((contact >> sw_toe) & 1)) advance = true;
+                ns2 = first ? rsContact : (state == rsUp ? -1 : state + 1);
+            } else {
+                if ((state == sBackStance || state == sFrontStance) && phase >= 1.0) advance = true;
+                if (state == sExtend && ((contact >> jFinger) & 1)) advance = true;
+                if (state == sGather && ((contact >> jToe) & 1)) advance = true;
+                ns2 = first ? sBackStance : (state == sGather ? -1 : state + 1);
+            }
             L.d(D_PHASE) = phase;
             if (advance) {
-                int ns2 = first ? sBackStance : (state == sGather ? -1 : state + 1);
-                if ((ns2 < 0) || first) end_step = 1;
-                else { L.i(I_STATE) = ns2; L.d(D_PHASE) = 0.0; set_state_params(L, ns2); }
+                if ((ns2 < 0) || first) {
+                    end_step = 1;
+                    if (m.char_type == 2 && !first) L.i(I_STANCE) = 1 - L.i(I_STANCE);   // FlipStance
+                } else { L.i(I_STATE) = ns2; L.d(D_PHASE) = 0.0; set_state_params(L, ns2); }
             }
         }
         end_step = shfi(end_step, 0);
+        __syncwarp();
         if (end_step) {
             // cycle boundary: build the policy state and hand the env to the decision kernel
             Kin k = kinematics(lc, e);
-            build_poli_state(lc, e, k, B, g, env, lane);
+            build_poli_state(lc, e, k, B, g, env, lane, m.char_type == 2 ? L.i(I_STANCE) : 0);
             double comx = e.ox + warp_sum_all(lc.mass * k.cx) / m.total_mass;
             double comy = e.oy + warp_sum_all(lc.mass * k.cy) / m.total_mass;
             if (lane == 0) {

@@ -12,7 +12,7 @@ namespace trl {
 
 constexpr int kMaxJoints = 21;      // dog / goat: 21 joints, raptor: 19
 constexpr int kMaxDof = 23;
-constexpr int kNumParams = 30;      // gait controller parameter vector (sim/DogController.h:14-46)
+constexpr int kNumParams = 37;      // max gait controller parameter vector: dog 30 (sim/DogController.h:14-46), raptor 37 (sim/RaptorController.h:14-47)
 constexpr int kNumGroundSamples = 200;
 constexpr int kTerrainCap = 512;    // floats per terrain segment (20 m nominal + overshoot + 2 m pad at 0.1 m)
 constexpr int kTerrainParams = 40;
@@ -44,6 +44,7 @@ enum IField : int {
     I_CYCLE_COUNT, I_EPISODE_COUNT, I_PENDING, I_CMD,
     I_SEG_N0, I_SEG_N1, I_SEG_FLIP, I_TERRAIN_RNG,   // minstd_rand0 state of the env's terrain generator
     I_TUPLE_FLAGS, I_RNG_CTR_LO, I_RNG_CTR_HI, I_STEPS_LO, I_STEPS_HI,
+    I_STANCE,           // raptor: 0 = right leg is the stance leg, 1 = left
     I_NUM_FIELDS
 };
 
@@ -69,9 +70,9 @@ struct ModelConst {
     double total_mass;
     // tree topology helpers for the level-synchronous warp passes
     int depth[kMaxJoints], max_depth;
-    int child[kMaxJoints][3];              // up to 3 children per link (-1 = none)
+    int child[kMaxJoints][4];              // up to 4 children per link (-1 = none)
     int anc_pow[kMaxJoints][4];            // 2^k-th ancestor of each link (k = 0..3), -1 if it does not exist
-    int level_slot[12][3];                 // level_slot[l][s] != 0: some link at depth l is child slot s of its parent
+    int level_slot[12][4];                 // level_slot[l][s] != 0: some link at depth l is child slot s of its parent
     int n_corners;                         // 4 * number of collidable bodies
     int corner_body[4 * kMaxJoints];
     double corner_lx[4 * kMaxJoints], corner_ly[4 * kMaxJoints];   // corner position in the link (joint) frame
@@ -82,6 +83,11 @@ struct ModelConst {
     double kp[kMaxJoints], kd[kMaxJoints], torque_lim[kMaxJoints], target_theta0[kMaxJoints], target_vel[kMaxJoints];
     int world_pd[kMaxJoints];
     // gait controller
+    int char_type;                         // 1 dog / goat, 2 raptor
+    int n_params, n_opt, misc_max, sp_max;  // parameter vector layout (30/29/6/6 dog, 37/28/5/8 raptor)
+    int opt_idx[kNumParams];               // indices of the optimised parameters (= actor outputs)
+    unsigned stumble_mask, fall_mask;      // parts whose ground contact counts as a stumble / towards a fall
+    double exp_noise;                      // exploration noise std (sim/DogControllerMACE.cpp:3-9, RaptorControllerMACE.cpp:7)
     int n_ctrl, n_actions, default_action, grav_comp, virt_forces, is_mace;
     double ctrl_params[kMaxCtrlSets][kNumParams];
     int act_idx0[kMaxActions], act_idx1[kMaxActions], act_cyclic[kMaxActions];
@@ -141,6 +147,7 @@ struct Buffers {
     int* dist_count;       // [1]
     int dist_cap;
     int S;                 // policy state size
+    int A;                 // action record size (1 + number of optimised parameters)
 };
 
 }  // namespace trl

@@ -148,9 +148,9 @@ class BatchedScenario:
         return q, qd
 
     def GetCtrl(self, env=0):
-        out = np.zeros(128)
+        out = np.zeros(160)
         n = C.c_int(0)
-        self._ck(self.L.trl_get_ctrl(self.h, env, _p(out), 128, C.byref(n)))
+        self._ck(self.L.trl_get_ctrl(self.h, env, _p(out), 160, C.byref(n)))
         return out[:n.value]
 
     def GetPoliState(self, env=0):

@@ -40,6 +40,44 @@ def test_goat_cliffs_parity(assets):
     assert g._stats()["episodes"] == o.eval_stats()["episodes"]
 
 
+def test_raptor_narrow_gaps_parity(assets):
+    """BASELINE config 3 (raptor + narrow_gaps, MACE policy): per-step state / controller parity over 600 env-steps,
+    then 3 s of the update loop incl. falls (stance flips, leg-swapped policy state, gated stance-hip PD)."""
+    from pyoracle import Oracle
+    import deepterrainrl_b200 as trl
+    pack = os.path.join(assets, "raptor_narrow_gaps.trlpack")
+    n = 8
+    g = trl.ScenarioPoliEval(pack, n)
+    o = Oracle(pack, n, 0)
+    assert g.state_size == 275 and g.num_dof == 21 and g.num_joints == 19
+    worst = 0.0
+    for k in range(600):
+        g.EnvStep(H)
+        for e in range(n):
+            o.env_step(e, H)
+        if k % 25 == 24 or k < 3:
+            for e in range(n):
+                gq, gqd, gt, gc = g.GetState(e)
+                oq, oqd, ot, oc = o.get_state(e)
+                worst = max(worst, _relerr(gq, oq), _relerr(gqd, oqd))
+                assert _relerr(gq, oq) < 1e-4 and _relerr(gqd, oqd) < 1e-4, (k, e)
+                assert _relerr(gt, ot) < 1e-4, (k, e)
+                np.testing.assert_array_equal(gc, oc)
+                gctl, octl = g.GetCtrl(e), o.get_ctrl(e)
+                assert gctl.size == octl.size
+                assert gctl[0] == octl[0] and gctl[-1] == octl[-1], (k, e, "fsm state / stance")
+    np.testing.assert_allclose(g.GetPoliState(0), o.poli_state(0), rtol=1e-8, atol=1e-8)
+    np.testing.assert_allclose(g.GetNetOut(0, 87), o.net_out(0, 87), rtol=1e-7, atol=1e-7)
+    print("raptor 600 steps worst rel err", worst)
+    g = trl.ScenarioPoliEval(pack, 32)
+    o = Oracle(pack, 32, 0)
+    for _ in range(90):
+        g.Update(1.0 / 30.0)
+        o.update(1.0 / 30.0, 8)
+    assert g._stats()["cycles"] == o.eval_stats()["cycles"]
+    assert g._stats()["episodes"] == o.eval_stats()["episodes"]
+
+
 def test_set_state_roundtrip_and_single_env_reset(assets):
     import deepterrainrl_b200 as trl
     pack = os.path.join(assets, "dog_slopes_mixed.trlpack")
