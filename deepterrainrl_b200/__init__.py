@@ -6,6 +6,6 @@ include/terrainrl_b200.h).  This package is the thin host-side mirror of the ref
 importing works anywhere, creating a scenario without the built library or without a GPU raises.
 """
 from .scenario import (BatchedScenario, ScenarioExpMACE, ScenarioPoliEval, build_library, library_path,  # noqa: F401
-                       load_library)
+                       load_library, pack_from_args)
 
-__all__ = ["BatchedScenario", "ScenarioExpMACE", "ScenarioPoliEval", "build_library", "library_path", "load_library"]
+__all__ = ["BatchedScenario", "ScenarioExpMACE", "ScenarioPoliEval", "build_library", "library_path", "load_library", "pack_from_args"]

@@ -26,6 +26,7 @@ public:
             in.read(reinterpret_cast<char*>(&len), 4);
             std::string name(len, ' ');
             in.read(&name[0], len);
+            order_.push_back(name);
             in.read(reinterpret_cast<char*>(&dtype), 4);
             in.read(reinterpret_cast<char*>(&n), 8);
             if (dtype == 1) {
@@ -52,10 +53,39 @@ public:
         return it == ints_.end() ? empty : it->second;
     }
     bool has(const std::string& name) const { return reals_.count(name) || ints_.count(name); }
+    void set_f64(const std::string& name, std::vector<double> v) { if (!has(name)) order_.push_back(name); reals_[name] = std::move(v); }
+    void set_i32(const std::string& name, std::vector<int32_t> v) { if (!has(name)) order_.push_back(name); ints_[name] = std::move(v); }
+    bool save(const std::string& path, std::string* err) const {
+        std::ofstream out(path, std::ios::binary);
+        if (!out) { if (err) *err = "cannot write " + path; return false; }
+        out.write("TRLPACK1", 8);
+        uint32_t count = (uint32_t)order_.size();
+        out.write(reinterpret_cast<const char*>(&count), 4);
+        for (const std::string& name : order_) {
+            uint32_t len = (uint32_t)name.size();
+            out.write(reinterpret_cast<const char*>(&len), 4);
+            out.write(name.data(), len);
+            auto it = ints_.find(name);
+            uint32_t dtype = it != ints_.end() ? 1 : 0;
+            out.write(reinterpret_cast<const char*>(&dtype), 4);
+            if (dtype == 1) {
+                uint64_t n = it->second.size();
+                out.write(reinterpret_cast<const char*>(&n), 8);
+                out.write(reinterpret_cast<const char*>(it->second.data()), (std::streamsize)(n * 4));
+            } else {
+                const std::vector<double>& v = reals_.at(name);
+                uint64_t n = v.size();
+                out.write(reinterpret_cast<const char*>(&n), 8);
+                out.write(reinterpret_cast<const char*>(v.data()), (std::streamsize)(n * 8));
+            }
+        }
+        return (bool)out;
+    }
 
 private:
     std::unordered_map<std::string, std::vector<double>> reals_;
     std::unordered_map<std::string, std::vector<int32_t>> ints_;
+    std::vector<std::string> order_;
 };
 
 }  // namespace trl

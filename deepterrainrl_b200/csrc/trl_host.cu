@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "../../include/terrainrl_b200.h"
+#include "ref_loader.h"
 #include "scene_pack.h"
 #include "trl_types.h"
 
@@ -278,9 +279,42 @@ extern "C" {
 
 const char* trl_last_error(void) { return g_err.c_str(); }
 
+static trl_handle* create_common(trl_handle* h, int num_envs, int device, int mode, const uint64_t* terrain_seeds, uint64_t rng_seed);
+
 trl_handle* trl_create_from_pack(const char* pack_path, int num_envs, int device, int mode, const uint64_t* terrain_seeds,
                                  uint64_t rng_seed) {
     auto* h = new trl_handle();
+    std::string err;
+    if (!h->scene.load(pack_path, &err)) { g_err = err; delete h; return nullptr; }
+    return create_common(h, num_envs, device, mode, terrain_seeds, rng_seed);
+}
+
+trl_handle* trl_create(int argc, const char* const* argv, const char* data_root, int num_envs, int device, int mode,
+                       const uint64_t* terrain_seeds, uint64_t rng_seed) {
+    auto* h = new trl_handle();
+    try {
+        build_scene_from_args(argc, argv, data_root ? data_root : "", &h->scene);
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        delete h;
+        return nullptr;
+    }
+    return create_common(h, num_envs, device, mode, terrain_seeds, rng_seed);
+}
+
+int trl_pack_from_args(int argc, const char* const* argv, const char* data_root, const char* out_path) {
+    ScenePack pack;
+    try {
+        build_scene_from_args(argc, argv, data_root ? data_root : "", &pack);
+    } catch (const std::exception& e) {
+        return fail(e.what());
+    }
+    std::string err;
+    if (!pack.save(out_path, &err)) return fail(err);
+    return 0;
+}
+
+static trl_handle* create_common(trl_handle* h, int num_envs, int device, int mode, const uint64_t* terrain_seeds, uint64_t rng_seed) {
     auto bail = [&](const std::string& why) -> trl_handle* {
         if (!why.empty()) g_err = why;
         trl_destroy(h);
@@ -288,8 +322,6 @@ trl_handle* trl_create_from_pack(const char* pack_path, int num_envs, int device
     };
     h->device = device; h->n = num_envs; h->mode = mode;
     if (num_envs <= 0) return bail("num_envs must be positive");
-    std::string err;
-    if (!h->scene.load(pack_path, &err)) return bail(err);
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return bail("terrainrl_b200 needs a CUDA device: no GPU visible (the product path has no CPU fallback)");

@@ -25,7 +25,7 @@ def library_path():
 def build_library(force=False, verbose=False):
     """Compile csrc/*.cu for sm_100a into lib/libterrainrl_b200.so (nvcc cross-compiles without a GPU)."""
     out = library_path()
-    srcs = [os.path.join(_PKG, "csrc", f) for f in ("trl_step.cu", "trl_host.cu")]
+    srcs = [os.path.join(_PKG, "csrc", f) for f in ("trl_step.cu", "trl_host.cu", "ref_loader.cpp")]
     deps = [os.path.join(_PKG, "csrc", f) for f in os.listdir(os.path.join(_PKG, "csrc"))]
     deps.append(os.path.join(_ROOT, "include", "terrainrl_b200.h"))
     if not force and os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in deps):
@@ -38,7 +38,7 @@ def build_library(force=False, verbose=False):
 
 
 EXPORTS = [
-    "trl_create_from_pack", "trl_destroy", "trl_reset", "trl_seed_terrain", "trl_update", "trl_env_step", "trl_sync",
+    "trl_create_from_pack", "trl_create", "trl_pack_from_args", "trl_destroy", "trl_reset", "trl_seed_terrain", "trl_update", "trl_env_step", "trl_sync",
     "trl_set_explore", "trl_set_phys_params", "trl_set_weights", "trl_sizes", "trl_num_tuples", "trl_get_tuples",
     "trl_get_tuples_f64", "trl_reset_tuples", "trl_eval_stats", "trl_dist_log", "trl_get_state", "trl_set_state",
     "trl_get_state_all", "trl_get_ctrl", "trl_get_poli_state", "trl_get_net_out", "trl_get_terrain",
@@ -67,18 +67,34 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
 
 
+def pack_from_args(args, data_root, out_path):
+    """Native (C++) scene packer: reference arg tokens + checkout directory -> .trlpack (no GPU needed)."""
+    L = load_library()
+    argv = (C.c_char_p * len(args))(*[a.encode() for a in args])
+    if L.trl_pack_from_args(len(args), argv, os.fspath(data_root).encode(), os.fspath(out_path).encode()) != 0:
+        raise RuntimeError(L.trl_last_error().decode())
+    return out_path
+
+
 class BatchedScenario:
     """N environments of one scene stepped in lock-step on one GPU (one handle of the C ABI)."""
 
     MODE = 0
 
-    def __init__(self, pack, num_envs, device=0, terrain_seeds=None, rng_seed=1234):
+    def __init__(self, pack, num_envs, device=0, terrain_seeds=None, rng_seed=1234, args=None, data_root=None):
+        """pack: path of a .trlpack; or pass args=[...] (cArgParser tokens) + data_root (a DeepTerrainRL checkout)."""
         self.L = load_library()
         seeds = None if terrain_seeds is None else np.ascontiguousarray(terrain_seeds, dtype=np.uint64)
-        h = self.L.trl_create_from_pack(os.fspath(pack).encode(), int(num_envs), int(device), self.MODE, _p(seeds),
-                                        C.c_uint64(rng_seed))
+        if args is not None:
+            self.L.trl_create.restype = C.c_void_p
+            argv = (C.c_char_p * len(args))(*[a.encode() for a in args])
+            h = self.L.trl_create(len(args), argv, os.fspath(data_root or "").encode(), int(num_envs), int(device), self.MODE,
+                                  _p(seeds), C.c_uint64(rng_seed))
+        else:
+            h = self.L.trl_create_from_pack(os.fspath(pack).encode(), int(num_envs), int(device), self.MODE, _p(seeds),
+                                            C.c_uint64(rng_seed))
         if not h:
-            raise RuntimeError("trl_create_from_pack: " + self.L.trl_last_error().decode())
+            raise RuntimeError("trl_create: " + self.L.trl_last_error().decode())
         self.h = C.c_void_p(h)
         v = [C.c_int(0) for _ in range(7)]
         self._ck(self.L.trl_sizes(self.h, *[C.byref(x) for x in v]))

@@ -28,6 +28,14 @@ enum { TRL_MODE_POLI_EVAL = 0, TRL_MODE_EXPLORE = 1 };
  * (env i gets seed 1+i).  Returns NULL on failure. */
 trl_handle* trl_create_from_pack(const char* pack_path, int num_envs, int device, int mode,
                                  const uint64_t* terrain_seeds, uint64_t rng_seed);
+/* Same, straight from the reference's own inputs: argv holds cArgParser-style tokens (e.g. "-arg_file=",
+ * "args/dog_slopes_mixed_args.txt", plus overrides, CLI first = CLI wins, optimizer/Main.cpp:19-32); relative paths
+ * inside are resolved against data_root (a DeepTerrainRL checkout).  Native readers for the arg file, the JSON assets
+ * and the Caffe HDF5 weights (util/ArgParser.cpp:42-140, anim/KinTree.cpp:9-60, learning/NeuralNet.cpp:81-215). */
+trl_handle* trl_create(int argc, const char* const* argv, const char* data_root, int num_envs, int device, int mode,
+                       const uint64_t* terrain_seeds, uint64_t rng_seed);
+/* Scene files -> .trlpack without touching the GPU (what tools/pack_scene.py does in Python) */
+int trl_pack_from_args(int argc, const char* const* argv, const char* data_root, const char* out_path);
 int trl_destroy(trl_handle* h);
 
 /* cScenario::Reset for the listed envs (NULL = all)            scenarios/ScenarioSimChar.cpp:121-132 */

@@ -63,9 +63,41 @@ def test_pack_cross_file_identities(assets):
 def test_packs_regenerate_from_reference(assets, tmp_path):
     from pack_scene import build_pack
     for arg, name in (("args/sim_dog_args.txt", "dog_flat.trlpack"), ("args/dog_slopes_mixed_args.txt", "dog_slopes_mixed.trlpack"),
-                      ("args/goat_cliffs_args.txt", "goat_cliffs.trlpack")):
+                      ("args/goat_cliffs_args.txt", "goat_cliffs.trlpack"), ("args/raptor_narrow_gaps_args.txt", "raptor_narrow_gaps.trlpack")):
         rec = build_pack(os.path.join("/root/reference", arg), "/root/reference")
         old = read_pack(os.path.join(assets, name))
         assert set(rec) == set(old)
         for k in rec:
             np.testing.assert_array_equal(np.asarray(rec[k]).ravel(), old[k])
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/data"), reason="reference tree not present on this box")
+def test_native_loaders_match_python_packer(assets, tmp_path):
+    """The C++ readers behind trl_create (arg file, JSON assets, Caffe HDF5 weights; csrc/ref_loader.*) produce the
+    same named arrays, bit for bit, as tools/pack_scene.py -- including the 570,474 f64 policy weights."""
+    for arg, name in (("args/sim_dog_args.txt", "dog_flat.trlpack"), ("args/dog_slopes_mixed_args.txt", "dog_slopes_mixed.trlpack"),
+                      ("args/goat_cliffs_args.txt", "goat_cliffs.trlpack"), ("args/raptor_narrow_gaps_args.txt", "raptor_narrow_gaps.trlpack")):
+        out = tmp_path / name
+        trl.pack_from_args(["-arg_file=", arg], "/root/reference", out)
+        a, b = read_pack(out), read_pack(os.path.join(assets, name))
+        assert list(a) == list(b)
+        for k in a:
+            np.testing.assert_array_equal(a[k], b[k])
+    # CLI tokens win over the arg file (optimizer/Main.cpp:19-32)
+    out = tmp_path / "override.trlpack"
+    trl.pack_from_args(["-num_sim_substeps=", "2", "-arg_file=", "args/sim_dog_args.txt"], "/root/reference", out)
+    assert read_pack(out)["meta_i32"][3] == 2
+    with pytest.raises(RuntimeError):
+        trl.pack_from_args(["-arg_file=", "args/does_not_exist.txt"], "/root/reference", tmp_path / "x.trlpack")
+
+
+def test_raptor_pack_identities(assets):
+    p = read_pack(os.path.join(assets, "raptor_narrow_gaps.trlpack"))
+    assert list(p["net_dims"]) == [275, 75, 87, 3, 28]          # sim/NNController.cpp:49-78 size contract for the raptor
+    assert p["meta_i32"][8] == 19 and p["meta_i32"][9] == 21 and p["meta_i32"][13] == 0 and p["meta_i32"][14] == 0
+    ctrl = p["ctrl_params"].reshape(3, 37)
+    mask = np.array([0, 1, 1, 0, 0] + [1, 0, 1, 1, 1, 1, 1, 1] * 2 + [0, 0, 1, 1, 1, 1, 1, 1] * 2, bool)
+    assert mask.sum() == 28
+    off = p["net_out_offset"]
+    for a in range(3):
+        np.testing.assert_allclose(off[3 + 28 * a:3 + 28 * (a + 1)], -ctrl[a][mask], atol=1e-6)   # BuildActorBias

@@ -151,3 +151,18 @@ def test_exploration_tuples_structure(mixed):
             if not (f[k] & 1):
                 np.testing.assert_array_equal(r[k][1 + 283 + 30:], r[k + 1][1:1 + 283])
     assert ok.sum() > 0
+
+
+def test_raptor_runs_and_flips_stance(assets):
+    """Behavioural check of the raptor controller restatement: with the shipped narrow_gaps policy the raptor runs at
+    ~4 m/s, alternating stance legs every cycle (sim/RaptorController.cpp:837-840)."""
+    o = Oracle(os.path.join(assets, "raptor_narrow_gaps.trlpack"), 4, 0)
+    stances = []
+    for k in range(60):
+        o.update(1.0 / 30.0, 4)
+        stances.append(int(o.get_ctrl(0)[-1]))
+    x = np.array([o.get_state(e)[0][0] for e in range(4)])
+    st = o.eval_stats()
+    assert np.sum(x > 6.0) + st["episodes"] >= 4 and np.max(x) > 7.0
+    assert 0 in stances and 1 in stances
+    assert st["cycles"] >= 4 * 8
