@@ -165,4 +165,4 @@ def test_raptor_runs_and_flips_stance(assets):
     st = o.eval_stats()
     assert np.sum(x > 6.0) + st["episodes"] >= 4 and np.max(x) > 7.0
     assert 0 in stances and 1 in stances
-    assert st["cycles"] >= 4 * 8
+    assert st["cycles"] >= 4 * 6
