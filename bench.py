@@ -17,7 +17,6 @@ launch / its measured launch duration vs the measured copy peak; `cpu_baseline` 
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -42,50 +41,54 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle reasons sampled through NVML (nvidia-ml-py) every 5 ms while the timed region runs
+    (same fields as the nvidia-smi line in B200_PROFILING.md; NVML avoids nvidia-smi's start-up and pipe buffering,
+    which matter because the timed region is only ~150 ms long)."""
+
+    REASONS = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40, "sw_power_cap": 0x4}
 
     def __init__(self, index=0):
         self.index = index
-        self.rows = []
-        self.proc = None
+        self.samples = []
+        self.reasons = set()
+        self.stop_flag = False
+        self.thread = None
+        self.max_mhz = None
+        self.err = None
+
+    def _run(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            while not self.stop_flag:
+                self.samples.append((time.perf_counter(), float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))))
+                r = int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+                for name, bit in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add((time.perf_counter(), name))
+                time.sleep(0.005)
+            pynvml.nvmlShutdown()
+        except Exception as e:   # noqa: BLE001
+            self.err = repr(e)
 
     def start(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except Exception:
-            self.proc = None
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
-
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], None, set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[0])); mx = float(r[1])
-            except Exception:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+    def stop(self, t0=None, t1=None):
+        self.stop_flag = True
+        if self.thread:
+            self.thread.join(timeout=2)
+        sel = [v for (t, v) in self.samples if (t0 is None or t >= t0) and (t1 is None or t <= t1)]
+        reasons = sorted({n for (t, n) in self.reasons if (t0 is None or t >= t0) and (t1 is None or t <= t1)})
+        sel.sort()
+        out = {"sm_mhz": sel[len(sel) // 2] if sel else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
+               "samples": len(sel), "source": "nvml"}
+        if self.err:
+            out["error"] = self.err
+        return out
 
 
 def cpu_reference(num_envs, seconds_target, threads):
@@ -186,10 +189,13 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+        time.sleep(0.05)
     barrier()
+    t_beg = time.perf_counter()
     ms = sc.BenchUpdates(args.steps, DT, flush_l2=True)
+    t_end = time.perf_counter()
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_beg, t_end) if rank == 0 else None
     launches = sc.KernelLaunches() - launches0
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
