@@ -62,9 +62,11 @@ class ClockSampler:
             pynvml.nvmlInit()
             h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
             self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
             while not self.stop_flag:
                 self.samples.append((time.perf_counter(), float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))))
-                r = int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+                r = int(get_reasons(h))
                 for name, bit in self.REASONS.items():
                     if r & bit:
                         self.reasons.add((time.perf_counter(), name))
@@ -89,6 +91,23 @@ class ClockSampler:
         if self.err:
             out["error"] = self.err
         return out
+
+
+def ncu_traffic_bytes():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one trl_step_kernel launch, from the committed `ncu --set full`
+    summary of the same workload (profiles/ncu_step_kernel_r01_final.csv); None if the summary is absent."""
+    path = os.path.join(ROOT, "profiles", "ncu_step_kernel_r01_final.csv")
+    unit_scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    total, seen = 0.0, 0
+    try:
+        for line in open(path):
+            f = line.strip().split(",")
+            if len(f) == 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                total += float(f[2]) * unit_scale.get(f[1], 1.0)
+                seen += 1
+    except OSError:
+        return None
+    return total if seen == 2 else None
 
 
 def cpu_reference(num_envs, seconds_target, threads):
@@ -257,7 +276,7 @@ def main():
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                     "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_kind": peak_kind,
+                     "frac": achieved / peaks["hbm_gbs"], "traffic": ncu_traffic_bytes(), "peak_kind": peak_kind,
                      "kernel": "trl_step_kernel", "launch_ms": launch_s * 1e3,
                      "algorithmic_bytes_per_env_step": ALGO_BYTES_PER_ENV_STEP,
                      "step_kernel_share_of_update": step_ms / (step_ms + dec_ms),
