@@ -8,6 +8,7 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <algorithm>
 #include <vector>
 
 #include "../../include/terrainrl_b200.h"
@@ -173,6 +174,32 @@ static int fill_model(trl_handle* h, uint64_t rng_seed) {
         m.level_slot[m.depth[j]][slot] = 1;
     }
     if (m.max_depth >= 16) return fail("kinematic tree too deep for the 4-round ancestor jumps");
+    if (m.nj > 31) return fail("lane 31 must stay idle (zero source of the warp passes)");
+    {
+        // inward-pass schedule (parents precede children in index order, so walk the links backwards)
+        std::vector<int> earliest(m.nj, 0);
+        for (int j = 0; j < m.nj; ++j) { m.acc_round[j] = -1; m.acc_src[j] = ~0ull; }
+        for (int p = m.nj - 1; p >= 0; --p) {
+            // children of p, by the earliest round they can be eliminated in
+            std::vector<std::pair<int, int>> ch;
+            for (int c = 0; c < 4; ++c) if (m.child[p][c] >= 0) ch.push_back({earliest[m.child[p][c]], m.child[p][c]});
+            std::sort(ch.begin(), ch.end());
+            int last = -1;
+            for (auto& ec : ch) {
+                int t = std::max(ec.first, last + 1);
+                m.acc_round[ec.second] = t;
+                last = t;
+            }
+            earliest[p] = last + 1;
+        }
+        m.acc_rounds = earliest[0];
+        m.acc_round[0] = m.acc_rounds;     // the root is never eliminated
+        if (m.acc_rounds > 12) return fail("inward-pass schedule longer than 12 rounds");
+        for (int j = 1; j < m.nj; ++j) {
+            const int p = m.parent[j], r = m.acc_round[j];
+            m.acc_src[p] = (m.acc_src[p] & ~(31ull << (5 * r))) | ((unsigned long long)j << (5 * r));
+        }
+    }
     for (int j = 0; j < m.nj; ++j) {
         m.anc_pow[j][0] = m.parent[j];
         for (int k = 1; k < 4; ++k) m.anc_pow[j][k] = m.anc_pow[j][k - 1] >= 0 ? m.anc_pow[m.anc_pow[j][k - 1]][k - 1] : -1;

@@ -35,6 +35,7 @@ __constant__ ModelConst c_model;
 constexpr int kWarpsPerBlock = 4;
 constexpr int kBlockThreads = kWarpsPerBlock * kWarp;
 constexpr unsigned kFull = 0xffffffffu;
+constexpr int kZeroLane = 31;   // always idle (nj <= 23): its per-link registers are zero, used as the "no source" lane
 constexpr int kTri = kMaxDof * (kMaxDof + 1) / 2;   // 276
 // per-warp shared scratch (doubles)
 constexpr int X_M = 0;
@@ -261,8 +262,10 @@ __device__ void store_rng(Lane& L, const CounterRng& r) {
 // Per-lane constants of link `lane` and the env state held in registers.
 struct LinkC {
     int act;            // lane < nj
-    int parent, depth, child0, child1, child2, child3;
-    int anc1, anc2, anc4, anc8;   // 2^k-th ancestors (-1 = none) for the pointer-jumping prefix sums
+    int parent, depth;
+    int acc_round;                // inward-pass round in which this link is eliminated (-1 idle lane, acc_rounds root)
+    unsigned long long acc_src;   // 5 bits per inward round: lane to receive from (31 = none)
+    int anc1, anc2, anc4, anc8;   // 2^k-th ancestors (31 = none: the idle zero lane) for the pointer-jumping prefix sums
     double ax, ay;      // attach point in the parent's joint frame
     double mass, bax, bay, izz_c;
     int has_lim;
@@ -285,12 +288,14 @@ __device__ __forceinline__ LinkC load_link(int lane) {
     int j = c.act ? lane : 0;
     c.parent = (c.act && j > 0) ? m.parent[j] : 0;
     c.depth = c.act ? m.depth[j] : -1;
-    c.child0 = c.act ? m.child[j][0] : -1;
-    c.child1 = c.act ? m.child[j][1] : -1;
-    c.child2 = c.act ? m.child[j][2] : -1;
-    c.child3 = c.act ? m.child[j][3] : -1;
+    c.acc_round = c.act ? m.acc_round[j] : -1;
+    c.acc_src = c.act ? m.acc_src[j] : ~0ull;
     c.anc1 = c.act ? m.anc_pow[j][0] : -1; c.anc2 = c.act ? m.anc_pow[j][1] : -1;
     c.anc4 = c.act ? m.anc_pow[j][2] : -1; c.anc8 = c.act ? m.anc_pow[j][3] : -1;
+    if (c.anc1 < 0) c.anc1 = kZeroLane;
+    if (c.anc2 < 0) c.anc2 = kZeroLane;
+    if (c.anc4 < 0) c.anc4 = kZeroLane;
+    if (c.anc8 < 0) c.anc8 = kZeroLane;
     c.ax = m.attach_x[j]; c.ay = m.attach_y[j];
     c.mass = c.act ? m.mass[j] : 0.0;
     c.bax = m.body_ax[j]; c.bay = m.body_ay[j];
@@ -301,13 +306,14 @@ __device__ __forceinline__ LinkC load_link(int lane) {
 }
 
 // root-ward prefix sums over the kinematic tree by pointer jumping: after 4 rounds every link holds the sum of its own
-// value and those of all its ancestors (depth <= 15), using the static 2^k-th ancestor table
+// value and those of all its ancestors (depth <= 15), using the static 2^k-th ancestor table.  A missing ancestor points
+// at lane 31, which is idle and holds zeros, so the adds need no predicate.
 #define TRL_TREE_PREFIX2(a, b)                                                                  \
     do {                                                                                        \
         _Pragma("unroll") for (int r_ = 0; r_ < 4; ++r_) {                                      \
             int an_ = (r_ == 0) ? c.anc1 : ((r_ == 1) ? c.anc2 : ((r_ == 2) ? c.anc4 : c.anc8)); \
-            double ta_ = shf((a), an_ >= 0 ? an_ : 0), tb_ = shf((b), an_ >= 0 ? an_ : 0);      \
-            if (an_ >= 0) { (a) += ta_; (b) += tb_; }                                           \
+            double ta_ = shf((a), an_), tb_ = shf((b), an_);                                    \
+            (a) += ta_; (b) += tb_;                                                             \
         }                                                                                       \
     } while (0)
 
@@ -333,19 +339,12 @@ __device__ __forceinline__ Kin kinematics(const LinkC& c, const EnvRegs& e) {
     return k;
 }
 
-// children -> parent accumulation of NV register values for tree level l (deterministic slot order)
-#define TRL_ACCUM_LEVEL(l, NV, vals)                                                        \
+// child -> parent hand-off at the end of inward round r: every lane adds the NV register values of the one lane its
+// schedule names for this round (lane 31 = none; it is idle and its values are zero, so the add is unconditional)
+#define TRL_ACCUM_ROUND(r, NV, vals)                                                        \
     do {                                                                                    \
-        _Pragma("unroll") for (int s_ = 0; s_ < 4; ++s_) {                                  \
-            if (!c_model.level_slot[(l)][s_]) continue;                                     \
-            int ch_ = (s_ == 0) ? lc.child0 : ((s_ == 1) ? lc.child1 : ((s_ == 2) ? lc.child2 : lc.child3)); \
-            int src_ = ch_ >= 0 ? ch_ : 0;                                                  \
-            bool take_ = (ch_ >= 0) && (lc.depth == (l)-1);                                 \
-            _Pragma("unroll") for (int v_ = 0; v_ < (NV); ++v_) {                           \
-                double t_ = shf((vals)[v_], src_);                                          \
-                if (take_) (vals)[v_] += t_;                                                \
-            }                                                                               \
-        }                                                                                   \
+        const int src_ = (int)(lc.acc_src >> (5 * (r))) & 31;                               \
+        _Pragma("unroll") for (int v_ = 0; v_ < (NV); ++v_) (vals)[v_] += shf((vals)[v_], src_); \
     } while (0)
 
 // ================================================================================================ controller half
@@ -384,7 +383,7 @@ __device__ double controller_torque(Lane& L, const LinkC& lc, const EnvRegs& e, 
         vals[6] = lc.mass * aly + k.w * hlx;
         if (!lc.act) { vals[4] = vals[5] = vals[6] = 0.0; }
     }
-    for (int l = md; l >= 1; --l) TRL_ACCUM_LEVEL(l, 7, vals);
+    for (int r = 0; r < m.acc_rounds; ++r) TRL_ACCUM_ROUND(r, 7, vals);
     const double s1 = k.ry, s2 = -k.rx;                       // S_j = (1, s1, s2)
     // bias force C (per link lane; the root's three entries live in lane 0)
     const double Cj = vals[4] + s1 * vals[5] + s2 * vals[6];
@@ -729,8 +728,8 @@ __device__ int physics_substep(const LinkC& lc, EnvRegs& e, const GroundView& g,
     // ---- pass 2: articulated inertias / bias forces inward (level-synchronous)
     const double s1 = k.ry, s2 = -k.rx;
     double U0 = 0.0, U1 = 0.0, U2 = 0.0, dinv = 0.0, uu = 0.0;
-    for (int l = md; l >= 1; --l) {
-        if (lc.depth == l) {
+    for (int r = 0; r < m.acc_rounds; ++r) {
+        if (lc.acc_round == r) {
             U0 = ia[0] + ia[1] * s1 + ia[2] * s2;
             U1 = ia[1] + ia[3] * s1 + ia[4] * s2;
             U2 = ia[2] + ia[4] * s1 + ia[5] * s2;
@@ -756,18 +755,18 @@ __device__ int physics_substep(const LinkC& lc, EnvRegs& e, const GroundView& g,
             ia[8] += n4 * cvx + n5 * cvy + U2 * ud;
             ia[0] = n0; ia[1] = n1; ia[2] = n2; ia[3] = n3; ia[4] = n4; ia[5] = n5;
         }
-        TRL_ACCUM_LEVEL(l, 9, ia);
+        TRL_ACCUM_ROUND(r, 9, ia);
     }
     // floating base: solve IA_0 a_0 = -pA_0 (symmetric 3x3 LDL^T); every lane computes it from lane 0's values
     double a0, a1, a2;
     {
         double a = shf(ia[0], 0), bx = shf(ia[1], 0), by = shf(ia[2], 0), cxx = shf(ia[3], 0), cxy = shf(ia[4], 0), cyy = shf(ia[5], 0);
         double r0 = -shf(ia[6], 0), r1 = -shf(ia[7], 0), r2 = -shf(ia[8], 0);
-        double d0 = a, l10 = bx / d0, l20 = by / d0;
-        double d1 = cxx - l10 * l10 * d0, l21 = (cxy - l20 * l10 * d0) / d1;
-        double d2 = cyy - l20 * l20 * d0 - l21 * l21 * d1;
-        double y0 = r0, y1 = r1 - l10 * y0, y2 = r2 - l20 * y0 - l21 * y1;
-        a2 = y2 / d2; a1 = y1 / d1 - l21 * a2; a0 = y0 / d0 - l10 * a1 - l20 * a2;
+        const double i0 = 1.0 / a, l10 = bx * i0, l20 = by * i0;
+        const double d1 = cxx - l10 * bx, i1 = 1.0 / d1, t21 = cxy - l20 * bx, l21 = t21 * i1;
+        const double d2 = cyy - l20 * by - l21 * t21, i2 = 1.0 / d2;
+        const double y0 = r0, y1 = r1 - l10 * y0, y2 = r2 - l20 * y0 - l21 * y1;
+        a2 = y2 * i2; a1 = y1 * i1 - l21 * a2; a0 = y0 * i0 - l10 * a1 - l20 * a2;
     }
     // pass 3: accelerations outward; each link lane integrates its own joint (semi-implicit Euler)
     double aw = a0, alx = a1, aly = a2;

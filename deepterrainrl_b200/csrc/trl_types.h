@@ -73,6 +73,11 @@ struct ModelConst {
     int child[kMaxJoints][4];              // up to 4 children per link (-1 = none)
     int anc_pow[kMaxJoints][4];            // 2^k-th ancestor of each link (k = 0..3), -1 if it does not exist
     int level_slot[12][4];                 // level_slot[l][s] != 0: some link at depth l is child slot s of its parent
+    // inward (leaf -> root) pass schedule: link j is eliminated in round acc_round[j] and handed to its parent at the end
+    // of that round; siblings get distinct rounds so that every lane receives from at most ONE lane per round.
+    // acc_src[j] packs, 5 bits per round, the lane that lane j receives from (31 = none: lane 31 is idle and holds zeros)
+    int acc_round[kMaxJoints], acc_rounds;
+    unsigned long long acc_src[kMaxJoints];
     int n_corners;                         // 4 * number of collidable bodies
     int corner_body[4 * kMaxJoints];
     double corner_lx[4 * kMaxJoints], corner_ly[4 * kMaxJoints];   // corner position in the link (joint) frame
