@@ -271,15 +271,15 @@ __device__ void net_forward_cluster(cg::cluster_group& cluster, const NetWeights
 }
 
 __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kDecideThreads, 2)
-trl_decide_kernel(Buffers B, NetWeights W, ExpSettings ex, int* done_count) {
+trl_decide_kernel(Buffers B, NetWeights W, ExpSettings ex, int* done_count, int list, int rearm) {
     extern __shared__ double sh[];
     cg::cluster_group cluster = cg::this_cluster();
     const ModelConst& m = c_model;
     const int rank = (int)cluster.block_rank();
     const int cid = blockIdx.x / kClusterSize, ncl = gridDim.x / kClusterSize;
-    const int count = *B.pending_count;
+    const int count = B.pending_count[list];
     for (int idx = cid; idx < count; idx += ncl) {
-        const int env = B.pending_list[idx];
+        const int env = B.pending_list[list * B.n + idx];
         Lane L{nullptr, env, B.n, B.d, B.i};
         CounterRng rng;
         double params[kNumParams];
@@ -347,16 +347,16 @@ trl_decide_kernel(Buffers B, NetWeights W, ExpSettings ex, int* done_count) {
         if (boss) {
             L.i(I_EXP_FLAGS) = eflags;
             apply_action(L, id, params, B.com_stash[env], B.com_stash[B.n + env]);
-            L.i(I_PENDING) = 0;
             store_rng(L, rng);
         }
         cluster.sync();   // rank 0's Y / peers' activations are reused by the next decision of this cluster
     }
-    // last CTA to finish re-arms the pending list for the next step
-    if (threadIdx.x == 0) {
+    // serial schedule: the last CTA to finish re-arms the list (in the overlapped schedule the catch-up launch, which
+    // still needs the count, does it)
+    if (rearm && threadIdx.x == 0) {
         __threadfence();
         int done = atomicAdd(done_count, 1);
-        if (done == (int)gridDim.x - 1) { *B.pending_count = 0; *done_count = 0; __threadfence(); }
+        if (done == (int)gridDim.x - 1) { B.pending_count[list] = 0; *done_count = 0; __threadfence(); }
     }
 }
 
@@ -364,8 +364,9 @@ size_t decide_smem_bytes() { return (size_t)kDecideSmemDoubles * sizeof(double);
 cudaError_t configure_decide_kernel() {
     return cudaFuncSetAttribute(trl_decide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decide_smem_bytes());
 }
-void launch_decide(const Buffers& B, const NetWeights& W, const ExpSettings& ex, int* done_count, int grid, cudaStream_t st) {
-    trl_decide_kernel<<<grid, kDecideThreads, decide_smem_bytes(), st>>>(B, W, ex, done_count);
+void launch_decide(const Buffers& B, const NetWeights& W, const ExpSettings& ex, int* done_count, int grid, int list, int rearm,
+                   cudaStream_t st) {
+    trl_decide_kernel<<<grid, kDecideThreads, decide_smem_bytes(), st>>>(B, W, ex, done_count, list, rearm);
 }
 
 }  // namespace trl

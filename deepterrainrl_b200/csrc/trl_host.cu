@@ -20,11 +20,12 @@ namespace trl {
 cudaError_t upload_model(const ModelConst& mc);
 size_t step_smem_bytes();
 cudaError_t configure_step_kernels();
-void launch_step(const Buffers& B, double h, int flags, cudaStream_t st);
+void launch_step(const Buffers& B, double h, int flags, int lists, cudaStream_t st);
 void launch_reset(const Buffers& B, const uint64_t* seeds, const int* env_ids, int count, int reseed, cudaStream_t st);
 size_t decide_smem_bytes();
 cudaError_t configure_decide_kernel();
-void launch_decide(const Buffers& B, const NetWeights& W, const ExpSettings& ex, int* done_count, int grid, cudaStream_t st);
+void launch_decide(const Buffers& B, const NetWeights& W, const ExpSettings& ex, int* done_count, int grid, int list, int rearm,
+                   cudaStream_t st);
 void launch_stats(const Buffers& B, double* out, cudaStream_t st);
 void launch_terrain(const Buffers& B, double lookahead, cudaStream_t st);
 }  // namespace trl
@@ -53,6 +54,9 @@ struct trl_handle {
     std::vector<int64_t> net_counts;
     int* done_count = nullptr;
     cudaStream_t stream = nullptr;
+    cudaStream_t aux_stream = nullptr;           // high-priority side stream: decisions + catch-up launches (overlapped schedule)
+    std::vector<cudaEvent_t> fork_events;        // dependencies between the two streams inside one update
+    bool overlap = true;                         // TRL_SERIAL_SCHEDULE=1 turns the overlapped schedule off
     int decide_grid = 288;   // multiple of the 8-CTA cluster size
     int num_update_steps = 20;
     int64_t launches = 0;
@@ -204,17 +208,41 @@ static int fill_model(trl_handle* h, uint64_t rng_seed) {
         m.anc_pow[j][0] = m.parent[j];
         for (int k = 1; k < 4; ++k) m.anc_pow[j][k] = m.anc_pow[j][k - 1] >= 0 ? m.anc_pow[m.anc_pow[j][k - 1]][k - 1] : -1;
     }
-    m.n_corners = 0;
-    for (int j = 0; j < m.nj; ++j) {
-        m.corner_base[j] = -1;
-        if (!m.collidable[j]) continue;
-        m.corner_base[j] = m.n_corners;
-        for (int cn = 0; cn < 4; ++cn) {
-            double bx = (cn & 1) ? m.half_x[j] : -m.half_x[j], by = (cn & 2) ? m.half_y[j] : -m.half_y[j];
-            m.corner_body[m.n_corners] = j;
-            m.corner_lx[m.n_corners] = m.body_ax[j] + m.body_cos[j] * bx - m.body_sin[j] * by;
-            m.corner_ly[m.n_corners] = m.body_ay[j] + m.body_sin[j] * bx + m.body_cos[j] * by;
-            ++m.n_corners;
+    {
+        // box corners, ordered so that the bodies most likely to touch the ground (lowest in the zero pose: feet, shanks)
+        // share the first 32-corner round; rounds whose corners are all clear of the terrain are skipped by the kernel.
+        // reach = upper bound of |corner - root joint| over all poses (bounds the terrain window the contacts can see)
+        std::vector<double> jy(m.nj, 0.0), jr(m.nj, 0.0), low(m.nj, 0.0);
+        std::vector<int> order;
+        m.reach = 0.0;
+        for (int j = 0; j < m.nj; ++j) {
+            if (j > 0) {
+                jy[j] = jy[m.parent[j]] + m.attach_y[j];
+                jr[j] = jr[m.parent[j]] + std::hypot(m.attach_x[j], m.attach_y[j]);
+            }
+            m.corner_base[j] = -1;
+            if (!m.collidable[j]) continue;
+            order.push_back(j);
+            low[j] = 1e30;
+            for (int cn = 0; cn < 4; ++cn) {
+                double bx = (cn & 1) ? m.half_x[j] : -m.half_x[j], by = (cn & 2) ? m.half_y[j] : -m.half_y[j];
+                double lx = m.body_ax[j] + m.body_cos[j] * bx - m.body_sin[j] * by;
+                double ly = m.body_ay[j] + m.body_sin[j] * bx + m.body_cos[j] * by;
+                low[j] = std::min(low[j], jy[j] + ly);
+                m.reach = std::max(m.reach, jr[j] + std::hypot(lx, ly));
+            }
+        }
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return low[a] < low[b]; });
+        m.n_corners = 0;
+        for (int j : order) {
+            m.corner_base[j] = m.n_corners;
+            for (int cn = 0; cn < 4; ++cn) {
+                double bx = (cn & 1) ? m.half_x[j] : -m.half_x[j], by = (cn & 2) ? m.half_y[j] : -m.half_y[j];
+                m.corner_body[m.n_corners] = j;
+                m.corner_lx[m.n_corners] = m.body_ax[j] + m.body_cos[j] * bx - m.body_sin[j] * by;
+                m.corner_ly[m.n_corners] = m.body_ay[j] + m.body_sin[j] * bx + m.body_cos[j] * by;
+                ++m.n_corners;
+            }
         }
     }
     {
@@ -291,15 +319,60 @@ static void destroy_graphs(trl_handle* h) {
     h->graphs.clear();
 }
 
-static void enqueue_update(trl_handle* h, double dt) {
+// One outer update = num_update_steps env-steps.  An env-step is split at the policy decision: launch S_i runs the
+// controller half of env-step i-1 and the physics half of env-step i for every env, then the decision kernel D_i serves the
+// (few) envs that reached a cycle boundary in S_i.
+//
+//   serial schedule      T  S_0  D_0  S_1  D_1 ... S_{ns-1}  D_{ns-1}  S_end
+//   overlapped schedule  main stream   T  S_0 ------ S_1 -------------- S_2 ----- ...  S_{ns-1} ----------- S_end
+//                        side stream          D_0 -> C_1        D_1 -> C_2        ...             D_{ns-1}
+//
+// In the overlapped schedule S_i (i >= 1) skips the envs that wait for D_{i-1}; the catch-up launch C_i steps exactly
+// those envs once their decision is made (same kernel, one warp per list entry), concurrently with S_i.  D_i needs
+// S_i and C_i; S_{i+1} needs S_i and C_i.  Two pending lists alternate so that S_i / C_i can append to one while D_{i-1} / C_i
+// read the other.  Every env still advances by exactly one env-step per S/C pair, so results are identical to the serial
+// schedule (tests/test_gpu_scenarios.py::test_overlap_matches_serial).
+static void enqueue_update(trl_handle* h, double dt, bool overlap) {
     const int ns = h->num_update_steps;
     const double step = dt / ns;
-    launch_terrain(h->B, 0.5, h->stream);
-    for (int i = 0; i < ns; ++i) {
-        launch_step(h->B, step, i == 0 ? 2 : 3, h->stream);
-        launch_decide(h->B, h->W, h->ex, h->done_count, h->decide_grid, h->stream);
+    cudaStream_t A = h->stream, S = h->aux_stream;
+    launch_terrain(h->B, 0.5, A);
+    if (!overlap) {
+        for (int i = 0; i < ns; ++i) {
+            launch_step(h->B, step, i == 0 ? 2 : 3, 0, A);
+            launch_decide(h->B, h->W, h->ex, h->done_count, h->decide_grid, 0, 1, A);
+        }
+        launch_step(h->B, step, 1 | 4, 0, A);
+        return;
     }
-    launch_step(h->B, step, 1 | 4, h->stream);
+    if ((int)h->fork_events.size() < 2 * ns + 2) {
+        size_t old = h->fork_events.size();
+        h->fork_events.resize(2 * ns + 2);
+        for (size_t i = old; i < h->fork_events.size(); ++i) cudaEventCreateWithFlags(&h->fork_events[i], cudaEventDisableTiming);
+    }
+    cudaEvent_t* ev_s = h->fork_events.data();            // ev_s[i]: S_i done
+    cudaEvent_t* ev_c = h->fork_events.data() + ns + 1;   // ev_c[i]: C_i (and everything before it on the side stream) done
+    launch_step(h->B, step, 2, /*app*/ 0, A);
+    cudaEventRecord(ev_s[0], A);
+    for (int i = 1; i < ns; ++i) {
+        const int app = i & 1, prev = (i - 1) & 1, lists = app | (prev << 1);
+        cudaStreamWaitEvent(S, ev_s[i - 1], 0);
+        launch_decide(h->B, h->W, h->ex, h->done_count, h->decide_grid, prev, 0, S);
+        launch_step(h->B, step, 1 | 2 | 16, lists, S);
+        cudaEventRecord(ev_c[i], S);
+        if (i >= 2) cudaStreamWaitEvent(A, ev_c[i - 1], 0);
+        launch_step(h->B, step, 1 | 2 | 8, lists, A);
+        cudaEventRecord(ev_s[i], A);
+    }
+    cudaStreamWaitEvent(S, ev_s[ns - 1], 0);
+    launch_decide(h->B, h->W, h->ex, h->done_count, h->decide_grid, (ns - 1) & 1, 1, S);
+    cudaEventRecord(ev_c[ns], S);
+    cudaStreamWaitEvent(A, ev_c[ns], 0);
+    launch_step(h->B, step, 1 | 4, 0, A);
+}
+static int update_launches(const trl_handle* h, bool overlap) {
+    const int ns = h->num_update_steps;
+    return overlap ? 3 * ns + 1 : 2 * ns + 2;    // terrain + S_0..S_{ns-1} + D_0..D_{ns-1} + S_end (+ C_1..C_{ns-1})
 }
 
 extern "C" {
@@ -355,6 +428,13 @@ static trl_handle* create_common(trl_handle* h, int num_envs, int device, int mo
     if (cudaSetDevice(device) != cudaSuccess) return bail("cudaSetDevice failed");
     if (fill_model(h, rng_seed)) return bail("");
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return bail("cudaStreamCreate failed");
+    {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);   // hi = numerically lowest = greatest priority
+        if (cudaStreamCreateWithPriority(&h->aux_stream, cudaStreamNonBlocking, hi) != cudaSuccess) return bail("cudaStreamCreate (side) failed");
+        const char* serial = std::getenv("TRL_SERIAL_SCHEDULE");
+        h->overlap = !(serial && serial[0] == '1');
+    }
     auto ck = [&](cudaError_t e, const char* what) -> bool {
         if (e != cudaSuccess) { g_err = std::string(what) + ": " + cudaGetErrorString(e); return false; }
         return true;
@@ -375,7 +455,8 @@ static trl_handle* create_common(trl_handle* h, int num_envs, int device, int mo
               ck(dalloc(h, &B.terrain, n * 2 * kTerrainCap), "alloc terrain") && ck(dalloc(h, &B.poli_state, n * B.S), "alloc poli") &&
               ck(dalloc(h, &B.net_out, n * kMaxNetOut), "alloc net_out") && ck(dalloc(h, &B.tuple_sbeg, n * B.S), "alloc sbeg") &&
               ck(dalloc(h, &B.tuple_action, n * kNumParams), "alloc action") && ck(dalloc(h, &B.com_stash, 2 * n), "alloc com") &&
-              ck(dalloc(h, &B.pending_list, n), "alloc pending") && ck(dalloc(h, &B.pending_count, 1), "alloc pc") &&
+              ck(dalloc(h, &B.pending_list, 2 * n), "alloc pending") && ck(dalloc(h, &B.pending_count, 2), "alloc pc") &&
+              ck(dalloc(h, &B.catchup_done, 1), "alloc cd") &&
               ck(dalloc(h, &B.tuples, (size_t)B.tuple_cap * (1 + B.S + A + B.S)), "alloc tuples") &&
               ck(dalloc(h, &B.tuple_flags, (size_t)B.tuple_cap), "alloc tf") && ck(dalloc(h, &B.tuple_env, (size_t)B.tuple_cap), "alloc te") &&
               ck(dalloc(h, &B.tuple_count, 1), "alloc tc") && ck(dalloc(h, &B.dist_log, (size_t)B.dist_cap), "alloc dl") &&
@@ -414,6 +495,8 @@ int trl_destroy(trl_handle* h) {
     if (h->snap_copied) cudaEventDestroy(h->snap_copied);
     if (h->snap_host) cudaFreeHost(h->snap_host);
     for (void* p : h->allocs) cudaFree(p);
+    if (h->aux_stream) { cudaStreamSynchronize(h->aux_stream); cudaStreamDestroy(h->aux_stream); }
+    for (auto e : h->fork_events) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return 0;
@@ -426,7 +509,7 @@ int trl_seed_terrain(trl_handle* h, const uint64_t* seeds, int n) {
         CK(cudaMalloc((void**)&d_seeds, (size_t)n * 8));
         CK(cudaMemcpyAsync(d_seeds, seeds, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
     }
-    CK(cudaMemsetAsync(h->B.pending_count, 0, 4, h->stream));
+    CK(cudaMemsetAsync(h->B.pending_count, 0, 8, h->stream));
     launch_reset(h->B, d_seeds, nullptr, h->n, 1, h->stream);
     h->launches += 1;
     CK(cudaGetLastError());
@@ -453,7 +536,7 @@ int trl_reset(trl_handle* h, const int32_t* env_ids, int n) {
 
 int trl_update(trl_handle* h, double dt) {
     if (!(dt > 0)) return 0;
-    const int nlaunch = 2 * h->num_update_steps + 2;
+    const int nlaunch = update_launches(h, h->overlap);
     if (h->use_graph) {
         long long key;
         std::memcpy(&key, &dt, 8);
@@ -461,7 +544,7 @@ int trl_update(trl_handle* h, double dt) {
         if (it == h->graphs.end()) {
             cudaGraph_t graph;
             CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-            enqueue_update(h, dt);
+            enqueue_update(h, dt, h->overlap);
             CK(cudaStreamEndCapture(h->stream, &graph));
             cudaGraphExec_t exec;
             CK(cudaGraphInstantiate(&exec, graph, 0));
@@ -470,7 +553,7 @@ int trl_update(trl_handle* h, double dt) {
         }
         CK(cudaGraphLaunch(it->second, h->stream));
     } else {
-        enqueue_update(h, dt);
+        enqueue_update(h, dt, h->overlap);
         CK(cudaGetLastError());
     }
     h->launches += nlaunch;
@@ -478,9 +561,9 @@ int trl_update(trl_handle* h, double dt) {
 }
 
 int trl_env_step(trl_handle* h, double step) {
-    launch_step(h->B, step, 2, h->stream);
-    launch_decide(h->B, h->W, h->ex, h->done_count, h->decide_grid, h->stream);
-    launch_step(h->B, step, 1, h->stream);
+    launch_step(h->B, step, 2, 0, h->stream);
+    launch_decide(h->B, h->W, h->ex, h->done_count, h->decide_grid, 0, 1, h->stream);
+    launch_step(h->B, step, 1, 0, h->stream);
     h->launches += 3;
     CK(cudaGetLastError());
     return 0;
@@ -722,7 +805,7 @@ int trl_debug_time_decide(trl_handle* h, int n_pending, int iters, double* ms_av
         CK(cudaMemcpyAsync(h->B.pending_list, ids.data(), (size_t)n_pending * 4, cudaMemcpyHostToDevice, h->stream));
         CK(cudaMemcpyAsync(h->B.pending_count, &n_pending, 4, cudaMemcpyHostToDevice, h->stream));
         CK(cudaEventRecord(e0, h->stream));
-        launch_decide(h->B, h->W, h->ex, h->done_count, h->decide_grid, h->stream);
+        launch_decide(h->B, h->W, h->ex, h->done_count, h->decide_grid, 0, 1, h->stream);
         CK(cudaEventRecord(e1, h->stream));
         CK(cudaEventSynchronize(e1));
         float ms = 0;
@@ -832,14 +915,14 @@ static int update_timed_impl(trl_handle* h, double dt, double* step_ms, int* ste
     launch_terrain(h->B, 0.5, h->stream);
     for (int i = 0; i < ns; ++i) {
         CK(cudaEventRecord(ev[k++], h->stream));
-        launch_step(h->B, step, i == 0 ? 2 : 3, h->stream);
+        launch_step(h->B, step, i == 0 ? 2 : 3, 0, h->stream);
         CK(cudaEventRecord(ev[k++], h->stream));
         CK(cudaEventRecord(ev[k++], h->stream));
-        launch_decide(h->B, h->W, h->ex, h->done_count, h->decide_grid, h->stream);
+        launch_decide(h->B, h->W, h->ex, h->done_count, h->decide_grid, 0, 1, h->stream);
         CK(cudaEventRecord(ev[k++], h->stream));
     }
     CK(cudaEventRecord(ev[k++], h->stream));
-    launch_step(h->B, step, 1 | 4, h->stream);
+    launch_step(h->B, step, 1 | 4, 0, h->stream);
     CK(cudaEventRecord(ev[k++], h->stream));
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaGetLastError());

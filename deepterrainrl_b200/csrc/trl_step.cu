@@ -35,6 +35,11 @@ __constant__ ModelConst c_model;
 constexpr int kWarpsPerBlock = 4;
 constexpr int kBlockThreads = kWarpsPerBlock * kWarp;
 constexpr unsigned kFull = 0xffffffffu;
+#ifndef TRL_STEP_MIN_BLOCKS
+#define TRL_STEP_MIN_BLOCKS 4   // CTAs of 4 warps per SM the register budget is sized for
+#endif
+constexpr int kStepSkipPending = 8, kStepCatchUp = 16;   // flag bits of trl_step_kernel beyond ctrl (1) / phys (2) / end (4)
+constexpr double kClearMargin = 0.05;   // >= contact_tol * sqrt(1 + slope^2) for any slope the generators produce
 constexpr int kZeroLane = 31;   // always idle (nj <= 23): its per-link registers are zero, used as the "no source" lane
 constexpr int kTri = kMaxDof * (kMaxDof + 1) / 2;   // 276
 // per-warp shared scratch (doubles)
@@ -301,7 +306,8 @@ __device__ __forceinline__ LinkC load_link(int lane) {
     c.bax = m.body_ax[j]; c.bay = m.body_ay[j];
     c.izz_c = c.act ? m.izz_c[j] : 0.0;
     c.has_lim = c.act ? m.has_limit[j] : 0;
-    c.lim_lo = m.lim_lo[j]; c.lim_hi = m.lim_hi[j];
+    c.lim_lo = c.has_lim ? m.lim_lo[j] : -INFINITY;    // no limit: never violated, so the limit force needs no branch
+    c.lim_hi = c.has_lim ? m.lim_hi[j] : INFINITY;
     return c;
 }
 
@@ -647,7 +653,7 @@ __device__ double controller_torque(Lane& L, const LinkC& lc, const EnvRegs& e, 
 // One sub-step of articulated-body forward dynamics with linearly-implicit contact / joint-limit terms.
 // Updates e (q, qd, root translation) in place and returns the contact bitmask (same value in every lane).
 __device__ int physics_substep(const LinkC& lc, EnvRegs& e, const GroundView& g, const double* s_clx, const double* s_cly,
-                               const int* s_cbody, int lane, double dt) {
+                               const int* s_cbody, int lane, double dt, double clear_y) {
     const ModelConst& m = c_model;
     const PhysParams& pp = m.phys;
     const int md = m.max_depth;
@@ -675,13 +681,17 @@ __device__ int physics_substep(const LinkC& lc, EnvRegs& e, const GroundView& g,
         const int b = valid ? s_cbody[ci] : 0;
         const double lx = valid ? s_clx[ci] : 0.0, ly = valid ? s_cly[ci] : 0.0;
         const double bcw = shf(k.cw, b), bsw = shf(k.sw, b), brx = shf(k.rx, b), bry = shf(k.ry, b);
+        const double rpx = brx + bcw * lx - bsw * ly, rpy = bry + bsw * lx + bcw * ly;   // corner rel. O
+        // broad phase: a corner above clear_y (terrain maximum under the character + margin) cannot be within the
+        // contact tolerance; a round with no candidate corner is skipped by the whole warp
+        const bool cand = valid && (e.oy + rpy <= clear_y);
+        if (!__any_sync(kFull, cand)) continue;
         const double bw = shf(k.w, b), bvx = shf(k.vx, b), bvy = shf(k.vy, b);
         double add[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
         bool touching = false;
-        if (valid) {
-            const double rpx = brx + bcw * lx - bsw * ly, rpy = bry + bsw * lx + bcw * ly;   // corner rel. O
+        if (cand) {
             double slope;
-            const double hgt = g.sample(e.ox + rpx, &slope);
+            const double hgt = g.sample_fast(e.ox + rpx, &slope);
             const double inv = rsqrt(1.0 + slope * slope);
             const double pen = (hgt - (e.oy + rpy)) * inv;
             if (pen > -pp.contact_tol) {
@@ -735,15 +745,12 @@ __device__ int physics_substep(const LinkC& lc, EnvRegs& e, const GroundView& g,
             U2 = ia[2] + ia[4] * s1 + ia[5] * s2;
             double Dj = U0 + s1 * U1 + s2 * U2;
             uu = e.tau - (ia[6] + s1 * ia[7] + s2 * ia[8]);
-            if (lc.has_lim) {
-                double viol = 0.0;
-                if (e.q > lc.lim_hi) viol = e.q - lc.lim_hi;
-                else if (e.q < lc.lim_lo) viol = e.q - lc.lim_lo;
-                if (viol != 0.0) {
-                    double cl = pp.d_lim + dt * pp.k_lim;
-                    uu += -pp.k_lim * viol - cl * e.qd;
-                    Dj += dt * cl;
-                }
+            {
+                // one-sided implicit spring-damper at the joint limits (branch-free: the range of a free joint is infinite)
+                const double viol = fmax(e.q - lc.lim_hi, 0.0) + fmin(e.q - lc.lim_lo, 0.0);
+                const double cl = (viol != 0.0) ? pp.d_lim + dt * pp.k_lim : 0.0;
+                uu -= pp.k_lim * viol + cl * e.qd;
+                Dj += dt * cl;
             }
             dinv = 1.0 / Dj;
             // Ia = IA - U U^T / D ;  pa = pA + Ia c + U u / D
@@ -885,8 +892,18 @@ __device__ __forceinline__ void store_env(Lane& L, const LinkC& lc, const EnvReg
 
 // ================================================================================================ the kernel
 // flags: bit0 do_ctrl (finish env-step k), bit1 do_phys (start env-step k+1), bit2 end of outer update
-__global__ void __launch_bounds__(kBlockThreads, 4)
-trl_step_kernel(Buffers B, double h, int flags) {
+// Catch-up launch bookkeeping: every warp calls this once when it is done; the last one of the grid re-arms the consumed list.
+__device__ __forceinline__ void catchup_leave(const Buffers& B, int prev) {
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) {
+        __threadfence();
+        const int total = (int)gridDim.x * kWarpsPerBlock;
+        if (atomicAdd(B.catchup_done, 1) == total - 1) { B.pending_count[prev] = 0; *B.catchup_done = 0; __threadfence(); }
+    }
+}
+
+__global__ void __launch_bounds__(kBlockThreads, TRL_STEP_MIN_BLOCKS)
+trl_step_kernel(Buffers B, double h, int flags, int lists) {
     __shared__ double s_clx[4 * kMaxJoints], s_cly[4 * kMaxJoints];
     __shared__ int s_cbody[4 * kMaxJoints];
     __shared__ double s_x[kWarpsPerBlock * X_END];
@@ -896,9 +913,28 @@ trl_step_kernel(Buffers B, double h, int flags) {
     }
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int env = blockIdx.x * kWarpsPerBlock + warp;
-    if (env >= B.n) return;
+    // pending-decision lists: envs that reach a cycle boundary in this launch are appended to list `app`; `prev` is the
+    // list the previous env-step filled.  An env's I_PENDING tag is 1 + the list it was last appended to.
+    const int app = lists & 1, prev = (lists >> 1) & 1;
+    int env = blockIdx.x * kWarpsPerBlock + warp;
+    if (flags & kStepCatchUp) {
+        // catch-up launch: one warp per entry of the previous step's list, after the decision kernel has served it.
+        // The last CTA to leave re-arms that list (the main launch of the step after next appends to it again).
+        const int count = B.pending_count[prev];
+        if (env >= count) { catchup_leave(B, prev); return; }
+        env = B.pending_list[prev * B.n + env];
+    } else if (env >= B.n) {
+        return;
+    }
     Lane L{nullptr, env, B.n, B.d, B.i};
+    if (flags & kStepSkipPending) {
+        // overlapped main launch: envs waiting for the previous step's decision are stepped by the catch-up launch
+        const int tag = L.i(I_PENDING);
+        if (tag == 1 + prev) return;
+        if (tag == 1 + app && lane == 0) L.i(I_PENDING) = 0;   // stale tag of two steps ago (already caught up)
+    } else if (!(flags & kStepCatchUp) && (flags & 1) && lane == 0) {
+        L.i(I_PENDING) = 0;    // serial schedule: every decision has been served before this launch
+    }
     double* xs = s_x + warp * X_END;
     const LinkC lc = load_link(lane);
     EnvRegs e;
@@ -969,7 +1005,10 @@ trl_step_kernel(Buffers B, double h, int flags) {
         GroundView g = load_ground(L, B);
         const int ns = m.num_sim_substeps;
         const double dt = h / ns;
-        for (int s = 0; s < ns; ++s) contact = physics_substep(lc, e, g, s_clx, s_cly, s_cbody, lane, dt);
+        // terrain maximum over the window the character's corners can reach during this env-step; kClearMargin covers the
+        // contact tolerance measured along the surface normal on (near-)vertical cliff faces and the root's travel
+        const double clear_y = g.window_max(e.ox - m.reach - 0.25, e.ox + m.reach + 0.25, lane) + kClearMargin;
+        for (int s = 0; s < ns; ++s) contact = physics_substep(lc, e, g, s_clx, s_cly, s_cbody, lane, dt, clear_y);
         // UpdateGround (scenarios/ScenarioSimChar.cpp:564-572): regenerate a segment when the view window crosses it
         {
             int smin = g.seg_id(0), smax = g.seg_id(1);
@@ -1024,13 +1063,14 @@ trl_step_kernel(Buffers B, double h, int flags) {
             if (lane == 0) {
                 B.com_stash[env] = comx; B.com_stash[B.n + env] = comy;
                 L.i(I_FIRST_CYCLE) = 0;
-                L.i(I_PENDING) = 1;
-                int slot = atomicAdd(B.pending_count, 1);
-                B.pending_list[slot] = env;
+                L.i(I_PENDING) = 1 + app;
+                int slot = atomicAdd(&B.pending_count[app], 1);
+                B.pending_list[app * B.n + slot] = env;
             }
         }
     }
     store_env(L, lc, e, lane);
+    if (flags & kStepCatchUp) catchup_leave(B, prev);
 }
 
 // Initial reset of every env (trl_create / trl_reset): seeds the terrain RNG and runs the episode reset.
@@ -1114,9 +1154,9 @@ void launch_stats(const Buffers& B, double* out, cudaStream_t st) { trl_stats_ke
 cudaError_t upload_model(const ModelConst& mc) { return cudaMemcpyToSymbol(c_model, &mc, sizeof(ModelConst)); }
 size_t step_smem_bytes() { return 0; }
 cudaError_t configure_step_kernels() { return cudaSuccess; }
-void launch_step(const Buffers& B, double h, int flags, cudaStream_t st) {
+void launch_step(const Buffers& B, double h, int flags, int lists, cudaStream_t st) {
     int blocks = (B.n + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    trl_step_kernel<<<blocks, kBlockThreads, 0, st>>>(B, h, flags);
+    trl_step_kernel<<<blocks, kBlockThreads, 0, st>>>(B, h, flags, lists);
 }
 void launch_reset(const Buffers& B, const uint64_t* seeds, const int* env_ids, int count, int reseed, cudaStream_t st) {
     int blocks = (count + kWarpsPerBlock - 1) / kWarpsPerBlock;

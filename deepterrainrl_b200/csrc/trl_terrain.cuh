@@ -310,6 +310,45 @@ struct GroundView {
         return sample_seg(id, x, slope);
     }
 
+    // sample() for the contact pass: same vertices and lerp, with the two divisions by the vertex spacing replaced by
+    // multiplications with its reciprocal (differs from sample() by an ulp or two; policy features and resets keep the
+    // division so that they stay bit-identical to cGroundVar2D::SampleHeight)
+    __device__ __forceinline__ double sample_fast(double x, double* slope) const {
+        const double inv_sp = 1.0 / TRL_VERT_SPACING_D;
+        const int ms = seg_id(0);
+        const int id = (x >= seg_max_x(ms)) ? seg_id(1) : ms;
+        const float* d = data + id * kTerrainCap;
+        const int w = n[id] < kTerrainCap ? n[id] : kTerrainCap;
+        double coord = (x - min_x[id]) * inv_sp;
+        coord = fmin(fmax(coord, 0.0), (double)(w - 1));
+        const int i = (int)coord;
+        const int j = min(w - 1, i + 1);
+        const double lerp = coord - (double)i;
+        const double a = (double)d[i], b = (double)d[j];
+        *slope = (b - a) * inv_sp;
+        return a + lerp * (b - a);
+    }
+
+    // Upper bound of sample(x) over x in [x0, x1]: max of the vertices either segment can interpolate between for that
+    // window (clamped sampling maps x outside a segment to its end vertex, which the clamped index range includes).
+    // Warp-cooperative; every lane returns the same value.
+    __device__ double window_max(double x0, double x1, int lane) const {
+        float mx = -INFINITY;
+#pragma unroll
+        for (int id = 0; id < 2; ++id) {
+            const int w = n[id] < kTerrainCap ? n[id] : kTerrainCap;
+            if (w <= 0) continue;
+            const float* d = data + id * kTerrainCap;
+            const double c0 = fmin(fmax((x0 - min_x[id]) / TRL_VERT_SPACING_D, 0.0), (double)(w - 1));
+            const double c1 = fmin(fmax((x1 - min_x[id]) / TRL_VERT_SPACING_D, 0.0), (double)(w - 1));
+            const int i0 = (int)c0, i1 = min(w - 1, (int)c1 + 1);
+            for (int i = i0 + lane; i <= i1; i += 32) mx = fmaxf(mx, d[i]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        return (double)mx;
+    }
+
     // cGroundVar2D::BuildSegment + AddPadding
     __device__ void build_segment(int id, double bmin, double bmax, bool align_min, double fix_y, int type,
                                   const double* params, double seg_width) {

@@ -82,6 +82,7 @@ struct ModelConst {
     int corner_body[4 * kMaxJoints];
     double corner_lx[4 * kMaxJoints], corner_ly[4 * kMaxJoints];   // corner position in the link (joint) frame
     int corner_base[kMaxJoints];           // first corner index of a body (-1 if not collidable)
+    double reach;                          // upper bound of |box corner - root joint| over all poses
     unsigned anc_mask_toe, anc_mask_finger;   // links on the chain effector -> root (inclusive)
     unsigned vf_mask_toe, vf_mask_finger;     // links that receive the virtual force (chain up to root / torso, exclusive)
     // PD
@@ -139,8 +140,9 @@ struct Buffers {
     double* tuple_sbeg;    // [n][S]
     double* tuple_action;  // [n][kNumParams]
     double* com_stash;     // [2][n]   COM at decision time
-    int* pending_list;     // [n]
-    int* pending_count;    // [1]
+    int* pending_list;     // [2][n]  two lists, used alternately by successive env-steps (see trl_host.cu: enqueue_update)
+    int* pending_count;    // [2]
+    int* catchup_done;     // [1]     CTA completion counter of the catch-up launch (re-arms the list it consumed)
     // outputs
     double* tuples;        // [tuple_cap][1 + S + A + S]
     uint32_t* tuple_flags; // [tuple_cap]

@@ -32,7 +32,8 @@ def build_library(force=False, verbose=False):
         return out
     os.makedirs(os.path.dirname(out), exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + srcs
+    extra = os.environ.get("TRL_NVCC_EXTRA", "").split()     # developer knob (e.g. -DTRL_STEP_MIN_BLOCKS=7)
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + srcs
     subprocess.run(cmd, check=True)
     return out
 
