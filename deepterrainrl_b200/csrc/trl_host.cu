@@ -29,8 +29,20 @@ void launch_decide(const Buffers& B, const NetWeights& W, const ExpSettings& ex,
 void launch_stats(const Buffers& B, double* out, cudaStream_t st);
 void launch_terrain(const Buffers& B, double lookahead, cudaStream_t st);
 }  // namespace trl
+namespace trl_cg {
+cudaError_t upload_model(const trl::ModelConst& mc);
+void launch_step(const trl::Buffers& B, double h, int flags, int lists, cudaStream_t st);
+}  // namespace trl_cg
 
 using namespace trl;
+
+// both builds of the step kernels keep their own copy of the model constants
+struct trl_handle;
+static const trl_handle* g_model_owner = nullptr;    // whose ModelConst currently sits in the __constant__ copies
+static cudaError_t upload_model_all(const ModelConst& mc) {
+    cudaError_t e = trl::upload_model(mc);
+    return e != cudaSuccess ? e : trl_cg::upload_model(mc);
+}
 
 static thread_local std::string g_err;
 static int fail(const std::string& msg) { g_err = msg; return 1; }
@@ -78,6 +90,16 @@ struct trl_handle {
     double* snap_host = nullptr;     // pinned mirror
     bool snap_pending = false;
 };
+
+// The kernels read the scene from __constant__ memory, of which there is one copy per process: a handle that is not the
+// current owner re-uploads its model (after draining the owner's work) before it launches anything.
+static int ensure_model(trl_handle* h) {
+    if (g_model_owner == h) return 0;
+    if (cudaDeviceSynchronize() != cudaSuccess) return 1;
+    if (upload_model_all(h->mc) != cudaSuccess) return 1;
+    g_model_owner = h;
+    return 0;
+}
 
 template <typename T>
 static cudaError_t dalloc(trl_handle* h, T** p, size_t count) {
@@ -358,7 +380,7 @@ static void enqueue_update(trl_handle* h, double dt, bool overlap) {
         const int app = i & 1, prev = (i - 1) & 1, lists = app | (prev << 1);
         cudaStreamWaitEvent(S, ev_s[i - 1], 0);
         launch_decide(h->B, h->W, h->ex, h->done_count, h->decide_grid, prev, 0, S);
-        launch_step(h->B, step, 1 | 2 | 16, lists, S);
+        trl_cg::launch_step(h->B, step, 1 | 2 | 16, lists, S);
         cudaEventRecord(ev_c[i], S);
         if (i >= 2) cudaStreamWaitEvent(A, ev_c[i - 1], 0);
         launch_step(h->B, step, 1 | 2 | 8, lists, A);
@@ -439,7 +461,8 @@ static trl_handle* create_common(trl_handle* h, int num_envs, int device, int mo
         if (e != cudaSuccess) { g_err = std::string(what) + ": " + cudaGetErrorString(e); return false; }
         return true;
     };
-    if (!ck(upload_model(h->mc), "upload_model")) return bail("");
+    g_model_owner = nullptr;
+    if (ensure_model(h)) return bail("upload_model failed");
     if (!ck(configure_step_kernels(), "configure_step_kernels")) return bail("");
     if (!ck(configure_decide_kernel(), "configure_decide_kernel")) return bail("");
     Buffers& B = h->B;
@@ -488,6 +511,7 @@ static trl_handle* create_common(trl_handle* h, int num_envs, int device, int mo
 
 int trl_destroy(trl_handle* h) {
     if (!h) return 0;
+    if (g_model_owner == h) g_model_owner = nullptr;
     if (h->stream) cudaStreamSynchronize(h->stream);
     destroy_graphs(h);
     if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
@@ -503,6 +527,7 @@ int trl_destroy(trl_handle* h) {
 }
 
 int trl_seed_terrain(trl_handle* h, const uint64_t* seeds, int n) {
+    if (ensure_model(h)) return fail("model upload failed");
     uint64_t* d_seeds = nullptr;
     if (seeds) {
         if (n != h->n) return fail("trl_seed_terrain: need one seed per env");
@@ -519,6 +544,7 @@ int trl_seed_terrain(trl_handle* h, const uint64_t* seeds, int n) {
 }
 
 int trl_reset(trl_handle* h, const int32_t* env_ids, int n) {
+    if (ensure_model(h)) return fail("model upload failed");
     int* d_ids = nullptr;
     int count = h->n;
     if (env_ids) {
@@ -535,6 +561,7 @@ int trl_reset(trl_handle* h, const int32_t* env_ids, int n) {
 }
 
 int trl_update(trl_handle* h, double dt) {
+    if (ensure_model(h)) return fail("model upload failed");
     if (!(dt > 0)) return 0;
     const int nlaunch = update_launches(h, h->overlap);
     if (h->use_graph) {
@@ -561,6 +588,7 @@ int trl_update(trl_handle* h, double dt) {
 }
 
 int trl_env_step(trl_handle* h, double step) {
+    if (ensure_model(h)) return fail("model upload failed");
     launch_step(h->B, step, 2, 0, h->stream);
     launch_decide(h->B, h->W, h->ex, h->done_count, h->decide_grid, 0, 1, h->stream);
     launch_step(h->B, step, 1, 0, h->stream);
@@ -584,7 +612,8 @@ int trl_set_explore(trl_handle* h, int enable, double rate, double temp, double 
 int trl_set_phys_params(trl_handle* h, const double* p) {
     CK(cudaStreamSynchronize(h->stream));
     h->mc.phys = PhysParams{p[0], p[1], p[2], p[3], p[4], p[5], p[6]};
-    CK(upload_model(h->mc));
+    g_model_owner = nullptr;
+    if (ensure_model(h)) return fail("model upload failed");
     return 0;
 }
 
@@ -597,7 +626,8 @@ int trl_set_weights(trl_handle* h, const double* const* blobs, const int64_t* co
     int64_t vcounts[4] = {h->mc.n_in, h->mc.n_in, h->mc.n_out, h->mc.n_out};
     if (upload_net(h, blobs, counts, vecs, vcounts)) return 1;
     for (int k = 0; k < h->mc.frag; ++k) h->mc.out_scale_actor0[k] = out_scale[h->mc.n_frags + k];
-    CK(upload_model(h->mc));
+    g_model_owner = nullptr;
+    if (ensure_model(h)) return fail("model upload failed");
     return 0;
 }
 
@@ -795,6 +825,7 @@ int64_t trl_kernel_launches(trl_handle* h) { return h->launches; }
 // Micro-benchmark of the decision kernel: marks the first `n_pending` envs as pending (their policy state is whatever the
 // last real decision left) and times `iters` launches.  Perturbs those envs' actions: measurement use only.
 int trl_debug_time_decide(trl_handle* h, int n_pending, int iters, double* ms_avg) {
+    if (ensure_model(h)) return fail("model upload failed");
     if (n_pending > h->n) n_pending = h->n;
     std::vector<int> ids(n_pending);
     for (int i = 0; i < n_pending; ++i) ids[i] = i;
@@ -875,6 +906,7 @@ int trl_device_tuple_block(trl_handle* h, void** rows_f64, void** flags_u32, voi
 // K outer updates timed with CUDA events on the handle's own stream (the stream the kernels are launched on);
 // optionally evicts L2 between updates by writing a 256 MiB scratch buffer.
 int trl_bench_updates(trl_handle* h, double dt, int k, int flush_l2, double* ms_total) {
+    if (ensure_model(h)) return fail("model upload failed");
     const size_t flush_bytes = (size_t)256 << 20;
     if (flush_l2 && !h->flush_buf) { CK(cudaMalloc(&h->flush_buf, flush_bytes)); h->allocs.push_back(h->flush_buf); }
     cudaEvent_t e0, e1;
@@ -907,6 +939,7 @@ int trl_update_timed_detail(trl_handle* h, double dt, double* per_step, double* 
 }
 static int update_timed_impl(trl_handle* h, double dt, double* step_ms, int* step_launches, double* decide_ms, int* decide_launches,
                              double* per_step, double* per_decide) {
+    if (ensure_model(h)) return fail("model upload failed");
     const int ns = h->num_update_steps;
     const double step = dt / ns;
     std::vector<cudaEvent_t> ev(2 * (2 * ns + 1));

@@ -28,7 +28,18 @@
 #include "trl_terrain.cuh"
 #include "trl_types.h"
 
-namespace trl {
+// The file is compiled twice: as is (namespace trl), and through trl_step_cg.cu with -Xptxas -dlcm=cg (namespace trl_cg), where
+// every global load bypasses L1.  The cg build serves the catch-up launches of the overlapped schedule: they read env state the
+// decision kernel has just written, while step CTAs running on the same SM may already have pulled the neighbouring envs'
+// words of the same 32-byte sectors into that SM's L1.
+#ifdef TRL_CG_VARIANT
+#define TRL_IMPL_NS trl_cg
+#else
+#define TRL_IMPL_NS trl
+#endif
+
+namespace TRL_IMPL_NS {
+using namespace trl;
 
 __constant__ ModelConst c_model;
 
@@ -1163,6 +1174,8 @@ void launch_reset(const Buffers& B, const uint64_t* seeds, const int* env_ids, i
     trl_reset_kernel<<<blocks, kBlockThreads, 0, st>>>(B, seeds, env_ids, count, reseed);
 }
 
-}  // namespace trl
+}  // namespace TRL_IMPL_NS
 
+#ifndef TRL_CG_VARIANT
 #include "trl_decide.cuh"
+#endif

@@ -14,8 +14,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 _LIB = None
 
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
-              "-shared"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
 
 
 def library_path():
@@ -23,18 +22,32 @@ def library_path():
 
 
 def build_library(force=False, verbose=False):
-    """Compile csrc/*.cu for sm_100a into lib/libterrainrl_b200.so (nvcc cross-compiles without a GPU)."""
+    """Compile csrc/*.cu for sm_100a into lib/libterrainrl_b200.so (nvcc cross-compiles without a GPU).
+    trl_step_cg.cu is the env-step translation unit again with -Xptxas -dlcm=cg (L1-bypassing loads, see trl_step.cu)."""
     out = library_path()
-    srcs = [os.path.join(_PKG, "csrc", f) for f in ("trl_step.cu", "trl_host.cu", "ref_loader.cpp")]
-    deps = [os.path.join(_PKG, "csrc", f) for f in os.listdir(os.path.join(_PKG, "csrc"))]
+    csrc = os.path.join(_PKG, "csrc")
+    units = [("trl_step.cu", []), ("trl_step_cg.cu", ["-Xptxas", "-dlcm=cg"]), ("trl_host.cu", []), ("ref_loader.cpp", [])]
+    deps = [os.path.join(csrc, f) for f in os.listdir(csrc)]
     deps.append(os.path.join(_ROOT, "include", "terrainrl_b200.h"))
     if not force and os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in deps):
         return out
-    os.makedirs(os.path.dirname(out), exist_ok=True)
+    objdir = os.path.join(_PKG, "lib", "obj")
+    os.makedirs(objdir, exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     extra = os.environ.get("TRL_NVCC_EXTRA", "").split()     # developer knob (e.g. -DTRL_STEP_MIN_BLOCKS=7)
-    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + srcs
-    subprocess.run(cmd, check=True)
+
+    def compile_unit(unit):
+        name, flags = unit
+        obj = os.path.join(objdir, os.path.splitext(name)[0] + ".o")
+        cmd = [nvcc] + NVCC_FLAGS + extra + flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj,
+                                                                                              os.path.join(csrc, name)]
+        subprocess.run(cmd, check=True)
+        return obj
+
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(len(units)) as ex:
+        objs = list(ex.map(compile_unit, units))
+    subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", out] + objs, check=True)
     return out
 
 

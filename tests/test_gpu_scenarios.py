@@ -195,3 +195,25 @@ def test_overlap_matches_serial(assets, monkeypatch):
     np.testing.assert_array_equal(ea[ka], eb[kb])
     np.testing.assert_array_equal(fa[ka], fb[kb])
     np.testing.assert_array_equal(ra[ka], rb[kb])
+
+
+def test_two_scenes_interleaved(assets):
+    """Two handles with different scenes alive in one process: the scene constants are re-uploaded on every switch, so
+    interleaved updates give the same states as running each scene alone."""
+    import deepterrainrl_b200 as trl
+    dog = os.path.join(assets, "dog_slopes_mixed.trlpack")
+    rap = os.path.join(assets, "raptor_narrow_gaps.trlpack")
+    a = trl.ScenarioPoliEval(dog, 32)
+    for _ in range(6):
+        a.Update(1.0 / 30.0)
+    qa = a.GetStateAll()[0].copy()
+    b = trl.ScenarioPoliEval(rap, 32)
+    for _ in range(6):
+        b.Update(1.0 / 30.0)
+    qb = b.GetStateAll()[0].copy()
+    a2 = trl.ScenarioPoliEval(dog, 32)
+    b2 = trl.ScenarioPoliEval(rap, 32)
+    for _ in range(6):
+        a2.Update(1.0 / 30.0); b2.Update(1.0 / 30.0)
+    np.testing.assert_array_equal(a2.GetStateAll()[0], qa)
+    np.testing.assert_array_equal(b2.GetStateAll()[0], qb)
