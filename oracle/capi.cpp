@@ -5,6 +5,7 @@
 #include <vector>
 
 #include "env.h"
+#include "trainer.h"
 
 using namespace orc;
 
@@ -165,4 +166,98 @@ int orc_dist_log(OrcBatch* b, int env, double* out, int cap) {
     return n;
 }
 
+
+// ---------------------------------------------------------------------------------------- MACE trainer (oracle/trainer.h)
+struct OrcTrainer {
+    Scene scene;
+    MaceTrainer tr;
+};
+// p[10]: replay_cap, num_init_samples, num_steps_per_iter, freeze_target_iters, init_input_offset_scale, discount, base_lr,
+//        momentum, weight_decay, seed
+OrcTrainer* orc_trainer_create(const char* pack_path, const double* p) {
+    try {
+        auto* t = new OrcTrainer();
+        t->scene.load(pack_path);
+        if (!t->scene.net.valid) throw std::runtime_error("scene has no policy net");
+        TrainerParams P;
+        P.replay_cap = (int)p[0]; P.num_init_samples = (int)p[1]; P.num_steps_per_iter = (int)p[2]; P.freeze_target_iters = (int)p[3];
+        P.init_input_offset_scale = (int)p[4]; P.discount = p[5]; P.base_lr = p[6]; P.momentum = p[7]; P.weight_decay = p[8];
+        P.seed = (uint64_t)p[9];
+        t->tr.init(t->scene.net, P);
+        return t;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return nullptr;
+    }
+}
+void orc_trainer_destroy(OrcTrainer* t) { delete t; }
+int orc_trainer_num_params(OrcTrainer* t) { return (int)t->tr.net.theta.size(); }
+int orc_trainer_tuple_width(OrcTrainer* t) { return t->tr.Wd; }
+void orc_trainer_add_tuples(OrcTrainer* t, const double* rows, const uint32_t* flags, int n) {
+    for (int i = 0; i < n; ++i) t->tr.add_tuple(rows + (size_t)i * t->tr.Wd, flags[i]);
+}
+void orc_trainer_train(OrcTrainer* t) { t->tr.train(); }
+void orc_trainer_get_rows(OrcTrainer* t, const int32_t* ids, int n, float* rows, int32_t* flags) {
+    for (int i = 0; i < n; ++i) {
+        std::memcpy(rows + (size_t)i * t->tr.Wd, t->tr.row(ids[i]), sizeof(float) * t->tr.Wd);
+        flags[i] = t->tr.flags[ids[i]];
+    }
+}
+// what: 0 theta, 1 target theta, 2 history, 3 in_off, 4 in_scale, 5 out_off, 6 out_scale
+void orc_trainer_get(OrcTrainer* t, int what, double* out) {
+    const std::vector<double>* v = nullptr;
+    switch (what) {
+        case 0: v = &t->tr.net.theta; break;
+        case 1: v = &t->tr.target.theta; break;
+        case 2: v = &t->tr.history; break;
+        case 3: v = &t->tr.net.in_off; break;
+        case 4: v = &t->tr.net.in_scale; break;
+        case 5: v = &t->tr.net.out_off; break;
+        default: v = &t->tr.net.out_scale; break;
+    }
+    std::memcpy(out, v->data(), v->size() * 8);
+}
+void orc_trainer_set_theta(OrcTrainer* t, const double* theta) { std::memcpy(t->tr.net.theta.data(), theta, t->tr.net.theta.size() * 8); }
+// counters: iter, actor_iter, stage, num, head, total, critic_count, actor_count, actor_batch_count
+void orc_trainer_counters(OrcTrainer* t, int64_t* c) {
+    c[0] = t->tr.iter; c[1] = t->tr.actor_iter; c[2] = t->tr.stage; c[3] = t->tr.num; c[4] = t->tr.head; c[5] = t->tr.total;
+    c[6] = (int64_t)t->tr.critic_buf.size(); c[7] = (int64_t)t->tr.actor_buf.size(); c[8] = (int64_t)t->tr.actor_batch.size();
+}
+void orc_trainer_losses(OrcTrainer* t, double* l) { l[0] = t->tr.last_critic_loss; l[1] = t->tr.last_actor_loss; }
+int orc_trainer_lists(OrcTrainer* t, int which, int32_t* out, int cap) {
+    const std::vector<int>& v = which == 0 ? t->tr.critic_buf : (which == 1 ? t->tr.actor_buf : (which == 2 ? t->tr.actor_batch :
+                                (which == 3 ? t->tr.last_critic_ids : t->tr.last_actor_ids)));
+    int n = std::min((int)v.size(), cap);
+    for (int i = 0; i < n; ++i) out[i] = v[i];
+    return (int)v.size();
+}
+// Euclidean loss and its gradient for an un-normalised problem (X [B][S], Y [B][n_out]) at the current weights; no update.
+double orc_trainer_loss_grad(OrcTrainer* t, const double* X, const double* Y, int B, double* grad_out) {
+    MaceNet& net = t->tr.net;
+    const int S = net.tp.n_in, no = net.tp.n_out;
+    std::vector<double> xn((size_t)B * S), dy((size_t)B * no), grad;
+    for (int n = 0; n < B; ++n)
+        for (int i = 0; i < S; ++i) xn[(size_t)n * S + i] = (X[(size_t)n * S + i] + net.in_off[i]) * net.in_scale[i];
+    BatchActs acts;
+    net.forward(B, xn.data(), acts);
+    double loss = 0;
+    for (int n = 0; n < B; ++n)
+        for (int i = 0; i < no; ++i) {
+            double lab = (Y[(size_t)n * no + i] + net.out_off[i]) * net.out_scale[i];
+            double d = acts.y[(size_t)n * no + i] - lab;
+            loss += d * d;
+            dy[(size_t)n * no + i] = d / B;
+        }
+    loss /= 2.0 * B;
+    if (grad_out) {
+        net.backward(B, acts, dy.data(), grad);
+        std::memcpy(grad_out, grad.data(), grad.size() * 8);
+    }
+    return loss;
+}
+void orc_trainer_eval_batch(OrcTrainer* t, int target, const double* X, int B, double* Y) {
+    std::vector<double> y;
+    (target ? t->tr.target : t->tr.net).eval_batch(B, X, y);
+    std::memcpy(Y, y.data(), y.size() * 8);
+}
 }  // extern "C"

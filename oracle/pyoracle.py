@@ -157,3 +157,107 @@ class Oracle:
         d = np.zeros(cap)
         n = self.L.orc_dist_log(self.h, env, _p(d), cap)
         return d[:n].copy()
+
+
+class OracleTrainer:
+    """CPU restatement of cMACETrainer + the Caffe SGD solver step (oracle/trainer.h)."""
+
+    DEFAULTS = dict(replay_cap=500000, num_init_samples=200, num_steps_per_iter=1, freeze_target_iters=0,
+                    init_input_offset_scale=1, discount=0.9, base_lr=1e-3, momentum=0.9, weight_decay=5e-4, seed=1)
+
+    def __init__(self, pack, **kw):
+        self.L = lib()
+        L = self.L
+        L.orc_trainer_create.restype = C.c_void_p
+        L.orc_trainer_create.argtypes = [C.c_char_p, C.c_void_p]
+        L.orc_trainer_loss_grad.restype = C.c_double
+        for name in ("orc_trainer_destroy", "orc_trainer_add_tuples", "orc_trainer_train", "orc_trainer_get",
+                     "orc_trainer_set_theta", "orc_trainer_counters", "orc_trainer_losses", "orc_trainer_eval_batch"):
+            getattr(L, name).restype = None
+        p = dict(self.DEFAULTS)
+        p.update(kw)
+        self.params = p
+        arr = np.array([p[k] for k in ("replay_cap", "num_init_samples", "num_steps_per_iter", "freeze_target_iters",
+                                       "init_input_offset_scale", "discount", "base_lr", "momentum", "weight_decay", "seed")], float)
+        h = L.orc_trainer_create(pack.encode(), _p(arr))
+        if not h:
+            raise RuntimeError(L.orc_last_error().decode())
+        self.h = C.c_void_p(h)
+        self.num_params = L.orc_trainer_num_params(self.h)
+        self.W = L.orc_trainer_tuple_width(self.h)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.orc_trainer_destroy(self.h)
+            self.h = None
+
+    def add_tuples(self, rows, flags):
+        rows = np.ascontiguousarray(rows, np.float64)
+        flags = np.ascontiguousarray(flags, np.uint32)
+        assert rows.shape[1] == self.W
+        self.L.orc_trainer_add_tuples(self.h, _p(rows), _p(flags), rows.shape[0])
+
+    def train(self):
+        self.L.orc_trainer_train(self.h)
+
+    def get(self, what, n=None):
+        idx = {"theta": 0, "target": 1, "history": 2, "in_off": 3, "in_scale": 4, "out_off": 5, "out_scale": 6}[what]
+        if n is None:
+            n = self.num_params if idx < 3 else (self.n_in if idx < 5 else self.n_out)
+        out = np.zeros(n)
+        self.L.orc_trainer_get(self.h, idx, _p(out))
+        return out
+
+    def set_theta(self, theta):
+        theta = np.ascontiguousarray(theta, np.float64)
+        self.L.orc_trainer_set_theta(self.h, _p(theta))
+
+    def counters(self):
+        c = np.zeros(9, np.int64)
+        self.L.orc_trainer_counters(self.h, _p(c))
+        return dict(zip(("iter", "actor_iter", "stage", "num", "head", "total", "critic", "actor", "actor_batch"), c.tolist()))
+
+    def losses(self):
+        l = np.zeros(2)
+        self.L.orc_trainer_losses(self.h, _p(l))
+        return l
+
+    def lists(self, which, cap=1 << 20):
+        out = np.zeros(cap, np.int32)
+        n = self.L.orc_trainer_lists(self.h, {"critic": 0, "actor": 1, "actor_batch": 2, "last_critic": 3, "last_actor": 4}[which], _p(out), cap)
+        return out[:n].copy()
+
+    def rows(self, ids):
+        ids = np.ascontiguousarray(ids, np.int32)
+        rows = np.zeros((ids.size, self.W), np.float32)
+        flags = np.zeros(ids.size, np.int32)
+        self.L.orc_trainer_get_rows.restype = None
+        self.L.orc_trainer_get_rows(self.h, _p(ids), ids.size, _p(rows), _p(flags))
+        return rows, flags
+
+    def loss_grad(self, X, Y, want_grad=True):
+        X = np.ascontiguousarray(X, np.float64); Y = np.ascontiguousarray(Y, np.float64)
+        g = np.zeros(self.num_params) if want_grad else None
+        loss = self.L.orc_trainer_loss_grad(self.h, _p(X), _p(Y), X.shape[0], _p(g))
+        return loss, g
+
+    def eval_batch(self, X, target=False):
+        X = np.ascontiguousarray(X, np.float64)
+        Y = np.zeros((X.shape[0], self.n_out))
+        self.L.orc_trainer_eval_batch(self.h, int(target), _p(X), X.shape[0], _p(Y))
+        return Y
+
+    @property
+    def n_in(self):
+        return (self.W - 1 - self._a()) // 2
+
+    def _a(self):
+        # tuple row = 1 + S + A + S with A = 1 + frag; frag is 29 (dog) / 28 (raptor): S = (W - 1 - A) / 2 must be integral
+        for a in (30, 29):
+            if (self.W - 1 - a) % 2 == 0:
+                return a
+        raise RuntimeError("unexpected tuple width")
+
+    @property
+    def n_out(self):
+        return 3 + 3 * (self._a() - 1)
