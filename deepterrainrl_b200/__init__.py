@@ -9,3 +9,4 @@ from .scenario import (BatchedScenario, ScenarioExpMACE, ScenarioPoliEval, build
                        load_library, pack_from_args)
 
 __all__ = ["BatchedScenario", "ScenarioExpMACE", "ScenarioPoliEval", "build_library", "library_path", "load_library", "pack_from_args"]
+from .trainer import MACETrainer  # noqa: F401,E402

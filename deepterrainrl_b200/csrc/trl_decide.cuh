@@ -271,13 +271,14 @@ __device__ void net_forward_cluster(cg::cluster_group& cluster, const NetWeights
 }
 
 __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kDecideThreads, 2)
-trl_decide_kernel(Buffers B, NetWeights W, ExpSettings ex, int* done_count, int list, int rearm) {
+trl_decide_kernel(Buffers B, NetWeights W, const ExpSettings* __restrict__ ex_dev, int* done_count, int list, int rearm) {
     extern __shared__ double sh[];
     cg::cluster_group cluster = cg::this_cluster();
     const ModelConst& m = c_model;
     const int rank = (int)cluster.block_rank();
     const int cid = blockIdx.x / kClusterSize, ncl = gridDim.x / kClusterSize;
     const int count = B.pending_count[list];
+    const ExpSettings ex = *ex_dev;
     for (int idx = cid; idx < count; idx += ncl) {
         const int env = B.pending_list[list * B.n + idx];
         Lane L{nullptr, env, B.n, B.d, B.i};
@@ -364,7 +365,7 @@ size_t decide_smem_bytes() { return (size_t)kDecideSmemDoubles * sizeof(double);
 cudaError_t configure_decide_kernel() {
     return cudaFuncSetAttribute(trl_decide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decide_smem_bytes());
 }
-void launch_decide(const Buffers& B, const NetWeights& W, const ExpSettings& ex, int* done_count, int grid, int list, int rearm,
+void launch_decide(const Buffers& B, const NetWeights& W, const ExpSettings* ex, int* done_count, int grid, int list, int rearm,
                    cudaStream_t st) {
     trl_decide_kernel<<<grid, kDecideThreads, decide_smem_bytes(), st>>>(B, W, ex, done_count, list, rearm);
 }

@@ -1,0 +1,55 @@
+// deepterrainrl_b200 -- the batch handle behind the C ABI (private to csrc/: trl_host.cu, trl_train.cu)
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "scene_pack.h"
+#include "trl_types.h"
+
+struct trl_trainer;
+
+struct trl_handle {
+    trl_trainer* trainer = nullptr;      // attached MACE trainer (trl_train.cu), owns the policy weights when present
+    int device = 0, n = 0, mode = 0;
+    trl::ScenePack scene;
+    trl::ModelConst mc;
+    trl::ExpSettings ex;                      // host copy; the kernels read the device copy d_ex
+    trl::ExpSettings* d_ex = nullptr;
+    trl::Buffers B;
+    trl::NetWeights W;
+    std::vector<double*> net_blobs;      // 26 + 4 device arrays
+    std::vector<int64_t> net_counts;
+    int* done_count = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaStream_t aux_stream = nullptr;           // high-priority side stream: decisions + catch-up launches (overlapped schedule)
+    std::vector<cudaEvent_t> fork_events;        // dependencies between the two streams inside one update
+    bool overlap = true;                         // TRL_SERIAL_SCHEDULE=1 turns the overlapped schedule off
+    int decide_grid = 288;   // multiple of the 8-CTA cluster size
+    int num_update_steps = 20;
+    int64_t launches = 0;
+    std::map<long long, cudaGraphExec_t> graphs;   // keyed by the bit pattern of dt
+    bool use_graph = true;
+    // host staging
+    std::vector<double> h_tuples;
+    std::vector<float> h_tuples_f32;
+    std::vector<uint32_t> h_tuple_flags;
+    std::vector<int32_t> h_tuple_env;
+    std::vector<double> h_dist;
+    std::vector<int32_t> h_dist_env;
+    std::vector<void*> allocs;
+    void* flush_buf = nullptr;
+    // pipelined read-back (trl_snapshot / trl_snapshot_wait)
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t snap_ready = nullptr, snap_copied = nullptr;
+    double* snap_dev = nullptr;      // [2 * ndof * n + 4] device staging (pose planes, vel planes, stats)
+    double* snap_host = nullptr;     // pinned mirror
+    bool snap_pending = false;
+};
+
+// shared by the translation units behind the C ABI
+int trl_fail(const std::string& msg);                 // records the message for trl_last_error(), returns 1
+void trl_drop_graphs(trl_handle* h);                  // captured graphs bake kernel arguments (weight pointers) in

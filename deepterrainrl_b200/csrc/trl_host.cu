@@ -24,7 +24,7 @@ void launch_step(const Buffers& B, double h, int flags, int lists, cudaStream_t 
 void launch_reset(const Buffers& B, const uint64_t* seeds, const int* env_ids, int count, int reseed, cudaStream_t st);
 size_t decide_smem_bytes();
 cudaError_t configure_decide_kernel();
-void launch_decide(const Buffers& B, const NetWeights& W, const ExpSettings& ex, int* done_count, int grid, int list, int rearm,
+void launch_decide(const Buffers& B, const NetWeights& W, const ExpSettings* ex, int* done_count, int grid, int list, int rearm,
                    cudaStream_t st);
 void launch_stats(const Buffers& B, double* out, cudaStream_t st);
 void launch_terrain(const Buffers& B, double lookahead, cudaStream_t st);
@@ -46,6 +46,7 @@ static cudaError_t upload_model_all(const ModelConst& mc) {
 
 static thread_local std::string g_err;
 static int fail(const std::string& msg) { g_err = msg; return 1; }
+int trl_fail(const std::string& msg) { return fail(msg); }
 #define CK(call)                                                                                   \
     do {                                                                                           \
         cudaError_t e__ = (call);                                                                  \
@@ -55,41 +56,7 @@ static int fail(const std::string& msg) { g_err = msg; return 1; }
 static const char* kNetLayers[13] = {"terr_conv0", "terr_conv1", "terr_conv2", "terr_ip0", "ip0", "val_ip0", "val_ip1",
                                      "a0_ip0", "a0_ip1", "a1_ip0", "a1_ip1", "a2_ip0", "a2_ip1"};
 
-struct trl_handle {
-    int device = 0, n = 0, mode = 0;
-    ScenePack scene;
-    ModelConst mc;
-    ExpSettings ex;
-    Buffers B;
-    NetWeights W;
-    std::vector<double*> net_blobs;      // 26 + 4 device arrays
-    std::vector<int64_t> net_counts;
-    int* done_count = nullptr;
-    cudaStream_t stream = nullptr;
-    cudaStream_t aux_stream = nullptr;           // high-priority side stream: decisions + catch-up launches (overlapped schedule)
-    std::vector<cudaEvent_t> fork_events;        // dependencies between the two streams inside one update
-    bool overlap = true;                         // TRL_SERIAL_SCHEDULE=1 turns the overlapped schedule off
-    int decide_grid = 288;   // multiple of the 8-CTA cluster size
-    int num_update_steps = 20;
-    int64_t launches = 0;
-    std::map<long long, cudaGraphExec_t> graphs;   // keyed by the bit pattern of dt
-    bool use_graph = true;
-    // host staging
-    std::vector<double> h_tuples;
-    std::vector<float> h_tuples_f32;
-    std::vector<uint32_t> h_tuple_flags;
-    std::vector<int32_t> h_tuple_env;
-    std::vector<double> h_dist;
-    std::vector<int32_t> h_dist_env;
-    std::vector<void*> allocs;
-    void* flush_buf = nullptr;
-    // pipelined read-back (trl_snapshot / trl_snapshot_wait)
-    cudaStream_t copy_stream = nullptr;
-    cudaEvent_t snap_ready = nullptr, snap_copied = nullptr;
-    double* snap_dev = nullptr;      // [2 * ndof * n + 4] device staging (pose planes, vel planes, stats)
-    double* snap_host = nullptr;     // pinned mirror
-    bool snap_pending = false;
-};
+#include "trl_handle.h"
 
 // The kernels read the scene from __constant__ memory, of which there is one copy per process: a handle that is not the
 // current owner re-uploads its model (after draining the owner's work) before it launches anything.
@@ -298,7 +265,7 @@ static int fill_model(trl_handle* h, uint64_t rng_seed) {
         for (int i = 0; i < kTerrainParams; ++i) m.terrain_params[i] = (1 - lerp) * tp[i0 * kTerrainParams + i] + lerp * tp[i1 * kTerrainParams + i];
     }
     m.phys = PhysParams{2.0e5, 2.0e3, 0.81, 0.01, 0.00025, 2.0e4, 20.0};
-    h->ex = ExpSettings{h->mode == TRL_MODE_EXPLORE ? 1 : 0, mf[4], mf[5], mf[6], m.exp_noise};
+    h->ex = ExpSettings{h->mode == TRL_MODE_EXPLORE ? 1 : 0, mf[4], mf[5], mf[6], m.exp_noise};   // uploaded by create_common
     if (m.has_net) {
         const auto& nd = s.i32("net_dims");
         m.n_in = nd[0]; m.n_char = nd[1]; m.n_out = nd[2]; m.n_frags = nd[3]; m.frag = nd[4];
@@ -336,6 +303,8 @@ static int upload_net(trl_handle* h, const double* const* blobs, const int64_t* 
     return 0;
 }
 
+static void destroy_graphs(trl_handle* h);
+void trl_drop_graphs(trl_handle* h) { destroy_graphs(h); }
 static void destroy_graphs(trl_handle* h) {
     for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second);
     h->graphs.clear();
@@ -362,7 +331,7 @@ static void enqueue_update(trl_handle* h, double dt, bool overlap) {
     if (!overlap) {
         for (int i = 0; i < ns; ++i) {
             launch_step(h->B, step, i == 0 ? 2 : 3, 0, A);
-            launch_decide(h->B, h->W, h->ex, h->done_count, h->decide_grid, 0, 1, A);
+            launch_decide(h->B, h->W, h->d_ex, h->done_count, h->decide_grid, 0, 1, A);
         }
         launch_step(h->B, step, 1 | 4, 0, A);
         return;
@@ -379,7 +348,7 @@ static void enqueue_update(trl_handle* h, double dt, bool overlap) {
     for (int i = 1; i < ns; ++i) {
         const int app = i & 1, prev = (i - 1) & 1, lists = app | (prev << 1);
         cudaStreamWaitEvent(S, ev_s[i - 1], 0);
-        launch_decide(h->B, h->W, h->ex, h->done_count, h->decide_grid, prev, 0, S);
+        launch_decide(h->B, h->W, h->d_ex, h->done_count, h->decide_grid, prev, 0, S);
         trl_cg::launch_step(h->B, step, 1 | 2 | 16, lists, S);
         cudaEventRecord(ev_c[i], S);
         if (i >= 2) cudaStreamWaitEvent(A, ev_c[i - 1], 0);
@@ -387,7 +356,7 @@ static void enqueue_update(trl_handle* h, double dt, bool overlap) {
         cudaEventRecord(ev_s[i], A);
     }
     cudaStreamWaitEvent(S, ev_s[ns - 1], 0);
-    launch_decide(h->B, h->W, h->ex, h->done_count, h->decide_grid, (ns - 1) & 1, 1, S);
+    launch_decide(h->B, h->W, h->d_ex, h->done_count, h->decide_grid, (ns - 1) & 1, 1, S);
     cudaEventRecord(ev_c[ns], S);
     cudaStreamWaitEvent(A, ev_c[ns], 0);
     launch_step(h->B, step, 1 | 4, 0, A);
@@ -484,7 +453,8 @@ static trl_handle* create_common(trl_handle* h, int num_envs, int device, int mo
               ck(dalloc(h, &B.tuple_flags, (size_t)B.tuple_cap), "alloc tf") && ck(dalloc(h, &B.tuple_env, (size_t)B.tuple_cap), "alloc te") &&
               ck(dalloc(h, &B.tuple_count, 1), "alloc tc") && ck(dalloc(h, &B.dist_log, (size_t)B.dist_cap), "alloc dl") &&
               ck(dalloc(h, &B.dist_env, (size_t)B.dist_cap), "alloc de") && ck(dalloc(h, &B.dist_count, 1), "alloc dc") &&
-              ck(dalloc(h, &h->done_count, 1), "alloc done");
+              ck(dalloc(h, &h->done_count, 1), "alloc done") && ck(dalloc(h, &h->d_ex, 1), "alloc ex");
+    if (ok) ok = ck(cudaMemcpy(h->d_ex, &h->ex, sizeof(ExpSettings), cudaMemcpyHostToDevice), "upload ex");
     if (!ok) return bail("");
     if (h->mc.has_net) {
         const double* blobs[26];
@@ -590,7 +560,7 @@ int trl_update(trl_handle* h, double dt) {
 int trl_env_step(trl_handle* h, double step) {
     if (ensure_model(h)) return fail("model upload failed");
     launch_step(h->B, step, 2, 0, h->stream);
-    launch_decide(h->B, h->W, h->ex, h->done_count, h->decide_grid, 0, 1, h->stream);
+    launch_decide(h->B, h->W, h->d_ex, h->done_count, h->decide_grid, 0, 1, h->stream);
     launch_step(h->B, step, 1, 0, h->stream);
     h->launches += 3;
     CK(cudaGetLastError());
@@ -603,9 +573,10 @@ int trl_sync(trl_handle* h) {
 }
 
 int trl_set_explore(trl_handle* h, int enable, double rate, double temp, double base_rate) {
-    CK(cudaStreamSynchronize(h->stream));
+    // the decision kernel reads the settings from device memory, so annealing them every update (cScenarioTrain::CalcExpRate
+    // ...) neither re-captures the update graph nor drains the stream: the copy is ordered behind the work already queued
     h->ex.enable = enable; h->ex.rate = rate; h->ex.temp = temp; h->ex.base_rate = base_rate;
-    destroy_graphs(h);   // kernel parameters are baked into captured graphs
+    CK(cudaMemcpyAsync(h->d_ex, &h->ex, sizeof(ExpSettings), cudaMemcpyHostToDevice, h->stream));
     return 0;
 }
 
@@ -621,6 +592,7 @@ int trl_set_weights(trl_handle* h, const double* const* blobs, const int64_t* co
                     const double* in_scale, const double* out_off, const double* out_scale) {
     if (nblobs != 26) return fail("trl_set_weights: expected 26 blobs");
     if (!h->mc.has_net) return fail("trl_set_weights: scene has no policy net");
+    if (h->trainer) return fail("trl_set_weights: a trainer owns the policy weights (use trl_trainer_set_theta)");
     CK(cudaStreamSynchronize(h->stream));
     const double* vecs[4] = {in_off, in_scale, out_off, out_scale};
     int64_t vcounts[4] = {h->mc.n_in, h->mc.n_in, h->mc.n_out, h->mc.n_out};
@@ -836,7 +808,7 @@ int trl_debug_time_decide(trl_handle* h, int n_pending, int iters, double* ms_av
         CK(cudaMemcpyAsync(h->B.pending_list, ids.data(), (size_t)n_pending * 4, cudaMemcpyHostToDevice, h->stream));
         CK(cudaMemcpyAsync(h->B.pending_count, &n_pending, 4, cudaMemcpyHostToDevice, h->stream));
         CK(cudaEventRecord(e0, h->stream));
-        launch_decide(h->B, h->W, h->ex, h->done_count, h->decide_grid, 0, 1, h->stream);
+        launch_decide(h->B, h->W, h->d_ex, h->done_count, h->decide_grid, 0, 1, h->stream);
         CK(cudaEventRecord(e1, h->stream));
         CK(cudaEventSynchronize(e1));
         float ms = 0;
@@ -951,7 +923,7 @@ static int update_timed_impl(trl_handle* h, double dt, double* step_ms, int* ste
         launch_step(h->B, step, i == 0 ? 2 : 3, 0, h->stream);
         CK(cudaEventRecord(ev[k++], h->stream));
         CK(cudaEventRecord(ev[k++], h->stream));
-        launch_decide(h->B, h->W, h->ex, h->done_count, h->decide_grid, 0, 1, h->stream);
+        launch_decide(h->B, h->W, h->d_ex, h->done_count, h->decide_grid, 0, 1, h->stream);
         CK(cudaEventRecord(ev[k++], h->stream));
     }
     CK(cudaEventRecord(ev[k++], h->stream));

@@ -1,0 +1,802 @@
+// deepterrainrl_b200 -- MACE trainer on the GPU: the consumer of the experience tuples.
+//
+// cMACETrainer (learning/MACETrainer.cpp) + cNeuralNetTrainer (learning/NeuralNetTrainer.cpp) in synchronous mode, pool size 1,
+// with the pieces of Caffe they drive written as CUDA kernels: batch-32 forward / backward of the MACE topology
+// (data/policies/dog/nets/dog_mace3_train.prototxt) in f64 like Caffe's Net<double>, the EuclideanLoss over the normalised outputs
+// and the SGD step of dog_mace3_solver.prototxt (lr 1e-3 fixed, momentum 0.9, L2 weight decay 5e-4, per-blob lr_mult / decay_mult).
+// The replay memory (float rows [r | s | a | s'], learning/MACETrainer.cpp:515-539), the critic / actor index buffers
+// (UpdateBuffers, :730-800), the positive-temporal-difference actor batch (:575-626) and the target net (:844-856) all live in
+// HBM; tuples arrive device-to-device from the rollout engine's tuple block, and the engine evaluates the trainer's weights in
+// place (cNeuralNetLearner::SyncNet becomes a pointer binding), so a training iteration involves no host copy.
+//
+// Control flow that depends on buffer sizes (critic batch available? actor batch full? target refresh due?) is decided on the
+// device: every kernel of a step starts by reading its predicate from the counter block and returns if it is off.  That
+// makes one cNeuralNetTrainer::Train() a fixed launch sequence, captured once as a CUDA graph.
+//
+// CPU restatement used by the tests: oracle/trainer.h.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/terrainrl_b200.h"
+#include "trl_handle.h"
+
+namespace trl_train {
+using namespace trl;
+
+constexpr int kB = 32;                               // MemoryData batch_size
+constexpr int C0 = 16, K0 = 8, W0 = 193, C1 = 32, K1 = 4, W1 = 190, C2 = 32, K2 = 4, W2 = 187, T = 64, H = 256, HH = 128;
+constexpr int kTerr = 200;                           // terrain samples at the head of the policy state
+
+enum Pred { P_ALWAYS = 0, P_CRITIC, P_CAND, P_ACTOR, P_INIT };
+
+struct Counters {
+    int head, num, iter, actor_iter, stage, critic_count, actor_count, actor_batch_count;
+    long long total;
+    unsigned long long rng_ctr;
+    int critic_ok, cand_count, actor_ok, succ, init_now, pad;
+    double critic_loss, actor_loss;
+};
+
+struct Dev {
+    int S, A, Wd, n_char, n_out, n_frags, frag, cap, P, cat;
+    int off[27];
+    double *theta, *target, *history, *grad;
+    double *in_off, *in_scale, *out_off, *out_scale;             // current net
+    double *t_in_off, *t_in_scale, *t_out_off, *t_out_scale;     // target net
+    float* mem;
+    int *flags, *pos_critic, *pos_actor, *critic_list, *actor_list, *actor_batch;
+    Counters* c;
+    int *valid, *slot, *ids, *cand;
+    double *xn, *a0, *a1, *a2, *t, *catb, *h, *hh, *y;           // activations of the most recent forward pass (kB rows)
+    double *v0, *v1;
+    double *dy, *dhh, *dh, *dt, *da2, *da1, *da0;
+    double *mean;
+    double discount, base_lr, momentum, weight_decay;
+    int freeze, nis, init_offset_scale, steps_per_iter;
+    unsigned long long rng_key;
+};
+
+__device__ __forceinline__ bool pred_on(const Dev& d, int pred) {
+    switch (pred) {
+        case P_CRITIC: return d.c->critic_ok != 0;
+        case P_CAND: return d.c->cand_count > 0;
+        case P_ACTOR: return d.c->actor_ok != 0;
+        case P_INIT: return d.c->init_now != 0;
+        default: return true;
+    }
+}
+__device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__device__ __forceinline__ int rand_int(const Dev& d, int mn, int mx) {      // cMathUtil::RandInt(min, max), counter RNG
+    if (mn == mx) return mn;
+    unsigned long long v = mix64(d.rng_key + (d.c->rng_ctr++) * 0xD1342543DE82EF95ull);
+    int r = (int)(v >> 33);
+    return mn + r % (mx - mn);
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ================================================================================================ replay memory
+// cNeuralNetTrainer::CheckTuple (learning/NeuralNetTrainer.cpp:541-576): one block per incoming tuple
+__global__ void k_add_check(Dev d, const double* rows, const int* count_ptr, int count_val) {
+    const int count = count_ptr ? *count_ptr : count_val;
+    const int i = blockIdx.x;
+    if (i >= count) return;
+    const double* r = rows + (size_t)i * d.Wd;
+    int bad = 0;
+    for (int k = threadIdx.x; k < d.Wd; k += blockDim.x) bad |= !isfinite(r[k]);
+    bad = __syncthreads_or(bad);
+    if (threadIdx.x == 0) d.valid[i] = !bad;
+}
+__device__ void list_remove(int* list, int* pos, int& count, int t) {
+    const int p = pos[t];
+    if (p < 0) return;
+    const int last = list[count - 1];
+    list[p] = last; pos[last] = p;
+    pos[t] = -1;
+    --count;
+}
+// cNeuralNetTrainer::AddTuple slot assignment + cMACETrainer::UpdateBuffers, in arrival order (one thread: O(1) per tuple)
+__global__ void k_add_assign(Dev d, const uint32_t* src_flags, const int* count_ptr, int count_val, int* reset_count) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int count = count_ptr ? *count_ptr : count_val;
+    Counters& c = *d.c;
+    for (int i = 0; i < count; ++i) {
+        if (!d.valid[i]) { d.slot[i] = -1; continue; }
+        const int t = c.head;
+        d.slot[i] = t;
+        c.head = (c.head + 1) % d.cap;
+        c.num = min(d.cap, c.num + 1);
+        ++c.total;
+        const bool ea = (src_flags[i] & 4u) != 0;          // eFlagExpActor
+        if (ea) {
+            if (d.pos_actor[t] < 0) { d.pos_actor[t] = c.actor_count; d.actor_list[c.actor_count++] = t; }
+            list_remove(d.critic_list, d.pos_critic, c.critic_count, t);
+        } else {
+            if (d.pos_critic[t] < 0) { d.pos_critic[t] = c.critic_count; d.critic_list[c.critic_count++] = t; }
+            list_remove(d.actor_list, d.pos_actor, c.actor_count, t);
+        }
+        for (int k = 0; k < c.actor_batch_count;) {        // the overwritten slot leaves the pending actor batch
+            if (d.actor_batch[k] == t) d.actor_batch[k] = d.actor_batch[--c.actor_batch_count];
+            else ++k;
+        }
+    }
+    if (reset_count) *reset_count = 0;                     // cScenarioExp::ResetTupleBuffer
+}
+__global__ void k_add_copy(Dev d, const double* rows, const uint32_t* src_flags, const int* count_ptr, int count_val) {
+    const int count = count_ptr ? *count_ptr : count_val;
+    const int i = blockIdx.x;
+    if (i >= count) return;
+    const int t = d.slot[i];
+    if (t < 0) return;
+    const double* r = rows + (size_t)i * d.Wd;
+    float* dst = d.mem + (size_t)t * d.Wd;
+    for (int k = threadIdx.x; k < d.Wd; k += blockDim.x) dst[k] = (float)r[k];     // SetTuple stores floats
+    if (threadIdx.x == 0) d.flags[t] = (int)src_flags[i];
+}
+
+// ================================================================================================ stage switch
+__global__ void k_stage_check(Dev d) {
+    Counters& c = *d.c;
+    c.init_now = 0;
+    c.succ = 0;
+    if (c.stage == 0) {
+        const int nis = min(d.nis, d.cap);
+        if (c.num >= nis && c.num > 0) c.init_now = (nis > 1 && d.init_offset_scale) ? 1 : 2;   // 2: switch without refit
+    }
+}
+// cNeuralNet::CalcOffsetScale (learning/NeuralNet.cpp:280-313) over the state-begin columns of the replay memory
+__global__ void k_col_mean(Dev d) {
+    if (d.c->init_now != 1) return;
+    const int j = blockIdx.x, num = d.c->num;
+    double s = 0;
+    for (int t = threadIdx.x; t < num; t += blockDim.x) s += (double)d.mem[(size_t)t * d.Wd + 1 + j];
+    __shared__ double red[32];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += red[w];
+        d.mean[j] = tot / num;
+    }
+}
+__global__ void k_col_scale(Dev d) {
+    if (d.c->init_now != 1) return;
+    const int j = blockIdx.x, num = d.c->num;
+    const double m = d.mean[j];
+    double s = 0;
+    for (int t = threadIdx.x; t < num; t += blockDim.x) { double x = (double)d.mem[(size_t)t * d.Wd + 1 + j] - m; s += x * x; }
+    __shared__ double red[32];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += red[w];
+        const double sd = sqrt(tot / num);
+        d.in_off[j] = -m; d.in_scale[j] = sd == 0 ? 0 : 1.0 / sd;
+        d.t_in_off[j] = d.in_off[j]; d.t_in_scale[j] = d.in_scale[j];       // SetInputOffsetScale reaches every net of the pool
+    }
+}
+__global__ void k_stage_commit(Dev d) {
+    if (d.c->init_now) d.c->stage = 1;
+}
+
+// ================================================================================================ sampling
+// cMACETrainer::FetchMinibatch (learning/MACETrainer.cpp:164-188)
+__global__ void k_sample_critic(Dev d) {
+    if (threadIdx.x != 0) return;
+    Counters& c = *d.c;
+    const bool ok = c.stage == 1 && c.critic_count >= kB;
+    c.critic_ok = ok;
+    c.succ = ok;
+    if (!ok) return;
+    for (int i = 0; i < kB; ++i) d.ids[i] = d.critic_list[rand_int(d, 0, c.critic_count)];
+}
+// cMACETrainer::FetchActorMinibatch (learning/MACETrainer.cpp:190-214)
+__global__ void k_sample_actor(Dev d) {
+    if (threadIdx.x != 0) return;
+    Counters& c = *d.c;
+    c.cand_count = 0;
+    c.actor_ok = 0;
+    if (c.stage != 1) return;
+    const int n_exp = c.actor_count, ns = min(kB, n_exp);
+    int nc = 0;
+    for (int i = 0; i < ns; ++i) {
+        const int t = d.actor_list[rand_int(d, 0, n_exp)];
+        bool contains = false;
+        for (int k = 0; k < c.actor_batch_count && !contains; ++k) contains = d.actor_batch[k] == t;
+        for (int k = 0; k < nc && !contains; ++k) contains = d.cand[k] == t;
+        if (!contains) d.cand[nc++] = t;
+    }
+    c.cand_count = nc;
+    for (int i = 0; i < kB; ++i) d.ids[i] = nc > 0 ? d.cand[i < nc ? i : 0] : 0;    // pad the batch with the first candidate
+}
+// UpdateActorBatchBuffer's test (learning/MACETrainer.cpp:556-573) + the batch for cMACETrainer::StepActor
+__global__ void k_actor_select(Dev d) {
+    if (threadIdx.x != 0) return;
+    Counters& c = *d.c;
+    if (c.stage != 1) return;
+    for (int i = 0; i < c.cand_count; ++i)
+        if (d.v1[i] > d.v0[i]) d.actor_batch[c.actor_batch_count++] = d.cand[i];
+    c.actor_ok = c.actor_batch_count >= kB;
+    if (c.actor_ok)
+        for (int i = 0; i < kB; ++i) d.ids[i] = d.actor_batch[i];
+}
+__global__ void k_actor_pop(Dev d) {
+    if (threadIdx.x != 0) return;
+    Counters& c = *d.c;
+    if (!c.actor_ok) return;
+    for (int i = kB; i < c.actor_batch_count; ++i) d.actor_batch[i - kB] = d.actor_batch[i];
+    c.actor_batch_count -= kB;
+    ++c.actor_iter;
+}
+__global__ void k_end_iter(Dev d) {
+    if (threadIdx.x == 0 && d.c->succ) ++d.c->iter;       // cNeuralNetTrainer::ApplySteps / IncIter
+}
+// cMACETrainer::Step's target refresh (learning/MACETrainer.cpp:350-358): uses the iteration count before IncIter
+__global__ void k_target_update(Dev d) {
+    const Counters& c = *d.c;
+    if (!(c.stage == 1 && d.freeze > 0 && c.iter > 0 && c.iter % d.freeze == 0)) return;
+    const int stride = gridDim.x * blockDim.x, tid = blockIdx.x * blockDim.x + threadIdx.x;
+    for (int i = tid; i < d.P; i += stride) d.target[i] = d.theta[i];
+    for (int i = tid; i < d.S; i += stride) { d.t_in_off[i] = d.in_off[i]; d.t_in_scale[i] = d.in_scale[i]; }
+    for (int i = tid; i < d.n_out; i += stride) { d.t_out_off[i] = d.out_off[i]; d.t_out_scale[i] = d.out_scale[i]; }
+}
+
+// ================================================================================================ forward
+// rows ids[0..kB) of the replay memory, columns [col0, col0 + S), normalised like cNeuralNet::NormalizeInput
+__global__ void k_gather_norm(Dev d, int pred, int col0, const double* in_off, const double* in_scale) {
+    if (!pred_on(d, pred)) return;
+    const int n = blockIdx.x;
+    const float* r = d.mem + (size_t)d.ids[n] * d.Wd + col0;
+    for (int i = threadIdx.x; i < d.S; i += blockDim.x) d.xn[(size_t)n * d.S + i] = ((double)r[i] + in_off[i]) * in_scale[i];
+}
+// Convolution (cross-correlation, stride 1) + ReLU.  grid (cout, kB), one thread per output position.
+__global__ void k_conv_fwd(Dev d, int pred, const double* x, int ldn, int cin, int win, const double* w, const double* b, int cout, int k,
+                           double* y) {
+    if (!pred_on(d, pred)) return;
+    __shared__ double ws[C1 * K1 > C0 * K0 ? C1 * K2 : C0 * K0];      // cin * k <= 128
+    const int o = blockIdx.x, n = blockIdx.y, wout = win - k + 1;
+    for (int i = threadIdx.x; i < cin * k; i += blockDim.x) ws[i] = w[(size_t)o * cin * k + i];
+    __syncthreads();
+    const int t = threadIdx.x;
+    if (t >= wout) return;
+    double acc = b[o];
+    const double* xr = x + (size_t)n * ldn;
+    for (int c = 0; c < cin; ++c)
+        for (int kk = 0; kk < k; ++kk) acc += ws[c * k + kk] * xr[(size_t)c * win + t + kk];
+    y[((size_t)n * cout + o) * wout + t] = acc > 0 ? acc : 0;
+}
+// InnerProduct (+ optional ReLU): one block per output neuron, all kB rows at once so each weight is read once.
+__global__ void k_fc_fwd(Dev d, int pred, const double* x, int ldx, int nin, const double* w, const double* b, int relu, double* y, int ldy) {
+    if (!pred_on(d, pred)) return;
+    const int o = blockIdx.x, tid = threadIdx.x;
+    double acc[kB];
+#pragma unroll
+    for (int n = 0; n < kB; ++n) acc[n] = 0.0;
+    const double* wr = w + (size_t)o * nin;
+    for (int i = tid; i < nin; i += blockDim.x) {
+        const double wv = wr[i];
+#pragma unroll
+        for (int n = 0; n < kB; ++n) acc[n] += wv * x[(size_t)n * ldx + i];
+    }
+    __shared__ double red[8][kB];
+#pragma unroll
+    for (int n = 0; n < kB; ++n) {
+        double v = warp_sum(acc[n]);
+        if ((tid & 31) == 0) red[tid >> 5][n] = v;
+    }
+    __syncthreads();
+    if (tid < kB) {
+        double s = b[o];
+        for (int wq = 0; wq < (int)(blockDim.x >> 5); ++wq) s += red[wq][tid];
+        y[(size_t)tid * ldy + o] = (relu && s < 0) ? 0 : s;
+    }
+}
+__global__ void k_concat(Dev d, int pred) {        // concat0: [terr_relu3 | char features]
+    if (!pred_on(d, pred)) return;
+    const int n = blockIdx.x;
+    for (int i = threadIdx.x; i < d.cat; i += blockDim.x)
+        d.catb[(size_t)n * d.cat + i] = i < T ? d.t[(size_t)n * T + i] : d.xn[(size_t)n * d.S + kTerr + (i - T)];
+}
+
+// ================================================================================================ labels + loss
+// max over the critic outputs of the un-normalised target-net output (GetMaxFragValAux) -> v0 (state begin) or the Bellman
+// value r (1 - gamma) + gamma max V'(s') -> v1 (CalcNewCumulativeRewardBatch, learning/MACETrainer.cpp:472-513)
+__global__ void k_vals(Dev d, int pred, int with_reward, double* out) {
+    if (!pred_on(d, pred)) return;
+    const int n = threadIdx.x;
+    if (n >= kB) return;
+    double m = -INFINITY;
+    for (int f = 0; f < d.n_frags; ++f) m = fmax(m, d.y[(size_t)n * d.n_out + f] / d.t_out_scale[f] - d.t_out_off[f]);
+    if (with_reward) {
+        const int t = d.ids[n];
+        const double r = (double)d.mem[(size_t)t * d.Wd] * (1.0 - d.discount);
+        m = (d.flags[t] & 1) ? r : r + d.discount * m;       // eFlagFail
+    }
+    out[n] = m;
+}
+// BuildProblemY / BuildActorProblemY + LoadTrainData's label normalisation + EuclideanLoss gradient.
+// mode 0: critic (value of the taken actor <- v1), mode 1: actor (fragment of the taken actor <- the action taken)
+__global__ void k_labels(Dev d, int pred, int mode) {
+    if (!pred_on(d, pred)) return;
+    const int no = d.n_out;
+    double part = 0;
+    for (int idx = threadIdx.x; idx < kB * no; idx += blockDim.x) {
+        const int n = idx / no, j = idx - n * no;
+        const float* r = d.mem + (size_t)d.ids[n] * d.Wd;
+        const int a = (int)r[1 + d.S];
+        const double yraw = d.y[idx];
+        double Y = yraw / d.out_scale[j] - d.out_off[j];                         // cNeuralNet::EvalBatch un-normalises
+        if (mode == 0) { if (j == a) Y = d.v1[n]; }
+        else if (j >= d.n_frags + a * d.frag && j < d.n_frags + (a + 1) * d.frag) Y = (double)r[1 + d.S + 1 + (j - d.n_frags - a * d.frag)];
+        const double lab = (Y + d.out_off[j]) * d.out_scale[j];                  // LoadTrainData normalises again
+        const double df = yraw - lab;
+        part += df * df;
+        d.dy[idx] = df / kB;
+    }
+    __shared__ double red[32];
+    part = warp_sum(part);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += red[w];
+        (mode == 0 ? d.c->critic_loss : d.c->actor_loss) = tot / (2.0 * kB);
+    }
+}
+
+// ================================================================================================ backward
+// dw[o][i] = sum_n dy[n][o] x[n][i], db[o] = sum_n dy[n][o].  grid (nout, ceil(nin / 256))
+__global__ void k_fc_bwd_w(Dev d, int pred, const double* dy, int ldy, const double* x, int ldx, int nin, double* dw, double* db) {
+    if (!pred_on(d, pred)) return;
+    __shared__ double dys[kB];
+    const int o = blockIdx.x;
+    if (threadIdx.x < kB) dys[threadIdx.x] = dy[(size_t)threadIdx.x * ldy + o];
+    __syncthreads();
+    const int i = blockIdx.y * blockDim.x + threadIdx.x;
+    if (i < nin) {
+        double s = 0;
+#pragma unroll
+        for (int n = 0; n < kB; ++n) s += dys[n] * x[(size_t)n * ldx + i];
+        dw[(size_t)o * nin + i] = s;
+    }
+    if (blockIdx.y == 0 && threadIdx.x == 0) {
+        double s = 0;
+        for (int n = 0; n < kB; ++n) s += dys[n];
+        db[o] = s;
+    }
+}
+// dx[n][i] (=|+=) mask(act[n][i]) * sum_o dy[n][o] w[o][i] for i < ncols.  grid (ceil(ncols / 256), kB)
+__global__ void k_fc_bwd_x(Dev d, int pred, const double* dy, int ldy, int nout, const double* w, int nin, int ncols, const double* act,
+                           int lda, double* dx, int ldx, int accumulate) {
+    if (!pred_on(d, pred)) return;
+    __shared__ double dys[H];
+    const int n = blockIdx.y;
+    for (int o = threadIdx.x; o < nout; o += blockDim.x) dys[o] = dy[(size_t)n * ldy + o];
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ncols) return;
+    double s = 0;
+    for (int o = 0; o < nout; ++o) s += dys[o] * w[(size_t)o * nin + i];
+    if (act && !(act[(size_t)n * lda + i] > 0)) s = 0;
+    if (accumulate) dx[(size_t)n * ldx + i] += s; else dx[(size_t)n * ldx + i] = s;
+}
+// dw[o][c][kk] = sum_{n,t} dy[n][o][t] x[n][c][t + kk]; db[o] = sum dy[n][o][t].  grid (cin, cout)
+__global__ void k_conv_bwd_w(Dev d, int pred, const double* dy, int cout, int k, const double* x, int ldn, int cin, int win, double* dw,
+                             double* db) {
+    if (!pred_on(d, pred)) return;
+    const int c = blockIdx.x, o = blockIdx.y, wout = win - k + 1;
+    double acc[K0 + 1];
+#pragma unroll
+    for (int kk = 0; kk <= K0; ++kk) acc[kk] = 0.0;
+    for (int idx = threadIdx.x; idx < kB * wout; idx += blockDim.x) {
+        const int n = idx / wout, t = idx - n * wout;
+        const double g = dy[((size_t)n * cout + o) * wout + t];
+        const double* xr = x + (size_t)n * ldn + (size_t)c * win + t;
+#pragma unroll
+        for (int kk = 0; kk < K0; ++kk)
+            if (kk < k) acc[kk] += g * xr[kk];
+        acc[K0] += g;
+    }
+    __shared__ double red[8][K0 + 1];
+#pragma unroll
+    for (int kk = 0; kk <= K0; ++kk) {
+        double v = warp_sum(acc[kk]);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][kk] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x <= K0) {
+        double s = 0;
+        for (int wq = 0; wq < (int)(blockDim.x >> 5); ++wq) s += red[wq][threadIdx.x];
+        if (threadIdx.x < k) dw[((size_t)o * cin + c) * k + threadIdx.x] = s;
+        else if (threadIdx.x == K0 && c == 0) db[o] = s;
+    }
+}
+// dx[n][c][s] = mask * sum_{o,kk} dy[n][o][s - kk] w[o][c][kk].  grid (cin, kB), one thread per input position
+__global__ void k_conv_bwd_x(Dev d, int pred, const double* dy, int cout, int k, const double* w, int cin, int win, const double* act,
+                             double* dx) {
+    if (!pred_on(d, pred)) return;
+    __shared__ double ws[C2 * K2];            // cout * k <= 128
+    const int c = blockIdx.x, n = blockIdx.y, wout = win - k + 1;
+    for (int i = threadIdx.x; i < cout * k; i += blockDim.x) { int o = i / k, kk = i - o * k; ws[i] = w[((size_t)o * cin + c) * k + kk]; }
+    __syncthreads();
+    const int s = threadIdx.x;
+    if (s >= win) return;
+    double acc = 0;
+    for (int o = 0; o < cout; ++o) {
+        const double* g = dy + ((size_t)n * cout + o) * wout;
+        for (int kk = 0; kk < k; ++kk) {
+            const int t = s - kk;
+            if (t >= 0 && t < wout) acc += g[t] * ws[o * k + kk];
+        }
+    }
+    const size_t idx = ((size_t)n * cin + c) * win + s;
+    dx[idx] = (act[idx] > 0) ? acc : 0;
+}
+// Caffe SGDSolver: Regularize (L2) + ComputeUpdateValue + Net::Update, one pass over all 26 blobs
+__global__ void k_sgd(Dev d, int pred) {
+    if (!pred_on(d, pred)) return;
+    const int stride = gridDim.x * blockDim.x;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < d.P; i += stride) {
+        int b = 0;
+        while (i >= d.off[b + 1]) ++b;
+        const double rate = d.base_lr * ((b & 1) ? 2.0 : 1.0);
+        const double decay = d.weight_decay * ((b & 1) ? (b < 6 ? 1.0 : 0.0) : 1.0);
+        const double g = d.grad[i] + decay * d.theta[i];
+        const double hst = rate * g + d.momentum * d.history[i];
+        d.history[i] = hst;
+        d.theta[i] -= hst;
+    }
+}
+
+}  // namespace trl_train
+
+// ==================================================================================================== host side
+using trl_train::Dev;
+using trl_train::Counters;
+
+struct trl_trainer {
+    trl_handle* h = nullptr;
+    Dev d;
+    std::vector<void*> allocs;
+    cudaGraphExec_t train_graph = nullptr;
+    double* stage_rows = nullptr;      // device staging for tuples handed in from the host
+    uint32_t* stage_flags = nullptr;
+    int stage_cap = 0;
+    int64_t launches = 0;
+};
+
+#define TCK(call)                                                                                       \
+    do {                                                                                                \
+        cudaError_t e__ = (call);                                                                       \
+        if (e__ != cudaSuccess) return trl_fail(std::string(#call) + ": " + cudaGetErrorString(e__));   \
+    } while (0)
+
+namespace {
+using namespace trl_train;
+
+template <typename Tp>
+cudaError_t talloc(trl_trainer* t, Tp** p, size_t count) {
+    cudaError_t e = cudaMalloc((void**)p, std::max<size_t>(count, 1) * sizeof(Tp));
+    if (e == cudaSuccess) { t->allocs.push_back(*p); e = cudaMemset(*p, 0, std::max<size_t>(count, 1) * sizeof(Tp)); }
+    return e;
+}
+
+struct NetRef { const double* theta; const double *in_off, *in_scale; };
+
+// forward pass of the kB rows named by d.ids (replay columns starting at col0) through `net`; activations stay in d.*
+int enqueue_forward(trl_trainer* t, int pred, int col0, const NetRef& net, cudaStream_t st) {
+    const Dev& d = t->d;
+    const double* th = net.theta;
+    auto blob = [&](int b) { return th + d.off[b]; };
+    k_gather_norm<<<kB, 128, 0, st>>>(d, pred, col0, net.in_off, net.in_scale);
+    k_conv_fwd<<<dim3(C0, kB), 224, 0, st>>>(d, pred, d.xn, d.S, 1, kTerr, blob(0), blob(1), C0, K0, d.a0);
+    k_conv_fwd<<<dim3(C1, kB), 224, 0, st>>>(d, pred, d.a0, C0 * W0, C0, W0, blob(2), blob(3), C1, K1, d.a1);
+    k_conv_fwd<<<dim3(C2, kB), 224, 0, st>>>(d, pred, d.a1, C1 * W1, C1, W1, blob(4), blob(5), C2, K2, d.a2);
+    k_fc_fwd<<<T, 256, 0, st>>>(d, pred, d.a2, C2 * W2, C2 * W2, blob(6), blob(7), 1, d.t, T);
+    k_concat<<<kB, 160, 0, st>>>(d, pred);
+    k_fc_fwd<<<H, 256, 0, st>>>(d, pred, d.catb, d.cat, d.cat, blob(8), blob(9), 1, d.h, H);
+    int col = 0;
+    for (int hd = 0; hd < 4; ++hd) {
+        const int nout = hd == 0 ? d.n_frags : d.frag;
+        double* hh = d.hh + (size_t)hd * kB * HH;
+        k_fc_fwd<<<HH, 256, 0, st>>>(d, pred, d.h, H, H, blob(10 + 4 * hd), blob(11 + 4 * hd), 1, hh, HH);
+        k_fc_fwd<<<nout, 128, 0, st>>>(d, pred, hh, HH, HH, blob(12 + 4 * hd), blob(13 + 4 * hd), 0, d.y + col, d.n_out);
+        col += nout;
+    }
+    t->launches += 15;
+    return 0;
+}
+// backward of the current net from d.dy (activations of the last forward) into d.grad, then the SGD step
+int enqueue_backward_update(trl_trainer* t, int pred, cudaStream_t st) {
+    const Dev& d = t->d;
+    auto W = [&](int b) { return d.theta + d.off[b]; };
+    auto G = [&](int b) { return d.grad + d.off[b]; };
+    int col = 0;
+    for (int hd = 0; hd < 4; ++hd) {
+        const int nout = hd == 0 ? d.n_frags : d.frag;
+        double* hh = d.hh + (size_t)hd * kB * HH;
+        k_fc_bwd_w<<<dim3(nout, 1), 128, 0, st>>>(d, pred, d.dy + col, d.n_out, hh, HH, HH, G(12 + 4 * hd), G(13 + 4 * hd));
+        k_fc_bwd_x<<<dim3(1, kB), 128, 0, st>>>(d, pred, d.dy + col, d.n_out, nout, W(12 + 4 * hd), HH, HH, hh, HH, d.dhh, HH, 0);
+        k_fc_bwd_w<<<dim3(HH, 1), 256, 0, st>>>(d, pred, d.dhh, HH, d.h, H, H, G(10 + 4 * hd), G(11 + 4 * hd));
+        k_fc_bwd_x<<<dim3(1, kB), 256, 0, st>>>(d, pred, d.dhh, HH, HH, W(10 + 4 * hd), H, H, d.h, H, d.dh, H, hd > 0);
+        col += nout;
+    }
+    k_fc_bwd_w<<<dim3(H, 1), 256, 0, st>>>(d, pred, d.dh, H, d.catb, d.cat, d.cat, G(8), G(9));
+    k_fc_bwd_x<<<dim3(1, kB), 64, 0, st>>>(d, pred, d.dh, H, H, W(8), d.cat, T, d.t, T, d.dt, T, 0);          // only the terr_ip0 columns
+    const int nflat = C2 * W2;
+    k_fc_bwd_w<<<dim3(T, (nflat + 255) / 256), 256, 0, st>>>(d, pred, d.dt, T, d.a2, nflat, nflat, G(6), G(7));
+    k_fc_bwd_x<<<dim3((nflat + 255) / 256, kB), 256, 0, st>>>(d, pred, d.dt, T, T, W(6), nflat, nflat, d.a2, nflat, d.da2, nflat, 0);
+    k_conv_bwd_w<<<dim3(C1, C2), 256, 0, st>>>(d, pred, d.da2, C2, K2, d.a1, C1 * W1, C1, W1, G(4), G(5));
+    k_conv_bwd_x<<<dim3(C1, kB), 224, 0, st>>>(d, pred, d.da2, C2, K2, W(4), C1, W1, d.a1, d.da1);
+    k_conv_bwd_w<<<dim3(C0, C1), 256, 0, st>>>(d, pred, d.da1, C1, K1, d.a0, C0 * W0, C0, W0, G(2), G(3));
+    k_conv_bwd_x<<<dim3(C0, kB), 224, 0, st>>>(d, pred, d.da1, C1, K1, W(2), C0, W0, d.a0, d.da0);
+    k_conv_bwd_w<<<dim3(1, C0), 256, 0, st>>>(d, pred, d.da0, C0, K0, d.xn, d.S, 1, kTerr, G(0), G(1));
+    k_sgd<<<296, 256, 0, st>>>(d, pred);
+    t->launches += 26;
+    return 0;
+}
+// cNeuralNetTrainer::Train: UpdateStage, then num_steps_per_iter x cMACETrainer::Step, then IncIter
+int enqueue_train(trl_trainer* t, cudaStream_t st) {
+    const Dev& d = t->d;
+    const NetRef cur{d.theta, d.in_off, d.in_scale}, tar{d.target, d.t_in_off, d.t_in_scale};
+    const int col_beg = 1, col_end = 1 + d.S + d.A;
+    k_stage_check<<<1, 1, 0, st>>>(d);
+    k_col_mean<<<d.S, 256, 0, st>>>(d);
+    k_col_scale<<<d.S, 256, 0, st>>>(d);
+    k_stage_commit<<<1, 1, 0, st>>>(d);
+    t->launches += 4;
+    for (int s = 0; s < d.steps_per_iter; ++s) {
+        // ---- critic: BuildProblem + UpdateNet (learning/NeuralNetTrainer.cpp:414-456, MACETrainer.cpp:222-247)
+        k_sample_critic<<<1, 32, 0, st>>>(d);
+        enqueue_forward(t, P_CRITIC, col_end, tar, st);
+        k_vals<<<1, 32, 0, st>>>(d, P_CRITIC, 1, d.v1);
+        enqueue_forward(t, P_CRITIC, col_beg, cur, st);
+        k_labels<<<1, 256, 0, st>>>(d, P_CRITIC, 0);
+        enqueue_backward_update(t, P_CRITIC, st);
+        // ---- actor: UpdateActorBatchBuffer + UpdateActor (learning/MACETrainer.cpp:541-626)
+        k_sample_actor<<<1, 32, 0, st>>>(d);
+        enqueue_forward(t, P_CAND, col_beg, tar, st);
+        k_vals<<<1, 32, 0, st>>>(d, P_CAND, 0, d.v0);
+        enqueue_forward(t, P_CAND, col_end, tar, st);
+        k_vals<<<1, 32, 0, st>>>(d, P_CAND, 1, d.v1);
+        k_actor_select<<<1, 32, 0, st>>>(d);
+        enqueue_forward(t, P_ACTOR, col_beg, cur, st);
+        k_labels<<<1, 256, 0, st>>>(d, P_ACTOR, 1);
+        enqueue_backward_update(t, P_ACTOR, st);
+        k_actor_pop<<<1, 32, 0, st>>>(d);
+        k_target_update<<<148, 256, 0, st>>>(d);
+        t->launches += 10;
+    }
+    k_end_iter<<<1, 32, 0, st>>>(d);
+    t->launches += 1;
+    return 0;
+}
+
+int enqueue_add(trl_trainer* t, const double* rows, const uint32_t* flags, const int* count_ptr, int count_val, int max_count, int* reset,
+                cudaStream_t st) {
+    const Dev& d = t->d;
+    if (max_count <= 0) return 0;
+    k_add_check<<<max_count, 128, 0, st>>>(d, rows, count_ptr, count_val);
+    k_add_assign<<<1, 32, 0, st>>>(d, flags, count_ptr, count_val, reset);
+    k_add_copy<<<max_count, 128, 0, st>>>(d, rows, flags, count_ptr, count_val);
+    t->launches += 3;
+    return 0;
+}
+}  // namespace
+
+extern "C" {
+
+// p[10]: replay_cap, num_init_samples, num_steps_per_iter, freeze_target_iters, init_input_offset_scale, discount, base_lr,
+//        momentum, weight_decay, seed   (cTrainerInterface::tParams + the solver prototxt)
+trl_trainer* trl_trainer_create(trl_handle* h, const double* p) {
+    if (!h || !h->mc.has_net) { trl_fail("trl_trainer_create: the scene has no policy net"); return nullptr; }
+    if (h->trainer) { trl_fail("trl_trainer_create: a trainer is already attached"); return nullptr; }
+    auto* t = new trl_trainer();
+    t->h = h;
+    Dev& d = t->d;
+    std::memset(&d, 0, sizeof(d));
+    const ModelConst& m = h->mc;
+    d.S = m.n_in; d.n_char = m.n_char; d.n_out = m.n_out; d.n_frags = m.n_frags; d.frag = m.frag;
+    d.A = 1 + m.frag; d.Wd = 1 + d.S + d.A + d.S; d.cat = T + m.n_char;
+    d.cap = (int)p[0]; d.nis = (int)p[1]; d.steps_per_iter = std::max(1, (int)p[2]); d.freeze = (int)p[3];
+    d.init_offset_scale = (int)p[4]; d.discount = p[5]; d.base_lr = p[6]; d.momentum = p[7]; d.weight_decay = p[8];
+    {
+        // CounterRng::seed(seed, stream) of the engine, stream tag "tran"
+        auto mix = [](unsigned long long z) {
+            z += 0x9E3779B97F4A7C15ull;
+            z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+            z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+            return z ^ (z >> 31);
+        };
+        d.rng_key = mix((unsigned long long)p[9] ^ mix(0x7472616eull));
+    }
+    if (d.S != kTerr + d.n_char || d.cat > 160 || d.n_out != d.n_frags * (1 + d.frag) || d.cap < 2 * kB) {
+        trl_fail("trl_trainer_create: unsupported net dimensions / replay capacity");
+        delete t;
+        return nullptr;
+    }
+    const int sizes[10] = {C0 * K0, C0, C1 * C0 * K1, C1, C2 * C1 * K2, C2, T * C2 * W2, T, H * d.cat, H};
+    d.off[0] = 0;
+    for (int b = 0; b < 26; ++b) {
+        int sz;
+        if (b < 10) sz = sizes[b];
+        else {
+            const int hd = (b - 10) / 4, r = (b - 10) % 4, nout = hd == 0 ? d.n_frags : d.frag;
+            sz = r == 0 ? HH * H : (r == 1 ? HH : (r == 2 ? nout * HH : nout));
+        }
+        if (sz != (int)h->net_counts[b]) { trl_fail("trl_trainer_create: weight blob sizes do not match the MACE topology"); delete t; return nullptr; }
+        d.off[b + 1] = d.off[b] + sz;
+    }
+    d.P = d.off[26];
+    bool ok = true;
+    auto A = [&](cudaError_t e) { if (e != cudaSuccess) { if (ok) trl_fail(std::string("trainer alloc: ") + cudaGetErrorString(e)); ok = false; } };
+    A(talloc(t, &d.theta, d.P)); A(talloc(t, &d.target, d.P)); A(talloc(t, &d.history, d.P)); A(talloc(t, &d.grad, d.P));
+    A(talloc(t, &d.in_off, d.S)); A(talloc(t, &d.in_scale, d.S)); A(talloc(t, &d.out_off, d.n_out)); A(talloc(t, &d.out_scale, d.n_out));
+    A(talloc(t, &d.t_in_off, d.S)); A(talloc(t, &d.t_in_scale, d.S)); A(talloc(t, &d.t_out_off, d.n_out)); A(talloc(t, &d.t_out_scale, d.n_out));
+    A(talloc(t, &d.mem, (size_t)d.cap * d.Wd)); A(talloc(t, &d.flags, d.cap));
+    A(talloc(t, &d.pos_critic, d.cap)); A(talloc(t, &d.pos_actor, d.cap)); A(talloc(t, &d.critic_list, d.cap)); A(talloc(t, &d.actor_list, d.cap));
+    A(talloc(t, &d.actor_batch, 4 * kB)); A(talloc(t, &d.c, 1));
+    const int add_cap = std::max(h->B.tuple_cap, 4096);
+    A(talloc(t, &d.valid, add_cap)); A(talloc(t, &d.slot, add_cap)); A(talloc(t, &d.ids, kB)); A(talloc(t, &d.cand, kB));
+    A(talloc(t, &d.xn, (size_t)kB * d.S)); A(talloc(t, &d.a0, (size_t)kB * C0 * W0)); A(talloc(t, &d.a1, (size_t)kB * C1 * W1));
+    A(talloc(t, &d.a2, (size_t)kB * C2 * W2)); A(talloc(t, &d.t, (size_t)kB * T)); A(talloc(t, &d.catb, (size_t)kB * d.cat));
+    A(talloc(t, &d.h, (size_t)kB * H)); A(talloc(t, &d.hh, (size_t)4 * kB * HH)); A(talloc(t, &d.y, (size_t)kB * d.n_out));
+    A(talloc(t, &d.v0, kB)); A(talloc(t, &d.v1, kB)); A(talloc(t, &d.dy, (size_t)kB * d.n_out)); A(talloc(t, &d.dhh, (size_t)kB * HH));
+    A(talloc(t, &d.dh, (size_t)kB * H)); A(talloc(t, &d.dt, (size_t)kB * T)); A(talloc(t, &d.da2, (size_t)kB * C2 * W2));
+    A(talloc(t, &d.da1, (size_t)kB * C1 * W1)); A(talloc(t, &d.da0, (size_t)kB * C0 * W0)); A(talloc(t, &d.mean, d.S));
+    t->stage_cap = add_cap;
+    A(talloc(t, &t->stage_rows, (size_t)add_cap * d.Wd)); A(talloc(t, &t->stage_flags, add_cap));
+    if (ok) {
+        A(cudaMemset(d.pos_critic, 0xff, (size_t)d.cap * 4));
+        A(cudaMemset(d.pos_actor, 0xff, (size_t)d.cap * 4));
+        cudaStreamSynchronize(h->stream);
+        // LoadModel: start from the engine's current policy (weights + offset / scale); the target net is a copy
+        for (int b = 0; b < 26 && ok; ++b) A(cudaMemcpy(d.theta + d.off[b], h->net_blobs[b], (size_t)h->net_counts[b] * 8, cudaMemcpyDeviceToDevice));
+        A(cudaMemcpy(d.target, d.theta, (size_t)d.P * 8, cudaMemcpyDeviceToDevice));
+        double* dst[8] = {d.in_off, d.in_scale, d.out_off, d.out_scale, d.t_in_off, d.t_in_scale, d.t_out_off, d.t_out_scale};
+        for (int k = 0; k < 8 && ok; ++k) A(cudaMemcpy(dst[k], h->net_blobs[26 + (k & 3)], (size_t)h->net_counts[26 + (k & 3)] * 8, cudaMemcpyDeviceToDevice));
+    }
+    if (!ok) {
+        for (void* q : t->allocs) cudaFree(q);
+        delete t;
+        return nullptr;
+    }
+    // cNeuralNetLearner::SyncNet as a binding: the decision kernel reads the trainer's weights from now on
+    NetWeights& Wt = h->W;
+    auto blob = [&](int b) { return (const double*)(d.theta + d.off[b]); };
+    Wt.conv0_w = blob(0); Wt.conv0_b = blob(1); Wt.conv1_w = blob(2); Wt.conv1_b = blob(3); Wt.conv2_w = blob(4); Wt.conv2_b = blob(5);
+    Wt.tip0_w = blob(6); Wt.tip0_b = blob(7); Wt.ip0_w = blob(8); Wt.ip0_b = blob(9);
+    for (int k = 0; k < 4; ++k) { Wt.h0_w[k] = blob(10 + 4 * k); Wt.h0_b[k] = blob(11 + 4 * k); Wt.h1_w[k] = blob(12 + 4 * k); Wt.h1_b[k] = blob(13 + 4 * k); }
+    Wt.in_off = d.in_off; Wt.in_scale = d.in_scale; Wt.out_off = d.out_off; Wt.out_scale = d.out_scale;
+    trl_drop_graphs(h);
+    h->trainer = t;
+    return t;
+}
+
+int trl_trainer_destroy(trl_trainer* t) {
+    if (!t) return 0;
+    trl_handle* h = t->h;
+    cudaStreamSynchronize(h->stream);
+    // hand the weights back to the engine's own buffers so the scenario stays usable
+    for (int b = 0; b < 26; ++b) cudaMemcpy(h->net_blobs[b], t->d.theta + t->d.off[b], (size_t)h->net_counts[b] * 8, cudaMemcpyDeviceToDevice);
+    cudaMemcpy(h->net_blobs[26], t->d.in_off, (size_t)h->net_counts[26] * 8, cudaMemcpyDeviceToDevice);
+    cudaMemcpy(h->net_blobs[27], t->d.in_scale, (size_t)h->net_counts[27] * 8, cudaMemcpyDeviceToDevice);
+    NetWeights& W = h->W;
+    double** b = h->net_blobs.data();
+    W.conv0_w = b[0]; W.conv0_b = b[1]; W.conv1_w = b[2]; W.conv1_b = b[3]; W.conv2_w = b[4]; W.conv2_b = b[5];
+    W.tip0_w = b[6]; W.tip0_b = b[7]; W.ip0_w = b[8]; W.ip0_b = b[9];
+    for (int k = 0; k < 4; ++k) { W.h0_w[k] = b[10 + 4 * k]; W.h0_b[k] = b[11 + 4 * k]; W.h1_w[k] = b[12 + 4 * k]; W.h1_b[k] = b[13 + 4 * k]; }
+    W.in_off = b[26]; W.in_scale = b[27]; W.out_off = b[28]; W.out_scale = b[29];
+    trl_drop_graphs(h);
+    h->trainer = nullptr;
+    if (t->train_graph) cudaGraphExecDestroy(t->train_graph);
+    for (void* q : t->allocs) cudaFree(q);
+    delete t;
+    return 0;
+}
+
+// cNeuralNetLearner::Train's AddTuples(exp->GetTuples()) + ResetTupleBuffer, device to device
+int trl_trainer_add_from_scene(trl_trainer* t) {
+    trl_handle* h = t->h;
+    enqueue_add(t, h->B.tuples, h->B.tuple_flags, h->B.tuple_count, 0, h->B.tuple_cap, h->B.tuple_count, h->stream);
+    TCK(cudaGetLastError());
+    return 0;
+}
+// tuples handed in from host memory (the adapter path of INTEGRATION.md, and the tests)
+int trl_trainer_add_tuples(trl_trainer* t, const double* rows, const uint32_t* flags, int n) {
+    trl_handle* h = t->h;
+    for (int base = 0; base < n; base += t->stage_cap) {
+        const int cnt = std::min(t->stage_cap, n - base);
+        TCK(cudaMemcpyAsync(t->stage_rows, rows + (size_t)base * t->d.Wd, (size_t)cnt * t->d.Wd * 8, cudaMemcpyHostToDevice, h->stream));
+        TCK(cudaMemcpyAsync(t->stage_flags, flags + base, (size_t)cnt * 4, cudaMemcpyHostToDevice, h->stream));
+        enqueue_add(t, t->stage_rows, t->stage_flags, nullptr, cnt, cnt, nullptr, h->stream);
+        TCK(cudaStreamSynchronize(h->stream));
+    }
+    TCK(cudaGetLastError());
+    return 0;
+}
+
+// `iters` x cNeuralNetTrainer::Train() on the engine's stream (ordered after the update that produced the tuples and before
+// the next one, which then evaluates the updated weights)
+int trl_trainer_train(trl_trainer* t, int iters) {
+    trl_handle* h = t->h;
+    if (!t->train_graph) {
+        cudaGraph_t graph;
+        const int64_t before = t->launches;
+        TCK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+        enqueue_train(t, h->stream);
+        TCK(cudaStreamEndCapture(h->stream, &graph));
+        TCK(cudaGraphInstantiate(&t->train_graph, graph, 0));
+        cudaGraphDestroy(graph);
+        t->launches = before;
+    }
+    const int per = 5 + t->d.steps_per_iter * (10 + 5 * 15 + 2 * 26);
+    for (int i = 0; i < iters; ++i) {
+        TCK(cudaGraphLaunch(t->train_graph, h->stream));
+        t->launches += per;
+    }
+    return 0;
+}
+
+// c[9]: iter, actor_iter, stage, num, head, total, critic buffer, actor buffer, pending actor batch; l[2]: last losses
+int trl_trainer_counters(trl_trainer* t, int64_t* c, double* l) {
+    Counters hc;
+    TCK(cudaStreamSynchronize(t->h->stream));
+    TCK(cudaMemcpy(&hc, t->d.c, sizeof(hc), cudaMemcpyDeviceToHost));
+    if (c) {
+        c[0] = hc.iter; c[1] = hc.actor_iter; c[2] = hc.stage; c[3] = hc.num; c[4] = hc.head; c[5] = hc.total;
+        c[6] = hc.critic_count; c[7] = hc.actor_count; c[8] = hc.actor_batch_count;
+    }
+    if (l) { l[0] = hc.critic_loss; l[1] = hc.actor_loss; }
+    return 0;
+}
+int trl_trainer_num_params(trl_trainer* t) { return t->d.P; }
+int64_t trl_trainer_launches(trl_trainer* t) { return t->launches; }
+
+// what: 0 theta, 1 target theta, 2 history, 3 in_off, 4 in_scale, 5 out_off, 6 out_scale, 7 last gradient
+int trl_trainer_get(trl_trainer* t, int what, double* out) {
+    const Dev& d = t->d;
+    const double* src[8] = {d.theta, d.target, d.history, d.in_off, d.in_scale, d.out_off, d.out_scale, d.grad};
+    const size_t cnt[8] = {(size_t)d.P, (size_t)d.P, (size_t)d.P, (size_t)d.S, (size_t)d.S, (size_t)d.n_out, (size_t)d.n_out, (size_t)d.P};
+    if (what < 0 || what > 7) return trl_fail("trl_trainer_get: bad selector");
+    TCK(cudaStreamSynchronize(t->h->stream));
+    TCK(cudaMemcpy(out, src[what], cnt[what] * 8, cudaMemcpyDeviceToHost));
+    return 0;
+}
+// cNeuralNetTrainer::LoadModel: weights (26 blobs concatenated in layer order) into the current AND the target net
+int trl_trainer_set_theta(trl_trainer* t, const double* theta) {
+    TCK(cudaStreamSynchronize(t->h->stream));
+    TCK(cudaMemcpy(t->d.theta, theta, (size_t)t->d.P * 8, cudaMemcpyHostToDevice));
+    TCK(cudaMemcpy(t->d.target, t->d.theta, (size_t)t->d.P * 8, cudaMemcpyDeviceToDevice));
+    return 0;
+}
+// which: 0 critic buffer, 1 actor buffer, 2 pending actor batch, 3 ids of the last sampled batch; returns the length
+int trl_trainer_list(trl_trainer* t, int which, int32_t* out, int cap, int* len) {
+    Counters hc;
+    TCK(cudaStreamSynchronize(t->h->stream));
+    TCK(cudaMemcpy(&hc, t->d.c, sizeof(hc), cudaMemcpyDeviceToHost));
+    const int* src = which == 0 ? t->d.critic_list : (which == 1 ? t->d.actor_list : (which == 2 ? t->d.actor_batch : t->d.ids));
+    const int n = which == 0 ? hc.critic_count : (which == 1 ? hc.actor_count : (which == 2 ? hc.actor_batch_count : trl_train::kB));
+    if (len) *len = n;
+    TCK(cudaMemcpy(out, src, (size_t)std::min(n, cap) * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+}  // extern "C"

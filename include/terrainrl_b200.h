@@ -114,6 +114,33 @@ int trl_update_timed_detail(trl_handle* h, double dt, double* per_step_ms, doubl
 
 int trl_debug_time_decide(trl_handle* h, int n_pending, int iters, double* ms_avg);
 
+/* ---------------------------------------------------------------------------------------------------------------------
+ * MACE trainer on the GPU -- replaces cMACETrainer / cNeuralNetLearner behind cScenarioTrainMACE:
+ *   trl_trainer_create        cTrainerInterface::Init + LoadModel (learning/NeuralNetTrainer.cpp:26-49, MACETrainer.cpp:78-90);
+ *                             p[10] = {replay_mem_size, num_init_samples, num_steps_per_iter, freeze_target_iters,
+ *                             init_input_offset_scale, discount, base_lr, momentum, weight_decay, seed}.  From this call on the
+ *                             scenario's decision kernel evaluates the trainer's current net (cNeuralNetLearner::SyncNet,
+ *                             learning/NeuralNetLearner.cpp:83-87, becomes a pointer binding).
+ *   trl_trainer_add_from_scene  AddTuples(exp.GetTuples()) + ResetTupleBuffer (learning/NeuralNetLearner.cpp:33-45,
+ *                             scenarios/ScenarioTrain.cpp:388-408), device to device
+ *   trl_trainer_add_tuples    cNeuralNetTrainer::AddTuples from host rows [n][1 + S + A + S] (learning/NeuralNetTrainer.cpp:145-173)
+ *   trl_trainer_train         iters x cNeuralNetTrainer::Train (learning/NeuralNetTrainer.cpp:175-183 -> cMACETrainer::Step,
+ *                             learning/MACETrainer.cpp:335-361), asynchronous on the scenario's stream
+ *   trl_trainer_counters      GetIter / GetNumTuples / buffer sizes / last losses
+ *   trl_trainer_get, _set_theta, _list   model read-back (OutputModel), LoadModel, buffer inspection for the tests */
+typedef struct trl_trainer trl_trainer;
+trl_trainer* trl_trainer_create(trl_handle* h, const double* params10);
+int trl_trainer_destroy(trl_trainer* t);
+int trl_trainer_add_from_scene(trl_trainer* t);
+int trl_trainer_add_tuples(trl_trainer* t, const double* rows, const uint32_t* flags, int n);
+int trl_trainer_train(trl_trainer* t, int iters);
+int trl_trainer_counters(trl_trainer* t, int64_t* counters9, double* losses2);
+int trl_trainer_num_params(trl_trainer* t);
+int64_t trl_trainer_launches(trl_trainer* t);
+int trl_trainer_get(trl_trainer* t, int what, double* out);
+int trl_trainer_set_theta(trl_trainer* t, const double* theta);
+int trl_trainer_list(trl_trainer* t, int which, int32_t* out, int cap, int* len);
+
 const char* trl_last_error(void);
 
 #ifdef __cplusplus

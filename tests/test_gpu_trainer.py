@@ -1,0 +1,103 @@
+"""GPU MACE trainer (csrc/trl_train.cu) against the CPU restatement (oracle/trainer.h): same tuple stream, same sampling RNG ->
+same replay buffers (exact) and the same weights after several critic + actor solver steps (f64, different summation order)."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _synthetic_tuples(n, S, A, in_off, in_scale, seed, actor_frac=0.45):
+    rng = np.random.default_rng(seed)
+    W = 1 + 2 * S + A
+    rows = np.zeros((n, W))
+    rows[:, 0] = rng.uniform(0, 8, n)                                 # large rewards: many positive temporal differences
+    for k in (1, 1 + S + A):
+        rows[:, k:k + S] = rng.normal(size=(n, S)) / np.where(in_scale == 0, 1.0, in_scale) - in_off
+    rows[:, 1 + S] = rng.integers(0, 3, n)
+    rows[:, 2 + S:1 + S + A] = rng.normal(size=(n, A - 1)) * 0.2
+    flags = np.where(rng.uniform(size=n) < actor_frac, 4, 0).astype(np.uint32)
+    flags |= (rng.uniform(size=n) < 0.1).astype(np.uint32)            # failures
+    return rows, flags
+
+
+def test_trainer_matches_oracle(assets):
+    from pyoracle import OracleTrainer
+    import deepterrainrl_b200 as trl
+    pack = os.path.join(assets, "dog_slopes_mixed.trlpack")
+    kw = dict(num_init_samples=96, num_steps_per_iter=1, freeze_target_iters=3, init_input_offset_scale=1, seed=21)
+    sc = trl.ScenarioExpMACE(pack, 64)
+    g = trl.MACETrainer(sc, replay_mem_size=160, **kw)
+    o = OracleTrainer(pack, replay_cap=160, **kw)
+    assert g.num_params == o.num_params == 570474
+    np.testing.assert_array_equal(g.get("theta"), o.get("theta"))
+    in_off, in_scale = o.get("in_off"), o.get("in_scale")
+    rows, flags = _synthetic_tuples(128, g.S, g.A, in_off, in_scale, 3)
+    rows[17, 40] = np.inf                                              # CheckTuple must drop it on both sides
+    g.AddTuples(rows, flags); o.add_tuples(rows, flags)
+    cg, co = g.counters(), o.counters()
+    for k in ("num", "head", "total", "critic", "actor", "stage"):
+        assert cg[k] == co[k], k
+    np.testing.assert_array_equal(g.lists("critic"), o.lists("critic"))
+    np.testing.assert_array_equal(g.lists("actor"), o.lists("actor"))
+    for it in range(8):
+        g.Train(1); o.train()
+        if it == 2:                                                    # wrap the ring: overwritten slots change buffers
+            r2, f2 = _synthetic_tuples(64, g.S, g.A, in_off, in_scale, 9)
+            g.AddTuples(r2, f2); o.add_tuples(r2, f2)
+        cg, co = g.counters(), o.counters()
+        for k in ("iter", "actor_iter", "stage", "num", "head", "total", "critic", "actor", "actor_batch"):
+            assert cg[k] == co[k], (it, k, cg, co)
+        np.testing.assert_array_equal(g.lists("critic"), o.lists("critic"))
+        np.testing.assert_array_equal(g.lists("actor"), o.lists("actor"))
+        np.testing.assert_array_equal(g.lists("actor_batch"), o.lists("actor_batch"))
+        lo = o.losses()
+        assert abs(cg["critic_loss"] - lo[0]) <= 1e-10 * max(1.0, lo[0])
+        tg, to = g.get("theta"), o.get("theta")
+        assert np.max(np.abs(tg - to)) <= 1e-10 * max(1.0, np.max(np.abs(to))), it
+    assert co["iter"] == 8 and co["actor_iter"] >= 1                   # both kinds of solver step happened
+    np.testing.assert_allclose(g.get("in_off"), o.get("in_off"), rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(g.get("in_scale"), o.get("in_scale"), rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(g.get("target"), o.get("target"), rtol=0, atol=1e-10)
+    np.testing.assert_allclose(g.get("history"), o.get("history"), rtol=0, atol=1e-10)
+    assert not np.array_equal(g.get("target"), g.get("theta"))
+
+
+def test_rollout_uses_trainer_weights_and_device_tuples(assets):
+    """The scenario evaluates the trainer's net in place: zeroing the actor heads through the trainer changes the rollout;
+    tuples flow from the scenario's device block into the replay memory without the host, and training runs on them."""
+    import deepterrainrl_b200 as trl
+    pack = os.path.join(assets, "dog_slopes_mixed.trlpack")
+    n = 512
+    a = trl.ScenarioExpMACE(pack, n, rng_seed=5)
+    b = trl.ScenarioExpMACE(pack, n, rng_seed=5)
+    for sc in (a, b):
+        sc.EnableExplore(True, 0.2, 0.025, 0.01)
+    tr = trl.MACETrainer(b, replay_mem_size=20000, num_init_samples=1500, freeze_target_iters=4, seed=2)
+    for _ in range(40):
+        a.Update(1.0 / 30.0); b.Update(1.0 / 30.0)
+    np.testing.assert_array_equal(a.GetStateAll()[0], b.GetStateAll()[0])      # binding alone changes nothing
+    nt = b.GetNumTuples()
+    assert nt > n
+    tr.AddTuplesFromScene()
+    c = tr.counters()
+    assert c["num"] == nt and c["critic"] + c["actor"] == nt and c["actor"] > 0
+    assert b.GetNumTuples() == 0                                               # ResetTupleBuffer happened on the device
+    theta0 = tr.get("theta")
+    for _ in range(30):
+        b.Update(1.0 / 30.0)
+        tr.AddTuplesFromScene()
+        tr.Train(2)
+    c = tr.counters()
+    assert c["stage"] == 1 and c["iter"] > 4 and np.isfinite(c["critic_loss"])
+    theta1 = tr.get("theta")
+    assert np.all(np.isfinite(theta1)) and not np.array_equal(theta0, theta1)
+    assert np.all(np.isfinite(b.GetStateAll()[0]))
+    # weights owned by the trainer: trl_set_weights is refused, set_theta reaches the rollout
+    with pytest.raises(RuntimeError):
+        b.SetWeights([np.zeros(1)] * 26, np.zeros(1), np.zeros(1), np.zeros(1), np.zeros(1))
+    tr.close()
+    for _ in range(3):
+        b.Update(1.0 / 30.0)                                                   # scenario stays usable with the trained weights
+    assert np.all(np.isfinite(b.GetStateAll()[0]))
