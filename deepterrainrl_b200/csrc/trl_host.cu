@@ -580,6 +580,39 @@ int trl_set_explore(trl_handle* h, int enable, double rate, double temp, double 
     return 0;
 }
 
+// cScenarioSimChar::SetTerrainParamsLerp (scenarios/ScenarioSimChar.cpp:255-272), as cScenarioTrain::UpdateSceneCurriculum calls it
+// (scenarios/ScenarioTrain.cpp:412-416): blends the scene's terrain parameter sets; segments generated from now on use the
+// blend (cGroundVar2D::SetTerrainParams), existing terrain stays.
+int trl_set_terrain_lerp(trl_handle* h, double lerp) {
+    const auto& tp = h->scene.f64("terrain_params");
+    const int n_sets = (int)(tp.size() / kTerrainParams);
+    if (n_sets <= 0) return 0;
+    lerp = std::min(std::max(lerp, 0.0), n_sets - 1.0);
+    const int i0 = (int)lerp, i1 = std::min(i0 + 1, n_sets - 1);
+    lerp -= i0;
+    CK(cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < kTerrainParams; ++i) h->mc.terrain_params[i] = (1 - lerp) * tp[i0 * kTerrainParams + i] + lerp * tp[i1 * kTerrainParams + i];
+    g_model_owner = nullptr;
+    if (ensure_model(h)) return fail("model upload failed");
+    return 0;
+}
+
+// cScenarioTrain::CalcExpRate / CalcExpTemp / CalcExpBaseRate / CalcCurriculumPhase (scenarios/ScenarioTrain.cpp:418-460).
+// sp[9] = {init_exp_rate, exp_rate, init_exp_temp, exp_temp, init_exp_base_rate, exp_base_rate, trainer_num_anneal_iters,
+// exp_base_anneal_iters, trainer_curriculum_iters}; out[4] = {exp_rate, exp_temp, exp_base_rate, curriculum_phase}
+int trl_train_schedule(const double* sp, int iters, double* out) {
+    auto clamp01 = [](double v) { return std::min(std::max(v, 0.0), 1.0); };
+    double lerp = clamp01((double)iters / sp[6]);
+    out[0] = (1 - lerp) * sp[0] + lerp * sp[1];
+    out[1] = (1 - lerp) * sp[2] + lerp * sp[3];
+    lerp = clamp01((double)iters / sp[7]);
+    out[2] = (1 - lerp) * sp[4] + lerp * sp[5];
+    const bool enable = sp[8] >= 1;
+    out[3] = clamp01(enable ? (double)iters / sp[8] : 1.0);
+    if (iters == 0) out[3] = 1.0;      // gInitCurriculumPhase
+    return 0;
+}
+
 int trl_set_phys_params(trl_handle* h, const double* p) {
     CK(cudaStreamSynchronize(h->stream));
     h->mc.phys = PhysParams{p[0], p[1], p[2], p[3], p[4], p[5], p[6]};

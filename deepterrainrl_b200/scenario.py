@@ -58,7 +58,7 @@ EXPORTS = [
     "trl_get_tuples_f64", "trl_reset_tuples", "trl_eval_stats", "trl_dist_log", "trl_get_state", "trl_set_state",
     "trl_get_state_all", "trl_get_ctrl", "trl_get_poli_state", "trl_get_net_out", "trl_get_terrain",
     "trl_kernel_launches", "trl_last_error", "trl_bench_updates", "trl_update_timed", "trl_device_tuple_block", "trl_snapshot", "trl_snapshot_wait", "trl_update_timed_detail", "trl_debug_time_decide",
-    "trl_trainer_create", "trl_trainer_destroy", "trl_trainer_add_from_scene", "trl_trainer_add_tuples", "trl_trainer_train",
+    "trl_set_terrain_lerp", "trl_train_schedule", "trl_trainer_create", "trl_trainer_destroy", "trl_trainer_add_from_scene", "trl_trainer_add_tuples", "trl_trainer_train",
     "trl_trainer_counters", "trl_trainer_num_params", "trl_trainer_launches", "trl_trainer_get", "trl_trainer_set_theta", "trl_trainer_list",
 ]
 
@@ -141,6 +141,10 @@ class BatchedScenario:
     def Reset(self, env_ids=None):
         ids = None if env_ids is None else np.ascontiguousarray(env_ids, dtype=np.int32)
         self._ck(self.L.trl_reset(self.h, _p(ids), 0 if ids is None else ids.size))
+
+    def SetTerrainParamsLerp(self, lerp):
+        """cScenarioSimChar::SetTerrainParamsLerp (scenarios/ScenarioSimChar.cpp:255-272)."""
+        self._ck(self.L.trl_set_terrain_lerp(self.h, C.c_double(lerp)))
 
     def SetRandSeed(self, seeds):
         s = np.ascontiguousarray(seeds, dtype=np.uint64)

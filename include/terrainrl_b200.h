@@ -128,6 +128,13 @@ int trl_debug_time_decide(trl_handle* h, int n_pending, int iters, double* ms_av
  *                             learning/MACETrainer.cpp:335-361), asynchronous on the scenario's stream
  *   trl_trainer_counters      GetIter / GetNumTuples / buffer sizes / last losses
  *   trl_trainer_get, _set_theta, _list   model read-back (OutputModel), LoadModel, buffer inspection for the tests */
+/* cScenarioSimChar::SetTerrainParamsLerp (scenarios/ScenarioSimChar.cpp:255-272) and cScenarioTrain's annealing schedule
+ * (scenarios/ScenarioTrain.cpp:412-460): sp[9] = {init_exp_rate, exp_rate, init_exp_temp, exp_temp, init_exp_base_rate,
+ * exp_base_rate, trainer_num_anneal_iters, exp_base_anneal_iters, trainer_curriculum_iters};
+ * out[4] = {exp_rate, exp_temp, exp_base_rate, curriculum_phase} */
+int trl_set_terrain_lerp(trl_handle* h, double lerp);
+int trl_train_schedule(const double* sp9, int iters, double* out4);
+
 typedef struct trl_trainer trl_trainer;
 trl_trainer* trl_trainer_create(trl_handle* h, const double* params10);
 int trl_trainer_destroy(trl_trainer* t);

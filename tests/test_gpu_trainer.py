@@ -101,3 +101,40 @@ def test_rollout_uses_trainer_weights_and_device_tuples(assets):
     for _ in range(3):
         b.Update(1.0 / 30.0)                                                   # scenario stays usable with the trained weights
     assert np.all(np.isfinite(b.GetStateAll()[0]))
+
+
+def test_training_driver_end_to_end(assets, tmp_path):
+    """ScenarioTrainMACE: rollout -> device tuples -> trainer iterations -> annealed exploration, model written in the Caffe
+    HDF5 layout equals the trainer's weights and loads back into a fresh scenario."""
+    import deepterrainrl_b200 as trl
+    from deepterrainrl_b200.model_io import read_model
+    from deepterrainrl_b200.train import ScenarioTrainMACE, TrainSchedule
+    pack = os.path.join(assets, "dog_slopes_mixed.trlpack")
+    sched = TrainSchedule(init_exp_rate=0.9, exp_rate=0.2, init_exp_temp=20, exp_temp=0.025, init_exp_base_rate=0.9, exp_base_rate=0.002,
+                          trainer_num_anneal_iters=40, exp_base_anneal_iters=40)
+    st = ScenarioTrainMACE(pack, 1024, schedule=sched, rng_seed=3,
+                           trainer_params=dict(replay_mem_size=50000, num_init_samples=800, freeze_target_iters=10, seed=4))
+    st.Run(45)
+    c = st.trainer.counters()
+    assert c["stage"] == 1 and c["iter"] >= 5 and c["num"] > 800 and np.isfinite(c["critic_loss"])
+    assert c["actor"] > 0 and c["critic"] > 0
+    s = sched(st.trainer.GetIter())
+    assert s["exp_rate"] < 0.9                                       # annealing follows the iteration count
+    out = str(tmp_path / "model.h5")
+    st.OutputModel(out)
+    layers, scale = read_model(out)
+    blobs = st.trainer.blobs()
+    for name, (w, b) in blobs.items():
+        np.testing.assert_array_equal(layers[name][0], w)
+        np.testing.assert_array_equal(layers[name][1], b)
+    np.testing.assert_array_equal(scale["InputOffset"], st.trainer.get("in_off"))
+    # the written model drives a fresh evaluation scenario (cNeuralNet::LoadModel path = SetWeights)
+    ev = trl.ScenarioPoliEval(pack, 64)
+    flat = []
+    from deepterrainrl_b200.trainer import NET_LAYERS
+    for name in NET_LAYERS:
+        flat += [layers[name][0].ravel(), layers[name][1]]
+    ev.SetWeights(flat, scale["InputOffset"], scale["InputScale"], scale["OutputOffset"], scale["OutputScale"])
+    for _ in range(10):
+        ev.Update(1.0 / 30.0)
+    assert np.all(np.isfinite(ev.GetStateAll()[0]))
