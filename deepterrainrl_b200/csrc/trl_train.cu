@@ -31,6 +31,7 @@ using namespace trl;
 
 constexpr int kB = 32;                               // MemoryData batch_size
 constexpr int C0 = 16, K0 = 8, W0 = 193, C1 = 32, K1 = 4, W1 = 190, C2 = 32, K2 = 4, W2 = 187, T = 64, H = 256, HH = 128;
+constexpr int kSplit = 8;                            // K slices of the wide terr_ip0 forward
 constexpr int kTerr = 200;                           // terrain samples at the head of the policy state
 
 enum Pred { P_ALWAYS = 0, P_CRITIC, P_CAND, P_ACTOR, P_INIT };
@@ -56,11 +57,30 @@ struct Dev {
     double *xn, *a0, *a1, *a2, *t, *catb, *h, *hh, *y;           // activations of the most recent forward pass (kB rows)
     double *v0, *v1;
     double *dy, *dhh, *dh, *dt, *da2, *da1, *da0;
-    double *mean;
+    double *mean, *part;
     double discount, base_lr, momentum, weight_decay;
     int freeze, nis, init_offset_scale, steps_per_iter;
     unsigned long long rng_key;
 };
+
+// Programmatic dependent launch: every trainer kernel is launched with programmatic stream serialization and starts with
+// pdl_sync(): wait until the preceding kernel has completed (and its writes are visible), then let the next kernel of the
+// stream be scheduled right away -- it parks at its own wait.  The dependency chain stays strictly serial; what disappears is
+// the launch latency between ~140 small dependent kernels per training iteration.
+__device__ __forceinline__ void pdl_sync() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+template <typename... KArgs, typename... Args>
+void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
 
 __device__ __forceinline__ bool pred_on(const Dev& d, int pred) {
     switch (pred) {
@@ -92,6 +112,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 // ================================================================================================ replay memory
 // cNeuralNetTrainer::CheckTuple (learning/NeuralNetTrainer.cpp:541-576): one block per incoming tuple
 __global__ void k_add_check(Dev d, const double* rows, const int* count_ptr, int count_val) {
+    pdl_sync();
     const int count = count_ptr ? *count_ptr : count_val;
     const int i = blockIdx.x;
     if (i >= count) return;
@@ -111,6 +132,7 @@ __device__ void list_remove(int* list, int* pos, int& count, int t) {
 }
 // cNeuralNetTrainer::AddTuple slot assignment + cMACETrainer::UpdateBuffers, in arrival order (one thread: O(1) per tuple)
 __global__ void k_add_assign(Dev d, const uint32_t* src_flags, const int* count_ptr, int count_val, int* reset_count) {
+    pdl_sync();
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     const int count = count_ptr ? *count_ptr : count_val;
     Counters& c = *d.c;
@@ -137,6 +159,7 @@ __global__ void k_add_assign(Dev d, const uint32_t* src_flags, const int* count_
     if (reset_count) *reset_count = 0;                     // cScenarioExp::ResetTupleBuffer
 }
 __global__ void k_add_copy(Dev d, const double* rows, const uint32_t* src_flags, const int* count_ptr, int count_val) {
+    pdl_sync();
     const int count = count_ptr ? *count_ptr : count_val;
     const int i = blockIdx.x;
     if (i >= count) return;
@@ -150,6 +173,7 @@ __global__ void k_add_copy(Dev d, const double* rows, const uint32_t* src_flags,
 
 // ================================================================================================ stage switch
 __global__ void k_stage_check(Dev d) {
+    pdl_sync();
     Counters& c = *d.c;
     c.init_now = 0;
     c.succ = 0;
@@ -160,6 +184,7 @@ __global__ void k_stage_check(Dev d) {
 }
 // cNeuralNet::CalcOffsetScale (learning/NeuralNet.cpp:280-313) over the state-begin columns of the replay memory
 __global__ void k_col_mean(Dev d) {
+    pdl_sync();
     if (d.c->init_now != 1) return;
     const int j = blockIdx.x, num = d.c->num;
     double s = 0;
@@ -175,6 +200,7 @@ __global__ void k_col_mean(Dev d) {
     }
 }
 __global__ void k_col_scale(Dev d) {
+    pdl_sync();
     if (d.c->init_now != 1) return;
     const int j = blockIdx.x, num = d.c->num;
     const double m = d.mean[j];
@@ -193,12 +219,14 @@ __global__ void k_col_scale(Dev d) {
     }
 }
 __global__ void k_stage_commit(Dev d) {
+    pdl_sync();
     if (d.c->init_now) d.c->stage = 1;
 }
 
 // ================================================================================================ sampling
 // cMACETrainer::FetchMinibatch (learning/MACETrainer.cpp:164-188)
 __global__ void k_sample_critic(Dev d) {
+    pdl_sync();
     if (threadIdx.x != 0) return;
     Counters& c = *d.c;
     const bool ok = c.stage == 1 && c.critic_count >= kB;
@@ -209,6 +237,7 @@ __global__ void k_sample_critic(Dev d) {
 }
 // cMACETrainer::FetchActorMinibatch (learning/MACETrainer.cpp:190-214)
 __global__ void k_sample_actor(Dev d) {
+    pdl_sync();
     if (threadIdx.x != 0) return;
     Counters& c = *d.c;
     c.cand_count = 0;
@@ -228,6 +257,7 @@ __global__ void k_sample_actor(Dev d) {
 }
 // UpdateActorBatchBuffer's test (learning/MACETrainer.cpp:556-573) + the batch for cMACETrainer::StepActor
 __global__ void k_actor_select(Dev d) {
+    pdl_sync();
     if (threadIdx.x != 0) return;
     Counters& c = *d.c;
     if (c.stage != 1) return;
@@ -238,6 +268,7 @@ __global__ void k_actor_select(Dev d) {
         for (int i = 0; i < kB; ++i) d.ids[i] = d.actor_batch[i];
 }
 __global__ void k_actor_pop(Dev d) {
+    pdl_sync();
     if (threadIdx.x != 0) return;
     Counters& c = *d.c;
     if (!c.actor_ok) return;
@@ -246,10 +277,12 @@ __global__ void k_actor_pop(Dev d) {
     ++c.actor_iter;
 }
 __global__ void k_end_iter(Dev d) {
+    pdl_sync();
     if (threadIdx.x == 0 && d.c->succ) ++d.c->iter;       // cNeuralNetTrainer::ApplySteps / IncIter
 }
 // cMACETrainer::Step's target refresh (learning/MACETrainer.cpp:350-358): uses the iteration count before IncIter
 __global__ void k_target_update(Dev d) {
+    pdl_sync();
     const Counters& c = *d.c;
     if (!(c.stage == 1 && d.freeze > 0 && c.iter > 0 && c.iter % d.freeze == 0)) return;
     const int stride = gridDim.x * blockDim.x, tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -261,36 +294,83 @@ __global__ void k_target_update(Dev d) {
 // ================================================================================================ forward
 // rows ids[0..kB) of the replay memory, columns [col0, col0 + S), normalised like cNeuralNet::NormalizeInput
 __global__ void k_gather_norm(Dev d, int pred, int col0, const double* in_off, const double* in_scale) {
+    pdl_sync();
     if (!pred_on(d, pred)) return;
     const int n = blockIdx.x;
     const float* r = d.mem + (size_t)d.ids[n] * d.Wd + col0;
     for (int i = threadIdx.x; i < d.S; i += blockDim.x) d.xn[(size_t)n * d.S + i] = ((double)r[i] + in_off[i]) * in_scale[i];
 }
-// Convolution (cross-correlation, stride 1) + ReLU.  grid (cout, kB), one thread per output position.
+// Convolution (cross-correlation, stride 1) + ReLU.  grid (cout / kConvOut, kB): the block stages all input channels of its
+// sample in (dynamic) shared memory once and produces kConvOut output channels from it, one thread per output position.
+constexpr int kConvOut = 8;
 __global__ void k_conv_fwd(Dev d, int pred, const double* x, int ldn, int cin, int win, const double* w, const double* b, int cout, int k,
                            double* y) {
+    pdl_sync();
     if (!pred_on(d, pred)) return;
-    __shared__ double ws[C1 * K1 > C0 * K0 ? C1 * K2 : C0 * K0];      // cin * k <= 128
-    const int o = blockIdx.x, n = blockIdx.y, wout = win - k + 1;
-    for (int i = threadIdx.x; i < cin * k; i += blockDim.x) ws[i] = w[(size_t)o * cin * k + i];
+    extern __shared__ double xs[];                         // [cin][win]
+    __shared__ double ws[kConvOut][C1 * K2];              // cin * k <= 128 per output channel
+    const int o0 = blockIdx.x * kConvOut, n = blockIdx.y, wout = win - k + 1, ck = cin * k;
+    const double* xr = x + (size_t)n * ldn;
+    for (int i = threadIdx.x; i < cin * win; i += blockDim.x) xs[i] = xr[i];
+    for (int i = threadIdx.x; i < kConvOut * ck; i += blockDim.x) { const int j = i / ck, r = i - j * ck; ws[j][r] = w[(size_t)(o0 + j) * ck + r]; }
     __syncthreads();
     const int t = threadIdx.x;
     if (t >= wout) return;
-    double acc = b[o];
-    const double* xr = x + (size_t)n * ldn;
+    double acc[kConvOut];
+#pragma unroll
+    for (int j = 0; j < kConvOut; ++j) acc[j] = b[o0 + j];
     for (int c = 0; c < cin; ++c)
-        for (int kk = 0; kk < k; ++kk) acc += ws[c * k + kk] * xr[(size_t)c * win + t + kk];
-    y[((size_t)n * cout + o) * wout + t] = acc > 0 ? acc : 0;
+        for (int kk = 0; kk < k; ++kk) {
+            const double xv = xs[c * win + t + kk];
+#pragma unroll
+            for (int j = 0; j < kConvOut; ++j) acc[j] += ws[j][c * k + kk] * xv;
+        }
+#pragma unroll
+    for (int j = 0; j < kConvOut; ++j) y[((size_t)n * cout + o0 + j) * wout + t] = acc[j] > 0 ? acc[j] : 0;
 }
-// InnerProduct (+ optional ReLU): one block per output neuron, all kB rows at once so each weight is read once.
-__global__ void k_fc_fwd(Dev d, int pred, const double* x, int ldx, int nin, const double* w, const double* b, int relu, double* y, int ldy) {
+// Narrow InnerProduct layers (nin <= 256): one warp per output neuron, lane = batch row, no reduction.  The block stages
+// 64-column tiles of the kB x nin input (transposed) and of its 8 weight rows in shared memory with coalesced loads; the inner
+// loop runs out of shared memory only (weight = broadcast read, input = conflict-free read).
+__global__ void k_fc_fwd_rows(Dev d, int pred, const double* x, int ldx, int nin, const double* w, const double* b, int nout, int relu,
+                              double* y, int ldy) {
+    pdl_sync();
     if (!pred_on(d, pred)) return;
-    const int o = blockIdx.x, tid = threadIdx.x;
+    __shared__ double xs[64][kB + 1];
+    __shared__ double ws[8][64 + 1];
+    const int wq = threadIdx.x >> 5, o = blockIdx.x * 8 + wq, n = threadIdx.x & 31;
+    double a0 = 0, a1 = 0;
+    for (int k0 = 0; k0 < nin; k0 += 64) {
+        const int kt = min(64, nin - k0);
+        for (int idx = threadIdx.x; idx < kB * 64; idx += blockDim.x) {
+            const int r = idx >> 6, kk = idx & 63;
+            if (kk < kt) xs[kk][r] = x[(size_t)r * ldx + k0 + kk];
+        }
+        for (int idx = threadIdx.x; idx < 8 * 64; idx += blockDim.x) {
+            const int r = idx >> 6, kk = idx & 63, oo = blockIdx.x * 8 + r;
+            ws[r][kk] = (oo < nout && kk < kt) ? w[(size_t)oo * nin + k0 + kk] : 0.0;
+        }
+        __syncthreads();
+        int kk = 0;
+        for (; kk + 1 < kt; kk += 2) { a0 += ws[wq][kk] * xs[kk][n]; a1 += ws[wq][kk + 1] * xs[kk + 1][n]; }
+        if (kk < kt) a0 += ws[wq][kk] * xs[kk][n];
+        __syncthreads();
+    }
+    if (o >= nout) return;
+    const double s = b[o] + (a0 + a1);
+    y[(size_t)n * ldy + o] = (relu && s < 0) ? 0 : s;
+}
+// Wide InnerProduct (terr_ip0, nin = 5984): K split over blockIdx.y, partial sums [ks][kB][nout] reduced (with bias + ReLU) by
+// k_fc_split_finish in a fixed order.
+__global__ void k_fc_fwd_split(Dev d, int pred, const double* x, int ldx, int nin, const double* w, int nout, double* part) {
+    pdl_sync();
+    if (!pred_on(d, pred)) return;
+    const int o = blockIdx.x, ks = blockIdx.y, nks = gridDim.y, tid = threadIdx.x;
+    const int chunk = (nin + nks - 1) / nks, k0 = ks * chunk, k1 = min(nin, k0 + chunk);
     double acc[kB];
 #pragma unroll
     for (int n = 0; n < kB; ++n) acc[n] = 0.0;
     const double* wr = w + (size_t)o * nin;
-    for (int i = tid; i < nin; i += blockDim.x) {
+    for (int i = k0 + tid; i < k1; i += blockDim.x) {
         const double wv = wr[i];
 #pragma unroll
         for (int n = 0; n < kB; ++n) acc[n] += wv * x[(size_t)n * ldx + i];
@@ -303,12 +383,23 @@ __global__ void k_fc_fwd(Dev d, int pred, const double* x, int ldx, int nin, con
     }
     __syncthreads();
     if (tid < kB) {
-        double s = b[o];
+        double s = 0;
         for (int wq = 0; wq < (int)(blockDim.x >> 5); ++wq) s += red[wq][tid];
-        y[(size_t)tid * ldy + o] = (relu && s < 0) ? 0 : s;
+        part[((size_t)ks * kB + tid) * nout + o] = s;
     }
 }
-__global__ void k_concat(Dev d, int pred) {        // concat0: [terr_relu3 | char features]
+__global__ void k_fc_split_finish(Dev d, int pred, const double* part, int nks, const double* b, int nout, int relu, double* y, int ldy) {
+    pdl_sync();
+    if (!pred_on(d, pred)) return;
+    const int n = blockIdx.x;
+    for (int o = threadIdx.x; o < nout; o += blockDim.x) {
+        double s = b[o];
+        for (int ks = 0; ks < nks; ++ks) s += part[((size_t)ks * kB + n) * nout + o];
+        y[(size_t)n * ldy + o] = (relu && s < 0) ? 0 : s;
+    }
+}
+__global__ void k_concat(Dev d, int pred) {
+    pdl_sync();        // concat0: [terr_relu3 | char features]
     if (!pred_on(d, pred)) return;
     const int n = blockIdx.x;
     for (int i = threadIdx.x; i < d.cat; i += blockDim.x)
@@ -319,6 +410,7 @@ __global__ void k_concat(Dev d, int pred) {        // concat0: [terr_relu3 | cha
 // max over the critic outputs of the un-normalised target-net output (GetMaxFragValAux) -> v0 (state begin) or the Bellman
 // value r (1 - gamma) + gamma max V'(s') -> v1 (CalcNewCumulativeRewardBatch, learning/MACETrainer.cpp:472-513)
 __global__ void k_vals(Dev d, int pred, int with_reward, double* out) {
+    pdl_sync();
     if (!pred_on(d, pred)) return;
     const int n = threadIdx.x;
     if (n >= kB) return;
@@ -334,6 +426,7 @@ __global__ void k_vals(Dev d, int pred, int with_reward, double* out) {
 // BuildProblemY / BuildActorProblemY + LoadTrainData's label normalisation + EuclideanLoss gradient.
 // mode 0: critic (value of the taken actor <- v1), mode 1: actor (fragment of the taken actor <- the action taken)
 __global__ void k_labels(Dev d, int pred, int mode) {
+    pdl_sync();
     if (!pred_on(d, pred)) return;
     const int no = d.n_out;
     double part = 0;
@@ -364,6 +457,7 @@ __global__ void k_labels(Dev d, int pred, int mode) {
 // ================================================================================================ backward
 // dw[o][i] = sum_n dy[n][o] x[n][i], db[o] = sum_n dy[n][o].  grid (nout, ceil(nin / 256))
 __global__ void k_fc_bwd_w(Dev d, int pred, const double* dy, int ldy, const double* x, int ldx, int nin, double* dw, double* db) {
+    pdl_sync();
     if (!pred_on(d, pred)) return;
     __shared__ double dys[kB];
     const int o = blockIdx.x;
@@ -382,24 +476,35 @@ __global__ void k_fc_bwd_w(Dev d, int pred, const double* dy, int ldy, const dou
         db[o] = s;
     }
 }
-// dx[n][i] (=|+=) mask(act[n][i]) * sum_o dy[n][o] w[o][i] for i < ncols.  grid (ceil(ncols / 256), kB)
+// dx[n][i] (=|+=) mask(act[n][i]) * sum_o dy[n][o] w[o][i] for i < ncols.  grid (ceil(ncols / 32), kB), block (32, 8): the
+// output neurons are split over threadIdx.y and reduced through shared memory in a fixed order.
 __global__ void k_fc_bwd_x(Dev d, int pred, const double* dy, int ldy, int nout, const double* w, int nin, int ncols, const double* act,
                            int lda, double* dx, int ldx, int accumulate) {
+    pdl_sync();
     if (!pred_on(d, pred)) return;
     __shared__ double dys[H];
-    const int n = blockIdx.y;
-    for (int o = threadIdx.x; o < nout; o += blockDim.x) dys[o] = dy[(size_t)n * ldy + o];
+    __shared__ double part[8][33];
+    const int n = blockIdx.y, tx = threadIdx.x, ty = threadIdx.y;
+    for (int o = ty * 32 + tx; o < nout; o += 256) dys[o] = dy[(size_t)n * ldy + o];
     __syncthreads();
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= ncols) return;
+    const int i = blockIdx.x * 32 + tx;
     double s = 0;
-    for (int o = 0; o < nout; ++o) s += dys[o] * w[(size_t)o * nin + i];
-    if (act && !(act[(size_t)n * lda + i] > 0)) s = 0;
-    if (accumulate) dx[(size_t)n * ldx + i] += s; else dx[(size_t)n * ldx + i] = s;
+    if (i < ncols)
+        for (int o = ty; o < nout; o += 8) s += dys[o] * w[(size_t)o * nin + i];
+    part[ty][tx] = s;
+    __syncthreads();
+    if (ty == 0 && i < ncols) {
+        double tot = 0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) tot += part[q][tx];
+        if (act && !(act[(size_t)n * lda + i] > 0)) tot = 0;
+        if (accumulate) dx[(size_t)n * ldx + i] += tot; else dx[(size_t)n * ldx + i] = tot;
+    }
 }
 // dw[o][c][kk] = sum_{n,t} dy[n][o][t] x[n][c][t + kk]; db[o] = sum dy[n][o][t].  grid (cin, cout)
 __global__ void k_conv_bwd_w(Dev d, int pred, const double* dy, int cout, int k, const double* x, int ldn, int cin, int win, double* dw,
                              double* db) {
+    pdl_sync();
     if (!pred_on(d, pred)) return;
     const int c = blockIdx.x, o = blockIdx.y, wout = win - k + 1;
     double acc[K0 + 1];
@@ -431,6 +536,7 @@ __global__ void k_conv_bwd_w(Dev d, int pred, const double* dy, int cout, int k,
 // dx[n][c][s] = mask * sum_{o,kk} dy[n][o][s - kk] w[o][c][kk].  grid (cin, kB), one thread per input position
 __global__ void k_conv_bwd_x(Dev d, int pred, const double* dy, int cout, int k, const double* w, int cin, int win, const double* act,
                              double* dx) {
+    pdl_sync();
     if (!pred_on(d, pred)) return;
     __shared__ double ws[C2 * K2];            // cout * k <= 128
     const int c = blockIdx.x, n = blockIdx.y, wout = win - k + 1;
@@ -451,6 +557,7 @@ __global__ void k_conv_bwd_x(Dev d, int pred, const double* dy, int cout, int k,
 }
 // Caffe SGDSolver: Regularize (L2) + ComputeUpdateValue + Net::Update, one pass over all 26 blobs
 __global__ void k_sgd(Dev d, int pred) {
+    pdl_sync();
     if (!pred_on(d, pred)) return;
     const int stride = gridDim.x * blockDim.x;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < d.P; i += stride) {
@@ -505,22 +612,23 @@ int enqueue_forward(trl_trainer* t, int pred, int col0, const NetRef& net, cudaS
     const Dev& d = t->d;
     const double* th = net.theta;
     auto blob = [&](int b) { return th + d.off[b]; };
-    k_gather_norm<<<kB, 128, 0, st>>>(d, pred, col0, net.in_off, net.in_scale);
-    k_conv_fwd<<<dim3(C0, kB), 224, 0, st>>>(d, pred, d.xn, d.S, 1, kTerr, blob(0), blob(1), C0, K0, d.a0);
-    k_conv_fwd<<<dim3(C1, kB), 224, 0, st>>>(d, pred, d.a0, C0 * W0, C0, W0, blob(2), blob(3), C1, K1, d.a1);
-    k_conv_fwd<<<dim3(C2, kB), 224, 0, st>>>(d, pred, d.a1, C1 * W1, C1, W1, blob(4), blob(5), C2, K2, d.a2);
-    k_fc_fwd<<<T, 256, 0, st>>>(d, pred, d.a2, C2 * W2, C2 * W2, blob(6), blob(7), 1, d.t, T);
-    k_concat<<<kB, 160, 0, st>>>(d, pred);
-    k_fc_fwd<<<H, 256, 0, st>>>(d, pred, d.catb, d.cat, d.cat, blob(8), blob(9), 1, d.h, H);
+    launch_pdl(k_gather_norm, dim3(kB), dim3(128), 0, st, d, pred, col0, net.in_off, net.in_scale);
+    launch_pdl(k_conv_fwd, dim3(dim3(C0 / kConvOut, kB)), dim3(224), (size_t)kTerr * 8, st, d, pred, d.xn, d.S, 1, kTerr, blob(0), blob(1), C0, K0, d.a0);
+    launch_pdl(k_conv_fwd, dim3(dim3(C1 / kConvOut, kB)), dim3(224), (size_t)C0 * W0 * 8, st, d, pred, d.a0, C0 * W0, C0, W0, blob(2), blob(3), C1, K1, d.a1);
+    launch_pdl(k_conv_fwd, dim3(dim3(C2 / kConvOut, kB)), dim3(224), (size_t)C1 * W1 * 8, st, d, pred, d.a1, C1 * W1, C1, W1, blob(4), blob(5), C2, K2, d.a2);
+    launch_pdl(k_fc_fwd_split, dim3(dim3(T, kSplit)), dim3(256), 0, st, d, pred, d.a2, C2 * W2, C2 * W2, blob(6), T, d.part);
+    launch_pdl(k_fc_split_finish, dim3(kB), dim3(64), 0, st, d, pred, d.part, kSplit, blob(7), T, 1, d.t, T);
+    launch_pdl(k_concat, dim3(kB), dim3(160), 0, st, d, pred);
+    launch_pdl(k_fc_fwd_rows, dim3(H / 8), dim3(256), 0, st, d, pred, d.catb, d.cat, d.cat, blob(8), blob(9), H, 1, d.h, H);
     int col = 0;
     for (int hd = 0; hd < 4; ++hd) {
         const int nout = hd == 0 ? d.n_frags : d.frag;
         double* hh = d.hh + (size_t)hd * kB * HH;
-        k_fc_fwd<<<HH, 256, 0, st>>>(d, pred, d.h, H, H, blob(10 + 4 * hd), blob(11 + 4 * hd), 1, hh, HH);
-        k_fc_fwd<<<nout, 128, 0, st>>>(d, pred, hh, HH, HH, blob(12 + 4 * hd), blob(13 + 4 * hd), 0, d.y + col, d.n_out);
+        launch_pdl(k_fc_fwd_rows, dim3(HH / 8), dim3(256), 0, st, d, pred, d.h, H, H, blob(10 + 4 * hd), blob(11 + 4 * hd), HH, 1, hh, HH);
+        launch_pdl(k_fc_fwd_rows, dim3((nout + 7) / 8), dim3(256), 0, st, d, pred, hh, HH, HH, blob(12 + 4 * hd), blob(13 + 4 * hd), nout, 0, d.y + col, d.n_out);
         col += nout;
     }
-    t->launches += 15;
+    t->launches += 16;
     return 0;
 }
 // backward of the current net from d.dy (activations of the last forward) into d.grad, then the SGD step
@@ -532,23 +640,23 @@ int enqueue_backward_update(trl_trainer* t, int pred, cudaStream_t st) {
     for (int hd = 0; hd < 4; ++hd) {
         const int nout = hd == 0 ? d.n_frags : d.frag;
         double* hh = d.hh + (size_t)hd * kB * HH;
-        k_fc_bwd_w<<<dim3(nout, 1), 128, 0, st>>>(d, pred, d.dy + col, d.n_out, hh, HH, HH, G(12 + 4 * hd), G(13 + 4 * hd));
-        k_fc_bwd_x<<<dim3(1, kB), 128, 0, st>>>(d, pred, d.dy + col, d.n_out, nout, W(12 + 4 * hd), HH, HH, hh, HH, d.dhh, HH, 0);
-        k_fc_bwd_w<<<dim3(HH, 1), 256, 0, st>>>(d, pred, d.dhh, HH, d.h, H, H, G(10 + 4 * hd), G(11 + 4 * hd));
-        k_fc_bwd_x<<<dim3(1, kB), 256, 0, st>>>(d, pred, d.dhh, HH, HH, W(10 + 4 * hd), H, H, d.h, H, d.dh, H, hd > 0);
+        launch_pdl(k_fc_bwd_w, dim3(dim3(nout, 1)), dim3(128), 0, st, d, pred, d.dy + col, d.n_out, hh, HH, HH, G(12 + 4 * hd), G(13 + 4 * hd));
+        launch_pdl(k_fc_bwd_x, dim3(dim3(HH / 32, kB)), dim3(dim3(32, 8)), 0, st, d, pred, d.dy + col, d.n_out, nout, W(12 + 4 * hd), HH, HH, hh, HH, d.dhh, HH, 0);
+        launch_pdl(k_fc_bwd_w, dim3(dim3(HH, 1)), dim3(256), 0, st, d, pred, d.dhh, HH, d.h, H, H, G(10 + 4 * hd), G(11 + 4 * hd));
+        launch_pdl(k_fc_bwd_x, dim3(dim3(H / 32, kB)), dim3(dim3(32, 8)), 0, st, d, pred, d.dhh, HH, HH, W(10 + 4 * hd), H, H, d.h, H, d.dh, H, hd > 0);
         col += nout;
     }
-    k_fc_bwd_w<<<dim3(H, 1), 256, 0, st>>>(d, pred, d.dh, H, d.catb, d.cat, d.cat, G(8), G(9));
-    k_fc_bwd_x<<<dim3(1, kB), 64, 0, st>>>(d, pred, d.dh, H, H, W(8), d.cat, T, d.t, T, d.dt, T, 0);          // only the terr_ip0 columns
+    launch_pdl(k_fc_bwd_w, dim3(dim3(H, 1)), dim3(256), 0, st, d, pred, d.dh, H, d.catb, d.cat, d.cat, G(8), G(9));
+    launch_pdl(k_fc_bwd_x, dim3(dim3(T / 32, kB)), dim3(dim3(32, 8)), 0, st, d, pred, d.dh, H, H, W(8), d.cat, T, d.t, T, d.dt, T, 0);          // only the terr_ip0 columns
     const int nflat = C2 * W2;
-    k_fc_bwd_w<<<dim3(T, (nflat + 255) / 256), 256, 0, st>>>(d, pred, d.dt, T, d.a2, nflat, nflat, G(6), G(7));
-    k_fc_bwd_x<<<dim3((nflat + 255) / 256, kB), 256, 0, st>>>(d, pred, d.dt, T, T, W(6), nflat, nflat, d.a2, nflat, d.da2, nflat, 0);
-    k_conv_bwd_w<<<dim3(C1, C2), 256, 0, st>>>(d, pred, d.da2, C2, K2, d.a1, C1 * W1, C1, W1, G(4), G(5));
-    k_conv_bwd_x<<<dim3(C1, kB), 224, 0, st>>>(d, pred, d.da2, C2, K2, W(4), C1, W1, d.a1, d.da1);
-    k_conv_bwd_w<<<dim3(C0, C1), 256, 0, st>>>(d, pred, d.da1, C1, K1, d.a0, C0 * W0, C0, W0, G(2), G(3));
-    k_conv_bwd_x<<<dim3(C0, kB), 224, 0, st>>>(d, pred, d.da1, C1, K1, W(2), C0, W0, d.a0, d.da0);
-    k_conv_bwd_w<<<dim3(1, C0), 256, 0, st>>>(d, pred, d.da0, C0, K0, d.xn, d.S, 1, kTerr, G(0), G(1));
-    k_sgd<<<296, 256, 0, st>>>(d, pred);
+    launch_pdl(k_fc_bwd_w, dim3(dim3(T, (nflat + 255) / 256)), dim3(256), 0, st, d, pred, d.dt, T, d.a2, nflat, nflat, G(6), G(7));
+    launch_pdl(k_fc_bwd_x, dim3(dim3((nflat + 31) / 32, kB)), dim3(dim3(32, 8)), 0, st, d, pred, d.dt, T, T, W(6), nflat, nflat, d.a2, nflat, d.da2, nflat, 0);
+    launch_pdl(k_conv_bwd_w, dim3(dim3(C1, C2)), dim3(256), 0, st, d, pred, d.da2, C2, K2, d.a1, C1 * W1, C1, W1, G(4), G(5));
+    launch_pdl(k_conv_bwd_x, dim3(dim3(C1, kB)), dim3(224), 0, st, d, pred, d.da2, C2, K2, W(4), C1, W1, d.a1, d.da1);
+    launch_pdl(k_conv_bwd_w, dim3(dim3(C0, C1)), dim3(256), 0, st, d, pred, d.da1, C1, K1, d.a0, C0 * W0, C0, W0, G(2), G(3));
+    launch_pdl(k_conv_bwd_x, dim3(dim3(C0, kB)), dim3(224), 0, st, d, pred, d.da1, C1, K1, W(2), C0, W0, d.a0, d.da0);
+    launch_pdl(k_conv_bwd_w, dim3(dim3(1, C0)), dim3(256), 0, st, d, pred, d.da0, C0, K0, d.xn, d.S, 1, kTerr, G(0), G(1));
+    launch_pdl(k_sgd, dim3(296), dim3(256), 0, st, d, pred);
     t->launches += 26;
     return 0;
 }
@@ -557,34 +665,34 @@ int enqueue_train(trl_trainer* t, cudaStream_t st) {
     const Dev& d = t->d;
     const NetRef cur{d.theta, d.in_off, d.in_scale}, tar{d.target, d.t_in_off, d.t_in_scale};
     const int col_beg = 1, col_end = 1 + d.S + d.A;
-    k_stage_check<<<1, 1, 0, st>>>(d);
-    k_col_mean<<<d.S, 256, 0, st>>>(d);
-    k_col_scale<<<d.S, 256, 0, st>>>(d);
-    k_stage_commit<<<1, 1, 0, st>>>(d);
+    launch_pdl(k_stage_check, dim3(1), dim3(1), 0, st, d);
+    launch_pdl(k_col_mean, dim3(d.S), dim3(256), 0, st, d);
+    launch_pdl(k_col_scale, dim3(d.S), dim3(256), 0, st, d);
+    launch_pdl(k_stage_commit, dim3(1), dim3(1), 0, st, d);
     t->launches += 4;
     for (int s = 0; s < d.steps_per_iter; ++s) {
         // ---- critic: BuildProblem + UpdateNet (learning/NeuralNetTrainer.cpp:414-456, MACETrainer.cpp:222-247)
-        k_sample_critic<<<1, 32, 0, st>>>(d);
+        launch_pdl(k_sample_critic, dim3(1), dim3(32), 0, st, d);
         enqueue_forward(t, P_CRITIC, col_end, tar, st);
-        k_vals<<<1, 32, 0, st>>>(d, P_CRITIC, 1, d.v1);
+        launch_pdl(k_vals, dim3(1), dim3(32), 0, st, d, P_CRITIC, 1, d.v1);
         enqueue_forward(t, P_CRITIC, col_beg, cur, st);
-        k_labels<<<1, 256, 0, st>>>(d, P_CRITIC, 0);
+        launch_pdl(k_labels, dim3(1), dim3(256), 0, st, d, P_CRITIC, 0);
         enqueue_backward_update(t, P_CRITIC, st);
         // ---- actor: UpdateActorBatchBuffer + UpdateActor (learning/MACETrainer.cpp:541-626)
-        k_sample_actor<<<1, 32, 0, st>>>(d);
+        launch_pdl(k_sample_actor, dim3(1), dim3(32), 0, st, d);
         enqueue_forward(t, P_CAND, col_beg, tar, st);
-        k_vals<<<1, 32, 0, st>>>(d, P_CAND, 0, d.v0);
+        launch_pdl(k_vals, dim3(1), dim3(32), 0, st, d, P_CAND, 0, d.v0);
         enqueue_forward(t, P_CAND, col_end, tar, st);
-        k_vals<<<1, 32, 0, st>>>(d, P_CAND, 1, d.v1);
-        k_actor_select<<<1, 32, 0, st>>>(d);
+        launch_pdl(k_vals, dim3(1), dim3(32), 0, st, d, P_CAND, 1, d.v1);
+        launch_pdl(k_actor_select, dim3(1), dim3(32), 0, st, d);
         enqueue_forward(t, P_ACTOR, col_beg, cur, st);
-        k_labels<<<1, 256, 0, st>>>(d, P_ACTOR, 1);
+        launch_pdl(k_labels, dim3(1), dim3(256), 0, st, d, P_ACTOR, 1);
         enqueue_backward_update(t, P_ACTOR, st);
-        k_actor_pop<<<1, 32, 0, st>>>(d);
-        k_target_update<<<148, 256, 0, st>>>(d);
+        launch_pdl(k_actor_pop, dim3(1), dim3(32), 0, st, d);
+        launch_pdl(k_target_update, dim3(148), dim3(256), 0, st, d);
         t->launches += 10;
     }
-    k_end_iter<<<1, 32, 0, st>>>(d);
+    launch_pdl(k_end_iter, dim3(1), dim3(32), 0, st, d);
     t->launches += 1;
     return 0;
 }
@@ -593,9 +701,9 @@ int enqueue_add(trl_trainer* t, const double* rows, const uint32_t* flags, const
                 cudaStream_t st) {
     const Dev& d = t->d;
     if (max_count <= 0) return 0;
-    k_add_check<<<max_count, 128, 0, st>>>(d, rows, count_ptr, count_val);
-    k_add_assign<<<1, 32, 0, st>>>(d, flags, count_ptr, count_val, reset);
-    k_add_copy<<<max_count, 128, 0, st>>>(d, rows, flags, count_ptr, count_val);
+    launch_pdl(k_add_check, dim3(max_count), dim3(128), 0, st, d, rows, count_ptr, count_val);
+    launch_pdl(k_add_assign, dim3(1), dim3(32), 0, st, d, flags, count_ptr, count_val, reset);
+    launch_pdl(k_add_copy, dim3(max_count), dim3(128), 0, st, d, rows, flags, count_ptr, count_val);
     t->launches += 3;
     return 0;
 }
@@ -660,10 +768,11 @@ trl_trainer* trl_trainer_create(trl_handle* h, const double* p) {
     A(talloc(t, &d.h, (size_t)kB * H)); A(talloc(t, &d.hh, (size_t)4 * kB * HH)); A(talloc(t, &d.y, (size_t)kB * d.n_out));
     A(talloc(t, &d.v0, kB)); A(talloc(t, &d.v1, kB)); A(talloc(t, &d.dy, (size_t)kB * d.n_out)); A(talloc(t, &d.dhh, (size_t)kB * HH));
     A(talloc(t, &d.dh, (size_t)kB * H)); A(talloc(t, &d.dt, (size_t)kB * T)); A(talloc(t, &d.da2, (size_t)kB * C2 * W2));
-    A(talloc(t, &d.da1, (size_t)kB * C1 * W1)); A(talloc(t, &d.da0, (size_t)kB * C0 * W0)); A(talloc(t, &d.mean, d.S));
+    A(talloc(t, &d.da1, (size_t)kB * C1 * W1)); A(talloc(t, &d.da0, (size_t)kB * C0 * W0)); A(talloc(t, &d.mean, d.S)); A(talloc(t, &d.part, (size_t)kSplit * kB * T));
     t->stage_cap = add_cap;
     A(talloc(t, &t->stage_rows, (size_t)add_cap * d.Wd)); A(talloc(t, &t->stage_flags, add_cap));
     if (ok) {
+        A(cudaFuncSetAttribute(k_conv_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, C1 * W1 * 8));
         A(cudaMemset(d.pos_critic, 0xff, (size_t)d.cap * 4));
         A(cudaMemset(d.pos_actor, 0xff, (size_t)d.cap * 4));
         cudaStreamSynchronize(h->stream);
@@ -747,7 +856,7 @@ int trl_trainer_train(trl_trainer* t, int iters) {
         cudaGraphDestroy(graph);
         t->launches = before;
     }
-    const int per = 5 + t->d.steps_per_iter * (10 + 5 * 15 + 2 * 26);
+    const int per = 5 + t->d.steps_per_iter * (10 + 5 * 16 + 2 * 26);
     for (int i = 0; i < iters; ++i) {
         TCK(cudaGraphLaunch(t->train_graph, h->stream));
         t->launches += per;

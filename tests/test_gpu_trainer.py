@@ -114,7 +114,7 @@ def test_training_driver_end_to_end(assets, tmp_path):
                           trainer_num_anneal_iters=40, exp_base_anneal_iters=40)
     st = ScenarioTrainMACE(pack, 1024, schedule=sched, rng_seed=3,
                            trainer_params=dict(replay_mem_size=50000, num_init_samples=800, freeze_target_iters=10, seed=4))
-    st.Run(45)
+    st.Run(90)
     c = st.trainer.counters()
     assert c["stage"] == 1 and c["iter"] >= 5 and c["num"] > 800 and np.isfinite(c["critic_loss"])
     assert c["actor"] > 0 and c["critic"] > 0
