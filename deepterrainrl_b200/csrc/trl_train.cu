@@ -842,6 +842,15 @@ int trl_trainer_add_tuples(trl_trainer* t, const double* rows, const uint32_t* f
     return 0;
 }
 
+// tuples already on the device (e.g. the NCCL all-gather of every rank's tuple block, parallel.gather_tuple_blocks*): rows f64
+// [n][1 + S + A + S], flags u32 [n]; enqueued on the scenario's stream, which the caller must have ordered after the producer
+int trl_trainer_add_device(trl_trainer* t, const double* rows_dev, const uint32_t* flags_dev, int n) {
+    if (n > t->stage_cap) return trl_fail("trl_trainer_add_device: more tuples than the staging capacity (split the call)");
+    enqueue_add(t, rows_dev, flags_dev, nullptr, n, n, nullptr, t->h->stream);
+    TCK(cudaGetLastError());
+    return 0;
+}
+
 // `iters` x cNeuralNetTrainer::Train() on the engine's stream (ordered after the update that produced the tuples and before
 // the next one, which then evaluates the updated weights)
 int trl_trainer_train(trl_trainer* t, int iters) {

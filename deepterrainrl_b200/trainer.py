@@ -29,7 +29,7 @@ class MACETrainer:
         L.trl_trainer_create.argtypes = [C.c_void_p, C.c_void_p]
         L.trl_trainer_launches.restype = C.c_int64
         for name in ("trl_trainer_destroy", "trl_trainer_add_from_scene", "trl_trainer_add_tuples", "trl_trainer_train",
-                     "trl_trainer_counters", "trl_trainer_get", "trl_trainer_set_theta", "trl_trainer_list"):
+                     "trl_trainer_add_device", "trl_trainer_counters", "trl_trainer_get", "trl_trainer_set_theta", "trl_trainer_list"):
             getattr(L, name).restype = C.c_int
         p = dict(self.DEFAULTS)
         p.update(kw)
@@ -67,6 +67,23 @@ class MACETrainer:
         flags = np.ascontiguousarray(flags, np.uint32)
         assert rows.ndim == 2 and rows.shape[1] == self.W
         self._ck(self.L.trl_trainer_add_tuples(self.h, _p(rows), _p(flags), rows.shape[0]))
+
+    def AddTuplesDevice(self, rows, flags):
+        """rows: CUDA tensor [n, W] (any float dtype), flags: CUDA int tensor [n] -- e.g. the output of
+        parallel.unpack_tuple_blocks.  The scenario's stream waits for the current torch stream first."""
+        import torch
+        n = int(rows.shape[0])
+        if n == 0:
+            return
+        r64 = rows.to(torch.float64).contiguous()
+        f32 = flags.to(torch.int32).contiguous()
+        torch.cuda.current_stream().synchronize()          # producer (NCCL / torch kernels) done before the engine stream reads
+        cap = self.params["replay_mem_size"]
+        step = 4096
+        for b in range(0, n, step):
+            e = min(n, b + step)
+            self._ck(self.L.trl_trainer_add_device(self.h, C.c_void_p(r64[b:e].data_ptr()), C.c_void_p(f32[b:e].data_ptr()), e - b))
+        self.scenario.Sync()                               # the tensors may be freed once the copies have run
 
     def Train(self, iters=1):
         self._ck(self.L.trl_trainer_train(self.h, int(iters)))

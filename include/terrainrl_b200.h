@@ -140,6 +140,8 @@ trl_trainer* trl_trainer_create(trl_handle* h, const double* params10);
 int trl_trainer_destroy(trl_trainer* t);
 int trl_trainer_add_from_scene(trl_trainer* t);
 int trl_trainer_add_tuples(trl_trainer* t, const double* rows, const uint32_t* flags, int n);
+/* same from device memory (the all-gathered tuple blocks of every rank); ordered on the scenario's stream */
+int trl_trainer_add_device(trl_trainer* t, const double* rows_dev, const uint32_t* flags_dev, int n);
 int trl_trainer_train(trl_trainer* t, int iters);
 int trl_trainer_counters(trl_trainer* t, int64_t* counters9, double* losses2);
 int trl_trainer_num_params(trl_trainer* t);

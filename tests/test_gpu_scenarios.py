@@ -217,3 +217,31 @@ def test_two_scenes_interleaved(assets):
         a2.Update(1.0 / 30.0); b2.Update(1.0 / 30.0)
     np.testing.assert_array_equal(a2.GetStateAll()[0], qa)
     np.testing.assert_array_equal(b2.GetStateAll()[0], qb)
+
+
+def test_baseline_config_sizes(assets):
+    """BASELINE.json configs[2] (raptor + narrow_gaps, 8192 envs on one GPU) and the per-GPU share of configs[4] (goat + cliffs,
+    16384 envs over 8 GPUs = 2048 per GPU, mixed terrain seeds): size-independent properties at the full sizes."""
+    import deepterrainrl_b200 as trl
+    rap = trl.ScenarioPoliEval(os.path.join(assets, "raptor_narrow_gaps.trlpack"), 8192)
+    small = trl.ScenarioPoliEval(os.path.join(assets, "raptor_narrow_gaps.trlpack"), 16)
+    for _ in range(20):
+        rap.Update(1.0 / 30.0); small.Update(1.0 / 30.0)
+    q, qd = rap.GetStateAll()
+    assert np.all(np.isfinite(q)) and np.all(np.isfinite(qd))
+    np.testing.assert_array_equal(q[:, :16], small.GetStateAll()[0])          # batch-size independence
+    st = rap._stats()
+    assert st["steps"] == 20 * 20 * 8192 and st["cycles"] >= 8192
+    assert np.median(q[0]) > 1.5                                               # the raptor runs forward
+    del rap, small
+    n = 2048
+    seeds = (1 + 7919 * (3 * n + np.arange(n))).astype(np.uint64)              # rank 3's shard of the mixed-seed config
+    goat = trl.ScenarioPoliEval(os.path.join(assets, "goat_cliffs.trlpack"), n, terrain_seeds=seeds)
+    for _ in range(30):
+        goat.Update(1.0 / 30.0)
+    q, qd = goat.GetStateAll()
+    assert np.all(np.isfinite(q)) and np.all(np.isfinite(qd))
+    st = goat._stats()
+    assert st["steps"] == 30 * 20 * n and st["cycles"] >= n
+    d, e = goat.GetDistLog()
+    assert d.size == st["episodes"]
