@@ -164,7 +164,6 @@ static int fill_model(trl_handle* h, uint64_t rng_seed) {
         while (slot < 4 && m.child[p][slot] >= 0) ++slot;
         if (slot == 4) return fail("a link has more than 4 children");
         m.child[p][slot] = j;
-        m.level_slot[m.depth[j]][slot] = 1;
     }
     if (m.max_depth >= 16) return fail("kinematic tree too deep for the 4-round ancestor jumps");
     if (m.nj > 31) return fail("lane 31 must stay idle (zero source of the warp passes)");

@@ -72,7 +72,6 @@ struct ModelConst {
     int depth[kMaxJoints], max_depth;
     int child[kMaxJoints][4];              // up to 4 children per link (-1 = none)
     int anc_pow[kMaxJoints][4];            // 2^k-th ancestor of each link (k = 0..3), -1 if it does not exist
-    int level_slot[12][4];                 // level_slot[l][s] != 0: some link at depth l is child slot s of its parent
     // inward (leaf -> root) pass schedule: link j is eliminated in round acc_round[j] and handed to its parent at the end
     // of that round; siblings get distinct rounds so that every lane receives from at most ONE lane per round.
     // acc_src[j] packs, 5 bits per round, the lane that lane j receives from (31 = none: lane 31 is idle and holds zeros)
