@@ -19,7 +19,10 @@ namespace trl {
 namespace cg = cooperative_groups;
 
 constexpr int kDecideThreads = 512;
-constexpr int kClusterSize = 8;                            // CTAs (SMs) cooperating on one decision
+#ifndef TRL_CLUSTER
+#define TRL_CLUSTER 8
+#endif
+constexpr int kClusterSize = TRL_CLUSTER;                            // CTAs (SMs) cooperating on one decision
 constexpr int kConv0Out = 16, kConv0K = 8, kW0 = 193;
 constexpr int kConv1Out = 32, kConv1K = 4, kW1 = 190;
 constexpr int kConv2Out = 32, kConv2K = 4, kW2 = 187;
