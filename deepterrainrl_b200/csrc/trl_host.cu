@@ -68,6 +68,11 @@ static int ensure_model(trl_handle* h) {
     return 0;
 }
 
+int trl_reupload_model(trl_handle* h) {
+    g_model_owner = nullptr;
+    return ensure_model(h) ? fail("model upload failed") : 0;
+}
+
 template <typename T>
 static cudaError_t dalloc(trl_handle* h, T** p, size_t count) {
     cudaError_t e = cudaMalloc((void**)p, count * sizeof(T));

@@ -20,6 +20,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <random>
 #include <string>
 #include <vector>
 
@@ -40,7 +41,7 @@ struct Counters {
     int head, num, iter, actor_iter, stage, critic_count, actor_count, actor_batch_count;
     long long total;
     unsigned long long rng_ctr;
-    int critic_ok, cand_count, actor_ok, succ, init_now, pad;
+    int critic_ok, cand_count, actor_ok, succ, init_now, add_count;
     double critic_loss, actor_loss;
 };
 
@@ -156,11 +157,12 @@ __global__ void k_add_assign(Dev d, const uint32_t* src_flags, const int* count_
             else ++k;
         }
     }
+    c.add_count = count;                                   // k_add_copy must not re-read a counter that is reset here
     if (reset_count) *reset_count = 0;                     // cScenarioExp::ResetTupleBuffer
 }
-__global__ void k_add_copy(Dev d, const double* rows, const uint32_t* src_flags, const int* count_ptr, int count_val) {
+__global__ void k_add_copy(Dev d, const double* rows, const uint32_t* src_flags) {
     pdl_sync();
-    const int count = count_ptr ? *count_ptr : count_val;
+    const int count = d.c->add_count;
     const int i = blockIdx.x;
     if (i >= count) return;
     const int t = d.slot[i];
@@ -703,7 +705,7 @@ int enqueue_add(trl_trainer* t, const double* rows, const uint32_t* flags, const
     if (max_count <= 0) return 0;
     launch_pdl(k_add_check, dim3(max_count), dim3(128), 0, st, d, rows, count_ptr, count_val);
     launch_pdl(k_add_assign, dim3(1), dim3(32), 0, st, d, flags, count_ptr, count_val, reset);
-    launch_pdl(k_add_copy, dim3(max_count), dim3(128), 0, st, d, rows, flags, count_ptr, count_val);
+    launch_pdl(k_add_copy, dim3(max_count), dim3(128), 0, st, d, rows, flags);
     t->launches += 3;
     return 0;
 }
@@ -873,6 +875,77 @@ int trl_trainer_train(trl_trainer* t, int iters) {
     return 0;
 }
 
+// Training from scratch: the net the reference builds when no -policy_model is given.
+//  * weights: Caffe `xavier` fillers of the train prototxt (uniform(-s, s), s = sqrt(3 / fan_in), fan_in = count / num_output),
+//    biases 0 (`constant` filler); the filler RNG is Caffe's own, so only the distribution is defined -- std::mt19937_64(seed) here;
+//  * output offset / scale: cScenarioTrain::SetupTrainerOutputOffsetScale -> cBaseControllerMACE::BuildNNOutputOffsetScale
+//    (scenarios/ScenarioTrain.cpp:322-336, sim/BaseControllerMACE.cpp:75-113,131-167): critic outputs offset -0.5 scale 2; actor f is
+//    centred on the optimised parameters of control-parameter set f % n_ctrl (cDogControllerMACE::BuildActorBias,
+//    sim/DogControllerMACE.cpp:93-99) and scaled by 1 / max_a |opt(a) - opt(default action)| over the action library;
+//  * input offset 0 / scale 1 until the init stage refits them from the replay memory; momentum history cleared; target = copy.
+int trl_trainer_init_fresh(trl_trainer* t, uint64_t seed) {
+    trl_handle* h = t->h;
+    const Dev& d = t->d;
+    ModelConst& m = h->mc;
+    TCK(cudaStreamSynchronize(h->stream));
+    const int fs = d.frag, nf = d.n_frags;
+    if (m.n_opt != fs) return trl_fail("trl_trainer_init_fresh: action fragment size does not match the controller's optimised parameters");
+    auto ctrl_opt = [&](int set, int k) {
+        const int idx = m.opt_idx[k];
+        double v = m.ctrl_params[set][idx];
+        if (idx == 0 /* TransTime */ || idx == 1 /* Cv */ || (m.char_type == 2 && idx == 2 /* Cd */)) v = std::fabs(v);   // PostProcessParams
+        return v;
+    };
+    auto action_opt = [&](int a, int k) {
+        const double b = m.act_blend[a];
+        return (1.0 - b) * ctrl_opt(m.act_idx0[a], k) + b * ctrl_opt(m.act_idx1[a], k);   // BlendCtrlParams + GetOptParams
+    };
+    std::vector<double> frag_scale(fs, 1.0), out_off(d.n_out, 0.0), out_scale(d.n_out, 1.0);
+    if (m.n_actions > 1) {
+        const int d0 = m.default_action >= 0 ? m.default_action : 0;
+        for (int k = 0; k < fs; ++k) {
+            double mx = 0;
+            for (int a = 0; a < m.n_actions; ++a)
+                if (a != d0) mx = std::max(mx, std::fabs(action_opt(a, k) - action_opt(d0, k)));
+            frag_scale[k] = mx > 0 ? 1.0 / mx : 1.0;
+        }
+    }
+    for (int f = 0; f < nf; ++f) {
+        out_off[f] = -0.5; out_scale[f] = 2.0;
+        for (int k = 0; k < fs; ++k) {
+            out_off[nf + f * fs + k] = -ctrl_opt(f % m.n_ctrl, k);
+            out_scale[nf + f * fs + k] = frag_scale[k];
+        }
+    }
+    std::vector<double> theta(d.P, 0.0);
+    std::mt19937_64 gen(seed);
+    const int num_out[13] = {C0, C1, C2, T, H, HH, nf, HH, fs, HH, fs, HH, fs};
+    for (int l = 0; l < 13; ++l) {
+        const int b = 2 * l, count = d.off[b + 1] - d.off[b];
+        const double sc = std::sqrt(3.0 / ((double)count / num_out[l]));
+        std::uniform_real_distribution<double> U(-sc, sc);
+        for (int i = d.off[b]; i < d.off[b + 1]; ++i) theta[i] = U(gen);
+    }
+    std::vector<double> zeros(d.S, 0.0), ones(d.S, 1.0);
+    TCK(cudaMemcpy(d.theta, theta.data(), (size_t)d.P * 8, cudaMemcpyHostToDevice));
+    TCK(cudaMemcpy(d.target, d.theta, (size_t)d.P * 8, cudaMemcpyDeviceToDevice));
+    TCK(cudaMemset(d.history, 0, (size_t)d.P * 8));
+    double* offs[2] = {d.in_off, d.t_in_off};
+    double* scls[2] = {d.in_scale, d.t_in_scale};
+    for (int k = 0; k < 2; ++k) {
+        TCK(cudaMemcpy(offs[k], zeros.data(), (size_t)d.S * 8, cudaMemcpyHostToDevice));
+        TCK(cudaMemcpy(scls[k], ones.data(), (size_t)d.S * 8, cudaMemcpyHostToDevice));
+    }
+    double* oo[2] = {d.out_off, d.t_out_off};
+    double* os[2] = {d.out_scale, d.t_out_scale};
+    for (int k = 0; k < 2; ++k) {
+        TCK(cudaMemcpy(oo[k], out_off.data(), (size_t)d.n_out * 8, cudaMemcpyHostToDevice));
+        TCK(cudaMemcpy(os[k], out_scale.data(), (size_t)d.n_out * 8, cudaMemcpyHostToDevice));
+    }
+    for (int k = 0; k < fs; ++k) m.out_scale_actor0[k] = out_scale[nf + k];       // exploration noise scale of the decision kernel
+    return trl_reupload_model(h);
+}
+
 // c[9]: iter, actor_iter, stage, num, head, total, critic buffer, actor buffer, pending actor batch; l[2]: last losses
 int trl_trainer_counters(trl_trainer* t, int64_t* c, double* l) {
     Counters hc;
@@ -903,6 +976,16 @@ int trl_trainer_set_theta(trl_trainer* t, const double* theta) {
     TCK(cudaStreamSynchronize(t->h->stream));
     TCK(cudaMemcpy(t->d.theta, theta, (size_t)t->d.P * 8, cudaMemcpyHostToDevice));
     TCK(cudaMemcpy(t->d.target, t->d.theta, (size_t)t->d.P * 8, cudaMemcpyDeviceToDevice));
+    return 0;
+}
+// replay rows (float, [n][1 + S + A + S]) and flags of the given slots
+int trl_trainer_rows(trl_trainer* t, const int32_t* ids, int n, float* rows, int32_t* flags) {
+    TCK(cudaStreamSynchronize(t->h->stream));
+    for (int i = 0; i < n; ++i) {
+        if (ids[i] < 0 || ids[i] >= t->d.cap) return trl_fail("trl_trainer_rows: slot out of range");
+        TCK(cudaMemcpy(rows + (size_t)i * t->d.Wd, t->d.mem + (size_t)ids[i] * t->d.Wd, (size_t)t->d.Wd * 4, cudaMemcpyDeviceToHost));
+        TCK(cudaMemcpy(flags + i, t->d.flags + ids[i], 4, cudaMemcpyDeviceToHost));
+    }
     return 0;
 }
 // which: 0 critic buffer, 1 actor buffer, 2 pending actor batch, 3 ids of the last sampled batch; returns the length

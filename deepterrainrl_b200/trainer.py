@@ -58,6 +58,10 @@ class MACETrainer:
         if rc != 0:
             raise RuntimeError(self.L.trl_last_error().decode())
 
+    def InitFresh(self, seed=1):
+        """Start from a freshly initialised net (no -policy_model): xavier weights, controller-derived output offset / scale."""
+        self._ck(self.L.trl_trainer_init_fresh(self.h, C.c_uint64(seed)))
+
     # ---- cNeuralNetLearner::Train = AddTuples + Train + SyncNet
     def AddTuplesFromScene(self):
         self._ck(self.L.trl_trainer_add_from_scene(self.h))
@@ -120,6 +124,13 @@ class MACETrainer:
         n = C.c_int(0)
         self._ck(self.L.trl_trainer_list(self.h, {"critic": 0, "actor": 1, "actor_batch": 2, "last_ids": 3}[which], _p(out), cap, C.byref(n)))
         return out[:n.value].copy()
+
+    def rows(self, slots):
+        slots = np.ascontiguousarray(slots, np.int32)
+        rows = np.zeros((slots.size, self.W), np.float32)
+        flags = np.zeros(slots.size, np.int32)
+        self._ck(self.L.trl_trainer_rows(self.h, _p(slots), slots.size, _p(rows), _p(flags)))
+        return rows, flags
 
     def KernelLaunches(self):
         return int(self.L.trl_trainer_launches(self.h))

@@ -138,6 +138,9 @@ int trl_train_schedule(const double* sp9, int iters, double* out4);
 typedef struct trl_trainer trl_trainer;
 trl_trainer* trl_trainer_create(trl_handle* h, const double* params10);
 int trl_trainer_destroy(trl_trainer* t);
+/* training from scratch: xavier-filled weights + cBaseControllerMACE::BuildNNOutputOffsetScale (sim/BaseControllerMACE.cpp:75-113),
+ * what cScenarioTrain::InitTrainer leaves when no -policy_model is given (scenarios/ScenarioTrain.cpp:253-259,322-336) */
+int trl_trainer_init_fresh(trl_trainer* t, uint64_t seed);
 int trl_trainer_add_from_scene(trl_trainer* t);
 int trl_trainer_add_tuples(trl_trainer* t, const double* rows, const uint32_t* flags, int n);
 /* same from device memory (the all-gathered tuple blocks of every rank); ordered on the scenario's stream */
@@ -149,6 +152,7 @@ int64_t trl_trainer_launches(trl_trainer* t);
 int trl_trainer_get(trl_trainer* t, int what, double* out);
 int trl_trainer_set_theta(trl_trainer* t, const double* theta);
 int trl_trainer_list(trl_trainer* t, int which, int32_t* out, int cap, int* len);
+int trl_trainer_rows(trl_trainer* t, const int32_t* slots, int n, float* rows, int32_t* flags);
 
 const char* trl_last_error(void);
 

@@ -81,9 +81,13 @@ def test_rollout_uses_trainer_weights_and_device_tuples(assets):
     np.testing.assert_array_equal(a.GetStateAll()[0], b.GetStateAll()[0])      # binding alone changes nothing
     nt = b.GetNumTuples()
     assert nt > n
+    src_rows, src_flags, _ = b.GetTuples(f64=True)                             # does not reset the scenario's buffer
     tr.AddTuplesFromScene()
     c = tr.counters()
     assert c["num"] == nt and c["critic"] + c["actor"] == nt and c["actor"] > 0
+    got_rows, got_flags = tr.rows(np.arange(nt))                               # replay slots 0..nt-1 in arrival order
+    np.testing.assert_array_equal(got_rows, src_rows.astype(np.float32))       # SetTuple stores floats
+    np.testing.assert_array_equal(got_flags, src_flags.astype(np.int32))
     assert b.GetNumTuples() == 0                                               # ResetTupleBuffer happened on the device
     theta0 = tr.get("theta")
     for _ in range(30):
@@ -139,3 +143,36 @@ def test_training_driver_end_to_end(assets, tmp_path):
     for _ in range(10):
         ev.Update(1.0 / 30.0)
     assert np.all(np.isfinite(ev.GetStateAll()[0]))
+
+
+def test_training_from_scratch(assets):
+    """trl_trainer_init_fresh: xavier weights inside their bounds, zero biases, controller-derived output offset / scale; the
+    rollout runs on the fresh net (exploring from the start like the reference) and the trainer leaves the init stage."""
+    import deepterrainrl_b200 as trl
+    from deepterrainrl_b200.train import ScenarioTrainMACE, TrainSchedule
+    pack = os.path.join(assets, "dog_slopes_mixed.trlpack")
+    # (with the reference's initial rates 0.9 / 0.9 only 1 % of the tuples reach the critic buffer; it then relies on 50000 initial samples)
+    sched = TrainSchedule(init_exp_rate=0.5, exp_rate=0.2, init_exp_temp=20, exp_temp=0.025, init_exp_base_rate=0.3, exp_base_rate=0.002,
+                          trainer_num_anneal_iters=50000, exp_base_anneal_iters=50000)
+    st = ScenarioTrainMACE(pack, 1024, schedule=sched, rng_seed=8, iters_per_update=2,
+                           trainer_params=dict(replay_mem_size=50000, num_init_samples=600, freeze_target_iters=20, seed=6))
+    shipped = st.trainer.get("theta")
+    st.trainer.InitFresh(seed=3)
+    blobs = st.trainer.blobs()
+    for name, (w, b) in blobs.items():
+        fan_in = w.size / w.shape[0]
+        s = np.sqrt(3.0 / fan_in)
+        assert np.all(np.abs(w) <= s) and np.abs(w).max() > 0.9 * s and abs(w.mean()) < 0.05 * s
+        assert np.all(b == 0)
+    assert not np.array_equal(st.trainer.get("theta"), shipped)
+    np.testing.assert_array_equal(st.trainer.get("target"), st.trainer.get("theta"))
+    oo, os_ = st.trainer.get("out_off"), st.trainer.get("out_scale")
+    assert np.all(oo[:3] == -0.5) and np.all(os_[:3] == 2.0)
+    assert np.all(np.isfinite(os_)) and np.all(os_[3:] > 0)
+    np.testing.assert_array_equal(os_[3:32], os_[32:61])               # every actor shares the action-library scale
+    assert np.all(st.trainer.get("in_off") == 0) and np.all(st.trainer.get("in_scale") == 1)
+    st.Run(70)
+    c = st.trainer.counters()
+    assert c["stage"] == 1 and c["iter"] > 10 and np.isfinite(c["critic_loss"])
+    assert np.all(np.isfinite(st.trainer.get("theta"))) and np.all(np.isfinite(st.exp.GetStateAll()[0]))
+    assert not np.all(st.trainer.get("in_off") == 0)                   # refitted from the replay memory at the stage switch
