@@ -14,6 +14,7 @@
 #include "../../include/terrainrl_b200.h"
 #include "ref_loader.h"
 #include "scene_pack.h"
+#include "model_io.h"
 #include "trl_types.h"
 
 namespace trl {
@@ -581,6 +582,117 @@ int trl_set_explore(trl_handle* h, int enable, double rate, double temp, double 
     // ...) neither re-captures the update graph nor drains the stream: the copy is ordered behind the work already queued
     h->ex.enable = enable; h->ex.rate = rate; h->ex.temp = temp; h->ex.base_rate = base_rate;
     CK(cudaMemcpyAsync(h->d_ex, &h->ex, sizeof(ExpSettings), cudaMemcpyHostToDevice, h->stream));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- model files
+static const char* kDeployLayers[27] = {"slice0", "terr_conv0", "terr_relu0", "terr_conv1", "terr_relu1", "terr_conv2", "terr_relu2",
+                                        "terr_ip0", "terr_relu3", "char_flatten0", "concat0", "ip0", "relu0", "relu0_relu0_0_split",
+                                        "val_ip0", "val_relu0", "val_ip1", "a0_ip0", "a0_relu0", "a0_ip1", "a1_ip0", "a1_relu0", "a1_ip1",
+                                        "a2_ip0", "a2_relu0", "a2_ip1", "output"};
+// Caffe blob shapes of the 13 parameter layers (weights; the bias of each is [num_output])
+static std::vector<std::vector<uint64_t>> mace_weight_dims(int n_char, int n_frags, int frag) {
+    std::vector<std::vector<uint64_t>> d = {{16, 1, 1, 8}, {32, 16, 1, 4}, {32, 32, 1, 4}, {64, 32 * 187}, {256, (uint64_t)(64 + n_char)}};
+    for (int hd = 0; hd < 4; ++hd) { d.push_back({128, 256}); d.push_back({(uint64_t)(hd == 0 ? n_frags : frag), 128}); }
+    return d;
+}
+// cNeuralNet::OutputModel for host-side weights: blobs[26] in layer order (w, b per layer)
+int trl_write_model(const char* path, const double* const* blobs, int n_char, int n_frags, int frag, const double* in_off,
+                    const double* in_scale, const double* out_off, const double* out_scale, uint32_t mtime) {
+    try {
+        auto dims = mace_weight_dims(n_char, n_frags, frag);
+        std::map<std::string, std::vector<H5Writer::Blob>> named;
+        for (int l = 0; l < 13; ++l)
+            named[kNetLayers[l]] = {H5Writer::Blob{dims[l], blobs[2 * l]}, H5Writer::Blob{{dims[l][0]}, blobs[2 * l + 1]}};
+        std::vector<std::string> layers(kDeployLayers, kDeployLayers + 27);
+        std::vector<uint8_t> img = H5Writer::build(layers, named, mtime);
+        const std::string p = path;
+        write_file(p, img.data(), img.size());
+        const size_t dot = p.find_last_of('.');
+        const int n_in = 200 + n_char, n_out = n_frags * (1 + frag);
+        write_scale_file((dot == std::string::npos ? p : p.substr(0, dot)) + "_scale.txt", in_off, in_scale, n_in, out_off, out_scale, n_out);
+    } catch (const std::exception& e) {
+        return fail(e.what());
+    }
+    return 0;
+}
+// the policy the scenario currently evaluates (the attached trainer's net if there is one)
+int trl_output_model(trl_handle* h, const char* path, uint32_t mtime) {
+    if (!h->mc.has_net) return fail("trl_output_model: scene has no policy net");
+    CK(cudaStreamSynchronize(h->stream));
+    const NetWeights& W = h->W;
+    const double* dev[30] = {W.conv0_w, W.conv0_b, W.conv1_w, W.conv1_b, W.conv2_w, W.conv2_b, W.tip0_w, W.tip0_b, W.ip0_w, W.ip0_b};
+    for (int k = 0; k < 4; ++k) { dev[10 + 4 * k] = W.h0_w[k]; dev[11 + 4 * k] = W.h0_b[k]; dev[12 + 4 * k] = W.h1_w[k]; dev[13 + 4 * k] = W.h1_b[k]; }
+    dev[26] = W.in_off; dev[27] = W.in_scale; dev[28] = W.out_off; dev[29] = W.out_scale;
+    std::vector<std::vector<double>> host(30);
+    const double* ptr[30];
+    for (int i = 0; i < 30; ++i) {
+        host[i].resize((size_t)h->net_counts[i]);
+        CK(cudaMemcpy(host[i].data(), dev[i], host[i].size() * 8, cudaMemcpyDeviceToHost));
+        ptr[i] = host[i].data();
+    }
+    return trl_write_model(path, ptr, h->mc.n_char, h->mc.n_frags, h->mc.frag, ptr[26], ptr[27], ptr[28], ptr[29], mtime);
+}
+int trl_trainer_set_theta(trl_trainer* t, const double* theta);
+// cNeuralNet::LoadModel + LoadScale (learning/NeuralNet.cpp:157-186): Caffe HDF5 weights + `_scale.txt`
+int trl_load_model(trl_handle* h, const char* h5_path, const char* scale_path) {
+    if (!h->mc.has_net) return fail("trl_load_model: scene has no policy net");
+    if (h->trainer) return fail("trl_load_model: a trainer owns the policy weights (load before trl_trainer_create)");
+    try {
+        H5Reader h5(h5_path);
+        const auto& ds = h5.datasets();
+        const double* blobs[26];
+        int64_t counts[26];
+        for (int l = 0; l < 13; ++l)
+            for (int k = 0; k < 2; ++k) {
+                auto it = ds.find(std::string("/data/") + kNetLayers[l] + "/" + std::to_string(k));
+                if (it == ds.end()) return fail(std::string("trl_load_model: missing dataset for layer ") + kNetLayers[l]);
+                blobs[2 * l + k] = it->second.data(); counts[2 * l + k] = (int64_t)it->second.size();
+            }
+        JValue sc = load_json(scale_path);
+        const char* keys[4] = {"InputOffset", "InputScale", "OutputOffset", "OutputScale"};
+        std::vector<double> vec[4];
+        for (int k = 0; k < 4; ++k) {
+            const JValue* v = sc.get(keys[k]);
+            if (!v || v->type != JValue::Arr) return fail(std::string("trl_load_model: scale file lacks ") + keys[k]);
+            for (auto& e : v->arr) vec[k].push_back(e.num);
+        }
+        return trl_set_weights(h, blobs, counts, 26, vec[0].data(), vec[1].data(), vec[2].data(), vec[3].data());
+    } catch (const std::exception& e) {
+        return fail(e.what());
+    }
+}
+// cBaseControllerMACE::BuildNNOutputOffsetScale (sim/BaseControllerMACE.cpp:75-113,131-167): critic outputs offset -0.5 scale 2;
+// actor f centred on the optimised parameters of control set f % n_ctrl (cDogControllerMACE::BuildActorBias) and scaled by
+// 1 / max_a |opt(a) - opt(default action)| over the action library
+int trl_get_output_offset_scale(trl_handle* h, double* off, double* scale, int n) {
+    const ModelConst& m = h->mc;
+    const int fs = m.n_opt, nf = m.has_net ? m.n_frags : 0;
+    if (n != nf * (1 + fs)) return fail("trl_get_output_offset_scale: size mismatch");
+    auto ctrl_opt = [&](int set, int k) {
+        const int idx = m.opt_idx[k];
+        double v = m.ctrl_params[set][idx];
+        if (idx == 0 || idx == 1 || (m.char_type == 2 && idx == 2)) v = std::fabs(v);     // PostProcessParams (TransTime, Cv, raptor Cd)
+        return v;
+    };
+    auto action_opt = [&](int a, int k) {
+        const double b = m.act_blend[a];
+        return (1.0 - b) * ctrl_opt(m.act_idx0[a], k) + b * ctrl_opt(m.act_idx1[a], k);   // BlendCtrlParams + GetOptParams
+    };
+    std::vector<double> frag_scale(fs, 1.0);
+    if (m.n_actions > 1) {
+        const int d0 = m.default_action >= 0 ? m.default_action : 0;
+        for (int k = 0; k < fs; ++k) {
+            double mx = 0;
+            for (int a = 0; a < m.n_actions; ++a)
+                if (a != d0) mx = std::max(mx, std::fabs(action_opt(a, k) - action_opt(d0, k)));
+            frag_scale[k] = mx > 0 ? 1.0 / mx : 1.0;
+        }
+    }
+    for (int f = 0; f < nf; ++f) {
+        off[f] = -0.5; scale[f] = 2.0;
+        for (int k = 0; k < fs; ++k) { off[nf + f * fs + k] = -ctrl_opt(f % m.n_ctrl, k); scale[nf + f * fs + k] = frag_scale[k]; }
+    }
     return 0;
 }
 

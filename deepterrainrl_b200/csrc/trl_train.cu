@@ -889,34 +889,8 @@ int trl_trainer_init_fresh(trl_trainer* t, uint64_t seed) {
     ModelConst& m = h->mc;
     TCK(cudaStreamSynchronize(h->stream));
     const int fs = d.frag, nf = d.n_frags;
-    if (m.n_opt != fs) return trl_fail("trl_trainer_init_fresh: action fragment size does not match the controller's optimised parameters");
-    auto ctrl_opt = [&](int set, int k) {
-        const int idx = m.opt_idx[k];
-        double v = m.ctrl_params[set][idx];
-        if (idx == 0 /* TransTime */ || idx == 1 /* Cv */ || (m.char_type == 2 && idx == 2 /* Cd */)) v = std::fabs(v);   // PostProcessParams
-        return v;
-    };
-    auto action_opt = [&](int a, int k) {
-        const double b = m.act_blend[a];
-        return (1.0 - b) * ctrl_opt(m.act_idx0[a], k) + b * ctrl_opt(m.act_idx1[a], k);   // BlendCtrlParams + GetOptParams
-    };
-    std::vector<double> frag_scale(fs, 1.0), out_off(d.n_out, 0.0), out_scale(d.n_out, 1.0);
-    if (m.n_actions > 1) {
-        const int d0 = m.default_action >= 0 ? m.default_action : 0;
-        for (int k = 0; k < fs; ++k) {
-            double mx = 0;
-            for (int a = 0; a < m.n_actions; ++a)
-                if (a != d0) mx = std::max(mx, std::fabs(action_opt(a, k) - action_opt(d0, k)));
-            frag_scale[k] = mx > 0 ? 1.0 / mx : 1.0;
-        }
-    }
-    for (int f = 0; f < nf; ++f) {
-        out_off[f] = -0.5; out_scale[f] = 2.0;
-        for (int k = 0; k < fs; ++k) {
-            out_off[nf + f * fs + k] = -ctrl_opt(f % m.n_ctrl, k);
-            out_scale[nf + f * fs + k] = frag_scale[k];
-        }
-    }
+    std::vector<double> out_off(d.n_out, 0.0), out_scale(d.n_out, 1.0);
+    if (trl_get_output_offset_scale(h, out_off.data(), out_scale.data(), d.n_out)) return 1;
     std::vector<double> theta(d.P, 0.0);
     std::mt19937_64 gen(seed);
     const int num_out[13] = {C0, C1, C2, T, H, HH, nf, HH, fs, HH, fs, HH, fs};

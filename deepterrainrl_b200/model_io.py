@@ -264,9 +264,9 @@ def write_model(path, blobs, in_off, in_scale, out_off, out_scale, layers=None, 
 
 
 def write_scale(path, in_off, in_scale, out_off, out_scale):
-    """cNeuralNet::WriteOffsetScale (learning/NeuralNet.cpp:1182-1205): same keys and key order; full-precision numbers."""
+    """cNeuralNet::WriteOffsetScale (learning/NeuralNet.cpp:1182-1205): same keys and key order; %.17g numbers (round-trip exact)."""
     def vec(v):
-        return "[" + ", ".join(repr(float(x)) for x in np.asarray(v).ravel()) + "]"
+        return "[" + ", ".join("%.17g" % float(x) for x in np.asarray(v).ravel()) + "]"
     with open(path, "w") as f:
         f.write("{\n\"InputOffset\": %s,\n\"InputScale\": %s,\n\"OutputOffset\": %s,\n\"OutputScale\": %s\n}" %
                 (vec(in_off), vec(in_scale), vec(out_off), vec(out_scale)))
@@ -287,3 +287,23 @@ def read_model(path):
         with open(sp) as f:
             scale = {k: np.array(v, float) for k, v in json.load(f).items()}
     return out, scale
+
+
+def write_model_native(path, blobs, in_off, in_scale, out_off, out_scale, mtime=0):
+    """The same file through the C ABI's native writer (csrc/model_io.h): blobs {layer: (w, b)} of the 13 parameter layers."""
+    import ctypes as C
+    from .scenario import load_library
+    L = load_library()
+    order = ["terr_conv0", "terr_conv1", "terr_conv2", "terr_ip0", "ip0", "val_ip0", "val_ip1", "a0_ip0", "a0_ip1", "a1_ip0", "a1_ip1",
+             "a2_ip0", "a2_ip1"]
+    arrs = []
+    for name in order:
+        arrs += [np.ascontiguousarray(blobs[name][0], np.float64), np.ascontiguousarray(blobs[name][1], np.float64)]
+    ptrs = (C.c_void_p * 26)(*[a.ctypes.data_as(C.c_void_p) for a in arrs])
+    n_char = blobs["ip0"][0].shape[1] - 64
+    n_frags, frag = blobs["val_ip1"][0].shape[0], blobs["a0_ip1"][0].shape[0]
+    vec = [np.ascontiguousarray(v, np.float64) for v in (in_off, in_scale, out_off, out_scale)]
+    os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+    rc = L.trl_write_model(path.encode(), ptrs, n_char, n_frags, frag, *[v.ctypes.data_as(C.c_void_p) for v in vec], C.c_uint32(mtime))
+    if rc != 0:
+        raise RuntimeError(L.trl_last_error().decode())

@@ -58,6 +58,7 @@ EXPORTS = [
     "trl_get_tuples_f64", "trl_reset_tuples", "trl_eval_stats", "trl_dist_log", "trl_get_state", "trl_set_state",
     "trl_get_state_all", "trl_get_ctrl", "trl_get_poli_state", "trl_get_net_out", "trl_get_terrain",
     "trl_kernel_launches", "trl_last_error", "trl_bench_updates", "trl_update_timed", "trl_device_tuple_block", "trl_snapshot", "trl_snapshot_wait", "trl_update_timed_detail", "trl_debug_time_decide",
+    "trl_load_model", "trl_output_model", "trl_write_model", "trl_get_output_offset_scale",
     "trl_set_terrain_lerp", "trl_train_schedule", "trl_trainer_create", "trl_trainer_destroy", "trl_trainer_init_fresh", "trl_trainer_add_from_scene", "trl_trainer_add_tuples", "trl_trainer_add_device", "trl_trainer_train",
     "trl_trainer_counters", "trl_trainer_num_params", "trl_trainer_launches", "trl_trainer_get", "trl_trainer_set_theta", "trl_trainer_list", "trl_trainer_rows",
 ]
@@ -141,6 +142,22 @@ class BatchedScenario:
     def Reset(self, env_ids=None):
         ids = None if env_ids is None else np.ascontiguousarray(env_ids, dtype=np.int32)
         self._ck(self.L.trl_reset(self.h, _p(ids), 0 if ids is None else ids.size))
+
+    def OutputModel(self, path, mtime=0):
+        """cNeuralNet::OutputModel of the policy the scenario evaluates: Caffe-layout HDF5 + `<stem>_scale.txt`, written natively."""
+        self._ck(self.L.trl_output_model(self.h, path.encode(), C.c_uint32(mtime)))
+
+    def LoadModel(self, h5_path, scale_path=None):
+        """cNeuralNet::LoadModel + LoadScale from the reference's file formats."""
+        scale_path = scale_path or (os.path.splitext(h5_path)[0] + "_scale.txt")
+        self._ck(self.L.trl_load_model(self.h, h5_path.encode(), scale_path.encode()))
+
+    def GetOutputOffsetScale(self):
+        """cBaseControllerMACE::BuildNNOutputOffsetScale."""
+        n = self.num_frags * (1 + self.frag_size)
+        off = np.zeros(n); scale = np.zeros(n)
+        self._ck(self.L.trl_get_output_offset_scale(self.h, _p(off), _p(scale), n))
+        return off, scale
 
     def SetTerrainParamsLerp(self, lerp):
         """cScenarioSimChar::SetTerrainParamsLerp (scenarios/ScenarioSimChar.cpp:255-272)."""

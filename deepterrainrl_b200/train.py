@@ -116,6 +116,6 @@ class ScenarioTrainMACE:
 
     def OutputModel(self, path):
         """cNeuralNet::OutputModel (learning/NeuralNet.cpp:571-587, 1182-1205): Caffe-layout HDF5 + `<stem>_scale.txt`."""
-        from .model_io import write_model
-        t = self.trainer
-        write_model(path, t.blobs(), t.get("in_off"), t.get("in_scale"), t.get("out_off"), t.get("out_scale"))
+        import time
+        os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+        self.exp.OutputModel(path, mtime=int(time.time()))            # native writer behind the C ABI (csrc/model_io.h)

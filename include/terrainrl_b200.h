@@ -128,6 +128,18 @@ int trl_debug_time_decide(trl_handle* h, int n_pending, int iters, double* ms_av
  *                             learning/MACETrainer.cpp:335-361), asynchronous on the scenario's stream
  *   trl_trainer_counters      GetIter / GetNumTuples / buffer sizes / last losses
  *   trl_trainer_get, _set_theta, _list   model read-back (OutputModel), LoadModel, buffer inspection for the tests */
+/* model files in the reference's formats, natively (no Python, no libhdf5):
+ *   trl_load_model     cNeuralNet::LoadModel + LoadScale (learning/NeuralNet.cpp:157-186): Caffe ToHDF5 weights + `_scale.txt`
+ *   trl_output_model   cNeuralNet::OutputModel + WriteOffsetScale (learning/NeuralNet.cpp:571-587,1182-1205) of the policy the
+ *                      scenario currently evaluates (the attached trainer's net if there is one); mtime = HDF5 modification stamp
+ *   trl_write_model    the same for host-side weights: blobs[26] = (weights, bias) of the 13 parameter layers in net order
+ *   trl_get_output_offset_scale   cBaseControllerMACE::BuildNNOutputOffsetScale (sim/BaseControllerMACE.cpp:75-113) */
+int trl_load_model(trl_handle* h, const char* h5_path, const char* scale_json_path);
+int trl_output_model(trl_handle* h, const char* path, uint32_t mtime);
+int trl_write_model(const char* path, const double* const* blobs26, int n_char, int n_frags, int frag_size, const double* in_off,
+                    const double* in_scale, const double* out_off, const double* out_scale, uint32_t mtime);
+int trl_get_output_offset_scale(trl_handle* h, double* offset, double* scale, int n_out);
+
 /* cScenarioSimChar::SetTerrainParamsLerp (scenarios/ScenarioSimChar.cpp:255-272) and cScenarioTrain's annealing schedule
  * (scenarios/ScenarioTrain.cpp:412-460): sp[9] = {init_exp_rate, exp_rate, init_exp_temp, exp_temp, init_exp_base_rate,
  * exp_base_rate, trainer_num_anneal_iters, exp_base_anneal_iters, trainer_curriculum_iters};

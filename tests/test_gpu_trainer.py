@@ -133,6 +133,16 @@ def test_training_driver_end_to_end(assets, tmp_path):
         np.testing.assert_array_equal(layers[name][0], w)
         np.testing.assert_array_equal(layers[name][1], b)
     np.testing.assert_array_equal(scale["InputOffset"], st.trainer.get("in_off"))
+    # native write-back of the same policy is byte-identical, and trl_load_model reads it into a fresh scenario
+    out2 = str(tmp_path / "native" / "model.h5")
+    os.makedirs(os.path.dirname(out2))
+    st.exp.OutputModel(out2, mtime=7)
+    from deepterrainrl_b200.model_io import write_model
+    write_model(str(tmp_path / "py7.h5"), blobs, st.trainer.get("in_off"), st.trainer.get("in_scale"), st.trainer.get("out_off"),
+                st.trainer.get("out_scale"), mtime=7)
+    assert open(out2, "rb").read() == open(tmp_path / "py7.h5", "rb").read()
+    ev2 = trl.ScenarioPoliEval(pack, 64)
+    ev2.LoadModel(out2)
     # the written model drives a fresh evaluation scenario (cNeuralNet::LoadModel path = SetWeights)
     ev = trl.ScenarioPoliEval(pack, 64)
     flat = []
@@ -141,8 +151,9 @@ def test_training_driver_end_to_end(assets, tmp_path):
         flat += [layers[name][0].ravel(), layers[name][1]]
     ev.SetWeights(flat, scale["InputOffset"], scale["InputScale"], scale["OutputOffset"], scale["OutputScale"])
     for _ in range(10):
-        ev.Update(1.0 / 30.0)
+        ev.Update(1.0 / 30.0); ev2.Update(1.0 / 30.0)
     assert np.all(np.isfinite(ev.GetStateAll()[0]))
+    np.testing.assert_array_equal(ev.GetStateAll()[0], ev2.GetStateAll()[0])       # both loading paths give the same policy
 
 
 def test_training_from_scratch(assets):
@@ -167,6 +178,8 @@ def test_training_from_scratch(assets):
     assert not np.array_equal(st.trainer.get("theta"), shipped)
     np.testing.assert_array_equal(st.trainer.get("target"), st.trainer.get("theta"))
     oo, os_ = st.trainer.get("out_off"), st.trainer.get("out_scale")
+    go, gs = st.exp.GetOutputOffsetScale()
+    np.testing.assert_array_equal(oo, go); np.testing.assert_array_equal(os_, gs)
     assert np.all(oo[:3] == -0.5) and np.all(os_[:3] == 2.0)
     assert np.all(np.isfinite(os_)) and np.all(os_[3:] > 0)
     np.testing.assert_array_equal(os_[3:32], os_[32:61])               # every actor shares the action-library scale

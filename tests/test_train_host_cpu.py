@@ -79,6 +79,18 @@ def test_model_write_back_round_trip(assets, tmp_path):
     assert body[:20].hex() == "11203f000800000000004000340b0034ff030000"
 
 
+def test_native_writer_is_byte_identical(assets, tmp_path):
+    """csrc/model_io.h (C ABI trl_write_model) and the Python writer produce the same bytes, HDF5 image and scale file."""
+    from deepterrainrl_b200.model_io import write_model, write_model_native
+    p, blobs = _pack_blobs(assets)
+    a, b = str(tmp_path / "py" / "m.h5"), str(tmp_path / "cc" / "m.h5")
+    args = (blobs, p["net_in_offset"], p["net_in_scale"], p["net_out_offset"], p["net_out_scale"])
+    write_model(a, *args, mtime=1459171656)
+    write_model_native(b, *args, mtime=1459171656)
+    assert open(a, "rb").read() == open(b, "rb").read()
+    assert open(a[:-3] + "_scale.txt").read() == open(b[:-3] + "_scale.txt").read()
+
+
 def test_cycle_recorder_formats(tmp_path):
     from deepterrainrl_b200.records import CycleRecorder
     S, A = 5, 3
