@@ -920,6 +920,45 @@ int trl_trainer_init_fresh(trl_trainer* t, uint64_t seed) {
     return trl_reupload_model(h);
 }
 
+// cScenarioTrain::Run for one batch (scenarios/ScenarioTrain.cpp:100-115,376-410): `num_updates` x { Update(time_step); hand the
+// tuples to the trainer; `iters_per_update` trainer iterations (0: one per `tuple_buffer_size` new tuples, which costs one small
+// read-back per update); anneal the exploration settings and the curriculum phase from the iteration count }.  sp[9] as in
+// trl_train_schedule.  Everything is enqueued on the scenario's stream; the call returns after the last update is queued
+// (iters_per_update > 0) -- synchronise with trl_sync / trl_trainer_counters.
+int trl_train_run(trl_trainer* t, const double* sp, int num_updates, int iters_per_update, int tuple_buffer_size, double time_step) {
+    trl_handle* h = t->h;
+    long long last_total = -1, carry = 0;
+    long long iters_req = 0;
+    double last_phase = -1.0;
+    for (int u = 0; u < num_updates; ++u) {
+        double s[4];
+        long long it = iters_req;
+        if (iters_per_update <= 0) {
+            int64_t c[9];
+            if (trl_trainer_counters(t, c, nullptr)) return 1;
+            it = c[0];
+            if (last_total < 0) last_total = c[5];
+        }
+        trl_train_schedule(sp, (int)std::min<long long>(it, 2000000000LL), s);
+        if (trl_set_explore(h, 1, s[0], s[1], s[2])) return 1;
+        if (s[3] != last_phase) { if (trl_set_terrain_lerp(h, s[3])) return 1; last_phase = s[3]; }
+        if (trl_update(h, time_step)) return 1;
+        if (trl_trainer_add_from_scene(t)) return 1;
+        int k = iters_per_update;
+        if (iters_per_update <= 0) {
+            int64_t c[9];
+            if (trl_trainer_counters(t, c, nullptr)) return 1;
+            const long long fresh = c[5] - last_total + carry;
+            last_total = c[5];
+            k = (int)(fresh / std::max(1, tuple_buffer_size));
+            carry = fresh % std::max(1, tuple_buffer_size);
+        }
+        if (k > 0 && trl_trainer_train(t, k)) return 1;
+        iters_req += k;
+    }
+    return 0;
+}
+
 // c[9]: iter, actor_iter, stage, num, head, total, critic buffer, actor buffer, pending actor batch; l[2]: last losses
 int trl_trainer_counters(trl_trainer* t, int64_t* c, double* l) {
     Counters hc;

@@ -102,6 +102,16 @@ class ScenarioTrainMACE:
         # iterations is its upper bound (equal once the trainer has left the init stage)
         return self._apply_schedule(self._iters if self.iters_per_update is not None else self.trainer.GetIter())
 
+    def RunNative(self, num_updates):
+        """The same loop entirely behind the C ABI (trl_train_run): no Python between the updates."""
+        sp = np.array([self.schedule.p[k] for k in TrainSchedule.KEYS], float)
+        L = self.trainer.L
+        rc = L.trl_train_run(self.trainer.h, sp.ctypes.data_as(C.c_void_p), int(num_updates), int(self.iters_per_update or 0),
+                             int(self.tuple_buffer_size), C.c_double(self.time_step))
+        if rc != 0:
+            raise RuntimeError(L.trl_last_error().decode())
+        self._iters = self.trainer.GetIter()
+
     def Run(self, num_updates, log_every=0):
         for u in range(num_updates):
             s = self.Update()

@@ -158,6 +158,9 @@ int trl_trainer_add_tuples(trl_trainer* t, const double* rows, const uint32_t* f
 /* same from device memory (the all-gathered tuple blocks of every rank); ordered on the scenario's stream */
 int trl_trainer_add_device(trl_trainer* t, const double* rows_dev, const uint32_t* flags_dev, int n);
 int trl_trainer_train(trl_trainer* t, int iters);
+/* cScenarioTrain::Run for one batch (scenarios/ScenarioTrain.cpp:100-115,376-410): num_updates x {update, tuple hand-over,
+ * trainer iterations (iters_per_update, or 0 = one per tuple_buffer_size new tuples), annealed exploration + curriculum} */
+int trl_train_run(trl_trainer* t, const double* sp9, int num_updates, int iters_per_update, int tuple_buffer_size, double time_step);
 int trl_trainer_counters(trl_trainer* t, int64_t* counters9, double* losses2);
 int trl_trainer_num_params(trl_trainer* t);
 int64_t trl_trainer_launches(trl_trainer* t);

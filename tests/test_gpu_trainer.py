@@ -189,3 +189,22 @@ def test_training_from_scratch(assets):
     assert c["stage"] == 1 and c["iter"] > 10 and np.isfinite(c["critic_loss"])
     assert np.all(np.isfinite(st.trainer.get("theta"))) and np.all(np.isfinite(st.exp.GetStateAll()[0]))
     assert not np.all(st.trainer.get("in_off") == 0)                   # refitted from the replay memory at the stage switch
+
+
+def test_native_training_loop_equals_python_loop(assets):
+    """trl_train_run (cScenarioTrain::Run behind the C ABI) and the Python ScenarioTrainMACE.Run drive the same sequence of calls:
+    identical weights, counters and env states."""
+    from deepterrainrl_b200.train import ScenarioTrainMACE, TrainSchedule
+    pack = os.path.join(assets, "dog_slopes_mixed.trlpack")
+    mk = lambda: ScenarioTrainMACE(pack, 512, rng_seed=11, iters_per_update=2,
+                                   schedule=TrainSchedule(init_exp_rate=0.5, exp_rate=0.2, init_exp_temp=5, exp_temp=0.025,
+                                                          init_exp_base_rate=0.2, exp_base_rate=0.002, trainer_num_anneal_iters=60,
+                                                          exp_base_anneal_iters=60),
+                                   trainer_params=dict(replay_mem_size=20000, num_init_samples=300, freeze_target_iters=7, seed=2))
+    a, b = mk(), mk()
+    a.Run(50)
+    b.RunNative(50)
+    ca, cb = a.trainer.counters(), b.trainer.counters()
+    assert ca == cb and ca["iter"] > 5
+    np.testing.assert_array_equal(a.trainer.get("theta"), b.trainer.get("theta"))
+    np.testing.assert_array_equal(a.exp.GetStateAll()[0], b.exp.GetStateAll()[0])
