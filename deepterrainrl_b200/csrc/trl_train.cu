@@ -54,7 +54,7 @@ struct Dev {
     float* mem;
     int *flags, *pos_critic, *pos_actor, *critic_list, *actor_list, *actor_batch;
     Counters* c;
-    int *valid, *slot, *ids, *cand;
+    int *valid, *slot, *order, *ids, *cand;
     double *xn, *a0, *a1, *a2, *t, *catb, *h, *hh, *y;           // activations of the most recent forward pass (kB rows)
     double *v0, *v1;
     double *dy, *dhh, *dh, *dt, *da2, *da1, *da0;
@@ -123,6 +123,29 @@ __global__ void k_add_check(Dev d, const double* rows, const int* count_ptr, int
     bad = __syncthreads_or(bad);
     if (threadIdx.x == 0) d.valid[i] = !bad;
 }
+// Canonical arrival order for tuples that come from the scenario's block: its slots are filled through an atomic cursor, so
+// their order is timing dependent; ranking them by env id (an env finishes at most one cycle per outer update) makes the
+// replay memory -- and with it the whole training run -- reproducible.  One block per tuple: rank = #tuples with a smaller key.
+__global__ void k_add_order(Dev d, const int* env_ids, const int* count_ptr) {
+    pdl_sync();
+    const int count = *count_ptr, i = blockIdx.x;
+    if (i >= count) return;
+    const int key = env_ids[i];
+    int r = 0;
+    for (int j = threadIdx.x; j < count; j += blockDim.x) {
+        const int kj = env_ids[j];
+        r += (kj < key) || (kj == key && j < i);
+    }
+    __shared__ int red[32];
+    for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = r;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tot = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += red[w];
+        d.order[tot] = i;
+    }
+}
 __device__ void list_remove(int* list, int* pos, int& count, int t) {
     const int p = pos[t];
     if (p < 0) return;
@@ -132,12 +155,13 @@ __device__ void list_remove(int* list, int* pos, int& count, int t) {
     --count;
 }
 // cNeuralNetTrainer::AddTuple slot assignment + cMACETrainer::UpdateBuffers, in arrival order (one thread: O(1) per tuple)
-__global__ void k_add_assign(Dev d, const uint32_t* src_flags, const int* count_ptr, int count_val, int* reset_count) {
+__global__ void k_add_assign(Dev d, const uint32_t* src_flags, const int* count_ptr, int count_val, int* reset_count, int use_order) {
     pdl_sync();
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     const int count = count_ptr ? *count_ptr : count_val;
     Counters& c = *d.c;
-    for (int i = 0; i < count; ++i) {
+    for (int r = 0; r < count; ++r) {
+        const int i = use_order ? d.order[r] : r;
         if (!d.valid[i]) { d.slot[i] = -1; continue; }
         const int t = c.head;
         d.slot[i] = t;
@@ -700,11 +724,12 @@ int enqueue_train(trl_trainer* t, cudaStream_t st) {
 }
 
 int enqueue_add(trl_trainer* t, const double* rows, const uint32_t* flags, const int* count_ptr, int count_val, int max_count, int* reset,
-                cudaStream_t st) {
+                cudaStream_t st, const int* env_ids = nullptr) {
     const Dev& d = t->d;
     if (max_count <= 0) return 0;
     launch_pdl(k_add_check, dim3(max_count), dim3(128), 0, st, d, rows, count_ptr, count_val);
-    launch_pdl(k_add_assign, dim3(1), dim3(32), 0, st, d, flags, count_ptr, count_val, reset);
+    if (env_ids) { launch_pdl(k_add_order, dim3(max_count), dim3(128), 0, st, d, env_ids, count_ptr); t->launches += 1; }
+    launch_pdl(k_add_assign, dim3(1), dim3(32), 0, st, d, flags, count_ptr, count_val, reset, env_ids ? 1 : 0);
     launch_pdl(k_add_copy, dim3(max_count), dim3(128), 0, st, d, rows, flags);
     t->launches += 3;
     return 0;
@@ -764,7 +789,7 @@ trl_trainer* trl_trainer_create(trl_handle* h, const double* p) {
     A(talloc(t, &d.pos_critic, d.cap)); A(talloc(t, &d.pos_actor, d.cap)); A(talloc(t, &d.critic_list, d.cap)); A(talloc(t, &d.actor_list, d.cap));
     A(talloc(t, &d.actor_batch, 4 * kB)); A(talloc(t, &d.c, 1));
     const int add_cap = std::max(h->B.tuple_cap, 4096);
-    A(talloc(t, &d.valid, add_cap)); A(talloc(t, &d.slot, add_cap)); A(talloc(t, &d.ids, kB)); A(talloc(t, &d.cand, kB));
+    A(talloc(t, &d.valid, add_cap)); A(talloc(t, &d.slot, add_cap)); A(talloc(t, &d.order, add_cap)); A(talloc(t, &d.ids, kB)); A(talloc(t, &d.cand, kB));
     A(talloc(t, &d.xn, (size_t)kB * d.S)); A(talloc(t, &d.a0, (size_t)kB * C0 * W0)); A(talloc(t, &d.a1, (size_t)kB * C1 * W1));
     A(talloc(t, &d.a2, (size_t)kB * C2 * W2)); A(talloc(t, &d.t, (size_t)kB * T)); A(talloc(t, &d.catb, (size_t)kB * d.cat));
     A(talloc(t, &d.h, (size_t)kB * H)); A(talloc(t, &d.hh, (size_t)4 * kB * HH)); A(talloc(t, &d.y, (size_t)kB * d.n_out));
@@ -826,7 +851,7 @@ int trl_trainer_destroy(trl_trainer* t) {
 // cNeuralNetLearner::Train's AddTuples(exp->GetTuples()) + ResetTupleBuffer, device to device
 int trl_trainer_add_from_scene(trl_trainer* t) {
     trl_handle* h = t->h;
-    enqueue_add(t, h->B.tuples, h->B.tuple_flags, h->B.tuple_count, 0, h->B.tuple_cap, h->B.tuple_count, h->stream);
+    enqueue_add(t, h->B.tuples, h->B.tuple_flags, h->B.tuple_count, 0, h->B.tuple_cap, h->B.tuple_count, h->stream, h->B.tuple_env);
     TCK(cudaGetLastError());
     return 0;
 }

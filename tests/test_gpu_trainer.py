@@ -81,11 +81,13 @@ def test_rollout_uses_trainer_weights_and_device_tuples(assets):
     np.testing.assert_array_equal(a.GetStateAll()[0], b.GetStateAll()[0])      # binding alone changes nothing
     nt = b.GetNumTuples()
     assert nt > n
-    src_rows, src_flags, _ = b.GetTuples(f64=True)                             # does not reset the scenario's buffer
+    src_rows, src_flags, src_env = b.GetTuples(f64=True)                       # does not reset the scenario's buffer
+    canon = np.argsort(src_env, kind="stable")                                 # the hand-over ranks the block by env id (reproducible)
+    src_rows, src_flags = src_rows[canon], src_flags[canon]
     tr.AddTuplesFromScene()
     c = tr.counters()
     assert c["num"] == nt and c["critic"] + c["actor"] == nt and c["actor"] > 0
-    got_rows, got_flags = tr.rows(np.arange(nt))                               # replay slots 0..nt-1 in arrival order
+    got_rows, got_flags = tr.rows(np.arange(nt))                               # replay slots 0..nt-1 in canonical arrival order
     np.testing.assert_array_equal(got_rows, src_rows.astype(np.float32))       # SetTuple stores floats
     np.testing.assert_array_equal(got_flags, src_flags.astype(np.int32))
     assert b.GetNumTuples() == 0                                               # ResetTupleBuffer happened on the device
