@@ -123,6 +123,25 @@ void orc_rbd(OrcBatch* b, int env, double* M, double* C) {
     e.ctrl_model.update(pose, e.qd);
     for (int a = 0; a < nd; ++a) { for (int c = 0; c < nd; ++c) M[a * nd + c] = e.ctrl_model.M[a][c]; C[a] = e.ctrl_model.C[a]; }
 }
+// what: 0 gravity force [ndof] (cRBDUtil::CalcGravityForce), 1 Jacobian [6][ndof] (cRBDUtil::BuildJacobian; rows omega xyz, v xyz),
+//       2 world position of every joint origin [nj][3]
+void orc_rbd_extra(OrcBatch* b, int env, int what, double* out) {
+    Env& e = *b->envs[env];
+    const int nd = b->scene.ndof;
+    double pose[kMaxDof];
+    e.build_pose(pose);
+    e.ctrl_model.update(pose, e.qd);
+    if (what == 0) e.ctrl_model.gravity_force(out);
+    else if (what == 1) {
+        for (int k = 0; k < nd; ++k) {
+            const SV& c = e.ctrl_model.J[k];
+            out[0 * nd + k] = c.o.x; out[1 * nd + k] = c.o.y; out[2 * nd + k] = c.o.z;
+            out[3 * nd + k] = c.v.x; out[4 * nd + k] = c.v.y; out[5 * nd + k] = c.v.z;
+        }
+    } else {
+        for (int j = 0; j < b->scene.nj; ++j) { V3 p = e.ctrl_model.joint_world_pos(j); out[3 * j] = p.x; out[3 * j + 1] = p.y; out[3 * j + 2] = p.z; }
+    }
+}
 void orc_forward_dynamics(OrcBatch* b, int env, const double* tau, double dt, double* qdd) {
     b->envs[env]->forward_dynamics(tau, dt, qdd, false);
 }
@@ -259,5 +278,42 @@ void orc_trainer_eval_batch(OrcTrainer* t, int target, const double* X, int B, d
     std::vector<double> y;
     (target ? t->tr.target : t->tr.net).eval_batch(B, X, y);
     std::memcpy(Y, y.data(), y.size() * 8);
+}
+
+// ---------------------------------------------------------------------------------------- generator-level terrain / RNG probes
+// (compared bit for bit with the reference's own cTerrainGen2D / cRand compiled into oracle/_ref, tests/test_ref_pinning_cpu.py)
+int orc_terrain_build(int type, const double* params40, unsigned long seed, double width, float* out, int cap, double* total_w) {
+    Rand r;
+    r.seed(seed);
+    std::vector<float> data;
+    double w = TerrainGen::build(type, width, params40, r, data);
+    if (total_w) *total_w = w;
+    int n = (int)data.size();
+    for (int i = 0; i < n && i < cap; ++i) out[i] = data[i];
+    return n;
+}
+int orc_terrain_build_after_flat(int type, const double* params40, unsigned long seed, double flat_w, double width, float* out, int cap) {
+    Rand r;
+    r.seed(seed);
+    std::vector<float> data;
+    TerrainGen::add_flat(flat_w, data);
+    TerrainGen::build(type, width, params40, r, data);
+    int n = (int)data.size();
+    for (int i = 0; i < n && i < cap; ++i) out[i] = data[i];
+    return n;
+}
+void orc_rand_stream(unsigned long seed, int kind, double a, double b, int n, double* out) {
+    Rand r;
+    r.seed(seed);
+    for (int i = 0; i < n; ++i) {
+        switch (kind) {
+            case 0: out[i] = r.rand_double(); break;
+            case 1: out[i] = r.rand_double(a, b); break;
+            case 2: out[i] = r.rand_int(); break;
+            case 3: out[i] = r.rand_int((int)a, (int)b); break;
+            case 4: out[i] = r.flip_coin() ? 1 : 0; break;
+            default: out[i] = r.rand_sign(); break;
+        }
+    }
 }
 }  // extern "C"

@@ -121,6 +121,14 @@ class Oracle:
         self.L.orc_rbd(self.h, env, _p(M), _p(Cb))
         return M, Cb
 
+    def rbd_extra(self, what, env=0):
+        """what: 'gravity' [ndof], 'jacobian' [6, ndof], 'joint_pos' [nj, 3] of the controller's RBD model at the env's state."""
+        idx = {"gravity": 0, "jacobian": 1, "joint_pos": 2}[what]
+        out = np.zeros({0: self.ndof, 1: 6 * self.ndof, 2: 3 * self.nj}[idx])
+        self.L.orc_rbd_extra.restype = None
+        self.L.orc_rbd_extra(self.h, env, idx, _p(out))
+        return out if idx == 0 else out.reshape((6, self.ndof) if idx == 1 else (self.nj, 3))
+
     def forward_dynamics(self, tau, dt=1.0 / 3000.0, env=0):
         tau = np.ascontiguousarray(tau, dtype=np.float64)
         qdd = np.zeros(self.ndof)

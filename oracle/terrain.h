@@ -4,6 +4,8 @@
 // Uses the *actual* libstdc++ <random> types the reference uses, so the product's hand-written device
 // restatement of minstd_rand0 / generate_canonical / uniform_int_distribution is checked against the real thing.
 //
+// Pinned bit for bit against the reference's own compiled cRand / cTerrainGen2D (oracle/_ref, tests/test_ref_pinning_cpu.py).
+//
 // Follows (file:line under /root/reference):
 //   util/Rand.cpp:6-104             cRand (default_random_engine + std distributions)
 //   sim/TerrainGen2D.cpp:4,185-707  gVertSpacing (a float!), Build*, Add*, Overlay*

@@ -1,0 +1,179 @@
+"""Pins the oracle against the REFERENCE's own code where that code can be compiled.  `make -C oracle ref` builds, unmodified from
+/root/reference and against stand-ins for the absent Eigen / jsoncpp headers (oracle/ref_shim):
+  oracle/_ref/libref_terrain.so  sim/TerrainGen2D.cpp, util/Rand.cpp, util/ArgParser.cpp, util/FileUtil.cpp
+  oracle/_ref/libref_rbd.so      anim/KinTree.cpp, sim/SpAlg.cpp, sim/RBDModel.cpp, sim/RBDUtil.cpp, util/MathUtil.cpp, util/JsonUtil.cpp
+Checked: the cRand streams, all 14 terrain generators, the default parameter table, the type names and the arg-file semantics
+(bit for bit); and, at random poses of the dog, goat and raptor read by the reference's own loaders from the character files,
+the mass matrix, the bias force (with the reference's BuildCjPlanar), the gravity force, the Jacobian, the centre of mass and
+the joint positions of the controller's rigid-body model (oracle/rbd.h).  Skipped where the libraries have not been built."""
+import ctypes as C
+import glob
+import os
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_LIB = os.path.join(HERE, "..", "oracle", "_ref", "libref_terrain.so")
+pytestmark = pytest.mark.skipif(not os.path.exists(REF_LIB), reason="oracle/_ref not built (reference sources absent)")
+
+TYPES = ["flat", "gaps", "steps", "walls", "bumps", "mixed", "narrow_gaps", "slopes", "slopes_gaps", "slopes_walls", "slopes_steps",
+         "slopes_mixed", "slopes_narrow_gaps", "cliffs"]
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+@pytest.fixture(scope="module")
+def libs():
+    from pyoracle import lib
+    ref = C.CDLL(REF_LIB)
+    orc = lib()
+    for L, pre in ((ref, "ref"), (orc, "orc")):
+        f = getattr(L, pre + "_terrain_build")
+        f.argtypes = [C.c_int, C.c_void_p, C.c_ulong, C.c_double, C.c_void_p, C.c_int, C.c_void_p]
+        g = getattr(L, pre + "_terrain_build_after_flat")
+        g.argtypes = [C.c_int, C.c_void_p, C.c_ulong, C.c_double, C.c_double, C.c_void_p, C.c_int]
+        r = getattr(L, pre + "_rand_stream")
+        r.argtypes = [C.c_ulong, C.c_int, C.c_double, C.c_double, C.c_int, C.c_void_p]
+        r.restype = None
+    return ref, orc
+
+
+def _params(ref, rng=None):
+    p = np.zeros(40)
+    ref.ref_terrain_default_params(_p(p))
+    if rng is not None:                                   # perturbed but ordered (min <= max) parameter sets
+        q = p * rng.uniform(0.6, 1.4, 40)
+        for i in range(0, 36, 2):
+            lo, hi = sorted((q[i], q[i + 1]))
+            q[i], q[i + 1] = lo, hi
+        q[28:30] = np.round(np.clip(q[28:30], 1, 4))      # narrow-gap counts
+        q[36] = np.round(q[36])                           # cliff mini count
+        q[38:40] = sorted(q[38:40])
+        p = q
+    return p
+
+
+def test_rand_streams_match_reference(libs):
+    ref, orc = libs
+    for seed in (1, 7, 123456789, 2 ** 31 + 5):
+        for kind, a, b in ((0, 0, 0), (1, -2.5, 7.25), (1, 3.0, 3.0), (2, 0, 0), (3, 0, 10), (3, -4, 9), (3, 5, 5), (4, 0, 0), (5, 0, 0)):
+            x = np.zeros(257); y = np.zeros(257)
+            ref.ref_rand_stream(seed, kind, a, b, 257, _p(x))
+            orc.orc_rand_stream(seed, kind, a, b, 257, _p(y))
+            np.testing.assert_array_equal(x, y)
+
+
+def test_terrain_generators_match_reference_bit_for_bit(libs):
+    ref, orc = libs
+    rng = np.random.default_rng(0)
+    cap = 4096
+    checked = 0
+    for t, name in enumerate(TYPES):
+        assert ref.ref_terrain_parse_type(name.encode()) == t
+        for trial in range(6):
+            p = _params(ref, rng if trial else None)
+            seed = int(rng.integers(1, 2 ** 31))
+            width = float(rng.uniform(3.0, 40.0))
+            a = np.zeros(cap, np.float32); b = np.zeros(cap, np.float32)
+            wa = C.c_double(0); wb = C.c_double(0)
+            na = ref.ref_terrain_build(t, _p(p), seed, width, _p(a), cap, C.byref(wa))
+            nb = orc.orc_terrain_build(t, _p(p), seed, width, _p(b), cap, C.byref(wb))
+            assert na == nb and 0 < na <= cap, (name, trial)
+            assert wa.value == wb.value
+            np.testing.assert_array_equal(a[:na].view(np.uint32), b[:nb].view(np.uint32))
+            flat_w = float(rng.uniform(0.5, 3.0))
+            na = ref.ref_terrain_build_after_flat(t, _p(p), seed, flat_w, width, _p(a), cap)
+            nb = orc.orc_terrain_build_after_flat(t, _p(p), seed, flat_w, width, _p(b), cap)
+            assert na == nb
+            np.testing.assert_array_equal(a[:na].view(np.uint32), b[:nb].view(np.uint32))
+            checked += 2
+    assert checked == 14 * 12
+
+
+def test_default_params_match_the_packs(libs, assets):
+    from pack_scene import read_pack
+    ref, _ = libs
+    p = _params(ref)
+    for pack in glob.glob(os.path.join(assets, "*.trlpack")):
+        np.testing.assert_array_equal(read_pack(pack)["terrain_default_params"], p)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/args"), reason="reference arg files absent")
+def test_arg_file_semantics_match_reference_parser(libs):
+    """cArgParser compiled from the reference vs the product's readers (train.parse_arg_file; tools/pack_scene tokenizer) on every
+    shipped arg file: same token count, same value for every key the product reads."""
+    from deepterrainrl_b200.train import parse_arg_file
+    from pack_scene import tokenize_arg_file
+    ref, _ = libs
+    ref.ref_args_string.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]
+    files = sorted(glob.glob("/root/reference/args/*.txt"))
+    assert len(files) >= 10
+    n_keys = 0
+    for f in files:
+        assert ref.ref_args_count(f.encode()) == len(tokenize_arg_file(f))
+        ours = parse_arg_file(f)
+        for key, val in ours.items():
+            buf = C.create_string_buffer(1024)
+            ok = ref.ref_args_string(f.encode(), key.encode(), buf, 1024)
+            if val == "":
+                assert not ok                                   # a key followed by another key parses as "absent"
+                continue
+            assert ok and buf.value.decode() == val.split()[0], (f, key)
+            n_keys += 1
+            try:
+                x = float(val.split()[0])
+            except ValueError:
+                continue
+            d = C.c_double(0)
+            assert ref.ref_args_double(f.encode(), key.encode(), C.byref(d)) and d.value == x
+    assert n_keys > 150
+
+
+REF_RBD = os.path.join(HERE, "..", "oracle", "_ref", "libref_rbd.so")
+CHARS = {"dog_slopes_mixed": "dog.txt", "goat_cliffs": "goat.txt", "raptor_narrow_gaps": "raptor.txt"}
+
+
+@pytest.mark.skipif(not (os.path.exists(REF_RBD) and os.path.isdir("/root/reference/data/characters")),
+                    reason="oracle/_ref/libref_rbd.so or the reference character files absent")
+@pytest.mark.parametrize("scene", sorted(CHARS))
+def test_rigid_body_model_matches_reference_code(assets, scene):
+    """cRBDModel::Update + cRBDUtil::{BuildMassMat, BuildBiasForce, CalcGravityForce, BuildJacobian, CalcCoM} compiled from the
+    reference vs oracle/rbd.h, the character read by cKinTree::Load / LoadBodyDefs vs the .trlpack the product and the oracle load."""
+    from pyoracle import Oracle
+    ref = C.CDLL(REF_RBD)
+    ref.ref_rbd_create.restype = C.c_void_p
+    ref.ref_rbd_create.argtypes = [C.c_char_p, C.c_double, C.c_double]
+    h = ref.ref_rbd_create(("/root/reference/data/characters/" + CHARS[scene]).encode(), 0.0, -9.8)
+    assert h
+    h = C.c_void_p(h)
+    o = Oracle(os.path.join(assets, scene + ".trlpack"), 1, 0)
+    nd, nj = ref.ref_rbd_num_dof(h), ref.ref_rbd_num_joints(h)
+    assert (nd, nj) == (o.ndof, o.nj)
+    rng = np.random.default_rng(5)
+    worst = 0.0
+    for trial in range(12):
+        q = rng.uniform(-1.2, 1.2, nd); q[0] = rng.uniform(-5, 50); q[1] = rng.uniform(0, 2); q[2] = rng.uniform(-3.1, 3.1)
+        qd = rng.normal(size=nd) * (0 if trial == 0 else 3.0)
+        ref.ref_rbd_update(h, _p(q), _p(qd))
+        o.set_state(0, q, qd)
+        M = np.zeros((nd, nd)); Cb = np.zeros(nd); G = np.zeros(nd); J = np.zeros((6, nd)); com = np.zeros(3); cv = np.zeros(3)
+        ref.ref_rbd_mass_bias(h, _p(M), _p(Cb)); ref.ref_rbd_gravity_force(h, _p(G)); ref.ref_rbd_jacobian(h, _p(J))
+        ref.ref_rbd_com(h, _p(com), _p(cv))
+        Mo, Co = o.rbd(0)
+        pairs = [(M, Mo), (Cb, Co), (G, o.rbd_extra("gravity")), (J, o.rbd_extra("jacobian"))]
+        oc, ov = o.com(0)
+        pairs += [(com[:2], oc), (cv[:2], ov)]
+        jp = np.zeros((nj, 3))
+        for j in range(nj):
+            ref.ref_rbd_joint_world_pos(h, j, _p(jp[j]))
+        pairs.append((jp, o.rbd_extra("joint_pos")))
+        for a, b in pairs:
+            err = np.max(np.abs(a - b)) / max(1.0, np.max(np.abs(a)))
+            worst = max(worst, err)
+            assert err < 1e-12, (scene, trial, err)
+        assert np.allclose(M, M.T, atol=1e-12) and np.all(np.linalg.eigvalsh(M) > 0)
+    ref.ref_rbd_destroy(h)
+    print(f"{scene}: worst relative difference vs the compiled reference {worst:.2e}")
