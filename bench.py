@@ -25,6 +25,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 PACK = os.path.join(ROOT, "assets", "dog_slopes_mixed.trlpack")
+WORKLOAD = "dog/slopes_mixed MACE poli_eval (BASELINE configs[1])"
+WORKLOADS = {"dog_slopes_mixed": WORKLOAD, "raptor_narrow_gaps": "raptor/narrow_gaps MACE poli_eval (BASELINE configs[2])",
+             "goat_cliffs": "goat/cliffs MACE poli_eval (BASELINE configs[4] per-GPU share)", "dog_flat": "dog/flat fixed gait (BASELINE configs[0])"}
 ENV_STEPS_PER_UPDATE = 20
 DT = 1.0 / 30.0
 # per env-step the persistent state must be read and written once (q, qd, held torque, 64-scalar
@@ -149,7 +152,7 @@ def run_reference_arm(args, rank):
         "impl": "reference", "metric": "env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step_s * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "dog/slopes_mixed MACE poli_eval (BASELINE configs[1])", "envs_per_gpu": args.envs},
+        "config": {"workload": WORKLOAD, "envs_per_gpu": args.envs},
         "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port",
                          "sample": f"{envs} envs x {args.steps} outer updates of 20 env-steps, thread-per-env-slice on {cores} threads; "
                                    "restated CPU oracle (reduced-coordinate physics), not Bullet"},
@@ -165,11 +168,16 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--envs", type=int, default=4096, help="environments per GPU")
     ap.add_argument("--impl", default="b200")
+    ap.add_argument("--scene", default="dog_slopes_mixed", choices=sorted(WORKLOADS),
+                    help="asset pack; the default is the configuration the metric is quoted on, the others are side measurements")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--presim", type=float, default=4.0,
                     help="seconds of simulated time run (untimed) before warm-up so gait cycles / episodes of the envs "
                          "are desynchronised like in a long evaluation (SURVEY §8d: warm-up 2 s sim)")
     args = ap.parse_args()
+    global PACK, WORKLOAD
+    PACK = os.path.join(ROOT, "assets", args.scene + ".trlpack")
+    WORKLOAD = WORKLOADS[args.scene]
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -268,7 +276,7 @@ def main():
         "metric": "env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "dog/slopes_mixed MACE poli_eval (BASELINE configs[1])", "envs_per_gpu": n,
+        "config": {"workload": WORKLOAD, "envs_per_gpu": n,
                    "env_steps_per_step": ENV_STEPS_PER_UPDATE * n, "sim_substeps": 5, "parallelism": f"env-shard x{world}",
                    "l2": "flushed between steps (256 MiB memset on the engine stream)",
                    "timing": "cudaEvent on the engine stream around K graph-launched updates",
