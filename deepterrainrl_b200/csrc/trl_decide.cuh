@@ -1,8 +1,8 @@
 // deepterrainrl_b200 -- policy decision kernel (included by trl_step.cu; same translation unit so the action
 // bookkeeping device functions are shared).
 //
-// One 8-CTA thread-block CLUSTER per environment that reached a gait-cycle boundary in the preceding step kernel (a
-// persistent grid of clusters walks the pending list); layers are split over the 8 SMs of the cluster and activations
+// One thread-block CLUSTER (kClusterSize CTAs, 4 by default) per environment that reached a gait-cycle boundary in the preceding
+// step kernel (a persistent grid of clusters walks the pending list); layers are split over the SMs of the cluster and activations
 // are exchanged through distributed shared memory.  Thread 0 of rank 0 runs the scalar decision logic of cDogControllerMACE::UpdateAction /
 // cBaseControllerMACE::DecideActionBoltzmann (sim/DogController.cpp:847-868, sim/BaseControllerMACE.cpp:254-318,
 // 339-396, 437-518); all 8 x 512 threads evaluate the MACE network (data/policies/dog/nets/dog_mace3_deploy.prototxt:
@@ -53,7 +53,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 
 // MACE forward pass of ONE decision spread over a thread-block cluster: every CTA owns 1/8 of the output channels /
 // rows of each layer and exchanges activations through distributed shared memory.  The pass is latency-bound (one
-// decision, ~3.5 MFLOP over 8 SMs), so every weight read is either staged in shared memory up front or issued as a
+// decision, ~3.5 MFLOP over the cluster's SMs), so every weight read is either staged in shared memory up front or issued as a
 // batch of independent loads before the first use.  Result (n_out values) lands in rank 0's Y.
 __device__ void net_forward_cluster(cg::cluster_group& cluster, const NetWeights& W, const double* __restrict__ x_in, double* sh,
                                     int n_char, int n_frags, int frag) {
