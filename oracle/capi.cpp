@@ -97,6 +97,11 @@ int orc_get_ctrl(OrcBatch* b, int env, double* out) {
     out[k++] = e.exp_critic; out[k++] = e.exp_actor; out[k++] = e.cycle_count; out[k++] = e.stance;
     return k;
 }
+// cSimCharacter::HasFallen / HasStumbled as the controller sees them, and the number of policy decisions taken so far
+void orc_flags(OrcBatch* b, int env, int* out3) {
+    Env& e = *b->envs[env];
+    out3[0] = e.has_fallen() ? 1 : 0; out3[1] = e.has_stumbled() ? 1 : 0; out3[2] = (int)e.cycle_count;
+}
 void orc_get_last_tau(OrcBatch* b, int env, double* tau) { std::memcpy(tau, b->envs[env]->last_tau, 8 * b->scene.ndof); }
 void orc_get_poli_state(OrcBatch* b, int env, double* s) {
     Env& e = *b->envs[env];

@@ -19,6 +19,10 @@
 //   sim/DogControllerMACE.cpp:16-91, sim/GoatControllerMACE.cpp:11-14
 //   sim/ImpPDController.cpp:234-310, sim/PDController.cpp:181-208    stable-PD torques
 //
+// The controller part is PINNED against the reference's own compiled controller sources (oracle/_ref/libref_ctrl.so,
+// tests/test_ref_pinning_cpu.py): same joint torques, gait-machine state and policy state vectors over 1200-1800 env-steps for the
+// dog (fixed gait and MACE), the goat and the raptor.  The scenario bookkeeping stays an unpinned restatement.
+//
 // PHYSICS IS NOT A RESTATEMENT.  The reference steps Bullet (btDiscreteDynamicsWorld, maximal coordinates, an
 // un-vendored dependency of unpinned version: premake4.lua:142-195, sim/World.cpp:61-105), which cannot be built
 // or restated here.  `physics_substep` below is this project's own reduced-coordinate planar model:

@@ -91,6 +91,13 @@ class Oracle:
         n = self.L.orc_get_ctrl(self.h, env, _p(out))
         return out[:n]
 
+    def flags(self, env=0):
+        """(has_fallen, has_stumbled, cycle_count)"""
+        out = np.zeros(3, np.int32)
+        self.L.orc_flags.restype = None
+        self.L.orc_flags(self.h, env, _p(out))
+        return out.tolist()
+
     def last_tau(self, env=0):
         t = np.zeros(self.ndof)
         self.L.orc_get_last_tau(self.h, env, _p(t))

@@ -1,0 +1,297 @@
+// TEST INFRASTRUCTURE ONLY -- the REFERENCE's own controller stack (sim/Controller.cpp, CharController.cpp, NNController.cpp,
+// TerrainRLCharController.cpp, DogController.cpp, DogControllerCacla.cpp, BaseControllerCacla.cpp, BaseControllerMACE.cpp,
+// DogControllerMACE.cpp, ImpPDController.cpp, PDController.cpp, anim/Character.cpp + the rigid-body sources of libref_rbd) compiled
+// where it lies under /root/reference into oracle/_ref/libref_ctrl.so, against header stand-ins for Eigen / jsoncpp / Bullet / Caffe
+// (oracle/ref_shim).  What those sources need from the simulation -- pose, velocity, contacts, body-part positions, ground heights,
+// network output -- they obtain through virtual calls on cSimCharacter / cSimObj / cJoint / cGround and through cNeuralNet; this
+// file supplies that back end from a state the test installs (the CPU oracle's state), using the reference's own cKinTree
+// kinematics for positions and velocities.  The torques the reference controller hands to cSimCharacter::ApplyControlForces and its
+// gait-machine state are what tests/test_ref_pinning_cpu.py compares with oracle/env.h.
+//
+// Every other virtual function of the Bullet-backed classes is resolved to ref_abort_stub by the link recipe (oracle/Makefile):
+// if the compiled reference code ever reached one, the test would abort instead of silently using made-up behaviour.
+#include <execinfo.h>
+#include <signal.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "learning/MACETrainer.h"
+#include "learning/NeuralNet.h"
+#include "sim/DogController.h"
+#include "sim/DogControllerQ.h"
+#include "sim/DogControllerMACE.h"
+#include "sim/GoatControllerMACE.h"
+#include "sim/RaptorControllerMACE.h"
+#include "sim/RaptorControllerQ.h"
+#include "sim/Ground.h"
+#include "sim/SimCharacter.h"
+
+extern "C" void ref_abort_stub() {
+    std::fprintf(stderr, "oracle/_ref: the compiled reference code called a Bullet/Caffe-backed function that has no stand-in\n");
+    void* frames[16];
+    backtrace_symbols_fd(frames, backtrace(frames, 16), 2);
+    std::abort();
+}
+
+static void ref_segv_handler(int) {
+    void* frames[24];
+    backtrace_symbols_fd(frames, backtrace(frames, 24), 2);
+    _exit(139);
+}
+#include <unistd.h>
+
+// ------------------------------------------------------------------------------------------------ state installed by the test
+struct FakeChar;
+typedef double (*height_fn)(double x, void* user);
+
+struct FakePart : public cSimObj {
+    FakeChar* owner = nullptr;
+    int id = 0;
+    bool contact = false;
+    tVector GetPos() const override;
+    tVector GetLinearVelocity() const override;
+    tVector LocalToWorldPos(const tVector& local_pos) const override;
+    bool IsInContact() const override { return contact; }
+};
+
+struct FakeJoint : public cJoint {
+    FakeChar* owner = nullptr;
+    int id = 0;
+    bool valid = true;
+    tVector axis_rel = tVector(0, 0, 1, 0);
+    tVector torque = tVector(0, 0, 0, 0);
+    double torque_lim = 1e30;
+    bool IsValid() const override { return valid; }
+    const tVector& GetAxisRel() const override { return axis_rel; }
+    tVector CalcAxisWorld() const override { return axis_rel; }                       // planar character: every hinge is about z
+    void CalcRotation(tVector& out_axis, double& out_theta) const override;           // joint angle
+    void GetChildRotation(tVector& out_axis, double& out_theta) const override;       // world rotation of the child link
+    tVector CalcJointVelRel() const override;                                         // relative angular velocity in the joint frame
+    void AddTorque(const tVector& t) override { torque += t; }
+    void SetTorqueLimit(double lim) override { torque_lim = lim; }
+};
+
+struct FakeChar : public cSimCharacter {
+    Eigen::VectorXd pose, vel, last_tau;
+    std::vector<std::shared_ptr<cSimObj>> parts;
+    std::vector<FakeJoint> joints;
+    tVector com = tVector(0, 0, 0, 0), com_vel = tVector(0, 0, 0, 0);
+    bool fallen = false, stumbled = false;
+    int n_apply = 0;
+
+    bool Load(const std::string& char_file) {
+        if (!cCharacter::Init(char_file)) return false;                // skeleton via the reference's own loader
+        if (!cKinTree::LoadBodyDefs(char_file, mBodyDefs)) return false;
+        const int nj = GetNumJoints();
+        joints.resize(nj);
+        for (int j = 0; j < nj; ++j) {
+            auto p = std::make_shared<FakePart>();
+            p->owner = this; p->id = j;
+            parts.push_back(p);
+            joints[j].owner = this; joints[j].id = j;
+            joints[j].valid = cKinTree::HasParent(mJointMat, j);       // the root has no actuated joint
+        }
+        pose = Eigen::VectorXd::Zero(GetNumDof());
+        vel = Eigen::VectorXd::Zero(GetNumDof());
+        last_tau = Eigen::VectorXd::Zero(GetNumDof());
+        return true;
+    }
+    void Clear() override { cCharacter::Clear(); }
+    void Reset() override { cCharacter::Reset(); }
+    void Update(double) override {}
+    void BuildPose(Eigen::VectorXd& out) const override { out = pose; }
+    void BuildVel(Eigen::VectorXd& out) const override { out = vel; }
+    tVector GetRootPos() const override { return cKinTree::GetRootPos(mJointMat, pose); }
+    // root orientation / angular rate as the reference extracts them from the root body (sim/SimCharacter.cpp:118-128,181-225):
+    // the planar root joint's angle and rate
+    void GetRootRotation(tVector& out_axis, double& out_theta) const override {
+        out_axis = tVector(0, 0, 1, 0);
+        out_theta = cKinTree::GetRootTheta(mJointMat, pose);
+    }
+    tVector GetRootAngVel() const override { return tVector(0, 0, vel[2], 0); }
+    tVector GetRootVel() const override { return tVector(vel[0], vel[1], 0, 0); }
+    const Eigen::MatrixXd& GetBodyDefs() const override { return mBodyDefs; }
+    int GetNumBodyParts() const override { return (int)parts.size(); }
+    tVector CalcCOM() const override { return com; }
+    tVector CalcCOMVel() const override { return com_vel; }
+    const cJoint& GetJoint(int j) const override { return joints[j]; }
+    cJoint& GetJoint(int j) override { return joints[j]; }
+    const std::shared_ptr<cSimObj>& GetBodyPart(int i) const override { return parts[i]; }
+    std::shared_ptr<cSimObj>& GetBodyPart(int i) override { return parts[i]; }
+    bool HasFallen() const override { return fallen; }
+    bool HasStumbled() const override { return stumbled; }
+    bool IsValidBodyPart(int idx) const override { return cKinTree::IsValidBody(mBodyDefs, idx); }
+    void ApplyControlForces(const Eigen::VectorXd& tau) override { last_tau = tau; ++n_apply; }
+};
+
+tVector FakePart::GetPos() const { return cKinTree::CalcBodyPartPos(owner->GetJointMat(), owner->pose, owner->GetBodyDefs(), id); }
+tVector FakePart::GetLinearVelocity() const {
+    const tVector attach = cKinTree::GetBodyAttachPt(owner->GetBodyDefs(), id);
+    return cKinTree::CalcWorldVel(owner->GetJointMat(), owner->pose, owner->vel, id, attach);
+}
+tVector FakePart::LocalToWorldPos(const tVector& local_pos) const {
+    tMatrix m = cKinTree::BodyWorldTrans(owner->GetJointMat(), owner->pose, owner->GetBodyDefs(), id);
+    tVector p = local_pos;
+    p[3] = 1;
+    tVector w = m * p;
+    w[3] = 0;
+    return w;
+}
+void FakeJoint::CalcRotation(tVector& out_axis, double& out_theta) const {
+    out_axis = axis_rel;
+    out_theta = cKinTree::GetJointTheta(owner->GetJointMat(), owner->pose, id);
+}
+void FakeJoint::GetChildRotation(tVector& out_axis, double& out_theta) const {
+    cKinTree::CalcJointWorldTheta(owner->GetJointMat(), owner->pose, id, out_axis, out_theta);
+}
+tVector FakeJoint::CalcJointVelRel() const {
+    const int o = cKinTree::GetParamOffset(owner->GetJointMat(), id);
+    return axis_rel * owner->vel[o];
+}
+
+struct FakeGround : public cGround {
+    height_fn fn = nullptr;
+    void* user = nullptr;
+    double SampleHeight(const tVector& pos) const override { return fn ? fn(pos[0], user) : 0.0; }
+    double SampleHeight(const tVector& pos, bool& out_valid) const override { out_valid = true; return SampleHeight(pos); }
+};
+
+// ---- trivial value types of the Bullet-backed classes (members of cSimObj / cJoint, so their constructors run)
+cContactManager::tContactHandle::tContactHandle() : mID(-1), mFlags(-1), mFilterFlags(-1) {}
+cWorld::tConstraintHandle::tConstraintHandle() : mCons(nullptr) {}
+cWorld::tJointParams::tJointParams() {}
+
+// ---- the Bullet-backed base classes: constructors / destructors only (their vtables land here; see the header comment)
+cSimObj::cSimObj() {}
+cSimObj::~cSimObj() {}
+cJoint::cJoint() {}
+cJoint::~cJoint() {}
+cSimCharacter::cSimCharacter() {}
+cSimCharacter::~cSimCharacter() {}
+cGround::cGround() {}
+cGround::~cGround() {}
+
+// ---- cNeuralNet: what the controllers ask of it; Eval returns the output vector the test installed for the current decision
+static Eigen::VectorXd g_net_output;
+static int g_net_in = 0, g_net_out = 0;
+static Eigen::VectorXd g_out_scale;
+cNeuralNet::cNeuralNet() {}
+cNeuralNet::~cNeuralNet() {}
+void cNeuralNet::Clear() {}
+void cNeuralNet::LoadNet(const std::string&) {}
+void cNeuralNet::LoadModel(const std::string&) {}
+void cNeuralNet::LoadScale(const std::string&) {}
+void cNeuralNet::OutputModel(const std::string&) const {}
+void cNeuralNet::CopyModel(const cNeuralNet&) {}
+bool cNeuralNet::HasNet() const { return g_net_out > 0; }
+bool cNeuralNet::HasLayer(const std::string) const { return false; }
+int cNeuralNet::GetInputSize() const { return g_net_in; }
+int cNeuralNet::GetOutputSize() const { return g_net_out; }
+const Eigen::VectorXd& cNeuralNet::GetOutputScale() const { return g_out_scale; }
+void cNeuralNet::Eval(const Eigen::VectorXd&, Eigen::VectorXd& out_y) const { out_y = g_net_output; }
+void cNeuralNet::ForwardInjectNoisePrefilled(double, double, const std::string&, Eigen::VectorXd&) const { ref_abort_stub(); }
+
+// ---- the index helpers of cMACETrainer the MACE controller uses (learning/MACETrainer.cpp:9-66; the trainer itself needs Caffe)
+int cMACETrainer::GetMaxFragIdx(const Eigen::VectorXd& params, int num_frags) {
+    int a = 0;
+    for (int i = 1; i < num_frags; ++i) if (params[i] > params[a]) a = i;
+    return a;
+}
+double cMACETrainer::GetMaxFragVal(const Eigen::VectorXd& params, int num_frags) { return params[GetMaxFragIdx(params, num_frags)]; }
+void cMACETrainer::GetFrag(const Eigen::VectorXd& params, int num_frags, int frag_size, int a_idx, Eigen::VectorXd& out) {
+    out = params.segment(num_frags + a_idx * frag_size, frag_size);
+}
+void cMACETrainer::SetFrag(const Eigen::VectorXd& frag, int a_idx, int num_frags, int frag_size, Eigen::VectorXd& out) {
+    out.segment(num_frags + a_idx * frag_size, frag_size) = frag;
+}
+double cMACETrainer::GetVal(const Eigen::VectorXd& params, int a_idx) { return params[a_idx]; }
+void cMACETrainer::SetVal(double val, int a_idx, Eigen::VectorXd& out) { out[a_idx] = val; }
+int cMACETrainer::CalcNumFrags(int param_size, int frag_size) { return param_size / (frag_size + 1); }
+void cMACETrainer::SetActionFragIdx(int a_idx, Eigen::VectorXd& out) { out[0] = a_idx; }
+void cMACETrainer::SetActionFrag(const Eigen::VectorXd& frag, Eigen::VectorXd& out) { out.segment(1, out.size() - 1) = frag; }
+
+// ------------------------------------------------------------------------------------------------ C entry points
+struct RefCtrl {
+    FakeChar ch;
+    std::shared_ptr<FakeGround> ground;
+    std::shared_ptr<cTerrainRLCharController> ctrl;
+};
+
+extern "C" {
+
+// kind 0: cDogControllerQ (what -char_ctrl dog builds: fixed gait / commanded actions), 1: cDogControllerMACE, 2: cGoatControllerMACE,
+//      3: cRaptorControllerQ, 4: cRaptorControllerMACE
+RefCtrl* ref_ctrl_create(const char* char_file, int kind, double gx, double gy, height_fn fn, void* user) {
+    if (std::getenv("REF_CTRL_DEBUG")) signal(SIGSEGV, ref_segv_handler);
+    RefCtrl* r = new RefCtrl();
+    if (!r->ch.Load(char_file)) { delete r; return nullptr; }
+    r->ground = std::make_shared<FakeGround>();
+    r->ground->fn = fn; r->ground->user = user;
+    const tVector g(gx, gy, 0, 0);
+    if (kind <= 2) {
+        std::shared_ptr<cDogController> c;
+        if (kind == 0) c = std::make_shared<cDogControllerQ>();
+        else if (kind == 1) c = std::make_shared<cDogControllerMACE>();
+        else c = std::make_shared<cGoatControllerMACE>();
+        c->SetGround(r->ground);
+        c->Init(&r->ch, g, char_file);
+        r->ctrl = c;
+    } else {
+        std::shared_ptr<cRaptorController> c;
+        if (kind == 3) c = std::make_shared<cRaptorControllerQ>();
+        else c = std::make_shared<cRaptorControllerMACE>();
+        c->SetGround(r->ground);
+        c->Init(&r->ch, g, char_file);
+        r->ctrl = c;
+    }
+    return r;
+}
+void ref_ctrl_destroy(RefCtrl* r) { delete r; }
+int ref_ctrl_valid(RefCtrl* r) { return r->ctrl->IsValid() ? 1 : 0; }
+int ref_ctrl_num_dof(RefCtrl* r) { return r->ch.GetNumDof(); }
+int ref_ctrl_num_joints(RefCtrl* r) { return r->ch.GetNumJoints(); }
+void ref_ctrl_set_state(RefCtrl* r, const double* pose, const double* vel, const unsigned char* contact, const double* com,
+                        const double* com_vel, int fallen, int stumbled) {
+    const int nd = r->ch.GetNumDof(), nj = r->ch.GetNumJoints();
+    for (int i = 0; i < nd; ++i) { r->ch.pose[i] = pose[i]; r->ch.vel[i] = vel[i]; }
+    for (int j = 0; j < nj; ++j) static_cast<FakePart*>(r->ch.parts[j].get())->contact = contact[j] != 0;
+    r->ch.com = tVector(com[0], com[1], 0, 0);
+    r->ch.com_vel = tVector(com_vel[0], com_vel[1], 0, 0);
+    r->ch.fallen = fallen != 0; r->ch.stumbled = stumbled != 0;
+}
+void ref_ctrl_reset(RefCtrl* r) { r->ctrl->Reset(); }
+void ref_ctrl_update(RefCtrl* r, double h) { r->ctrl->Update(h); }
+void ref_ctrl_get_tau(RefCtrl* r, double* out) { for (int i = 0; i < r->ch.GetNumDof(); ++i) out[i] = r->ch.last_tau[i]; }
+// state, phase, action id, then the full parameter vector of the current action
+int ref_ctrl_get_fsm(RefCtrl* r, double* out, int cap) {
+    int k = 0;
+    out[k++] = r->ctrl->GetState();
+    out[k++] = r->ctrl->GetPhase();
+    out[k++] = r->ctrl->GetCurrActionID();
+    Eigen::VectorXd p;
+    r->ctrl->BuildOptParams(p);
+    for (int i = 0; i < p.size() && k < cap; ++i) out[k++] = p[i];
+    return k;
+}
+int ref_ctrl_num_actions(RefCtrl* r) { return r->ctrl->GetNumActions(); }
+int ref_ctrl_poli_state(RefCtrl* r, double* out, int cap) {
+    Eigen::VectorXd s;
+    r->ctrl->RecordPoliState(s);
+    for (int i = 0; i < s.size() && i < cap; ++i) out[i] = s[i];
+    return s.size();
+}
+// cNNController::LoadNet on the stand-in net (sizes installed with ref_ctrl_set_net_output first): runs the reference's own size
+// checks and cBaseControllerMACE::UpdateFragParams (number of actor-critic pairs, fragment size)
+int ref_ctrl_load_net(RefCtrl* r) { return r->ctrl->LoadNet("stand-in") ? 1 : 0; }
+void ref_ctrl_set_net_output(int n_in, const double* y, const double* out_scale, int n_out) {
+    g_net_in = n_in; g_net_out = n_out;
+    g_net_output.resize(n_out); g_out_scale.resize(n_out);
+    for (int i = 0; i < n_out; ++i) { g_net_output[i] = y[i]; g_out_scale[i] = out_scale[i]; }
+}
+
+}  // extern "C"

@@ -177,3 +177,86 @@ def test_rigid_body_model_matches_reference_code(assets, scene):
         assert np.allclose(M, M.T, atol=1e-12) and np.all(np.linalg.eigvalsh(M) > 0)
     ref.ref_rbd_destroy(h)
     print(f"{scene}: worst relative difference vs the compiled reference {worst:.2e}")
+
+
+REF_CTRL = os.path.join(HERE, "..", "oracle", "_ref", "libref_ctrl.so")
+# scene -> (character file, controller kind: 0 cDogControllerQ (fixed gait), 1 cDogControllerMACE, 2 cGoatControllerMACE,
+#           4 cRaptorControllerMACE, env-steps)
+CTRL_CASES = {"dog_flat": ("dog.txt", 0, 1200), "dog_slopes_mixed": ("dog.txt", 1, 1500), "goat_cliffs": ("goat.txt", 2, 1800),
+              "raptor_narrow_gaps": ("raptor.txt", 4, 1500)}
+
+
+@pytest.mark.skipif(not (os.path.exists(REF_CTRL) and os.path.isdir("/root/reference/data/characters")),
+                    reason="oracle/_ref/libref_ctrl.so or the reference data files absent")
+@pytest.mark.parametrize("scene", sorted(CTRL_CASES))
+def test_controller_matches_reference_code(assets, scene):
+    """The reference's OWN controller stack (DogController / DogControllerQ / DogControllerMACE / BaseControllerMACE /
+    TerrainRLCharController / NNController / ImpPDController / PDController + KinTree / RBDUtil, compiled unmodified into
+    oracle/_ref/libref_ctrl.so) is driven, env-step by env-step, with the oracle's state (pose, velocity, contacts, COM, terrain
+    heights, and -- at policy decisions -- the oracle's network output), on a character back end that answers cSimCharacter's
+    virtual calls with the reference's own cKinTree kinematics.  Compared every step: the joint torques handed to
+    ApplyControlForces vs the oracle's controller torques, the gait-machine state / phase / action id, the action parameters,
+    and at every decision the policy state vector (terrain samples + character features) the reference built."""
+    from pyoracle import Oracle
+    char_file, kind, n_steps = CTRL_CASES[scene]
+    ref = C.CDLL(REF_CTRL)
+    HFN = C.CFUNCTYPE(C.c_double, C.c_double, C.c_void_p)
+    o = Oracle(os.path.join(assets, scene + ".trlpack"), 1, 0)
+    o.L.orc_sample_height.restype = C.c_double
+    o.L.orc_sample_height.argtypes = [C.c_void_p, C.c_int, C.c_double]
+    cb = HFN(lambda x, u: o.L.orc_sample_height(o.h, 0, x))
+    ref.ref_ctrl_create.restype = C.c_void_p
+    ref.ref_ctrl_create.argtypes = [C.c_char_p, C.c_int, C.c_double, C.c_double, HFN, C.c_void_p]
+    cwd = os.getcwd()
+    os.chdir("/root/reference")                       # the controller files are named relative to the reference's root
+    try:
+        h = ref.ref_ctrl_create(("data/characters/" + char_file).encode(), kind, 0.0, -9.8, cb, None)
+    finally:
+        os.chdir(cwd)
+    assert h
+    h = C.c_void_p(h)
+    assert ref.ref_ctrl_valid(h) == 1
+    if kind >= 1:
+        n_out = 3 * (1 + (o.A - 1))
+        ref.ref_ctrl_set_net_output(o.S, _p(np.zeros(n_out)), _p(np.ones(n_out)), n_out)
+        assert ref.ref_ctrl_load_net(h) == 1           # the reference's own size checks: 283 inputs, 90 outputs for the dog
+    nd = ref.ref_ctrl_num_dof(h)
+    assert nd == o.ndof
+    H = 1.0 / 600.0
+    worst_tau = worst_state = 0.0
+    decisions = 0
+    last_cycles = o.flags(0)[2]
+    out_scale = np.ones(o.n_out if hasattr(o, "n_out") else 90)
+    for k in range(n_steps):
+        o.env_step(0, H)
+        q, qd, _, contact = o.get_state(0)
+        com, cv = o.com(0)
+        fallen, stumbled, cycles = o.flags(0)
+        if kind >= 1:
+            y = o.net_out(0, 90)
+            ref.ref_ctrl_set_net_output(o.S, _p(y), _p(out_scale), 90)
+        ref.ref_ctrl_set_state(h, _p(q), _p(qd), _p(contact.astype(np.uint8)), _p(com), _p(cv), int(fallen), int(stumbled))
+        ref.ref_ctrl_update(h, C.c_double(H))
+        tr = np.zeros(nd)
+        ref.ref_ctrl_get_tau(h, _p(tr))
+        to = o.last_tau(0)
+        err = np.max(np.abs(tr - to)) / max(1.0, np.max(np.abs(to)))
+        worst_tau = max(worst_tau, err)
+        assert err < 1e-9, (scene, k, err)
+        f = np.zeros(64)
+        n = ref.ref_ctrl_get_fsm(h, _p(f), 64)
+        oc = o.get_ctrl(0)
+        assert int(f[0]) == int(oc[0]) and abs(f[1] - oc[1]) < 1e-12, (scene, k, f[:3], oc[:3])     # gait state, phase
+        if cycles != last_cycles:
+            decisions += 1
+            last_cycles = cycles
+            if kind >= 1:
+                s_ref = np.zeros(o.S)
+                assert ref.ref_ctrl_poli_state(h, _p(s_ref), o.S) == o.S
+                es = np.max(np.abs(s_ref - o.poli_state(0)))
+                worst_state = max(worst_state, es)
+                assert es < 1e-9, (scene, k, es)
+    ref.ref_ctrl_destroy(h)
+    assert decisions >= 3
+    print(f"{scene}: {n_steps} env-steps, {decisions} cycles; worst torque difference {worst_tau:.2e} (relative), "
+          f"worst policy-state difference {worst_state:.2e}")
