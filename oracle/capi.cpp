@@ -102,6 +102,14 @@ void orc_flags(OrcBatch* b, int env, int* out3) {
     Env& e = *b->envs[env];
     out3[0] = e.has_fallen() ? 1 : 0; out3[1] = e.has_stumbled() ? 1 : 0; out3[2] = (int)e.cycle_count;
 }
+// the soft-fall bookkeeping alone (no physics, no controller): reset as at an episode start, then one check per call
+void orc_fall_reset(OrcBatch* b, int env) {
+    Env& e = *b->envs[env];
+    e.fall_dist_counter = 5; e.prev_check_pos[0] = e.q[0]; e.prev_check_pos[1] = e.q[1]; e.fail_fall_dist = false;
+    e.fall_contact_counter = 0.1; e.sum_fall_contact = 0;
+}
+void orc_fall_update(OrcBatch* b, int env, double h) { b->envs[env]->update_fall_checks(h); }
+double orc_calc_reward(OrcBatch* b, int env) { return b->envs[env]->calc_reward(); }
 void orc_get_last_tau(OrcBatch* b, int env, double* tau) { std::memcpy(tau, b->envs[env]->last_tau, 8 * b->scene.ndof); }
 void orc_get_poli_state(OrcBatch* b, int env, double* s) {
     Env& e = *b->envs[env];

@@ -728,6 +728,24 @@ struct Env {
     }
 
     // cDogController::CalcReward (sim/DogController.cpp:594-623)
+    // cSimCharSoftFall::UpdateFallDistCheck / UpdateFallContactCheck (sim/SimCharSoftFall.cpp:74-125)
+    void update_fall_checks(double h) {
+        fall_dist_counter -= h;
+        if (fall_dist_counter <= 0) {
+            double dx = q[0] - prev_check_pos[0], dy = q[1] - prev_check_pos[1];
+            if (dx * dx + dy * dy < 0.5 * 0.5) fail_fall_dist = true;
+            prev_check_pos[0] = q[0]; prev_check_pos[1] = q[1];
+            fall_dist_counter = 5;
+        }
+        fall_contact_counter -= h;
+        if (fall_contact_counter <= 0) {
+            bool hc = (contact_mask() & sc->fall_mask) != 0;
+            const double norm = (1 + 1 / (1 - 0.9));
+            sum_fall_contact = (hc ? 1.0 : 0.0) / norm + 0.9 * sum_fall_contact;
+            fall_contact_counter = 0.1;
+        }
+    }
+
     double calc_reward() const {
         double vel_r = 0, stum_r = 0;
         if (!has_fallen()) {
@@ -938,20 +956,7 @@ struct Env {
             if (std::abs(t) > lim) t *= lim / std::abs(t);
             tau_held[o] = t;
         }
-        fall_dist_counter -= h;                                               // UpdateFallDistCheck
-        if (fall_dist_counter <= 0) {
-            double dx = q[0] - prev_check_pos[0], dy = q[1] - prev_check_pos[1];
-            if (dx * dx + dy * dy < 0.5 * 0.5) fail_fall_dist = true;
-            prev_check_pos[0] = q[0]; prev_check_pos[1] = q[1];
-            fall_dist_counter = 5;
-        }
-        fall_contact_counter -= h;                                            // UpdateFallContactCheck
-        if (fall_contact_counter <= 0) {
-            bool hc = (contact_mask() & sc->fall_mask) != 0;
-            const double norm = (1 + 1 / (1 - 0.9));
-            sum_fall_contact = (hc ? 1.0 : 0.0) / norm + 0.9 * sum_fall_contact;
-            fall_contact_counter = 0.1;
-        }
+        update_fall_checks(h);
         if (is_new_cycle()) {                                                 // PostSubstepUpdate
             if (exp_mode) exp_new_cycle_update();
             else ++cycle_count;

@@ -98,6 +98,10 @@ class Oracle:
         self.L.orc_flags(self.h, env, _p(out))
         return out.tolist()
 
+    def calc_reward(self, env=0):
+        self.L.orc_calc_reward.restype = C.c_double
+        return self.L.orc_calc_reward(self.h, env)
+
     def last_tau(self, env=0):
         t = np.zeros(self.ndof)
         self.L.orc_get_last_tau(self.h, env, _p(t))

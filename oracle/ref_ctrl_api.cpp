@@ -30,6 +30,8 @@
 #include "sim/RaptorControllerQ.h"
 #include "sim/Ground.h"
 #include "sim/SimCharacter.h"
+#include "sim/SimDog.h"
+#include "sim/SimRaptor.h"
 
 extern "C" void ref_abort_stub() {
     std::fprintf(stderr, "oracle/_ref: the compiled reference code called a Bullet/Caffe-backed function that has no stand-in\n");
@@ -76,46 +78,59 @@ struct FakeJoint : public cJoint {
     void SetTorqueLimit(double lim) override { torque_lim = lim; }
 };
 
-struct FakeChar : public cSimCharacter {
+// the state the test installs + the answers to the character's virtual calls; Base is the reference's own character class
+// (cSimDog / cSimRaptor), so fall and stumble detection (cSimCharSoftFall, cSimDog::HasStumbled, ...) is the reference's code
+struct FakeCharData {
     Eigen::VectorXd pose, vel, last_tau;
     std::vector<std::shared_ptr<cSimObj>> parts;
     std::vector<FakeJoint> joints;
     tVector com = tVector(0, 0, 0, 0), com_vel = tVector(0, 0, 0, 0);
-    bool fallen = false, stumbled = false;
     int n_apply = 0;
+    virtual ~FakeCharData() {}
+    virtual cSimCharacter* sim() = 0;
+    virtual void soft_fall_update(double h) = 0;
+    virtual void soft_fall_reset() = 0;
+};
+struct FakeChar : public FakeCharData {};          // name used by the part / joint stand-ins
 
+template <typename Base>
+struct FakeCharT : public Base, public FakeChar {
+    cSimCharacter* sim() override { return this; }
+    void soft_fall_update(double h) override { Base::cSimCharSoftFall::Update(h); }
+    void soft_fall_reset() override { Base::cSimCharSoftFall::Reset(); }
     bool Load(const std::string& char_file) {
         if (!cCharacter::Init(char_file)) return false;                // skeleton via the reference's own loader
-        if (!cKinTree::LoadBodyDefs(char_file, mBodyDefs)) return false;
-        const int nj = GetNumJoints();
+        if (!cKinTree::LoadBodyDefs(char_file, this->mBodyDefs)) return false;
+        const int nj = this->GetNumJoints();
         joints.resize(nj);
         for (int j = 0; j < nj; ++j) {
             auto p = std::make_shared<FakePart>();
             p->owner = this; p->id = j;
             parts.push_back(p);
             joints[j].owner = this; joints[j].id = j;
-            joints[j].valid = cKinTree::HasParent(mJointMat, j);       // the root has no actuated joint
+            joints[j].valid = cKinTree::HasParent(this->mJointMat, j);  // the root has no actuated joint
         }
-        pose = Eigen::VectorXd::Zero(GetNumDof());
-        vel = Eigen::VectorXd::Zero(GetNumDof());
-        last_tau = Eigen::VectorXd::Zero(GetNumDof());
+        pose = Eigen::VectorXd::Zero(this->GetNumDof());
+        vel = Eigen::VectorXd::Zero(this->GetNumDof());
+        last_tau = Eigen::VectorXd::Zero(this->GetNumDof());
         return true;
     }
     void Clear() override { cCharacter::Clear(); }
-    void Reset() override { cCharacter::Reset(); }
     void Update(double) override {}
+    void SetPose(const Eigen::VectorXd& p) override { pose = p; }
+    void SetVel(const Eigen::VectorXd& v) override { vel = v; }
     void BuildPose(Eigen::VectorXd& out) const override { out = pose; }
     void BuildVel(Eigen::VectorXd& out) const override { out = vel; }
-    tVector GetRootPos() const override { return cKinTree::GetRootPos(mJointMat, pose); }
+    tVector GetRootPos() const override { return cKinTree::GetRootPos(this->mJointMat, pose); }
     // root orientation / angular rate as the reference extracts them from the root body (sim/SimCharacter.cpp:118-128,181-225):
     // the planar root joint's angle and rate
     void GetRootRotation(tVector& out_axis, double& out_theta) const override {
         out_axis = tVector(0, 0, 1, 0);
-        out_theta = cKinTree::GetRootTheta(mJointMat, pose);
+        out_theta = cKinTree::GetRootTheta(this->mJointMat, pose);
     }
     tVector GetRootAngVel() const override { return tVector(0, 0, vel[2], 0); }
     tVector GetRootVel() const override { return tVector(vel[0], vel[1], 0, 0); }
-    const Eigen::MatrixXd& GetBodyDefs() const override { return mBodyDefs; }
+    const Eigen::MatrixXd& GetBodyDefs() const override { return this->mBodyDefs; }
     int GetNumBodyParts() const override { return (int)parts.size(); }
     tVector CalcCOM() const override { return com; }
     tVector CalcCOMVel() const override { return com_vel; }
@@ -123,19 +138,20 @@ struct FakeChar : public cSimCharacter {
     cJoint& GetJoint(int j) override { return joints[j]; }
     const std::shared_ptr<cSimObj>& GetBodyPart(int i) const override { return parts[i]; }
     std::shared_ptr<cSimObj>& GetBodyPart(int i) override { return parts[i]; }
-    bool HasFallen() const override { return fallen; }
-    bool HasStumbled() const override { return stumbled; }
-    bool IsValidBodyPart(int idx) const override { return cKinTree::IsValidBody(mBodyDefs, idx); }
+    bool IsValidBodyPart(int idx) const override { return cKinTree::IsValidBody(this->mBodyDefs, idx); }
     void ApplyControlForces(const Eigen::VectorXd& tau) override { last_tau = tau; ++n_apply; }
 };
 
-tVector FakePart::GetPos() const { return cKinTree::CalcBodyPartPos(owner->GetJointMat(), owner->pose, owner->GetBodyDefs(), id); }
+static const Eigen::MatrixXd& jm(const FakeChar* c) { return const_cast<FakeChar*>(c)->sim()->GetJointMat(); }
+static const Eigen::MatrixXd& bd(const FakeChar* c) { return const_cast<FakeChar*>(c)->sim()->GetBodyDefs(); }
+
+tVector FakePart::GetPos() const { return cKinTree::CalcBodyPartPos(jm(owner), owner->pose, bd(owner), id); }
 tVector FakePart::GetLinearVelocity() const {
-    const tVector attach = cKinTree::GetBodyAttachPt(owner->GetBodyDefs(), id);
-    return cKinTree::CalcWorldVel(owner->GetJointMat(), owner->pose, owner->vel, id, attach);
+    const tVector attach = cKinTree::GetBodyAttachPt(bd(owner), id);
+    return cKinTree::CalcWorldVel(jm(owner), owner->pose, owner->vel, id, attach);
 }
 tVector FakePart::LocalToWorldPos(const tVector& local_pos) const {
-    tMatrix m = cKinTree::BodyWorldTrans(owner->GetJointMat(), owner->pose, owner->GetBodyDefs(), id);
+    tMatrix m = cKinTree::BodyWorldTrans(jm(owner), owner->pose, bd(owner), id);
     tVector p = local_pos;
     p[3] = 1;
     tVector w = m * p;
@@ -144,13 +160,13 @@ tVector FakePart::LocalToWorldPos(const tVector& local_pos) const {
 }
 void FakeJoint::CalcRotation(tVector& out_axis, double& out_theta) const {
     out_axis = axis_rel;
-    out_theta = cKinTree::GetJointTheta(owner->GetJointMat(), owner->pose, id);
+    out_theta = cKinTree::GetJointTheta(jm(owner), owner->pose, id);
 }
 void FakeJoint::GetChildRotation(tVector& out_axis, double& out_theta) const {
-    cKinTree::CalcJointWorldTheta(owner->GetJointMat(), owner->pose, id, out_axis, out_theta);
+    cKinTree::CalcJointWorldTheta(jm(owner), owner->pose, id, out_axis, out_theta);
 }
 tVector FakeJoint::CalcJointVelRel() const {
-    const int o = cKinTree::GetParamOffset(owner->GetJointMat(), id);
+    const int o = cKinTree::GetParamOffset(jm(owner), id);
     return axis_rel * owner->vel[o];
 }
 
@@ -173,6 +189,10 @@ cJoint::cJoint() {}
 cJoint::~cJoint() {}
 cSimCharacter::cSimCharacter() {}
 cSimCharacter::~cSimCharacter() {}
+// called as base-class functions by cSimCharSoftFall (the real ones drive Bullet)
+void cSimCharacter::Update(double) {}
+void cSimCharacter::Reset() {}          // the state is whatever the test installed
+bool cSimCharacter::Init(std::shared_ptr<cWorld>, const tParams&) { return true; }
 cGround::cGround() {}
 cGround::~cGround() {}
 
@@ -217,7 +237,7 @@ void cMACETrainer::SetActionFrag(const Eigen::VectorXd& frag, Eigen::VectorXd& o
 
 // ------------------------------------------------------------------------------------------------ C entry points
 struct RefCtrl {
-    FakeChar ch;
+    std::unique_ptr<FakeChar> chp;
     std::shared_ptr<FakeGround> ground;
     std::shared_ptr<cTerrainRLCharController> ctrl;
 };
@@ -229,7 +249,11 @@ extern "C" {
 RefCtrl* ref_ctrl_create(const char* char_file, int kind, double gx, double gy, height_fn fn, void* user) {
     if (std::getenv("REF_CTRL_DEBUG")) signal(SIGSEGV, ref_segv_handler);
     RefCtrl* r = new RefCtrl();
-    if (!r->ch.Load(char_file)) { delete r; return nullptr; }
+    bool ok;
+    if (kind <= 2) { auto* c = new FakeCharT<cSimDog>(); r->chp.reset(c); ok = c->Load(char_file); }       // the goat is a cSimDog too
+    else { auto* c = new FakeCharT<cSimRaptor>(); r->chp.reset(c); ok = c->Load(char_file); }
+    if (!ok) { delete r; return nullptr; }
+    cSimCharacter* sim = r->chp->sim();
     r->ground = std::make_shared<FakeGround>();
     r->ground->fn = fn; r->ground->user = user;
     const tVector g(gx, gy, 0, 0);
@@ -239,34 +263,40 @@ RefCtrl* ref_ctrl_create(const char* char_file, int kind, double gx, double gy, 
         else if (kind == 1) c = std::make_shared<cDogControllerMACE>();
         else c = std::make_shared<cGoatControllerMACE>();
         c->SetGround(r->ground);
-        c->Init(&r->ch, g, char_file);
+        c->Init(sim, g, char_file);
         r->ctrl = c;
     } else {
         std::shared_ptr<cRaptorController> c;
         if (kind == 3) c = std::make_shared<cRaptorControllerQ>();
         else c = std::make_shared<cRaptorControllerMACE>();
         c->SetGround(r->ground);
-        c->Init(&r->ch, g, char_file);
+        c->Init(sim, g, char_file);
         r->ctrl = c;
     }
     return r;
 }
 void ref_ctrl_destroy(RefCtrl* r) { delete r; }
 int ref_ctrl_valid(RefCtrl* r) { return r->ctrl->IsValid() ? 1 : 0; }
-int ref_ctrl_num_dof(RefCtrl* r) { return r->ch.GetNumDof(); }
-int ref_ctrl_num_joints(RefCtrl* r) { return r->ch.GetNumJoints(); }
+int ref_ctrl_num_dof(RefCtrl* r) { return r->chp->sim()->GetNumDof(); }
+int ref_ctrl_num_joints(RefCtrl* r) { return r->chp->sim()->GetNumJoints(); }
+// installs the simulation state the controller and the fall logic will see (pose, velocity, per-part contact bits, COM)
 void ref_ctrl_set_state(RefCtrl* r, const double* pose, const double* vel, const unsigned char* contact, const double* com,
-                        const double* com_vel, int fallen, int stumbled) {
-    const int nd = r->ch.GetNumDof(), nj = r->ch.GetNumJoints();
-    for (int i = 0; i < nd; ++i) { r->ch.pose[i] = pose[i]; r->ch.vel[i] = vel[i]; }
-    for (int j = 0; j < nj; ++j) static_cast<FakePart*>(r->ch.parts[j].get())->contact = contact[j] != 0;
-    r->ch.com = tVector(com[0], com[1], 0, 0);
-    r->ch.com_vel = tVector(com_vel[0], com_vel[1], 0, 0);
-    r->ch.fallen = fallen != 0; r->ch.stumbled = stumbled != 0;
+                        const double* com_vel) {
+    FakeChar& ch = *r->chp;
+    const int nd = ch.sim()->GetNumDof(), nj = ch.sim()->GetNumJoints();
+    for (int i = 0; i < nd; ++i) { ch.pose[i] = pose[i]; ch.vel[i] = vel[i]; }
+    for (int j = 0; j < nj; ++j) static_cast<FakePart*>(ch.parts[j].get())->contact = contact[j] != 0;
+    ch.com = tVector(com[0], com[1], 0, 0);
+    ch.com_vel = tVector(com_vel[0], com_vel[1], 0, 0);
 }
+// cSimCharSoftFall::Reset / Update (fall-distance and fall-contact counters) and the reference's own verdicts
+void ref_char_reset(RefCtrl* r) { r->chp->soft_fall_reset(); }
+void ref_char_update(RefCtrl* r, double h) { r->chp->soft_fall_update(h); }
+int ref_char_has_fallen(RefCtrl* r) { return r->chp->sim()->HasFallen() ? 1 : 0; }
+int ref_char_has_stumbled(RefCtrl* r) { return r->chp->sim()->HasStumbled() ? 1 : 0; }
 void ref_ctrl_reset(RefCtrl* r) { r->ctrl->Reset(); }
 void ref_ctrl_update(RefCtrl* r, double h) { r->ctrl->Update(h); }
-void ref_ctrl_get_tau(RefCtrl* r, double* out) { for (int i = 0; i < r->ch.GetNumDof(); ++i) out[i] = r->ch.last_tau[i]; }
+void ref_ctrl_get_tau(RefCtrl* r, double* out) { for (int i = 0; i < r->chp->sim()->GetNumDof(); ++i) out[i] = r->chp->last_tau[i]; }
 // state, phase, action id, then the full parameter vector of the current action
 int ref_ctrl_get_fsm(RefCtrl* r, double* out, int cap) {
     int k = 0;
@@ -279,6 +309,7 @@ int ref_ctrl_get_fsm(RefCtrl* r, double* out, int cap) {
     return k;
 }
 int ref_ctrl_num_actions(RefCtrl* r) { return r->ctrl->GetNumActions(); }
+double ref_ctrl_calc_reward(RefCtrl* r) { return r->ctrl->CalcReward(); }     // c{Dog,Raptor}Controller::CalcReward of the last cycle
 int ref_ctrl_poli_state(RefCtrl* r, double* out, int cap) {
     Eigen::VectorXd s;
     r->ctrl->RecordPoliState(s);

@@ -194,9 +194,12 @@ def test_controller_matches_reference_code(assets, scene):
     TerrainRLCharController / NNController / ImpPDController / PDController + KinTree / RBDUtil, compiled unmodified into
     oracle/_ref/libref_ctrl.so) is driven, env-step by env-step, with the oracle's state (pose, velocity, contacts, COM, terrain
     heights, and -- at policy decisions -- the oracle's network output), on a character back end that answers cSimCharacter's
-    virtual calls with the reference's own cKinTree kinematics.  Compared every step: the joint torques handed to
+    virtual calls with the reference's own cKinTree kinematics; the character class is the reference's own cSimDog / cSimRaptor,
+    so fall and stumble detection (cSimCharSoftFall, cSimDog::HasStumbled / CheckFallContact / FailFallMisc) run as compiled.
+    Compared every step: HasFallen / HasStumbled, the joint torques handed to
     ApplyControlForces vs the oracle's controller torques, the gait-machine state / phase / action id, the action parameters,
-    and at every decision the policy state vector (terrain samples + character features) the reference built."""
+    at every decision the policy state vector (terrain samples + character features) the reference built, and at the end of every
+    cycle the reward c{Dog,Raptor}Controller::CalcReward returns."""
     from pyoracle import Oracle
     char_file, kind, n_steps = CTRL_CASES[scene]
     ref = C.CDLL(REF_CTRL)
@@ -223,8 +226,17 @@ def test_controller_matches_reference_code(assets, scene):
     nd = ref.ref_ctrl_num_dof(h)
     assert nd == o.ndof
     H = 1.0 / 600.0
+    # cSimCharSoftFall::Reset with the initial state installed (the fall-distance check starts from the root position)
+    q, qd, _, contact = o.get_state(0)
+    com, cv = o.com(0)
+    ref.ref_ctrl_set_state(h, _p(q), _p(qd), _p(contact.astype(np.uint8)), _p(com), _p(cv))
+    ref.ref_char_reset(h)
+    ref.ref_char_update.argtypes = [C.c_void_p, C.c_double]
     worst_tau = worst_state = 0.0
+    n_stumbled = 0
     decisions = 0
+    rewards = []
+    ref.ref_ctrl_calc_reward.restype = C.c_double
     last_cycles = o.flags(0)[2]
     out_scale = np.ones(o.n_out if hasattr(o, "n_out") else 90)
     for k in range(n_steps):
@@ -235,8 +247,11 @@ def test_controller_matches_reference_code(assets, scene):
         if kind >= 1:
             y = o.net_out(0, 90)
             ref.ref_ctrl_set_net_output(o.S, _p(y), _p(out_scale), 90)
-        ref.ref_ctrl_set_state(h, _p(q), _p(qd), _p(contact.astype(np.uint8)), _p(com), _p(cv), int(fallen), int(stumbled))
+        ref.ref_ctrl_set_state(h, _p(q), _p(qd), _p(contact.astype(np.uint8)), _p(com), _p(cv))
         ref.ref_ctrl_update(h, C.c_double(H))
+        ref.ref_char_update(h, H)                     # cSimCharSoftFall::Update: controller first, then the fall checks
+        assert (ref.ref_char_has_fallen(h), ref.ref_char_has_stumbled(h)) == (fallen, stumbled), (scene, k)
+        n_stumbled += stumbled
         tr = np.zeros(nd)
         ref.ref_ctrl_get_tau(h, _p(tr))
         to = o.last_tau(0)
@@ -250,6 +265,10 @@ def test_controller_matches_reference_code(assets, scene):
         if cycles != last_cycles:
             decisions += 1
             last_cycles = cycles
+            if decisions >= 2:                                    # the start-up "cycle" has no previous cycle to rate (its tuple is dropped)
+                r_ref = ref.ref_ctrl_calc_reward(h)               # reward of the cycle that just ended (cScenarioExp::CalcReward)
+                assert abs(r_ref - o.calc_reward(0)) < 1e-12, (scene, k, r_ref, o.calc_reward(0))
+                rewards.append(r_ref)
             if kind >= 1:
                 s_ref = np.zeros(o.S)
                 assert ref.ref_ctrl_poli_state(h, _p(s_ref), o.S) == o.S
@@ -257,6 +276,65 @@ def test_controller_matches_reference_code(assets, scene):
                 worst_state = max(worst_state, es)
                 assert es < 1e-9, (scene, k, es)
     ref.ref_ctrl_destroy(h)
-    assert decisions >= 3
+    assert decisions >= 3 and max(rewards) > 0.2
     print(f"{scene}: {n_steps} env-steps, {decisions} cycles; worst torque difference {worst_tau:.2e} (relative), "
           f"worst policy-state difference {worst_state:.2e}")
+
+
+@pytest.mark.skipif(not (os.path.exists(REF_CTRL) and os.path.isdir("/root/reference/data/characters")),
+                    reason="oracle/_ref/libref_ctrl.so or the reference data files absent")
+@pytest.mark.parametrize("scene,char_file,kind", [("dog_slopes_mixed", "dog.txt", 1), ("raptor_narrow_gaps", "raptor.txt", 4)])
+def test_fall_and_stumble_logic_matches_reference_code(assets, scene, char_file, kind):
+    """cSimCharSoftFall + cSimDog / cSimRaptor (HasFallen, HasStumbled, CheckFallContact, FailFallMisc, the 5 s progress check and
+    the discounted body-contact sum) compiled from the reference vs the oracle, on scripted sequences that trigger every branch:
+    random part contacts, long body contact, a flipped root, and standing still for more than 5 s."""
+    from pyoracle import Oracle
+    ref = C.CDLL(REF_CTRL)
+    HFN = C.CFUNCTYPE(C.c_double, C.c_double, C.c_void_p)
+    o = Oracle(os.path.join(assets, scene + ".trlpack"), 1, 0)
+    cb = HFN(lambda x, u: 0.0)
+    ref.ref_ctrl_create.restype = C.c_void_p
+    ref.ref_ctrl_create.argtypes = [C.c_char_p, C.c_int, C.c_double, C.c_double, HFN, C.c_void_p]
+    ref.ref_char_update.argtypes = [C.c_void_p, C.c_double]
+    o.L.orc_fall_update.argtypes = [C.c_void_p, C.c_int, C.c_double]
+    cwd = os.getcwd()
+    os.chdir("/root/reference")
+    try:
+        h = C.c_void_p(ref.ref_ctrl_create(("data/characters/" + char_file).encode(), kind, 0.0, -9.8, cb, None))
+    finally:
+        os.chdir(cwd)
+    nd, nj = o.ndof, o.nj
+    H = 1.0 / 600.0
+    rng = np.random.default_rng(3)
+    q0, qd0, _, _ = o.get_state(0)
+    seen = {"fallen": 0, "stumbled": 0, "both_clear": 0}
+    for episode, script in enumerate(("contacts", "body", "flip", "still")):
+        q = q0.copy(); qd = qd0.copy()
+        contact = np.zeros(nj, np.uint8)
+        o.set_state(0, q, qd, None, contact)
+        ref.ref_ctrl_set_state(h, _p(q), _p(qd), _p(contact), _p(np.zeros(2)), _p(np.zeros(2)))
+        o.L.orc_fall_reset(o.h, 0)
+        ref.ref_char_reset(h)
+        steps = 3400 if script == "still" else 700
+        for k in range(steps):
+            if script != "still":
+                q[0] += 4.0 * H                                            # keeps the progress check quiet
+            if script == "contacts" and k % 7 == 0:
+                contact = (rng.uniform(size=nj) < 0.15).astype(np.uint8)
+            if script == "body":
+                contact[:] = 0
+                contact[rng.integers(0, 6)] = 1 if (k // 60) % 3 != 2 else 0   # spine / torso on the ground most of the time
+            if script == "flip":
+                q[2] = 0.005 * k * (1 if episode % 2 else -1)              # root pitch walks past 0.8 pi
+            o.set_state(0, q, qd, None, contact)
+            ref.ref_ctrl_set_state(h, _p(q), _p(qd), _p(contact), _p(np.zeros(2)), _p(np.zeros(2)))
+            o.L.orc_fall_update(o.h, 0, H)
+            ref.ref_char_update(h, H)
+            fo, so, _ = o.flags(0)
+            fr, sr = ref.ref_char_has_fallen(h), ref.ref_char_has_stumbled(h)
+            assert (fr, sr) == (fo, so), (scene, script, k, (fr, sr), (fo, so))
+            seen["fallen"] += fr; seen["stumbled"] += sr; seen["both_clear"] += (not fr and not sr)
+        if script in ("body", "flip", "still"):
+            assert ref.ref_char_has_fallen(h) == 1, (scene, script)       # every scripted failure mode ends fallen
+    ref.ref_ctrl_destroy(h)
+    assert min(seen.values()) > 100
