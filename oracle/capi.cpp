@@ -329,4 +329,26 @@ void orc_rand_stream(unsigned long seed, int kind, double a, double b, int n, do
         }
     }
 }
+
+// ---------------------------------------------------------------------------------------- streaming ground alone (terrain.h: Ground)
+struct OrcGround { Ground g; };
+OrcGround* orc_ground_create(int type, const double* params40, unsigned long seed, double bmin, double bmax) {
+    OrcGround* o = new OrcGround();
+    o->g.type = type;
+    for (int i = 0; i < pTerrainParamMax; ++i) o->g.params[i] = params40[i];
+    o->g.rand.seed(seed);
+    o->g.init_segments(bmin, bmax);
+    return o;
+}
+void orc_ground_destroy(OrcGround* o) { delete o; }
+void orc_ground_update(OrcGround* o, double bmin, double bmax) { o->g.update(bmin, bmax); }
+int orc_ground_segment(OrcGround* o, int s, float* out, int cap, double* min_x) {
+    const Ground::Seg& sg = o->g.seg[o->g.seg_id(s)];
+    int n = (int)sg.data.size();
+    for (int i = 0; i < n && i < cap; ++i) out[i] = sg.data[i];
+    *min_x = sg.min_x;
+    return n;
+}
+int orc_ground_flipped(OrcGround* o) { return o->g.flip ? 1 : 0; }
+double orc_ground_sample(OrcGround* o, double x) { return o->g.sample(x); }
 }  // extern "C"

@@ -16,6 +16,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <memory>
 #include <string>
 #include <vector>
@@ -29,6 +30,7 @@
 #include "sim/RaptorControllerMACE.h"
 #include "sim/RaptorControllerQ.h"
 #include "sim/Ground.h"
+#include "sim/GroundVar2D.h"
 #include "sim/SimCharacter.h"
 #include "sim/SimDog.h"
 #include "sim/SimRaptor.h"
@@ -193,8 +195,58 @@ cSimCharacter::~cSimCharacter() {}
 void cSimCharacter::Update(double) {}
 void cSimCharacter::Reset() {}          // the state is whatever the test installed
 bool cSimCharacter::Init(std::shared_ptr<cWorld>, const tParams&) { return true; }
-cGround::cGround() {}
-cGround::~cGround() {}
+
+// ---- the world, as far as sim/GroundVar2D.cpp needs it: the length scale, and the position of a terrain segment's (Bullet) body,
+// which the reference stores in single precision at world scale (cWorld::SetPos / GetPos, sim/World.cpp:288-309)
+cWorld::tParams::tParams() : mNumSubsteps(1), mScale(1), mGravity(gGravity) {}
+cContactManager::cContactManager(cWorld& world) : mWorld(world) {}
+cContactManager::~cContactManager() {}
+cPerturbManager::cPerturbManager() {}
+cPerturbManager::~cPerturbManager() {}
+cWorld::cWorld() : mContactManager(*this) {}
+cWorld::~cWorld() {}
+struct FakeWorld : public cWorld {
+    double scale = 4.0;
+    mutable std::map<const cSimObj*, btVector3> origin;
+    double GetScale() const override { return scale; }
+    void SetPos(const tVector& pos, cSimObj* obj) const override {
+        const btScalar s = static_cast<btScalar>(GetScale());
+        origin[obj] = btVector3(s * static_cast<btScalar>(pos[0]), s * static_cast<btScalar>(pos[1]), s * static_cast<btScalar>(pos[2]));
+    }
+    // Bullet's body->getAabb for a height field, WITHOUT its collision margin and in double precision from the stored (float)
+    // origin: the ideal box of the grid.  (What real Bullet returns -- float arithmetic plus the shape's collision margin -- is
+    // the part of the reference's ground that cannot be reproduced without Bullet; see tests/test_ref_pinning_cpu.py.)
+    void CalcAABB(const cSimObj* obj, tVector& out_min, tVector& out_max) const override {
+        const auto* hf = dynamic_cast<const btHeightfieldTerrainShape*>(obj->GetCollisionShape().get());
+        const btVector3& o = origin[obj];
+        const btVector3& sc = hf->getLocalScaling();
+        const double hx = 0.5 * (hf->width_ - 1) * sc[0], hz = 0.5 * (hf->length_ - 1) * sc[2];
+        const double ymid = 0.5 * ((double)hf->min_h_ + hf->max_h_), hy = 0.5 * ((double)hf->max_h_ - hf->min_h_);
+        (void)ymid;
+        out_min = tVector(o[0] - hx, o[1] - hy, o[2] - hz, 0) / GetScale();
+        out_max = tVector(o[0] + hx, o[1] + hy, o[2] + hz, 0) / GetScale();
+    }
+    tVector GetPos(const cSimObj* obj) const override {
+        const btVector3& o = origin[obj];
+        tVector p(o[0], o[1], o[2], 0);
+        p /= GetScale();
+        return p;
+    }
+};
+void cSimObj::Init(std::shared_ptr<cWorld> world) { mWorld = world; }
+tVector cSimObj::GetPos() const { return mWorld->GetPos(this); }                 // sim/SimObj.cpp:16-24
+void cSimObj::SetPos(const tVector& pos) { mWorld->SetPos(pos, this); }
+void cSimObj::CalcAABB(tVector& out_min, tVector& out_max) const { mWorld->CalcAABB(this, out_min, out_max); }   // sim/SimObj.cpp:202-205
+const std::unique_ptr<btCollisionShape>& cSimObj::GetCollisionShape() const { return mShape; }
+void cSimObj::UpdateContact(int, int) {}
+void cSimObj::RemoveFromWorld() {}
+
+struct FakeGroundVar : public cGroundVar2D {
+    int num_verts(int s) const { return GetSegment(s)->GetGridWidth(); }      // first row of the (duplicated) height grid
+    const float* verts(int s) const { return GetSegment(s)->mData.data(); }
+    double min_x(int s) const { return GetSegment(s)->GetMinX(); }
+    bool flipped() const { return mFlipSeg; }
+};
 
 // ---- cNeuralNet: what the controllers ask of it; Eval returns the output vector the test installed for the current decision
 static Eigen::VectorXd g_net_output;
@@ -324,5 +376,36 @@ void ref_ctrl_set_net_output(int n_in, const double* y, const double* out_scale,
     g_net_output.resize(n_out); g_out_scale.resize(n_out);
     for (int i = 0; i < n_out; ++i) { g_net_output[i] = y[i]; g_out_scale[i] = out_scale[i]; }
 }
+
+
+// ---------------------------------------------------------------------------------------- streaming ground (sim/GroundVar2D.cpp)
+struct RefGround {
+    std::shared_ptr<FakeWorld> world;
+    FakeGroundVar ground;
+};
+// cScenarioSimChar::BuildGround / ResetGround: terrain function + parameters, seed, Init over the initial view window
+RefGround* ref_ground_create(int type, const double* params40, unsigned long seed, double bmin, double bmax) {
+    RefGround* g = new RefGround();
+    g->world = std::make_shared<FakeWorld>();
+    Eigen::VectorXd p(cTerrainGen2D::eParamsMax);
+    for (int i = 0; i < cTerrainGen2D::eParamsMax; ++i) p[i] = params40[i];
+    g->ground.SetTerrainFunc(cTerrainGen2D::GetTerrainFunc(static_cast<cTerrainGen2D::eType>(type)));
+    g->ground.SetTerrainParams(p);
+    g->ground.SeedRand(seed);
+    cGroundVar2D::tParams gp;
+    g->ground.Init(g->world, gp, tVector(bmin, 0, 0, 0), tVector(bmax, 0, 0, 0));
+    return g;
+}
+void ref_ground_destroy(RefGround* g) { delete g; }
+void ref_ground_update(RefGround* g, double bmin, double bmax) { g->ground.Update(tVector(bmin, 0, 0, 0), tVector(bmax, 0, 0, 0)); }
+// logical segment s (0 = min, 1 = max side as the reference orders them): vertex data (at world scale, as stored), min x
+int ref_ground_segment(RefGround* g, int s, float* out, int cap, double* min_x) {
+    const int n = g->ground.num_verts(s);
+    for (int i = 0; i < n && i < cap; ++i) out[i] = g->ground.verts(s)[i];
+    *min_x = g->ground.min_x(s);
+    return n;
+}
+int ref_ground_flipped(RefGround* g) { return g->ground.flipped() ? 1 : 0; }
+double ref_ground_sample(RefGround* g, double x) { return g->ground.SampleHeight(tVector(x, 0, 0, 0)); }
 
 }  // extern "C"

@@ -338,3 +338,60 @@ def test_fall_and_stumble_logic_matches_reference_code(assets, scene, char_file,
             assert ref.ref_char_has_fallen(h) == 1, (scene, script)       # every scripted failure mode ends fallen
     ref.ref_ctrl_destroy(h)
     assert min(seen.values()) > 100
+
+
+@pytest.mark.skipif(not os.path.exists(REF_CTRL), reason="oracle/_ref/libref_ctrl.so not built")
+def test_streaming_ground_matches_reference_code(libs):
+    """cGroundVar2D (sim/GroundVar2D.cpp compiled from the reference: InitSegments, Update, BuildSegment, AddPadding, the segment
+    ping-pong, SampleHeight) vs oracle/terrain.h's Ground: the view window [x - 2, x + 11] of a character running forward (and,
+    for a while, backward) over every terrain type.  Vertex data and the segment bookkeeping must be identical; segment origins
+    and sampled heights agree to 1e-6 relative -- the reference keeps each segment's origin in single precision at world scale
+    (cWorld::SetPos), the oracle and the product keep it in double.  The stand-in for Bullet's body->getAabb is the ideal box of
+    the height grid: real Bullet adds the shape's collision margin in float arithmetic, which is the one part of the reference's
+    ground that cannot be reproduced without Bullet (it shifts where successive segments start by about a centimetre)."""
+    terr, orc = libs
+    ref = C.CDLL(REF_CTRL)
+    for L, pre in ((ref, "ref"), (orc, "orc")):
+        getattr(L, pre + "_ground_create").restype = C.c_void_p
+        getattr(L, pre + "_ground_create").argtypes = [C.c_int, C.c_void_p, C.c_ulong, C.c_double, C.c_double]
+        getattr(L, pre + "_ground_update").argtypes = [C.c_void_p, C.c_double, C.c_double]
+        getattr(L, pre + "_ground_segment").argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+        getattr(L, pre + "_ground_sample").restype = C.c_double
+        getattr(L, pre + "_ground_sample").argtypes = [C.c_void_p, C.c_double]
+        getattr(L, pre + "_ground_flipped").argtypes = [C.c_void_p]
+        getattr(L, pre + "_ground_destroy").argtypes = [C.c_void_p]
+    rng = np.random.default_rng(11)
+    cap = 2048
+    rebuilds = 0
+    for t in range(14):
+        p = _params(terr, rng if t % 2 else None)
+        seed = int(rng.integers(1, 2 ** 31))
+        x = 0.0
+        r = C.c_void_p(ref.ref_ground_create(t, _p(p), seed, x - 2.0, x + 11.0))
+        o = C.c_void_p(orc.orc_ground_create(t, _p(p), seed, x - 2.0, x + 11.0))
+        last_flip = ref.ref_ground_flipped(r)
+        for step in range(260):
+            x += rng.uniform(0.0, 0.9) if step < 200 else -rng.uniform(0.0, 0.9)      # forward 90 m, then back
+            ref.ref_ground_update(r, x - 2.0, x + 11.0)
+            orc.orc_ground_update(o, x - 2.0, x + 11.0)
+            fl = ref.ref_ground_flipped(r)
+            assert fl == orc.orc_ground_flipped(o), (t, step)
+            if fl != last_flip:
+                rebuilds += 1
+                last_flip = fl
+            for s in (0, 1):
+                a = np.zeros(cap, np.float32); b = np.zeros(cap, np.float32)
+                ma = C.c_double(0); mb = C.c_double(0)
+                na = ref.ref_ground_segment(r, s, _p(a), cap, C.byref(ma))
+                nb = orc.orc_ground_segment(o, s, _p(b), cap, C.byref(mb))
+                assert na == nb and abs(ma.value - mb.value) < 2e-6 * max(1.0, abs(mb.value)), (t, step, s, na, nb, ma.value, mb.value)
+                np.testing.assert_array_equal((a[:na] / np.float32(4.0)).view(np.uint32), b[:nb].view(np.uint32))   # stored x world scale 4
+            for xs in rng.uniform(x - 2.0, x + 11.0, 6):
+                # the reference's segment origin is a float: its sample equals the oracle's within that shift of the abscissa
+                d = 2e-6 * max(1.0, abs(xs))
+                band = [orc.orc_ground_sample(o, xs + e) for e in (-d, 0.0, d)]
+                hr = ref.ref_ground_sample(r, xs)
+                slack = 1e-7 + (max(band) - min(band))           # a vertex (kink) may lie inside the +-d window
+                assert min(band) - slack <= hr <= max(band) + slack, (t, step, xs, hr, band)
+        ref.ref_ground_destroy(r); orc.orc_ground_destroy(o)
+    assert rebuilds > 14 * 4
