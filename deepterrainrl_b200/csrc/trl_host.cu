@@ -662,6 +662,17 @@ int trl_load_model(trl_handle* h, const char* h5_path, const char* scale_path) {
         return fail(e.what());
     }
 }
+int trl_get_output_offset_scale(trl_handle* h, double* off, double* scale, int n);
+// the same for a scene pack, without a device (host-only: parses the pack and the controller tables); used to check the
+// restatement against the reference's own compiled BuildNNOutputOffsetScale (tests/test_ref_pinning_cpu.py)
+int trl_pack_output_offset_scale(const char* pack_path, double* off, double* scale, int n) {
+    trl_handle h;
+    std::string err;
+    if (!h.scene.load(pack_path, &err)) return fail(err);
+    if (fill_model(&h, 0)) return 1;
+    return trl_get_output_offset_scale(&h, off, scale, n);
+}
+
 // cBaseControllerMACE::BuildNNOutputOffsetScale (sim/BaseControllerMACE.cpp:75-113,131-167): critic outputs offset -0.5 scale 2;
 // actor f centred on the optimised parameters of control set f % n_ctrl (cDogControllerMACE::BuildActorBias) and scaled by
 // 1 / max_a |opt(a) - opt(default action)| over the action library

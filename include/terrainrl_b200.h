@@ -139,6 +139,7 @@ int trl_output_model(trl_handle* h, const char* path, uint32_t mtime);
 int trl_write_model(const char* path, const double* const* blobs26, int n_char, int n_frags, int frag_size, const double* in_off,
                     const double* in_scale, const double* out_off, const double* out_scale, uint32_t mtime);
 int trl_get_output_offset_scale(trl_handle* h, double* offset, double* scale, int n_out);
+int trl_pack_output_offset_scale(const char* pack_path, double* offset, double* scale, int n_out);   /* host only, no device */
 
 /* cScenarioSimChar::SetTerrainParamsLerp (scenarios/ScenarioSimChar.cpp:255-272) and cScenarioTrain's annealing schedule
  * (scenarios/ScenarioTrain.cpp:412-460): sp[9] = {init_exp_rate, exp_rate, init_exp_temp, exp_temp, init_exp_base_rate,

@@ -361,6 +361,13 @@ int ref_ctrl_get_fsm(RefCtrl* r, double* out, int cap) {
     return k;
 }
 int ref_ctrl_num_actions(RefCtrl* r) { return r->ctrl->GetNumActions(); }
+// cBaseControllerMACE::BuildNNOutputOffsetScale of the compiled reference controller
+int ref_ctrl_output_offset_scale(RefCtrl* r, double* off, double* scale, int cap) {
+    Eigen::VectorXd o, s;
+    r->ctrl->BuildNNOutputOffsetScale(o, s);
+    for (int i = 0; i < o.size() && i < cap; ++i) { off[i] = o[i]; scale[i] = s[i]; }
+    return o.size();
+}
 double ref_ctrl_calc_reward(RefCtrl* r) { return r->ctrl->CalcReward(); }     // c{Dog,Raptor}Controller::CalcReward of the last cycle
 int ref_ctrl_poli_state(RefCtrl* r, double* out, int cap) {
     Eigen::VectorXd s;

@@ -395,3 +395,38 @@ def test_streaming_ground_matches_reference_code(libs):
                 assert min(band) - slack <= hr <= max(band) + slack, (t, step, xs, hr, band)
         ref.ref_ground_destroy(r); orc.orc_ground_destroy(o)
     assert rebuilds > 14 * 4
+
+
+@pytest.mark.skipif(not (os.path.exists(REF_CTRL) and os.path.isdir("/root/reference/data/characters")),
+                    reason="oracle/_ref/libref_ctrl.so or the reference data files absent")
+@pytest.mark.parametrize("scene,char_file,kind", [("dog_slopes_mixed", "dog.txt", 1), ("goat_cliffs", "goat.txt", 2),
+                                                  ("raptor_narrow_gaps", "raptor.txt", 4)])
+def test_output_offset_scale_matches_reference_code(assets, scene, char_file, kind):
+    """cBaseControllerMACE::BuildNNOutputOffsetScale as compiled from the reference vs the PRODUCT's host function behind
+    trl_get_output_offset_scale / trl_trainer_init_fresh (evaluated from the scene pack, no device needed)."""
+    import deepterrainrl_b200 as trl
+    L = trl.load_library()
+    ref = C.CDLL(REF_CTRL)
+    HFN = C.CFUNCTYPE(C.c_double, C.c_double, C.c_void_p)
+    cb = HFN(lambda x, u: 0.0)
+    ref.ref_ctrl_create.restype = C.c_void_p
+    ref.ref_ctrl_create.argtypes = [C.c_char_p, C.c_int, C.c_double, C.c_double, HFN, C.c_void_p]
+    cwd = os.getcwd()
+    os.chdir("/root/reference")
+    try:
+        h = C.c_void_p(ref.ref_ctrl_create(("data/characters/" + char_file).encode(), kind, 0.0, -9.8, cb, None))
+    finally:
+        os.chdir(cwd)
+    frag = 28 if kind == 4 else 29
+    n = 3 * (1 + frag)
+    ref.ref_ctrl_set_net_output(275 if kind == 4 else 283, _p(np.zeros(n)), _p(np.ones(n)), n)
+    assert ref.ref_ctrl_load_net(h) == 1
+    ro = np.zeros(n); rs = np.zeros(n)
+    assert ref.ref_ctrl_output_offset_scale(h, _p(ro), _p(rs), n) == n
+    po = np.zeros(n); ps = np.zeros(n)
+    rc = L.trl_pack_output_offset_scale(os.path.join(assets, scene + ".trlpack").encode(), _p(po), _p(ps), n)
+    assert rc == 0, L.trl_last_error().decode()
+    np.testing.assert_allclose(po, ro, rtol=0, atol=1e-15)
+    np.testing.assert_allclose(ps, rs, rtol=1e-15, atol=0)
+    assert np.all(ro[:3] == -0.5) and np.all(rs[:3] == 2.0)
+    ref.ref_ctrl_destroy(h)
