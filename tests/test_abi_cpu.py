@@ -101,3 +101,19 @@ def test_raptor_pack_identities(assets):
     off = p["net_out_offset"]
     for a in range(3):
         np.testing.assert_allclose(off[3 + 28 * a:3 + 28 * (a + 1)], -ctrl[a][mask], atol=1e-6)   # BuildActorBias
+
+
+def test_plain_c_client_builds_and_fails_loudly_without_gpu(tmp_path):
+    """examples/eval_and_train.c: the header is valid C99, the library links from C, and without a GPU the first create call
+    fails with a message instead of falling back to anything."""
+    import subprocess
+    import deepterrainrl_b200 as trl
+    lib = trl.library_path()
+    exe = str(tmp_path / "client")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "eval_and_train.c"),
+                    "-L", os.path.dirname(lib), "-lterrainrl_b200", "-Wl,-rpath," + os.path.dirname(lib), "-o", exe], check=True)
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: the client would run the full example")
+    r = subprocess.run([exe, os.path.join(ROOT, "assets", "dog_flat.trlpack"), "8"], capture_output=True, text=True)
+    assert r.returncode == 2 and "no GPU visible" in r.stderr
