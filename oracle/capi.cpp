@@ -63,6 +63,10 @@ void orc_update(OrcBatch* b, double dt, int num_threads) {
 }
 void orc_env_step(OrcBatch* b, int env, double h) { b->envs[env]->env_step(h); }
 void orc_reset(OrcBatch* b, int env) { b->envs[env]->reset(); }
+// scenario-level pinning (tests/test_ref_pinning_cpu.py): the end-of-update tail on its own, and the action id CommandRandAction
+// queued at the last reset (-1: none pending)
+void orc_end_update(OrcBatch* b, int env, double dt) { b->envs[env]->time += dt; b->envs[env]->end_update(); }
+int orc_pending_command(OrcBatch* b, int env) { auto& c = b->envs[env]->commands; return c.empty() ? -1 : c.back(); }
 
 void orc_get_state(OrcBatch* b, int env, double* q, double* qd, double* tau_held, uint8_t* contact) {
     Env& e = *b->envs[env];

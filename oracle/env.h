@@ -969,6 +969,12 @@ struct Env {
         time += dt;
         double h = dt / sc->num_update_steps;
         for (int i = 0; i < sc->num_update_steps; ++i) env_step(h);
+        end_update();
+    }
+
+    // the tail of cScenarioPoliEval::Update / cScenarioExp::Update, after the env-steps (scenarios/ScenarioPoliEval.cpp:112-124,
+    // scenarios/ScenarioExp.cpp:84-97); separate so that a test can interleave the env-steps with the compiled reference scenario
+    void end_update() {
         if (exp_mode) {
             if (!is_new_cycle() && has_fallen()) { exp_new_cycle_update(); reset(); }
         } else if (has_fallen()) {

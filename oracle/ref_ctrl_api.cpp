@@ -34,6 +34,9 @@
 #include "sim/SimCharacter.h"
 #include "sim/SimDog.h"
 #include "sim/SimRaptor.h"
+#include "scenarios/ScenarioExpMACE.h"
+#include "scenarios/ScenarioPoliEval.h"
+#include "util/ArgParser.h"
 
 extern "C" void ref_abort_stub() {
     std::fprintf(stderr, "oracle/_ref: the compiled reference code called a Bullet/Caffe-backed function that has no stand-in\n");
@@ -92,6 +95,7 @@ struct FakeCharData {
     virtual cSimCharacter* sim() = 0;
     virtual void soft_fall_update(double h) = 0;
     virtual void soft_fall_reset() = 0;
+    virtual bool load(const std::string& char_file, const std::string& state_file) = 0;
 };
 struct FakeChar : public FakeCharData {};          // name used by the part / joint stand-ins
 
@@ -117,10 +121,16 @@ struct FakeCharT : public Base, public FakeChar {
         last_tau = Eigen::VectorXd::Zero(this->GetNumDof());
         return true;
     }
+    bool load(const std::string& char_file, const std::string& state_file) override {
+        if (!Load(char_file)) return false;
+        if (state_file != "" && !this->ReadState(state_file)) return false;      // cCharacter::ReadState -> SetPose / SetVel below
+        this->RecordDefaultState();                                               // pose0 / vel0 for Reset
+        return true;
+    }
     void Clear() override { cCharacter::Clear(); }
-    void Update(double) override {}
-    void SetPose(const Eigen::VectorXd& p) override { pose = p; }
-    void SetVel(const Eigen::VectorXd& v) override { vel = v; }
+    void SetRootPos(const tVector& pos) override { cKinTree::SetRootPos(this->mJointMat, pos, pose); cCharacter::SetPose(pose); }
+    void SetPose(const Eigen::VectorXd& p) override { pose = p; cCharacter::SetPose(p); }
+    void SetVel(const Eigen::VectorXd& v) override { vel = v; cCharacter::SetVel(v); }
     void BuildPose(Eigen::VectorXd& out) const override { out = pose; }
     void BuildVel(Eigen::VectorXd& out) const override { out = vel; }
     tVector GetRootPos() const override { return cKinTree::GetRootPos(this->mJointMat, pose); }
@@ -134,8 +144,31 @@ struct FakeCharT : public Base, public FakeChar {
     tVector GetRootVel() const override { return tVector(vel[0], vel[1], 0, 0); }
     const Eigen::MatrixXd& GetBodyDefs() const override { return this->mBodyDefs; }
     int GetNumBodyParts() const override { return (int)parts.size(); }
-    tVector CalcCOM() const override { return com; }
-    tVector CalcCOMVel() const override { return com_vel; }
+    // cSimCharacter::CalcCOM / CalcCOMVel (sim/SimCharacter.cpp:396-434): mass-weighted body-part positions / velocities
+    tVector CalcCOM() const override {
+        tVector c = tVector::Zero();
+        double total = 0;
+        for (int i = 0; i < (int)parts.size(); ++i) {
+            if (!IsValidBodyPart(i)) continue;
+            const double m = cKinTree::GetBodyMass(this->mBodyDefs, i);
+            c += m * parts[i]->GetPos();
+            total += m;
+        }
+        c /= total;
+        return c;
+    }
+    tVector CalcCOMVel() const override {
+        tVector c = tVector::Zero();
+        double total = 0;
+        for (int i = 0; i < (int)parts.size(); ++i) {
+            if (!IsValidBodyPart(i)) continue;
+            const double m = cKinTree::GetBodyMass(this->mBodyDefs, i);
+            c += m * parts[i]->GetLinearVelocity();
+            total += m;
+        }
+        c /= total;
+        return c;
+    }
     const cJoint& GetJoint(int j) const override { return joints[j]; }
     cJoint& GetJoint(int j) override { return joints[j]; }
     const std::shared_ptr<cSimObj>& GetBodyPart(int i) const override { return parts[i]; }
@@ -192,9 +225,27 @@ cJoint::~cJoint() {}
 cSimCharacter::cSimCharacter() {}
 cSimCharacter::~cSimCharacter() {}
 // called as base-class functions by cSimCharSoftFall (the real ones drive Bullet)
-void cSimCharacter::Update(double) {}
-void cSimCharacter::Reset() {}          // the state is whatever the test installed
-bool cSimCharacter::Init(std::shared_ptr<cWorld>, const tParams&) { return true; }
+// cSimCharacter::Update / Reset / Init without their Bullet halves (sim/SimCharacter.cpp:25-107): run the controller; restore
+// pose0 / vel0 and reset the controller; load skeleton + state file.  g_reset_loads_pose0 is off for the tests that install
+// every state themselves.
+static bool g_reset_loads_pose0 = false;
+void cSimCharacter::Update(double time_step) { if (mController) mController->Update(time_step); }
+void cSimCharacter::Reset() {
+    if (g_reset_loads_pose0) cCharacter::Reset();
+    if (mController) mController->Reset();
+}
+bool cSimCharacter::Init(std::shared_ptr<cWorld> world, const tParams& params) {
+    mWorld = world;
+    FakeChar* f = dynamic_cast<FakeChar*>(this);
+    return f && f->load(params.mCharFile, params.mStateFile);
+}
+cSimCharacter::tParams::tParams() : mCharFile(""), mStateFile(""), mPos(0, 0, 0, 0), mPlaneCons(cWorld::ePlaneConsNone) {}
+void cSimCharacter::SetController(std::shared_ptr<cCharController> ctrl) { mController = ctrl; }
+void cSimCharacter::RemoveController() { mController.reset(); }
+bool cSimCharacter::HasController() const { return mController != nullptr; }
+const std::shared_ptr<cCharController>& cSimCharacter::GetController() { return mController; }
+const std::shared_ptr<cCharController>& cSimCharacter::GetController() const { return mController; }
+void cSimCharacter::RegisterContacts(int, int) {}
 
 // ---- the world, as far as sim/GroundVar2D.cpp needs it: the length scale, and the position of a terrain segment's (Bullet) body,
 // which the reference stores in single precision at world scale (cWorld::SetPos / GetPos, sim/World.cpp:288-309)
@@ -205,20 +256,33 @@ cPerturbManager::cPerturbManager() {}
 cPerturbManager::~cPerturbManager() {}
 cWorld::cWorld() : mContactManager(*this) {}
 cWorld::~cWorld() {}
+typedef void (*world_fn)(double h, void* user);
+// Bullet keeps a body's position in single precision, so the reference's terrain segments sit at float origins (at world scale)
+// and its height samples carry that rounding (~1e-7 m).  With this flag the stand-in world keeps the origin in double instead:
+// the scenario pin runs once each way -- exact origin to show that everything else agrees to rounding, float origin (the
+// reference as it is) to bound the effect of the single-precision origin.
+static bool g_world_exact_origin = false;
+extern "C" void ref_world_exact_origin(int on) { g_world_exact_origin = on != 0; }
 struct FakeWorld : public cWorld {
     double scale = 4.0;
+    world_fn cb = nullptr;          // cWorld::Update: the test advances the physics (the oracle's) and installs the new state
+    void* user = nullptr;
+    void Update(double time_elapsed) override { if (cb) cb(time_elapsed, user); }
+    void Reset() override {}
     mutable std::map<const cSimObj*, btVector3> origin;
+    mutable std::map<const cSimObj*, tVector> origin_exact;     // see g_world_exact_origin
     double GetScale() const override { return scale; }
     void SetPos(const tVector& pos, cSimObj* obj) const override {
         const btScalar s = static_cast<btScalar>(GetScale());
         origin[obj] = btVector3(s * static_cast<btScalar>(pos[0]), s * static_cast<btScalar>(pos[1]), s * static_cast<btScalar>(pos[2]));
+        origin_exact[obj] = pos * GetScale();
     }
     // Bullet's body->getAabb for a height field, WITHOUT its collision margin and in double precision from the stored (float)
     // origin: the ideal box of the grid.  (What real Bullet returns -- float arithmetic plus the shape's collision margin -- is
     // the part of the reference's ground that cannot be reproduced without Bullet; see tests/test_ref_pinning_cpu.py.)
     void CalcAABB(const cSimObj* obj, tVector& out_min, tVector& out_max) const override {
         const auto* hf = dynamic_cast<const btHeightfieldTerrainShape*>(obj->GetCollisionShape().get());
-        const btVector3& o = origin[obj];
+        const tVector o = org(obj);
         const btVector3& sc = hf->getLocalScaling();
         const double hx = 0.5 * (hf->width_ - 1) * sc[0], hz = 0.5 * (hf->length_ - 1) * sc[2];
         const double ymid = 0.5 * ((double)hf->min_h_ + hf->max_h_), hy = 0.5 * ((double)hf->max_h_ - hf->min_h_);
@@ -226,8 +290,13 @@ struct FakeWorld : public cWorld {
         out_min = tVector(o[0] - hx, o[1] - hy, o[2] - hz, 0) / GetScale();
         out_max = tVector(o[0] + hx, o[1] + hy, o[2] + hz, 0) / GetScale();
     }
-    tVector GetPos(const cSimObj* obj) const override {
+    tVector org(const cSimObj* obj) const {
+        if (g_world_exact_origin) return origin_exact[obj];
         const btVector3& o = origin[obj];
+        return tVector(o[0], o[1], o[2], 0);
+    }
+    tVector GetPos(const cSimObj* obj) const override {
+        const tVector o = org(obj);
         tVector p(o[0], o[1], o[2], 0);
         p /= GetScale();
         return p;
@@ -265,7 +334,17 @@ bool cNeuralNet::HasLayer(const std::string) const { return false; }
 int cNeuralNet::GetInputSize() const { return g_net_in; }
 int cNeuralNet::GetOutputSize() const { return g_net_out; }
 const Eigen::VectorXd& cNeuralNet::GetOutputScale() const { return g_out_scale; }
-void cNeuralNet::Eval(const Eigen::VectorXd&, Eigen::VectorXd& out_y) const { out_y = g_net_output; }
+typedef void (*net_fn)(const double* x, int n_in, double* y, int n_out, void* user);
+static net_fn g_net_cb = nullptr;          // scenario pin: the test evaluates the network (the oracle's) on the input the reference built
+static void* g_net_user = nullptr;
+void cNeuralNet::Eval(const Eigen::VectorXd& x, Eigen::VectorXd& out_y) const {
+    if (!g_net_cb) { out_y = g_net_output; return; }
+    std::vector<double> xi(x.size()), yo(g_net_out);
+    for (int i = 0; i < (int)x.size(); ++i) xi[i] = x[i];
+    g_net_cb(xi.data(), (int)xi.size(), yo.data(), g_net_out, g_net_user);
+    out_y.resize(g_net_out);
+    for (int i = 0; i < g_net_out; ++i) out_y[i] = yo[i];
+}
 void cNeuralNet::ForwardInjectNoisePrefilled(double, double, const std::string&, Eigen::VectorXd&) const { ref_abort_stub(); }
 
 // ---- the index helpers of cMACETrainer the MACE controller uses (learning/MACETrainer.cpp:9-66; the trainer itself needs Caffe)
@@ -414,5 +493,119 @@ int ref_ground_segment(RefGround* g, int s, float* out, int cap, double* min_x) 
 }
 int ref_ground_flipped(RefGround* g) { return g->ground.flipped() ? 1 : 0; }
 double ref_ground_sample(RefGround* g, double x) { return g->ground.SampleHeight(tVector(x, 0, 0, 0)); }
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------ whole scenarios
+// cScenarioPoliEval / cScenarioExpMACE (+ cScenarioExp, cScenarioSimChar, cScenario) compiled as they are.  Two of their factory
+// functions are overridden: BuildWorld makes the FakeWorld above (whose Update hands the env-step to the test, which advances the
+// oracle's physics and installs the new state) and CreateCharacter makes the fake-backed cSimDog / cSimRaptor.  Everything else --
+// the step loop, ground streaming on the reference's own cGroundVar2D, the controller, the cycle / tuple / episode bookkeeping,
+// fall handling and Reset -- runs as compiled.  cScenarioExp::CommandRandAction draws from the reference's process-global random
+// engine; the override commands the action the test names (the oracle's own draw) instead.
+typedef int (*cmd_fn)(void* user);
+template <typename Base>
+struct FakeScn : public Base {
+    world_fn wcb = nullptr;
+    cmd_fn ccb = nullptr;
+    void* user = nullptr;
+    void BuildWorld() override {
+        auto w = std::make_shared<FakeWorld>();
+        w->scale = this->mWorldScale;
+        w->cb = wcb; w->user = user;
+        this->mWorld = w;
+    }
+    void CreateCharacter(std::shared_ptr<cSimCharacter>& out_char) const override {
+        if (this->mCharType == cScenarioSimChar::eCharDog) out_char = std::shared_ptr<cSimCharacter>(new FakeCharT<cSimDog>());
+        else out_char = std::shared_ptr<cSimCharacter>(new FakeCharT<cSimRaptor>());
+    }
+    FakeChar* fake() { return dynamic_cast<FakeChar*>(this->mChar.get()); }
+    cGroundVar2D* ground() { return static_cast<cGroundVar2D*>(this->mGround.get()); }
+    cTerrainRLCharController* ctrl() { return dynamic_cast<cTerrainRLCharController*>(this->mChar->GetController().get()); }
+    double time() const { return this->mTime; }
+};
+struct FakeScnEval : public FakeScn<cScenarioPoliEval> {};
+struct FakeScnExp : public FakeScn<cScenarioExpMACE> {
+    void CommandRandAction() override { this->mChar->GetController()->CommandAction(ccb(user)); }
+    int tuple_count() const { return mTupleCount; }
+    int cycle_count() const { return mCycleCount; }
+};
+struct RefScn {
+    int mode = 0;
+    std::unique_ptr<FakeScnEval> ev;
+    std::unique_ptr<FakeScnExp> ex;
+    cScenarioSimChar* scn() { return mode == 0 ? static_cast<cScenarioSimChar*>(ev.get()) : static_cast<cScenarioSimChar*>(ex.get()); }
+    FakeChar* fake() { return mode == 0 ? ev->fake() : ex->fake(); }
+    cGroundVar2D* ground() { return mode == 0 ? ev->ground() : ex->ground(); }
+    cTerrainRLCharController* ctrl() { return mode == 0 ? ev->ctrl() : ex->ctrl(); }
+};
+
+extern "C" {
+
+// mode 0: cScenarioPoliEval, 1: cScenarioExpMACE; arg_file as the reference's Main reads it (-arg_file=); extra: further "-key=
+// value" tokens (tuple buffer size, exploration rates).  Seeds the ground and rebuilds it with Reset, as
+// cOptScenarioPoliEval::BuildScenePool does (optimizer/scenarios/OptScenarioPoliEval.cpp:150-160).
+RefScn* ref_scn_create(const char* arg_file, int mode, char** extra, int n_extra, unsigned long seed, world_fn wcb, net_fn ncb, cmd_fn ccb,
+                       void* user) {
+    if (std::getenv("REF_CTRL_DEBUG")) signal(SIGSEGV, ref_segv_handler);
+    g_net_cb = ncb; g_net_user = user;
+    g_reset_loads_pose0 = true;
+    cArgParser parser;
+    parser.AppendArgs(std::string(arg_file));
+    if (n_extra > 0) parser.AppendArgs(extra, n_extra);
+    RefScn* r = new RefScn();
+    r->mode = mode;
+    if (mode == 0) { r->ev.reset(new FakeScnEval()); r->ev->wcb = wcb; r->ev->ccb = ccb; r->ev->user = user; }
+    else { r->ex.reset(new FakeScnExp()); r->ex->wcb = wcb; r->ex->ccb = ccb; r->ex->user = user; }
+    cScenarioSimChar* s = r->scn();
+    s->ParseArgs(parser);
+    s->Init();
+    r->ground()->SeedRand(seed);
+    s->Reset();
+    return r;
+}
+void ref_scn_destroy(RefScn* r) { g_net_cb = nullptr; g_reset_loads_pose0 = false; delete r; }
+void ref_scn_update(RefScn* r, double dt) { r->scn()->Update(dt); }
+// what the test's world callback installs after advancing the physics: pose, velocity, contact bits
+void ref_scn_set_state(RefScn* r, const double* pose, const double* vel, const unsigned char* contact) {
+    FakeChar& ch = *r->fake();
+    const int nd = ch.sim()->GetNumDof(), nj = ch.sim()->GetNumJoints();
+    for (int i = 0; i < nd; ++i) { ch.pose[i] = pose[i]; ch.vel[i] = vel[i]; }
+    for (int j = 0; j < nj; ++j) static_cast<FakePart*>(ch.parts[j].get())->contact = contact[j] != 0;
+}
+void ref_scn_get_state(RefScn* r, double* pose, double* vel, double* tau) {
+    FakeChar& ch = *r->fake();
+    const int nd = ch.sim()->GetNumDof();
+    for (int i = 0; i < nd; ++i) { pose[i] = ch.pose[i]; vel[i] = ch.vel[i]; tau[i] = ch.last_tau[i]; }
+}
+int ref_scn_num_dof(RefScn* r) { return r->fake()->sim()->GetNumDof(); }
+int ref_scn_get_fsm(RefScn* r, double* out) {
+    out[0] = r->ctrl()->GetState(); out[1] = r->ctrl()->GetPhase(); out[2] = r->ctrl()->GetCurrActionID();
+    return 3;
+}
+int ref_scn_has_fallen(RefScn* r) { return r->scn()->HasFallen() ? 1 : 0; }
+double ref_scn_time(RefScn* r) { return r->mode == 0 ? r->ev->time() : r->ex->time(); }
+double ref_scn_sample_height(RefScn* r, double x) { return r->ground()->SampleHeight(tVector(x, 0, 0, 0)); }
+// cScenarioPoliEval: cycles, episodes, average distance, distance log
+void ref_scn_eval_stats(RefScn* r, long* cycles, long* episodes, double* avg_dist) {
+    *cycles = r->ev->GetNumCycles(); *episodes = r->ev->GetNumEpisodes(); *avg_dist = r->ev->GetAvgDist();
+}
+int ref_scn_dist_log(RefScn* r, double* out, int cap) {
+    const auto& log = r->ev->GetDistLog();
+    for (int i = 0; i < (int)log.size() && i < cap; ++i) out[i] = log[i];
+    return (int)log.size();
+}
+// cScenarioExp: tuples recorded so far (total count; the buffer keeps the last `tuple_buffer_size`), cycle count of this episode
+void ref_scn_exp_counts(RefScn* r, long* tuples, long* cycles) { *tuples = r->ex->tuple_count(); *cycles = r->ex->cycle_count(); }
+// tuple `idx` of the ring buffer: reward, flags, state_beg | action | state_end
+int ref_scn_get_tuple(RefScn* r, int idx, double* reward, unsigned* flags, double* row, int cap) {
+    const tExpTuple& t = r->ex->GetTuples()[idx];
+    *reward = t.mReward; *flags = t.mFlags;
+    int k = 0;
+    for (int i = 0; i < (int)t.mStateBeg.size() && k < cap; ++i) row[k++] = t.mStateBeg[i];
+    for (int i = 0; i < (int)t.mAction.size() && k < cap; ++i) row[k++] = t.mAction[i];
+    for (int i = 0; i < (int)t.mStateEnd.size() && k < cap; ++i) row[k++] = t.mStateEnd[i];
+    return k;
+}
 
 }  // extern "C"

@@ -430,3 +430,183 @@ def test_output_offset_scale_matches_reference_code(assets, scene, char_file, ki
     np.testing.assert_allclose(ps, rs, rtol=1e-15, atol=0)
     assert np.all(ro[:3] == -0.5) and np.all(rs[:3] == 2.0)
     ref.ref_ctrl_destroy(h)
+
+
+# ---------------------------------------------------------------------------------------------------- whole scenarios
+SCN_ARGS = {"dog_slopes_mixed": "args/dog_slopes_mixed_args.txt", "goat_cliffs": "args/goat_cliffs_args.txt",
+            "raptor_narrow_gaps": "args/raptor_narrow_gaps_args.txt"}
+# (scene, mode 0 cScenarioPoliEval / 1 cScenarioExpMACE, outer updates, exact segment origin)
+SCN_CASES = [("goat_cliffs", 0, 400, True), ("raptor_narrow_gaps", 0, 400, True), ("dog_slopes_mixed", 0, 200, True),
+             ("dog_slopes_mixed", 0, 200, False), ("dog_slopes_mixed", 1, 250, True), ("goat_cliffs", 1, 250, True),
+             ("raptor_narrow_gaps", 1, 250, True)]
+
+
+@pytest.mark.skipif(not (os.path.exists(REF_CTRL) and os.path.isdir("/root/reference/args")),
+                    reason="oracle/_ref/libref_ctrl.so or the reference arg / data files absent")
+@pytest.mark.parametrize("scene,mode,n_updates,exact_origin", SCN_CASES)
+def test_scenario_matches_reference_code(assets, scene, mode, n_updates, exact_origin):
+    """The reference's OWN scenario classes -- cScenario, cScenarioSimChar, cScenarioPoliEval, cScenarioExp, cScenarioExpMACE,
+    compiled unmodified into oracle/_ref/libref_ctrl.so together with the controller stack, cGroundVar2D, cTerrainGen2D,
+    cArgParser and tExpTuple -- run from the reference's own arg file (args/*_args.txt: character, controller, terrain, step
+    counts, world scale).  Two factory functions are overridden (oracle/ref_ctrl_api.cpp): BuildWorld makes a world whose
+    Update(h) calls back into this test, which advances the ORACLE by one env-step and installs the oracle's pose, velocity and
+    contact bits as the simulation state; CreateCharacter makes the reference's cSimDog / cSimRaptor on the kinematic back end.
+    cNeuralNet::Eval calls back with the input vector the reference built and receives the oracle's network output for it.
+    Everything else is the reference's compiled code: the 20-step loop and its order (world, ground, character, post-substep),
+    terrain streaming and sampling on its own cGroundVar2D, the controller, cycle counting, tuple recording (states, action,
+    reward, flags, warm-up rule, ring buffer), the end-of-update fall test, distance bookkeeping, and Reset (pose0, controller
+    reset, ground rebuild from the seeded generator, spawn height).
+
+    Compared after every env-step: torques and gait state / phase; after every outer update: pose and velocity (i.e. the reset
+    state when the episode ended), scenario time, cycle / episode / tuple counts, average distance; at the end the distance log or
+    every recorded tuple.
+
+    exact_origin: Bullet keeps a terrain segment's position in single precision, so the reference samples heights ~1e-7 m off;
+    the stand-in world can keep the origin in double instead.  With it everything agrees to rounding (1e-10 bound, ~2e-12
+    seen); without it (the reference as it is) the single-precision origin shows up as ~1e-6 relative in the torques.
+
+    The exploration scenario runs with exp_rate = exp_base_rate = 0 and a Boltzmann temperature of 1e-6 (selection = argmax):
+    the reference draws exploration noise from a process-global engine the oracle replaces by counter-based streams, so only
+    the deterministic path can be compared; cScenarioExp::CommandRandAction is overridden to command the oracle's draw."""
+    from pyoracle import Oracle
+    seed = 77
+    ref = C.CDLL(REF_CTRL)
+    ref.ref_world_exact_origin(1 if exact_origin else 0)
+    tol = 1e-10 if exact_origin else 2e-5
+    o = Oracle(os.path.join(assets, scene + ".trlpack"), 1, mode, terrain_seeds=[seed])
+    if mode == 1:
+        o.set_explore(1, 0.0, 1e-6, 0.0)
+    L = o.L
+    L.orc_end_update.argtypes = [C.c_void_p, C.c_int, C.c_double]
+    L.orc_pending_command.argtypes = [C.c_void_p, C.c_int]
+    WFN = C.CFUNCTYPE(None, C.c_double, C.c_void_p)
+    NFN = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double), C.c_int, C.c_void_p)
+    CFN = C.CFUNCTYPE(C.c_int, C.c_void_p)
+    nd = o.ndof
+    DT = 1.0 / 30.0
+    st = dict(h=None, steps=0, worst_tau=0.0, worst_pose=0.0, ended=False, in_update=False, cmp=False, err=None, evals=0)
+
+    def ref_state():
+        pose = np.zeros(nd); vel = np.zeros(nd); tau = np.zeros(nd)
+        ref.ref_scn_get_state(st["h"], _p(pose), _p(vel), _p(tau))
+        return pose, vel, tau
+
+    def compare_step():
+        _, _, tau = ref_state()
+        to = o.last_tau(0)
+        err = np.max(np.abs(tau - to)) / max(1.0, np.max(np.abs(to)))
+        st["worst_tau"] = max(st["worst_tau"], err)
+        f = np.zeros(3)
+        ref.ref_scn_get_fsm(st["h"], _p(f))
+        oc = o.get_ctrl(0)
+        assert int(f[0]) == int(oc[0]) and abs(f[1] - oc[1]) < 1e-9, (st["steps"], f, oc[:3])
+        assert err < tol, (st["steps"], err)
+
+    def world(hh, user):
+        # cWorld::Update(h) of the compiled scenario: the previous env-step's controller output is compared first
+        if st["err"] is not None:
+            return
+        try:
+            if st["cmp"]:
+                compare_step()
+            o.env_step(0, hh)
+            q, qd, _, contact = o.get_state(0)
+            ref.ref_scn_set_state(st["h"], _p(q), _p(qd), _p(contact.astype(np.uint8)))
+            st["steps"] += 1
+            st["cmp"] = True
+        except BaseException as e:          # an exception cannot cross the C frames: keep it for the main loop
+            st["err"] = e
+
+    def net(x, n_in, y, n_out, user):
+        xi = np.ctypeslib.as_array(x, (n_in,)).copy()
+        yo = o.net_eval(xi, n_out)
+        for i in range(n_out):
+            y[i] = yo[i]
+        st["evals"] += 1
+
+    def cmd(user):
+        # cScenarioExp::Reset at the end of an update: the oracle's own end-of-update (and reset) has to come first
+        if st["in_update"] and not st["ended"]:
+            L.orc_end_update(o.h, 0, DT)
+            st["ended"] = True
+        return L.orc_pending_command(o.h, 0)
+
+    wcb, ncb, ccb = WFN(world), NFN(net), CFN(cmd)
+    n_out = 3 * (1 + (o.A - 1))
+    ref.ref_ctrl_set_net_output(o.S, _p(np.zeros(n_out)), _p(np.ones(n_out)), n_out)      # sizes for cNNController::LoadNet's checks
+    ref.ref_scn_create.restype = C.c_void_p
+    ref.ref_scn_create.argtypes = [C.c_char_p, C.c_int, C.c_void_p, C.c_int, C.c_ulong, WFN, NFN, CFN, C.c_void_p]
+    ref.ref_scn_update.argtypes = [C.c_void_p, C.c_double]
+    ref.ref_scn_time.restype = C.c_double
+    extra = [b"-exp_rate=", b"0", b"-exp_base_rate=", b"0", b"-exp_temp=", b"0.000001", b"-tuple_buffer_size=", b"4096"]
+    arr = (C.c_char_p * len(extra))(*extra)
+    cwd = os.getcwd()
+    os.chdir("/root/reference")                       # the arg file names its data files relative to the reference's root
+    try:
+        h = ref.ref_scn_create(SCN_ARGS[scene].encode(), mode, arr, len(extra), seed, wcb, ncb, ccb, None)
+    finally:
+        os.chdir(cwd)
+    assert h
+    h = C.c_void_p(h)
+    st["h"] = h
+    try:
+        assert ref.ref_scn_num_dof(h) == nd
+        pose, vel, _ = ref_state()
+        q, qd, _, _ = o.get_state(0)
+        assert np.max(np.abs(pose - q)) < tol and np.max(np.abs(vel - qd)) < tol      # spawn state on the first terrain
+        resets = 0
+        for k in range(n_updates):
+            st["in_update"], st["ended"] = True, False
+            ref.ref_scn_update(h, DT)
+            if st["err"] is not None:
+                raise st["err"]
+            if not st["ended"]:
+                L.orc_end_update(o.h, 0, DT)
+            st["in_update"] = False
+            compare_step()
+            st["cmp"] = False
+            pose, vel, _ = ref_state()
+            q, qd, _, _ = o.get_state(0)
+            d = max(np.max(np.abs(pose - q)), np.max(np.abs(vel - qd)))
+            st["worst_pose"] = max(st["worst_pose"], d)
+            assert d < tol, (k, d)
+            t_ref = ref.ref_scn_time(h)
+            resets += t_ref == 0.0
+            if mode == 0:
+                cy, ep, ad = C.c_long(), C.c_long(), C.c_double()
+                ref.ref_scn_eval_stats(h, C.byref(cy), C.byref(ep), C.byref(ad))
+                es = o.eval_stats()
+                assert (cy.value, ep.value) == (es["cycles"], es["episodes"]), (k, cy.value, ep.value, es)
+                assert abs(ad.value - es["avg_dist"]) <= tol * max(1.0, abs(ad.value)), (k, ad.value, es)
+            else:
+                tc, cy = C.c_long(), C.c_long()
+                ref.ref_scn_exp_counts(h, C.byref(tc), C.byref(cy))
+                assert tc.value == L.orc_num_tuples(o.h), (k, tc.value, L.orc_num_tuples(o.h))
+                assert cy.value == int(o.get_ctrl(0)[-2]), (k, cy.value)
+        assert st["steps"] == 20 * n_updates and st["evals"] >= 5
+        if mode == 0:
+            log = np.zeros(4096)
+            n = ref.ref_scn_dist_log(h, _p(log), 4096)
+            olog = o.dist_log(0)
+            assert n == len(olog)
+            assert np.allclose(log[:n], olog, rtol=0, atol=tol)
+            if scene != "dog_slopes_mixed":
+                assert n >= 1 and resets >= 1             # episodes ended by the reference's own fall test
+            summary = f"{es['cycles']} cycles, {n} episodes"
+        else:
+            rows, flags, _ = o.tuples()
+            assert len(rows) >= 5
+            W = o.S + o.A + o.S
+            worst = 0.0
+            for i in range(len(rows)):
+                r, fl, row = C.c_double(), C.c_uint(), np.zeros(W)
+                assert ref.ref_scn_get_tuple(h, i, C.byref(r), C.byref(fl), _p(row), W) == W
+                assert fl.value == int(flags[i]), (i, fl.value, flags[i])
+                worst = max(worst, abs(r.value - rows[i, 0]), np.max(np.abs(row - rows[i, 1:])))
+            assert worst < tol, worst
+            summary = f"{len(rows)} tuples ({int(np.sum((flags & 1) != 0))} ending in a fall), worst tuple difference {worst:.1e}"
+        print(f"{scene} mode {mode} {'exact' if exact_origin else 'float'} origin: {st['steps']} env-steps, {resets} resets, {summary}; "
+              f"worst torque difference {st['worst_tau']:.1e} (relative), worst pose difference {st['worst_pose']:.1e}")
+    finally:
+        ref.ref_scn_destroy(h)
+        ref.ref_world_exact_origin(0)
