@@ -297,6 +297,26 @@ void orc_trainer_eval_batch(OrcTrainer* t, int target, const double* X, int B, d
     std::memcpy(Y, y.data(), y.size() * 8);
 }
 
+// ---- network-level operations of the trainer, for the pinning test that runs the reference's compiled cMACETrainer on top of them
+// (its cNeuralNet calls land here), and the switch that makes the restated trainer draw like the reference
+void orc_trainer_use_ref_rand(OrcTrainer* t, unsigned long seed) { t->tr.use_ref_rand = true; t->tr.ref_rand.seed(seed); }
+double orc_trainer_solver_step(OrcTrainer* t, const double* X, const double* Y) {
+    const int B = t->tr.P.batch;
+    std::vector<double> x(X, X + (size_t)B * t->tr.S), y(Y, Y + (size_t)B * t->tr.net.tp.n_out);
+    return t->tr.solver_step(x, y);
+}
+void orc_trainer_copy_to_target(OrcTrainer* t) {
+    auto& tr = t->tr;
+    tr.target.theta = tr.net.theta;
+    tr.target.in_off = tr.net.in_off; tr.target.in_scale = tr.net.in_scale;
+    tr.target.out_off = tr.net.out_off; tr.target.out_scale = tr.net.out_scale;
+}
+void orc_trainer_set_input_offset_scale(OrcTrainer* t, int target, const double* off, const double* scale) {
+    auto& n = target ? t->tr.target : t->tr.net;
+    for (int i = 0; i < t->tr.S; ++i) { n.in_off[i] = off[i]; n.in_scale[i] = scale[i]; }
+}
+void orc_calc_offset_scale(const double* X, int n, int S, double* off, double* scale) { MaceTrainer::calc_offset_scale(X, n, S, off, scale); }
+
 // ---------------------------------------------------------------------------------------- generator-level terrain / RNG probes
 // (compared bit for bit with the reference's own cTerrainGen2D / cRand compiled into oracle/_ref, tests/test_ref_pinning_cpu.py)
 int orc_terrain_build(int type, const double* params40, unsigned long seed, double width, float* out, int cap, double* total_w) {

@@ -259,6 +259,12 @@ struct MaceTrainer {
     long long total = 0;
     std::vector<int> critic_buf, actor_buf, actor_batch;
     CounterRng rng;
+    // pinning mode (tests/test_ref_pinning_cpu.py): draw the sample indices like the reference does -- cMathUtil::RandInt on its
+    // process-global cRand (util/MathUtil.cpp, util/Rand.cpp:48-61), restated in terrain.h's Rand -- so that the compiled
+    // cMACETrainer and this restatement can be compared draw for draw
+    bool use_ref_rand = false;
+    Rand ref_rand;
+    int draw(int n) { return use_ref_rand ? ref_rand.rand_int(0, n) : rng.rand_int(0, n); }
     double last_critic_loss = 0, last_actor_loss = 0;
     std::vector<int> last_critic_ids, last_actor_ids;       // tuples of the most recent critic / actor solver step (for tests)
 
@@ -363,7 +369,7 @@ struct MaceTrainer {
         const int B = P.batch, no = net.tp.n_out;
         if ((int)critic_buf.size() < B) return false;
         std::vector<int> ids(B);
-        for (int i = 0; i < B; ++i) ids[i] = critic_buf[rng.rand_int(0, (int)critic_buf.size())];
+        for (int i = 0; i < B; ++i) ids[i] = critic_buf[draw((int)critic_buf.size())];
         std::vector<double> X((size_t)B * S), Y, q;
         for (int i = 0; i < B; ++i)
             for (int j = 0; j < S; ++j) X[(size_t)i * S + j] = row(ids[i])[1 + j];
@@ -385,7 +391,7 @@ struct MaceTrainer {
             const int ns = std::min(B, n_exp);
             std::vector<int> cand;
             for (int i = 0; i < ns; ++i) {
-                int t = actor_buf[rng.rand_int(0, n_exp)];
+                int t = actor_buf[draw(n_exp)];
                 bool contains = std::find(actor_batch.begin(), actor_batch.end(), t) != actor_batch.end() ||
                                 std::find(cand.begin(), cand.end(), t) != cand.end();
                 if (!contains) cand.push_back(t);
@@ -414,18 +420,24 @@ struct MaceTrainer {
         }
     }
     // cNeuralNet::CalcOffsetScale over the replay memory (learning/NeuralNet.cpp:280-313, NeuralNetTrainer.cpp:696-719)
-    void update_offset_scale() {
+    static void calc_offset_scale(const double* X, int n, int S, double* off, double* scale) {
         std::vector<double> mean(S, 0.0), var(S, 0.0);
-        const double norm = 1.0 / num;
-        for (int t = 0; t < num; ++t)
-            for (int j = 0; j < S; ++j) mean[j] += norm * (double)row(t)[1 + j];
-        for (int t = 0; t < num; ++t)
-            for (int j = 0; j < S; ++j) { double d = (double)row(t)[1 + j] - mean[j]; var[j] += norm * d * d; }
+        const double norm = 1.0 / n;
+        for (int t = 0; t < n; ++t)
+            for (int j = 0; j < S; ++j) mean[j] += norm * X[(size_t)t * S + j];
+        for (int t = 0; t < n; ++t)
+            for (int j = 0; j < S; ++j) { double d = X[(size_t)t * S + j] - mean[j]; var[j] += norm * d * d; }
         for (int j = 0; j < S; ++j) {
             double sd = std::sqrt(var[j]);
-            net.in_off[j] = -mean[j];
-            net.in_scale[j] = sd == 0 ? 0 : 1.0 / sd;
+            off[j] = -mean[j];
+            scale[j] = sd == 0 ? 0 : 1.0 / sd;
         }
+    }
+    void update_offset_scale() {
+        std::vector<double> X((size_t)num * S);
+        for (int t = 0; t < num; ++t)
+            for (int j = 0; j < S; ++j) X[(size_t)t * S + j] = (double)row(t)[1 + j];
+        calc_offset_scale(X.data(), num, S, net.in_off.data(), net.in_scale.data());
         target.in_off = net.in_off; target.in_scale = net.in_scale;
     }
     // cNeuralNetTrainer::Train -> UpdateStage / ApplySteps / cMACETrainer::Step

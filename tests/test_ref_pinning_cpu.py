@@ -610,3 +610,150 @@ def test_scenario_matches_reference_code(assets, scene, mode, n_updates, exact_o
     finally:
         ref.ref_scn_destroy(h)
         ref.ref_world_exact_origin(0)
+
+
+# ---------------------------------------------------------------------------------------------------- the MACE trainer
+REF_TRAIN = os.path.join(HERE, "..", "oracle", "_ref", "libref_train.so")
+
+
+@pytest.mark.skipif(not os.path.exists(REF_TRAIN), reason="oracle/_ref/libref_train.so not built")
+def test_mace_trainer_matches_reference_code(assets):
+    """The reference's OWN trainer -- cTrainerInterface, cNeuralNetTrainer, cMACETrainer, cNeuralNetLearner, tExpTuple, with
+    cMathUtil / cRand behind the sampling, compiled unmodified into oracle/_ref/libref_train.so -- is driven the way
+    cScenarioTrain drives it (cNeuralNetLearner::Train(tuples) per full tuple buffer).  Its cNeuralNet (Caffe in the reference) is
+    a stand-in whose EvalBatch / Train / CopyModel / CalcOffsetScale / SetInputOffsetScale call back into this test, which answers
+    with the network-level operations of a first oracle trainer object (forward pass, one solver step on a problem, copy to the
+    target).  A second oracle trainer object runs oracle/trainer.h's restatement of the whole algorithm independently on the same
+    tuples, drawing its sample indices from the restated cRand (seeded like cMathUtil::SeedRand).
+
+    Everything the reference trainer does itself is therefore compared as compiled: replay memory (float rows, ring buffer with
+    wrap-around, flag buffer), critic / actor index buffers incl. swap-removal on overwrite, minibatch sampling (order and number
+    of draws), target values (reward normalisation, fail flag, discounted max over the target net's critic outputs), the problem
+    matrices handed to the solver, the positive-temporal-difference filter and FIFO of the actor batch buffer, the initial
+    stage (input offset / scale from the first samples), iteration counters, target refresh every `freeze_target_iters`.
+    Since both sides use the same network arithmetic, the weights must come out bit-identical -- any difference in a sampled id,
+    a label or the order of solver steps would show."""
+    from pyoracle import OracleTrainer
+    pack = os.path.join(assets, "dog_slopes_mixed.trlpack")
+    ref = C.CDLL(REF_TRAIN)
+    kw = dict(replay_cap=400, num_init_samples=96, num_steps_per_iter=2, freeze_target_iters=3, init_input_offset_scale=1, seed=11)
+    eng = OracleTrainer(pack, **kw)      # the network under the compiled reference trainer
+    orc = OracleTrainer(pack, **kw)      # the restated trainer, on its own
+    L = orc.L
+    L.orc_trainer_use_ref_rand.argtypes = [C.c_void_p, C.c_ulong]
+    L.orc_trainer_use_ref_rand(orc.h, 4242)
+    L.orc_trainer_solver_step.restype = C.c_double
+    S, no, W = orc.n_in, orc.n_out, orc.W
+    A = W - 1 - 2 * S
+    B, n_frags, frag = 32, 3, A - 1
+    DP = C.POINTER(C.c_double)
+    EV = C.CFUNCTYPE(None, C.c_int, DP, C.c_int, DP, C.c_void_p)
+    TR = C.CFUNCTYPE(None, C.c_int, DP, DP, C.c_int, C.c_void_p)
+    CP = C.CFUNCTYPE(None, C.c_int, C.c_int, C.c_void_p)
+    CO = C.CFUNCTYPE(None, DP, C.c_int, DP, DP, C.c_void_p)
+    SO = C.CFUNCTYPE(None, C.c_int, DP, DP, C.c_void_p)
+    log = dict(evals=0, trains=0, copies=[], calc=0, set=[], err=None)
+
+    def guarded(fn):
+        def w(*a):
+            try:
+                fn(*a)
+            except BaseException as e:       # cannot cross the C frames
+                log["err"] = e
+        return w
+
+    def ev(net, X, Bn, Y, u):
+        x = np.ctypeslib.as_array(X, (Bn, S)).copy()
+        y = np.zeros((Bn, no))
+        L.orc_trainer_eval_batch(eng.h, 1 if net == 1 else 0, _p(x), Bn, _p(y))
+        np.ctypeslib.as_array(Y, (Bn, no))[:] = y
+        log["evals"] += 1
+
+    def tr(net, X, Y, Bn, u):
+        assert net == 0 and Bn == B
+        x = np.ctypeslib.as_array(X, (Bn, S)).copy()
+        y = np.ctypeslib.as_array(Y, (Bn, no)).copy()
+        L.orc_trainer_solver_step(eng.h, _p(x), _p(y))
+        log["trains"] += 1
+
+    def cp(dst, src, u):
+        log["copies"].append((dst, src))
+        if (dst, src) == (1, 0):
+            L.orc_trainer_copy_to_target(eng.h)
+
+    def co(X, n, off, sc, u):
+        x = np.ctypeslib.as_array(X, (n, S)).copy()
+        o, s = np.zeros(S), np.zeros(S)
+        L.orc_calc_offset_scale(_p(x), n, S, _p(o), _p(s))
+        np.ctypeslib.as_array(off, (S,))[:] = o
+        np.ctypeslib.as_array(sc, (S,))[:] = s
+        log["calc"] += 1
+
+    def so(net, off, sc, u):
+        o = np.ctypeslib.as_array(off, (S,)).copy()
+        s = np.ctypeslib.as_array(sc, (S,)).copy()
+        if net in (0, 1):
+            L.orc_trainer_set_input_offset_scale(eng.h, net, _p(o), _p(s))
+        log["set"].append(net)
+
+    cbs = (EV(guarded(ev)), TR(guarded(tr)), CP(guarded(cp)), CO(guarded(co)), SO(guarded(so)))
+    p = np.array([S, no, B, n_frags, frag, kw["replay_cap"], kw["num_init_samples"], kw["num_steps_per_iter"],
+                  kw["freeze_target_iters"], 0.9, kw["init_input_offset_scale"], 4242], float)
+    ref.ref_trainer_create.restype = C.c_void_p
+    ref.ref_trainer_create.argtypes = [C.c_void_p, EV, TR, CP, CO, SO, C.c_void_p]
+    ref.ref_trainer_learn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    h = C.c_void_p(ref.ref_trainer_create(_p(p), *cbs, None))
+    assert log["copies"] == [(1, 0)]                  # cMACETrainer::BuildNetPool: the target starts as a copy
+    assert ref.ref_trainer_width(h) == W
+    rng = np.random.default_rng(0)
+    in_off, in_scale = orc.get("in_off"), orc.get("in_scale")
+
+    def make(n):
+        rows = np.zeros((n, W))
+        rows[:, 0] = rng.uniform(0, 1, n)
+        for k in (1, 1 + S + A):
+            rows[:, k:k + S] = rng.normal(size=(n, S)) / np.where(in_scale == 0, 1.0, in_scale) - in_off
+        rows[:, 1 + S] = rng.integers(0, n_frags, n)
+        rows[:, 2 + S:1 + S + A] = rng.normal(size=(n, frag))
+        fl = np.zeros(n, np.uint32)
+        u = rng.uniform(size=n)
+        fl[u < 0.1] |= 1                    # cMACETrainer::eFlagFail
+        fl[(u > 0.3) & (u < 0.5)] |= 2      # eFlagExpCritic
+        fl[(u > 0.4) & (u < 0.8)] |= 4      # eFlagExpActor
+        return rows, fl
+
+    try:
+        n_calls = 22
+        for k in range(n_calls):
+            rows, fl = make(32)
+            ref.ref_trainer_learn(h, _p(rows), _p(fl), 32)
+            if log["err"] is not None:
+                raise log["err"]
+            orc.add_tuples(rows, fl)
+            orc.train()
+            c = (C.c_long * 8)()
+            ref.ref_trainer_counters(h, c)
+            oc = orc.counters()
+            assert (c[0], c[1], c[2], c[3], c[4], c[5]) == (oc["iter"], oc["actor_iter"], oc["stage"], oc["num"], oc["head"], oc["total"]), (k, list(c), oc)
+            assert (c[6], c[7]) == (c[0], c[5])                       # the learner mirrors the trainer's iteration / tuple counts
+            for which, name in enumerate(("critic", "actor", "actor_batch")):
+                buf = np.zeros(4096, np.int32)
+                n = ref.ref_trainer_list(h, which, _p(buf), 4096)
+                ol = orc.lists(name)
+                assert n == len(ol) and np.array_equal(buf[:n], ol), (k, name)
+            assert np.array_equal(eng.get("theta"), orc.get("theta")), (k, np.max(np.abs(eng.get("theta") - orc.get("theta"))))
+        assert np.array_equal(eng.get("target"), orc.get("target"))
+        assert np.array_equal(eng.get("in_off"), orc.get("in_off")) and np.array_equal(eng.get("in_scale"), orc.get("in_scale"))
+        ids = np.arange(kw["replay_cap"], dtype=np.int32)
+        rr = np.zeros((len(ids), W), np.float32)
+        rf = np.zeros(len(ids), np.int32)
+        ref.ref_trainer_rows(h, _p(ids), len(ids), _p(rr), _p(rf))
+        orows, oflags = orc.rows(ids)
+        assert np.array_equal(rr, orows) and np.array_equal(rf, oflags)
+        oc = orc.counters()
+        assert oc["total"] == 32 * n_calls > kw["replay_cap"] and oc["iter"] >= 15 and oc["actor_iter"] >= 5      # wrapped, trained
+        assert log["calc"] == 1 and log["set"] == [0, 1] and log["copies"].count((1, 0)) >= 4
+        print(f"compiled cMACETrainer vs oracle/trainer.h: {oc['iter']} iterations ({log['trains']} solver steps, {oc['actor_iter']} of "
+              f"them actor steps), {oc['total']} tuples through a {kw['replay_cap']}-row replay memory, weights bit-identical")
+    finally:
+        ref.ref_trainer_destroy(h)
