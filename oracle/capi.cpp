@@ -13,6 +13,7 @@ struct OrcBatch {
     Scene scene;
     std::vector<std::unique_ptr<Env>> envs;
     std::string err;
+    Rand ref_rand;      // see orc_use_ref_rand
 };
 
 static thread_local std::string g_err;
@@ -66,6 +67,16 @@ void orc_reset(OrcBatch* b, int env) { b->envs[env]->reset(); }
 // scenario-level pinning (tests/test_ref_pinning_cpu.py): the end-of-update tail on its own, and the action id CommandRandAction
 // queued at the last reset (-1: none pending)
 void orc_end_update(OrcBatch* b, int env, double dt) { b->envs[env]->time += dt; b->envs[env]->end_update(); }
+// every exploration draw of every env from one restated cRand (the reference has one process-global engine), then a fresh
+// terrain stream + reset for env `env` (what cOptScenarioPoliEval::BuildScenePool / the pinning harness do after Init)
+void orc_use_ref_rand(OrcBatch* b, unsigned long seed) {
+    b->ref_rand.seed(seed);
+    for (auto& e : b->envs) e->rng.ref = &b->ref_rand;
+}
+void orc_reseed_reset(OrcBatch* b, int env, unsigned long terrain_seed) {
+    b->envs[env]->ground.rand.seed(terrain_seed);
+    b->envs[env]->reset();
+}
 int orc_pending_command(OrcBatch* b, int env) { auto& c = b->envs[env]->commands; return c.empty() ? -1 : c.back(); }
 
 void orc_get_state(OrcBatch* b, int env, double* q, double* qd, double* tau_held, uint8_t* contact) {

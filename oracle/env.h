@@ -93,6 +93,9 @@ inline double wrap_pi(double a) {
 // threads, util/MathUtil.cpp:4 -- only distributional parity is meaningful; ours is deterministic per env)
 struct CounterRng {
     uint64_t key = 0, ctr = 0;
+    // pinning mode (tests/test_ref_pinning_cpu.py): draw from the restated cRand instead (terrain.h's Rand, the engine behind the
+    // reference's process-global cMathUtil::Rand*), so that exploration can be compared draw for draw with the compiled reference
+    Rand* ref = nullptr;
     static uint64_t mix(uint64_t z) {
         z += 0x9E3779B97F4A7C15ull;
         z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
@@ -101,14 +104,16 @@ struct CounterRng {
     }
     void seed(uint64_t s, uint64_t stream) { key = mix(s ^ mix(stream)); ctr = 0; }
     uint64_t next() { return mix(key + (ctr++) * 0xD1342543DE82EF95ull); }
-    double uniform() { return (double)(next() >> 11) * (1.0 / 9007199254740992.0); }
+    double uniform() { return ref ? ref->rand_double() : (double)(next() >> 11) * (1.0 / 9007199254740992.0); }
     int rand_int(int mn, int mx) {  // cRand::RandInt(min, max)
+        if (ref) return ref->rand_int(mn, mx);
         if (mn == mx) return mn;
         int r = (int)(next() >> 33);
         return mn + r % (mx - mn);
     }
-    bool flip_coin() { return uniform() < 0.5; }
+    bool flip_coin() { return ref ? ref->flip_coin() : uniform() < 0.5; }
     double normal() {
+        if (ref) return ref->nd(ref->gen);          // cRand::RandDoubleNorm(0, 1)
         double u1 = 1.0 - uniform(), u2 = uniform();
         return std::sqrt(-2.0 * std::log(u1)) * std::cos(6.283185307179586476925 * u2);
     }

@@ -504,6 +504,7 @@ double ref_ground_sample(RefGround* g, double x) { return g->ground.SampleHeight
 // fall handling and Reset -- runs as compiled.  cScenarioExp::CommandRandAction draws from the reference's process-global random
 // engine; the override commands the action the test names (the oracle's own draw) instead.
 typedef int (*cmd_fn)(void* user);
+extern cRand g_math_util_rand asm("_ZN9cMathUtil5gRandE");      // cMathUtil::gRand (a private static member of the reference class)
 template <typename Base>
 struct FakeScn : public Base {
     world_fn wcb = nullptr;
@@ -526,7 +527,10 @@ struct FakeScn : public Base {
 };
 struct FakeScnEval : public FakeScn<cScenarioPoliEval> {};
 struct FakeScnExp : public FakeScn<cScenarioExpMACE> {
-    void CommandRandAction() override { this->mChar->GetController()->CommandAction(ccb(user)); }
+    void CommandRandAction() override {
+        if (ccb) this->mChar->GetController()->CommandAction(ccb(user));
+        else cScenarioExpMACE::CommandRandAction();          // draws from cMathUtil's engine (ref_scn_create seeds it)
+    }
     int tuple_count() const { return mTupleCount; }
     int cycle_count() const { return mCycleCount; }
 };
@@ -543,10 +547,10 @@ struct RefScn {
 extern "C" {
 
 // mode 0: cScenarioPoliEval, 1: cScenarioExpMACE; arg_file as the reference's Main reads it (-arg_file=); extra: further "-key=
-// value" tokens (tuple buffer size, exploration rates).  Seeds the ground and rebuilds it with Reset, as
+// value" tokens (tuple buffer size, exploration rates); rand_seed != 0: seed cMathUtil's process-global engine after Init.  Seeds the ground and rebuilds it with Reset, as
 // cOptScenarioPoliEval::BuildScenePool does (optimizer/scenarios/OptScenarioPoliEval.cpp:150-160).
 RefScn* ref_scn_create(const char* arg_file, int mode, char** extra, int n_extra, unsigned long seed, world_fn wcb, net_fn ncb, cmd_fn ccb,
-                       void* user) {
+                       void* user, unsigned long rand_seed) {
     if (std::getenv("REF_CTRL_DEBUG")) signal(SIGSEGV, ref_segv_handler);
     g_net_cb = ncb; g_net_user = user;
     g_reset_loads_pose0 = true;
@@ -561,6 +565,10 @@ RefScn* ref_scn_create(const char* arg_file, int mode, char** extra, int n_extra
     s->ParseArgs(parser);
     s->Init();
     r->ground()->SeedRand(seed);
+    if (rand_seed) {                                     // the engine behind every cMathUtil::Rand* call (exploration, random commands)
+        g_math_util_rand = cRand();                      // a fresh object: cRand::Seed re-seeds the engine but leaves the normal distribution's cached value
+        cMathUtil::SeedRand(rand_seed);
+    }
     s->Reset();
     return r;
 }

@@ -435,10 +435,11 @@ def test_output_offset_scale_matches_reference_code(assets, scene, char_file, ki
 # ---------------------------------------------------------------------------------------------------- whole scenarios
 SCN_ARGS = {"dog_slopes_mixed": "args/dog_slopes_mixed_args.txt", "goat_cliffs": "args/goat_cliffs_args.txt",
             "raptor_narrow_gaps": "args/raptor_narrow_gaps_args.txt"}
-# (scene, mode 0 cScenarioPoliEval / 1 cScenarioExpMACE, outer updates, exact segment origin)
+# (scene, mode 0 cScenarioPoliEval / 1 cScenarioExpMACE / 2 cScenarioExpMACE with exploration on, outer updates, exact segment origin)
 SCN_CASES = [("goat_cliffs", 0, 400, True), ("raptor_narrow_gaps", 0, 400, True), ("dog_slopes_mixed", 0, 200, True),
              ("dog_slopes_mixed", 0, 200, False), ("dog_slopes_mixed", 1, 250, True), ("goat_cliffs", 1, 250, True),
-             ("raptor_narrow_gaps", 1, 250, True)]
+             ("raptor_narrow_gaps", 1, 250, True), ("dog_slopes_mixed", 2, 400, True), ("goat_cliffs", 2, 400, True),
+             ("raptor_narrow_gaps", 2, 400, True)]
 
 
 @pytest.mark.skipif(not (os.path.exists(REF_CTRL) and os.path.isdir("/root/reference/args")),
@@ -465,18 +466,31 @@ def test_scenario_matches_reference_code(assets, scene, mode, n_updates, exact_o
     the stand-in world can keep the origin in double instead.  With it everything agrees to rounding (1e-10 bound, ~2e-12
     seen); without it (the reference as it is) the single-precision origin shows up as ~1e-6 relative in the torques.
 
-    The exploration scenario runs with exp_rate = exp_base_rate = 0 and a Boltzmann temperature of 1e-6 (selection = argmax):
-    the reference draws exploration noise from a process-global engine the oracle replaces by counter-based streams, so only
-    the deterministic path can be compared; cScenarioExp::CommandRandAction is overridden to command the oracle's draw."""
-    from pyoracle import Oracle
+    Mode 1 runs the exploration scenario with exp_rate = exp_base_rate = 0 and a Boltzmann temperature of 1e-6 (selection =
+    argmax), cScenarioExp::CommandRandAction overridden to command the oracle's draw: the deterministic path, with the oracle's
+    counter-based random streams as shipped.
+    Mode 2 turns exploration ON (exp_rate 0.3, temperature 0.1, base-action rate 0.05): the reference draws from its
+    process-global cMathUtil engine (seeded after Init), the oracle -- for this test -- from the restated cRand seeded alike, so
+    random commands, random base actions (incl. the fragment assignment draws), Boltzmann actor selection, exploration noise and
+    the ExpCritic / ExpActor flags are compared draw for draw (the product replaces the engine by counter-based streams per
+    environment -- the reference's is shared by all threads -- but keeps this order and arithmetic)."""
+    from pyoracle import Oracle, OracleTrainer
     seed = 77
+    explore = mode == 2
+    mode = min(mode, 1)
     ref = C.CDLL(REF_CTRL)
     ref.ref_world_exact_origin(1 if exact_origin else 0)
     tol = 1e-10 if exact_origin else 2e-5
     o = Oracle(os.path.join(assets, scene + ".trlpack"), 1, mode, terrain_seeds=[seed])
-    if mode == 1:
-        o.set_explore(1, 0.0, 1e-6, 0.0)
     L = o.L
+    if explore:
+        o.set_explore(1, 0.3, 0.1, 0.05)
+        L.orc_use_ref_rand.argtypes = [C.c_void_p, C.c_ulong]
+        L.orc_reseed_reset.argtypes = [C.c_void_p, C.c_int, C.c_ulong]
+        L.orc_use_ref_rand(o.h, 999)
+        L.orc_reseed_reset(o.h, 0, seed)
+    elif mode == 1:
+        o.set_explore(1, 0.0, 1e-6, 0.0)
     L.orc_end_update.argtypes = [C.c_void_p, C.c_int, C.c_double]
     L.orc_pending_command.argtypes = [C.c_void_p, C.c_int]
     WFN = C.CFUNCTYPE(None, C.c_double, C.c_void_p)
@@ -533,17 +547,21 @@ def test_scenario_matches_reference_code(assets, scene, mode, n_updates, exact_o
 
     wcb, ncb, ccb = WFN(world), NFN(net), CFN(cmd)
     n_out = 3 * (1 + (o.A - 1))
-    ref.ref_ctrl_set_net_output(o.S, _p(np.zeros(n_out)), _p(np.ones(n_out)), n_out)      # sizes for cNNController::LoadNet's checks
+    out_scale = np.ascontiguousarray(OracleTrainer(os.path.join(assets, scene + ".trlpack")).get("out_scale"))
+    ref.ref_ctrl_set_net_output(o.S, _p(np.zeros(n_out)), _p(out_scale), n_out)   # sizes for cNNController::LoadNet's checks; noise scale
     ref.ref_scn_create.restype = C.c_void_p
-    ref.ref_scn_create.argtypes = [C.c_char_p, C.c_int, C.c_void_p, C.c_int, C.c_ulong, WFN, NFN, CFN, C.c_void_p]
+    ref.ref_scn_create.argtypes = [C.c_char_p, C.c_int, C.c_void_p, C.c_int, C.c_ulong, WFN, NFN, CFN, C.c_void_p, C.c_ulong]
     ref.ref_scn_update.argtypes = [C.c_void_p, C.c_double]
     ref.ref_scn_time.restype = C.c_double
     extra = [b"-exp_rate=", b"0", b"-exp_base_rate=", b"0", b"-exp_temp=", b"0.000001", b"-tuple_buffer_size=", b"4096"]
+    if explore:
+        extra = [b"-exp_rate=", b"0.3", b"-exp_base_rate=", b"0.05", b"-exp_temp=", b"0.1", b"-tuple_buffer_size=", b"4096"]
     arr = (C.c_char_p * len(extra))(*extra)
     cwd = os.getcwd()
     os.chdir("/root/reference")                       # the arg file names its data files relative to the reference's root
     try:
-        h = ref.ref_scn_create(SCN_ARGS[scene].encode(), mode, arr, len(extra), seed, wcb, ncb, ccb, None)
+        h = ref.ref_scn_create(SCN_ARGS[scene].encode(), mode, arr, len(extra), seed, wcb, ncb,
+                               C.cast(None, CFN) if explore else ccb, None, 999 if explore else 0)
     finally:
         os.chdir(cwd)
     assert h
@@ -604,8 +622,11 @@ def test_scenario_matches_reference_code(assets, scene, mode, n_updates, exact_o
                 assert fl.value == int(flags[i]), (i, fl.value, flags[i])
                 worst = max(worst, abs(r.value - rows[i, 0]), np.max(np.abs(row - rows[i, 1:])))
             assert worst < tol, worst
-            summary = f"{len(rows)} tuples ({int(np.sum((flags & 1) != 0))} ending in a fall), worst tuple difference {worst:.1e}"
-        print(f"{scene} mode {mode} {'exact' if exact_origin else 'float'} origin: {st['steps']} env-steps, {resets} resets, {summary}; "
+            if explore:                                   # every flag combination the trainer distinguishes was produced
+                assert np.any(flags & 2) and np.any(flags & 4) and np.any((flags & 6) == 6), flags
+            summary = (f"{len(rows)} tuples ({int(np.sum((flags & 1) != 0))} ending in a fall, {int(np.sum((flags & 2) != 0))} ExpCritic, "
+                       f"{int(np.sum((flags & 4) != 0))} ExpActor), worst tuple difference {worst:.1e}")
+        print(f"{scene} mode {mode}{' exploring' if explore else ''} {'exact' if exact_origin else 'float'} origin: {st['steps']} env-steps, {resets} resets, {summary}; "
               f"worst torque difference {st['worst_tau']:.1e} (relative), worst pose difference {st['worst_pose']:.1e}")
     finally:
         ref.ref_scn_destroy(h)
