@@ -36,6 +36,7 @@
 #include "sim/SimRaptor.h"
 #include "scenarios/ScenarioExpMACE.h"
 #include "scenarios/ScenarioPoliEval.h"
+#include "scenarios/ScenarioTrainMACE.h"
 #include "util/ArgParser.h"
 
 extern "C" void ref_abort_stub() {
@@ -317,54 +318,8 @@ struct FakeGroundVar : public cGroundVar2D {
     bool flipped() const { return mFlipSeg; }
 };
 
-// ---- cNeuralNet: what the controllers ask of it; Eval returns the output vector the test installed for the current decision
-static Eigen::VectorXd g_net_output;
-static int g_net_in = 0, g_net_out = 0;
-static Eigen::VectorXd g_out_scale;
-cNeuralNet::cNeuralNet() {}
-cNeuralNet::~cNeuralNet() {}
-void cNeuralNet::Clear() {}
-void cNeuralNet::LoadNet(const std::string&) {}
-void cNeuralNet::LoadModel(const std::string&) {}
-void cNeuralNet::LoadScale(const std::string&) {}
-void cNeuralNet::OutputModel(const std::string&) const {}
-void cNeuralNet::CopyModel(const cNeuralNet&) {}
-bool cNeuralNet::HasNet() const { return g_net_out > 0; }
-bool cNeuralNet::HasLayer(const std::string) const { return false; }
-int cNeuralNet::GetInputSize() const { return g_net_in; }
-int cNeuralNet::GetOutputSize() const { return g_net_out; }
-const Eigen::VectorXd& cNeuralNet::GetOutputScale() const { return g_out_scale; }
-typedef void (*net_fn)(const double* x, int n_in, double* y, int n_out, void* user);
-static net_fn g_net_cb = nullptr;          // scenario pin: the test evaluates the network (the oracle's) on the input the reference built
-static void* g_net_user = nullptr;
-void cNeuralNet::Eval(const Eigen::VectorXd& x, Eigen::VectorXd& out_y) const {
-    if (!g_net_cb) { out_y = g_net_output; return; }
-    std::vector<double> xi(x.size()), yo(g_net_out);
-    for (int i = 0; i < (int)x.size(); ++i) xi[i] = x[i];
-    g_net_cb(xi.data(), (int)xi.size(), yo.data(), g_net_out, g_net_user);
-    out_y.resize(g_net_out);
-    for (int i = 0; i < g_net_out; ++i) out_y[i] = yo[i];
-}
-void cNeuralNet::ForwardInjectNoisePrefilled(double, double, const std::string&, Eigen::VectorXd&) const { ref_abort_stub(); }
-
-// ---- the index helpers of cMACETrainer the MACE controller uses (learning/MACETrainer.cpp:9-66; the trainer itself needs Caffe)
-int cMACETrainer::GetMaxFragIdx(const Eigen::VectorXd& params, int num_frags) {
-    int a = 0;
-    for (int i = 1; i < num_frags; ++i) if (params[i] > params[a]) a = i;
-    return a;
-}
-double cMACETrainer::GetMaxFragVal(const Eigen::VectorXd& params, int num_frags) { return params[GetMaxFragIdx(params, num_frags)]; }
-void cMACETrainer::GetFrag(const Eigen::VectorXd& params, int num_frags, int frag_size, int a_idx, Eigen::VectorXd& out) {
-    out = params.segment(num_frags + a_idx * frag_size, frag_size);
-}
-void cMACETrainer::SetFrag(const Eigen::VectorXd& frag, int a_idx, int num_frags, int frag_size, Eigen::VectorXd& out) {
-    out.segment(num_frags + a_idx * frag_size, frag_size) = frag;
-}
-double cMACETrainer::GetVal(const Eigen::VectorXd& params, int a_idx) { return params[a_idx]; }
-void cMACETrainer::SetVal(double val, int a_idx, Eigen::VectorXd& out) { out[a_idx] = val; }
-int cMACETrainer::CalcNumFrags(int param_size, int frag_size) { return param_size / (frag_size + 1); }
-void cMACETrainer::SetActionFragIdx(int a_idx, Eigen::VectorXd& out) { out[0] = a_idx; }
-void cMACETrainer::SetActionFrag(const Eigen::VectorXd& frag, Eigen::VectorXd& out) { out.segment(1, out.size() - 1) = frag; }
+// ---- cNeuralNet: what the controllers, scenarios and trainers ask of it
+#include "ref_net_standin.h"
 
 // ------------------------------------------------------------------------------------------------ C entry points
 struct RefCtrl {
@@ -527,6 +482,19 @@ struct FakeScn : public Base {
 };
 struct FakeScnEval : public FakeScn<cScenarioPoliEval> {};
 struct FakeScnExp : public FakeScn<cScenarioExpMACE> {
+    // cScenarioTrain::BuildScenePool calls Init, sets the initial exploration rates, then Reset ("rebuild ground"): the seeds go in
+    // at that Reset, as ref_scn_create does for a stand-alone scenario
+    bool seed_pending = false;
+    unsigned long ground_seed = 0, rand_seed = 0;
+    void Reset() override {
+        if (seed_pending) {
+            seed_pending = false;
+            ground()->SeedRand(ground_seed);
+            g_math_util_rand = cRand();
+            cMathUtil::SeedRand(rand_seed);
+        }
+        cScenarioExpMACE::Reset();
+    }
     void CommandRandAction() override {
         if (ccb) this->mChar->GetController()->CommandAction(ccb(user));
         else cScenarioExpMACE::CommandRandAction();          // draws from cMathUtil's engine (ref_scn_create seeds it)
@@ -615,5 +583,86 @@ int ref_scn_get_tuple(RefScn* r, int idx, double* reward, unsigned* flags, doubl
     for (int i = 0; i < (int)t.mStateEnd.size() && k < cap; ++i) row[k++] = t.mStateEnd[i];
     return k;
 }
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------ the training scenario
+// cScenarioTrain + cScenarioTrainMACE compiled as they are, with the compiled cMACETrainer / cNeuralNetTrainer / cNeuralNetLearner
+// behind them and one exploration scenario (the fake-backed cScenarioExpMACE above) in the pool: tuple hand-over when the buffer is
+// full, cNeuralNetLearner::Train, the annealed exploration rates and temperature, the curriculum phase -> SetTerrainParamsLerp.
+// Only BuildExpScene is overridden (to make the exploration scenario the fake-backed one).
+struct FakeScnTrain : public cScenarioTrainMACE {
+    world_fn wcb = nullptr;
+    void* user = nullptr;
+    unsigned long ground_seed = 0, rand_seed = 0;
+    void BuildExpScene(std::shared_ptr<cScenarioExp>& out_exp) const override {
+        auto e = std::make_shared<FakeScnExp>();
+        e->wcb = wcb; e->user = user; e->ccb = nullptr;
+        e->seed_pending = true; e->ground_seed = ground_seed; e->rand_seed = rand_seed;
+        out_exp = e;
+    }
+    FakeScnExp* exp0() { return static_cast<FakeScnExp*>(mExpPool[0].get()); }
+    void sched(int iters, double* out) const {
+        out[0] = CalcExpRate(iters); out[1] = CalcExpTemp(iters); out[2] = CalcExpBaseRate(iters); out[3] = CalcCurriculumPhase(iters);
+    }
+    long trainer_tuples() const { return std::static_pointer_cast<cNeuralNetTrainer>(mTrainer)->GetNumTuples(); }
+};
+struct RefTrainScn {
+    std::unique_ptr<FakeScnTrain> scn;
+};
+
+extern "C" {
+
+// net sizes / batch and the network callbacks, then the scenario from the reference's training arg file (+ extra tokens)
+RefTrainScn* ref_strain_create(const char* arg_file, char** extra, int n_extra, unsigned long ground_seed, unsigned long rand_seed,
+                               const int* net_dims, world_fn wcb, eval_fn ev, train_fn tr, copy_fn cp, calc_os_fn cos, set_os_fn sos,
+                               void* user) {
+    if (std::getenv("REF_CTRL_DEBUG")) signal(SIGSEGV, ref_segv_handler);
+    g_hooks.n_in = net_dims[0]; g_hooks.n_out = net_dims[1]; g_hooks.batch = net_dims[2];
+    g_hooks.eval = ev; g_hooks.train = tr; g_hooks.copy = cp; g_hooks.calc_os = cos; g_hooks.set_os = sos; g_hooks.user = user;
+    g_next_net = 0;
+    g_net_id.clear();
+    g_net_cb = nullptr;
+    g_reset_loads_pose0 = true;
+    cArgParser parser;
+    parser.AppendArgs(std::string(arg_file));
+    if (n_extra > 0) parser.AppendArgs(extra, n_extra);
+    RefTrainScn* r = new RefTrainScn();
+    r->scn.reset(new FakeScnTrain());
+    r->scn->wcb = wcb; r->scn->user = user; r->scn->ground_seed = ground_seed; r->scn->rand_seed = rand_seed;
+    r->scn->ParseArgs(parser);
+    r->scn->SetExpPoolSize(1);
+    r->scn->Init();
+    return r;
+}
+void ref_strain_destroy(RefTrainScn* r) {
+    delete r;
+    g_hooks = NetHooks();
+    g_reset_loads_pose0 = false;
+}
+void ref_strain_update(RefTrainScn* r, double dt) { r->scn->Update(dt); }        // cScenarioTrain::Update -> UpdateExpScene
+void ref_strain_set_state(RefTrainScn* r, const double* pose, const double* vel, const unsigned char* contact) {
+    FakeChar& ch = *r->scn->exp0()->fake();
+    const int nd = ch.sim()->GetNumDof(), nj = ch.sim()->GetNumJoints();
+    for (int i = 0; i < nd; ++i) { ch.pose[i] = pose[i]; ch.vel[i] = vel[i]; }
+    for (int j = 0; j < nj; ++j) static_cast<FakePart*>(ch.parts[j].get())->contact = contact[j] != 0;
+}
+void ref_strain_get_state(RefTrainScn* r, double* pose, double* vel, double* tau) {
+    FakeChar& ch = *r->scn->exp0()->fake();
+    const int nd = ch.sim()->GetNumDof();
+    for (int i = 0; i < nd; ++i) { pose[i] = ch.pose[i]; vel[i] = ch.vel[i]; tau[i] = ch.last_tau[i]; }
+}
+void ref_strain_get_fsm(RefTrainScn* r, double* out) {
+    auto* c = r->scn->exp0()->ctrl();
+    out[0] = c->GetState(); out[1] = c->GetPhase(); out[2] = c->GetCurrActionID();
+}
+// iter, tuples seen by the trainer, tuples in the scenario's buffer, then the scenario's current exploration rate / temperature /
+// base-action rate
+void ref_strain_status(RefTrainScn* r, long* counts, double* rates) {
+    counts[0] = r->scn->GetIter(); counts[1] = r->scn->trainer_tuples(); counts[2] = r->scn->exp0()->tuple_count();
+    rates[0] = r->scn->exp0()->GetExpRate(); rates[1] = r->scn->exp0()->GetExpTemp(); rates[2] = r->scn->exp0()->GetExpBaseActionRate();
+}
+// cScenarioTrain::CalcExpRate / CalcExpTemp / CalcExpBaseRate / CalcCurriculumPhase at `iters`
+void ref_strain_schedule(RefTrainScn* r, int iters, double* out4) { r->scn->sched(iters, out4); }
 
 }  // extern "C"

@@ -22,84 +22,7 @@ extern "C" void ref_abort_stub() {
     std::abort();
 }
 
-// ------------------------------------------------------------------------------------------------ cNeuralNet over callbacks
-typedef void (*eval_fn)(int net, const double* X, int B, double* Y, void* user);
-typedef void (*train_fn)(int net, const double* X, const double* Y, int B, void* user);
-typedef void (*copy_fn)(int dst, int src, void* user);
-typedef void (*calc_os_fn)(const double* X, int n, double* off, double* scale, void* user);
-typedef void (*set_os_fn)(int net, const double* off, const double* scale, void* user);
-struct NetHooks {
-    int n_in = 0, n_out = 0, batch = 32;
-    eval_fn eval = nullptr;
-    train_fn train = nullptr;
-    copy_fn copy = nullptr;
-    calc_os_fn calc_os = nullptr;
-    set_os_fn set_os = nullptr;
-    void* user = nullptr;
-};
-static NetHooks g_hooks;
-static std::map<const cNeuralNet*, int> g_net_id;       // construction order: 0 trainer net, 1 its target net, 2 the learner's net
-static int g_next_net = 0;
-static int id_of(const cNeuralNet* n) { return g_net_id.at(n); }
-
-static std::vector<double> flat(const Eigen::MatrixXd& M) {
-    std::vector<double> v((size_t)M.rows() * M.cols());
-    for (int i = 0; i < (int)M.rows(); ++i)
-        for (int j = 0; j < (int)M.cols(); ++j) v[(size_t)i * M.cols() + j] = M(i, j);
-    return v;
-}
-
-std::mutex cNeuralNet::gOutputLock;
-cNeuralNet::tProblem::tProblem() : mPassesPerStep(1) {}
-bool cNeuralNet::tProblem::HasData() const { return mX.size() > 0; }
-cNeuralNet::cNeuralNet() : mValidModel(true), mAsync(false) { g_net_id[this] = g_next_net++; }
-cNeuralNet::~cNeuralNet() { g_net_id.erase(this); }
-void cNeuralNet::LoadNet(const std::string&) {}
-void cNeuralNet::LoadModel(const std::string&) {}
-void cNeuralNet::LoadSolver(const std::string&, bool) {}
-void cNeuralNet::LoadScale(const std::string&) {}
-void cNeuralNet::Clear() {}
-void cNeuralNet::ResetSolver() {}
-void cNeuralNet::OutputModel(const std::string&) const {}
-bool cNeuralNet::HasNet() const { return true; }
-bool cNeuralNet::HasSolver() const { return true; }
-bool cNeuralNet::HasValidModel() const { return true; }
-int cNeuralNet::GetInputSize() const { return g_hooks.n_in; }
-int cNeuralNet::GetOutputSize() const { return g_hooks.n_out; }
-int cNeuralNet::GetBatchSize() const { return g_hooks.batch; }
-void cNeuralNet::Train(const tProblem& prob) {
-    const std::vector<double> x = flat(prob.mX), y = flat(prob.mY);
-    g_hooks.train(id_of(this), x.data(), y.data(), (int)prob.mX.rows(), g_hooks.user);
-}
-void cNeuralNet::EvalBatch(const Eigen::MatrixXd& X, Eigen::MatrixXd& out_Y) const {
-    const int B = (int)X.rows();
-    const std::vector<double> x = flat(X);
-    std::vector<double> y((size_t)B * g_hooks.n_out);
-    g_hooks.eval(id_of(this), x.data(), B, y.data(), g_hooks.user);
-    out_Y.resize(B, g_hooks.n_out);
-    for (int i = 0; i < B; ++i)
-        for (int j = 0; j < g_hooks.n_out; ++j) out_Y(i, j) = y[(size_t)i * g_hooks.n_out + j];
-}
-void cNeuralNet::Eval(const Eigen::VectorXd& x, Eigen::VectorXd& out_y) const {
-    std::vector<double> xi(x.size()), y(g_hooks.n_out);
-    for (int i = 0; i < (int)x.size(); ++i) xi[i] = x[i];
-    g_hooks.eval(id_of(this), xi.data(), 1, y.data(), g_hooks.user);
-    out_y.resize(g_hooks.n_out);
-    for (int j = 0; j < g_hooks.n_out; ++j) out_y[j] = y[j];
-}
-void cNeuralNet::CopyModel(const cNeuralNet& other) { g_hooks.copy(id_of(this), id_of(&other), g_hooks.user); }
-void cNeuralNet::CalcOffsetScale(const Eigen::MatrixXd& X, Eigen::VectorXd& out_offset, Eigen::VectorXd& out_scale) const {
-    const std::vector<double> x = flat(X);
-    std::vector<double> off(X.cols()), sc(X.cols());
-    g_hooks.calc_os(x.data(), (int)X.rows(), off.data(), sc.data(), g_hooks.user);
-    out_offset.resize(X.cols()); out_scale.resize(X.cols());
-    for (int j = 0; j < (int)X.cols(); ++j) { out_offset[j] = off[j]; out_scale[j] = sc[j]; }
-}
-void cNeuralNet::SetInputOffsetScale(const Eigen::VectorXd& offset, const Eigen::VectorXd& scale) {
-    std::vector<double> off(offset.size()), sc(scale.size());
-    for (int j = 0; j < (int)offset.size(); ++j) { off[j] = offset[j]; sc[j] = scale[j]; }
-    g_hooks.set_os(id_of(this), off.data(), sc.data(), g_hooks.user);
-}
+#include "ref_net_standin.h"
 
 // ------------------------------------------------------------------------------------------------ the compiled trainer, opened up
 struct PinTrainer : public cMACETrainer {
