@@ -73,6 +73,7 @@ void orc_use_ref_rand(OrcBatch* b, unsigned long seed) {
     b->ref_rand.seed(seed);
     for (auto& e : b->envs) e->rng.ref = &b->ref_rand;
 }
+int orc_rand_peek(OrcBatch* b) { Rand c = b->ref_rand; return c.rand_int(); }
 void orc_reseed_reset(OrcBatch* b, int env, unsigned long terrain_seed) {
     b->envs[env]->ground.rand.seed(terrain_seed);
     b->envs[env]->reset();
@@ -326,6 +327,12 @@ void orc_trainer_set_input_offset_scale(OrcTrainer* t, int target, const double*
     auto& n = target ? t->tr.target : t->tr.net;
     for (int i = 0; i < t->tr.S; ++i) { n.in_off[i] = off[i]; n.in_scale[i] = scale[i]; }
 }
+// training-loop pin: the trainer draws from the environments' restated cRand (orc_use_ref_rand), the environments evaluate the
+// trainer's current weights, and the curriculum sets the terrain parameters (cScenarioSimChar::SetTerrainParamsLerp)
+void orc_trainer_set_batch(OrcTrainer* t, int batch) { t->tr.P.batch = batch; }      // Caffe's batch size comes from the net file (32); smaller for quick tests
+void orc_trainer_share_rand(OrcTrainer* t, OrcBatch* b) { t->tr.shared_rand = &b->ref_rand; }
+void orc_set_net_from_trainer(OrcBatch* b, OrcTrainer* t) { t->tr.net.store_to(b->scene.net); }
+void orc_set_terrain_lerp(OrcBatch* b, double lerp) { for (auto& e : b->envs) b->scene.terrain_params_lerp(lerp, e->ground.params); }
 void orc_calc_offset_scale(const double* X, int n, int S, double* off, double* scale) { MaceTrainer::calc_offset_scale(X, n, S, off, scale); }
 
 // ---------------------------------------------------------------------------------------- generator-level terrain / RNG probes

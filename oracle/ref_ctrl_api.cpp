@@ -198,8 +198,14 @@ void FakeJoint::CalcRotation(tVector& out_axis, double& out_theta) const {
     out_axis = axis_rel;
     out_theta = cKinTree::GetJointTheta(jm(owner), owner->pose, id);
 }
+// cSimObj::GetRotation of the child body: Bullet hands back an axis-angle extracted from the body's orientation, not an accumulated
+// angle, so a link that has turned past half a revolution reads wrapped.  The accumulated angle (cKinTree::CalcJointWorldTheta)
+// goes through the reference's own rotation-matrix -> axis-angle extraction here (angle in [0, pi], axis +-z).
 void FakeJoint::GetChildRotation(tVector& out_axis, double& out_theta) const {
-    cKinTree::CalcJointWorldTheta(jm(owner), owner->pose, id, out_axis, out_theta);
+    tVector z;
+    double acc = 0;
+    cKinTree::CalcJointWorldTheta(jm(owner), owner->pose, id, z, acc);
+    cMathUtil::RotMatToAxisAngle(cMathUtil::RotateMat(z, acc), out_axis, out_theta);
 }
 tVector FakeJoint::CalcJointVelRel() const {
     const int o = cKinTree::GetParamOffset(jm(owner), id);
@@ -523,8 +529,8 @@ RefScn* ref_scn_create(const char* arg_file, int mode, char** extra, int n_extra
     g_net_cb = ncb; g_net_user = user;
     g_reset_loads_pose0 = true;
     cArgParser parser;
+    if (n_extra > 0) parser.AppendArgs(extra, n_extra);       // cArgParser returns the FIRST occurrence of a key: overrides go first
     parser.AppendArgs(std::string(arg_file));
-    if (n_extra > 0) parser.AppendArgs(extra, n_extra);
     RefScn* r = new RefScn();
     r->mode = mode;
     if (mode == 0) { r->ev.reset(new FakeScnEval()); r->ev->wcb = wcb; r->ev->ccb = ccb; r->ev->user = user; }
@@ -625,8 +631,8 @@ RefTrainScn* ref_strain_create(const char* arg_file, char** extra, int n_extra, 
     g_net_cb = nullptr;
     g_reset_loads_pose0 = true;
     cArgParser parser;
+    if (n_extra > 0) parser.AppendArgs(extra, n_extra);       // cArgParser returns the FIRST occurrence of a key: overrides go first
     parser.AppendArgs(std::string(arg_file));
-    if (n_extra > 0) parser.AppendArgs(extra, n_extra);
     RefTrainScn* r = new RefTrainScn();
     r->scn.reset(new FakeScnTrain());
     r->scn->wcb = wcb; r->scn->user = user; r->scn->ground_seed = ground_seed; r->scn->rand_seed = rand_seed;
@@ -635,6 +641,8 @@ RefTrainScn* ref_strain_create(const char* arg_file, char** extra, int n_extra, 
     r->scn->Init();
     return r;
 }
+// the next value of cMathUtil's engine without advancing it (a copy draws): lets the test locate a divergence of the draw sequences
+int ref_rand_peek() { cRand c = g_math_util_rand; return c.RandInt(); }
 void ref_strain_destroy(RefTrainScn* r) {
     delete r;
     g_hooks = NetHooks();
@@ -652,9 +660,15 @@ void ref_strain_get_state(RefTrainScn* r, double* pose, double* vel, double* tau
     const int nd = ch.sim()->GetNumDof();
     for (int i = 0; i < nd; ++i) { pose[i] = ch.pose[i]; vel[i] = ch.vel[i]; tau[i] = ch.last_tau[i]; }
 }
-void ref_strain_get_fsm(RefTrainScn* r, double* out) {
+// state, phase, action id, then the current action's parameter vector; returns the number of values
+int ref_strain_get_fsm(RefTrainScn* r, double* out, int cap) {
     auto* c = r->scn->exp0()->ctrl();
-    out[0] = c->GetState(); out[1] = c->GetPhase(); out[2] = c->GetCurrActionID();
+    int k = 0;
+    out[k++] = c->GetState(); out[k++] = c->GetPhase(); out[k++] = c->GetCurrActionID();
+    Eigen::VectorXd p;
+    c->BuildOptParams(p);
+    for (int i = 0; i < (int)p.size() && k < cap; ++i) out[k++] = p[i];
+    return k;
 }
 // iter, tuples seen by the trainer, tuples in the scenario's buffer, then the scenario's current exploration rate / temperature /
 // base-action rate
@@ -662,6 +676,7 @@ void ref_strain_status(RefTrainScn* r, long* counts, double* rates) {
     counts[0] = r->scn->GetIter(); counts[1] = r->scn->trainer_tuples(); counts[2] = r->scn->exp0()->tuple_count();
     rates[0] = r->scn->exp0()->GetExpRate(); rates[1] = r->scn->exp0()->GetExpTemp(); rates[2] = r->scn->exp0()->GetExpBaseActionRate();
 }
+double ref_strain_sample_height(RefTrainScn* r, double x) { return r->scn->exp0()->ground()->SampleHeight(tVector(x, 0, 0, 0)); }
 // cScenarioTrain::CalcExpRate / CalcExpTemp / CalcExpBaseRate / CalcCurriculumPhase at `iters`
 void ref_strain_schedule(RefTrainScn* r, int iters, double* out4) { r->scn->sched(iters, out4); }
 

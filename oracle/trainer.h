@@ -76,6 +76,18 @@ struct MaceNet {
         for (int b = 0; b < 26; ++b) std::copy(blobs[b]->begin(), blobs[b]->end(), theta.begin() + off[b]);
         in_off = n.in_off; in_scale = n.in_scale; out_off = n.out_off; out_scale = n.out_scale;
     }
+    // the inverse of init_from: the trained weights back into the policy network the environments evaluate (what
+    // cNeuralNetLearner::SyncNet does with the controller's network after every cNeuralNetLearner::Train)
+    void store_to(Net& n) const {
+        std::vector<double>* blobs[26] = {&n.conv0_w, &n.conv0_b, &n.conv1_w, &n.conv1_b, &n.conv2_w, &n.conv2_b, &n.tip0_w,
+                                          &n.tip0_b, &n.ip0_w, &n.ip0_b};
+        for (int h = 0; h < 4; ++h) {
+            blobs[10 + 4 * h] = &n.head0_w[h]; blobs[11 + 4 * h] = &n.head0_b[h];
+            blobs[12 + 4 * h] = &n.head1_w[h]; blobs[13 + 4 * h] = &n.head1_b[h];
+        }
+        for (int b = 0; b < 26; ++b) std::copy(theta.begin() + off[b], theta.begin() + off[b + 1], blobs[b]->begin());
+        n.in_off = in_off; n.in_scale = in_scale; n.out_off = out_off; n.out_scale = out_scale;
+    }
     const double* blob(int b) const { return theta.data() + off[b]; }
 
     static void conv_fwd(int B, const double* x, int cin, int win, const double* w, const double* b, int cout, int k, double* y) {
@@ -264,7 +276,8 @@ struct MaceTrainer {
     // cMACETrainer and this restatement can be compared draw for draw
     bool use_ref_rand = false;
     Rand ref_rand;
-    int draw(int n) { return use_ref_rand ? ref_rand.rand_int(0, n) : rng.rand_int(0, n); }
+    Rand* shared_rand = nullptr;        // the reference has ONE engine for exploration and sampling: share the environments' one
+    int draw(int n) { return shared_rand ? shared_rand->rand_int(0, n) : use_ref_rand ? ref_rand.rand_int(0, n) : rng.rand_int(0, n); }
     double last_critic_loss = 0, last_actor_loss = 0;
     std::vector<int> last_critic_ids, last_actor_ids;       // tuples of the most recent critic / actor solver step (for tests)
 

@@ -778,3 +778,219 @@ def test_mace_trainer_matches_reference_code(assets):
               f"them actor steps), {oc['total']} tuples through a {kw['replay_cap']}-row replay memory, weights bit-identical")
     finally:
         ref.ref_trainer_destroy(h)
+
+
+# ---------------------------------------------------------------------------------------------------- the training scenario
+@pytest.mark.skipif(not (os.path.exists(REF_CTRL) and os.path.isdir("/root/reference/args")),
+                    reason="oracle/_ref/libref_ctrl.so or the reference arg / data files absent")
+def test_training_scenario_matches_reference_code(assets):
+    """The reference's OWN training scenario -- cScenarioTrain + cScenarioTrainMACE, with the compiled cMACETrainer /
+    cNeuralNetTrainer / cNeuralNetLearner behind it and one compiled cScenarioExpMACE (fake-backed as in
+    test_scenario_matches_reference_code) in its pool -- runs from args/opt_args_train_mace.txt (overrides: slopes_mixed terrain to
+    match the pack, small replay memory / initial sample count / tuple buffer / anneal horizons so that everything happens within
+    ~1200 updates; the net's batch size, which Caffe reads from the net file, is 8 here).  Only BuildExpScene is overridden.
+    As compiled: BuildScenePool (initial exploration rates, curriculum phase, "rebuild ground" reset), InitTrainer / InitLearners
+    (learner network = the controller's network, first SyncNet), UpdateExpScene (update, IsTupleBufferFull, UpdateTrainer ->
+    cNeuralNetLearner::Train -> AddTuples / Train / SyncNet, CalcExpRate / CalcExpTemp / CalcExpBaseRate / CalcCurriculumPhase,
+    SetExp*, UpdateSceneCurriculum, ResetTupleBuffer) -- with exploration ON and annealed, every random draw (exploration AND
+    minibatch sampling) coming from the reference's single cMathUtil engine.
+
+    Against it, in lock-step: the oracle's exploration environment + the oracle's trainer (sharing one restated cRand, as the
+    reference shares its engine) + the PRODUCT's schedule function (trl_train_schedule through deepterrainrl_b200.train.TrainSchedule)
+    + weight hand-over to the environment after every trainer call.  The compiled trainer's network operations are answered by a
+    second oracle network object; the reference controller's evaluations by that object's weights after each SyncNet.
+
+    Compared: torques / gait state at every env-step, pose after every update, the exploration rates the compiled scenario holds
+    vs the product's schedule, the schedule function itself, trainer iteration / tuple counts, and after every trainer call the
+    weights -- bit-identical, which they can only be if every exploration draw, tuple, sampled index, label and solver step
+    agreed."""
+    from pyoracle import Oracle, OracleTrainer
+    from deepterrainrl_b200.train import TrainSchedule
+    pack = os.path.join(assets, "dog_slopes_mixed.trlpack")
+    ref = C.CDLL(REF_CTRL)
+    ref.ref_world_exact_origin(1)
+    tol = 1e-9
+    gseed, rseed, B, TB = 77, 999, 8, 8
+    kw = dict(replay_cap=400, num_init_samples=24, num_steps_per_iter=1, freeze_target_iters=3, init_input_offset_scale=1, seed=1)
+    o = Oracle(pack, 1, 1, terrain_seeds=[gseed])           # the oracle's exploration environment
+    oe = Oracle(pack, 1, 1, terrain_seeds=[gseed])          # holds the weights the reference controller evaluates (after SyncNet)
+    orc = OracleTrainer(pack, **kw)                          # the oracle's trainer
+    eng = OracleTrainer(pack, **kw)                          # the network under the compiled reference trainer
+    L = o.L
+    for f, a in (("orc_use_ref_rand", [C.c_void_p, C.c_ulong]), ("orc_reseed_reset", [C.c_void_p, C.c_int, C.c_ulong]),
+                 ("orc_end_update", [C.c_void_p, C.c_int, C.c_double]), ("orc_trainer_share_rand", [C.c_void_p, C.c_void_p]),
+                 ("orc_set_net_from_trainer", [C.c_void_p, C.c_void_p]), ("orc_set_terrain_lerp", [C.c_void_p, C.c_double]),
+                 ("orc_trainer_set_batch", [C.c_void_p, C.c_int])):
+        getattr(L, f).argtypes = a
+    L.orc_trainer_solver_step.restype = C.c_double
+    L.orc_trainer_set_batch(orc.h, B)
+    L.orc_trainer_set_batch(eng.h, B)
+    SCHED = dict(init_exp_rate=0.5, exp_rate=0.2, init_exp_temp=20, exp_temp=0.025, init_exp_base_rate=0.3, exp_base_rate=0.002,
+                 trainer_num_anneal_iters=12, exp_base_anneal_iters=8, trainer_curriculum_iters=10)
+    sched = TrainSchedule(**SCHED)                           # the product's trl_train_schedule
+    L.orc_use_ref_rand(o.h, rseed)
+    o.set_explore(1, SCHED["init_exp_rate"], SCHED["init_exp_temp"], SCHED["init_exp_base_rate"])
+    L.orc_set_terrain_lerp(o.h, 1.0)                         # gInitCurriculumPhase (scenarios/ScenarioTrain.cpp:6,213)
+    L.orc_reseed_reset(o.h, 0, gseed)
+    L.orc_trainer_share_rand(orc.h, o.h)
+    S, no = orc.n_in, orc.n_out
+    nd = o.ndof
+    DP = C.POINTER(C.c_double)
+    WFN = C.CFUNCTYPE(None, C.c_double, C.c_void_p)
+    EV = C.CFUNCTYPE(None, C.c_int, DP, C.c_int, DP, C.c_void_p)
+    TR = C.CFUNCTYPE(None, C.c_int, DP, DP, C.c_int, C.c_void_p)
+    CP = C.CFUNCTYPE(None, C.c_int, C.c_int, C.c_void_p)
+    CO = C.CFUNCTYPE(None, DP, C.c_int, DP, DP, C.c_void_p)
+    SO = C.CFUNCTYPE(None, C.c_int, DP, DP, C.c_void_p)
+    st = dict(h=None, steps=0, worst_tau=0.0, cmp=False, err=None)
+    log = dict(evals=[0, 0, 0], trains=0, copies=[], calc=0, set=[])
+
+    def ref_state():
+        pose = np.zeros(nd); vel = np.zeros(nd); tau = np.zeros(nd)
+        ref.ref_strain_get_state(st["h"], _p(pose), _p(vel), _p(tau))
+        return pose, vel, tau
+
+    def compare_step():
+        _, _, tau = ref_state()
+        to = o.last_tau(0)
+        err = np.max(np.abs(tau - to)) / max(1.0, np.max(np.abs(to)))
+        st["worst_tau"] = max(st["worst_tau"], err)
+        f = np.zeros(64)
+        ref.ref_strain_get_fsm(st["h"], _p(f), 64)
+        oc = o.get_ctrl(0)
+        assert int(f[0]) == int(oc[0]) and abs(f[1] - oc[1]) < 1e-9, (st["steps"], f[:3], oc[:3])
+        assert err < tol, (st["steps"], err)
+
+    def guarded(fn):
+        def w(*a):
+            if st["err"] is not None:
+                return
+            try:
+                fn(*a)
+            except BaseException as e:       # cannot cross the C frames
+                st["err"] = e
+        return w
+
+    def world(hh, u):
+        if st["cmp"]:
+            compare_step()
+        o.env_step(0, hh)
+        q, qd, _, contact = o.get_state(0)
+        ref.ref_strain_set_state(st["h"], _p(q), _p(qd), _p(contact.astype(np.uint8)))
+        st["steps"] += 1
+        st["cmp"] = True
+
+    # cNeuralNet instances in construction order: 0 the controller's (= the learner's) network, 1 the trainer's, 2 its target
+    def ev(net, X, Bn, Y, u):
+        x = np.ctypeslib.as_array(X, (Bn, S)).copy()
+        log["evals"][net] += 1
+        if net == 0:
+            assert Bn == 1
+            np.ctypeslib.as_array(Y, (1, no))[0] = oe.net_eval(x[0], no)
+        else:
+            y = np.zeros((Bn, no))
+            L.orc_trainer_eval_batch(eng.h, 1 if net == 2 else 0, _p(x), Bn, _p(y))
+            np.ctypeslib.as_array(Y, (Bn, no))[:] = y
+
+    def tr(net, X, Y, Bn, u):
+        assert net == 1 and Bn == B
+        x = np.ctypeslib.as_array(X, (Bn, S)).copy()
+        y = np.ctypeslib.as_array(Y, (Bn, no)).copy()
+        L.orc_trainer_solver_step(eng.h, _p(x), _p(y))
+        log["trains"] += 1
+
+    def cp(dst, src, u):
+        log["copies"].append((dst, src))
+        if (dst, src) == (2, 1):
+            L.orc_trainer_copy_to_target(eng.h)
+        elif (dst, src) == (0, 1):
+            L.orc_set_net_from_trainer(oe.h, eng.h)          # cNeuralNetLearner::SyncNet: the controller gets the trained weights
+        else:
+            raise AssertionError((dst, src))
+
+    def co(X, n, off, sc, u):
+        x = np.ctypeslib.as_array(X, (n, S)).copy()
+        of, s = np.zeros(S), np.zeros(S)
+        L.orc_calc_offset_scale(_p(x), n, S, _p(of), _p(s))
+        np.ctypeslib.as_array(off, (S,))[:] = of
+        np.ctypeslib.as_array(sc, (S,))[:] = s
+        log["calc"] += 1
+
+    def so(net, off, sc, u):
+        assert net in (1, 2)
+        of = np.ctypeslib.as_array(off, (S,)).copy()
+        s = np.ctypeslib.as_array(sc, (S,)).copy()
+        L.orc_trainer_set_input_offset_scale(eng.h, 1 if net == 2 else 0, _p(of), _p(s))
+        log["set"].append(net)
+
+    cbs = (WFN(guarded(world)), EV(guarded(ev)), TR(guarded(tr)), CP(guarded(cp)), CO(guarded(co)), SO(guarded(so)))
+    out_scale = np.ascontiguousarray(orc.get("out_scale"))
+    ref.ref_ctrl_set_net_output(S, _p(np.zeros(no)), _p(out_scale), no)           # the exploration-noise scale the controller reads
+    extra = ["-init_exp_rate=", "0.5", "-init_exp_base_rate=", "0.3", "-terrain_file=", "data/terrain/slopes_mixed.txt",
+             "-tuple_buffer_size=", str(TB), "-trainer_replay_mem_size=", "400", "-trainer_num_init_samples=", "24",
+             "-trainer_freeze_target_iters=", "3", "-trainer_num_anneal_iters=", "12", "-exp_base_anneal_iters=", "8",
+             "-trainer_curriculum_iters=", "10", "-trainer_int_iter=", "0", "-trainer_iters_per_output=", "100000",
+             "-output_path=", "/tmp/ref_strain_model.h5"]
+    extra = [e.encode() for e in extra]
+    arr = (C.c_char_p * len(extra))(*extra)
+    dims = np.array([S, no, B], np.int32)
+    ref.ref_strain_create.restype = C.c_void_p
+    ref.ref_strain_create.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_ulong, C.c_ulong, C.c_void_p, WFN, EV, TR, CP, CO, SO, C.c_void_p]
+    ref.ref_strain_update.argtypes = [C.c_void_p, C.c_double]
+    cwd = os.getcwd()
+    os.chdir("/root/reference")
+    try:
+        h = ref.ref_strain_create(b"args/opt_args_train_mace.txt", arr, len(extra), gseed, rseed, _p(dims), *cbs, None)
+    finally:
+        os.chdir(cwd)
+    assert h and st["err"] is None, st["err"]
+    h = C.c_void_p(h)
+    st["h"] = h
+    try:
+        assert log["copies"] == [(2, 1), (0, 1)]       # cMACETrainer::BuildNetPool (target), cNeuralNetLearner::Init (SyncNet)
+        pose, _, _ = ref_state()
+        assert np.max(np.abs(pose - o.get_state(0)[0])) < tol
+        DT = 1.0 / 30.0
+        n_calls = 0
+        rates_seen = []
+        for k in range(1250):
+            ref.ref_strain_update(h, DT)
+            if st["err"] is not None:
+                raise st["err"]
+            L.orc_end_update(o.h, 0, DT)
+            compare_step()
+            st["cmp"] = False
+            if L.orc_num_tuples(o.h) >= TB:             # the oracle's side of cScenarioTrain::UpdateExpScene
+                rows, flags, _ = o.tuples()
+                assert len(rows) == TB
+                orc.add_tuples(rows, flags)
+                orc.train()
+                L.orc_set_net_from_trainer(o.h, orc.h)
+                it = orc.counters()["iter"]
+                s = sched(it)
+                o.set_explore(1, s["exp_rate"], s["exp_temp"], s["exp_base_rate"])
+                L.orc_set_terrain_lerp(o.h, s["curriculum_phase"])
+                o.reset_tuples()
+                n_calls += 1
+                cnt, rates, r4 = (C.c_long * 3)(), (C.c_double * 3)(), (C.c_double * 4)()
+                ref.ref_strain_status(h, cnt, rates)
+                ref.ref_strain_schedule(h, it, r4)
+                assert (cnt[0], cnt[1], cnt[2]) == (it, TB * n_calls, 0), (k, list(cnt), it)
+                want = [s["exp_rate"], s["exp_temp"], s["exp_base_rate"]]
+                assert np.allclose(list(rates), want, rtol=1e-15, atol=0), (list(rates), want)        # what the compiled scenario now holds
+                assert np.allclose(list(r4), want + [s["curriculum_phase"]], rtol=1e-15, atol=0)      # cScenarioTrain::Calc* vs trl_train_schedule
+                assert np.array_equal(eng.get("theta"), orc.get("theta")), (k, it)
+                rates_seen.append(want)
+            pose, vel, _ = ref_state()
+            q, qd, _, _ = o.get_state(0)
+            assert max(np.max(np.abs(pose - q)), np.max(np.abs(vel - qd))) < tol, k
+        oc = orc.counters()
+        assert oc["iter"] >= 6 and log["trains"] >= 6 and log["evals"][0] >= 30 and log["calc"] == 1
+        assert np.array_equal(eng.get("target"), orc.get("target"))
+        assert rates_seen[-1][0] < rates_seen[0][0] and rates_seen[-1][1] < rates_seen[0][1] and rates_seen[-1][2] < rates_seen[0][2]
+        print(f"compiled cScenarioTrainMACE vs oracle loop: {st['steps']} env-steps, {n_calls} trainer calls, {oc['iter']} iterations "
+              f"({log['trains']} solver steps), rates annealed to {rates_seen[-1]}, weights bit-identical; worst torque difference "
+              f"{st['worst_tau']:.1e}")
+    finally:
+        ref.ref_strain_destroy(h)
+        ref.ref_world_exact_origin(0)
