@@ -72,16 +72,13 @@ struct FakeJoint : public cJoint {
     int id = 0;
     bool valid = true;
     tVector axis_rel = tVector(0, 0, 1, 0);
-    tVector torque = tVector(0, 0, 0, 0);
-    double torque_lim = 1e30;
     bool IsValid() const override { return valid; }
     const tVector& GetAxisRel() const override { return axis_rel; }
     tVector CalcAxisWorld() const override { return axis_rel; }                       // planar character: every hinge is about z
     void CalcRotation(tVector& out_axis, double& out_theta) const override;           // joint angle
     void GetChildRotation(tVector& out_axis, double& out_theta) const override;       // world rotation of the child link
     tVector CalcJointVelRel() const override;                                         // relative angular velocity in the joint frame
-    void AddTorque(const tVector& t) override { torque += t; }
-    void SetTorqueLimit(double lim) override { torque_lim = lim; }
+    // AddTorque / GetTorque / ClearTorque / SetTorqueLimit / ClampTotalTorque are the reference's own (sim/Joint.cpp, compiled)
 };
 
 // the state the test installs + the answers to the character's virtual calls; Base is the reference's own character class
@@ -175,7 +172,17 @@ struct FakeCharT : public Base, public FakeChar {
     const std::shared_ptr<cSimObj>& GetBodyPart(int i) const override { return parts[i]; }
     std::shared_ptr<cSimObj>& GetBodyPart(int i) override { return parts[i]; }
     bool IsValidBodyPart(int idx) const override { return cKinTree::IsValidBody(this->mBodyDefs, idx); }
-    void ApplyControlForces(const Eigen::VectorXd& tau) override { last_tau = tau; ++n_apply; }
+    // cSimCharacter::ApplyControlForces (sim/SimCharacter.cpp:637-654): one z-torque per valid joint, accumulated in the joint
+    // (cSimCharacter::ClearJointTorques empties the accumulators after the world step, here before the next accumulation)
+    void ApplyControlForces(const Eigen::VectorXd& tau) override {
+        last_tau = tau;
+        ++n_apply;
+        for (int j = 0; j < this->GetNumJoints(); ++j) {
+            if (!joints[j].IsValid()) continue;
+            joints[j].ClearTorque();
+            joints[j].AddTorque(tVector(0, 0, tau[this->GetParamOffset(j)], 0));
+        }
+    }
 };
 
 static const Eigen::MatrixXd& jm(const FakeChar* c) { return const_cast<FakeChar*>(c)->sim()->GetJointMat(); }
@@ -227,8 +234,8 @@ cWorld::tJointParams::tJointParams() {}
 // ---- the Bullet-backed base classes: constructors / destructors only (their vtables land here; see the header comment)
 cSimObj::cSimObj() {}
 cSimObj::~cSimObj() {}
-cJoint::cJoint() {}
-cJoint::~cJoint() {}
+bool cWorld::tConstraintHandle::IsValid() const { return mCons != nullptr; }
+void cWorld::tConstraintHandle::Clear() { mCons = nullptr; }
 cSimCharacter::cSimCharacter() {}
 cSimCharacter::~cSimCharacter() {}
 // called as base-class functions by cSimCharSoftFall (the real ones drive Bullet)
@@ -388,6 +395,19 @@ int ref_char_has_fallen(RefCtrl* r) { return r->chp->sim()->HasFallen() ? 1 : 0;
 int ref_char_has_stumbled(RefCtrl* r) { return r->chp->sim()->HasStumbled() ? 1 : 0; }
 void ref_ctrl_reset(RefCtrl* r) { r->ctrl->Reset(); }
 void ref_ctrl_update(RefCtrl* r, double h) { r->ctrl->Update(h); }
+// what cJoint::ApplyTorque would hand to the physics: the accumulated joint torque after cJoint::ClampTotalTorque with the limit
+// cPDController installed (sim/Joint.cpp:171-190,257-264, sim/PDController.cpp:99-100)
+void ref_ctrl_get_applied_tau(RefCtrl* r, double* out) {
+    FakeChar& ch = *r->chp;
+    cSimCharacter* sim = ch.sim();
+    for (int i = 0; i < sim->GetNumDof(); ++i) out[i] = 0;
+    for (int j = 0; j < sim->GetNumJoints(); ++j) {
+        if (!ch.joints[j].IsValid()) continue;
+        tVector t = ch.joints[j].GetTorque();
+        ch.joints[j].ClampTotalTorque(t);
+        out[sim->GetParamOffset(j)] = t[2];
+    }
+}
 void ref_ctrl_get_tau(RefCtrl* r, double* out) { for (int i = 0; i < r->chp->sim()->GetNumDof(); ++i) out[i] = r->chp->last_tau[i]; }
 // state, phase, action id, then the full parameter vector of the current action
 int ref_ctrl_get_fsm(RefCtrl* r, double* out, int cap) {

@@ -197,7 +197,8 @@ def test_controller_matches_reference_code(assets, scene):
     virtual calls with the reference's own cKinTree kinematics; the character class is the reference's own cSimDog / cSimRaptor,
     so fall and stumble detection (cSimCharSoftFall, cSimDog::HasStumbled / CheckFallContact / FailFallMisc) run as compiled.
     Compared every step: HasFallen / HasStumbled, the joint torques handed to
-    ApplyControlForces vs the oracle's controller torques, the gait-machine state / phase / action id, the action parameters,
+    ApplyControlForces vs the oracle's controller torques, the clamped torques the reference's own cJoint (sim/Joint.cpp, compiled)
+    would pass to the physics vs the oracle's held torques, the gait-machine state / phase / action id, the action parameters,
     at every decision the policy state vector (terrain samples + character features) the reference built, and at the end of every
     cycle the reward c{Dog,Raptor}Controller::CalcReward returns."""
     from pyoracle import Oracle
@@ -233,7 +234,7 @@ def test_controller_matches_reference_code(assets, scene):
     ref.ref_char_reset(h)
     ref.ref_char_update.argtypes = [C.c_void_p, C.c_double]
     worst_tau = worst_state = 0.0
-    n_stumbled = 0
+    n_stumbled = n_clamped = 0
     decisions = 0
     rewards = []
     ref.ref_ctrl_calc_reward.restype = C.c_double
@@ -258,6 +259,12 @@ def test_controller_matches_reference_code(assets, scene):
         err = np.max(np.abs(tr - to)) / max(1.0, np.max(np.abs(to)))
         worst_tau = max(worst_tau, err)
         assert err < 1e-9, (scene, k, err)
+        # the torque the physics receives: cJoint's accumulator after cJoint::ClampTotalTorque (limit from the PD parameters)
+        ta = np.zeros(nd)
+        ref.ref_ctrl_get_applied_tau(h, _p(ta))
+        held = o.get_state(0)[2]
+        assert np.max(np.abs(ta - held)) <= 1e-9 * max(1.0, np.max(np.abs(held))), (scene, k)
+        n_clamped += int(np.any(np.abs(ta - tr) > 1e-6))
         f = np.zeros(64)
         n = ref.ref_ctrl_get_fsm(h, _p(f), 64)
         oc = o.get_ctrl(0)
@@ -277,7 +284,7 @@ def test_controller_matches_reference_code(assets, scene):
                 assert es < 1e-9, (scene, k, es)
     ref.ref_ctrl_destroy(h)
     assert decisions >= 3 and max(rewards) > 0.2
-    print(f"{scene}: {n_steps} env-steps, {decisions} cycles; worst torque difference {worst_tau:.2e} (relative), "
+    print(f"{scene}: {n_steps} env-steps ({n_clamped} with a joint at its torque limit), {decisions} cycles; worst torque difference {worst_tau:.2e} (relative), "
           f"worst policy-state difference {worst_state:.2e}")
 
 
