@@ -790,11 +790,14 @@ def test_mace_trainer_matches_reference_code(assets):
 # ---------------------------------------------------------------------------------------------------- the training scenario
 @pytest.mark.skipif(not (os.path.exists(REF_CTRL) and os.path.isdir("/root/reference/args")),
                     reason="oracle/_ref/libref_ctrl.so or the reference arg / data files absent")
-def test_training_scenario_matches_reference_code(assets):
+@pytest.mark.parametrize("scene,arg_file,terrain_file,exp_rate,exp_base_rate",
+                         [("dog_slopes_mixed", "args/opt_args_train_mace.txt", "data/terrain/slopes_mixed.txt", 0.2, 0.002),
+                          ("raptor_narrow_gaps", "args/opt_args_train_raptor_mace.txt", "data/terrain/narrow_gaps.txt", 0.1, 0.001)])
+def test_training_scenario_matches_reference_code(assets, scene, arg_file, terrain_file, exp_rate, exp_base_rate):
     """The reference's OWN training scenario -- cScenarioTrain + cScenarioTrainMACE, with the compiled cMACETrainer /
     cNeuralNetTrainer / cNeuralNetLearner behind it and one compiled cScenarioExpMACE (fake-backed as in
-    test_scenario_matches_reference_code) in its pool -- runs from args/opt_args_train_mace.txt (overrides: slopes_mixed terrain to
-    match the pack, small replay memory / initial sample count / tuple buffer / anneal horizons so that everything happens within
+    test_scenario_matches_reference_code) in its pool -- runs from args/opt_args_train_mace.txt / opt_args_train_raptor_mace.txt
+    (overrides: the terrain of the pack, small replay memory / initial sample count / tuple buffer / anneal horizons so that everything happens within
     ~1200 updates; the net's batch size, which Caffe reads from the net file, is 8 here).  Only BuildExpScene is overridden.
     As compiled: BuildScenePool (initial exploration rates, curriculum phase, "rebuild ground" reset), InitTrainer / InitLearners
     (learner network = the controller's network, first SyncNet), UpdateExpScene (update, IsTupleBufferFull, UpdateTrainer ->
@@ -813,7 +816,7 @@ def test_training_scenario_matches_reference_code(assets):
     agreed."""
     from pyoracle import Oracle, OracleTrainer
     from deepterrainrl_b200.train import TrainSchedule
-    pack = os.path.join(assets, "dog_slopes_mixed.trlpack")
+    pack = os.path.join(assets, scene + ".trlpack")
     ref = C.CDLL(REF_CTRL)
     ref.ref_world_exact_origin(1)
     tol = 1e-9
@@ -832,7 +835,7 @@ def test_training_scenario_matches_reference_code(assets):
     L.orc_trainer_solver_step.restype = C.c_double
     L.orc_trainer_set_batch(orc.h, B)
     L.orc_trainer_set_batch(eng.h, B)
-    SCHED = dict(init_exp_rate=0.5, exp_rate=0.2, init_exp_temp=20, exp_temp=0.025, init_exp_base_rate=0.3, exp_base_rate=0.002,
+    SCHED = dict(init_exp_rate=0.5, exp_rate=exp_rate, init_exp_temp=20, exp_temp=0.025, init_exp_base_rate=0.3, exp_base_rate=exp_base_rate,
                  trainer_num_anneal_iters=12, exp_base_anneal_iters=8, trainer_curriculum_iters=10)
     sched = TrainSchedule(**SCHED)                           # the product's trl_train_schedule
     L.orc_use_ref_rand(o.h, rseed)
@@ -933,7 +936,7 @@ def test_training_scenario_matches_reference_code(assets):
     cbs = (WFN(guarded(world)), EV(guarded(ev)), TR(guarded(tr)), CP(guarded(cp)), CO(guarded(co)), SO(guarded(so)))
     out_scale = np.ascontiguousarray(orc.get("out_scale"))
     ref.ref_ctrl_set_net_output(S, _p(np.zeros(no)), _p(out_scale), no)           # the exploration-noise scale the controller reads
-    extra = ["-init_exp_rate=", "0.5", "-init_exp_base_rate=", "0.3", "-terrain_file=", "data/terrain/slopes_mixed.txt",
+    extra = ["-init_exp_rate=", "0.5", "-init_exp_base_rate=", "0.3", "-terrain_file=", terrain_file,
              "-tuple_buffer_size=", str(TB), "-trainer_replay_mem_size=", "400", "-trainer_num_init_samples=", "24",
              "-trainer_freeze_target_iters=", "3", "-trainer_num_anneal_iters=", "12", "-exp_base_anneal_iters=", "8",
              "-trainer_curriculum_iters=", "10", "-trainer_int_iter=", "0", "-trainer_iters_per_output=", "100000",
@@ -947,7 +950,7 @@ def test_training_scenario_matches_reference_code(assets):
     cwd = os.getcwd()
     os.chdir("/root/reference")
     try:
-        h = ref.ref_strain_create(b"args/opt_args_train_mace.txt", arr, len(extra), gseed, rseed, _p(dims), *cbs, None)
+        h = ref.ref_strain_create(arg_file.encode(), arr, len(extra), gseed, rseed, _p(dims), *cbs, None)
     finally:
         os.chdir(cwd)
     assert h and st["err"] is None, st["err"]
@@ -995,7 +998,7 @@ def test_training_scenario_matches_reference_code(assets):
         assert oc["iter"] >= 6 and log["trains"] >= 6 and log["evals"][0] >= 30 and log["calc"] == 1
         assert np.array_equal(eng.get("target"), orc.get("target"))
         assert rates_seen[-1][0] < rates_seen[0][0] and rates_seen[-1][1] < rates_seen[0][1] and rates_seen[-1][2] < rates_seen[0][2]
-        print(f"compiled cScenarioTrainMACE vs oracle loop: {st['steps']} env-steps, {n_calls} trainer calls, {oc['iter']} iterations "
+        print(f"{scene}: compiled cScenarioTrainMACE vs oracle loop: {st['steps']} env-steps, {n_calls} trainer calls, {oc['iter']} iterations "
               f"({log['trains']} solver steps), rates annealed to {rates_seen[-1]}, weights bit-identical; worst torque difference "
               f"{st['worst_tau']:.1e}")
     finally:
