@@ -1,15 +1,23 @@
-// TEST INFRASTRUCTURE ONLY -- the REFERENCE's own controller stack (sim/Controller.cpp, CharController.cpp, NNController.cpp,
-// TerrainRLCharController.cpp, DogController.cpp, DogControllerCacla.cpp, BaseControllerCacla.cpp, BaseControllerMACE.cpp,
-// DogControllerMACE.cpp, ImpPDController.cpp, PDController.cpp, anim/Character.cpp + the rigid-body sources of libref_rbd) compiled
-// where it lies under /root/reference into oracle/_ref/libref_ctrl.so, against header stand-ins for Eigen / jsoncpp / Bullet / Caffe
-// (oracle/ref_shim).  What those sources need from the simulation -- pose, velocity, contacts, body-part positions, ground heights,
-// network output -- they obtain through virtual calls on cSimCharacter / cSimObj / cJoint / cGround and through cNeuralNet; this
-// file supplies that back end from a state the test installs (the CPU oracle's state), using the reference's own cKinTree
-// kinematics for positions and velocities.  The torques the reference controller hands to cSimCharacter::ApplyControlForces and its
-// gait-machine state are what tests/test_ref_pinning_cpu.py compares with oracle/env.h.
+// TEST INFRASTRUCTURE ONLY -- the REFERENCE's own sources for the hot path, compiled where they lie under /root/reference into
+// oracle/_ref/libref_ctrl.so (recipe: oracle/Makefile, REF_CTRL_SRCS) against header stand-ins for Eigen / jsoncpp / Bullet / Caffe
+// (oracle/ref_shim):
+//   * the controller stack (sim/Controller, CharController, NNController, TerrainRLCharController, Dog / Goat / Raptor controllers
+//     incl. the Q / Cacla / MACE layers, ImpPDController, PDController, Joint), the characters (anim/Character, sim/SimCharSoftFall,
+//     SimDog, SimRaptor), the kinematics and rigid-body sources of libref_rbd, the ground (sim/Ground, GroundVar2D, TerrainGen2D);
+//   * the scenarios (scenarios/Scenario, ScenarioSimChar, ScenarioPoliEval, ScenarioExp, ScenarioExpMACE, ScenarioTrain,
+//     ScenarioTrainMACE), util/ArgParser, learning/ExpTuple;
+//   * the trainer (learning/TrainerInterface, NeuralNetTrainer, MACETrainer, NeuralNetLearner).
+// What those sources need from the simulation -- pose, velocity, contacts, body-part positions and rotations, the world step, the
+// network -- they obtain through virtual calls on cSimCharacter / cSimObj / cJoint / cWorld and through cNeuralNet; this file supplies
+// that back end from a state the test installs (the CPU oracle's state), using the reference's own cKinTree kinematics for positions
+// and velocities, and hands the world step and the network operations back to the test (ref_net_standin.h).
+// tests/test_ref_pinning_cpu.py compares what the compiled reference code then computes -- torques, gait machine, policy states,
+// rewards, fall verdicts, terrain, tuples, statistics, resets, exploration draws, trainer buffers and weights, annealing schedule --
+// with oracle/env.h, oracle/trainer.h and the product's host functions.
 //
-// Every other virtual function of the Bullet-backed classes is resolved to ref_abort_stub by the link recipe (oracle/Makefile):
-// if the compiled reference code ever reached one, the test would abort instead of silently using made-up behaviour.
+// Every other virtual function of the Bullet / Caffe-backed classes is resolved to ref_abort_stub by the link recipe
+// (link_with_stubs.sh): if the compiled reference code ever reached one, the test would abort instead of silently using made-up
+// behaviour.
 #include <execinfo.h>
 #include <signal.h>
 
