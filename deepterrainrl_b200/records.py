@@ -1,7 +1,9 @@
 """cScenarioPoliEval's per-cycle analysis dumps (scenarios/ScenarioPoliEval.cpp:262-404) for one env of a batch, derived from the
 tuple stream (one tuple per gait cycle: state at the decision, action taken, reward): `RecordAction` (action id + optimised
 parameters), `RecordActionIDState` (action id + policy state) and the reward per cycle, in the reference's text formats
-(std::to_string -> 6 decimals, ",\\t" separated)."""
+(std::to_string -> 6 decimals, ",\\t" separated).  The record lines are byte-identical to the files the reference's compiled
+cScenarioPoliEval writes for the same cycles (tests/test_ref_pinning_cpu.py); the table of base actions that
+cScenarioPoliEval::InitActionRecord puts in front of the action records (:297-317) is not emitted."""
 import numpy as np
 
 

@@ -452,7 +452,7 @@ SCN_CASES = [("goat_cliffs", 0, 400, True), ("raptor_narrow_gaps", 0, 400, True)
 @pytest.mark.skipif(not (os.path.exists(REF_CTRL) and os.path.isdir("/root/reference/args")),
                     reason="oracle/_ref/libref_ctrl.so or the reference arg / data files absent")
 @pytest.mark.parametrize("scene,mode,n_updates,exact_origin", SCN_CASES)
-def test_scenario_matches_reference_code(assets, scene, mode, n_updates, exact_origin):
+def test_scenario_matches_reference_code(assets, tmp_path, scene, mode, n_updates, exact_origin):
     """The reference's OWN scenario classes -- cScenario, cScenarioSimChar, cScenarioPoliEval, cScenarioExp, cScenarioExpMACE,
     compiled unmodified into oracle/_ref/libref_ctrl.so together with the controller stack, cGroundVar2D, cTerrainGen2D,
     cArgParser and tExpTuple -- run from the reference's own arg file (args/*_args.txt: character, controller, terrain, step
@@ -535,6 +535,18 @@ def test_scenario_matches_reference_code(assets, scene, mode, n_updates, exact_o
             ref.ref_scn_set_state(st["h"], _p(q), _p(qd), _p(contact.astype(np.uint8)))
             st["steps"] += 1
             st["cmp"] = True
+            cyc = o.flags(0)[2]
+            if record and cyc != st["cyc"]:
+                # a new gait cycle: what one tuple of the stream carries for it (state at the decision, action id + optimised
+                # parameters; for the dog every parameter but the first is optimised)
+                oc = o.get_ctrl(0)
+                row = np.zeros(1 + 2 * o.S + o.A)
+                row[1:1 + o.S] = o.poli_state(0)
+                row[1 + o.S] = oc[11]
+                row[2 + o.S:1 + o.S + o.A] = oc[13:12 + o.num_params]
+                if st["cyc"] >= 1:           # cScenarioPoliEval::IsValidCycle: the first cycle is warm-up
+                    rec.consume(row[None, :], np.zeros(1, np.uint32), np.zeros(1, np.int32))
+                st["cyc"] = cyc
         except BaseException as e:          # an exception cannot cross the C frames: keep it for the main loop
             st["err"] = e
 
@@ -563,6 +575,15 @@ def test_scenario_matches_reference_code(assets, scene, mode, n_updates, exact_o
     extra = [b"-exp_rate=", b"0", b"-exp_base_rate=", b"0", b"-exp_temp=", b"0.000001", b"-tuple_buffer_size=", b"4096"]
     if explore:
         extra = [b"-exp_rate=", b"0.3", b"-exp_base_rate=", b"0.05", b"-exp_temp=", b"0.1", b"-tuple_buffer_size=", b"4096"]
+    # the analysis dumps of cScenarioPoliEval (RecordAction, RecordActionIDState; scenarios/ScenarioPoliEval.cpp:262-404), written by
+    # the compiled scenario, against the product's deepterrainrl_b200.records.CycleRecorder fed with the same cycles
+    record = scene == "dog_slopes_mixed" and mode == 0 and exact_origin
+    st["cyc"] = 0
+    if record:
+        from deepterrainrl_b200.records import CycleRecorder
+        rec = CycleRecorder(0, o.S, o.A, str(tmp_path / "actions.txt"), str(tmp_path / "ids.txt"))
+        extra += [b"-record_actions=", b"true", b"-action_output_file=", str(tmp_path / "ref_actions.txt").encode(),
+                  b"-record_action_id_state=", b"true", b"-action_id_state_output_file=", str(tmp_path / "ref_ids.txt").encode()]
     arr = (C.c_char_p * len(extra))(*extra)
     cwd = os.getcwd()
     os.chdir("/root/reference")                       # the arg file names its data files relative to the reference's root
@@ -618,6 +639,13 @@ def test_scenario_matches_reference_code(assets, scene, mode, n_updates, exact_o
             if scene != "dog_slopes_mixed":
                 assert n >= 1 and resets >= 1             # episodes ended by the reference's own fall test
             summary = f"{es['cycles']} cycles, {n} episodes"
+            if record:
+                ref_a = open(tmp_path / "ref_actions.txt").read().splitlines()
+                n_act = len(ref_a) - rec.cycles           # InitActionRecord first lists the base actions ("%i, %.5f"), not emitted by the product
+                assert n_act >= 1 and rec.cycles >= 10 and all(", " in l and ",\t" not in l for l in ref_a[:n_act])
+                assert ref_a[n_act:] == open(tmp_path / "actions.txt").read().splitlines()
+                assert open(tmp_path / "ref_ids.txt").read() == open(tmp_path / "ids.txt").read()
+                summary += f", {rec.cycles} action / action-id-state records byte-identical to the reference's files"
         else:
             rows, flags, _ = o.tuples()
             assert len(rows) >= 5
