@@ -55,7 +55,16 @@ constexpr int kZeroLane = 31;   // always idle (nj <= 23): its per-link register
 constexpr int kTri = kMaxDof * (kMaxDof + 1) / 2;   // 276
 // per-warp shared scratch (doubles)
 constexpr int X_M = 0;
+#ifndef TRL_ACCUM_SMEM
+#define TRL_ACCUM_SMEM 0          // 1: child -> parent hand-off of the inward rounds through shared memory instead of shuffles (experiment)
+#endif
+#if TRL_ACCUM_SMEM
+constexpr int kAccStride = 10;                              // doubles per lane slot: 9 values, padded to 80 B (128-bit accesses stay conflict-free)
+constexpr int X_ACC = (X_M + kTri + 4 + 1) & ~1;            // 16-byte aligned
+constexpr int X_END = X_ACC + kWarp * kAccStride;
+#else
 constexpr int X_END = X_M + kTri + 4;
+#endif
 
 __device__ __forceinline__ int tri(int a, int b) { return a * (a + 1) / 2 + b; }  // a >= b
 __device__ __forceinline__ double shf(double v, int src) { return __shfl_sync(kFull, v, src); }
@@ -358,11 +367,33 @@ __device__ __forceinline__ Kin kinematics(const LinkC& c, const EnvRegs& e) {
 
 // child -> parent hand-off at the end of inward round r: every lane adds the NV register values of the one lane its
 // schedule names for this round (lane 31 = none; it is idle and its values are zero, so the add is unconditional)
+#if TRL_ACCUM_SMEM
+// Experiment (profiles/step_kernel_r01_source_phases.md): the same hand-off staged through shared memory -- every lane stores its
+// NV values as 128-bit words into its slot, the receiver loads the slot of its source lane.  Same values, same additions, so
+// the results are bit-identical to the shuffle form; ~10 memory instructions per round instead of ~4 per value.
+// `xs` (the warp's shared-memory block) must be in scope.
+#define TRL_ACCUM_ROUND(r, NV, vals)                                                        \
+    do {                                                                                    \
+        const int src_ = (int)(lc.acc_src >> (5 * (r))) & 31;                               \
+        double2* mine_ = reinterpret_cast<double2*>(xs + X_ACC + lane * kAccStride);        \
+        _Pragma("unroll") for (int v_ = 0; v_ + 1 < (NV); v_ += 2) mine_[v_ / 2] = make_double2((vals)[v_], (vals)[v_ + 1]); \
+        if ((NV) & 1) xs[X_ACC + lane * kAccStride + (NV) - 1] = (vals)[(NV) - 1];         \
+        __syncwarp();                                                                       \
+        const double2* from_ = reinterpret_cast<const double2*>(xs + X_ACC + src_ * kAccStride); \
+        _Pragma("unroll") for (int v_ = 0; v_ + 1 < (NV); v_ += 2) {                        \
+            const double2 t_ = from_[v_ / 2];                                               \
+            (vals)[v_] += t_.x; (vals)[v_ + 1] += t_.y;                                     \
+        }                                                                                   \
+        if ((NV) & 1) (vals)[(NV) - 1] += xs[X_ACC + src_ * kAccStride + (NV) - 1];         \
+        __syncwarp();                                                                       \
+    } while (0)
+#else
 #define TRL_ACCUM_ROUND(r, NV, vals)                                                        \
     do {                                                                                    \
         const int src_ = (int)(lc.acc_src >> (5 * (r))) & 31;                               \
         _Pragma("unroll") for (int v_ = 0; v_ < (NV); ++v_) (vals)[v_] += shf((vals)[v_], src_); \
     } while (0)
+#endif
 
 // ================================================================================================ controller half
 // Returns the clamped joint torque of link `lane` (0 for the root and idle lanes).
@@ -664,7 +695,11 @@ __device__ double controller_torque(Lane& L, const LinkC& lc, const EnvRegs& e, 
 // One sub-step of articulated-body forward dynamics with linearly-implicit contact / joint-limit terms.
 // Updates e (q, qd, root translation) in place and returns the contact bitmask (same value in every lane).
 __device__ int physics_substep(const LinkC& lc, EnvRegs& e, const GroundView& g, const double* s_clx, const double* s_cly,
-                               const int* s_cbody, int lane, double dt, double clear_y) {
+                               const int* s_cbody, int lane, double dt, double clear_y
+#if TRL_ACCUM_SMEM
+                               , double* xs
+#endif
+                               ) {
     const ModelConst& m = c_model;
     const PhysParams& pp = m.phys;
     const int md = m.max_depth;
@@ -917,7 +952,11 @@ __global__ void __launch_bounds__(kBlockThreads, TRL_STEP_MIN_BLOCKS)
 trl_step_kernel(Buffers B, double h, int flags, int lists) {
     __shared__ double s_clx[4 * kMaxJoints], s_cly[4 * kMaxJoints];
     __shared__ int s_cbody[4 * kMaxJoints];
+#if TRL_ACCUM_SMEM
+    __shared__ __align__(16) double s_x[kWarpsPerBlock * X_END];
+#else
     __shared__ double s_x[kWarpsPerBlock * X_END];
+#endif
     const ModelConst& m = c_model;
     for (int t = threadIdx.x; t < m.n_corners; t += kBlockThreads) {
         s_clx[t] = m.corner_lx[t]; s_cly[t] = m.corner_ly[t]; s_cbody[t] = m.corner_body[t];
@@ -1019,7 +1058,11 @@ trl_step_kernel(Buffers B, double h, int flags, int lists) {
         // terrain maximum over the window the character's corners can reach during this env-step; kClearMargin covers the
         // contact tolerance measured along the surface normal on (near-)vertical cliff faces and the root's travel
         const double clear_y = g.window_max(e.ox - m.reach - 0.25, e.ox + m.reach + 0.25, lane) + kClearMargin;
+#if TRL_ACCUM_SMEM
+        for (int s = 0; s < ns; ++s) contact = physics_substep(lc, e, g, s_clx, s_cly, s_cbody, lane, dt, clear_y, xs);
+#else
         for (int s = 0; s < ns; ++s) contact = physics_substep(lc, e, g, s_clx, s_cly, s_cbody, lane, dt, clear_y);
+#endif
         // UpdateGround (scenarios/ScenarioSimChar.cpp:564-572): regenerate a segment when the view window crosses it
         {
             int smin = g.seg_id(0), smax = g.seg_id(1);
