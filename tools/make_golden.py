@@ -1,9 +1,8 @@
 """Generates the small golden fixtures under tests/golden/ from the CPU oracle (regression pins of the oracle itself).
 
-There are NO reference-side golden vectors: DeepTerrainRL ships no tests, and its binaries cannot be built here
-(Bullet/Eigen/Caffe/jsoncpp absent), so these fixtures pin the restated oracle against drift -- they are not
-reference outputs.  What *is* taken from the reference are the assets (tools/pack_scene.py) and the cross-file
-identities checked in tests/test_assets.py.
+These fixtures pin the restated oracle against drift -- they are not reference outputs (DeepTerrainRL ships no tests or golden
+vectors).  Reference-side fixtures exist too: tools/make_ref_golden.py writes tests/golden/ref_*.npz from the reference's own
+sources compiled into oracle/_ref.
 
     python tools/make_golden.py
 """
