@@ -405,8 +405,10 @@ void ref_ctrl_reset(RefCtrl* r) { r->ctrl->Reset(); }
 void ref_ctrl_update(RefCtrl* r, double h) { r->ctrl->Update(h); }
 // what cJoint::ApplyTorque would hand to the physics: the accumulated joint torque after cJoint::ClampTotalTorque with the limit
 // cPDController installed (sim/Joint.cpp:171-190,257-264, sim/PDController.cpp:99-100)
-void ref_ctrl_get_applied_tau(RefCtrl* r, double* out) {
-    FakeChar& ch = *r->chp;
+static void applied_tau(FakeChar& ch, double* out);
+void ref_ctrl_get_applied_tau(RefCtrl* r, double* out) { applied_tau(*r->chp, out); }
+}  // extern "C"
+static void applied_tau(FakeChar& ch, double* out) {
     cSimCharacter* sim = ch.sim();
     for (int i = 0; i < sim->GetNumDof(); ++i) out[i] = 0;
     for (int j = 0; j < sim->GetNumJoints(); ++j) {
@@ -416,6 +418,7 @@ void ref_ctrl_get_applied_tau(RefCtrl* r, double* out) {
         out[sim->GetParamOffset(j)] = t[2];
     }
 }
+extern "C" {
 void ref_ctrl_get_tau(RefCtrl* r, double* out) { for (int i = 0; i < r->chp->sim()->GetNumDof(); ++i) out[i] = r->chp->last_tau[i]; }
 // state, phase, action id, then the full parameter vector of the current action
 int ref_ctrl_get_fsm(RefCtrl* r, double* out, int cap) {
@@ -588,6 +591,7 @@ void ref_scn_get_state(RefScn* r, double* pose, double* vel, double* tau) {
     const int nd = ch.sim()->GetNumDof();
     for (int i = 0; i < nd; ++i) { pose[i] = ch.pose[i]; vel[i] = ch.vel[i]; tau[i] = ch.last_tau[i]; }
 }
+void ref_scn_get_applied_tau(RefScn* r, double* out) { applied_tau(*r->fake(), out); }      // as ref_ctrl_get_applied_tau
 int ref_scn_num_dof(RefScn* r) { return r->fake()->sim()->GetNumDof(); }
 int ref_scn_get_fsm(RefScn* r, double* out) {
     out[0] = r->ctrl()->GetState(); out[1] = r->ctrl()->GetPhase(); out[2] = r->ctrl()->GetCurrActionID();

@@ -29,6 +29,7 @@ def test_oracle_reproduces_the_compiled_reference_scenario(assets, scene):
     o = Oracle(os.path.join(assets, scene + ".trlpack"), 1, 0, terrain_seeds=[int(g["seed"])])
     o.L.orc_end_update.argtypes = [C.c_void_p, C.c_int, C.c_double]
     tau, fsm, root = g["tau"], g["fsm"], g["root"]
+    g = {k: g[k] for k in g.files}
     worst = 0.0
     k = 0
     for u in range(int(g["n_updates"])):
@@ -38,6 +39,8 @@ def test_oracle_reproduces_the_compiled_reference_scenario(assets, scene):
             err = np.max(np.abs(tau[k] - to)) / max(1.0, np.max(np.abs(to)))
             worst = max(worst, err)
             assert err < 1e-9, (scene, k, err)
+            held = o.get_state(0)[2]                     # what the physics receives: the reference's cJoint clamp vs the oracle's
+            assert np.max(np.abs(g["applied"][k] - held)) <= 1e-9 * max(1.0, np.max(np.abs(held))), (scene, k)
             if i == 19:                                  # the fixture's last sample of an update is taken after the reference's
                 o.L.orc_end_update(o.h, 0, 1.0 / 30.0)   # end-of-update handling (a reset puts the gait machine back to its start)
             oc = o.get_ctrl(0)

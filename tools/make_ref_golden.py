@@ -51,7 +51,10 @@ def scenario(scene, n_updates):
         ref.ref_scn_get_state(st["h"], _p(pose), _p(vel), _p(tau))
         f = np.zeros(3)
         ref.ref_scn_get_fsm(st["h"], _p(f))
+        ta = np.zeros(nd)
+        ref.ref_scn_get_applied_tau(st["h"], _p(ta))
         rec["tau"].append(tau)
+        rec["applied"].append(ta)
         rec["fsm"].append(f[:2].copy())
 
     def world(hh, user):
@@ -100,7 +103,8 @@ def scenario(scene, n_updates):
     ref.ref_scn_destroy(h)
     tau = np.array(rec["tau"])
     assert tau.shape == (20 * n_updates, nd)
-    np.savez_compressed(os.path.join(OUT, "ref_scenario_%s.npz" % scene), tau=tau, fsm=np.array(rec["fsm"]), root=np.array(rec["root"]),
+    np.savez_compressed(os.path.join(OUT, "ref_scenario_%s.npz" % scene), tau=tau, applied=np.array(rec["applied"]), fsm=np.array(rec["fsm"]),
+                        root=np.array(rec["root"]),
                         stats=np.array([cy.value, ep.value, ad.value]), dist_log=log[:n], seed=SEED, n_updates=n_updates)
     print(scene, tau.shape, "cycles", cy.value, "episodes", ep.value)
 
