@@ -278,7 +278,7 @@ __device__ void net_forward_cluster(cg::cluster_group& cluster, const NetWeights
 
 __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kDecideThreads, 2)
 trl_decide_kernel(Buffers B, NetWeights W, const ExpSettings* __restrict__ ex_dev, int* done_count, int list, int rearm) {
-    extern __shared__ double sh[];
+    TRL_DYN_SHARED(double, sh);
     cg::cluster_group cluster = cg::this_cluster();
     const ModelConst& m = c_model;
     const int rank = (int)cluster.block_rank();
@@ -373,7 +373,7 @@ cudaError_t configure_decide_kernel() {
 }
 void launch_decide(const Buffers& B, const NetWeights& W, const ExpSettings* ex, int* done_count, int grid, int list, int rearm,
                    cudaStream_t st) {
-    trl_decide_kernel<<<grid, kDecideThreads, decide_smem_bytes(), st>>>(B, W, ex, done_count, list, rearm);
+    TRL_LAUNCH_CLUSTER(kClusterSize, trl_decide_kernel, grid, kDecideThreads, decide_smem_bytes(), st, B, W, ex, done_count, list, rearm);
 }
 
 }  // namespace trl

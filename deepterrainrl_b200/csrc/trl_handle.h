@@ -53,4 +53,5 @@ struct trl_handle {
 // shared by the translation units behind the C ABI
 int trl_fail(const std::string& msg);                 // records the message for trl_last_error(), returns 1
 void trl_drop_graphs(trl_handle* h);
+extern "C" void trl_trainer_orphan(trl_trainer* t);              // trl_destroy with a trainer still attached (trl_train.cu)
 int trl_reupload_model(trl_handle* h);                // after editing h->mc: refresh the __constant__ copies                  // captured graphs bake kernel arguments (weight pointers) in

@@ -486,6 +486,7 @@ static trl_handle* create_common(trl_handle* h, int num_envs, int device, int mo
 
 int trl_destroy(trl_handle* h) {
     if (!h) return 0;
+    if (h->trainer) trl_trainer_orphan(h->trainer);   // the trainer object outlives its scenario as an inert shell
     if (g_model_owner == h) g_model_owner = nullptr;
     if (h->stream) cudaStreamSynchronize(h->stream);
     destroy_graphs(h);

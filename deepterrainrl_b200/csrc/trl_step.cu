@@ -1174,7 +1174,7 @@ __global__ void trl_terrain_kernel(Buffers B, double lookahead) {
     store_ground(L, g);
 }
 void launch_terrain(const Buffers& B, double lookahead, cudaStream_t st) {
-    trl_terrain_kernel<<<(B.n + 127) / 128, 128, 0, st>>>(B, lookahead);
+    TRL_LAUNCH(trl_terrain_kernel, (B.n + 127) / 128, 128, 0, st, B, lookahead);
 }
 
 // Batch statistics (cOptScenarioPoliEval::OutputResults merges the same counters under a mutex): one block reduces
@@ -1202,7 +1202,7 @@ __global__ void trl_stats_kernel(Buffers B, double* out) {
         }
     }
 }
-void launch_stats(const Buffers& B, double* out, cudaStream_t st) { trl_stats_kernel<<<1, 1024, 0, st>>>(B, out); }
+void launch_stats(const Buffers& B, double* out, cudaStream_t st) { TRL_LAUNCH(trl_stats_kernel, 1, 1024, 0, st, B, out); }
 
 // ---- host-side launch helpers (called from trl_host.cu)
 cudaError_t upload_model(const ModelConst& mc) { return cudaMemcpyToSymbol(c_model, &mc, sizeof(ModelConst)); }
@@ -1210,11 +1210,11 @@ size_t step_smem_bytes() { return 0; }
 cudaError_t configure_step_kernels() { return cudaSuccess; }
 void launch_step(const Buffers& B, double h, int flags, int lists, cudaStream_t st) {
     int blocks = (B.n + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    trl_step_kernel<<<blocks, kBlockThreads, 0, st>>>(B, h, flags, lists);
+    TRL_LAUNCH(trl_step_kernel, blocks, kBlockThreads, 0, st, B, h, flags, lists);
 }
 void launch_reset(const Buffers& B, const uint64_t* seeds, const int* env_ids, int count, int reseed, cudaStream_t st) {
     int blocks = (count + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    trl_reset_kernel<<<blocks, kBlockThreads, 0, st>>>(B, seeds, env_ids, count, reseed);
+    TRL_LAUNCH(trl_reset_kernel, blocks, kBlockThreads, 0, st, B, seeds, env_ids, count, reseed);
 }
 
 }  // namespace TRL_IMPL_NS

@@ -69,8 +69,10 @@ struct Dev {
 // stream be scheduled right away -- it parks at its own wait.  The dependency chain stays strictly serial; what disappears is
 // the launch latency between ~140 small dependent kernels per training iteration.
 __device__ __forceinline__ void pdl_sync() {
+#ifndef TRL_SIMT_EMU   // the test-only emulator runs launches strictly in order
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
 }
 template <typename... KArgs, typename... Args>
 void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
@@ -333,7 +335,7 @@ __global__ void k_conv_fwd(Dev d, int pred, const double* x, int ldn, int cin, i
                            double* y) {
     pdl_sync();
     if (!pred_on(d, pred)) return;
-    extern __shared__ double xs[];                         // [cin][win]
+    TRL_DYN_SHARED(double, xs);                            // [cin][win]
     __shared__ double ws[kConvOut][C1 * K2];              // cin * k <= 128 per output channel
     const int o0 = blockIdx.x * kConvOut, n = blockIdx.y, wout = win - k + 1, ck = cin * k;
     const double* xr = x + (size_t)n * ldn;
@@ -826,9 +828,24 @@ trl_trainer* trl_trainer_create(trl_handle* h, const double* p) {
     return t;
 }
 
+// trl_destroy of the scenario a trainer is still attached to: the trainer's device state goes with it; the (host) object stays
+// valid so that a later trl_trainer_destroy is harmless and every other call on it fails with a message instead of
+// touching freed memory.
+void trl_trainer_orphan(trl_trainer* t) {
+    if (!t || !t->h) return;
+    cudaStreamSynchronize(t->h->stream);
+    if (t->train_graph) { cudaGraphExecDestroy(t->train_graph); t->train_graph = nullptr; }
+    for (void* q : t->allocs) cudaFree(q);
+    t->allocs.clear();
+    t->h->trainer = nullptr;
+    t->h = nullptr;
+}
+#define TRL_TRAINER_LIVE(t) do { if (!(t) || !(t)->h) return trl_fail("trainer: the scenario it was attached to has been destroyed"); } while (0)
+
 int trl_trainer_destroy(trl_trainer* t) {
     if (!t) return 0;
     trl_handle* h = t->h;
+    if (!h) { delete t; return 0; }
     cudaStreamSynchronize(h->stream);
     // hand the weights back to the engine's own buffers so the scenario stays usable
     for (int b = 0; b < 26; ++b) cudaMemcpy(h->net_blobs[b], t->d.theta + t->d.off[b], (size_t)h->net_counts[b] * 8, cudaMemcpyDeviceToDevice);
@@ -850,6 +867,7 @@ int trl_trainer_destroy(trl_trainer* t) {
 
 // cNeuralNetLearner::Train's AddTuples(exp->GetTuples()) + ResetTupleBuffer, device to device
 int trl_trainer_add_from_scene(trl_trainer* t) {
+    TRL_TRAINER_LIVE(t);
     trl_handle* h = t->h;
     enqueue_add(t, h->B.tuples, h->B.tuple_flags, h->B.tuple_count, 0, h->B.tuple_cap, h->B.tuple_count, h->stream, h->B.tuple_env);
     TCK(cudaGetLastError());
@@ -857,6 +875,7 @@ int trl_trainer_add_from_scene(trl_trainer* t) {
 }
 // tuples handed in from host memory (the adapter path of INTEGRATION.md, and the tests)
 int trl_trainer_add_tuples(trl_trainer* t, const double* rows, const uint32_t* flags, int n) {
+    TRL_TRAINER_LIVE(t);
     trl_handle* h = t->h;
     for (int base = 0; base < n; base += t->stage_cap) {
         const int cnt = std::min(t->stage_cap, n - base);
@@ -872,6 +891,7 @@ int trl_trainer_add_tuples(trl_trainer* t, const double* rows, const uint32_t* f
 // tuples already on the device (e.g. the NCCL all-gather of every rank's tuple block, parallel.gather_tuple_blocks*): rows f64
 // [n][1 + S + A + S], flags u32 [n]; enqueued on the scenario's stream, which the caller must have ordered after the producer
 int trl_trainer_add_device(trl_trainer* t, const double* rows_dev, const uint32_t* flags_dev, int n) {
+    TRL_TRAINER_LIVE(t);
     if (n > t->stage_cap) return trl_fail("trl_trainer_add_device: more tuples than the staging capacity (split the call)");
     enqueue_add(t, rows_dev, flags_dev, nullptr, n, n, nullptr, t->h->stream);
     TCK(cudaGetLastError());
@@ -881,6 +901,7 @@ int trl_trainer_add_device(trl_trainer* t, const double* rows_dev, const uint32_
 // `iters` x cNeuralNetTrainer::Train() on the engine's stream (ordered after the update that produced the tuples and before
 // the next one, which then evaluates the updated weights)
 int trl_trainer_train(trl_trainer* t, int iters) {
+    TRL_TRAINER_LIVE(t);
     trl_handle* h = t->h;
     if (!t->train_graph) {
         cudaGraph_t graph;
@@ -909,6 +930,7 @@ int trl_trainer_train(trl_trainer* t, int iters) {
 //    sim/DogControllerMACE.cpp:93-99) and scaled by 1 / max_a |opt(a) - opt(default action)| over the action library;
 //  * input offset 0 / scale 1 until the init stage refits them from the replay memory; momentum history cleared; target = copy.
 int trl_trainer_init_fresh(trl_trainer* t, uint64_t seed) {
+    TRL_TRAINER_LIVE(t);
     trl_handle* h = t->h;
     const Dev& d = t->d;
     ModelConst& m = h->mc;
@@ -951,6 +973,7 @@ int trl_trainer_init_fresh(trl_trainer* t, uint64_t seed) {
 // trl_train_schedule.  Everything is enqueued on the scenario's stream; the call returns after the last update is queued
 // (iters_per_update > 0) -- synchronise with trl_sync / trl_trainer_counters.
 int trl_train_run(trl_trainer* t, const double* sp, int num_updates, int iters_per_update, int tuple_buffer_size, double time_step) {
+    TRL_TRAINER_LIVE(t);
     trl_handle* h = t->h;
     long long last_total = -1, carry = 0;
     long long iters_req = 0;
@@ -986,6 +1009,7 @@ int trl_train_run(trl_trainer* t, const double* sp, int num_updates, int iters_p
 
 // c[9]: iter, actor_iter, stage, num, head, total, critic buffer, actor buffer, pending actor batch; l[2]: last losses
 int trl_trainer_counters(trl_trainer* t, int64_t* c, double* l) {
+    TRL_TRAINER_LIVE(t);
     Counters hc;
     TCK(cudaStreamSynchronize(t->h->stream));
     TCK(cudaMemcpy(&hc, t->d.c, sizeof(hc), cudaMemcpyDeviceToHost));
@@ -1001,6 +1025,7 @@ int64_t trl_trainer_launches(trl_trainer* t) { return t->launches; }
 
 // what: 0 theta, 1 target theta, 2 history, 3 in_off, 4 in_scale, 5 out_off, 6 out_scale, 7 last gradient
 int trl_trainer_get(trl_trainer* t, int what, double* out) {
+    TRL_TRAINER_LIVE(t);
     const Dev& d = t->d;
     const double* src[8] = {d.theta, d.target, d.history, d.in_off, d.in_scale, d.out_off, d.out_scale, d.grad};
     const size_t cnt[8] = {(size_t)d.P, (size_t)d.P, (size_t)d.P, (size_t)d.S, (size_t)d.S, (size_t)d.n_out, (size_t)d.n_out, (size_t)d.P};
@@ -1011,6 +1036,7 @@ int trl_trainer_get(trl_trainer* t, int what, double* out) {
 }
 // cNeuralNetTrainer::LoadModel: weights (26 blobs concatenated in layer order) into the current AND the target net
 int trl_trainer_set_theta(trl_trainer* t, const double* theta) {
+    TRL_TRAINER_LIVE(t);
     TCK(cudaStreamSynchronize(t->h->stream));
     TCK(cudaMemcpy(t->d.theta, theta, (size_t)t->d.P * 8, cudaMemcpyHostToDevice));
     TCK(cudaMemcpy(t->d.target, t->d.theta, (size_t)t->d.P * 8, cudaMemcpyDeviceToDevice));
@@ -1018,6 +1044,7 @@ int trl_trainer_set_theta(trl_trainer* t, const double* theta) {
 }
 // replay rows (float, [n][1 + S + A + S]) and flags of the given slots
 int trl_trainer_rows(trl_trainer* t, const int32_t* ids, int n, float* rows, int32_t* flags) {
+    TRL_TRAINER_LIVE(t);
     TCK(cudaStreamSynchronize(t->h->stream));
     for (int i = 0; i < n; ++i) {
         if (ids[i] < 0 || ids[i] >= t->d.cap) return trl_fail("trl_trainer_rows: slot out of range");
@@ -1028,6 +1055,7 @@ int trl_trainer_rows(trl_trainer* t, const int32_t* ids, int n, float* rows, int
 }
 // which: 0 critic buffer, 1 actor buffer, 2 pending actor batch, 3 ids of the last sampled batch; returns the length
 int trl_trainer_list(trl_trainer* t, int which, int32_t* out, int cap, int* len) {
+    TRL_TRAINER_LIVE(t);
     Counters hc;
     TCK(cudaStreamSynchronize(t->h->stream));
     TCK(cudaMemcpy(&hc, t->d.c, sizeof(hc), cudaMemcpyDeviceToHost));

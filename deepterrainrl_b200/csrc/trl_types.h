@@ -8,6 +8,19 @@
 #pragma once
 #include <cstdint>
 
+// Kernel launches and dynamic shared memory are spelled through two macros so that the same sources also compile for the
+// test-only SIMT emulator (tests/simt/, -DTRL_SIMT_EMU: g++, one fiber per CUDA thread).  In the product build they expand to
+// exactly the CUDA syntax they name.
+#ifdef TRL_SIMT_EMU
+#define TRL_LAUNCH(kern, grid, block, smem, st, ...) SIMT_LAUNCH(1, kern, grid, block, smem, st, __VA_ARGS__)
+#define TRL_LAUNCH_CLUSTER(csize, kern, grid, block, smem, st, ...) SIMT_LAUNCH(csize, kern, grid, block, smem, st, __VA_ARGS__)
+#define TRL_DYN_SHARED(type, name) type* name = reinterpret_cast<type*>(simt::dyn_smem())
+#else
+#define TRL_LAUNCH(kern, grid, block, smem, st, ...) kern<<<grid, block, smem, st>>>(__VA_ARGS__)
+#define TRL_LAUNCH_CLUSTER(csize, kern, grid, block, smem, st, ...) kern<<<grid, block, smem, st>>>(__VA_ARGS__)   // cluster size: __cluster_dims__ of the kernel
+#define TRL_DYN_SHARED(type, name) extern __shared__ type name[]
+#endif
+
 namespace trl {
 
 constexpr int kMaxJoints = 21;      // dog / goat: 21 joints, raptor: 19

@@ -1,0 +1,212 @@
+"""The CUDA kernel *sources* executed on the CPU, thread for thread, by the test-only SIMT emulator (tests/simt/): every CUDA
+thread is a fiber, warp collectives / __syncthreads / cluster.sync() are barriers, streams run in issue order, graphs replay.
+
+What this tier pins without a GPU (the `-m gpu` tests remain the parity tests proper -- the emulator's arithmetic is not
+FMA-contracted, so it is not the GPU's rounding):
+  * the env-step, decision, terrain, reset, statistics and trainer kernels, driven through the real host code behind the C ABI
+    (graph capture, overlapped two-stream schedule, pending lists), against the CPU oracle;
+  * convergence: a collective some live lane does not reach deadlocks the fibers and aborts the test;
+  * races: with a seeded scheduler the lanes of a warp run in varying orders between collectives, so a shared-memory hand-off
+    without its barrier gives seed-dependent results -- results must be bit-identical across seeds;
+  * experimental kernel variants (TRL_NVCC_EXTRA knobs of the nvcc build) are bit-identical to the default build before any
+    GPU time is spent on them.
+Nothing here is a fallback of the product: the library is built under tests/simt/_build/ and only this file loads it."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "simt"))
+from loader import open_simt, simt_library  # noqa: E402
+
+H = 1.0 / 600.0
+
+
+def _relerr(a, b):
+    return np.max(np.abs(a - b) / (1.0 + np.abs(b)))
+
+
+# ------------------------------------------------------------------------------------------------ the emulator itself
+def _selftest(L, which, arg=0, seed=0):
+    out = np.zeros(4096, np.int32)
+    L.simt_set_sched_seed(C.c_ulonglong(seed))
+    try:
+        assert L.simt_selftest(which, out.ctypes.data_as(C.c_void_p), arg) == 0
+    finally:
+        L.simt_set_sched_seed(C.c_ulonglong(0))
+    return out
+
+
+def test_emulator_collectives_clusters_and_race_detection():
+    L = open_simt()
+    o = _selftest(L, 0)   # shuffle from lane+1, ballot of the odd lanes, xor-butterfly sum, double shuffle
+    for blk in range(3):
+        for t in range(64):
+            lane = t & 31
+            assert o[blk * 64 + t] == 100 * blk + (t & 32) + ((lane + 1) & 31) + 1000 * 16 + 100000 * 496
+    # shared-memory neighbour exchange: with its __syncwarp the result does not depend on the schedule ...
+    ref = _selftest(L, 1, 1)
+    for r in range(4):
+        for t in range(64):
+            assert ref[r * 64 + t] == 10 * r + ((t & 32) | ((t + 1) & 31))
+    assert all(np.array_equal(ref, _selftest(L, 1, 1, s)) for s in (7, 77, 123456))
+    # ... without it, it does: this is how the kernel tests below would see a missing barrier
+    assert any(not np.array_equal(_selftest(L, 1, 0), _selftest(L, 1, 0, s)) for s in (7, 77, 123456))
+    o = _selftest(L, 2)   # 2 clusters x 4 CTAs x 96 threads: rank r reads rank r+1's dynamic shared memory
+    for blk in range(8):
+        peer = (blk // 4) * 4 + (blk % 4 + 1) % 4
+        for t in range(96):
+            assert o[blk * 96 + t] == 1000 * peer + (t + 3) % 96
+    o = _selftest(L, 3)   # __syncthreads_or + barriers after two of four warps have exited
+    assert (o[:64] == 100000 + 2016).all() and (o[64:256] == 0).all()
+
+
+# ------------------------------------------------------------------------------------------------ kernels vs the oracle
+def _pair(assets, name, n, mode=0, rng_seed=1234):
+    from pyoracle import Oracle
+    import deepterrainrl_b200 as trl
+    pack = os.path.join(assets, name)
+    cls = trl.ScenarioExpMACE if mode else trl.ScenarioPoliEval
+    return cls(pack, n, rng_seed=rng_seed), Oracle(pack, n, mode, rng_seed=rng_seed)
+
+
+def test_step_kernel_flat_dog_vs_oracle(assets):
+    """BASELINE config 1 through the kernel source: q, qd, torques, contact bits, gait state every step."""
+    with simt_library():
+        g, o = _pair(assets, "dog_flat.trlpack", 1)
+        for k in range(120):
+            g.EnvStep(H)
+            o.env_step(0, H)
+            gq, gqd, gt, gc = g.GetState(0)
+            oq, oqd, ot, oc = o.get_state(0)
+            assert _relerr(gq, oq) < 1e-9 and _relerr(gqd, oqd) < 1e-8 and _relerr(gt, ot) < 1e-8, k
+            np.testing.assert_array_equal(gc, oc)
+            assert g.GetCtrl(0)[0] == o.get_ctrl(0)[0]
+        g.close()
+
+
+@pytest.mark.parametrize("scene,steps", [("dog_slopes_mixed", 140), ("raptor_narrow_gaps", 100), ("goat_cliffs", 100)])
+def test_step_and_decision_kernels_vs_oracle(assets, scene, steps):
+    """Policy in the loop: terrain bit-exact, the cluster decision kernel's network output, states after the decisions."""
+    n = 3
+    with simt_library():
+        g, o = _pair(assets, scene + ".trlpack", n)
+        for env in range(n):
+            for seg in (0, 1):
+                gd, gmx, gfl = g.GetTerrain(env, seg)
+                od, omx, ofl = o.terrain(env, seg)
+                assert gmx == omx and gfl == ofl
+                np.testing.assert_array_equal(gd, od)
+        for k in range(steps):
+            g.EnvStep(H)
+            for e in range(n):
+                o.env_step(e, H)
+        for e in range(n):
+            gq, gqd, gt, gc = g.GetState(e)
+            oq, oqd, ot, oc = o.get_state(e)
+            assert _relerr(gq, oq) < 1e-8 and _relerr(gqd, oqd) < 1e-7, (scene, e)
+            np.testing.assert_array_equal(gc, oc)
+        np.testing.assert_allclose(g.GetPoliState(0), o.poli_state(0), rtol=1e-9, atol=1e-9)
+        np.testing.assert_allclose(g.GetNetOut(0), o.net_out(0), rtol=1e-8, atol=1e-8)
+        g.close()
+
+
+def test_update_graph_overlapped_schedule_and_tuples_vs_oracle(assets):
+    """trl_update: captured graph, two-stream schedule with catch-up launches, exploration on; tuples and counters."""
+    n = 4
+    with simt_library():
+        g, o = _pair(assets, "dog_slopes_mixed.trlpack", n, mode=1)
+        g.EnableExplore(1, 0.2, 0.025, 0.002)
+        o.set_explore(1, 0.2, 0.025, 0.002)
+        for k in range(45):
+            g.Update(1.0 / 30.0)
+            o.update(1.0 / 30.0, threads=4)
+        gr, gf, ge = g.GetTuples(f64=True)
+        orr, of, oe = o.tuples()
+        assert gr.shape == orr.shape and gr.shape[0] > 0
+        gi = np.lexsort((np.arange(len(ge)), ge))
+        oi = np.lexsort((np.arange(len(oe)), oe))
+        np.testing.assert_array_equal(ge[gi], oe[oi])
+        np.testing.assert_array_equal(gf[gi], of[oi])
+        np.testing.assert_allclose(gr[gi], orr[oi], rtol=1e-7, atol=1e-7)
+        g.close()
+
+
+def test_trainer_kernels_vs_oracle(assets):
+    from pyoracle import OracleTrainer
+    from test_gpu_trainer import _synthetic_tuples
+    import deepterrainrl_b200 as trl
+    pack = os.path.join(assets, "dog_slopes_mixed.trlpack")
+    kw = dict(num_init_samples=96, num_steps_per_iter=1, freeze_target_iters=3, init_input_offset_scale=1, seed=21)
+    with simt_library():
+        sc = trl.ScenarioExpMACE(pack, 4)
+        g = trl.MACETrainer(sc, replay_mem_size=160, **kw)
+        o = OracleTrainer(pack, replay_cap=160, **kw)
+        rows, flags = _synthetic_tuples(128, g.S, g.A, o.get("in_off"), o.get("in_scale"), 3)
+        g.AddTuples(rows, flags)
+        o.add_tuples(rows, flags)
+        for it in range(2):   # the second iteration includes an actor step
+            g.Train(1)
+            o.train()
+            cg, co = g.counters(), o.counters()
+            for k in ("iter", "actor_iter", "stage", "num", "head", "total", "critic", "actor", "actor_batch"):
+                assert cg[k] == co[k], (it, k)
+            np.testing.assert_array_equal(g.lists("critic"), o.lists("critic"))
+            tg, to = g.get("theta"), o.get("theta")
+            assert np.max(np.abs(tg - to)) <= 1e-12 * max(1.0, np.max(np.abs(to))), it
+        assert co["actor_iter"] >= 1
+        # destroying the scenario first leaves the trainer an inert shell: calls fail with a message, destroy is harmless
+        sc.close()
+        with pytest.raises(RuntimeError, match="has been destroyed"):
+            g.Train(1)
+        g.close()
+
+
+# ------------------------------------------------------------------------------------------------ schedules and variants
+def _trajectory(defines, pack, n, steps, seed=0, updates=0):
+    import deepterrainrl_b200 as trl
+    with simt_library(defines) as L:
+        L.simt_set_sched_seed(C.c_ulonglong(seed))
+        try:
+            g = trl.ScenarioPoliEval(pack, n)
+            out = []
+            for k in range(steps):
+                g.EnvStep(H)
+                if k % 10 == 9:
+                    q, qd = g.GetStateAll()
+                    out.append(np.concatenate([q, qd]).copy())
+            for k in range(updates):
+                g.Update(1.0 / 30.0)
+                q, qd = g.GetStateAll()
+                out.append(np.concatenate([q, qd]).copy())
+            g.close()
+        finally:
+            L.simt_set_sched_seed(C.c_ulonglong(0))
+        return np.stack(out)
+
+
+def test_kernels_have_no_schedule_dependent_results(assets):
+    """Race check: the lanes of every warp run in seed-dependent orders between collectives; a shared-memory hand-off
+    (mass matrix, L^T read-back, corner tables, decision activations, pending lists) without its barrier would show."""
+    pack = os.path.join(assets, "dog_slopes_mixed.trlpack")
+    ref = _trajectory([], pack, 3, 130, 0, updates=2)
+    for seed in (11, 2024):
+        assert np.array_equal(ref, _trajectory([], pack, 3, 130, seed, updates=2)), seed
+
+
+VARIANTS = [
+    ["-DTRL_ACCUM_SMEM=1"],
+]
+
+
+@pytest.mark.parametrize("defines", VARIANTS, ids=lambda d: " ".join(d))
+@pytest.mark.parametrize("scene", ["dog_slopes_mixed", "raptor_narrow_gaps"])
+def test_experimental_variant_is_bit_identical(assets, defines, scene):
+    """Opt-in builds of the step kernel (profiles/step_kernel_r01_source_phases.md) only move data differently: same values,
+    same operation order -> bit-identical trajectories, also under a permuted lane schedule."""
+    pack = os.path.join(assets, scene + ".trlpack")
+    ref = _trajectory([], pack, 3, 130)
+    assert np.array_equal(ref, _trajectory(defines, pack, 3, 130))
+    assert np.array_equal(ref, _trajectory(defines, pack, 3, 130, seed=99))
