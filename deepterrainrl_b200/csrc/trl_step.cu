@@ -55,15 +55,83 @@ constexpr int kZeroLane = 31;   // always idle (nj <= 23): its per-link register
 constexpr int kTri = kMaxDof * (kMaxDof + 1) / 2;   // 276
 // per-warp shared scratch (doubles)
 constexpr int X_M = 0;
-#ifndef TRL_ACCUM_SMEM
-#define TRL_ACCUM_SMEM 0          // 1: child -> parent hand-off of the inward rounds through shared memory instead of shuffles (experiment)
+// Experiments (profiles/step_kernel_r01_source_phases.md: shuffles are 27 % of the kernel's instructions).  Each knob moves one
+// family of lane-to-lane exchanges from warp shuffles (2 SHFL + register moves per double) to per-warp shared memory (128-bit
+// stores / loads); values and operation order are untouched, so every variant is bit-identical to the default build
+// (tests/test_simt_cpu.py checks that on the CPU emulator).  Default build: all off, SASS unchanged.  -DTRL_SMEM_XCHG=1: all on.
+#ifndef TRL_SMEM_XCHG
+#define TRL_SMEM_XCHG 0
 #endif
-#if TRL_ACCUM_SMEM
+#ifndef TRL_ACCUM_SMEM
+#define TRL_ACCUM_SMEM TRL_SMEM_XCHG     // child -> parent hand-off of the inward rounds (9 doubles x 9 rounds x 5 sub-steps)
+#endif
+#ifndef TRL_LDLT_SMEM
+#define TRL_LDLT_SMEM TRL_SMEM_XCHG      // pivot column of the register LDL^T + fused forward substitution (253 + 23 doubles)
+#endif
+#ifndef TRL_KIN_SMEM
+#define TRL_KIN_SMEM TRL_SMEM_XCHG       // pointer-jumping prefix sums of the kinematics (26 doubles x 6 per env-step)
+#endif
+#ifndef TRL_OUTWARD_SMEM
+#define TRL_OUTWARD_SMEM TRL_SMEM_XCHG   // parent -> child accelerations of the outward pass + floating-base broadcast (36 doubles x 5)
+#endif
+#ifndef TRL_CONTACT_SMEM
+#define TRL_CONTACT_SMEM TRL_SMEM_XCHG   // corner lanes read their body's kinematics, owners collect contact forces (7-21 + 9 per contact, x 5)
+#endif
+#define TRL_SMEM_ALIGNED (TRL_ACCUM_SMEM || TRL_LDLT_SMEM || TRL_KIN_SMEM || TRL_OUTWARD_SMEM || TRL_CONTACT_SMEM)
+constexpr int X_M_END = X_M + kTri + 4;
+#if TRL_ACCUM_SMEM || TRL_CONTACT_SMEM
 constexpr int kAccStride = 10;                              // doubles per lane slot: 9 values, padded to 80 B (128-bit accesses stay conflict-free)
-constexpr int X_ACC = (X_M + kTri + 4 + 1) & ~1;            // 16-byte aligned
-constexpr int X_END = X_ACC + kWarp * kAccStride;
+constexpr int X_ACC = (X_M_END + 1) & ~1;                   // 16-byte aligned
+constexpr int X_ACC_END = X_ACC + kWarp * kAccStride;
 #else
-constexpr int X_END = X_M + kTri + 4;
+constexpr int X_ACC_END = X_M_END;
+#endif
+#if TRL_LDLT_SMEM
+constexpr int kColStride = kWarp + 2;                       // 32 column entries + the solved right-hand-side entry, even (16-byte rows)
+constexpr int X_COL = (X_ACC_END + 1) & ~1;                 // two buffers: step j writes buffer j & 1
+constexpr int X_COL_END = X_COL + 2 * kColStride;
+#else
+constexpr int X_COL_END = X_ACC_END;
+#endif
+#if TRL_KIN_SMEM
+constexpr int X_PFX = (X_COL_END + 1) & ~1;                 // three buffers of 32 double2: prefix rounds alternate 0 / 1, buffer 2 = (cos, sin) exchange
+constexpr int X_PFX_END = X_PFX + 3 * 2 * kWarp;
+#else
+constexpr int X_PFX_END = X_COL_END;
+#endif
+#if TRL_OUTWARD_SMEM
+constexpr int kOutBuf = 3 * kWarp;                          // (aw, ax) as double2 [32] + ay [32]
+constexpr int X_OUT = (X_PFX_END + 1) & ~1;                 // two buffers (level parity) + the 9 floating-base values of lane 0
+constexpr int X_BASE = X_OUT + 2 * kOutBuf;
+constexpr int X_OUT_END = X_BASE + 10;
+#else
+constexpr int X_OUT_END = X_PFX_END;
+#endif
+#if TRL_CONTACT_SMEM
+constexpr int X_KIN = (X_OUT_END + 1) & ~1;                 // per-link (cw, sw) | (rx, ry) | (w, vx) as double2 [32] each, vy [32]
+constexpr int X_KIN_END = X_KIN + 7 * kWarp;
+#else
+constexpr int X_KIN_END = X_OUT_END;
+#endif
+constexpr int X_END = TRL_SMEM_ALIGNED ? ((X_KIN_END + 1) & ~1) : X_KIN_END;
+// the scratch pointer is only threaded through the helpers that need it, so the default build's code is untouched
+#if TRL_KIN_SMEM
+#define TRL_KIN_XS_DECL , double* xs, int lane
+#define TRL_KIN_XS_ARG , xs, lane
+#define TRL_RESET_XS_DECL , double* xs
+#define TRL_RESET_XS_ARG , xs
+#else
+#define TRL_KIN_XS_DECL
+#define TRL_KIN_XS_ARG
+#define TRL_RESET_XS_DECL
+#define TRL_RESET_XS_ARG
+#endif
+#if TRL_SMEM_ALIGNED
+#define TRL_PHYS_XS_DECL , double* xs
+#define TRL_PHYS_XS_ARG , xs
+#else
+#define TRL_PHYS_XS_DECL
+#define TRL_PHYS_XS_ARG
 #endif
 
 __device__ __forceinline__ int tri(int a, int b) { return a * (a + 1) / 2 + b; }  // a >= b
@@ -334,6 +402,22 @@ __device__ __forceinline__ LinkC load_link(int lane) {
 // root-ward prefix sums over the kinematic tree by pointer jumping: after 4 rounds every link holds the sum of its own
 // value and those of all its ancestors (depth <= 15), using the static 2^k-th ancestor table.  A missing ancestor points
 // at lane 31, which is idle and holds zeros, so the adds need no predicate.
+#if TRL_KIN_SMEM
+// the same rounds through shared memory: every lane stores its pair, the receiver loads the pair of its 2^r-th ancestor.
+// Rounds alternate between two buffers, so one __syncwarp per round suffices (a buffer is rewritten two rounds later, and
+// the barrier of the round in between orders that write after every read).  `xs`, `lane` must be in scope.
+#define TRL_TREE_PREFIX2(a, b)                                                                  \
+    do {                                                                                        \
+        _Pragma("unroll") for (int r_ = 0; r_ < 4; ++r_) {                                      \
+            int an_ = (r_ == 0) ? c.anc1 : ((r_ == 1) ? c.anc2 : ((r_ == 2) ? c.anc4 : c.anc8)); \
+            double2* buf_ = reinterpret_cast<double2*>(xs + X_PFX + (r_ & 1) * 2 * kWarp);      \
+            buf_[lane] = make_double2((a), (b));                                                \
+            __syncwarp();                                                                       \
+            const double2 t_ = buf_[an_];                                                       \
+            (a) += t_.x; (b) += t_.y;                                                           \
+        }                                                                                       \
+    } while (0)
+#else
 #define TRL_TREE_PREFIX2(a, b)                                                                  \
     do {                                                                                        \
         _Pragma("unroll") for (int r_ = 0; r_ < 4; ++r_) {                                      \
@@ -343,15 +427,28 @@ __device__ __forceinline__ LinkC load_link(int lane) {
         }                                                                                       \
     } while (0)
 
+#endif
+
 // outward kinematics: world rotation, joint origin (rel. O) and spatial velocity of every link
-__device__ __forceinline__ Kin kinematics(const LinkC& c, const EnvRegs& e) {
+__device__ __forceinline__ Kin kinematics(const LinkC& c, const EnvRegs& e TRL_KIN_XS_DECL) {
     Kin k;
     double phi = e.q, w = e.qd;
     TRL_TREE_PREFIX2(phi, w);
     k.phi = phi; k.w = w;
     sincos(phi, &k.sw, &k.cw);
     // offset of this joint from its parent's joint, in world axes
+#if TRL_KIN_SMEM
+    double pcw, psw;
+    {
+        double2* buf = reinterpret_cast<double2*>(xs + X_PFX + 2 * 2 * kWarp);
+        buf[lane] = make_double2(k.cw, k.sw);
+        __syncwarp();
+        const double2 t = buf[c.parent];
+        pcw = t.x; psw = t.y;
+    }
+#else
     double pcw = shf(k.cw, c.parent), psw = shf(k.sw, c.parent);
+#endif
     double rx = 0.0, ry = 0.0;
     if (c.depth > 0) { rx = pcw * c.ax - psw * c.ay; ry = psw * c.ax + pcw * c.ay; }
     TRL_TREE_PREFIX2(rx, ry);
@@ -532,6 +629,33 @@ __device__ double controller_torque(Lane& L, const LinkC& lc, const EnvRegs& e, 
     }
     // register-resident LDL^T: pivot broadcast by shuffle, trailing update predicated on lane >= column
     double diag = 1.0;
+#if TRL_LDLT_SMEM
+    // Experiment: the pivot column travels through shared memory -- every lane stores its A_ij once, all lanes read the column
+    // entries as broadcast 128-bit loads -- and the forward substitution rides along (y_j is final at step j).  Same
+    // operations in the same order per lane as the shuffle form below, so the results are bit-identical.
+    double y = rhs;
+#pragma unroll
+    for (int j = 0; j < kMaxDof; ++j) {
+        double* col = xs + X_COL + (j & 1) * kColStride;
+        col[lane] = row[j];
+        if (lane == j) col[kWarp] = y;
+        __syncwarp();
+        double dj = col[j];
+        if (j >= nd) dj = 1.0;
+        const double inv = 1.0 / dj;
+        if (lane == j) diag = dj;
+        const double lij = row[j] * inv;
+#pragma unroll
+        for (int c0 = (j + 1) & ~1; c0 < kMaxDof; c0 += 2) {
+            const double2 t = *reinterpret_cast<const double2*>(col + c0);
+            if (c0 > j && lane >= c0) row[c0] -= lij * t.x;
+            if (c0 + 1 < kMaxDof && lane >= c0 + 1) row[c0 + 1] -= lij * t.y;
+        }
+        const double yj = col[kWarp];
+        if (lane > j) { y -= lij * yj; row[j] = lij; }
+    }
+    y /= diag;
+#else
 #pragma unroll
     for (int j = 0; j < kMaxDof; ++j) {
         double dj = shf(row[j], j);
@@ -555,6 +679,7 @@ __device__ double controller_torque(Lane& L, const LinkC& lc, const EnvRegs& e, 
         if (lane > c) y -= row[c] * yc;
     }
     y /= diag;
+#endif
 #pragma unroll
     for (int c = 0; c < kMaxDof; ++c) if (lane < nd && c < lane) M[tri(lane, c)] = row[c];
     __syncwarp();
@@ -695,15 +820,11 @@ __device__ double controller_torque(Lane& L, const LinkC& lc, const EnvRegs& e, 
 // One sub-step of articulated-body forward dynamics with linearly-implicit contact / joint-limit terms.
 // Updates e (q, qd, root translation) in place and returns the contact bitmask (same value in every lane).
 __device__ int physics_substep(const LinkC& lc, EnvRegs& e, const GroundView& g, const double* s_clx, const double* s_cly,
-                               const int* s_cbody, int lane, double dt, double clear_y
-#if TRL_ACCUM_SMEM
-                               , double* xs
-#endif
-                               ) {
+                               const int* s_cbody, int lane, double dt, double clear_y TRL_PHYS_XS_DECL) {
     const ModelConst& m = c_model;
     const PhysParams& pp = m.phys;
     const int md = m.max_depth;
-    Kin k = kinematics(lc, e);
+    Kin k = kinematics(lc, e TRL_KIN_XS_ARG);
 
     // rigid inertia about O, bias force incl. gravity as an external force
     const double hx = lc.mass * k.cx, hy = lc.mass * k.cy, Io = lc.izz_c + lc.mass * (k.cx * k.cx + k.cy * k.cy);
@@ -721,18 +842,38 @@ __device__ int physics_substep(const LinkC& lc, EnvRegs& e, const GroundView& g,
     // ---- contacts: one box corner per lane per round against the height field
     int contact = 0;
     const int nc = m.n_corners;
+#if TRL_CONTACT_SMEM
+    // per-link kinematics staged once per sub-step; a corner lane reads the entries of the body it belongs to
+    double2* kin0 = reinterpret_cast<double2*>(xs + X_KIN);                  // (cw, sw)
+    double2* kin1 = reinterpret_cast<double2*>(xs + X_KIN + 2 * kWarp);      // (rx, ry)
+    double2* kin2 = reinterpret_cast<double2*>(xs + X_KIN + 4 * kWarp);      // (w, vx)
+    double* kin3 = xs + X_KIN + 6 * kWarp;                                   // vy
+    kin0[lane] = make_double2(k.cw, k.sw); kin1[lane] = make_double2(k.rx, k.ry);
+    kin2[lane] = make_double2(k.w, k.vx); kin3[lane] = k.vy;
+    __syncwarp();
+#endif
     for (int base = 0; base < nc; base += kWarp) {
         const int ci = base + lane;
         const bool valid = ci < nc;
         const int b = valid ? s_cbody[ci] : 0;
         const double lx = valid ? s_clx[ci] : 0.0, ly = valid ? s_cly[ci] : 0.0;
+#if TRL_CONTACT_SMEM
+        const double2 k0_ = kin0[b], k1_ = kin1[b];
+        const double bcw = k0_.x, bsw = k0_.y, brx = k1_.x, bry = k1_.y;
+#else
         const double bcw = shf(k.cw, b), bsw = shf(k.sw, b), brx = shf(k.rx, b), bry = shf(k.ry, b);
+#endif
         const double rpx = brx + bcw * lx - bsw * ly, rpy = bry + bsw * lx + bcw * ly;   // corner rel. O
         // broad phase: a corner above clear_y (terrain maximum under the character + margin) cannot be within the
         // contact tolerance; a round with no candidate corner is skipped by the whole warp
         const bool cand = valid && (e.oy + rpy <= clear_y);
         if (!__any_sync(kFull, cand)) continue;
+#if TRL_CONTACT_SMEM
+        const double2 k2_ = kin2[b];
+        const double bw = k2_.x, bvx = k2_.y, bvy = kin3[b];
+#else
         const double bw = shf(k.w, b), bvx = shf(k.vx, b), bvy = shf(k.vy, b);
+#endif
         double add[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
         bool touching = false;
         if (cand) {
@@ -767,6 +908,31 @@ __device__ int physics_substep(const LinkC& lc, EnvRegs& e, const GroundView& g,
         unsigned fmask = __ballot_sync(kFull, add[3] != 0.0 || add[5] != 0.0);
         const int cb = lc.act ? m.corner_base[lane] : -1;
         const bool mine = cb >= base && cb < base + kWarp;
+#if TRL_CONTACT_SMEM
+        if (fmask) {
+            // force-producing corner lanes publish their 9 values; the lane that owns the body adds its (up to 4) corners in
+            // corner order -- the order the shuffle loop below visits them in
+            double* slot = xs + X_ACC + lane * kAccStride;
+            if ((fmask >> lane) & 1u) {
+                double2* s2 = reinterpret_cast<double2*>(slot);
+                s2[0] = make_double2(add[0], add[1]); s2[1] = make_double2(add[2], add[3]); s2[2] = make_double2(add[4], add[5]);
+                s2[3] = make_double2(add[6], add[7]); slot[8] = add[8];
+            }
+            __syncwarp();
+            const unsigned my = mine ? ((fmask >> (cb - base)) & 0xfu) : 0u;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if ((my >> q) & 1u) {
+                    const double* from = xs + X_ACC + (cb - base + q) * kAccStride;
+                    const double2* f2 = reinterpret_cast<const double2*>(from);
+                    const double2 t0 = f2[0], t1 = f2[1], t2 = f2[2], t3 = f2[3];
+                    ia[0] += t0.x; ia[1] += t0.y; ia[2] += t1.x; ia[3] += t1.y; ia[4] += t2.x; ia[5] += t2.y;
+                    ia[6] += t3.x; ia[7] += t3.y; ia[8] += from[8];
+                }
+            }
+            __syncwarp();
+        }
+#else
         while (fmask) {
             const int src = __ffs(fmask) - 1;
             fmask &= fmask - 1;
@@ -777,6 +943,7 @@ __device__ int physics_substep(const LinkC& lc, EnvRegs& e, const GroundView& g,
                 if (to_me) ia[v] += t;
             }
         }
+#endif
         if (mine && ((tmask >> (cb - base)) & 0xfu)) contact |= 1 << lane;
     }
     contact = (int)__ballot_sync(kFull, contact != 0);   // lane index == link index
@@ -813,8 +980,22 @@ __device__ int physics_substep(const LinkC& lc, EnvRegs& e, const GroundView& g,
     // floating base: solve IA_0 a_0 = -pA_0 (symmetric 3x3 LDL^T); every lane computes it from lane 0's values
     double a0, a1, a2;
     {
+#if TRL_OUTWARD_SMEM
+        double* bs = xs + X_BASE;
+        if (lane == 0) {
+            double2* b2 = reinterpret_cast<double2*>(bs);
+            b2[0] = make_double2(ia[0], ia[1]); b2[1] = make_double2(ia[2], ia[3]); b2[2] = make_double2(ia[4], ia[5]);
+            b2[3] = make_double2(ia[6], ia[7]); bs[8] = ia[8];
+        }
+        __syncwarp();
+        const double2 q0 = reinterpret_cast<const double2*>(bs)[0], q1 = reinterpret_cast<const double2*>(bs)[1],
+                      q2 = reinterpret_cast<const double2*>(bs)[2], q3 = reinterpret_cast<const double2*>(bs)[3];
+        double a = q0.x, bx = q0.y, by = q1.x, cxx = q1.y, cxy = q2.x, cyy = q2.y;
+        double r0 = -q3.x, r1 = -q3.y, r2 = -bs[8];
+#else
         double a = shf(ia[0], 0), bx = shf(ia[1], 0), by = shf(ia[2], 0), cxx = shf(ia[3], 0), cxy = shf(ia[4], 0), cyy = shf(ia[5], 0);
         double r0 = -shf(ia[6], 0), r1 = -shf(ia[7], 0), r2 = -shf(ia[8], 0);
+#endif
         const double i0 = 1.0 / a, l10 = bx * i0, l20 = by * i0;
         const double d1 = cxx - l10 * bx, i1 = 1.0 / d1, t21 = cxy - l20 * bx, l21 = t21 * i1;
         const double d2 = cyy - l20 * by - l21 * t21, i2 = 1.0 / d2;
@@ -825,7 +1006,18 @@ __device__ int physics_substep(const LinkC& lc, EnvRegs& e, const GroundView& g,
     double aw = a0, alx = a1, aly = a2;
     const double thd0 = shf(e.qd, 0);
     for (int l = 1; l <= md; ++l) {
+#if TRL_OUTWARD_SMEM
+        // every lane publishes its current (aw, ax, ay); a link of depth l reads its parent's, which is final since level l-1.
+        // Levels alternate between two buffers: one barrier per level (see TRL_TREE_PREFIX2)
+        double2* o2 = reinterpret_cast<double2*>(xs + X_OUT + (l & 1) * kOutBuf);
+        double* o1 = xs + X_OUT + (l & 1) * kOutBuf + 2 * kWarp;
+        o2[lane] = make_double2(aw, alx); o1[lane] = aly;
+        __syncwarp();
+        const double2 pp_ = o2[lc.parent];
+        const double paw = pp_.x, pax = pp_.y, pay = o1[lc.parent];
+#else
         double paw = shf(aw, lc.parent), pax = shf(alx, lc.parent), pay = shf(aly, lc.parent);
+#endif
         if (lc.depth == l) {
             double bx = pax + cvx, by = pay + cvy;
             double qdd = (uu - (U0 * paw + U1 * bx + U2 * by)) * dinv;
@@ -872,13 +1064,13 @@ __device__ void build_poli_state(const LinkC& lc, const EnvRegs& e, const Kin& k
 
 // cScenarioSimChar::Reset (+ PoliEval / Exp specifics): scenarios/ScenarioSimChar.cpp:121-132.  Cooperative kinematics,
 // scalar bookkeeping + terrain generation on lane 0.
-__device__ void reset_env(Lane& L, const LinkC& lc, EnvRegs& e, const Buffers& B, int lane) {
+__device__ void reset_env(Lane& L, const LinkC& lc, EnvRegs& e, const Buffers& B, int lane TRL_RESET_XS_DECL) {
     const ModelConst& m = c_model;
     e.q = lc.act ? m.pose0[lane == 0 ? 2 : lane + 2] : 0.0;
     e.qd = lc.act ? m.vel0[lane == 0 ? 2 : lane + 2] : 0.0;
     e.ox = m.pose0[0]; e.oy = m.pose0[1]; e.oxd = m.vel0[0]; e.oyd = m.vel0[1];
     e.tau = 0.0;
-    Kin k = kinematics(lc, e);
+    Kin k = kinematics(lc, e TRL_KIN_XS_ARG);
     double comx = e.ox + warp_sum_all(lc.mass * k.cx) / m.total_mass;
     double comy = e.oy + warp_sum_all(lc.mass * k.cy) / m.total_mass;
     double newx = e.ox, newy = e.oy;
@@ -952,7 +1144,7 @@ __global__ void __launch_bounds__(kBlockThreads, TRL_STEP_MIN_BLOCKS)
 trl_step_kernel(Buffers B, double h, int flags, int lists) {
     __shared__ double s_clx[4 * kMaxJoints], s_cly[4 * kMaxJoints];
     __shared__ int s_cbody[4 * kMaxJoints];
-#if TRL_ACCUM_SMEM
+#if TRL_SMEM_ALIGNED
     __shared__ __align__(16) double s_x[kWarpsPerBlock * X_END];
 #else
     __shared__ double s_x[kWarpsPerBlock * X_END];
@@ -993,7 +1185,7 @@ trl_step_kernel(Buffers B, double h, int flags, int lists) {
 
     if (flags & 1) {
         // ---------------- controller half of env-step k
-        Kin k = kinematics(lc, e);
+        Kin k = kinematics(lc, e TRL_KIN_XS_ARG);
         e.tau = controller_torque(L, lc, e, k, xs, lane, h, contact);
         if (lane == 0) {
             // fall checks (sim/SimCharSoftFall.cpp:74-125)
@@ -1047,7 +1239,7 @@ trl_step_kernel(Buffers B, double h, int flags, int lists) {
             }
             do_reset = true;
         }
-        if (do_reset) { reset_env(L, lc, e, B, lane); contact = 0; }
+        if (do_reset) { reset_env(L, lc, e, B, lane TRL_RESET_XS_ARG); contact = 0; }
     }
 
     if (flags & 2) {
@@ -1058,11 +1250,7 @@ trl_step_kernel(Buffers B, double h, int flags, int lists) {
         // terrain maximum over the window the character's corners can reach during this env-step; kClearMargin covers the
         // contact tolerance measured along the surface normal on (near-)vertical cliff faces and the root's travel
         const double clear_y = g.window_max(e.ox - m.reach - 0.25, e.ox + m.reach + 0.25, lane) + kClearMargin;
-#if TRL_ACCUM_SMEM
-        for (int s = 0; s < ns; ++s) contact = physics_substep(lc, e, g, s_clx, s_cly, s_cbody, lane, dt, clear_y, xs);
-#else
-        for (int s = 0; s < ns; ++s) contact = physics_substep(lc, e, g, s_clx, s_cly, s_cbody, lane, dt, clear_y);
-#endif
+        for (int s = 0; s < ns; ++s) contact = physics_substep(lc, e, g, s_clx, s_cly, s_cbody, lane, dt, clear_y TRL_PHYS_XS_ARG);
         // UpdateGround (scenarios/ScenarioSimChar.cpp:564-572): regenerate a segment when the view window crosses it
         {
             int smin = g.seg_id(0), smax = g.seg_id(1);
@@ -1110,7 +1298,7 @@ trl_step_kernel(Buffers B, double h, int flags, int lists) {
         __syncwarp();
         if (end_step) {
             // cycle boundary: build the policy state and hand the env to the decision kernel
-            Kin k = kinematics(lc, e);
+            Kin k = kinematics(lc, e TRL_KIN_XS_ARG);
             build_poli_state(lc, e, k, B, g, env, lane, m.char_type == 2 ? L.i(I_STANCE) : 0);
             double comx = e.ox + warp_sum_all(lc.mass * k.cx) / m.total_mass;
             double comy = e.oy + warp_sum_all(lc.mass * k.cy) / m.total_mass;
@@ -1150,7 +1338,11 @@ trl_reset_kernel(Buffers B, const uint64_t* terrain_seeds, const int* env_ids, i
     __syncwarp();
     const LinkC lc = load_link(lane);
     EnvRegs e;
-    reset_env(L, lc, e, B, lane);
+#if TRL_KIN_SMEM
+    __shared__ __align__(16) double s_pfx[kWarpsPerBlock * 3 * 2 * kWarp];
+    double* xs = s_pfx + warp * 3 * 2 * kWarp - X_PFX;    // kinematics() only touches [X_PFX, X_PFX_END)
+#endif
+    reset_env(L, lc, e, B, lane TRL_RESET_XS_ARG);
     store_env(L, lc, e, lane);
 }
 
@@ -1207,7 +1399,15 @@ void launch_stats(const Buffers& B, double* out, cudaStream_t st) { TRL_LAUNCH(t
 // ---- host-side launch helpers (called from trl_host.cu)
 cudaError_t upload_model(const ModelConst& mc) { return cudaMemcpyToSymbol(c_model, &mc, sizeof(ModelConst)); }
 size_t step_smem_bytes() { return 0; }
-cudaError_t configure_step_kernels() { return cudaSuccess; }
+cudaError_t configure_step_kernels() {
+#if TRL_SMEM_ALIGNED && !defined(TRL_SIMT_EMU)
+    // experiment builds stage lane-to-lane exchanges in shared memory (up to 42 KB per CTA): ask for the largest carve-out so
+    // that the register-limited 4 CTAs per SM still fit
+    return cudaFuncSetAttribute(trl_step_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+#else
+    return cudaSuccess;
+#endif
+}
 void launch_step(const Buffers& B, double h, int flags, int lists, cudaStream_t st) {
     int blocks = (B.n + kWarpsPerBlock - 1) / kWarpsPerBlock;
     TRL_LAUNCH(trl_step_kernel, blocks, kBlockThreads, 0, st, B, h, flags, lists);
