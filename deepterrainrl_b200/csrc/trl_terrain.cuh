@@ -13,6 +13,15 @@
 #pragma once
 #include "trl_types.h"
 
+#ifndef TRL_NOINLINE_COLD
+#define TRL_NOINLINE_COLD 0
+#endif
+#if TRL_NOINLINE_COLD && !defined(TRL_SIMT_EMU)
+#define TRL_COLD_ATTR __noinline__
+#else
+#define TRL_COLD_ATTR
+#endif
+
 namespace trl {
 
 struct TerrainRng {
@@ -380,8 +389,10 @@ struct GroundView {
             build_segment(i, lo, hi, !align_max, 0.0, type, params, seg_width);
         }
     }
-    // cGroundVar2D::Update; returns true if anything was rebuilt
-    __device__ bool update(double bmin, double bmax, int type, const double* params, double seg_width) {
+    // cGroundVar2D::Update; returns true if anything was rebuilt.  -DTRL_NOINLINE_COLD=1 (experiment) keeps this rare, large
+    // path (the generators are ~19 k instructions) out of line, so the env-step kernel's hot loop is not interleaved with it
+    // in the instruction cache; same arithmetic, bit-identical results.
+    __device__ TRL_COLD_ATTR bool update(double bmin, double bmax, int type, const double* params, double seg_width) {
         int smin = seg_id(0), smax = seg_id(1);
         double mn = seg_min_x(smin), mx = seg_max_x(smax);
         if (bmax < mx && bmin > mn) return false;

@@ -17,13 +17,48 @@ _LIB = None
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
 
 
+# Experimental builds of the env-step kernel (profiles/step_kernel_r02_experiment_queue.md).  Selected with TRL_VARIANT=<name> in
+# the environment of a measurement run; every variant is the same CUDA path compiled with one more -D flag and lives beside
+# the product library (lib/variants/<name>/).  Unset = the product build.  There is still no CPU path behind any of them.
+VARIANTS = {
+    "accum_smem": ["-DTRL_ACCUM_SMEM=1"],
+    "ldlt_smem": ["-DTRL_LDLT_SMEM=1"],
+    "kin_smem": ["-DTRL_KIN_SMEM=1"],
+    "outward_smem": ["-DTRL_OUTWARD_SMEM=1"],
+    "contact_smem": ["-DTRL_CONTACT_SMEM=1"],
+    "smem_xchg": ["-DTRL_SMEM_XCHG=1"],
+    "smem_xchg_3cta": ["-DTRL_SMEM_XCHG=1", "-DTRL_STEP_MIN_BLOCKS=3"],
+    "noinline_cold": ["-DTRL_NOINLINE_COLD=1"],
+}
+STEP_UNITS = ("trl_step.cu", "trl_step_cg.cu")      # the only translation units the variant flags reach
+
+
+def _variant():
+    v = os.environ.get("TRL_VARIANT", "")
+    if v and v not in VARIANTS:
+        raise RuntimeError(f"TRL_VARIANT={v!r}: unknown variant (known: {sorted(VARIANTS)})")
+    return v
+
+
 def library_path():
+    v = _variant()
+    if v:
+        return os.path.join(_PKG, "lib", "variants", v, "libterrainrl_b200.so")
     return os.path.join(_PKG, "lib", "libterrainrl_b200.so")
 
 
 def build_library(force=False, verbose=False):
     """Compile csrc/*.cu for sm_100a into lib/libterrainrl_b200.so (nvcc cross-compiles without a GPU).
-    trl_step_cg.cu is the env-step translation unit again with -Xptxas -dlcm=cg (L1-bypassing loads, see trl_step.cu)."""
+    trl_step_cg.cu is the env-step translation unit again with -Xptxas -dlcm=cg (L1-bypassing loads, see trl_step.cu).
+    With TRL_VARIANT set, the two env-step units are compiled with the variant's flags and linked with the product's other
+    objects into lib/variants/<name>/."""
+    variant = _variant()
+    if variant:
+        prev = os.environ.pop("TRL_VARIANT")
+        try:
+            build_library(force=False)          # the shared objects (host, trainer, loaders) come from the product build
+        finally:
+            os.environ["TRL_VARIANT"] = prev
     out = library_path()
     csrc = os.path.join(_PKG, "csrc")
     units = [("trl_step.cu", []), ("trl_step_cg.cu", ["-Xptxas", "-dlcm=cg"]), ("trl_host.cu", []), ("trl_train.cu", []),
@@ -32,13 +67,18 @@ def build_library(force=False, verbose=False):
     deps.append(os.path.join(_ROOT, "include", "terrainrl_b200.h"))
     if not force and os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in deps):
         return out
-    objdir = os.path.join(_PKG, "lib", "obj")
+    base_objdir = os.path.join(_PKG, "lib", "obj")
+    objdir = os.path.join(base_objdir, "variants", variant) if variant else base_objdir
     os.makedirs(objdir, exist_ok=True)
+    os.makedirs(os.path.dirname(out), exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     extra = os.environ.get("TRL_NVCC_EXTRA", "").split()     # developer knob (e.g. -DTRL_STEP_MIN_BLOCKS=7)
+    extra += VARIANTS.get(variant, [])
 
     def compile_unit(unit):
         name, flags = unit
+        if variant and name not in STEP_UNITS:
+            return os.path.join(base_objdir, os.path.splitext(name)[0] + ".o")
         obj = os.path.join(objdir, os.path.splitext(name)[0] + ".o")
         cmd = [nvcc] + NVCC_FLAGS + extra + flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj,
                                                                                               os.path.join(csrc, name)]
