@@ -42,7 +42,8 @@ thread_local Thread* cur = nullptr;
 thread_local Graph* capturing = nullptr;
 
 static std::atomic<long long> n_launches{0}, n_switches{0};
-long long counters(int which) { return which == 0 ? n_launches.load() : n_switches.load(); }
+long long coll_count[kCollEnd] = {0};
+long long counters(int which) { return which == 0 ? n_launches.load() : which == 1 ? n_switches.load() : which < kCollEnd ? coll_count[which] : 0; }
 
 void submit(std::function<void()> op) {
     if (capturing) capturing->ops.push_back(std::move(op));

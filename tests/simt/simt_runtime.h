@@ -88,7 +88,9 @@ extern thread_local Thread* cur;
 
 void yield_until_changed(const volatile unsigned* gen, unsigned val);   // suspends the calling fiber
 void run_grid(dim3 grid, dim3 block, size_t dyn_smem, int cluster_size, const std::function<void()>& body);
-long long counters(int which);   // 0: launches executed, 1: fiber switches, 2: warp collectives
+long long counters(int which);   // 0: launches executed, 1: fiber switches, 2.. : lane-calls of the collectives (kColl*)
+enum { kCollShfl64 = 2, kCollShfl32 = 3, kCollBallot = 4, kCollSyncwarp = 5, kCollSyncthreads = 6, kCollCluster = 7, kCollEnd = 8 };
+extern long long coll_count[kCollEnd];
 
 // ---- barriers
 inline void warp_arrive_and_wait(Warp* w, unsigned g) {
@@ -165,6 +167,7 @@ inline double max(double a, double b) { return std::fmax(a, b); }
 template <typename T>
 inline T __shfl_sync(unsigned, T v, int src, int width = 32) {
     (void)width;
+    ++simt::coll_count[sizeof(T) == 8 ? simt::kCollShfl64 : simt::kCollShfl32];
     const int b = simt::warp_publish(simt::to_bits(v));
     simt::Warp* w = simt::cur->warp;
     const int s = src & 31;
@@ -173,6 +176,7 @@ inline T __shfl_sync(unsigned, T v, int src, int width = 32) {
 template <typename T>
 inline T __shfl_xor_sync(unsigned, T v, int m, int width = 32) {
     (void)width;
+    ++simt::coll_count[sizeof(T) == 8 ? simt::kCollShfl64 : simt::kCollShfl32];
     const int b = simt::warp_publish(simt::to_bits(v));
     simt::Warp* w = simt::cur->warp;
     const int s = (simt::cur->lane ^ m) & 31;
@@ -195,6 +199,7 @@ inline T __shfl_up_sync(unsigned, T v, unsigned d, int width = 32) {
     return (s >= 0 && w->present[b][s]) ? simt::from_bits<T>(w->slot[b][s]) : v;
 }
 inline unsigned __ballot_sync(unsigned, int pred) {
+    ++simt::coll_count[simt::kCollBallot];
     const int b = simt::warp_publish(pred ? 1u : 0u);
     simt::Warp* w = simt::cur->warp;
     unsigned m = 0;
@@ -203,8 +208,8 @@ inline unsigned __ballot_sync(unsigned, int pred) {
 }
 inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0; }
 inline int __all_sync(unsigned m, int pred) { return __ballot_sync(m, !pred) == 0; }
-inline void __syncwarp(unsigned = 0xffffffffu) { simt::warp_publish(0); }
-inline void __syncthreads() { simt::block_barrier(0, nullptr); }
+inline void __syncwarp(unsigned = 0xffffffffu) { ++simt::coll_count[simt::kCollSyncwarp]; simt::warp_publish(0); }
+inline void __syncthreads() { ++simt::coll_count[simt::kCollSyncthreads]; simt::block_barrier(0, nullptr); }
 inline int __syncthreads_or(int pred) { int r; simt::block_barrier(pred, &r); return r; }
 inline void __threadfence() {}
 inline void __threadfence_block() {}

@@ -113,6 +113,25 @@ def test_step_and_decision_kernels_vs_oracle(assets, scene, steps):
         g.close()
 
 
+@pytest.mark.parametrize("scene", ["dog_slopes_mixed", "raptor_narrow_gaps"])
+def test_kernel_sources_reproduce_the_compiled_reference(assets, scene):
+    """tests/test_gpu_ref_golden.py without the GPU: the kernel sources against the torques / gait states the reference's own
+    compiled controller stack + cJoint clamp produced (tests/golden/ref_scenario_*.npz, tools/make_ref_golden.py)."""
+    import deepterrainrl_b200 as trl
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_scenario_%s.npz" % scene))
+    applied, fsm = g["applied"], g["fsm"]
+    with simt_library():
+        sc = trl.ScenarioPoliEval(os.path.join(assets, scene + ".trlpack"), 1, terrain_seeds=[int(g["seed"])])
+        n = min(400, len(applied))
+        for k in range(n):
+            sc.EnvStep(H)
+            _, _, tau, _ = sc.GetState(0)
+            err = np.max(np.abs(tau - applied[k]) / (1.0 + np.abs(applied[k])))
+            assert err < 1e-7, (scene, k, err)
+            assert int(sc.GetCtrl(0)[0]) == int(fsm[k, 0]), (scene, k, "gait state")
+        sc.close()
+
+
 def test_update_graph_overlapped_schedule_and_tuples_vs_oracle(assets):
     """trl_update: captured graph, two-stream schedule with catch-up launches, exploration on; tuples and counters."""
     n = 4
