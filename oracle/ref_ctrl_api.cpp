@@ -713,3 +713,77 @@ double ref_strain_sample_height(RefTrainScn* r, double x) { return r->scn->exp0(
 void ref_strain_schedule(RefTrainScn* r, int iters, double* out4) { r->scn->sched(iters, out4); }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------ the drop-in seam, compiled
+// include/terrainrl_b200_adapter.h (the binding INTEGRATION.md describes) compiled against the reference's headers and put under
+// the reference's own compiled cScenarioTrainMACE: BuildExpScene returns the batched adapter, everything else -- BuildScenePool,
+// SetupLearner, UpdateExpScene, the annealing schedule, cNeuralNetLearner / cMACETrainer -- runs as compiled and drives the C ABI.
+// The trl_* entry points are weak references: the test loads a library that exports them (RTLD_GLOBAL) before this one; every
+// other test of this library never reaches them.
+#pragma weak trl_create_from_pack
+#pragma weak trl_destroy
+#pragma weak trl_reset
+#pragma weak trl_update
+#pragma weak trl_sizes
+#pragma weak trl_num_tuples
+#pragma weak trl_get_tuples_f64
+#pragma weak trl_reset_tuples
+#pragma weak trl_set_explore
+#pragma weak trl_set_terrain_lerp
+#pragma weak trl_set_weights
+#pragma weak trl_last_error
+#include "../include/terrainrl_b200_adapter.h"
+
+typedef cScenarioExpBatchedT<FakeScnExp> BatchedExp;
+struct BatchedScnTrain : public cScenarioTrainMACE {
+    std::string pack;
+    int num_envs = 1;
+    unsigned long long rng_seed = 1234;
+    void BuildExpScene(std::shared_ptr<cScenarioExp>& out_exp) const override {
+        auto e = std::make_shared<BatchedExp>();
+        e->SetBatch(pack, num_envs, 0, rng_seed, nullptr);
+        out_exp = e;
+    }
+    BatchedExp* exp0() { return static_cast<BatchedExp*>(mExpPool[0].get()); }
+    long trainer_tuples() const { return std::static_pointer_cast<cNeuralNetTrainer>(mTrainer)->GetNumTuples(); }
+};
+
+extern "C" {
+// as ref_strain_create, with the exploration scene replaced by the adapter over a batch of `num_envs` environments of `pack`
+BatchedScnTrain* ref_btrain_create(const char* arg_file, char** extra, int n_extra, const char* pack, int num_envs, unsigned long long rng_seed,
+                                   unsigned long rand_seed, const int* net_dims, eval_fn ev, train_fn tr, copy_fn cp, calc_os_fn cos,
+                                   set_os_fn sos, void* user) {
+    if (std::getenv("REF_CTRL_DEBUG")) signal(SIGSEGV, ref_segv_handler);
+    if (!trl_create_from_pack) { std::fprintf(stderr, "ref_btrain_create: no library exporting the C ABI is loaded\n"); return nullptr; }
+    g_hooks.n_in = net_dims[0]; g_hooks.n_out = net_dims[1]; g_hooks.batch = net_dims[2];
+    g_hooks.eval = ev; g_hooks.train = tr; g_hooks.copy = cp; g_hooks.calc_os = cos; g_hooks.set_os = sos; g_hooks.user = user;
+    g_next_net = 0;
+    g_net_id.clear();
+    g_net_cb = nullptr;
+    g_reset_loads_pose0 = true;
+    cArgParser parser;
+    if (n_extra > 0) parser.AppendArgs(extra, n_extra);
+    parser.AppendArgs(std::string(arg_file));
+    auto* r = new BatchedScnTrain();
+    r->pack = pack; r->num_envs = num_envs; r->rng_seed = rng_seed;
+    g_math_util_rand = cRand();                  // the trainer's minibatch sampling draws from cMathUtil's engine
+    cMathUtil::SeedRand(rand_seed);
+    r->ParseArgs(parser);
+    r->SetExpPoolSize(1);
+    r->Init();
+    return r;
+}
+void ref_btrain_destroy(BatchedScnTrain* r) {
+    delete r;
+    g_hooks = NetHooks();
+    g_reset_loads_pose0 = false;
+}
+void ref_btrain_reseed(unsigned long rand_seed) { g_math_util_rand = cRand(); cMathUtil::SeedRand(rand_seed); }
+void ref_btrain_update(BatchedScnTrain* r, double dt) { r->Update(dt); }          // cScenarioTrain::Update -> UpdateExpScene
+void* ref_btrain_handle(BatchedScnTrain* r) { return r->exp0()->GetHandle(); }    // the trl_handle the adapter owns
+// iter, tuples seen by the trainer; the exploration rate / temperature / base-action rate the compiled scenario holds
+void ref_btrain_status(BatchedScnTrain* r, long* counts, double* rates) {
+    counts[0] = r->GetIter(); counts[1] = r->trainer_tuples();
+    rates[0] = r->exp0()->GetExpRate(); rates[1] = r->exp0()->GetExpTemp(); rates[2] = r->exp0()->GetExpBaseActionRate();
+}
+}  // extern "C"

@@ -70,6 +70,7 @@ thread_local StackPool pool;
 thread_local void* sched_sp = nullptr;
 thread_local const std::function<void()>* body_fn = nullptr;
 thread_local long long local_switches = 0;
+thread_local int live_fibers = 0;
 
 void release_if_complete(Thread* t) {
     // a thread that exits no longer takes part in barriers (whole warps return early in the env-step kernel)
@@ -85,6 +86,7 @@ void fiber_entry() {
     Thread* t = cur;
     (*body_fn)();
     t->done = true;
+    --live_fibers;
     release_if_complete(t);
     void* dummy;
     simt_switch(&dummy, sched_sp);
@@ -97,6 +99,20 @@ void yield_until_changed(const volatile unsigned* gen, unsigned val) {
     t->wait_gen = gen;
     t->wait_val = val;
     ++local_switches;
+    // fast path (default schedule only): a lane that waits hands the processor straight to the next runnable lane of its own
+    // warp -- the common case inside warp collectives -- instead of going through the scheduler loop
+    if (!sched_seed && t->warp_lanes > 1) {
+        const int nl = t->warp_lanes;
+        for (int k = 1; k < nl; ++k) {
+            Thread& c = t->warp_base[(t->lane + k) % nl];
+            if (c.done || (c.wait_gen && *c.wait_gen == c.wait_val)) continue;
+            c.wait_gen = nullptr;
+            cur = &c;
+            threadIdx = c.tid;
+            simt_switch(&t->sp, c.sp);
+            return;
+        }
+    }
     simt_switch(&t->sp, sched_sp);
 }
 
@@ -140,6 +156,8 @@ void run_grid(dim3 grid, dim3 block, size_t dyn_smem_bytes, int cluster_size, co
                 th.warp = &warps[(size_t)b * nwarps + t / 32];
                 th.block = &blocks[b];
                 th.cluster = &cl;
+                th.warp_base = &threads[(size_t)b * nthreads + (t / 32) * 32];
+                th.warp_lanes = std::min(32, nthreads - (t / 32) * 32);
                 char* top = pool.get((size_t)b * nthreads + t) + kStackBytes;
                 void** sp = (void**)(((uintptr_t)top & ~(uintptr_t)15));
                 *--sp = nullptr;                    // fake return address of fiber_entry (keeps rsp = 8 mod 16 at entry)
@@ -148,8 +166,8 @@ void run_grid(dim3 grid, dim3 block, size_t dyn_smem_bytes, int cluster_size, co
                 th.sp = sp;
             }
         }
-        int remaining = group_threads;
-        while (remaining > 0) {
+        live_fibers = group_threads;
+        while (live_fibers > 0) {
             bool progressed = false;
             // SIMT_SCHED_SEED: visit the fibers in a different rotation / direction on every pass.  Between two collectives the
             // lanes of a warp then run in varying orders, so a shared-memory hand-off that lacks its __syncwarp / __syncthreads
@@ -171,11 +189,10 @@ void run_grid(dim3 grid, dim3 block, size_t dyn_smem_bytes, int cluster_size, co
                 simt_switch(&sched_sp, th.sp);
                 cur = nullptr;
                 progressed = true;
-                if (th.done) --remaining;
             }
             if (!progressed) {
                 std::fprintf(stderr, "simt: deadlock -- a collective / barrier was not reached by every live thread "
-                                     "(block %d, %d threads still waiting)\n", first, remaining);
+                                     "(block %d, %d threads still waiting)\n", first, live_fibers);
                 for (int i = 0; i < group_threads && i < 64; ++i)
                     if (!threads[i].done) std::fprintf(stderr, "  thread %d (block rank %d) waits\n", i % nthreads, i / nthreads);
                 std::abort();

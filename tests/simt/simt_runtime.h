@@ -82,6 +82,8 @@ struct Thread {
     bool done = false;
     const volatile unsigned* wait_gen = nullptr;
     unsigned wait_val = 0;
+    Thread* warp_base = nullptr;   // lane 0 of this thread's warp (the lanes are contiguous)
+    int warp_lanes = 0;
 };
 
 extern thread_local Thread* cur;
