@@ -822,6 +822,16 @@ int trl_reset_tuples(trl_handle* h) {
     return 0;
 }
 
+// cScenarioPoliEval::ResetAvgDist (scenarios/ScenarioPoliEval.cpp:132-136) for every env: mean distance and episode count back to
+// zero, cycle count and distance log kept -- cOptScenarioPoliEval::EvalHelper calls it after each UpdateRecord
+// (optimizer/scenarios/OptScenarioPoliEval.cpp:189-195)
+int trl_reset_avg_dist(trl_handle* h) {
+    const size_t n = (size_t)h->n;
+    CK(cudaMemsetAsync(h->B.d + (size_t)D_AVG_DIST * n, 0, n * 8, h->stream));
+    CK(cudaMemsetAsync(h->B.i + (size_t)I_EPISODE_COUNT * n, 0, n * 4, h->stream));
+    return 0;
+}
+
 int trl_eval_stats(trl_handle* h, int64_t* cycles, int64_t* episodes, double* avg_dist, int64_t* env_steps) {
     const size_t n = (size_t)h->n;
     std::vector<int> cyc(n), eps(n), lo(n), hi(n);

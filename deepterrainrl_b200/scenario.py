@@ -95,7 +95,7 @@ def build_library(force=False, verbose=False):
 EXPORTS = [
     "trl_create_from_pack", "trl_create", "trl_pack_from_args", "trl_destroy", "trl_reset", "trl_seed_terrain", "trl_update", "trl_env_step", "trl_sync",
     "trl_set_explore", "trl_set_phys_params", "trl_set_weights", "trl_sizes", "trl_num_tuples", "trl_get_tuples",
-    "trl_get_tuples_f64", "trl_reset_tuples", "trl_eval_stats", "trl_dist_log", "trl_get_state", "trl_set_state",
+    "trl_get_tuples_f64", "trl_reset_tuples", "trl_eval_stats", "trl_dist_log", "trl_reset_avg_dist", "trl_get_state", "trl_set_state",
     "trl_get_state_all", "trl_get_ctrl", "trl_get_poli_state", "trl_get_net_out", "trl_get_terrain",
     "trl_kernel_launches", "trl_last_error", "trl_bench_updates", "trl_update_timed", "trl_device_tuple_block", "trl_snapshot", "trl_snapshot_wait", "trl_update_timed_detail", "trl_debug_time_decide",
     "trl_load_model", "trl_output_model", "trl_write_model", "trl_get_output_offset_scale", "trl_pack_output_offset_scale",
@@ -307,6 +307,9 @@ class BatchedScenario:
 
     def GetAvgDist(self):
         return self._stats()["avg_dist"]
+
+    def ResetAvgDist(self):
+        self._ck(self.L.trl_reset_avg_dist(self.h))
 
     def GetNumEnvSteps(self):
         return self._stats()["steps"]

@@ -77,6 +77,8 @@ int trl_reset_tuples(trl_handle* h);
 /* cScenarioPoliEval::{GetNumCycles,GetNumEpisodes,GetAvgDist,GetDistLog}   scenarios/ScenarioPoliEval.cpp:127-151 */
 int trl_eval_stats(trl_handle* h, int64_t* cycles, int64_t* episodes, double* avg_dist, int64_t* env_steps);
 int trl_dist_log(trl_handle* h, const double** dist, const int32_t** env_id, int* n);
+/* cScenarioPoliEval::ResetAvgDist for every env                scenarios/ScenarioPoliEval.cpp:132-136 */
+int trl_reset_avg_dist(trl_handle* h);
 
 /* cSimCharacter::{BuildPose,BuildVel} / SetPose+SetVel and contact bits for one env (sim/SimCharacter.cpp:166-315) */
 int trl_get_state(trl_handle* h, int env, double* pose, double* vel, double* held_torque, uint8_t* contact);

@@ -137,7 +137,92 @@ protected:
     mutable std::vector<tExpTuple> mTuples;
 };
 
+// Policy evaluation: what cOptScenarioPoliEval::{BuildScenePool, EvalHelper, OutputResults} call on a pooled evaluation scene
+// (optimizer/scenarios/OptScenarioPoliEval.cpp:135-163,170-198,213-237): ParseArgs, Init, SetRandSeed, Reset, Update,
+// GetNumCycles, GetNumEpisodes, GetAvgDist, ResetAvgDist, GetDistLog.  Base = cScenarioPoliEval in a deployment.  The counters
+// are those of the whole batch (sums; the mean distance is episode-weighted, as OutputResults merges its pool).
+template <class Base>
+class cScenarioPoliEvalBatchedT : public Base {
+public:
+    cScenarioPoliEvalBatchedT() {}
+    virtual ~cScenarioPoliEvalBatchedT() {
+        if (mHandle) trl_destroy(mHandle);
+    }
+    void SetBatch(const std::string& pack, int num_envs, int device, uint64_t rng_seed = 1234) {
+        mPack = pack; mNumEnvs = num_envs; mDevice = device; mRngSeed = rng_seed;
+    }
+    trl_handle* GetHandle() const { return mHandle; }
+
+    virtual void Init() {
+        Base::Init();
+        mHandle = trl_create_from_pack(mPack.c_str(), mNumEnvs, mDevice, TRL_MODE_POLI_EVAL, nullptr, mRngSeed);
+        if (!mHandle) { printf("cScenarioPoliEvalBatched: %s\n", trl_last_error()); assert(false); }
+    }
+    virtual void Clear() {
+        if (mHandle) { trl_destroy(mHandle); mHandle = nullptr; }
+        Base::Clear();
+    }
+    // one seed per pooled scene in the reference (OptScenarioPoliEval.cpp:150-160); a batch derives its environments' terrain
+    // seeds from it: seed, seed + 1, ...  (followed by the Reset the reference issues right after)
+    virtual void SetRandSeed(unsigned long seed) {
+        if (!mHandle) { Base::SetRandSeed(seed); return; }
+        std::vector<uint64_t> seeds(mNumEnvs);
+        for (int i = 0; i < mNumEnvs; ++i) seeds[i] = (uint64_t)seed + (uint64_t)i;
+        Check(trl_seed_terrain(mHandle, seeds.data(), mNumEnvs));
+    }
+    virtual void Reset() {
+        if (!mHandle) { Base::Reset(); return; }
+        Check(trl_reset(mHandle, nullptr, 0));
+    }
+    virtual void Update(double time_elapsed) {
+        if (!mHandle) { Base::Update(time_elapsed); return; }
+        Check(trl_update(mHandle, time_elapsed));
+    }
+    virtual double GetAvgDist() const {
+        if (!mHandle) return Base::GetAvgDist();
+        double avg = 0;
+        Check(trl_eval_stats(mHandle, nullptr, nullptr, &avg, nullptr));
+        return avg;
+    }
+    virtual void ResetAvgDist() {
+        if (!mHandle) { Base::ResetAvgDist(); return; }
+        Check(trl_reset_avg_dist(mHandle));
+    }
+    virtual int GetNumEpisodes() const {
+        if (!mHandle) return Base::GetNumEpisodes();
+        int64_t e = 0;
+        Check(trl_eval_stats(mHandle, nullptr, &e, nullptr, nullptr));
+        return (int)e;
+    }
+    virtual int GetNumCycles() const {
+        if (!mHandle) return Base::GetNumCycles();
+        int64_t c = 0;
+        Check(trl_eval_stats(mHandle, &c, nullptr, nullptr, nullptr));
+        return (int)c;
+    }
+    virtual const std::vector<double>& GetDistLog() const {
+        if (!mHandle) return Base::GetDistLog();
+        const double* d = nullptr; const int32_t* env = nullptr;
+        int n = 0;
+        Check(trl_dist_log(mHandle, &d, &env, &n));
+        mLog.assign(d, d + n);
+        return mLog;
+    }
+
+protected:
+    void Check(int rc) const {
+        if (rc != 0) { printf("cScenarioPoliEvalBatched: %s\n", trl_last_error()); assert(false); }
+    }
+    trl_handle* mHandle = nullptr;
+    std::string mPack;
+    int mNumEnvs = 1, mDevice = 0;
+    uint64_t mRngSeed = 1234;
+    mutable std::vector<double> mLog;
+};
+
 #ifdef TRL_ADAPTER_WITH_REFERENCE_SCENARIO
 #include "scenarios/ScenarioExpMACE.h"
+#include "scenarios/ScenarioPoliEval.h"
 typedef cScenarioExpBatchedT<cScenarioExpMACE> cScenarioExpBatched;
+typedef cScenarioPoliEvalBatchedT<cScenarioPoliEval> cScenarioPoliEvalBatched;
 #endif

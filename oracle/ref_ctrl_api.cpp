@@ -732,6 +732,10 @@ void ref_strain_schedule(RefTrainScn* r, int iters, double* out4) { r->scn->sche
 #pragma weak trl_set_terrain_lerp
 #pragma weak trl_set_weights
 #pragma weak trl_last_error
+#pragma weak trl_seed_terrain
+#pragma weak trl_eval_stats
+#pragma weak trl_dist_log
+#pragma weak trl_reset_avg_dist
 #include "../include/terrainrl_b200_adapter.h"
 
 typedef cScenarioExpBatchedT<FakeScnExp> BatchedExp;
@@ -785,5 +789,42 @@ void* ref_btrain_handle(BatchedScnTrain* r) { return r->exp0()->GetHandle(); }  
 void ref_btrain_status(BatchedScnTrain* r, long* counts, double* rates) {
     counts[0] = r->GetIter(); counts[1] = r->trainer_tuples();
     rates[0] = r->exp0()->GetExpRate(); rates[1] = r->exp0()->GetExpTemp(); rates[2] = r->exp0()->GetExpBaseActionRate();
+}
+}  // extern "C"
+
+// ---- policy evaluation through the adapter: the calls cOptScenarioPoliEval makes on a pooled scene, on a cScenarioPoliEval pointer
+typedef cScenarioPoliEvalBatchedT<FakeScnEval> BatchedEval;
+struct RefBEval {
+    std::unique_ptr<BatchedEval> scn;
+    cScenarioPoliEval* base() { return scn.get(); }       // every call below goes through the reference's own virtual interface
+};
+extern "C" {
+RefBEval* ref_beval_create(const char* arg_file, const char* pack, int num_envs, unsigned long long rng_seed, unsigned long seed) {
+    if (!trl_create_from_pack) { std::fprintf(stderr, "ref_beval_create: no library exporting the C ABI is loaded\n"); return nullptr; }
+    g_net_cb = nullptr;
+    g_reset_loads_pose0 = true;
+    cArgParser parser;
+    parser.AppendArgs(std::string(arg_file));
+    auto* r = new RefBEval();
+    r->scn.reset(new BatchedEval());
+    r->scn->SetBatch(pack, num_envs, 0, rng_seed);
+    cScenarioPoliEval* s = r->base();
+    s->ParseArgs(parser);                                  // cOptScenarioPoliEval::BuildScenePool (OptScenarioPoliEval.cpp:135-163)
+    s->Init();
+    s->SetRandSeed(seed);
+    s->Reset();
+    return r;
+}
+void ref_beval_destroy(RefBEval* r) { g_reset_loads_pose0 = false; delete r; }
+void* ref_beval_handle(RefBEval* r) { return r->scn->GetHandle(); }
+void ref_beval_update(RefBEval* r, double dt) { r->base()->Update(dt); }
+void ref_beval_stats(RefBEval* r, long* cycles, long* episodes, double* avg_dist) {
+    *cycles = r->base()->GetNumCycles(); *episodes = r->base()->GetNumEpisodes(); *avg_dist = r->base()->GetAvgDist();
+}
+void ref_beval_reset_avg_dist(RefBEval* r) { r->base()->ResetAvgDist(); }
+int ref_beval_dist_log(RefBEval* r, double* out, int cap) {
+    const std::vector<double>& log = r->base()->GetDistLog();
+    for (int i = 0; i < (int)log.size() && i < cap; ++i) out[i] = log[i];
+    return (int)log.size();
 }
 }  // extern "C"

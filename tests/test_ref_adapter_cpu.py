@@ -40,26 +40,105 @@ def _blob_sizes(n_char, n_frags, frag):
     return sizes
 
 
-def test_reference_training_scenario_drives_the_batch_through_the_adapter(assets):
+def _load_abi_and_reference():
+    """The C ABI the adapter binds (the emulator build, its symbols visible to what is loaded next) and a private image of the
+    reference library: its weak references to the C ABI are bound when it is loaded, and another test of this process may have
+    loaded the shared one before any exporter of trl_* existed."""
+    import shutil
+    import tempfile
     import build as simt_build
+    from loader import open_simt
+    C.CDLL(simt_build.build(), mode=C.RTLD_GLOBAL)
+    L = open_simt()
+    tmpdir = tempfile.mkdtemp(prefix="ref_adapter_")
+    ref = C.CDLL(shutil.copy(REF_CTRL, os.path.join(tmpdir, "libref_ctrl_adapter.so")))
+    shutil.rmtree(tmpdir, ignore_errors=True)
+    return L, ref
+
+
+def test_policy_evaluation_calls_of_the_reference_through_the_adapter(assets):
+    """cScenarioPoliEvalBatchedT under a cScenarioPoliEval pointer: the calls cOptScenarioPoliEval makes on a pooled scene
+    (ParseArgs, Init, SetRandSeed, Reset, Update, GetNumCycles / GetNumEpisodes / GetAvgDist / ResetAvgDist / GetDistLog)
+    against the same batch driven through the Python mirror."""
+    from deepterrainrl_b200 import scenario
+    import deepterrainrl_b200 as trl
+    L, ref = _load_abi_and_reference()
+    pack = os.path.join(assets, "dog_slopes_mixed.trlpack")
+    n, seed = 6, 500
+    ref.ref_beval_create.restype = C.c_void_p
+    ref.ref_beval_create.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_ulonglong, C.c_ulong]
+    for f in ("ref_beval_destroy", "ref_beval_reset_avg_dist"):
+        getattr(ref, f).argtypes = [C.c_void_p]
+    ref.ref_beval_update.argtypes = [C.c_void_p, C.c_double]
+    ref.ref_beval_handle.restype = C.c_void_p
+    ref.ref_beval_handle.argtypes = [C.c_void_p]
+    ref.ref_beval_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    ref.ref_beval_dist_log.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    saved = scenario._LIB
+    scenario._LIB = L
+    cwd = os.getcwd()
+    os.chdir("/root/reference")
+    try:
+        h = ref.ref_beval_create(b"args/dog_slopes_mixed_args.txt", pack.encode(), n, 1234, seed)
+    finally:
+        os.chdir(cwd)
+    assert h
+    h = C.c_void_p(h)
+    try:
+        g = trl.ScenarioPoliEval(pack, n, terrain_seeds=np.arange(seed, seed + n, dtype=np.uint64))
+        g.Reset()
+
+        def ref_stats():
+            c, e, a = C.c_long(0), C.c_long(0), C.c_double(0)
+            ref.ref_beval_stats(h, C.byref(c), C.byref(e), C.byref(a))
+            return c.value, e.value, a.value
+
+        class View(trl.ScenarioPoliEval):             # the adapter's handle through the Python mirror (no ownership)
+            def __init__(self, hh):
+                self.L, self.h, self.num_dof, self.num_joints, self.num_envs = L, C.c_void_p(hh), g.num_dof, g.num_joints, n
+
+            def close(self):
+                self.h = None
+        v = View(ref.ref_beval_handle(h))
+        for k in range(30):
+            ref.ref_beval_update(h, 1.0 / 30.0)
+            g.Update(1.0 / 30.0)
+            if k == 24:        # tip env 2 over on both sides: the next update ends its episode (fall -> distance record -> reset)
+                for sc in (v, g):
+                    q, qd, _, _ = sc.GetState(2)
+                    q[2] = 3.0
+                    sc.SetState(2, q=q, qd=qd)
+        s = g._stats()
+        assert ref_stats() == (s["cycles"], s["episodes"], s["avg_dist"])
+        assert s["episodes"] >= 1 and s["cycles"] > 0 and s["avg_dist"] != 0.0
+        log = np.zeros(64)
+        nl = ref.ref_beval_dist_log(h, _p(log), 64)
+        gl = g.GetDistLog()
+        glog = gl[0] if isinstance(gl, tuple) else gl
+        assert nl == len(glog) >= 1 and np.array_equal(log[:nl], np.asarray(glog))
+        ref.ref_beval_reset_avg_dist(h)                 # cScenarioPoliEval::ResetAvgDist: episodes and mean back to 0, cycles kept
+        g.ResetAvgDist()
+        s2 = g._stats()
+        assert ref_stats() == (s["cycles"], 0, 0.0) == (s2["cycles"], s2["episodes"], s2["avg_dist"])
+        q1, _ = v.GetStateAll()
+        q2, _ = g.GetStateAll()
+        assert np.array_equal(q1, q2)
+        v.close()
+        g.close()
+    finally:
+        ref.ref_beval_destroy(h)
+        scenario._LIB = saved
+
+
+def test_reference_training_scenario_drives_the_batch_through_the_adapter(assets):
     from pyoracle import Oracle, OracleTrainer
     from deepterrainrl_b200 import scenario
     from deepterrainrl_b200.train import TrainSchedule
-    from loader import open_simt
     import deepterrainrl_b200 as trl
 
     pack = os.path.join(assets, "dog_slopes_mixed.trlpack")
     n_envs, B, TB, rseed, rng_seed = 8, 8, 8, 4321, 77
-    # the C ABI the adapter binds: the emulator build, with its symbols visible to the library loaded next
-    C.CDLL(simt_build.build(), mode=C.RTLD_GLOBAL)
-    L = open_simt()
-    # a private image of the reference library: its weak references to the C ABI are bound when it is loaded, and another test of
-    # this process may have loaded the shared one before any exporter of trl_* existed
-    import shutil
-    import tempfile
-    tmpdir = tempfile.mkdtemp(prefix="ref_adapter_")
-    ref = C.CDLL(shutil.copy(REF_CTRL, os.path.join(tmpdir, "libref_ctrl_adapter.so")))
-    shutil.rmtree(tmpdir, ignore_errors=True)
+    L, ref = _load_abi_and_reference()
 
     kw = dict(replay_cap=400, num_init_samples=16, num_steps_per_iter=1, freeze_target_iters=3, init_input_offset_scale=1, seed=1)
     eng = OracleTrainer(pack, **kw)         # the network under the compiled reference trainer
