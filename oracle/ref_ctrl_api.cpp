@@ -828,3 +828,58 @@ int ref_beval_dist_log(RefBEval* r, double* out, int cap) {
     return (int)log.size();
 }
 }  // extern "C"
+
+// ---- the reference's own evaluation driver (optimizer/scenarios/OptScenarioPoliEval.cpp, compiled as it is): Run -> one thread per
+// pooled scene -> EvalHelper (Update until the episode / cycle budget is spent, UpdateRecord + ResetAvgDist every 10 episodes) ->
+// OutputResults.  BuildScenePool names the scene class in a `new` expression, so the one edit a maintainer makes is restated
+// here as an override: the reference's own lines (OptScenarioPoliEval.cpp:135-163) with `new cScenarioPoliEval()` replaced by the
+// batched adapter.
+#include "optimizer/scenarios/OptScenarioPoliEval.h"
+struct BatchedOptEval : public cOptScenarioPoliEval {
+    std::string pack;
+    int num_envs = 1;
+    unsigned long long rng_seed = 1234;
+    unsigned long first_seed = 0;
+    void BuildScenePool() override {
+        mEvalPool.resize(mPoolSize);
+        cRand rand;
+        bool valid_seed = mRandSeed != 0;
+        if (valid_seed) rand.Seed(mRandSeed);
+        unsigned long curr_seed = static_cast<unsigned long>(std::abs(rand.RandInt()));
+        first_seed = curr_seed;
+        for (int i = 0; i < GetPoolSize(); ++i) {
+            auto e = std::make_shared<BatchedEval>();
+            e->SetBatch(pack, num_envs, 0, rng_seed);
+            mEvalPool[i] = e;
+            e->ParseArgs(mArgParser);
+            e->Init();
+            if (valid_seed) {
+                e->SetRandSeed(curr_seed);
+                e->Reset();
+                curr_seed = static_cast<unsigned long>(std::abs(rand.RandInt()));
+            }
+        }
+    }
+    void results(long* counts, double* avg) const { counts[0] = mEpisodeCount; counts[1] = mCycleCount; *avg = mAvgDist; }
+    BatchedEval* eval0() { return static_cast<BatchedEval*>(mEvalPool[0].get()); }
+};
+extern "C" {
+BatchedOptEval* ref_opteval_create(const char* arg_file, char** extra, int n_extra, const char* pack, int num_envs, unsigned long long rng_seed) {
+    if (!trl_create_from_pack) { std::fprintf(stderr, "ref_opteval_create: no library exporting the C ABI is loaded\n"); return nullptr; }
+    g_net_cb = nullptr;
+    g_reset_loads_pose0 = true;
+    cArgParser parser;
+    if (n_extra > 0) parser.AppendArgs(extra, n_extra);
+    parser.AppendArgs(std::string(arg_file));
+    auto* r = new BatchedOptEval();
+    r->pack = pack; r->num_envs = num_envs; r->rng_seed = rng_seed;
+    r->ParseArgs(parser);
+    r->SetPoolSize(1);
+    r->Init();
+    return r;
+}
+void ref_opteval_run(BatchedOptEval* r) { r->Run(); }
+void ref_opteval_results(BatchedOptEval* r, long* counts, double* avg, unsigned long* first_seed) { r->results(counts, avg); *first_seed = r->first_seed; }
+void* ref_opteval_handle(BatchedOptEval* r) { return r->eval0()->GetHandle(); }
+void ref_opteval_destroy(BatchedOptEval* r) { g_reset_loads_pose0 = false; delete r; }
+}  // extern "C"

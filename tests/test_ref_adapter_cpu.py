@@ -130,6 +130,90 @@ def test_policy_evaluation_calls_of_the_reference_through_the_adapter(assets):
         scenario._LIB = saved
 
 
+def test_reference_evaluation_driver_runs_over_the_adapter(assets, tmp_path):
+    """optimizer/scenarios/OptScenarioPoliEval.cpp compiled as it is -- Run, its worker thread, EvalHelper (Update until the
+    episode / cycle budget is spent, UpdateRecord, ResetAvgDist), OutputResults -- over the batched adapter; BuildScenePool is the
+    reference's own lines with the scene class swapped.  Against the same protocol written out over the Python mirror."""
+    from deepterrainrl_b200 import scenario
+    import deepterrainrl_b200 as trl
+    L, ref = _load_abi_and_reference()
+    pack = os.path.join(assets, "dog_slopes_mixed.trlpack")
+    n, max_ep = 6, 1
+    out_file = str(tmp_path / "poli_eval.txt")
+    extra = ["-poli_eval_max_episodes=", str(max_ep), "-poli_eval_max_cycles=", "100000", "-poli_eval_rand_seed=", "31",
+             "-output_path=", out_file]
+    extra = [e.encode() for e in extra]
+    arr = (C.c_char_p * len(extra))(*extra)
+    ref.ref_opteval_create.restype = C.c_void_p
+    ref.ref_opteval_create.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.c_ulonglong]
+    ref.ref_opteval_handle.restype = C.c_void_p
+    for f in ("ref_opteval_run", "ref_opteval_destroy", "ref_opteval_handle"):
+        getattr(ref, f).argtypes = [C.c_void_p]
+    ref.ref_opteval_results.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    saved = scenario._LIB
+    scenario._LIB = L
+    cwd = os.getcwd()
+    os.chdir("/root/reference")
+    try:
+        h = ref.ref_opteval_create(b"args/dog_slopes_mixed_args.txt", arr, len(extra), pack.encode(), n, 1234)
+    finally:
+        os.chdir(cwd)
+    assert h
+    h = C.c_void_p(h)
+    try:
+        counts, avg, seed0 = (C.c_long * 2)(), C.c_double(0), C.c_ulong(0)
+        ref.ref_opteval_results(h, counts, C.byref(avg), C.byref(seed0))
+        # the product-side batch, seeded as the compiled BuildScenePool seeded the adapter's (cRand(31) -> first RandInt)
+        g = trl.ScenarioPoliEval(pack, n, terrain_seeds=np.arange(seed0.value, seed0.value + n, dtype=np.uint64))
+        g.Reset()
+
+        class View(trl.ScenarioPoliEval):
+            def __init__(self, hh):
+                self.L, self.h, self.num_dof, self.num_joints, self.num_envs = L, C.c_void_p(hh), g.num_dof, g.num_joints, n
+
+            def close(self):
+                self.h = None
+        v = View(ref.ref_opteval_handle(h))
+        q1, _ = v.GetStateAll()
+        q2, _ = g.GetStateAll()
+        assert np.array_equal(q1, q2)
+        for sc in (v, g):                               # run both batches past their first cycles, then tip one environment over
+            for k in range(24):
+                sc.Update(1.0 / 30.0)
+            q, qd, _, _ = sc.GetState(1)
+            q[2] = 3.0
+            sc.SetState(1, q=q, qd=qd)
+        ref.ref_opteval_run(h)                          # cOptScenarioPoliEval::Run: thread -> EvalHelper -> OutputResults
+        # EvalHelper over the Python mirror (optimizer/scenarios/OptScenarioPoliEval.cpp:170-198)
+        rec = dict(avg=0.0, ep=0, cyc=0)
+        num_episodes, num_cycles, prev = 0, 0, 0
+        while num_episodes < max_ep and num_cycles < 100000:
+            g.Update(1.0 / 30.0)
+            num_cycles = g.GetNumCycles()
+            cur = g.GetNumEpisodes()
+            if cur >= 10 or cur + num_episodes >= max_ep:
+                a = g.GetAvgDist()
+                rec["avg"] = (rec["ep"] * rec["avg"] + cur * a) / (rec["ep"] + cur)        # cMathUtil::AddAverage
+                rec["ep"] += cur
+                rec["cyc"] += num_cycles - prev
+                g.ResetAvgDist()
+                num_episodes += cur
+                prev = num_cycles
+        ref.ref_opteval_results(h, counts, C.byref(avg), C.byref(seed0))
+        assert (counts[0], counts[1]) == (rec["ep"], rec["cyc"]) and rec["ep"] >= 1 and rec["cyc"] > 0
+        assert avg.value == rec["avg"] != 0.0
+        dist = g.GetDistLog()[0]
+        assert open(out_file).read() == ", ".join("%f" % d for d in dist) + "\n"            # OutputResults: std::to_string per entry
+        q1, _ = v.GetStateAll()
+        q2, _ = g.GetStateAll()
+        assert np.array_equal(q1, q2)
+        v.close()
+        g.close()
+    finally:
+        ref.ref_opteval_destroy(h)
+        scenario._LIB = saved
+
+
 def test_reference_training_scenario_drives_the_batch_through_the_adapter(assets):
     from pyoracle import Oracle, OracleTrainer
     from deepterrainrl_b200 import scenario
