@@ -221,10 +221,10 @@ def test_reference_training_scenario_drives_the_batch_through_the_adapter(assets
     import deepterrainrl_b200 as trl
 
     pack = os.path.join(assets, "dog_slopes_mixed.trlpack")
-    n_envs, B, TB, rseed, rng_seed = 8, 8, 8, 4321, 77
+    n_envs, B, TB, rseed, rng_seed = 8, 8, 4, 4321, 77
     L, ref = _load_abi_and_reference()
 
-    kw = dict(replay_cap=400, num_init_samples=16, num_steps_per_iter=1, freeze_target_iters=3, init_input_offset_scale=1, seed=1)
+    kw = dict(replay_cap=400, num_init_samples=8, num_steps_per_iter=1, freeze_target_iters=3, init_input_offset_scale=1, seed=1)
     eng = OracleTrainer(pack, **kw)         # the network under the compiled reference trainer
     orc = OracleTrainer(pack, **kw)         # the trainer of the product-side loop
     dummy = Oracle(pack, 1, 1)              # never stepped: carries the restated cRand the oracle trainer samples from
@@ -333,7 +333,7 @@ def test_reference_training_scenario_drives_the_batch_through_the_adapter(assets
         cbs = (EV(guarded(ev)), TR(guarded(tr)), CP(guarded(cp)), CO(guarded(co)), SO(guarded(so)))
         ref.ref_ctrl_set_net_output(S, _p(np.zeros(no)), _p(np.ascontiguousarray(orc.get("out_scale"))), no)
         extra = ["-init_exp_rate=", "0.5", "-init_exp_base_rate=", "0.3", "-terrain_file=", "data/terrain/slopes_mixed.txt",
-                 "-tuple_buffer_size=", str(TB), "-trainer_replay_mem_size=", "400", "-trainer_num_init_samples=", "16",
+                 "-tuple_buffer_size=", str(TB), "-trainer_replay_mem_size=", "400", "-trainer_num_init_samples=", "8",
                  "-trainer_freeze_target_iters=", "3", "-trainer_num_anneal_iters=", "12", "-exp_base_anneal_iters=", "8",
                  "-trainer_curriculum_iters=", "10", "-trainer_int_iter=", "0", "-trainer_iters_per_output=", "100000",
                  "-output_path=", "/tmp/ref_btrain_model.h5"]
