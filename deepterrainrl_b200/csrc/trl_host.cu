@@ -70,6 +70,7 @@ static int ensure_model(trl_handle* h) {
 }
 
 int trl_reupload_model(trl_handle* h) {
+    if (!h) return fail("trl_reupload_model: null handle");
     g_model_owner = nullptr;
     return ensure_model(h) ? fail("model upload failed") : 0;
 }
@@ -503,6 +504,7 @@ int trl_destroy(trl_handle* h) {
 }
 
 int trl_seed_terrain(trl_handle* h, const uint64_t* seeds, int n) {
+    if (!h) return fail("trl_seed_terrain: null handle");
     if (ensure_model(h)) return fail("model upload failed");
     uint64_t* d_seeds = nullptr;
     if (seeds) {
@@ -520,6 +522,7 @@ int trl_seed_terrain(trl_handle* h, const uint64_t* seeds, int n) {
 }
 
 int trl_reset(trl_handle* h, const int32_t* env_ids, int n) {
+    if (!h) return fail("trl_reset: null handle");
     if (ensure_model(h)) return fail("model upload failed");
     int* d_ids = nullptr;
     int count = h->n;
@@ -537,6 +540,7 @@ int trl_reset(trl_handle* h, const int32_t* env_ids, int n) {
 }
 
 int trl_update(trl_handle* h, double dt) {
+    if (!h) return fail("trl_update: null handle");
     if (ensure_model(h)) return fail("model upload failed");
     if (!(dt > 0)) return 0;
     const int nlaunch = update_launches(h, h->overlap);
@@ -564,6 +568,7 @@ int trl_update(trl_handle* h, double dt) {
 }
 
 int trl_env_step(trl_handle* h, double step) {
+    if (!h) return fail("trl_env_step: null handle");
     if (ensure_model(h)) return fail("model upload failed");
     launch_step(h->B, step, 2, 0, h->stream);
     launch_decide(h->B, h->W, h->d_ex, h->done_count, h->decide_grid, 0, 1, h->stream);
@@ -574,11 +579,13 @@ int trl_env_step(trl_handle* h, double step) {
 }
 
 int trl_sync(trl_handle* h) {
+    if (!h) return fail("trl_sync: null handle");
     CK(cudaStreamSynchronize(h->stream));
     return 0;
 }
 
 int trl_set_explore(trl_handle* h, int enable, double rate, double temp, double base_rate) {
+    if (!h) return fail("trl_set_explore: null handle");
     // the decision kernel reads the settings from device memory, so annealing them every update (cScenarioTrain::CalcExpRate
     // ...) neither re-captures the update graph nor drains the stream: the copy is ordered behind the work already queued
     h->ex.enable = enable; h->ex.rate = rate; h->ex.temp = temp; h->ex.base_rate = base_rate;
@@ -619,6 +626,7 @@ int trl_write_model(const char* path, const double* const* blobs, int n_char, in
 }
 // the policy the scenario currently evaluates (the attached trainer's net if there is one)
 int trl_output_model(trl_handle* h, const char* path, uint32_t mtime) {
+    if (!h) return fail("trl_output_model: null handle");
     if (!h->mc.has_net) return fail("trl_output_model: scene has no policy net");
     CK(cudaStreamSynchronize(h->stream));
     const NetWeights& W = h->W;
@@ -637,6 +645,7 @@ int trl_output_model(trl_handle* h, const char* path, uint32_t mtime) {
 int trl_trainer_set_theta(trl_trainer* t, const double* theta);
 // cNeuralNet::LoadModel + LoadScale (learning/NeuralNet.cpp:157-186): Caffe HDF5 weights + `_scale.txt`
 int trl_load_model(trl_handle* h, const char* h5_path, const char* scale_path) {
+    if (!h) return fail("trl_load_model: null handle");
     if (!h->mc.has_net) return fail("trl_load_model: scene has no policy net");
     if (h->trainer) return fail("trl_load_model: a trainer owns the policy weights (load before trl_trainer_create)");
     try {
@@ -678,6 +687,7 @@ int trl_pack_output_offset_scale(const char* pack_path, double* off, double* sca
 // actor f centred on the optimised parameters of control set f % n_ctrl (cDogControllerMACE::BuildActorBias) and scaled by
 // 1 / max_a |opt(a) - opt(default action)| over the action library
 int trl_get_output_offset_scale(trl_handle* h, double* off, double* scale, int n) {
+    if (!h) return fail("trl_get_output_offset_scale: null handle");
     const ModelConst& m = h->mc;
     const int fs = m.n_opt, nf = m.has_net ? m.n_frags : 0;
     if (n != nf * (1 + fs)) return fail("trl_get_output_offset_scale: size mismatch");
@@ -712,6 +722,7 @@ int trl_get_output_offset_scale(trl_handle* h, double* off, double* scale, int n
 // (scenarios/ScenarioTrain.cpp:412-416): blends the scene's terrain parameter sets; segments generated from now on use the
 // blend (cGroundVar2D::SetTerrainParams), existing terrain stays.
 int trl_set_terrain_lerp(trl_handle* h, double lerp) {
+    if (!h) return fail("trl_set_terrain_lerp: null handle");
     const auto& tp = h->scene.f64("terrain_params");
     const int n_sets = (int)(tp.size() / kTerrainParams);
     if (n_sets <= 0) return 0;
@@ -742,6 +753,7 @@ int trl_train_schedule(const double* sp, int iters, double* out) {
 }
 
 int trl_set_phys_params(trl_handle* h, const double* p) {
+    if (!h) return fail("trl_set_phys_params: null handle");
     CK(cudaStreamSynchronize(h->stream));
     h->mc.phys = PhysParams{p[0], p[1], p[2], p[3], p[4], p[5], p[6]};
     g_model_owner = nullptr;
@@ -751,6 +763,7 @@ int trl_set_phys_params(trl_handle* h, const double* p) {
 
 int trl_set_weights(trl_handle* h, const double* const* blobs, const int64_t* counts, int nblobs, const double* in_off,
                     const double* in_scale, const double* out_off, const double* out_scale) {
+    if (!h) return fail("trl_set_weights: null handle");
     if (nblobs != 26) return fail("trl_set_weights: expected 26 blobs");
     if (!h->mc.has_net) return fail("trl_set_weights: scene has no policy net");
     if (h->trainer) return fail("trl_set_weights: a trainer owns the policy weights (use trl_trainer_set_theta)");
@@ -765,6 +778,7 @@ int trl_set_weights(trl_handle* h, const double* const* blobs, const int64_t* co
 }
 
 int trl_sizes(trl_handle* h, int* num_envs, int* state, int* action, int* num_frags, int* frag_size, int* num_dof, int* num_joints) {
+    if (!h) return fail("trl_sizes: null handle");
     if (num_envs) *num_envs = h->n;
     if (state) *state = h->B.S;
     if (action) *action = h->B.A;
@@ -795,6 +809,7 @@ static int fetch_tuples(trl_handle* h, int* n_out) {
 }
 
 int trl_num_tuples(trl_handle* h, int* out) {
+    if (!h) return fail("trl_num_tuples: null handle");
     int n = 0;
     CK(cudaMemcpyAsync(&n, h->B.tuple_count, 4, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -803,12 +818,14 @@ int trl_num_tuples(trl_handle* h, int* out) {
 }
 
 int trl_get_tuples_f64(trl_handle* h, const double** rows, const uint32_t** flags, const int32_t** env_id, int* n) {
+    if (!h) return fail("trl_get_tuples_f64: null handle");
     if (fetch_tuples(h, n)) return 1;
     *rows = h->h_tuples.data(); *flags = h->h_tuple_flags.data(); *env_id = h->h_tuple_env.data();
     return 0;
 }
 
 int trl_get_tuples(trl_handle* h, const float** rows, const uint32_t** flags, const int32_t** env_id, int* n) {
+    if (!h) return fail("trl_get_tuples: null handle");
     if (fetch_tuples(h, n)) return 1;
     const size_t W = 1 + h->B.S + h->B.A + h->B.S;
     h->h_tuples_f32.resize((size_t)std::max(*n, 1) * W);
@@ -818,6 +835,7 @@ int trl_get_tuples(trl_handle* h, const float** rows, const uint32_t** flags, co
 }
 
 int trl_reset_tuples(trl_handle* h) {
+    if (!h) return fail("trl_reset_tuples: null handle");
     CK(cudaMemsetAsync(h->B.tuple_count, 0, 4, h->stream));
     return 0;
 }
@@ -826,6 +844,7 @@ int trl_reset_tuples(trl_handle* h) {
 // zero, cycle count and distance log kept -- cOptScenarioPoliEval::EvalHelper calls it after each UpdateRecord
 // (optimizer/scenarios/OptScenarioPoliEval.cpp:189-195)
 int trl_reset_avg_dist(trl_handle* h) {
+    if (!h) return fail("trl_reset_avg_dist: null handle");
     const size_t n = (size_t)h->n;
     CK(cudaMemsetAsync(h->B.d + (size_t)D_AVG_DIST * n, 0, n * 8, h->stream));
     CK(cudaMemsetAsync(h->B.i + (size_t)I_EPISODE_COUNT * n, 0, n * 4, h->stream));
@@ -833,6 +852,7 @@ int trl_reset_avg_dist(trl_handle* h) {
 }
 
 int trl_eval_stats(trl_handle* h, int64_t* cycles, int64_t* episodes, double* avg_dist, int64_t* env_steps) {
+    if (!h) return fail("trl_eval_stats: null handle");
     const size_t n = (size_t)h->n;
     std::vector<int> cyc(n), eps(n), lo(n), hi(n);
     std::vector<double> avg(n);
@@ -856,6 +876,7 @@ int trl_eval_stats(trl_handle* h, int64_t* cycles, int64_t* episodes, double* av
 }
 
 int trl_dist_log(trl_handle* h, const double** dist, const int32_t** env_id, int* n) {
+    if (!h) return fail("trl_dist_log: null handle");
     int cnt = 0;
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaMemcpy(&cnt, h->B.dist_count, 4, cudaMemcpyDeviceToHost));
@@ -879,6 +900,7 @@ static int copy_plane_i(trl_handle* h, int field, int count, int env, int* out) 
 }
 
 int trl_get_state(trl_handle* h, int env, double* pose, double* vel, double* held_torque, uint8_t* contact) {
+    if (!h) return fail("trl_get_state: null handle");
     if (env < 0 || env >= h->n) return fail("env out of range");
     CK(cudaStreamSynchronize(h->stream));
     int nd = h->mc.ndof;
@@ -894,6 +916,7 @@ int trl_get_state(trl_handle* h, int env, double* pose, double* vel, double* hel
 }
 
 int trl_set_state(trl_handle* h, int env, const double* pose, const double* vel, const double* held_torque, const uint8_t* contact) {
+    if (!h) return fail("trl_set_state: null handle");
     if (env < 0 || env >= h->n) return fail("env out of range");
     CK(cudaStreamSynchronize(h->stream));
     int nd = h->mc.ndof;
@@ -912,6 +935,7 @@ int trl_set_state(trl_handle* h, int env, const double* pose, const double* vel,
 }
 
 int trl_get_state_all(trl_handle* h, double* pose, double* vel) {
+    if (!h) return fail("trl_get_state_all: null handle");
     CK(cudaStreamSynchronize(h->stream));
     size_t bytes = (size_t)h->mc.ndof * h->n * 8;
     if (pose) CK(cudaMemcpy(pose, h->B.d + (size_t)D_Q * h->n, bytes, cudaMemcpyDeviceToHost));
@@ -920,6 +944,7 @@ int trl_get_state_all(trl_handle* h, double* pose, double* vel) {
 }
 
 int trl_get_ctrl(trl_handle* h, int env, double* out, int cap, int* n_out) {
+    if (!h) return fail("trl_get_ctrl: null handle");
     if (env < 0 || env >= h->n) return fail("env out of range");
     CK(cudaStreamSynchronize(h->stream));
     std::vector<double> d(D_NUM_FIELDS);
@@ -941,16 +966,19 @@ int trl_get_ctrl(trl_handle* h, int env, double* out, int cap, int* n_out) {
 }
 
 int trl_get_poli_state(trl_handle* h, int env, double* out) {
+    if (!h) return fail("trl_get_poli_state: null handle");
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaMemcpy(out, h->B.poli_state + (size_t)env * h->B.S, (size_t)h->B.S * 8, cudaMemcpyDeviceToHost));
     return 0;
 }
 int trl_get_net_out(trl_handle* h, int env, double* out) {
+    if (!h) return fail("trl_get_net_out: null handle");
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaMemcpy(out, h->B.net_out + (size_t)env * kMaxNetOut, (size_t)h->mc.n_out * 8, cudaMemcpyDeviceToHost));
     return 0;
 }
 int trl_get_terrain(trl_handle* h, int env, int seg, float* data, int cap, int* n, double* min_x, int* flip) {
+    if (!h) return fail("trl_get_terrain: null handle");
     CK(cudaStreamSynchronize(h->stream));
     int sn = 0, fl = 0;
     double mx = 0;
@@ -968,6 +996,7 @@ int64_t trl_kernel_launches(trl_handle* h) { return h->launches; }
 // Micro-benchmark of the decision kernel: marks the first `n_pending` envs as pending (their policy state is whatever the
 // last real decision left) and times `iters` launches.  Perturbs those envs' actions: measurement use only.
 int trl_debug_time_decide(trl_handle* h, int n_pending, int iters, double* ms_avg) {
+    if (!h) return fail("trl_debug_time_decide: null handle");
     if (ensure_model(h)) return fail("model upload failed");
     if (n_pending > h->n) n_pending = h->n;
     std::vector<int> ids(n_pending);
@@ -996,6 +1025,7 @@ int trl_debug_time_decide(trl_handle* h, int n_pending, int iters, double* ms_av
 // stream; trl_snapshot_wait() blocks on that copy only, so the caller can enqueue the next trl_update() first and
 // read update k's results while update k+1 runs.
 int trl_snapshot(trl_handle* h) {
+    if (!h) return fail("trl_snapshot: null handle");
     const size_t plane = (size_t)h->mc.ndof * h->n;
     const size_t total = 2 * plane + 4;
     if (!h->snap_dev) {
@@ -1019,6 +1049,7 @@ int trl_snapshot(trl_handle* h) {
 }
 
 int trl_snapshot_wait(trl_handle* h, double* pose, double* vel, int64_t* cycles, int64_t* episodes, double* avg_dist, int64_t* env_steps) {
+    if (!h) return fail("trl_snapshot_wait: null handle");
     if (!h->snap_pending) return fail("trl_snapshot_wait: no snapshot in flight");
     CK(cudaEventSynchronize(h->snap_copied));
     h->snap_pending = false;
@@ -1037,6 +1068,7 @@ int trl_snapshot_wait(trl_handle* h, double* pose, double* vel, int64_t* cycles,
 // SURVEY §8e).  Pointers are device addresses on the handle's GPU; the caller must trl_sync() before using them on
 // another stream.
 int trl_device_tuple_block(trl_handle* h, void** rows_f64, void** flags_u32, void** env_i32, void** count_i32, int* cap, int* width) {
+    if (!h) return fail("trl_device_tuple_block: null handle");
     if (rows_f64) *rows_f64 = h->B.tuples;
     if (flags_u32) *flags_u32 = h->B.tuple_flags;
     if (env_i32) *env_i32 = h->B.tuple_env;
@@ -1049,6 +1081,7 @@ int trl_device_tuple_block(trl_handle* h, void** rows_f64, void** flags_u32, voi
 // K outer updates timed with CUDA events on the handle's own stream (the stream the kernels are launched on);
 // optionally evicts L2 between updates by writing a 256 MiB scratch buffer.
 int trl_bench_updates(trl_handle* h, double dt, int k, int flush_l2, double* ms_total) {
+    if (!h) return fail("trl_bench_updates: null handle");
     if (ensure_model(h)) return fail("model upload failed");
     const size_t flush_bytes = (size_t)256 << 20;
     if (flush_l2 && !h->flush_buf) { CK(cudaMalloc(&h->flush_buf, flush_bytes)); h->allocs.push_back(h->flush_buf); }
@@ -1074,10 +1107,12 @@ int trl_bench_updates(trl_handle* h, double dt, int k, int flush_l2, double* ms_
 static int update_timed_impl(trl_handle* h, double dt, double* step_ms, int* step_launches, double* decide_ms, int* decide_launches,
                              double* per_step, double* per_decide);
 int trl_update_timed(trl_handle* h, double dt, double* step_ms, int* step_launches, double* decide_ms, int* decide_launches) {
+    if (!h) return fail("trl_update_timed: null handle");
     return update_timed_impl(h, dt, step_ms, step_launches, decide_ms, decide_launches, nullptr, nullptr);
 }
 // same, also returning every launch's duration: per_step[num_update_steps + 1], per_decide[num_update_steps]
 int trl_update_timed_detail(trl_handle* h, double dt, double* per_step, double* per_decide) {
+    if (!h) return fail("trl_update_timed_detail: null handle");
     return update_timed_impl(h, dt, nullptr, nullptr, nullptr, nullptr, per_step, per_decide);
 }
 static int update_timed_impl(trl_handle* h, double dt, double* step_ms, int* step_launches, double* decide_ms, int* decide_launches,

@@ -31,6 +31,19 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(trl.scenario.EXPORTS)
 
 
+def test_null_handles_are_refused_with_a_message():
+    """The reference asserts on misuse (scenarios/ScenarioTrain.cpp:282); across the ABI that is a non-zero return + trl_last_error."""
+    import ctypes as C
+    L = trl.load_library()
+    out = C.c_int(0)
+    for call in (lambda: L.trl_update(None, C.c_double(1.0 / 30.0)), lambda: L.trl_reset(None, None, 0), lambda: L.trl_reset_tuples(None),
+                 lambda: L.trl_num_tuples(None, C.byref(out)), lambda: L.trl_set_explore(None, 1, C.c_double(0.1), C.c_double(0.1), C.c_double(0.1)),
+                 lambda: L.trl_reset_avg_dist(None), lambda: L.trl_set_terrain_lerp(None, C.c_double(0.5))):
+        assert call() != 0
+        assert b"null handle" in L.trl_last_error()
+    assert L.trl_destroy(None) == 0 and L.trl_trainer_destroy(None) == 0
+
+
 def test_sm100a_cubin_and_no_cpu_fallback(assets):
     import subprocess
     out = subprocess.run(["/usr/local/cuda/bin/cuobjdump", "-lelf", trl.library_path()], capture_output=True, text=True).stdout
