@@ -22,6 +22,13 @@ constexpr int kDecideThreads = 512;
 #ifndef TRL_CLUSTER
 #define TRL_CLUSTER 4    // measured: 4-CTA clusters 21.5 M env-steps/s, 8-CTA 20.6 M, 2-CTA 21.4 M (smaller footprint beside the step launch)
 #endif
+#ifndef TRL_DECIDE_TILE
+#define TRL_DECIDE_TILE 0   // 1: register-tiled conv1 / conv2 (experiment, bit-identical; see net_forward_cluster)
+#endif
+#ifndef TRL_CONV_TILE
+#define TRL_CONV_TILE 4
+#endif
+constexpr int kConvTile = TRL_CONV_TILE;                                         // adjacent output positions per thread in the tiled conv loops
 constexpr int kClusterSize = TRL_CLUSTER;                            // CTAs (SMs) cooperating on one decision
 constexpr int kConv0Out = 16, kConv0K = 8, kW0 = 193;
 constexpr int kConv1Out = 32, kConv1K = 4, kW1 = 190;
@@ -88,6 +95,40 @@ __device__ void net_forward_cluster(cg::cluster_group& cluster, const NetWeights
         A0[idx] = acc > 0.0 ? acc : 0.0;
     }
     __syncthreads();
+#if TRL_DECIDE_TILE
+    // Experiment: kConvTile adjacent output positions per thread -- the activations a[t .. t + tile + K - 2] and the K weights of
+    // an input channel are loaded once and used for tile x K multiply-adds (shared-memory loads per multiply-add 2.0 -> 0.7; the
+    // untiled loop is shared-memory-bandwidth bound).  Every output still sums in the same order (4 accumulators by c & 3, k
+    // inner), so the results are bit-identical to the loop below.
+    {
+        constexpr int nt = (kW1 + kConvTile - 1) / kConvTile;
+        for (int item = tid; item < kC1Slice * nt; item += kDecideThreads) {
+            const int ol = item / nt, t0 = (item - ol * nt) * kConvTile, o = rank * kC1Slice + ol;
+            const double* w = W1s + ol * kConv0Out * kConv1K;
+            double acc[kConvTile][4];
+#pragma unroll
+            for (int j = 0; j < kConvTile; ++j) { acc[j][0] = W.conv1_b[o]; acc[j][1] = 0.0; acc[j][2] = 0.0; acc[j][3] = 0.0; }
+#pragma unroll
+            for (int c = 0; c < kConv0Out; ++c) {
+                const double* a = A0 + c * kW0;
+                double av[kConvTile + kConv1K - 1];
+#pragma unroll
+                for (int i = 0; i < kConvTile + kConv1K - 1; ++i) av[i] = a[min(t0 + i, kW0 - 1)];
+#pragma unroll
+                for (int k = 0; k < kConv1K; ++k) {
+                    const double wk = w[c * kConv1K + k];
+#pragma unroll
+                    for (int j = 0; j < kConvTile; ++j) acc[j][c & 3] += wk * av[j + k];
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < kConvTile; ++j) {
+                const double v = (acc[j][0] + acc[j][1]) + (acc[j][2] + acc[j][3]);
+                if (t0 + j < kW1) A1[o * kW1 + t0 + j] = v > 0.0 ? v : 0.0;
+            }
+        }
+    }
+#else
     // conv1: this CTA's 4 output channels; 4 independent accumulators per output
     for (int idx = tid; idx < kC1Slice * kW1; idx += kDecideThreads) {
         int ol = idx / kW1, t = idx - ol * kW1, o = rank * kC1Slice + ol;
@@ -102,6 +143,7 @@ __device__ void net_forward_cluster(cg::cluster_group& cluster, const NetWeights
         double v = (acc[0] + acc[1]) + (acc[2] + acc[3]);
         A1[o * kW1 + t] = v > 0.0 ? v : 0.0;
     }
+#endif
     cluster.sync();
     // gather the other CTAs' conv1 slices through DSMEM
     for (int r = 1; r < kClusterSize; ++r) {
@@ -113,6 +155,36 @@ __device__ void net_forward_cluster(cg::cluster_group& cluster, const NetWeights
         }
     }
     __syncthreads();
+#if TRL_DECIDE_TILE
+    {
+        constexpr int nt = (kW2 + kConvTile - 1) / kConvTile;
+        for (int item = tid; item < kC2Slice * nt; item += kDecideThreads) {
+            const int ol = item / nt, t0 = (item - ol * nt) * kConvTile, o = rank * kC2Slice + ol;
+            const double* w = W2s + ol * kConv1Out * kConv2K;
+            double acc[kConvTile][4];
+#pragma unroll
+            for (int j = 0; j < kConvTile; ++j) { acc[j][0] = W.conv2_b[o]; acc[j][1] = 0.0; acc[j][2] = 0.0; acc[j][3] = 0.0; }
+#pragma unroll 8
+            for (int c = 0; c < kConv1Out; ++c) {
+                const double* a = A1 + c * kW1;
+                double av[kConvTile + kConv2K - 1];
+#pragma unroll
+                for (int i = 0; i < kConvTile + kConv2K - 1; ++i) av[i] = a[min(t0 + i, kW1 - 1)];
+#pragma unroll
+                for (int k = 0; k < kConv2K; ++k) {
+                    const double wk = w[c * kConv2K + k];
+#pragma unroll
+                    for (int j = 0; j < kConvTile; ++j) acc[j][c & 3] += wk * av[j + k];
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < kConvTile; ++j) {
+                const double v = (acc[j][0] + acc[j][1]) + (acc[j][2] + acc[j][3]);
+                if (t0 + j < kW2) A2[ol * kW2 + t0 + j] = v > 0.0 ? v : 0.0;
+            }
+        }
+    }
+#else
     // conv2: this CTA's 4 output channels; 4 independent accumulators per output
     for (int idx = tid; idx < kC2Slice * kW2; idx += kDecideThreads) {
         int ol = idx / kW2, t = idx - ol * kW2, o = rank * kC2Slice + ol;
@@ -127,6 +199,7 @@ __device__ void net_forward_cluster(cg::cluster_group& cluster, const NetWeights
         double v = (acc[0] + acc[1]) + (acc[2] + acc[3]);
         A2[idx] = v > 0.0 ? v : 0.0;
     }
+#endif
     __syncthreads();
     // terr_ip0 (64 x 5984): K-split -- this CTA multiplies its own 4 x 187 slice of the flattened conv2 output.
     // 4 rows per warp, 4 columns per trip: 16 independent weight loads in flight per lane.
@@ -276,7 +349,10 @@ __device__ void net_forward_cluster(cg::cluster_group& cluster, const NetWeights
     cluster.sync();   // Y complete in rank 0; peers may reuse T / H / HH afterwards
 }
 
-__global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kDecideThreads, 2)
+#ifndef TRL_DECIDE_MIN_BLOCKS
+#define TRL_DECIDE_MIN_BLOCKS 2
+#endif
+__global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kDecideThreads, TRL_DECIDE_MIN_BLOCKS)
 trl_decide_kernel(Buffers B, NetWeights W, const ExpSettings* __restrict__ ex_dev, int* done_count, int list, int rearm) {
     TRL_DYN_SHARED(double, sh);
     cg::cluster_group cluster = cg::this_cluster();

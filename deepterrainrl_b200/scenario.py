@@ -29,6 +29,11 @@ VARIANTS = {
     "smem_xchg": ["-DTRL_SMEM_XCHG=1"],
     "smem_xchg_3cta": ["-DTRL_SMEM_XCHG=1", "-DTRL_STEP_MIN_BLOCKS=3"],
     "noinline_cold": ["-DTRL_NOINLINE_COLD=1"],
+    # decision kernel: register-tiled conv1 / conv2 (the untiled loops are shared-memory-bandwidth bound)
+    "decide_tile2": ["-DTRL_DECIDE_TILE=1", "-DTRL_CONV_TILE=2"],
+    "decide_tile4": ["-DTRL_DECIDE_TILE=1", "-DTRL_CONV_TILE=4"],
+    "decide_tile4_128r": ["-DTRL_DECIDE_TILE=1", "-DTRL_CONV_TILE=4", "-DTRL_DECIDE_MIN_BLOCKS=1"],
+    "smem_xchg_decide_tile4": ["-DTRL_SMEM_XCHG=1", "-DTRL_DECIDE_TILE=1", "-DTRL_CONV_TILE=4"],
 }
 STEP_UNITS = ("trl_step.cu", "trl_step_cg.cu")      # the only translation units the variant flags reach
 

@@ -184,7 +184,7 @@ def test_trainer_kernels_vs_oracle(assets):
 
 
 # ------------------------------------------------------------------------------------------------ schedules and variants
-def _trajectory(defines, pack, n, steps, seed=0, updates=0):
+def _trajectory(defines, pack, n, steps, seed=0, updates=0, net_out=False):
     import deepterrainrl_b200 as trl
     with simt_library(defines) as L:
         L.simt_set_sched_seed(C.c_ulonglong(seed))
@@ -200,10 +200,11 @@ def _trajectory(defines, pack, n, steps, seed=0, updates=0):
                 g.Update(1.0 / 30.0)
                 q, qd = g.GetStateAll()
                 out.append(np.concatenate([q, qd]).copy())
+            y = np.stack([g.GetNetOut(e) for e in range(n)]) if net_out else None
             g.close()
         finally:
             L.simt_set_sched_seed(C.c_ulonglong(0))
-        return np.stack(out)
+        return (np.stack(out), y) if net_out else np.stack(out)
 
 
 def test_kernels_have_no_schedule_dependent_results(assets):
@@ -222,6 +223,8 @@ VARIANTS = [
     ["-DTRL_OUTWARD_SMEM=1"],
     ["-DTRL_CONTACT_SMEM=1"],
     ["-DTRL_SMEM_XCHG=1"],
+    ["-DTRL_DECIDE_TILE=1", "-DTRL_CONV_TILE=2"],
+    ["-DTRL_DECIDE_TILE=1", "-DTRL_CONV_TILE=4"],
 ]
 
 
@@ -230,6 +233,15 @@ VARIANTS = [
 def test_experimental_variant_is_bit_identical(assets, defines, scene):
     """Opt-in builds of the step kernel (profiles/step_kernel_r01_source_phases.md) only move data differently: same values,
     same operation order -> bit-identical trajectories, also under a permuted lane schedule."""
+    if "-DTRL_DECIDE_TILE=1" in defines:
+        # decision-kernel variants: what matters is the network output of every decision, compared bit for bit
+        if scene != "raptor_narrow_gaps" and defines[-1] != "-DTRL_CONV_TILE=4":
+            pytest.skip("one scene per tile size (suite time)")
+        pack = os.path.join(assets, scene + ".trlpack")
+        ref_t, ref_y = _trajectory([], pack, 3, 130, updates=1, net_out=True)
+        t, y = _trajectory(defines, pack, 3, 130, updates=1, net_out=True)
+        assert np.array_equal(ref_y, y) and np.array_equal(ref_t, t) and np.abs(y).max() > 0
+        return
     if scene == "goat_cliffs" and defines != ["-DTRL_SMEM_XCHG=1"]:
         pytest.skip("third scene only for the all-on build (suite time)")
     pack = os.path.join(assets, scene + ".trlpack")
