@@ -55,3 +55,65 @@ def test_gloo_world2_tuple_gather(assets, tmp_path):
     assert r0["env"][:n0].max() < 4 and r0["env"][n0:].min() >= 4
     assert int(r0["steps"]) == 2 * 4 * 60 * 20
     assert set(r0["seeds"]).isdisjoint(set(r1["seeds"]))
+
+
+def _emu_worker(rank, world, port, pack, out_dir):
+    """tools/train_multi.py at world size 2 without GPUs: every rank's engine AND trainer are the kernel sources on the SIMT emulator
+    (tests/simt/), the exchange is the product's fixed-block all-gather over gloo."""
+    import ctypes as C
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests", "simt"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from loader import open_simt
+    from deepterrainrl_b200 import parallel, scenario
+    import deepterrainrl_b200 as trl
+    L = open_simt()
+    scenario._LIB = L                                   # this process only ever sees the emulator build
+    n = 6
+    sc = trl.ScenarioExpMACE(pack, n, terrain_seeds=parallel.shard_seeds(rank, n), rng_seed=100 + rank)
+    tr = trl.MACETrainer(sc, replay_mem_size=160, num_init_samples=32, freeze_target_iters=3, seed=9)
+    sc.EnableExplore(True, 0.1, 0.025, 0.0)
+    # the device tuple block as torch views (BatchedScenario.DeviceTupleBlock does the same through the CUDA array interface)
+    ptrs = [C.c_void_p() for _ in range(4)]
+    cap, width = C.c_int(0), C.c_int(0)
+    assert L.trl_device_tuple_block(sc.h, *[C.byref(p) for p in ptrs], C.byref(cap), C.byref(width)) == 0
+
+    def view(p, shape, ctype):
+        return torch.from_numpy(np.ctypeslib.as_array(C.cast(p, C.POINTER(ctype)), shape))
+    rows, flags = view(ptrs[0], (cap.value, width.value), C.c_double), view(ptrs[1], (cap.value,), C.c_int32)
+    env, count = view(ptrs[2], (cap.value,), C.c_int32), view(ptrs[3], (1,), C.c_int32)
+    total = 0
+    for k in range(74):
+        sc.Update(1.0 / 30.0)
+        sc.Sync()
+        g = parallel.gather_tuple_blocks_fixed(rows, flags, env, count, env_offset=rank * n, block_rows=64)
+        sc.ResetTupleBuffer()
+        r, f, e = parallel.unpack_tuple_blocks(g)
+        if len(r):                                      # MACETrainer.AddTuplesDevice without its CUDA stream handling
+            r64, f32 = r.to(torch.float64).contiguous(), f.to(torch.int32).contiguous()
+            assert L.trl_trainer_add_device(tr.h, C.c_void_p(r64.data_ptr()), C.c_void_p(f32.data_ptr()), len(r64)) == 0
+            sc.Sync()
+            total += len(r64)
+        if k >= 70:
+            tr.Train(1)                                 # the first call initialises the input offset / scale
+    c = tr.counters()
+    np.savez(os.path.join(out_dir, f"e{rank}.npz"), theta=tr.get("theta"), total=total, iters=c["iter"], num=c["num"], critic=c["critic"], stage=c["stage"],
+             local_cycles=sc._stats()["cycles"])
+    tr.close(); sc.close()
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_emulated_engines_replicated_trainers(assets, tmp_path):
+    """BASELINE configs[3] in miniature on the CPU tier: two ranks, each rolling out its own shard with the env-step / decision
+    kernel sources, ONE fixed-block all-gather of the tuple blocks per outer update, the gathered block fed to each rank's own
+    on-device trainer -- the replicas must stay bit-identical without a weight broadcast."""
+    pack = os.path.join(assets, "dog_slopes_mixed.trlpack")
+    port = 29500 + ((os.getpid() + 517) % 1000)
+    mp.spawn(_emu_worker, args=(2, port, pack, str(tmp_path)), nprocs=2, join=True)
+    e0 = np.load(tmp_path / "e0.npz"); e1 = np.load(tmp_path / "e1.npz")
+    assert int(e0["total"]) == int(e1["total"]) >= 32 and int(e0["num"]) == int(e1["num"]) == int(e0["total"])
+    assert int(e0["iters"]) == int(e1["iters"]) >= 2, (int(e0["total"]), int(e0["critic"]), int(e0["stage"]))
+    assert int(e0["local_cycles"]) > 0 and int(e1["local_cycles"]) > 0
+    np.testing.assert_array_equal(e0["theta"], e1["theta"])          # bit-identical replicas
