@@ -183,6 +183,31 @@ def test_trainer_kernels_vs_oracle(assets):
         g.close()
 
 
+def test_trainer_kernels_have_no_schedule_dependent_results(assets):
+    """The trainer's ~140 launches per iteration lean on __syncthreads and shared-memory staging: same race check as for the
+    step / decision kernels -- a permuted thread schedule must not change a single weight."""
+    from test_gpu_trainer import _synthetic_tuples
+    import deepterrainrl_b200 as trl
+    pack = os.path.join(assets, "raptor_narrow_gaps.trlpack")
+    kw = dict(num_init_samples=64, num_steps_per_iter=1, freeze_target_iters=3, init_input_offset_scale=1, seed=5)
+    thetas = []
+    with simt_library() as L:
+        for seed in (0, 31337):
+            sc = trl.ScenarioExpMACE(pack, 2)
+            g = trl.MACETrainer(sc, replay_mem_size=128, **kw)
+            rows, flags = _synthetic_tuples(96, g.S, g.A, g.get("in_off"), g.get("in_scale"), 8)
+            L.simt_set_sched_seed(C.c_ulonglong(seed))
+            try:
+                g.AddTuples(rows, flags)
+                g.Train(2)
+            finally:
+                L.simt_set_sched_seed(C.c_ulonglong(0))
+            assert g.counters()["iter"] >= 1
+            thetas.append(g.get("theta"))
+            g.close(); sc.close()
+    assert np.array_equal(thetas[0], thetas[1])
+
+
 # ------------------------------------------------------------------------------------------------ schedules and variants
 def _trajectory(defines, pack, n, steps, seed=0, updates=0, net_out=False):
     import deepterrainrl_b200 as trl
