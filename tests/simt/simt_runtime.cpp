@@ -113,6 +113,21 @@ void yield_until_changed(const volatile unsigned* gen, unsigned val) {
             return;
         }
     }
+    // ... or to the next runnable thread of the group (CTA-wide and cluster-wide barriers)
+    if (!sched_seed) {
+        const int ng = t->group_size;
+        for (int k = 1; k < ng; ++k) {
+            int i = t->group_index + k;
+            if (i >= ng) i -= ng;
+            Thread& c = t->group_base[i];
+            if (c.done || (c.wait_gen && *c.wait_gen == c.wait_val)) continue;
+            c.wait_gen = nullptr;
+            cur = &c;
+            threadIdx = c.tid; blockIdx = c.bid;
+            simt_switch(&t->sp, c.sp);
+            return;
+        }
+    }
     simt_switch(&t->sp, sched_sp);
 }
 
@@ -158,6 +173,7 @@ void run_grid(dim3 grid, dim3 block, size_t dyn_smem_bytes, int cluster_size, co
                 th.cluster = &cl;
                 th.warp_base = &threads[(size_t)b * nthreads + (t / 32) * 32];
                 th.warp_lanes = std::min(32, nthreads - (t / 32) * 32);
+                th.group_base = threads.data(); th.group_size = group_threads; th.group_index = b * nthreads + t;
                 char* top = pool.get((size_t)b * nthreads + t) + kStackBytes;
                 void** sp = (void**)(((uintptr_t)top & ~(uintptr_t)15));
                 *--sp = nullptr;                    // fake return address of fiber_entry (keeps rsp = 8 mod 16 at entry)

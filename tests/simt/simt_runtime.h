@@ -84,6 +84,8 @@ struct Thread {
     unsigned wait_val = 0;
     Thread* warp_base = nullptr;   // lane 0 of this thread's warp (the lanes are contiguous)
     int warp_lanes = 0;
+    Thread* group_base = nullptr;  // first thread of the co-scheduled group (CTA, or all CTAs of a cluster)
+    int group_size = 0, group_index = 0;
 };
 
 extern thread_local Thread* cur;

@@ -199,7 +199,7 @@ def test_trainer_kernels_have_no_schedule_dependent_results(assets):
             L.simt_set_sched_seed(C.c_ulonglong(seed))
             try:
                 g.AddTuples(rows, flags)
-                g.Train(2)
+                g.Train(1)
             finally:
                 L.simt_set_sched_seed(C.c_ulonglong(0))
             assert g.counters()["iter"] >= 1
