@@ -596,7 +596,9 @@ def test_scenario_matches_reference_code(assets, tmp_path, scene, mode, n_update
     st["cyc"] = 0
     if record:
         from deepterrainrl_b200.records import CycleRecorder
-        rec = CycleRecorder(0, o.S, o.A, str(tmp_path / "actions.txt"), str(tmp_path / "ids.txt"))
+        rec = CycleRecorder(0, o.S, o.A, str(tmp_path / "actions.txt"), str(tmp_path / "ids.txt"), vel_file=str(tmp_path / "vel.txt"),
+                            pack=pack)
+        extra += [b"-record_vel=", b"true", b"-vel_output_file=", str(tmp_path / "ref_vel.txt").encode()]
         extra += [b"-record_actions=", b"true", b"-action_output_file=", str(tmp_path / "ref_actions.txt").encode(),
                   b"-record_action_id_state=", b"true", b"-action_id_state_output_file=", str(tmp_path / "ref_ids.txt").encode()]
     arr = (C.c_char_p * len(extra))(*extra)
@@ -624,6 +626,8 @@ def test_scenario_matches_reference_code(assets, tmp_path, scene, mode, n_update
             if not st["ended"]:
                 L.orc_end_update(o.h, 0, DT)
             st["in_update"] = False
+            if record:
+                rec.poll(o.get_ctrl(0), DT)               # RecordVel
             compare_step()
             st["cmp"] = False
             pose, vel, _ = ref_state()
@@ -656,10 +660,14 @@ def test_scenario_matches_reference_code(assets, tmp_path, scene, mode, n_update
             summary = f"{es['cycles']} cycles, {n} episodes"
             if record:
                 ref_a = open(tmp_path / "ref_actions.txt").read().splitlines()
-                n_act = len(ref_a) - rec.cycles           # InitActionRecord first lists the base actions ("%i, %.5f"), not emitted by the product
+                n_act = len(ref_a) - rec.cycles           # InitActionRecord first lists the base actions ("%i, %.5f")
                 assert n_act >= 1 and rec.cycles >= 10 and all(", " in l and ",\t" not in l for l in ref_a[:n_act])
-                assert ref_a[n_act:] == open(tmp_path / "actions.txt").read().splitlines()
+                assert ref_a == open(tmp_path / "actions.txt").read().splitlines()          # table + records, byte for byte
                 assert open(tmp_path / "ref_ids.txt").read() == open(tmp_path / "ids.txt").read()
+                ref_v = open(tmp_path / "ref_vel.txt").read().splitlines()
+                got_v = open(tmp_path / "vel.txt").read().splitlines()
+                assert len(ref_v) == len(got_v) == rec.cycles
+                assert np.max(np.abs(np.array(ref_v, float) - np.array(got_v, float))) <= 2e-6     # "%f" of values equal to ~1e-12
                 summary += f", {rec.cycles} action / action-id-state records byte-identical to the reference's files"
         else:
             rows, flags, _ = o.tuples()
