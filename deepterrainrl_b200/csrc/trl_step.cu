@@ -134,6 +134,19 @@ constexpr int X_END = TRL_SMEM_ALIGNED ? ((X_KIN_END + 1) & ~1) : X_KIN_END;
 #define TRL_PHYS_XS_ARG
 #endif
 
+// 128-bit shared-memory accesses of the experiment builds need 16-byte aligned addresses (a misaligned one faults on the GPU);
+// the emulator build checks every such cast, the CUDA build compiles to the plain cast
+#ifdef TRL_SIMT_EMU
+template <typename T2, typename T>
+inline T2* trl_as2(T* p) {
+    if (reinterpret_cast<uintptr_t>(p) & 15u) { std::fprintf(stderr, "simt: misaligned 128-bit shared-memory access\n"); std::abort(); }
+    return reinterpret_cast<T2*>(p);
+}
+#else
+template <typename T2, typename T>
+__device__ __forceinline__ T2* trl_as2(T* p) { return reinterpret_cast<T2*>(p); }
+#endif
+
 __device__ __forceinline__ int tri(int a, int b) { return a * (a + 1) / 2 + b; }  // a >= b
 __device__ __forceinline__ double shf(double v, int src) { return __shfl_sync(kFull, v, src); }
 __device__ __forceinline__ int shfi(int v, int src) { return __shfl_sync(kFull, v, src); }
@@ -410,7 +423,7 @@ __device__ __forceinline__ LinkC load_link(int lane) {
     do {                                                                                        \
         _Pragma("unroll") for (int r_ = 0; r_ < 4; ++r_) {                                      \
             int an_ = (r_ == 0) ? c.anc1 : ((r_ == 1) ? c.anc2 : ((r_ == 2) ? c.anc4 : c.anc8)); \
-            double2* buf_ = reinterpret_cast<double2*>(xs + X_PFX + (r_ & 1) * 2 * kWarp);      \
+            double2* buf_ = trl_as2<double2>(xs + X_PFX + (r_ & 1) * 2 * kWarp);      \
             buf_[lane] = make_double2((a), (b));                                                \
             __syncwarp();                                                                       \
             const double2 t_ = buf_[an_];                                                       \
@@ -440,7 +453,7 @@ __device__ __forceinline__ Kin kinematics(const LinkC& c, const EnvRegs& e TRL_K
 #if TRL_KIN_SMEM
     double pcw, psw;
     {
-        double2* buf = reinterpret_cast<double2*>(xs + X_PFX + 2 * 2 * kWarp);
+        double2* buf = trl_as2<double2>(xs + X_PFX + 2 * 2 * kWarp);
         buf[lane] = make_double2(k.cw, k.sw);
         __syncwarp();
         const double2 t = buf[c.parent];
@@ -472,11 +485,11 @@ __device__ __forceinline__ Kin kinematics(const LinkC& c, const EnvRegs& e TRL_K
 #define TRL_ACCUM_ROUND(r, NV, vals)                                                        \
     do {                                                                                    \
         const int src_ = (int)(lc.acc_src >> (5 * (r))) & 31;                               \
-        double2* mine_ = reinterpret_cast<double2*>(xs + X_ACC + lane * kAccStride);        \
+        double2* mine_ = trl_as2<double2>(xs + X_ACC + lane * kAccStride);        \
         _Pragma("unroll") for (int v_ = 0; v_ + 1 < (NV); v_ += 2) mine_[v_ / 2] = make_double2((vals)[v_], (vals)[v_ + 1]); \
         if ((NV) & 1) xs[X_ACC + lane * kAccStride + (NV) - 1] = (vals)[(NV) - 1];         \
         __syncwarp();                                                                       \
-        const double2* from_ = reinterpret_cast<const double2*>(xs + X_ACC + src_ * kAccStride); \
+        const double2* from_ = trl_as2<const double2>(xs + X_ACC + src_ * kAccStride); \
         _Pragma("unroll") for (int v_ = 0; v_ + 1 < (NV); v_ += 2) {                        \
             const double2 t_ = from_[v_ / 2];                                               \
             (vals)[v_] += t_.x; (vals)[v_ + 1] += t_.y;                                     \
@@ -647,7 +660,7 @@ __device__ double controller_torque(Lane& L, const LinkC& lc, const EnvRegs& e, 
         const double lij = row[j] * inv;
 #pragma unroll
         for (int c0 = (j + 1) & ~1; c0 < kMaxDof; c0 += 2) {
-            const double2 t = *reinterpret_cast<const double2*>(col + c0);
+            const double2 t = *trl_as2<const double2>(col + c0);
             if (c0 > j && lane >= c0) row[c0] -= lij * t.x;
             if (c0 + 1 < kMaxDof && lane >= c0 + 1) row[c0 + 1] -= lij * t.y;
         }
@@ -844,9 +857,9 @@ __device__ int physics_substep(const LinkC& lc, EnvRegs& e, const GroundView& g,
     const int nc = m.n_corners;
 #if TRL_CONTACT_SMEM
     // per-link kinematics staged once per sub-step; a corner lane reads the entries of the body it belongs to
-    double2* kin0 = reinterpret_cast<double2*>(xs + X_KIN);                  // (cw, sw)
-    double2* kin1 = reinterpret_cast<double2*>(xs + X_KIN + 2 * kWarp);      // (rx, ry)
-    double2* kin2 = reinterpret_cast<double2*>(xs + X_KIN + 4 * kWarp);      // (w, vx)
+    double2* kin0 = trl_as2<double2>(xs + X_KIN);                  // (cw, sw)
+    double2* kin1 = trl_as2<double2>(xs + X_KIN + 2 * kWarp);      // (rx, ry)
+    double2* kin2 = trl_as2<double2>(xs + X_KIN + 4 * kWarp);      // (w, vx)
     double* kin3 = xs + X_KIN + 6 * kWarp;                                   // vy
     kin0[lane] = make_double2(k.cw, k.sw); kin1[lane] = make_double2(k.rx, k.ry);
     kin2[lane] = make_double2(k.w, k.vx); kin3[lane] = k.vy;
@@ -914,7 +927,7 @@ __device__ int physics_substep(const LinkC& lc, EnvRegs& e, const GroundView& g,
             // corner order -- the order the shuffle loop below visits them in
             double* slot = xs + X_ACC + lane * kAccStride;
             if ((fmask >> lane) & 1u) {
-                double2* s2 = reinterpret_cast<double2*>(slot);
+                double2* s2 = trl_as2<double2>(slot);
                 s2[0] = make_double2(add[0], add[1]); s2[1] = make_double2(add[2], add[3]); s2[2] = make_double2(add[4], add[5]);
                 s2[3] = make_double2(add[6], add[7]); slot[8] = add[8];
             }
@@ -924,7 +937,7 @@ __device__ int physics_substep(const LinkC& lc, EnvRegs& e, const GroundView& g,
             for (int q = 0; q < 4; ++q) {
                 if ((my >> q) & 1u) {
                     const double* from = xs + X_ACC + (cb - base + q) * kAccStride;
-                    const double2* f2 = reinterpret_cast<const double2*>(from);
+                    const double2* f2 = trl_as2<const double2>(from);
                     const double2 t0 = f2[0], t1 = f2[1], t2 = f2[2], t3 = f2[3];
                     ia[0] += t0.x; ia[1] += t0.y; ia[2] += t1.x; ia[3] += t1.y; ia[4] += t2.x; ia[5] += t2.y;
                     ia[6] += t3.x; ia[7] += t3.y; ia[8] += from[8];
@@ -983,13 +996,13 @@ __device__ int physics_substep(const LinkC& lc, EnvRegs& e, const GroundView& g,
 #if TRL_OUTWARD_SMEM
         double* bs = xs + X_BASE;
         if (lane == 0) {
-            double2* b2 = reinterpret_cast<double2*>(bs);
+            double2* b2 = trl_as2<double2>(bs);
             b2[0] = make_double2(ia[0], ia[1]); b2[1] = make_double2(ia[2], ia[3]); b2[2] = make_double2(ia[4], ia[5]);
             b2[3] = make_double2(ia[6], ia[7]); bs[8] = ia[8];
         }
         __syncwarp();
-        const double2 q0 = reinterpret_cast<const double2*>(bs)[0], q1 = reinterpret_cast<const double2*>(bs)[1],
-                      q2 = reinterpret_cast<const double2*>(bs)[2], q3 = reinterpret_cast<const double2*>(bs)[3];
+        const double2 q0 = trl_as2<const double2>(bs)[0], q1 = trl_as2<const double2>(bs)[1],
+                      q2 = trl_as2<const double2>(bs)[2], q3 = trl_as2<const double2>(bs)[3];
         double a = q0.x, bx = q0.y, by = q1.x, cxx = q1.y, cxy = q2.x, cyy = q2.y;
         double r0 = -q3.x, r1 = -q3.y, r2 = -bs[8];
 #else
@@ -1009,7 +1022,7 @@ __device__ int physics_substep(const LinkC& lc, EnvRegs& e, const GroundView& g,
 #if TRL_OUTWARD_SMEM
         // every lane publishes its current (aw, ax, ay); a link of depth l reads its parent's, which is final since level l-1.
         // Levels alternate between two buffers: one barrier per level (see TRL_TREE_PREFIX2)
-        double2* o2 = reinterpret_cast<double2*>(xs + X_OUT + (l & 1) * kOutBuf);
+        double2* o2 = trl_as2<double2>(xs + X_OUT + (l & 1) * kOutBuf);
         double* o1 = xs + X_OUT + (l & 1) * kOutBuf + 2 * kWarp;
         o2[lane] = make_double2(aw, alx); o1[lane] = aly;
         __syncwarp();
