@@ -21,6 +21,15 @@ for v in "${names[@]}"; do
     ( TRL_VARIANT=$v python -c "import deepterrainrl_b200 as t; t.build_library()" > gpurun_out/variants/$v.build.txt 2>&1 ) &
 done
 wait
+# the experiment builds have never run on a GPU: one tiny update under compute-sanitizer first (out-of-range / misaligned shared
+# or global accesses would otherwise surface as a dead context in the middle of the A/B)
+for v in "${names[@]}"; do
+    case "$v" in smem_xchg|decide_tile4|smem_xchg_decide_tile4)
+        TRL_VARIANT=$v timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python -c "import __graft_entry__ as g; g.smoke()" \
+            > gpurun_out/variants/$v.memcheck.txt 2>&1
+        echo "$v memcheck: exit $? $(grep -c 'Invalid\|Misaligned' gpurun_out/variants/$v.memcheck.txt) errors" ;;
+    esac
+done
 for v in "${names[@]}"; do
     if [ "$v" = product ]; then export -n TRL_VARIANT; unset TRL_VARIANT; else export TRL_VARIANT=$v; fi
     timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_ref_golden.py -m gpu -x -q > gpurun_out/variants/$v.parity.txt 2>&1
