@@ -209,7 +209,20 @@ def test_trainer_kernels_have_no_schedule_dependent_results(assets):
 
 
 # ------------------------------------------------------------------------------------------------ schedules and variants
+_REF_CACHE = {}
+
+
 def _trajectory(defines, pack, n, steps, seed=0, updates=0, net_out=False):
+    """(cached for the product build at seed 0: every variant test compares with the same reference run)"""
+    key = (pack, n, steps, updates, net_out)
+    if not defines and seed == 0:
+        if key not in _REF_CACHE:
+            _REF_CACHE[key] = _trajectory_run(defines, pack, n, steps, seed, updates, net_out)
+        return _REF_CACHE[key]
+    return _trajectory_run(defines, pack, n, steps, seed, updates, net_out)
+
+
+def _trajectory_run(defines, pack, n, steps, seed, updates, net_out):
     import deepterrainrl_b200 as trl
     with simt_library(defines) as L:
         L.simt_set_sched_seed(C.c_ulonglong(seed))
