@@ -280,7 +280,7 @@ def main():
                    "env_steps_per_step": ENV_STEPS_PER_UPDATE * n, "sim_substeps": 5, "parallelism": f"env-shard x{world}",
                    "l2": "flushed between steps (256 MiB memset on the engine stream)",
                    "timing": "cudaEvent on the engine stream around K graph-launched updates",
-                   "presim_s": args.presim},
+                   "presim_s": args.presim, "build": os.environ.get("TRL_VARIANT") or "product"},
         "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": d2h,
                 "note": "poli_eval is closed-loop: no per-step host inputs exist; each step reads the counters and all poses/velocities back to host arrays (pinned staging, read-back of step k overlapped with step k+1)"},
         "gpu_launches": launches,
