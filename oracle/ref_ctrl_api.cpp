@@ -736,7 +736,11 @@ void ref_strain_schedule(RefTrainScn* r, int iters, double* out4) { r->scn->sche
 #pragma weak trl_eval_stats
 #pragma weak trl_dist_log
 #pragma weak trl_reset_avg_dist
+#define TRL_ADAPTER_WITH_REFERENCE_SCENARIO 1
 #include "../include/terrainrl_b200_adapter.h"
+// the deployment classes (Base = the reference's own cScenarioExpMACE / cScenarioPoliEval), every member instantiated: compile check
+template class cScenarioExpBatchedT<cScenarioExpMACE>;
+template class cScenarioPoliEvalBatchedT<cScenarioPoliEval>;
 
 typedef cScenarioExpBatchedT<FakeScnExp> BatchedExp;
 struct BatchedScnTrain : public cScenarioTrainMACE {
