@@ -789,6 +789,11 @@ void ref_btrain_destroy(BatchedScnTrain* r) {
 void ref_btrain_reseed(unsigned long rand_seed) { g_math_util_rand = cRand(); cMathUtil::SeedRand(rand_seed); }
 void ref_btrain_update(BatchedScnTrain* r, double dt) { r->Update(dt); }          // cScenarioTrain::Update -> UpdateExpScene
 void* ref_btrain_handle(BatchedScnTrain* r) { return r->exp0()->GetHandle(); }    // the trl_handle the adapter owns
+// what a deployment does after cNeuralNetLearner::SyncNet with the blobs of the (real) cNeuralNet: cScenarioExpBatched::PushWeights
+void ref_btrain_push_weights(BatchedScnTrain* r, const double* const* blobs, const int64_t* counts, int nblobs, const double* in_off,
+                             const double* in_scale, const double* out_off, const double* out_scale) {
+    r->exp0()->PushWeights(blobs, counts, nblobs, in_off, in_scale, out_off, out_scale);
+}
 // iter, tuples seen by the trainer; the exploration rate / temperature / base-action rate the compiled scenario holds
 void ref_btrain_status(BatchedScnTrain* r, long* counts, double* rates) {
     counts[0] = r->GetIter(); counts[1] = r->trainer_tuples();

@@ -244,7 +244,7 @@ def test_reference_training_scenario_drives_the_batch_through_the_adapter(assets
 
     saved = scenario._LIB
     scenario._LIB = L
-    st = dict(err=None, adapter=None)
+    st = dict(err=None, adapter=None, h=None)
     log = dict(copies=[], trains=0, evals=[0, 0, 0])
     try:
         # ---- the product-side loop's environment batch (same pack, seeds, call sequence as BuildScenePool makes through the adapter)
@@ -306,13 +306,20 @@ def test_reference_training_scenario_drives_the_batch_through_the_adapter(assets
 
         pending_sync = [False]
 
+        def push_weights(trainer):               # cScenarioExpBatched::PushWeights through the compiled adapter
+            blobs, in_off, in_scale, out_off, out_scale = weights_of(trainer)
+            blobs = [np.ascontiguousarray(b) for b in blobs]
+            ptrs = (C.c_void_p * len(blobs))(*[b.ctypes.data for b in blobs])
+            counts = np.array([b.size for b in blobs], np.int64)
+            ref.ref_btrain_push_weights(st["h"], ptrs, _p(counts), len(blobs), _p(in_off), _p(in_scale), _p(out_off), _p(out_scale))
+
         def cp(dst, src, u):
             log["copies"].append((dst, src))
             if (dst, src) == (2, 1):
                 OL.orc_trainer_copy_to_target(eng.h)
             elif (dst, src) == (0, 1):           # cNeuralNetLearner::SyncNet: hand the trained weights to the batch
                 if st["adapter"] is not None:
-                    st["adapter"].SetWeights(*weights_of(eng))
+                    push_weights(eng)
                 else:
                     pending_sync[0] = True       # the first SyncNet happens inside Init, before the handle is reachable from here
             else:
@@ -348,6 +355,7 @@ def test_reference_training_scenario_drives_the_batch_through_the_adapter(assets
         ref.ref_btrain_handle.argtypes = [C.c_void_p]
         ref.ref_btrain_status.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         ref.ref_btrain_destroy.argtypes = [C.c_void_p]
+        ref.ref_btrain_push_weights.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 4
         cwd = os.getcwd()
         os.chdir("/root/reference")
         try:
@@ -356,6 +364,7 @@ def test_reference_training_scenario_drives_the_batch_through_the_adapter(assets
             os.chdir(cwd)
         assert h and st["err"] is None, st["err"]
         h = C.c_void_p(h)
+        st["h"] = h
         # Init of the (never stepped) reference scene behind the adapter drew from cMathUtil's engine (CommandRandAction); from here
         # on only the compiled trainer's minibatch sampling does -- start it where the oracle trainer's restated cRand starts
         ref.ref_btrain_reseed.argtypes = [C.c_ulong]
@@ -366,7 +375,7 @@ def test_reference_training_scenario_drives_the_batch_through_the_adapter(assets
             st["adapter"] = ad
             assert (ad.num_envs, ad.state_size, ad.action_size) == (n_envs, g2.state_size, g2.action_size)
             if pending_sync[0]:
-                ad.SetWeights(*weights_of(eng))
+                push_weights(eng)
             # the product-side loop, brought to the state BuildScenePool leaves the adapter's batch in
             g2.SetWeights(*weights_of(orc))
             g2.EnableExplore(1, SCHED["init_exp_rate"], SCHED["init_exp_temp"], SCHED["init_exp_base_rate"])
