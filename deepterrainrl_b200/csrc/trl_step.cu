@@ -126,6 +126,14 @@ constexpr int X_END = TRL_SMEM_ALIGNED ? ((X_KIN_END + 1) & ~1) : X_KIN_END;
 #define TRL_RESET_XS_DECL
 #define TRL_RESET_XS_ARG
 #endif
+#ifndef TRL_REUSE_KIN
+#define TRL_REUSE_KIN 0    // 1 (experiment): the first physics sub-step of a launch reuses the kinematics the controller half of the same
+#endif                     // launch computed for the same state (one of six kinematics() per env-step); same inputs, bit-identical
+#if TRL_REUSE_KIN
+#define TRL_REUSE_KIN_DECL , const Kin* k0
+#else
+#define TRL_REUSE_KIN_DECL
+#endif
 #if TRL_SMEM_ALIGNED
 #define TRL_PHYS_XS_DECL , double* xs
 #define TRL_PHYS_XS_ARG , xs
@@ -833,11 +841,16 @@ __device__ double controller_torque(Lane& L, const LinkC& lc, const EnvRegs& e, 
 // One sub-step of articulated-body forward dynamics with linearly-implicit contact / joint-limit terms.
 // Updates e (q, qd, root translation) in place and returns the contact bitmask (same value in every lane).
 __device__ int physics_substep(const LinkC& lc, EnvRegs& e, const GroundView& g, const double* s_clx, const double* s_cly,
-                               const int* s_cbody, int lane, double dt, double clear_y TRL_PHYS_XS_DECL) {
+                               const int* s_cbody, int lane, double dt, double clear_y TRL_PHYS_XS_DECL TRL_REUSE_KIN_DECL) {
     const ModelConst& m = c_model;
     const PhysParams& pp = m.phys;
     const int md = m.max_depth;
+#if TRL_REUSE_KIN
+    Kin k;
+    if (k0) k = *k0; else k = kinematics(lc, e TRL_KIN_XS_ARG);
+#else
     Kin k = kinematics(lc, e TRL_KIN_XS_ARG);
+#endif
 
     // rigid inertia about O, bias force incl. gravity as an external force
     const double hx = lc.mass * k.cx, hy = lc.mass * k.cy, Io = lc.izz_c + lc.mass * (k.cx * k.cx + k.cy * k.cy);
@@ -1196,9 +1209,16 @@ trl_step_kernel(Buffers B, double h, int flags, int lists) {
     load_env(L, lc, e, lane);
     int contact = L.i(I_CONTACT);
 
+#if TRL_REUSE_KIN
+    Kin k_ctrl;
+    bool have_k = false;       // warp-uniform: the controller half ran and nothing has moved the state since
+#endif
     if (flags & 1) {
         // ---------------- controller half of env-step k
         Kin k = kinematics(lc, e TRL_KIN_XS_ARG);
+#if TRL_REUSE_KIN
+        k_ctrl = k; have_k = true;
+#endif
         e.tau = controller_torque(L, lc, e, k, xs, lane, h, contact);
         if (lane == 0) {
             // fall checks (sim/SimCharSoftFall.cpp:74-125)
@@ -1252,7 +1272,12 @@ trl_step_kernel(Buffers B, double h, int flags, int lists) {
             }
             do_reset = true;
         }
-        if (do_reset) { reset_env(L, lc, e, B, lane TRL_RESET_XS_ARG); contact = 0; }
+        if (do_reset) {
+            reset_env(L, lc, e, B, lane TRL_RESET_XS_ARG); contact = 0;
+#if TRL_REUSE_KIN
+            have_k = false;
+#endif
+        }
     }
 
     if (flags & 2) {
@@ -1263,7 +1288,12 @@ trl_step_kernel(Buffers B, double h, int flags, int lists) {
         // terrain maximum over the window the character's corners can reach during this env-step; kClearMargin covers the
         // contact tolerance measured along the surface normal on (near-)vertical cliff faces and the root's travel
         const double clear_y = g.window_max(e.ox - m.reach - 0.25, e.ox + m.reach + 0.25, lane) + kClearMargin;
+#if TRL_REUSE_KIN
+        for (int s = 0; s < ns; ++s)
+            contact = physics_substep(lc, e, g, s_clx, s_cly, s_cbody, lane, dt, clear_y TRL_PHYS_XS_ARG, (s == 0 && have_k) ? &k_ctrl : nullptr);
+#else
         for (int s = 0; s < ns; ++s) contact = physics_substep(lc, e, g, s_clx, s_cly, s_cbody, lane, dt, clear_y TRL_PHYS_XS_ARG);
+#endif
         // UpdateGround (scenarios/ScenarioSimChar.cpp:564-572): regenerate a segment when the view window crosses it
         {
             int smin = g.seg_id(0), smax = g.seg_id(1);

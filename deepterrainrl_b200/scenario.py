@@ -29,6 +29,8 @@ VARIANTS = {
     "smem_xchg": ["-DTRL_SMEM_XCHG=1"],
     "smem_xchg_3cta": ["-DTRL_SMEM_XCHG=1", "-DTRL_STEP_MIN_BLOCKS=3"],
     "noinline_cold": ["-DTRL_NOINLINE_COLD=1"],
+    "reuse_kin": ["-DTRL_REUSE_KIN=1"],
+    "smem_xchg_reuse_kin": ["-DTRL_SMEM_XCHG=1", "-DTRL_REUSE_KIN=1"],
     # decision kernel: register-tiled conv1 / conv2 (the untiled loops are shared-memory-bandwidth bound)
     "decide_tile2": ["-DTRL_DECIDE_TILE=1", "-DTRL_CONV_TILE=2"],
     "decide_tile4": ["-DTRL_DECIDE_TILE=1", "-DTRL_CONV_TILE=4"],
