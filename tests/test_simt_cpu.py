@@ -267,9 +267,19 @@ VARIANTS = [
 ]
 
 
+@pytest.fixture(scope="module")
+def variant_builds():
+    """compile every experiment build up front, several at a time (g++ is the slow part of this file, not the emulation)"""
+    from concurrent.futures import ThreadPoolExecutor
+    import build as simt_build
+    simt_build.build([])
+    with ThreadPoolExecutor(4) as ex:
+        list(ex.map(simt_build.build, VARIANTS))
+
+
 @pytest.mark.parametrize("defines", VARIANTS, ids=lambda d: " ".join(d))
 @pytest.mark.parametrize("scene", ["dog_slopes_mixed", "raptor_narrow_gaps", "goat_cliffs"])
-def test_experimental_variant_is_bit_identical(assets, defines, scene):
+def test_experimental_variant_is_bit_identical(assets, defines, scene, variant_builds):
     """Opt-in builds of the step kernel (profiles/step_kernel_r01_source_phases.md) only move data differently: same values,
     same operation order -> bit-identical trajectories, also under a permuted lane schedule."""
     if "-DTRL_DECIDE_TILE=1" in defines:
