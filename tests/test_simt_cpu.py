@@ -153,6 +153,70 @@ def test_update_graph_overlapped_schedule_and_tuples_vs_oracle(assets):
         g.close()
 
 
+def test_serial_schedule_single_env_reset_and_two_scenes(assets, monkeypatch):
+    """Host paths of tests/test_gpu_scenarios.py in miniature: the overlapped two-stream schedule equals the serial one bit for
+    bit (states, counters, tuples as sets); trl_reset of one env / trl_set_state leave the neighbours alone; two handles with
+    different scenes interleave (the constant-memory model is re-uploaded on every switch)."""
+    import deepterrainrl_b200 as trl
+    dog = os.path.join(assets, "dog_slopes_mixed.trlpack")
+    rap = os.path.join(assets, "raptor_narrow_gaps.trlpack")
+    with simt_library():
+        n = 5
+        monkeypatch.setenv("TRL_SERIAL_SCHEDULE", "1")
+        ser = trl.ScenarioExpMACE(dog, n, rng_seed=7)
+        monkeypatch.setenv("TRL_SERIAL_SCHEDULE", "0")
+        ovl = trl.ScenarioExpMACE(dog, n, rng_seed=7)
+        for sc in (ser, ovl):
+            sc.EnableExplore(True, 0.2, 0.025, 0.01)
+        l0s, l0o = ser.KernelLaunches(), ovl.KernelLaunches()
+        for _ in range(36):
+            ser.Update(1.0 / 30.0)
+            ovl.Update(1.0 / 30.0)
+        assert ser.KernelLaunches() - l0s == 36 * 42 and ovl.KernelLaunches() - l0o == 36 * 61
+        for a, b in zip(ser.GetStateAll(), ovl.GetStateAll()):
+            np.testing.assert_array_equal(a, b)
+        assert ser._stats() == ovl._stats()
+        ra, fa, ea = ser.GetTuples(f64=True)
+        rb, fb, eb = ovl.GetTuples(f64=True)
+        assert ra.shape == rb.shape and ra.shape[0] >= n
+        ka = np.lexsort(np.column_stack([ea, fa, ra]).T[::-1])
+        kb = np.lexsort(np.column_stack([eb, fb, rb]).T[::-1])
+        np.testing.assert_array_equal(ea[ka], eb[kb])
+        np.testing.assert_array_equal(fa[ka], fb[kb])
+        np.testing.assert_array_equal(ra[ka], rb[kb])
+        # one env reset / state installed, neighbours untouched
+        q0 = trl.ScenarioExpMACE(dog, 1, rng_seed=7).GetState(0)
+        q1, qd1, tau1, c1 = ovl.GetState(3)
+        other = ovl.GetState(4)[0].copy()
+        ovl.Reset([3])
+        q2, qd2, tau2, _ = ovl.GetState(3)
+        np.testing.assert_array_equal(q2[2:], q0[0][2:])
+        np.testing.assert_array_equal(qd2, q0[1])
+        assert np.all(tau2 == 0)
+        np.testing.assert_array_equal(ovl.GetState(4)[0], other)
+        ovl.SetState(2, q=q1, qd=qd1, tau=tau1, contact=c1)
+        q3, qd3, tau3, c3 = ovl.GetState(2)
+        assert all(np.array_equal(x, y) for x, y in ((q3, q1), (qd3, qd1), (tau3, tau1), (c3, c1)))
+        ser.close(); ovl.close()
+        # two scenes alive at once
+        a = trl.ScenarioPoliEval(dog, 3)
+        for _ in range(4):
+            a.Update(1.0 / 30.0)
+        qa = a.GetStateAll()[0].copy()
+        b = trl.ScenarioPoliEval(rap, 3)
+        for _ in range(4):
+            b.Update(1.0 / 30.0)
+        qb = b.GetStateAll()[0].copy()
+        a2, b2 = trl.ScenarioPoliEval(dog, 3), trl.ScenarioPoliEval(rap, 3)
+        for _ in range(4):
+            a2.Update(1.0 / 30.0)
+            b2.Update(1.0 / 30.0)
+        np.testing.assert_array_equal(a2.GetStateAll()[0], qa)
+        np.testing.assert_array_equal(b2.GetStateAll()[0], qb)
+        for sc in (a, b, a2, b2):
+            sc.close()
+
+
 def test_trainer_kernels_vs_oracle(assets):
     from pyoracle import OracleTrainer
     from test_gpu_trainer import _synthetic_tuples
