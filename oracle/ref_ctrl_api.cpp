@@ -6,7 +6,10 @@
 //     SimDog, SimRaptor), the kinematics and rigid-body sources of libref_rbd, the ground (sim/Ground, GroundVar2D, TerrainGen2D);
 //   * the scenarios (scenarios/Scenario, ScenarioSimChar, ScenarioPoliEval, ScenarioExp, ScenarioExpMACE, ScenarioTrain,
 //     ScenarioTrainMACE), util/ArgParser, learning/ExpTuple;
-//   * the trainer (learning/TrainerInterface, NeuralNetTrainer, MACETrainer, NeuralNetLearner).
+//   * the trainer (learning/TrainerInterface, NeuralNetTrainer, MACETrainer, NeuralNetLearner);
+//   * the evaluation driver (optimizer/scenarios/OptScenarioPoliEval) and, compiled against the reference's headers, the product's
+//     C++ adapter (include/terrainrl_b200_adapter.h): the drop-in seam as a maintainer would build it (end of this file,
+//     tests/test_ref_adapter_cpu.py).
 // What those sources need from the simulation -- pose, velocity, contacts, body-part positions and rotations, the world step, the
 // network -- they obtain through virtual calls on cSimCharacter / cSimObj / cJoint / cWorld and through cNeuralNet; this file supplies
 // that back end from a state the test installs (the CPU oracle's state), using the reference's own cKinTree kinematics for positions
