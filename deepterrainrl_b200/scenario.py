@@ -36,6 +36,7 @@ VARIANTS = {
     "decide_tile4": ["-DTRL_DECIDE_TILE=1", "-DTRL_CONV_TILE=4"],
     "decide_tile4_128r": ["-DTRL_DECIDE_TILE=1", "-DTRL_CONV_TILE=4", "-DTRL_DECIDE_MIN_BLOCKS=1"],
     "smem_xchg_decide_tile4": ["-DTRL_SMEM_XCHG=1", "-DTRL_DECIDE_TILE=1", "-DTRL_CONV_TILE=4"],
+    "all": ["-DTRL_SMEM_XCHG=1", "-DTRL_REUSE_KIN=1", "-DTRL_DECIDE_TILE=1", "-DTRL_CONV_TILE=4"],
 }
 STEP_UNITS = ("trl_step.cu", "trl_step_cg.cu")      # the only translation units the variant flags reach
 

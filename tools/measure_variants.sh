@@ -24,7 +24,7 @@ wait
 # the experiment builds have never run on a GPU: one tiny update under compute-sanitizer first (out-of-range / misaligned shared
 # or global accesses would otherwise surface as a dead context in the middle of the A/B)
 for v in "${names[@]}"; do
-    case "$v" in smem_xchg|decide_tile4|smem_xchg_decide_tile4)
+    case "$v" in smem_xchg|decide_tile4|smem_xchg_decide_tile4|all)
         TRL_VARIANT=$v timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python -c "import __graft_entry__ as g; g.smoke()" \
             > gpurun_out/variants/$v.memcheck.txt 2>&1
         echo "$v memcheck: exit $? $(grep -c 'Invalid\|Misaligned' gpurun_out/variants/$v.memcheck.txt) errors" ;;
