@@ -25,8 +25,9 @@ sys.path.insert(0, os.path.join(HERE, "simt"))
 REF_CTRL = os.path.join(HERE, "..", "oracle", "_ref", "libref_ctrl.so")
 ARG_FILE = "args/opt_args_train_mace.txt"
 
-pytestmark = pytest.mark.skipif(not (os.path.exists(REF_CTRL) and os.path.isdir("/root/reference/args")),
-                                reason="oracle/_ref/libref_ctrl.so or the reference arg / data files absent")
+pytestmark = pytest.mark.skipif(not (os.path.exists(REF_CTRL) and os.path.isdir("/root/reference/args"))
+                                or __import__("platform").machine() != "x86_64",
+                                reason="oracle/_ref/libref_ctrl.so or the reference arg / data files absent (or not x86-64: emulator)")
 
 
 def _p(a):

@@ -22,6 +22,8 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "sim
 from loader import open_simt, simt_library  # noqa: E402
 
 H = 1.0 / 600.0
+pytestmark = pytest.mark.skipif(__import__("platform").machine() != "x86_64",
+                                reason="the emulator's fiber switch is written for x86-64")
 
 
 def _relerr(a, b):
