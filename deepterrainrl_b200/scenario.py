@@ -26,6 +26,8 @@ VARIANTS = {
     "kin_smem": ["-DTRL_KIN_SMEM=1"],
     "outward_smem": ["-DTRL_OUTWARD_SMEM=1"],
     "contact_smem": ["-DTRL_CONTACT_SMEM=1"],
+    "accum_ldlt": ["-DTRL_ACCUM_SMEM=1", "-DTRL_LDLT_SMEM=1"],                                  # the two largest families, 23 KB smem / CTA
+    "xchg_no_contact": ["-DTRL_ACCUM_SMEM=1", "-DTRL_LDLT_SMEM=1", "-DTRL_KIN_SMEM=1", "-DTRL_OUTWARD_SMEM=1"],   # 36 KB
     "smem_xchg": ["-DTRL_SMEM_XCHG=1"],
     "smem_xchg_3cta": ["-DTRL_SMEM_XCHG=1", "-DTRL_STEP_MIN_BLOCKS=3"],
     "noinline_cold": ["-DTRL_NOINLINE_COLD=1"],
