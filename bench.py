@@ -297,6 +297,17 @@ def main():
         line["cpu_baseline"] = {"value": cpu_val, "unit": "env-steps/s", "cores": cores, "kind": "port",
                                 "sample": f"{cpu_envs} envs x {cpu_updates} outer updates ({cpu_dt:.1f} s) on {cores} threads; "
                                           "restated CPU oracle (reduced-coordinate physics), not Bullet"}
+    try:
+        # the bound that actually binds: thread-level FP64 instructions of the step kernel against the FP64 pipe
+        # (64 lanes per SM and clock).  138 k per env-step = ncu's 566 M FP64 thread-instructions of one 4096-env launch
+        # (profiles/ncu_step_kernel_r01_final.csv, dog / slopes_mixed); an explanatory figure beside the contract's HBM roofline.
+        sm_mhz = float((clocks or {}).get("sm_mhz") or 1965.0)
+        fp64_peak = 148 * 64 * sm_mhz * 1e6
+        fp64_ach = 138.0e3 * n / launch_s
+        line["roofline"]["fp64_pipe"] = {"achieved_ginst_s": fp64_ach / 1e9, "peak_ginst_s": fp64_peak / 1e9, "frac": fp64_ach / fp64_peak,
+                                         "thread_inst_per_env_step": 138.0e3, "peak": "148 SMs x 64 FP64 lanes x measured SM clock"}
+    except Exception:
+        pass
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
