@@ -33,6 +33,7 @@ DT = 1.0 / 30.0
 # per env-step the persistent state must be read and written once (q, qd, held torque, 64-scalar
 # controller block = 133 scalars each way) plus <= 42 terrain vertices read: (133 * 2) * 8 B + 42 * 4 B for f64 state
 ALGO_BYTES_PER_ENV_STEP = 133 * 2 * 8 + 42 * 4
+FP64_INST_PER_LAUNCH_ENV = 138.0e3     # ncu smsp__sass_thread_inst_executed_op_fp64 of one 4096-env step launch / 4096 (dog)
 
 
 def measured_peaks():
@@ -98,8 +99,11 @@ class ClockSampler:
 
 def ncu_traffic_bytes():
     """dram__bytes_read.sum + dram__bytes_write.sum of one trl_step_kernel launch, from the committed `ncu --set full`
-    summary of the same workload (profiles/ncu_step_kernel_r01_final.csv); None if the summary is absent."""
-    path = os.path.join(ROOT, "profiles", "ncu_step_kernel_r01_final.csv")
+    summary of the same workload and build (profiles/ncu_step_kernel_r02.csv, regenerated whenever the kernel changes;
+    tools/ncu_summary.py writes it); None if the summary is absent."""
+    path = os.path.join(ROOT, "profiles", "ncu_step_kernel_r02.csv")
+    if not os.path.exists(path):
+        path = os.path.join(ROOT, "profiles", "ncu_step_kernel_r01_final.csv")
     unit_scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     total, seen = 0.0, 0
     try:
@@ -113,52 +117,161 @@ def ncu_traffic_bytes():
     return total if seen == 2 else None
 
 
-def cpu_reference(num_envs, seconds_target, threads):
-    """Times the CPU oracle (restated reference controller + this project's reduced-coordinate physics, f64) with
-    thread-per-env-slice like cOptScenarioPoliEval::Run (optimizer/scenarios/OptScenarioPoliEval.cpp:72-110)."""
+def granted_cores():
+    """CPUs this process can actually use: the affinity mask, capped by the cgroup CPU quota (cpu.max / cfs_quota).
+    os.cpu_count() reports the host's CPUs, which a container may not get."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    info = {"affinity": n, "host": os.cpu_count() or 1, "cgroup_quota": None}
+    quota = None
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:               # cgroup v2: "<quota|max> <period>"
+            q, per = f.read().split()[:2]
+            if q != "max":
+                quota = float(q) / float(per)
+    except (OSError, ValueError):
+        try:
+            with open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us") as f, open("/sys/fs/cgroup/cpu/cpu.cfs_period_us") as g:
+                q, per = float(f.read()), float(g.read())
+                if q > 0:
+                    quota = q / per
+        except (OSError, ValueError):
+            pass
+    if quota is not None:
+        info["cgroup_quota"] = quota
+        n = max(1, min(n, int(quota + 0.5)))
+    info["used"] = n
+    return n, info
+
+
+def cpu_reference(num_envs, seconds_target, threads, min_updates=1):
+    """Times the CPU oracle (restated reference controller + this project's reduced-coordinate physics, f64; the
+    -O3 -march=x86-64-v3 build when the host has AVX2 + FMA) with thread-per-env-slice like cOptScenarioPoliEval::Run
+    (optimizer/scenarios/OptScenarioPoliEval.cpp:72-110), one pinned thread per granted core."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    from pyoracle import Oracle
-    o = Oracle(PACK, num_envs, 0)
+    import pyoracle
+    o = pyoracle.Oracle(PACK, num_envs, 0, fast=True)
     o.update(DT, threads)   # warm-up
     t0 = time.perf_counter()
     updates = 0
-    while time.perf_counter() - t0 < seconds_target:
+    while updates < min_updates or time.perf_counter() - t0 < seconds_target:
         o.update(DT, threads)
         updates += 1
     dt = time.perf_counter() - t0
     steps = updates * ENV_STEPS_PER_UPDATE * num_envs
-    return steps / dt, dt, updates
+    build = "x86-64-v3 (AVX2+FMA)" if pyoracle.host_has_avx2_fma() else "portable x86-64"
+    return steps / dt, dt, updates, build
 
 
 def run_reference_arm(args, rank):
-    cores = os.cpu_count() or 1
+    """The CPU arm on the SAME configuration as the GPU arm (args.envs environments, one outer update per step), on every core
+    this process is granted.  A step is one outer update of all args.envs envs (81,920 env-steps at 4096); at least
+    --cpu-seconds (default 12 s) of timed CPU work, so a fast host runs more than K steps and the rate is a mean over all of them."""
     if rank != 0:
         return
-    envs = 4 * cores
-    per_step_s = 0.0
-    # warm-up + K steps, each step a bounded sample: `envs` environments advanced by one outer update
+    cores, core_info = granted_cores()
+    envs = args.envs
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    from pyoracle import Oracle
-    o = Oracle(PACK, envs, 0)
-    for _ in range(args.warmup):
+    import pyoracle
+    o = pyoracle.Oracle(PACK, envs, 0, fast=True)
+    for _ in range(max(1, min(args.warmup, 2))):       # the CPU has no clocks to ramp: two warm-up updates fill caches / page in
         o.update(DT, cores)
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    done = 0
+    while done < args.steps or time.perf_counter() - t0 < args.cpu_seconds:
         o.update(DT, cores)
+        done += 1
+        if time.perf_counter() - t0 > 150.0:            # hard stop: the whole arm stays within a few minutes on any host
+            break
     el = time.perf_counter() - t0
-    per_step_s = el / args.steps
+    per_step_s = el / done
     value = envs * ENV_STEPS_PER_UPDATE / per_step_s
+    build = "x86-64-v3 (AVX2+FMA)" if pyoracle.host_has_avx2_fma() else "portable x86-64"
     line = {
         "impl": "reference", "metric": "env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step_s * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "envs_per_gpu": args.envs},
+        "config": {"workload": WORKLOAD, "envs_per_gpu": envs, "env_steps_per_step": ENV_STEPS_PER_UPDATE * envs, "sim_substeps": 5,
+                   "steps_timed": done, "seconds_timed": el},
         "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port",
-                         "sample": f"{envs} envs x {args.steps} outer updates of 20 env-steps, thread-per-env-slice on {cores} threads; "
+                         "per_thread": value / cores, "core_info": core_info, "oracle_build": build,
+                         "sample": f"{envs} envs x {done} outer updates of 20 env-steps ({el:.1f} s), thread-per-env-slice on {cores} pinned threads; "
                                    "restated CPU oracle (reduced-coordinate physics), not Bullet"},
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+def run_config4(args, trl, rank, local_rank, world, n, dist, torch):
+    """BASELINE configs[3]: dog / slopes_mixed, args.envs envs per GPU, exploration on (args/opt_args_train_mace.txt rates), tuples of
+    all ranks all-gathered once per outer update into every rank's on-device trainer, args.train_iters trainer iterations per
+    update.  The whole loop is the C ABI's trl_train_run_timed (no Python between updates), device-timed on the engine stream, max
+    over ranks.  Returns the `config4` block of the JSON line."""
+    import ctypes as C
+    import numpy as np
+    from deepterrainrl_b200 import parallel
+    seeds = parallel.shard_seeds(rank, n)
+    sc = trl.ScenarioExpMACE(PACK, n, device=local_rank, terrain_seeds=seeds, rng_seed=100 + rank)
+    tr = trl.MACETrainer(sc, replay_mem_size=200000, num_init_samples=4000 * world, freeze_target_iters=50, seed=9)
+    L = sc.L
+    if world > 1:
+        comm = parallel.Comm(sc, rank, world, backend="nccl")          # the library's own NCCL communicator; id shipped over torch.distributed
+    else:
+        uid = (C.c_ubyte * 128)()
+        if L.trl_comm_unique_id(uid) != 0:
+            raise RuntimeError(L.trl_last_error().decode())
+        comm = parallel.Comm(sc, 0, 1, backend="nccl", unique_id=bytes(uid))
+    sp = np.array([0.9, 0.2, 20.0, 0.025, 0.9, 0.002, 2000.0, 2000.0, 0.0])    # cScenarioTrain annealing, shortened to 2000 iterations
+    L.trl_train_run_timed.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
+    state = C.c_int64(0)
+    ms = C.c_double(0)
+
+    def run(k, flush=1):
+        if L.trl_train_run_timed(tr.h, sp.ctypes.data_as(C.c_void_p), int(k), int(args.train_iters), int(args.block_rows), C.c_double(DT),
+                                 int(flush), C.byref(state), C.byref(ms)) != 0:
+            raise RuntimeError(L.trl_last_error().decode())
+        return ms.value
+
+    run(int(round(args.presim / DT)), flush=0)        # pre-roll: desynchronise the gait cycles, fill the replay memory past the init stage
+    run(max(args.warmup, 3))
+    l0, t0 = sc.KernelLaunches(), tr.KernelLaunches()
+    if dist is not None:
+        dist.barrier()
+    sc.Sync()
+    t_ms = run(args.steps)
+    launches = (sc.KernelLaunches() - l0) + (tr.KernelLaunches() - t0)
+    # the same K updates without exchange and trainer = what the rollout alone costs in exploration mode on this rank
+    sc.Sync()
+    roll_ms = sc.BenchUpdates(args.steps, DT, flush_l2=True)
+    # exposed device time of one exchange (pack end -> all-gather end on the comm stream), mean over 8 updates
+    gm = []
+    for _ in range(8):
+        sc.Update(DT); comm.GatherTuples(args.block_rows); comm.AddGathered(tr)
+        gm.append(comm.LastGatherMs())
+    counts = comm.Fetch(cap=1)[0]
+    spread = comm.ReplicaSpread(tr)
+    c = tr.counters()
+    dropped = comm.TuplesDropped()
+    if dist is not None:
+        t = torch.tensor([t_ms, roll_ms, float(np.mean(gm))], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_ms, roll_ms, g_ms = [float(x) for x in t.tolist()]
+    else:
+        g_ms = float(np.mean(gm))
+    out = {"workload": "dog/slopes_mixed exploration + tuple all-gather + MACE trainer (BASELINE configs[3])",
+           "value": args.steps * ENV_STEPS_PER_UPDATE * n * world / (t_ms * 1e-3), "unit": "env-steps/s", "ms_per_step": t_ms / args.steps,
+           "rollout_only_ms_per_step": roll_ms / args.steps, "gather_ms": g_ms,
+           "gather": "device pack kernel + one ncclAllGather of a fixed block per rank on a side stream (trl_gather_tuples), no host sync",
+           "block_rows": args.block_rows, "block_bytes_per_rank": 16 + 8 * args.block_rows + 4 * args.block_rows * sc.tuple_width,
+           "tuples_last_update_per_rank": [int(x) for x in counts], "tuples_dropped": int(dropped),
+           "train_iters_per_update": args.train_iters, "trainer": "replicated on every rank (deterministic; no weight broadcast needed)",
+           "trainer_iter": c["iter"], "actor_iter": c["actor_iter"], "replay_tuples": c["num"], "replica_spread": spread,
+           "gpu_launches": launches, "envs_per_gpu": n, "l2": "flushed between updates (256 MiB memset on the engine stream)",
+           "timing": "cudaEvent on the engine stream around K x {update, pack + all-gather, hand-over, trainer iterations}, max over ranks"}
+    tr.close(); comm.close(); sc.close()
+    return out
 
 
 def main():
@@ -171,6 +284,11 @@ def main():
     ap.add_argument("--scene", default="dog_slopes_mixed", choices=sorted(WORKLOADS),
                     help="asset pack; the default is the configuration the metric is quoted on, the others are side measurements")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--config4", type=int, default=1,
+                    help="also measure BASELINE configs[3] in the same run: exploration on, tuple all-gather every outer update, "
+                         "trainer iterations (0 = skip)")
+    ap.add_argument("--train-iters", type=int, default=4, help="trainer iterations per outer update in the config-4 block")
+    ap.add_argument("--block-rows", type=int, default=1024, help="tuple rows per rank and all-gather in the config-4 block")
     ap.add_argument("--presim", type=float, default=4.0,
                     help="seconds of simulated time run (untimed) before warm-up so gait cycles / episodes of the envs "
                          "are desynchronised like in a long evaluation (SURVEY §8d: warm-up 2 s sim)")
@@ -206,6 +324,9 @@ def main():
 
     # ---- untimed pre-roll to a statistically steady state (all envs start from the same pose, so their gait cycles,
     # policy decisions and falls are synchronised at first: per-update cost is atypically low then), then W warm-up steps
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()                # nvmlInit on a cold box takes a while: started before the pre-roll, checked before the timed region
     presim_updates = int(round(args.presim / DT))
     if presim_updates > 0:
         sc.BenchUpdates(presim_updates, DT, flush_l2=False)
@@ -213,10 +334,10 @@ def main():
     launches0 = sc.KernelLaunches()
 
     # ---- timed: exactly K steps, device-timed on the engine's stream, max over ranks
-    sampler = ClockSampler(local_rank)
     if rank == 0:
-        sampler.start()
-        time.sleep(0.05)
+        t_wait = time.perf_counter()
+        while not sampler.samples and sampler.err is None and time.perf_counter() - t_wait < 10.0:
+            time.sleep(0.01)
     barrier()
     t_beg = time.perf_counter()
     ms = sc.BenchUpdates(args.steps, DT, flush_l2=True)
@@ -258,8 +379,17 @@ def main():
     step_ms, step_l, dec_ms, dec_l = sc.UpdateTimed(DT)
     peaks, peak_kind = measured_peaks()
     launch_s = step_ms * 1e-3 / step_l
-    achieved = ALGO_BYTES_PER_ENV_STEP * n / launch_s / 1e9
+    # the step_l = 21 launches of one update advance every env by 20 env-steps (S_0 runs the physics half only, S_end the
+    # controller half only): one launch carries 20/21 of an env-step's algorithmic bytes per env
+    env_steps_per_launch = ENV_STEPS_PER_UPDATE / step_l
+    achieved = ALGO_BYTES_PER_ENV_STEP * n * env_steps_per_launch / launch_s / 1e9
     stats = sc._stats()
+
+    # ---- BASELINE configs[3] in the same run: exploration on, ONE all-gather of the tuple blocks per outer update through the
+    # C ABI (trl_gather_tuples), every rank's trainer fed with all ranks' tuples, trainer iterations between the updates
+    cfg4 = None
+    if args.config4 and args.scene == "dog_slopes_mixed":
+        cfg4 = run_config4(args, trl, rank, local_rank, world, n, dist if world > 1 else None, torch)
 
     if world > 1:
         dist.barrier()
@@ -268,9 +398,9 @@ def main():
             dist.destroy_process_group()
         return
 
-    cores = os.cpu_count() or 1
-    cpu_envs = 4 * cores
-    cpu_val, cpu_dt, cpu_updates = cpu_reference(cpu_envs, args.cpu_seconds, cores) if world == 1 else (None, 0, 0)
+    cores, core_info = granted_cores()
+    cpu_envs = n if args.cpu_seconds >= 8.0 else 4 * cores      # the stated configuration unless a short smoke run asked for less
+    cpu_val, cpu_dt, cpu_updates, cpu_build = cpu_reference(cpu_envs, args.cpu_seconds, cores) if world == 1 else (None, 0, 0, "")
 
     line = {
         "metric": "env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
@@ -288,26 +418,28 @@ def main():
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": achieved / peaks["hbm_gbs"], "traffic": ncu_traffic_bytes(), "peak_kind": peak_kind,
                      "kernel": "trl_step_kernel", "launch_ms": launch_s * 1e3,
-                     "algorithmic_bytes_per_env_step": ALGO_BYTES_PER_ENV_STEP,
+                     "algorithmic_bytes_per_env_step": ALGO_BYTES_PER_ENV_STEP, "env_steps_per_launch": env_steps_per_launch,
                      "step_kernel_share_of_update": step_ms / (step_ms + dec_ms),
                      "note": "path is FP64-latency bound, not HBM bound (SURVEY §8d): see DESIGN.md"},
         "sim": {"episodes": stats["episodes"], "cycles": stats["cycles"], "avg_dist_m": stats["avg_dist"]},
     }
     if cpu_val is not None:
-        line["cpu_baseline"] = {"value": cpu_val, "unit": "env-steps/s", "cores": cores, "kind": "port",
-                                "sample": f"{cpu_envs} envs x {cpu_updates} outer updates ({cpu_dt:.1f} s) on {cores} threads; "
+        line["cpu_baseline"] = {"value": cpu_val, "unit": "env-steps/s", "cores": cores, "kind": "port", "per_thread": cpu_val / cores,
+                                "core_info": core_info, "oracle_build": cpu_build,
+                                "sample": f"{cpu_envs} envs x {cpu_updates} outer updates ({cpu_dt:.1f} s) on {cores} pinned threads; "
                                           "restated CPU oracle (reduced-coordinate physics), not Bullet"}
-    try:
+    if cfg4 is not None:
+        line["config4"] = cfg4
+    if args.scene == "dog_slopes_mixed":
         # the bound that actually binds: thread-level FP64 instructions of the step kernel against the FP64 pipe
-        # (64 lanes per SM and clock).  138 k per env-step = ncu's 566 M FP64 thread-instructions of one 4096-env launch
-        # (profiles/ncu_step_kernel_r01_final.csv, dog / slopes_mixed); an explanatory figure beside the contract's HBM roofline.
+        # (64 lanes per SM and clock).  FP64_INST_PER_LAUNCH_ENV = ncu's FP64 thread-instructions of one 4096-env launch / 4096
+        # (profiles/ncu_step_kernel_r0x.csv, dog / slopes_mixed only -- other scenes carry no figure); an explanatory number beside
+        # the contract's HBM roofline.
         sm_mhz = float((clocks or {}).get("sm_mhz") or 1965.0)
         fp64_peak = 148 * 64 * sm_mhz * 1e6
-        fp64_ach = 138.0e3 * n / launch_s
+        fp64_ach = FP64_INST_PER_LAUNCH_ENV * n / launch_s
         line["roofline"]["fp64_pipe"] = {"achieved_ginst_s": fp64_ach / 1e9, "peak_ginst_s": fp64_peak / 1e9, "frac": fp64_ach / fp64_peak,
-                                         "thread_inst_per_env_step": 138.0e3, "peak": "148 SMs x 64 FP64 lanes x measured SM clock"}
-    except Exception:
-        pass
+                                         "thread_inst_per_launch_env": FP64_INST_PER_LAUNCH_ENV, "peak": "148 SMs x 64 FP64 lanes x measured SM clock"}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

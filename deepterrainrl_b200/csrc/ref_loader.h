@@ -202,8 +202,13 @@ private:
     struct Entry { uint64_t name_off = 0, ohdr = 0, btree = 0, heap = 0; bool group = false; };
     std::vector<char> b_;
     std::map<std::string, std::vector<double>> out_;
+    // every address and length below comes from the file: nothing is dereferenced before it has been checked against the image
+    void need(uint64_t p, uint64_t n) const {
+        if (p > b_.size() || n > b_.size() - p) throw std::runtime_error("hdf5: address past the end of the file");
+    }
+    bool tag(uint64_t p, const char* t4) const { need(p, 4); return std::memcmp(b_.data() + p, t4, 4) == 0; }
     template <typename T> T rd(uint64_t p) const {
-        if (p + sizeof(T) > b_.size()) throw std::runtime_error("hdf5: read past end");
+        if (p > b_.size() || sizeof(T) > b_.size() - p) throw std::runtime_error("hdf5: read past end");
         T v;
         std::memcpy(&v, b_.data() + p, sizeof(T));
         return v;
@@ -232,33 +237,40 @@ private:
         }
         return msgs;
     }
-    void leaves(uint64_t addr, std::vector<uint64_t>& out) const {
-        if (std::memcmp(b_.data() + addr, "TREE", 4) != 0) throw std::runtime_error("hdf5: bad B-tree node");
+    void leaves(uint64_t addr, std::vector<uint64_t>& out, int depth = 0) const {
+        if (depth > 16 || out.size() > 65536) throw std::runtime_error("hdf5: B-tree too deep / too wide (damaged file?)");
+        if (!tag(addr, "TREE")) throw std::runtime_error("hdf5: bad B-tree node");
         uint8_t level = rd<uint8_t>(addr + 5);
         uint16_t n = rd<uint16_t>(addr + 6);
         uint64_t p = addr + 8 + 16 + 8;
         for (uint16_t i = 0; i < n; ++i) {
             uint64_t child = rd<uint64_t>(p);
             p += 16;
-            if (level > 0) leaves(child, out); else out.push_back(child);
+            if (level > 0) leaves(child, out, depth + 1); else out.push_back(child);
         }
     }
-    void walk(Entry e, const std::string& prefix) {
+    void walk(Entry e, const std::string& prefix, int depth = 0) {
+        if (depth > 8) throw std::runtime_error("hdf5: group nesting too deep (damaged file?)");
         if (!e.group)
             for (auto& m : messages(e.ohdr))
                 if (m.type == 0x11) { e.group = true; e.btree = rd<uint64_t>(m.body); e.heap = rd<uint64_t>(m.body + 8); }
         if (e.group) {
-            if (std::memcmp(b_.data() + e.heap, "HEAP", 4) != 0) throw std::runtime_error("hdf5: bad local heap");
+            if (!tag(e.heap, "HEAP")) throw std::runtime_error("hdf5: bad local heap");
             uint64_t heap_data = rd<uint64_t>(e.heap + 24);
             std::vector<uint64_t> nodes;
             leaves(e.btree, nodes);
             for (uint64_t snod : nodes) {
-                if (std::memcmp(b_.data() + snod, "SNOD", 4) != 0) throw std::runtime_error("hdf5: bad symbol node");
+                if (!tag(snod, "SNOD")) throw std::runtime_error("hdf5: bad symbol node");
                 uint16_t n = rd<uint16_t>(snod + 6);
                 for (uint16_t i = 0; i < n; ++i) {
                     Entry c = ste(snod + 8 + 40ull * i);
-                    std::string name(b_.data() + heap_data + c.name_off);
-                    walk(c, prefix + "/" + name);
+                    need(heap_data, c.name_off);
+                    const uint64_t np = heap_data + c.name_off;
+                    need(np, 1);
+                    const void* nul = std::memchr(b_.data() + np, 0, b_.size() - np);
+                    if (!nul || (const char*)nul - (b_.data() + np) > 255) throw std::runtime_error("hdf5: unterminated link name");
+                    std::string name(b_.data() + np);
+                    walk(c, prefix + "/" + name, depth + 1);
                 }
             }
             return;
@@ -269,7 +281,11 @@ private:
                 uint8_t ver = rd<uint8_t>(m.body), rank = rd<uint8_t>(m.body + 1);
                 uint64_t p = m.body + (ver == 1 ? 8 : 4);
                 count = 1;
-                for (uint8_t r = 0; r < rank; ++r) count *= rd<uint64_t>(p + 8ull * r);
+                for (uint8_t r = 0; r < rank; ++r) {
+                    const uint64_t dim = rd<uint64_t>(p + 8ull * r);
+                    if (dim != 0 && count > b_.size() / dim) throw std::runtime_error("hdf5: dataspace larger than the file at " + prefix);
+                    count *= dim;
+                }
             } else if (m.type == 0x3) {
                 if ((rd<uint8_t>(m.body) & 0x0f) != 1 || rd<uint32_t>(m.body + 4) != 8) throw std::runtime_error("hdf5: only f64 datasets are supported");
             } else if (m.type == 0x8) {
@@ -277,7 +293,8 @@ private:
                 addr = rd<uint64_t>(m.body + 2); size = rd<uint64_t>(m.body + 10);
             }
         }
-        if (size != count * 8) throw std::runtime_error("hdf5: dataset size mismatch at " + prefix);
+        if (count > b_.size() / 8 || size != count * 8) throw std::runtime_error("hdf5: dataset size mismatch at " + prefix);
+        need(addr, size);
         std::vector<double> v(count);
         std::memcpy(v.data(), b_.data() + addr, count * 8);
         out_[prefix] = std::move(v);

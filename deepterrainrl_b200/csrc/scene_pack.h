@@ -20,15 +20,25 @@ public:
         if (!in || std::string(magic, 8) != "TRLPACK1") { if (err) *err = "not a TRLPACK1 file: " + path; return false; }
         uint32_t count = 0;
         in.read(reinterpret_cast<char*>(&count), 4);
+        // every length in the file is checked against what is left of it before anything is allocated
+        in.seekg(0, std::ios::end);
+        const uint64_t file_size = (uint64_t)in.tellg();
+        in.seekg(12, std::ios::beg);
+        auto remaining = [&]() { return file_size - (uint64_t)in.tellg(); };
         for (uint32_t r = 0; r < count && in; ++r) {
             uint32_t len = 0, dtype = 0;
             uint64_t n = 0;
             in.read(reinterpret_cast<char*>(&len), 4);
+            if (!in || len > 256 || len > remaining()) { if (err) *err = "damaged scene pack (record name): " + path; return false; }
             std::string name(len, ' ');
             in.read(&name[0], len);
-            order_.push_back(name);
             in.read(reinterpret_cast<char*>(&dtype), 4);
             in.read(reinterpret_cast<char*>(&n), 8);
+            if (!in || dtype > 1 || n > remaining() / (dtype == 1 ? 4 : 8)) {
+                if (err) *err = "damaged scene pack (record '" + name + "' is longer than the file): " + path;
+                return false;
+            }
+            order_.push_back(name);
             if (dtype == 1) {
                 std::vector<int32_t>& v = ints_[name];
                 v.resize(n);

@@ -11,9 +11,12 @@
 #include "trl_types.h"
 
 struct trl_trainer;
+struct trl_comm;
 
 struct trl_handle {
     trl_trainer* trainer = nullptr;      // attached MACE trainer (trl_train.cu), owns the policy weights when present
+    trl_comm* comm = nullptr;            // multi-GPU exchange (trl_comm.cu), present after trl_comm_init*
+    int64_t tuples_dropped = 0;          // tuples the full tuple block refused, as observed by the host-side readers
     int device = 0, n = 0, mode = 0;
     trl::ScenePack scene;
     trl::ModelConst mc;
@@ -28,7 +31,7 @@ struct trl_handle {
     cudaStream_t aux_stream = nullptr;           // high-priority side stream: decisions + catch-up launches (overlapped schedule)
     std::vector<cudaEvent_t> fork_events;        // dependencies between the two streams inside one update
     bool overlap = true;                         // TRL_SERIAL_SCHEDULE=1 turns the overlapped schedule off
-    int decide_grid = 288;   // multiple of the 8-CTA cluster size
+    int decide_grid = 288;   // CTAs of the decision launch: a multiple of its cluster size (create_common sizes it from the SM count)
     int num_update_steps = 20;
     int64_t launches = 0;
     std::map<long long, cudaGraphExec_t> graphs;   // keyed by the bit pattern of dt

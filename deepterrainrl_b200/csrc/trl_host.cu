@@ -40,6 +40,7 @@ using namespace trl;
 // both builds of the step kernels keep their own copy of the model constants
 struct trl_handle;
 static const trl_handle* g_model_owner = nullptr;    // whose ModelConst currently sits in the __constant__ copies
+static int g_device = -1;                             // the one device this process drives (set by the first handle)
 static cudaError_t upload_model_all(const ModelConst& mc) {
     cudaError_t e = trl::upload_model(mc);
     return e != cudaSuccess ? e : trl_cg::upload_model(mc);
@@ -62,6 +63,8 @@ static const char* kNetLayers[13] = {"terr_conv0", "terr_conv1", "terr_conv2", "
 // The kernels read the scene from __constant__ memory, of which there is one copy per process: a handle that is not the
 // current owner re-uploads its model (after draining the owner's work) before it launches anything.
 static int ensure_model(trl_handle* h) {
+    // one process drives one GPU: __constant__ scene memory and the streams belong to the device of the handle
+    // that was created first; a handle on another device is refused at creation (create_common)
     if (g_model_owner == h) return 0;
     if (cudaDeviceSynchronize() != cudaSuccess) return 1;
     if (upload_model_all(h->mc) != cudaSuccess) return 1;
@@ -88,6 +91,7 @@ static int fill_model(trl_handle* h, uint64_t rng_seed) {
     std::memset(&m, 0, sizeof(m));
     const auto& mi = s.i32("meta_i32");
     const auto& mf = s.f64("meta_f64");
+    if (mi.size() < 15 || mf.size() < 7) return fail("scene pack: meta records missing or too short");
     int char_type = mi[0], ctrl = mi[1];
     m.nj = mi[8]; m.ndof = mi[9];
     const bool raptor = char_type == 2;
@@ -131,6 +135,23 @@ static int fill_model(trl_handle* h, uint64_t rng_seed) {
     const auto& J = s.f64("joints");
     const auto& Bd = s.f64("bodies");
     const auto& P = s.f64("pd");
+    {
+        // every table the loops below index, against the sizes they assume
+        const size_t nj = (size_t)m.nj, np = (size_t)m.n_params;
+        const int n_ctrl = mi[10], n_act = mi[11];
+        if (n_ctrl < 1 || n_ctrl > kMaxCtrlSets || n_act < 0 || n_act > kMaxActions) return fail("too many controller sets / actions");
+        if (J.size() < 7 * nj || Bd.size() < 9 * nj || P.size() < 6 * nj) return fail("scene pack: joints / bodies / pd tables too short");
+        if (s.f64("ctrl_params").size() < (size_t)n_ctrl * np || s.f64("actions").size() < (size_t)4 * n_act)
+            return fail("scene pack: controller parameter / action tables too short");
+        if (s.f64("pose0").size() < (size_t)m.ndof || s.f64("vel0").size() < (size_t)m.ndof) return fail("scene pack: initial state too short");
+        if (s.f64("terrain_default_params").size() < (size_t)kTerrainParams || mi[6] < 0 ||
+            s.f64("terrain_params").size() < (size_t)mi[6] * kTerrainParams)
+            return fail("scene pack: terrain parameter sets too short");
+        for (size_t j = 0; j < nj; ++j) {
+            const int par = (int)J[7 * j + 1];
+            if (par >= (int)j || par < -1) return fail("scene pack: a joint's parent must precede it");
+        }
+    }
     int off = 0;
     m.total_mass = 0;
     for (int j = 0; j < m.nj; ++j) {
@@ -274,9 +295,11 @@ static int fill_model(trl_handle* h, uint64_t rng_seed) {
     h->ex = ExpSettings{h->mode == TRL_MODE_EXPLORE ? 1 : 0, mf[4], mf[5], mf[6], m.exp_noise};   // uploaded by create_common
     if (m.has_net) {
         const auto& nd = s.i32("net_dims");
+        if (nd.size() < 5) return fail("scene pack: net_dims missing");
         m.n_in = nd[0]; m.n_char = nd[1]; m.n_out = nd[2]; m.n_frags = nd[3]; m.frag = nd[4];
         if (m.n_out > kMaxNetOut || m.frag > 32 || m.n_frags > 8 || m.n_char > 96) return fail("unsupported net dimensions");
         const auto& os = s.f64("net_out_scale");
+        if (m.n_frags < 1 || m.frag < 1 || os.size() < (size_t)(m.n_frags + m.frag)) return fail("scene pack: net_out_scale too short");
         for (int k = 0; k < m.frag; ++k) m.out_scale_actor0[k] = os[m.n_frags + k];
     }
     return 0;
@@ -306,6 +329,28 @@ static int upload_net(trl_handle* h, const double* const* blobs, const int64_t* 
     W.tip0_w = b[6]; W.tip0_b = b[7]; W.ip0_w = b[8]; W.ip0_b = b[9];
     for (int k = 0; k < 4; ++k) { W.h0_w[k] = b[10 + 4 * k]; W.h0_b[k] = b[11 + 4 * k]; W.h1_w[k] = b[12 + 4 * k]; W.h1_b[k] = b[13 + 4 * k]; }
     W.in_off = b[26]; W.in_scale = b[27]; W.out_off = b[28]; W.out_scale = b[29];
+    return 0;
+}
+
+// the decision kernel indexes the 26 blobs with the MACE topology's strides (data/policies/dog/nets/dog_mace3_deploy.prototxt):
+// anything else must be refused before it reaches the device
+static int check_net_counts(const ModelConst& m, const int64_t* counts, const int64_t* vcounts) {
+    const int64_t want[10] = {16 * 8, 16, 32 * 16 * 4, 32, 32 * 32 * 4, 32, 64 * 32 * 187, 64, 256 * (int64_t)(64 + m.n_char), 256};
+    for (int b = 0; b < 26; ++b) {
+        int64_t w;
+        if (b < 10) w = want[b];
+        else {
+            const int hd = (b - 10) / 4, r = (b - 10) % 4, nout = hd == 0 ? m.n_frags : m.frag;
+            w = r == 0 ? 128 * 256 : (r == 1 ? 128 : (r == 2 ? (int64_t)nout * 128 : nout));
+        }
+        if (counts[b] != w) return fail("policy net: blob " + std::to_string(b) + " has " + std::to_string(counts[b]) + " values, the MACE topology needs " + std::to_string(w));
+    }
+    if (vcounts) {
+        const int64_t vw[4] = {m.n_in, m.n_in, m.n_out, m.n_out};
+        for (int k = 0; k < 4; ++k)
+            if (vcounts[k] != vw[k]) return fail("policy net: offset / scale vector " + std::to_string(k) + " has the wrong length");
+    }
+    if (m.n_in != 200 + m.n_char || m.n_out != m.n_frags * (1 + m.frag)) return fail("policy net: input / output sizes do not match the MACE topology");
     return 0;
 }
 
@@ -381,9 +426,15 @@ static trl_handle* create_common(trl_handle* h, int num_envs, int device, int mo
 trl_handle* trl_create_from_pack(const char* pack_path, int num_envs, int device, int mode, const uint64_t* terrain_seeds,
                                  uint64_t rng_seed) {
     auto* h = new trl_handle();
-    std::string err;
-    if (!h->scene.load(pack_path, &err)) { g_err = err; delete h; return nullptr; }
-    return create_common(h, num_envs, device, mode, terrain_seeds, rng_seed);
+    try {
+        std::string err;
+        if (!h->scene.load(pack_path, &err)) { g_err = err; delete h; return nullptr; }
+        return create_common(h, num_envs, device, mode, terrain_seeds, rng_seed);
+    } catch (const std::exception& e) {       // bad_alloc / out_of_range from a damaged pack must not cross the C ABI
+        g_err = std::string("trl_create_from_pack: ") + e.what();
+        delete h;
+        return nullptr;
+    }
 }
 
 trl_handle* trl_create(int argc, const char* const* argv, const char* data_root, int num_envs, int device, int mode,
@@ -422,7 +473,10 @@ static trl_handle* create_common(trl_handle* h, int num_envs, int device, int mo
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return bail("terrainrl_b200 needs a CUDA device: no GPU visible (the product path has no CPU fallback)");
+    if (g_device >= 0 && g_device != device)
+        return bail("terrainrl_b200 drives one GPU per process (device " + std::to_string(g_device) + " is in use): start one process per GPU");
     if (cudaSetDevice(device) != cudaSuccess) return bail("cudaSetDevice failed");
+    g_device = device;
     if (fill_model(h, rng_seed)) return bail("");
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return bail("cudaStreamCreate failed");
     {
@@ -475,6 +529,7 @@ static trl_handle* create_common(trl_handle* h, int num_envs, int device, int mo
         const double* vecs[4];
         int64_t vcounts[4];
         for (int k = 0; k < 4; ++k) { const auto& v = h->scene.f64(vn[k]); vecs[k] = v.data(); vcounts[k] = (int64_t)v.size(); }
+        if (check_net_counts(h->mc, counts, vcounts)) return bail("");
         if (upload_net(h, blobs, counts, vecs, vcounts)) return bail("");
     } else {
         std::memset(&h->W, 0, sizeof(h->W));
@@ -487,6 +542,7 @@ static trl_handle* create_common(trl_handle* h, int num_envs, int device, int mo
 
 int trl_destroy(trl_handle* h) {
     if (!h) return 0;
+    if (h->comm) trl_comm_destroy(h);
     if (h->trainer) trl_trainer_orphan(h->trainer);   // the trainer object outlives its scenario as an inert shell
     if (g_model_owner == h) g_model_owner = nullptr;
     if (h->stream) cudaStreamSynchronize(h->stream);
@@ -510,14 +566,18 @@ int trl_seed_terrain(trl_handle* h, const uint64_t* seeds, int n) {
     if (seeds) {
         if (n != h->n) return fail("trl_seed_terrain: need one seed per env");
         CK(cudaMalloc((void**)&d_seeds, (size_t)n * 8));
-        CK(cudaMemcpyAsync(d_seeds, seeds, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
+        cudaError_t e = cudaMemcpyAsync(d_seeds, seeds, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream);
+        if (e != cudaSuccess) { cudaFree(d_seeds); return fail(std::string("trl_seed_terrain: ") + cudaGetErrorString(e)); }
     }
-    CK(cudaMemsetAsync(h->B.pending_count, 0, 8, h->stream));
-    launch_reset(h->B, d_seeds, nullptr, h->n, 1, h->stream);
-    h->launches += 1;
-    CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(h->stream));
+    cudaError_t e = cudaMemsetAsync(h->B.pending_count, 0, 8, h->stream);
+    if (e == cudaSuccess) {
+        launch_reset(h->B, d_seeds, nullptr, h->n, 1, h->stream);
+        h->launches += 1;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
     if (d_seeds) cudaFree(d_seeds);
+    if (e != cudaSuccess) return fail(std::string("trl_seed_terrain: ") + cudaGetErrorString(e));
     return 0;
 }
 
@@ -527,15 +587,21 @@ int trl_reset(trl_handle* h, const int32_t* env_ids, int n) {
     int* d_ids = nullptr;
     int count = h->n;
     if (env_ids) {
+        if (n < 0 || n > h->n) return fail("trl_reset: env count out of range");
+        for (int k = 0; k < n; ++k)
+            if (env_ids[k] < 0 || env_ids[k] >= h->n) return fail("trl_reset: env id out of range");
+        if (n == 0) return 0;
         count = n;
         CK(cudaMalloc((void**)&d_ids, (size_t)n * 4));
-        CK(cudaMemcpyAsync(d_ids, env_ids, (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
+        cudaError_t e = cudaMemcpyAsync(d_ids, env_ids, (size_t)n * 4, cudaMemcpyHostToDevice, h->stream);
+        if (e != cudaSuccess) { cudaFree(d_ids); return fail(std::string("trl_reset: ") + cudaGetErrorString(e)); }
     }
     launch_reset(h->B, nullptr, d_ids, count, 0, h->stream);
     h->launches += 1;
-    CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(h->stream));
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
     if (d_ids) cudaFree(d_ids);
+    if (e != cudaSuccess) return fail(std::string("trl_reset: ") + cudaGetErrorString(e));
     return 0;
 }
 
@@ -666,6 +732,9 @@ int trl_load_model(trl_handle* h, const char* h5_path, const char* scale_path) {
             const JValue* v = sc.get(keys[k]);
             if (!v || v->type != JValue::Arr) return fail(std::string("trl_load_model: scale file lacks ") + keys[k]);
             for (auto& e : v->arr) vec[k].push_back(e.num);
+            const size_t want = (size_t)(k < 2 ? h->mc.n_in : h->mc.n_out);
+            if (vec[k].size() != want)
+                return fail(std::string("trl_load_model: ") + keys[k] + " has " + std::to_string(vec[k].size()) + " entries, the net needs " + std::to_string(want));
         }
         return trl_set_weights(h, blobs, counts, 26, vec[0].data(), vec[1].data(), vec[2].data(), vec[3].data());
     } catch (const std::exception& e) {
@@ -729,8 +798,15 @@ int trl_set_terrain_lerp(trl_handle* h, double lerp) {
     lerp = std::min(std::max(lerp, 0.0), n_sets - 1.0);
     const int i0 = (int)lerp, i1 = std::min(i0 + 1, n_sets - 1);
     lerp -= i0;
+    double blended[kTerrainParams];
+    bool same = true;
+    for (int i = 0; i < kTerrainParams; ++i) {
+        blended[i] = (1 - lerp) * tp[i0 * kTerrainParams + i] + lerp * tp[i1 * kTerrainParams + i];
+        same = same && blended[i] == h->mc.terrain_params[i];
+    }
+    if (same) return 0;      // cScenarioTrain calls this after every trainer step; an unchanged blend must not drain the device
     CK(cudaStreamSynchronize(h->stream));
-    for (int i = 0; i < kTerrainParams; ++i) h->mc.terrain_params[i] = (1 - lerp) * tp[i0 * kTerrainParams + i] + lerp * tp[i1 * kTerrainParams + i];
+    for (int i = 0; i < kTerrainParams; ++i) h->mc.terrain_params[i] = blended[i];
     g_model_owner = nullptr;
     if (ensure_model(h)) return fail("model upload failed");
     return 0;
@@ -767,6 +843,8 @@ int trl_set_weights(trl_handle* h, const double* const* blobs, const int64_t* co
     if (nblobs != 26) return fail("trl_set_weights: expected 26 blobs");
     if (!h->mc.has_net) return fail("trl_set_weights: scene has no policy net");
     if (h->trainer) return fail("trl_set_weights: a trainer owns the policy weights (use trl_trainer_set_theta)");
+    if (!blobs || !counts || !in_off || !in_scale || !out_off || !out_scale) return fail("trl_set_weights: null argument");
+    if (check_net_counts(h->mc, counts, nullptr)) return 1;
     CK(cudaStreamSynchronize(h->stream));
     const double* vecs[4] = {in_off, in_scale, out_off, out_scale};
     int64_t vcounts[4] = {h->mc.n_in, h->mc.n_in, h->mc.n_out, h->mc.n_out};
@@ -789,10 +867,19 @@ int trl_sizes(trl_handle* h, int* num_envs, int* state, int* action, int* num_fr
     return 0;
 }
 
-static int fetch_tuples(trl_handle* h, int* n_out) {
+// The step kernel takes tuple slots from an atomic cursor and refuses rows past tuple_cap (trl_step.cu: exp_new_cycle_update), so the
+// cursor itself says how many were refused.  The readers deliver what fits, count the rest in h->tuples_dropped when the block is
+// reset, and answer TRL_E_TUPLE_OVERFLOW so that the loss cannot go unnoticed.
+static int overflow_error(trl_handle* h, int overflow) {
+    g_err = "tuple block overflow: " + std::to_string(overflow) + " tuples were refused (capacity " + std::to_string(h->B.tuple_cap) +
+            "); hand the tuples over more often";
+    return TRL_E_TUPLE_OVERFLOW;
+}
+static int fetch_tuples(trl_handle* h, int* n_out, int* overflow) {
     int n = 0;
     CK(cudaMemcpyAsync(&n, h->B.tuple_count, 4, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    *overflow = n > h->B.tuple_cap ? n - h->B.tuple_cap : 0;
     if (n > h->B.tuple_cap) n = h->B.tuple_cap;
     const size_t W = 1 + h->B.S + h->B.A + h->B.S;
     h->h_tuples.resize((size_t)std::max(n, 1) * W);
@@ -814,28 +901,34 @@ int trl_num_tuples(trl_handle* h, int* out) {
     CK(cudaMemcpyAsync(&n, h->B.tuple_count, 4, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     *out = std::min(n, h->B.tuple_cap);
-    return 0;
+    return n > h->B.tuple_cap ? overflow_error(h, n - h->B.tuple_cap) : 0;
 }
 
 int trl_get_tuples_f64(trl_handle* h, const double** rows, const uint32_t** flags, const int32_t** env_id, int* n) {
     if (!h) return fail("trl_get_tuples_f64: null handle");
-    if (fetch_tuples(h, n)) return 1;
+    int overflow = 0;
+    if (fetch_tuples(h, n, &overflow)) return 1;
     *rows = h->h_tuples.data(); *flags = h->h_tuple_flags.data(); *env_id = h->h_tuple_env.data();
-    return 0;
+    return overflow ? overflow_error(h, overflow) : 0;
 }
 
 int trl_get_tuples(trl_handle* h, const float** rows, const uint32_t** flags, const int32_t** env_id, int* n) {
     if (!h) return fail("trl_get_tuples: null handle");
-    if (fetch_tuples(h, n)) return 1;
+    int overflow = 0;
+    if (fetch_tuples(h, n, &overflow)) return 1;
     const size_t W = 1 + h->B.S + h->B.A + h->B.S;
     h->h_tuples_f32.resize((size_t)std::max(*n, 1) * W);
     for (size_t k = 0; k < (size_t)*n * W; ++k) h->h_tuples_f32[k] = (float)h->h_tuples[k];
     *rows = h->h_tuples_f32.data(); *flags = h->h_tuple_flags.data(); *env_id = h->h_tuple_env.data();
-    return 0;
+    return overflow ? overflow_error(h, overflow) : 0;
 }
 
 int trl_reset_tuples(trl_handle* h) {
     if (!h) return fail("trl_reset_tuples: null handle");
+    int n = 0;
+    CK(cudaMemcpyAsync(&n, h->B.tuple_count, 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (n > h->B.tuple_cap) h->tuples_dropped += n - h->B.tuple_cap;
     CK(cudaMemsetAsync(h->B.tuple_count, 0, 4, h->stream));
     return 0;
 }
@@ -967,18 +1060,22 @@ int trl_get_ctrl(trl_handle* h, int env, double* out, int cap, int* n_out) {
 
 int trl_get_poli_state(trl_handle* h, int env, double* out) {
     if (!h) return fail("trl_get_poli_state: null handle");
+    if (env < 0 || env >= h->n) return fail("env out of range");
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaMemcpy(out, h->B.poli_state + (size_t)env * h->B.S, (size_t)h->B.S * 8, cudaMemcpyDeviceToHost));
     return 0;
 }
 int trl_get_net_out(trl_handle* h, int env, double* out) {
     if (!h) return fail("trl_get_net_out: null handle");
+    if (env < 0 || env >= h->n) return fail("env out of range");
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaMemcpy(out, h->B.net_out + (size_t)env * kMaxNetOut, (size_t)h->mc.n_out * 8, cudaMemcpyDeviceToHost));
     return 0;
 }
 int trl_get_terrain(trl_handle* h, int env, int seg, float* data, int cap, int* n, double* min_x, int* flip) {
     if (!h) return fail("trl_get_terrain: null handle");
+    if (env < 0 || env >= h->n) return fail("env out of range");
+    if (seg < 0 || seg > 1) return fail("terrain segment out of range (0 or 1)");
     CK(cudaStreamSynchronize(h->stream));
     int sn = 0, fl = 0;
     double mx = 0;
@@ -991,7 +1088,7 @@ int trl_get_terrain(trl_handle* h, int env, int seg, float* data, int cap, int* 
     return 0;
 }
 
-int64_t trl_kernel_launches(trl_handle* h) { return h->launches; }
+int64_t trl_kernel_launches(trl_handle* h) { return h ? h->launches : -1; }
 
 // Micro-benchmark of the decision kernel: marks the first `n_pending` envs as pending (their policy state is whatever the
 // last real decision left) and times `iters` launches.  Perturbs those envs' actions: measurement use only.

@@ -26,6 +26,7 @@
 
 #include "../../include/terrainrl_b200.h"
 #include "trl_handle.h"
+#include "trl_comm.h"
 
 namespace trl_train {
 using namespace trl;
@@ -116,7 +117,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 // cNeuralNetTrainer::CheckTuple (learning/NeuralNetTrainer.cpp:541-576): one block per incoming tuple
 __global__ void k_add_check(Dev d, const double* rows, const int* count_ptr, int count_val) {
     pdl_sync();
-    const int count = count_ptr ? *count_ptr : count_val;
+    const int count = count_ptr ? min(*count_ptr, (int)gridDim.x) : count_val;     // the scenario's cursor may run past its capacity
     const int i = blockIdx.x;
     if (i >= count) return;
     const double* r = rows + (size_t)i * d.Wd;
@@ -130,7 +131,7 @@ __global__ void k_add_check(Dev d, const double* rows, const int* count_ptr, int
 // replay memory -- and with it the whole training run -- reproducible.  One block per tuple: rank = #tuples with a smaller key.
 __global__ void k_add_order(Dev d, const int* env_ids, const int* count_ptr) {
     pdl_sync();
-    const int count = *count_ptr, i = blockIdx.x;
+    const int count = min(*count_ptr, (int)gridDim.x), i = blockIdx.x;
     if (i >= count) return;
     const int key = env_ids[i];
     int r = 0;
@@ -156,32 +157,36 @@ __device__ void list_remove(int* list, int* pos, int& count, int t) {
     pos[t] = -1;
     --count;
 }
+// one incoming tuple: replay slot (cNeuralNetTrainer::AddTuple) + cMACETrainer::UpdateBuffers; returns the slot
+__device__ int assign_slot(const Dev& d, Counters& c, uint32_t flags) {
+    const int t = c.head;
+    c.head = (c.head + 1) % d.cap;
+    c.num = min(d.cap, c.num + 1);
+    ++c.total;
+    const bool ea = (flags & 4u) != 0;          // eFlagExpActor
+    if (ea) {
+        if (d.pos_actor[t] < 0) { d.pos_actor[t] = c.actor_count; d.actor_list[c.actor_count++] = t; }
+        list_remove(d.critic_list, d.pos_critic, c.critic_count, t);
+    } else {
+        if (d.pos_critic[t] < 0) { d.pos_critic[t] = c.critic_count; d.critic_list[c.critic_count++] = t; }
+        list_remove(d.actor_list, d.pos_actor, c.actor_count, t);
+    }
+    for (int k = 0; k < c.actor_batch_count;) {        // the overwritten slot leaves the pending actor batch
+        if (d.actor_batch[k] == t) d.actor_batch[k] = d.actor_batch[--c.actor_batch_count];
+        else ++k;
+    }
+    return t;
+}
 // cNeuralNetTrainer::AddTuple slot assignment + cMACETrainer::UpdateBuffers, in arrival order (one thread: O(1) per tuple)
-__global__ void k_add_assign(Dev d, const uint32_t* src_flags, const int* count_ptr, int count_val, int* reset_count, int use_order) {
+__global__ void k_add_assign(Dev d, const uint32_t* src_flags, const int* count_ptr, int count_val, int max_count, int* reset_count, int use_order) {
     pdl_sync();
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    const int count = count_ptr ? *count_ptr : count_val;
+    const int count = count_ptr ? min(*count_ptr, max_count) : count_val;
     Counters& c = *d.c;
     for (int r = 0; r < count; ++r) {
         const int i = use_order ? d.order[r] : r;
         if (!d.valid[i]) { d.slot[i] = -1; continue; }
-        const int t = c.head;
-        d.slot[i] = t;
-        c.head = (c.head + 1) % d.cap;
-        c.num = min(d.cap, c.num + 1);
-        ++c.total;
-        const bool ea = (src_flags[i] & 4u) != 0;          // eFlagExpActor
-        if (ea) {
-            if (d.pos_actor[t] < 0) { d.pos_actor[t] = c.actor_count; d.actor_list[c.actor_count++] = t; }
-            list_remove(d.critic_list, d.pos_critic, c.critic_count, t);
-        } else {
-            if (d.pos_critic[t] < 0) { d.pos_critic[t] = c.critic_count; d.critic_list[c.critic_count++] = t; }
-            list_remove(d.actor_list, d.pos_actor, c.actor_count, t);
-        }
-        for (int k = 0; k < c.actor_batch_count;) {        // the overwritten slot leaves the pending actor batch
-            if (d.actor_batch[k] == t) d.actor_batch[k] = d.actor_batch[--c.actor_batch_count];
-            else ++k;
-        }
+        d.slot[i] = assign_slot(d, c, src_flags[i]);
     }
     c.add_count = count;                                   // k_add_copy must not re-read a counter that is reset here
     if (reset_count) *reset_count = 0;                     // cScenarioExp::ResetTupleBuffer
@@ -197,6 +202,68 @@ __global__ void k_add_copy(Dev d, const double* rows, const uint32_t* src_flags)
     float* dst = d.mem + (size_t)t * d.Wd;
     for (int k = threadIdx.x; k < d.Wd; k += blockDim.x) dst[k] = (float)r[k];     // SetTuple stores floats
     if (threadIdx.x == 0) d.flags[t] = (int)src_flags[i];
+}
+
+// ---- tuples from the all-gathered blocks of every rank (trl_comm.cu: {i32 count, i32 queued, i32 rank, i32 R, u32 flags[R],
+// i32 env[R], f32 rows[R][Wd]} per rank).  Arrival order = rank order, env order inside a rank: the same on every rank, so
+// replicated trainers stay bit-identical.  The validity bit (cNeuralNetTrainer::CheckTuple on the f64 values) was set by the
+// pack kernel; rows are already the floats SetTuple would store.  Flat index i = rank * R + j for valid/slot/order.
+struct GBlocks { const unsigned char* recv; size_t block_bytes; int R, world; };
+__device__ __forceinline__ const int* gb_hdr(const GBlocks& g, int r) { return (const int*)(g.recv + (size_t)r * g.block_bytes); }
+__device__ __forceinline__ const uint32_t* gb_flags(const GBlocks& g, int r) { return (const uint32_t*)(g.recv + (size_t)r * g.block_bytes + 16); }
+__device__ __forceinline__ const int* gb_env(const GBlocks& g, int r) { return (const int*)(g.recv + (size_t)r * g.block_bytes + 16 + (size_t)4 * g.R); }
+__device__ __forceinline__ const float* gb_rows(const GBlocks& g, int r) { return (const float*)(g.recv + (size_t)r * g.block_bytes + 16 + (size_t)8 * g.R); }
+// grid (R, world): rank of tuple j inside its block by env id -> d.order[r * R + rank_in_block] = j
+__global__ void k_addg_order(Dev d, GBlocks g) {
+    pdl_sync();
+    const int r = blockIdx.y, i = blockIdx.x;
+    const int count = min(max(gb_hdr(g, r)[0], 0), g.R);
+    if (i >= count) return;
+    const int* env = gb_env(g, r);
+    const int key = env[i];
+    int rk = 0;
+    for (int j = threadIdx.x; j < count; j += blockDim.x) {
+        const int kj = env[j];
+        rk += (kj < key) || (kj == key && j < i);
+    }
+    __shared__ int red[32];
+    for (int o = 16; o > 0; o >>= 1) rk += __shfl_xor_sync(0xffffffffu, rk, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = rk;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tot = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += red[w];
+        d.order[r * g.R + tot] = i;
+    }
+}
+__global__ void k_addg_assign(Dev d, GBlocks g) {
+    pdl_sync();
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    Counters& c = *d.c;
+    int total = 0;
+    for (int r = 0; r < g.world; ++r) {
+        const int count = min(max(gb_hdr(g, r)[0], 0), g.R);
+        const uint32_t* flags = gb_flags(g, r);
+        for (int k = 0; k < count; ++k) {
+            const int j = d.order[r * g.R + k];
+            const uint32_t f = flags[j];
+            d.slot[r * g.R + j] = (f & 0x80000000u) ? -1 : assign_slot(d, c, f);
+        }
+        total += count;
+    }
+    c.add_count = total;
+}
+__global__ void k_addg_copy(Dev d, GBlocks g) {
+    pdl_sync();
+    const int r = blockIdx.y, j = blockIdx.x;
+    const int count = min(max(gb_hdr(g, r)[0], 0), g.R);
+    if (j >= count) return;
+    const int t = d.slot[r * g.R + j];
+    if (t < 0) return;
+    const float* src = gb_rows(g, r) + (size_t)j * d.Wd;
+    float* dst = d.mem + (size_t)t * d.Wd;
+    for (int k = threadIdx.x; k < d.Wd; k += blockDim.x) dst[k] = src[k];
+    if (threadIdx.x == 0) d.flags[t] = (int)(gb_flags(g, r)[j] & 0x7fffffffu);
 }
 
 // ================================================================================================ stage switch
@@ -614,6 +681,7 @@ struct trl_trainer {
     double* stage_rows = nullptr;      // device staging for tuples handed in from the host
     uint32_t* stage_flags = nullptr;
     int stage_cap = 0;
+    long long gather_cap = 0;          // entries of valid / slot / order (>= stage_cap; grown by trl_trainer_add_gathered)
     int64_t launches = 0;
 };
 
@@ -731,7 +799,7 @@ int enqueue_add(trl_trainer* t, const double* rows, const uint32_t* flags, const
     if (max_count <= 0) return 0;
     launch_pdl(k_add_check, dim3(max_count), dim3(128), 0, st, d, rows, count_ptr, count_val);
     if (env_ids) { launch_pdl(k_add_order, dim3(max_count), dim3(128), 0, st, d, env_ids, count_ptr); t->launches += 1; }
-    launch_pdl(k_add_assign, dim3(1), dim3(32), 0, st, d, flags, count_ptr, count_val, reset, env_ids ? 1 : 0);
+    launch_pdl(k_add_assign, dim3(1), dim3(32), 0, st, d, flags, count_ptr, count_val, max_count, reset, env_ids ? 1 : 0);
     launch_pdl(k_add_copy, dim3(max_count), dim3(128), 0, st, d, rows, flags);
     t->launches += 3;
     return 0;
@@ -799,6 +867,7 @@ trl_trainer* trl_trainer_create(trl_handle* h, const double* p) {
     A(talloc(t, &d.dh, (size_t)kB * H)); A(talloc(t, &d.dt, (size_t)kB * T)); A(talloc(t, &d.da2, (size_t)kB * C2 * W2));
     A(talloc(t, &d.da1, (size_t)kB * C1 * W1)); A(talloc(t, &d.da0, (size_t)kB * C0 * W0)); A(talloc(t, &d.mean, d.S)); A(talloc(t, &d.part, (size_t)kSplit * kB * T));
     t->stage_cap = add_cap;
+    t->gather_cap = add_cap;
     A(talloc(t, &t->stage_rows, (size_t)add_cap * d.Wd)); A(talloc(t, &t->stage_flags, add_cap));
     if (ok) {
         A(cudaFuncSetAttribute(k_conv_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, C1 * W1 * 8));
@@ -898,6 +967,50 @@ int trl_trainer_add_device(trl_trainer* t, const double* rows_dev, const uint32_
     return 0;
 }
 
+// AddTuples of the blocks every rank contributed to the last trl_gather_tuples (rank order, env order inside a rank), on the
+// scenario's stream behind the all-gather; identical input on every rank keeps replicated trainers bit-identical
+int trl_trainer_add_gathered(trl_trainer* t) {
+    TRL_TRAINER_LIVE(t);
+    trl_handle* h = t->h;
+    trl_comm_blocks v;
+    if (trl_comm_view(h, &v)) return 1;
+    if (v.width != t->d.Wd) return trl_fail("trl_trainer_add_gathered: tuple width mismatch");
+    if ((long long)v.world * v.block_rows > t->gather_cap) {
+        // valid / slot / order are indexed by rank * block_rows + j
+        const size_t need = (size_t)v.world * v.block_rows;
+        int *nv = nullptr, *ns = nullptr, *no = nullptr;
+        TCK(cudaStreamSynchronize(h->stream));
+        TCK(talloc(t, &nv, need)); TCK(talloc(t, &ns, need)); TCK(talloc(t, &no, need));
+        t->d.valid = nv; t->d.slot = ns; t->d.order = no;
+        t->gather_cap = (long long)need;
+    }
+    const Dev& d = t->d;
+    const GBlocks g{v.recv, v.block_bytes, v.block_rows, v.world};
+    launch_pdl(k_addg_order, dim3(v.block_rows, v.world), dim3(128), 0, h->stream, d, g);
+    launch_pdl(k_addg_assign, dim3(1), dim3(32), 0, h->stream, d, g);
+    launch_pdl(k_addg_copy, dim3(v.block_rows, v.world), dim3(128), 0, h->stream, d, g);
+    t->launches += 3;
+    TCK(cudaGetLastError());
+    return 0;
+}
+
+// cNeuralNetLearner::SyncNet across ranks (learning/NeuralNetLearner.cpp:85-89): the complete net state of `root`'s trainer --
+// weights, target net, momentum history, the eight offset / scale vectors -- reaches every rank's trainer, and with it the
+// policy each rank's decision kernel evaluates (pointer binding)
+int trl_trainer_broadcast(trl_trainer* t, int root) {
+    TRL_TRAINER_LIVE(t);
+    const Dev& d = t->d;
+    double* arrays[11] = {d.theta, d.target, d.history, d.in_off, d.in_scale, d.out_off, d.out_scale, d.t_in_off, d.t_in_scale, d.t_out_off, d.t_out_scale};
+    const size_t counts[11] = {(size_t)d.P, (size_t)d.P, (size_t)d.P, (size_t)d.S, (size_t)d.S, (size_t)d.n_out, (size_t)d.n_out,
+                               (size_t)d.S, (size_t)d.S, (size_t)d.n_out, (size_t)d.n_out};
+    return trl_comm_broadcast_list(t->h, arrays, counts, 11, root);
+}
+
+int trl_trainer_replica_spread(trl_trainer* t, double* max_abs_diff) {
+    TRL_TRAINER_LIVE(t);
+    return trl_comm_replica_spread(t->h, t->d.theta, (size_t)t->d.P, max_abs_diff);
+}
+
 // `iters` x cNeuralNetTrainer::Train() on the engine's stream (ordered after the update that produced the tuples and before
 // the next one, which then evaluates the updated weights)
 int trl_trainer_train(trl_trainer* t, int iters) {
@@ -972,11 +1085,11 @@ int trl_trainer_init_fresh(trl_trainer* t, uint64_t seed) {
 // read-back per update); anneal the exploration settings and the curriculum phase from the iteration count }.  sp[9] as in
 // trl_train_schedule.  Everything is enqueued on the scenario's stream; the call returns after the last update is queued
 // (iters_per_update > 0) -- synchronise with trl_sync / trl_trainer_counters.
-int trl_train_run(trl_trainer* t, const double* sp, int num_updates, int iters_per_update, int tuple_buffer_size, double time_step) {
-    TRL_TRAINER_LIVE(t);
+static int train_run_impl(trl_trainer* t, const double* sp, int num_updates, int iters_per_update, int tuple_buffer_size, double time_step,
+                          int block_rows, long long* iters_state, void* flush_buf = nullptr, size_t flush_bytes = 0) {
     trl_handle* h = t->h;
     long long last_total = -1, carry = 0;
-    long long iters_req = 0;
+    long long iters_req = iters_state ? *iters_state : 0;
     double last_phase = -1.0;
     for (int u = 0; u < num_updates; ++u) {
         double s[4];
@@ -990,8 +1103,13 @@ int trl_train_run(trl_trainer* t, const double* sp, int num_updates, int iters_p
         trl_train_schedule(sp, (int)std::min<long long>(it, 2000000000LL), s);
         if (trl_set_explore(h, 1, s[0], s[1], s[2])) return 1;
         if (s[3] != last_phase) { if (trl_set_terrain_lerp(h, s[3])) return 1; last_phase = s[3]; }
+        if (flush_buf) TCK(cudaMemsetAsync(flush_buf, u & 0xff, flush_bytes, h->stream));     // measurement: evict L2 between updates
         if (trl_update(h, time_step)) return 1;
-        if (trl_trainer_add_from_scene(t)) return 1;
+        if (h->comm) {
+            // N GPUs: the tuples of every rank reach every rank's trainer (one all-gather), scenarios/ScenarioTrain.cpp:388-395
+            if (trl_gather_tuples(h, block_rows)) return 1;
+            if (trl_trainer_add_gathered(t)) return 1;
+        } else if (trl_trainer_add_from_scene(t)) return 1;
         int k = iters_per_update;
         if (iters_per_update <= 0) {
             int64_t c[9];
@@ -1004,7 +1122,38 @@ int trl_train_run(trl_trainer* t, const double* sp, int num_updates, int iters_p
         if (k > 0 && trl_trainer_train(t, k)) return 1;
         iters_req += k;
     }
+    if (iters_state) *iters_state = iters_req;
     return 0;
+}
+int trl_train_run(trl_trainer* t, const double* sp, int num_updates, int iters_per_update, int tuple_buffer_size, double time_step) {
+    TRL_TRAINER_LIVE(t);
+    return train_run_impl(t, sp, num_updates, iters_per_update, tuple_buffer_size, time_step, 0, nullptr);
+}
+// the same loop, device-timed: CUDA events on the scenario's stream around `num_updates` iterations of {update, tuple exchange,
+// hand-over, trainer iterations} (bench.py's config-4 figure).  *iters_state carries the annealing position from call to call.
+int trl_train_run_timed(trl_trainer* t, const double* sp, int num_updates, int iters_per_update, int block_rows, double time_step,
+                        int flush_l2, int64_t* iters_state, double* ms) {
+    TRL_TRAINER_LIVE(t);
+    if (iters_per_update <= 0) return trl_fail("trl_train_run_timed: iters_per_update must be positive (no read-backs inside a timed region)");
+    trl_handle* h = t->h;
+    const size_t flush_bytes = (size_t)256 << 20;
+    if (flush_l2 && !h->flush_buf) { TCK(cudaMalloc(&h->flush_buf, flush_bytes)); h->allocs.push_back(h->flush_buf); }
+    cudaEvent_t e0, e1;
+    TCK(cudaEventCreate(&e0)); TCK(cudaEventCreate(&e1));
+    TCK(cudaStreamSynchronize(h->stream));
+    TCK(cudaEventRecord(e0, h->stream));
+    long long st = iters_state ? (long long)*iters_state : 0;
+    const int rc = train_run_impl(t, sp, num_updates, iters_per_update, 32, time_step, block_rows, &st, flush_l2 ? h->flush_buf : nullptr, flush_bytes);
+    if (iters_state) *iters_state = (int64_t)st;
+    if (rc == 0) {
+        TCK(cudaEventRecord(e1, h->stream));
+        TCK(cudaEventSynchronize(e1));
+        float f = 0;
+        TCK(cudaEventElapsedTime(&f, e0, e1));
+        if (ms) *ms = f;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return rc;
 }
 
 // c[9]: iter, actor_iter, stage, num, head, total, critic buffer, actor buffer, pending actor batch; l[2]: last losses

@@ -1,11 +1,15 @@
-"""Multi-GPU plumbing: environments shard across ranks (one process per GPU, torch.distributed), no collective in
-the rollout data path.  The only exchange is the hand-off of finished ExpTuples to the trainer side, done as one
-all-gather of fixed-shape tuple blocks per outer update -- this replaces the reference's in-process
-`learner->Train(tuples)` under the trainer mutex (scenarios/ScenarioTrain.cpp:388-395, learning/NeuralNetLearner.cpp:33-46).
+"""Multi-GPU plumbing: environments shard across ranks (one process per GPU), no collective in the rollout data path.
 
-Works on any backend: NCCL with the device-resident block from ScenarioExpMACE.DeviceTupleBlock() (zero-copy), or
-gloo with CPU tensors (what the CPU tests exercise at world_size 2).
+The exchange itself is native (csrc/trl_comm.cu, include/terrainrl_b200.h `trl_comm_*`, `trl_gather_tuples`,
+`trl_trainer_add_gathered`, `trl_trainer_broadcast`): a device pack kernel + ONE all-gather of a fixed-capacity tuple block per
+rank and outer update on a side stream, replacing the reference's in-process `learner->Train(exp->GetTuples())` under the
+trainer mutex (scenarios/ScenarioTrain.cpp:388-395, learning/NeuralNetLearner.cpp:33-46), and a broadcast for `SyncNet`
+(learning/NeuralNetLearner.cpp:85-89).  This module is only the ctypes mirror of those entry points plus the rendezvous glue a
+Python launcher needs (shipping the NCCL unique id through torch.distributed, or wrapping a torch.distributed group as the
+external-collectives backend for CPU tests over gloo).
 """
+import ctypes as C
+
 import numpy as np
 
 
@@ -14,89 +18,135 @@ def shard_seeds(rank, envs_per_rank, base=1):
     return np.arange(base + rank * envs_per_rank, base + (rank + 1) * envs_per_rank, dtype=np.uint64)
 
 
-def gather_tuple_blocks(rows, flags, env_ids, count, env_offset=0, pad_to=64, group=None):
-    """All-gather the first `count` tuple rows of every rank.
-
-    rows: [cap, W] float tensor (f64 on device or CPU), flags/env_ids: [cap] int32, count: [1] int32, all on the
-    backend's device.  Returns (rows_f32 [total, W], flags [total], env_ids [total] globalised with env_offset) on
-    every rank -- float32 rows are what cMACETrainer::AddTuples stores (learning/MACETrainer.cpp:515-539).
-    """
-    import torch
-    import torch.distributed as dist
-    world = dist.get_world_size(group)
-    counts = [torch.zeros_like(count) for _ in range(world)]
-    dist.all_gather(counts, count.clone(), group=group)
-    counts = [int(c.item()) for c in counts]
-    cap = rows.shape[0]
-    m = min(max(counts), cap)
-    if m == 0:
-        W = rows.shape[1]
-        return (torch.zeros((0, W), dtype=torch.float32, device=rows.device),
-                torch.zeros((0,), dtype=torch.int32, device=rows.device),
-                torch.zeros((0,), dtype=torch.int32, device=rows.device))
-    m = min(cap, ((m + pad_to - 1) // pad_to) * pad_to)
-    blk_rows = rows[:m].to(torch.float32).contiguous()
-    blk_flags = flags[:m].to(torch.int32).contiguous()
-    blk_env = (env_ids[:m].to(torch.int32) + int(env_offset)).contiguous()
-    out_rows = torch.empty((world,) + tuple(blk_rows.shape), dtype=blk_rows.dtype, device=rows.device)
-    out_flags = torch.empty((world, m), dtype=torch.int32, device=rows.device)
-    out_env = torch.empty((world, m), dtype=torch.int32, device=rows.device)
-    dist.all_gather_into_tensor(out_rows.view(-1), blk_rows.view(-1), group=group) if rows.is_cuda else \
-        dist.all_gather(list(out_rows.unbind(0)), blk_rows, group=group)
-    dist.all_gather_into_tensor(out_flags.view(-1), blk_flags, group=group) if rows.is_cuda else \
-        dist.all_gather(list(out_flags.unbind(0)), blk_flags, group=group)
-    dist.all_gather_into_tensor(out_env.view(-1), blk_env, group=group) if rows.is_cuda else \
-        dist.all_gather(list(out_env.unbind(0)), blk_env, group=group)
-    keep = [torch.arange(min(c, m), device=rows.device) + r * m for r, c in enumerate(counts)]
-    keep = torch.cat(keep)
-    return (out_rows.view(world * m, -1)[keep], out_flags.view(-1)[keep], out_env.view(-1)[keep])
+class _Collectives(C.Structure):
+    AG = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p)
+    BC = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p)
+    AR = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p)
+    _fields_ = [("ctx", C.c_void_p), ("all_gather", AG), ("broadcast", BC), ("all_reduce_sum_f64", AR)]
 
 
-def gather_tuple_blocks_fixed(rows, flags, env_ids, count, env_offset=0, block_rows=1024, group=None):
-    """Sync-free variant: ONE all-gather of a fixed-shape f32 block per rank, no host round-trip.
+class Comm:
+    """The communicator of one BatchedScenario (one rank).  backend="nccl": the library opens libnccl itself; the 128-byte
+    unique id is created on rank 0 and shipped through `torch.distributed` (any backend) or given as `unique_id`.
+    backend="external": the collectives are the given torch.distributed group's (host memory: the emulator build / gloo)."""
 
-    Block layout per rank: [block_rows + 1, W + 2] float32; row 0 carries the rank's tuple count in column 0, rows
-    1.. are [flags, global env id, reward, s, a, s'].  Returns the gathered tensor [world, block_rows + 1, W + 2] on the
-    backend device; `unpack_tuple_blocks` trims it on the consumer side.  Rows beyond block_rows stay queued on the
-    producer (the caller only resets its tuple buffer when count <= block_rows).
-    """
-    import torch
-    import torch.distributed as dist
-    world = dist.get_world_size(group)
-    W = rows.shape[1]
-    m = min(block_rows, rows.shape[0])
-    blk = torch.zeros((block_rows + 1, W + 2), dtype=torch.float32, device=rows.device)
-    blk[0, 0] = torch.clamp(count[0], max=m).to(torch.float32)
-    blk[1:m + 1, 0] = flags[:m].to(torch.float32)
-    blk[1:m + 1, 1] = (env_ids[:m] + int(env_offset)).to(torch.float32)
-    blk[1:m + 1, 2:] = rows[:m].to(torch.float32)
-    out = torch.empty((world,) + tuple(blk.shape), dtype=torch.float32, device=rows.device)
-    if rows.is_cuda:
-        dist.all_gather_into_tensor(out.view(-1), blk.view(-1), group=group)
-    else:
-        dist.all_gather(list(out.unbind(0)), blk, group=group)
-    return out
+    def __init__(self, scenario, rank, world, backend="nccl", unique_id=None, group=None):
+        self.sc, self.rank, self.world = scenario, int(rank), int(world)
+        self.L = scenario.L
+        L = self.L
+        L.trl_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.trl_gather_tuples.argtypes = [C.c_void_p, C.c_int]
+        L.trl_comm_set_env_offset.argtypes = [C.c_void_p, C.c_int64]
+        self._keep = None
+        if backend == "nccl":
+            if unique_id is None:
+                unique_id = self.exchange_unique_id(L, self.rank, group)
+            buf = (C.c_ubyte * 128).from_buffer_copy(bytes(unique_id))
+            self._ck(L.trl_comm_init(scenario.h, buf, self.rank, self.world))
+        elif backend == "external":
+            self._keep = self._torch_collectives(group)
+            self._ck(L.trl_comm_init_external(scenario.h, C.byref(self._keep[0]), self.rank, self.world))
+        else:
+            raise ValueError(backend)
 
+    def _ck(self, rc):
+        if rc != 0:
+            raise RuntimeError(self.L.trl_last_error().decode())
 
-def unpack_tuple_blocks(gathered):
-    """(rows_f32 [total, W], flags int32, env int32) from the output of gather_tuple_blocks_fixed (syncs)."""
-    import torch
-    rows, flags, env = [], [], []
-    for r in range(gathered.shape[0]):
-        c = int(gathered[r, 0, 0].item())
-        rows.append(gathered[r, 1:c + 1, 2:]); flags.append(gathered[r, 1:c + 1, 0].to(torch.int32))
-        env.append(gathered[r, 1:c + 1, 1].to(torch.int32))
-    return torch.cat(rows), torch.cat(flags), torch.cat(env)
+    @staticmethod
+    def exchange_unique_id(L, rank, group=None):
+        """rank 0 asks the library (ncclGetUniqueId) and broadcasts the 128 bytes over torch.distributed"""
+        import torch
+        import torch.distributed as dist
+        buf = (C.c_ubyte * 128)()
+        if rank == 0 and L.trl_comm_unique_id(buf) != 0:
+            raise RuntimeError(L.trl_last_error().decode())
+        dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+        t = torch.tensor(list(bytes(buf)), dtype=torch.uint8, device=dev)
+        dist.broadcast(t, src=0, group=group)
+        return bytes(t.cpu().tolist())
 
+    @staticmethod
+    def _torch_collectives(group):
+        """trl_collectives over a torch.distributed group, for buffers in host memory (the library hands over raw pointers)"""
+        import torch
+        import torch.distributed as dist
+        world = dist.get_world_size(group)
 
-def reduce_eval_stats(stats, group=None):
-    """Sum (cycles, episodes, steps) and episode-weighted avg_dist over ranks (cOptScenarioPoliEval::OutputResults
-    merges per-thread results under a mutex: optimizer/scenarios/OptScenarioPoliEval.cpp:213-237)."""
-    import torch
-    import torch.distributed as dist
-    dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
-    t = torch.tensor([stats["cycles"], stats["episodes"], stats["steps"], stats["avg_dist"] * stats["episodes"]],
-                     dtype=torch.float64, device=dev)
-    dist.all_reduce(t, group=group)
-    ep = t[1].item()
-    return dict(cycles=int(t[0].item()), episodes=int(ep), steps=int(t[2].item()), avg_dist=(t[3].item() / ep if ep else 0.0))
+        def view(ptr, nbytes, dtype=torch.uint8):
+            arr = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_ubyte)), (nbytes,))
+            return torch.from_numpy(arr).view(dtype)
+
+        def all_gather(ctx, send, recv, nbytes, stream):
+            out = view(recv, nbytes * world)
+            dist.all_gather(list(out.view(world, nbytes).unbind(0)), view(send, nbytes).clone(), group=group)
+            return 0
+
+        def broadcast(ctx, buf, nbytes, root, stream):
+            dist.broadcast(view(buf, nbytes), src=root, group=group)
+            return 0
+
+        def all_reduce(ctx, buf, count, stream):
+            dist.all_reduce(view(buf, 8 * count, torch.float64), group=group)
+            return 0
+
+        fns = (_Collectives.AG(all_gather), _Collectives.BC(broadcast), _Collectives.AR(all_reduce))
+        return _Collectives(None, *fns), fns
+
+    def close(self):
+        if self.sc is not None and getattr(self.sc, "h", None):
+            self.L.trl_comm_destroy(self.sc.h)
+        self.sc = None
+
+    # ---- the exchange
+    def SetEnvOffset(self, offset):
+        self._ck(self.L.trl_comm_set_env_offset(self.sc.h, int(offset)))
+
+    def GatherTuples(self, block_rows=1024):
+        """pack + all-gather of this update's tuples (asynchronous; shipped tuples leave the scenario's tuple block)"""
+        self._ck(self.L.trl_gather_tuples(self.sc.h, int(block_rows)))
+
+    def Fetch(self, cap=None):
+        """host copy of what the last GatherTuples delivered: (counts[world], rows f32 [n, W], flags u32 [n], env i32 [n])"""
+        W = self.sc.tuple_width
+        br = C.c_int(0)
+        self._ck(self.L.trl_comm_info(self.sc.h, None, None, C.byref(br)))
+        cap = int(cap or br.value * self.world)
+        counts = np.zeros(self.world, np.int32)
+        rows = np.zeros((cap, W), np.float32); flags = np.zeros(cap, np.uint32); env = np.zeros(cap, np.int32)
+        n = C.c_int(0)
+        self._ck(self.L.trl_gathered_fetch(self.sc.h, counts.ctypes.data_as(C.c_void_p), rows.ctypes.data_as(C.c_void_p),
+                                           flags.ctypes.data_as(C.c_void_p), env.ctypes.data_as(C.c_void_p), cap, C.byref(n)))
+        k = min(n.value, cap)
+        return counts, rows[:k], flags[:k], env[:k]
+
+    def LastGatherMs(self):
+        ms = C.c_double(0)
+        self._ck(self.L.trl_gather_last_ms(self.sc.h, C.byref(ms)))
+        return ms.value
+
+    def AddGathered(self, trainer):
+        self._ck(self.L.trl_trainer_add_gathered(trainer.h))
+
+    def BroadcastTrainer(self, trainer, root=0):
+        self._ck(self.L.trl_trainer_broadcast(trainer.h, int(root)))
+
+    def BroadcastWeights(self, root=0):
+        self._ck(self.L.trl_comm_broadcast_weights(self.sc.h, int(root)))
+
+    def ReplicaSpread(self, trainer):
+        """sum over ranks of max |theta - theta(rank 0)|: 0.0 iff all replicas are bit-identical"""
+        d = C.c_double(0)
+        self._ck(self.L.trl_trainer_replica_spread(trainer.h, C.byref(d)))
+        return d.value
+
+    def EvalStats(self):
+        """cOptScenarioPoliEval::OutputResults' merge over all ranks (optimizer/scenarios/OptScenarioPoliEval.cpp:213-237)"""
+        c = C.c_int64(0); e = C.c_int64(0); a = C.c_double(0); s = C.c_int64(0)
+        self._ck(self.L.trl_comm_eval_stats(self.sc.h, C.byref(c), C.byref(e), C.byref(a), C.byref(s)))
+        return dict(cycles=c.value, episodes=e.value, avg_dist=a.value, steps=s.value)
+
+    def TuplesDropped(self):
+        n = C.c_int64(0)
+        self._ck(self.L.trl_tuples_dropped(self.sc.h, C.byref(n)))
+        return n.value

@@ -72,7 +72,7 @@ def build_library(force=False, verbose=False):
     out = library_path()
     csrc = os.path.join(_PKG, "csrc")
     units = [("trl_step.cu", []), ("trl_step_cg.cu", ["-Xptxas", "-dlcm=cg"]), ("trl_host.cu", []), ("trl_train.cu", []),
-             ("ref_loader.cpp", [])]
+             ("trl_comm.cu", []), ("ref_loader.cpp", [])]
     deps = [os.path.join(csrc, f) for f in os.listdir(csrc)]
     deps.append(os.path.join(_ROOT, "include", "terrainrl_b200.h"))
     if not force and os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in deps):
@@ -98,7 +98,7 @@ def build_library(force=False, verbose=False):
     from concurrent.futures import ThreadPoolExecutor
     with ThreadPoolExecutor(len(units)) as ex:
         objs = list(ex.map(compile_unit, units))
-    subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", out] + objs, check=True)
+    subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", out] + objs + ["-ldl"], check=True)
     return out
 
 
@@ -109,8 +109,11 @@ EXPORTS = [
     "trl_get_state_all", "trl_get_ctrl", "trl_get_poli_state", "trl_get_net_out", "trl_get_terrain",
     "trl_kernel_launches", "trl_last_error", "trl_bench_updates", "trl_update_timed", "trl_device_tuple_block", "trl_snapshot", "trl_snapshot_wait", "trl_update_timed_detail", "trl_debug_time_decide",
     "trl_load_model", "trl_output_model", "trl_write_model", "trl_get_output_offset_scale", "trl_pack_output_offset_scale",
-    "trl_set_terrain_lerp", "trl_train_schedule", "trl_trainer_create", "trl_trainer_destroy", "trl_trainer_init_fresh", "trl_trainer_add_from_scene", "trl_trainer_add_tuples", "trl_trainer_add_device", "trl_trainer_train", "trl_train_run",
+    "trl_set_terrain_lerp", "trl_train_schedule", "trl_trainer_create", "trl_trainer_destroy", "trl_trainer_init_fresh", "trl_trainer_add_from_scene", "trl_trainer_add_tuples", "trl_trainer_add_device", "trl_trainer_train", "trl_train_run", "trl_train_run_timed",
     "trl_trainer_counters", "trl_trainer_num_params", "trl_trainer_launches", "trl_trainer_get", "trl_trainer_set_theta", "trl_trainer_list", "trl_trainer_rows",
+    "trl_tuples_dropped", "trl_comm_unique_id", "trl_comm_init", "trl_comm_init_external", "trl_comm_destroy", "trl_comm_info", "trl_comm_set_env_offset",
+    "trl_gather_tuples", "trl_gathered_blocks", "trl_gathered_fetch", "trl_gather_last_ms", "trl_trainer_add_gathered", "trl_trainer_broadcast",
+    "trl_comm_broadcast_weights", "trl_comm_eval_stats", "trl_trainer_replica_spread",
 ]
 
 

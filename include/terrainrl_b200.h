@@ -164,6 +164,11 @@ int trl_trainer_train(trl_trainer* t, int iters);
 /* cScenarioTrain::Run for one batch (scenarios/ScenarioTrain.cpp:100-115,376-410): num_updates x {update, tuple hand-over,
  * trainer iterations (iters_per_update, or 0 = one per tuple_buffer_size new tuples), annealed exploration + curriculum} */
 int trl_train_run(trl_trainer* t, const double* sp9, int num_updates, int iters_per_update, int tuple_buffer_size, double time_step);
+/* the same loop with the tuple exchange of a multi-GPU run (when the scenario has a communicator: trl_gather_tuples(block_rows) +
+ * trl_trainer_add_gathered instead of the local hand-over), timed with CUDA events on the scenario's stream (flush_l2: a 256 MiB
+ * memset before every update, as trl_bench_updates does); *iters_state carries the annealing position across calls (start at 0) */
+int trl_train_run_timed(trl_trainer* t, const double* sp9, int num_updates, int iters_per_update, int block_rows, double time_step,
+                        int flush_l2, int64_t* iters_state, double* ms);
 int trl_trainer_counters(trl_trainer* t, int64_t* counters9, double* losses2);
 int trl_trainer_num_params(trl_trainer* t);
 int64_t trl_trainer_launches(trl_trainer* t);
@@ -171,6 +176,56 @@ int trl_trainer_get(trl_trainer* t, int what, double* out);
 int trl_trainer_set_theta(trl_trainer* t, const double* theta);
 int trl_trainer_list(trl_trainer* t, int which, int32_t* out, int cap, int* len);
 int trl_trainer_rows(trl_trainer* t, const int32_t* slots, int n, float* rows, int32_t* flags);
+
+/* number of tuples the engine could not record because the tuple block was full (cScenarioExp's ring overwrites, scenarios/
+ * ScenarioExp.cpp:296-301; a batch block refuses instead and counts).  trl_num_tuples / trl_get_tuples* return
+ * TRL_E_TUPLE_OVERFLOW (rows up to the capacity are still delivered) once this is non-zero since the last trl_reset_tuples. */
+enum { TRL_E_TUPLE_OVERFLOW = 2 };
+int trl_tuples_dropped(trl_handle* h, int64_t* out);
+
+/* ---------------------------------------------------------------------------------------------------------------------
+ * Multi-GPU exchange: one process per GPU, environments sharded by rank, no collective in the rollout.
+ * The two couplings of the reference's training loop become two collectives on a side stream of the handle:
+ *   trl_gather_tuples      every rank's finished tuples of this update -> every rank; replaces `learner->Train(exp->GetTuples())`
+ *                          under the trainer mutex (scenarios/ScenarioTrain.cpp:388-395, learning/NeuralNetLearner.cpp:33-46):
+ *                          a device pack kernel (f32 rows like cMACETrainer's replay memory, learning/MACETrainer.cpp:515-539, flags,
+ *                          global env ids, count header) + ONE all-gather of a fixed-capacity block per rank.  No host
+ *                          synchronisation; rows beyond block_rows stay queued in the tuple block for the next call.
+ *   trl_trainer_add_gathered   AddTuples of all gathered blocks (rank order, env order inside a rank) into the attached trainer
+ *   trl_trainer_broadcast  cNeuralNetLearner::SyncNet across ranks (learning/NeuralNetLearner.cpp:85-89): weights + offset/scale
+ *                          (and the trainer's target net / momentum history) from `root` to every rank
+ *   trl_comm_eval_stats    cOptScenarioPoliEval::OutputResults' merge of the per-thread results
+ *                          (optimizer/scenarios/OptScenarioPoliEval.cpp:213-237) as one all-reduce
+ * Backends: NCCL (libnccl.so.2 is opened at run time by trl_comm_init; the library does not link against it), or caller-supplied
+ * collectives (trl_comm_init_external: MPI, gloo, a test double) that receive device pointers and the CUDA stream to enqueue on. */
+enum { TRL_COMM_ID_BYTES = 128 };
+int trl_comm_unique_id(void* id128);                                           /* ncclGetUniqueId; call on one rank, ship to all */
+int trl_comm_init(trl_handle* h, const void* id128, int rank, int world);     /* ncclCommInitRank on the handle's device */
+typedef struct trl_collectives {
+    void* ctx;
+    int (*all_gather)(void* ctx, const void* send, void* recv, size_t bytes_per_rank, void* cuda_stream);
+    int (*broadcast)(void* ctx, void* buf, size_t bytes, int root, void* cuda_stream);
+    int (*all_reduce_sum_f64)(void* ctx, void* buf, size_t count, void* cuda_stream);
+} trl_collectives;
+int trl_comm_init_external(trl_handle* h, const trl_collectives* coll, int rank, int world);
+int trl_comm_destroy(trl_handle* h);
+int trl_comm_info(trl_handle* h, int* rank, int* world, int* block_rows);
+/* env i of this rank is reported as env_offset + i in gathered blocks (default rank * num_envs) */
+int trl_comm_set_env_offset(trl_handle* h, int64_t env_offset);
+int trl_gather_tuples(trl_handle* h, int block_rows);
+/* gathered blocks as device memory: world blocks of block_bytes; block = {i32 count, i32 queued, i32 rank, i32 block_rows,
+ * u32 flags[block_rows], i32 env[block_rows], f32 rows[block_rows][1+S+A+S]}.  Ordered on the handle's stream. */
+int trl_gathered_blocks(trl_handle* h, const void** dev_blocks, size_t* block_bytes, int* block_rows, int* row_width);
+/* host copy for tests / a CPU-side trainer: counts[world]; rows/flags/env may be NULL; cap in rows; synchronises */
+int trl_gathered_fetch(trl_handle* h, int32_t* counts, float* rows, uint32_t* flags, int32_t* env, int cap, int* n_total);
+/* exposed device time of the last gather (pack end -> all-gather end on the comm stream), ms; synchronises */
+int trl_gather_last_ms(trl_handle* h, double* ms);
+int trl_trainer_add_gathered(trl_trainer* t);
+int trl_trainer_broadcast(trl_trainer* t, int root);
+int trl_comm_broadcast_weights(trl_handle* h, int root);                       /* same for a handle without a trainer (eval ranks) */
+int trl_comm_eval_stats(trl_handle* h, int64_t* cycles, int64_t* episodes, double* avg_dist, int64_t* env_steps);
+/* max - min over ranks of every trainer parameter (replica drift check), via two all-reduces of +/-theta maxima; synchronises */
+int trl_trainer_replica_spread(trl_trainer* t, double* max_abs_diff);
 
 const char* trl_last_error(void);
 

@@ -2,6 +2,8 @@
 #include <cstring>
 #include <memory>
 #include <thread>
+#include <pthread.h>
+#include <sched.h>
 #include <vector>
 
 #include "env.h"
@@ -57,9 +59,23 @@ void orc_set_explore(OrcBatch* b, int enable, double rate, double temp, double b
 void orc_update(OrcBatch* b, double dt, int num_threads) {
     int n = (int)b->envs.size();
     if (num_threads <= 1) { for (auto& e : b->envs) e->update(dt); return; }
+    // each worker is pinned to one of the CPUs this process may run on (the timed baseline should not migrate)
+    std::vector<int> cpus;
+    cpu_set_t allowed;
+    CPU_ZERO(&allowed);
+    if (sched_getaffinity(0, sizeof(allowed), &allowed) == 0)
+        for (int c = 0; c < CPU_SETSIZE; ++c) if (CPU_ISSET(c, &allowed)) cpus.push_back(c);
     std::vector<std::thread> th;
     for (int t = 0; t < num_threads; ++t)
-        th.emplace_back([=]() { for (int i = t; i < n; i += num_threads) b->envs[i]->update(dt); });
+        th.emplace_back([=]() {
+            if (!cpus.empty()) {
+                cpu_set_t one;
+                CPU_ZERO(&one);
+                CPU_SET(cpus[t % cpus.size()], &one);
+                pthread_setaffinity_np(pthread_self(), sizeof(one), &one);
+            }
+            for (int i = t; i < n; i += num_threads) b->envs[i]->update(dt);
+        });
     for (auto& t : th) t.join();
 }
 void orc_env_step(OrcBatch* b, int env, double h) { b->envs[env]->env_step(h); }

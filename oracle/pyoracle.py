@@ -13,24 +13,50 @@ def build():
     subprocess.run(["make", "-s", "-C", _HERE], check=True)
 
 
-def lib():
-    global _LIB
+def host_has_avx2_fma():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("flags"):
+                    fl = set(line.split(":", 1)[1].split())
+                    return "avx2" in fl and "fma" in fl
+    except OSError:
+        pass
+    return False
+
+
+_FAST = None
+
+
+def lib(fast=False):
+    """fast=True: the -march=x86-64-v3 build (bench.py's CPU baseline); falls back to the portable build on a host without AVX2/FMA"""
+    global _LIB, _FAST
+    if fast and host_has_avx2_fma():
+        if _FAST is None:
+            path = os.path.join(_HERE, "_build", "liboracle_fast.so")
+            if not os.path.exists(path):
+                build()
+            _FAST = _bind(C.CDLL(path))
+        return _FAST
     if _LIB is None:
         path = os.path.join(_HERE, "_build", "liboracle.so")
         if not os.path.exists(path):
             build()
-        L = C.CDLL(path)
-        L.orc_create.restype = C.c_void_p
-        L.orc_create.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_void_p, C.c_uint64]
-        L.orc_last_error.restype = C.c_char_p
-        L.orc_sample_height.restype = C.c_double
-        for name in ("orc_destroy", "orc_update", "orc_env_step", "orc_reset", "orc_get_state", "orc_set_state",
-                     "orc_get_last_tau", "orc_get_poli_state", "orc_get_net_out", "orc_rbd", "orc_forward_dynamics",
-                     "orc_net_eval", "orc_com", "orc_reset_tuples", "orc_eval_stats", "orc_set_phys",
-                     "orc_set_explore"):
-            getattr(L, name).restype = None
-        _LIB = L
+        _LIB = _bind(C.CDLL(path))
     return _LIB
+
+
+def _bind(L):
+    L.orc_create.restype = C.c_void_p
+    L.orc_create.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_void_p, C.c_uint64]
+    L.orc_last_error.restype = C.c_char_p
+    L.orc_sample_height.restype = C.c_double
+    for name in ("orc_destroy", "orc_update", "orc_env_step", "orc_reset", "orc_get_state", "orc_set_state",
+                 "orc_get_last_tau", "orc_get_poli_state", "orc_get_net_out", "orc_rbd", "orc_forward_dynamics",
+                 "orc_net_eval", "orc_com", "orc_reset_tuples", "orc_eval_stats", "orc_set_phys",
+                 "orc_set_explore"):
+        getattr(L, name).restype = None
+    return L
 
 
 def _p(a):
@@ -38,8 +64,8 @@ def _p(a):
 
 
 class Oracle:
-    def __init__(self, pack, num_envs=1, mode=0, terrain_seeds=None, rng_seed=1234):
-        self.L = lib()
+    def __init__(self, pack, num_envs=1, mode=0, terrain_seeds=None, rng_seed=1234, fast=False):
+        self.L = lib(fast)
         seeds = None
         if terrain_seeds is not None:
             seeds = np.ascontiguousarray(terrain_seeds, dtype=np.uint64)

@@ -9,7 +9,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "deepterrainrl_b200", "csrc")
-UNITS = ["trl_step.cu", "trl_step_cg.cu", "trl_host.cu", "trl_train.cu", "ref_loader.cpp"]
+UNITS = ["trl_step.cu", "trl_step_cg.cu", "trl_host.cu", "trl_train.cu", "trl_comm.cu", "ref_loader.cpp"]
 LOCAL_UNITS = ["simt_runtime.cpp", "selftest.cu"]
 VARIANT_UNITS = ["trl_step.cu", "trl_step_cg.cu"]     # the only units the TRL_* experiment knobs reach
 CXXFLAGS = ["-std=c++17", "-O2", "-g1", "-fPIC", "-ffp-contract=off", "-fno-strict-aliasing", "-DTRL_SIMT_EMU=1", "-w",
@@ -65,7 +65,7 @@ def _build_locked(out, bdir, deps, defines, force):
         common = _compile(cxx, [u for u in UNITS + LOCAL_UNITS if u not in VARIANT_UNITS], common_dir, [], deps, force)
     objs = common + _compile(cxx, VARIANT_UNITS, bdir, defines, deps, force)
     # device functions defined in headers are not `inline` in CUDA sources: the same definition appears in several objects
-    subprocess.run([cxx, "-shared", "-o", out + ".tmp"] + objs + ["-Wl,--allow-multiple-definition", "-lpthread"], check=True)
+    subprocess.run([cxx, "-shared", "-o", out + ".tmp"] + objs + ["-Wl,--allow-multiple-definition", "-lpthread", "-ldl"], check=True)
     os.replace(out + ".tmp", out)
     return out
 
