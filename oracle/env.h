@@ -37,6 +37,7 @@
 
 #include "net.h"
 #include "pack_reader.h"
+#include <cstdlib>
 #include "rbd.h"
 #include "terrain.h"
 
@@ -51,6 +52,7 @@ struct PhysParams {
     double contact_tol = 0.00025;  // 0.001 Bullet units / world_scale 4 (sim/ContactManager.cpp:74)
     double k_lim = 2.0e4;   // joint-limit stiffness [N m/rad]
     double d_lim = 20.0;    // joint-limit damping [N m s/rad]
+    int vertex_contacts = std::getenv("ORC_VTX") ? std::atoi(std::getenv("ORC_VTX")) : 0;   // terrain vertices inside boxes (experiment switch)
 };
 
 // dog / goat joint indices (sim/SimDog.h:11-36)
@@ -768,6 +770,48 @@ struct Env {
     struct ContactPoint { int body; double px, py; };
     double last_qdd[kMaxDof] = {0};
 
+    // one compliant contact on body i at world point (px, py): penetration `pen` along the unit direction (nx, ny) the force pushes
+    // the body in.  Implicit in the point velocity: adds dt J^T D J to A and J^T w to rhs, D = cnn n n^T + ctt t t^T.
+    void add_contact(int i, double px, double py, double pen, double nx, double ny, double dt, const SV* avp, double (*A)[kMaxDof], double* rhs) {
+        const Skeleton& sk = sc->sk;
+        const PhysParams& pp = sc->phys;
+        const int nd = sk.ndof;
+        const double tx = ny, ty = -nx;
+        // point Jacobian rows along the chain, point velocity, velocity-product acceleration at the point
+        double Jx[kMaxDof] = {0}, Jy[kMaxDof] = {0};
+        double vx = 0, vy = 0;
+        for (int cj = i; cj >= 0; cj = sk.parent[cj]) {
+            int o = sk.offset[cj];
+            for (int k = 0; k < sk.size[cj]; ++k) {
+                const SV& col = phys_model.J[o + k];
+                Jx[o + k] = col.v.x - col.o.z * py;
+                Jy[o + k] = col.v.y + col.o.z * px;
+                vx += Jx[o + k] * qd[o + k];
+                vy += Jy[o + k] * qd[o + k];
+            }
+        }
+        double ax = avp[i].v.x - avp[i].o.z * py, ay = avp[i].v.y + avp[i].o.z * px;
+        double vn = vx * nx + vy * ny, vt = vx * tx + vy * ty;
+        double fn0 = pp.kn * pen - pp.dn * vn;
+        if (fn0 <= 0) return;
+        double cnn = pp.dn + dt * pp.kn;
+        double ctt = pp.mu * fn0 / std::max(std::abs(vt), pp.v_eps);
+        // D = cnn n n^T + ctt t t^T ; w = F0 - D (v + dt a_vp)
+        double ux = vx + dt * ax, uy = vy + dt * ay;
+        double un = ux * nx + uy * ny, ut = ux * tx + uy * ty;
+        double wx = pp.kn * pen * nx - cnn * un * nx - ctt * ut * tx;
+        double wy = pp.kn * pen * ny - cnn * un * ny - ctt * ut * ty;
+        for (int a = 0; a < nd; ++a) {
+            if (Jx[a] == 0 && Jy[a] == 0) continue;
+            rhs[a] += Jx[a] * wx + Jy[a] * wy;
+            double jan = Jx[a] * nx + Jy[a] * ny, jat = Jx[a] * tx + Jy[a] * ty;
+            for (int b = 0; b < nd; ++b) {
+                double jbn = Jx[b] * nx + Jy[b] * ny, jbt = Jx[b] * tx + Jy[b] * ty;
+                A[a][b] += dt * (cnn * jan * jbn + ctt * jat * jbt);
+            }
+        }
+    }
+
     // forward dynamics with implicit contact / joint-limit terms; returns qdd, optionally refreshes contact bits
     void forward_dynamics(const double* tau, double dt, double* qdd, bool write_contacts) {
         const Skeleton& sk = sc->sk;
@@ -805,41 +849,25 @@ struct Env {
                 if (pen <= -pp.contact_tol) continue;
                 if (write_contacts) contact[i] = true;
                 if (pen <= 0) continue;
-                double nx = -slope * inv, ny = inv, tx = inv, ty = slope * inv;
-                // point Jacobian rows along the chain, point velocity, velocity-product acceleration at the point
-                double Jx[kMaxDof] = {0}, Jy[kMaxDof] = {0};
-                double vx = 0, vy = 0;
-                for (int cj = i; cj >= 0; cj = sk.parent[cj]) {
-                    int o = sk.offset[cj];
-                    for (int k = 0; k < sk.size[cj]; ++k) {
-                        const SV& col = phys_model.J[o + k];
-                        Jx[o + k] = col.v.x - col.o.z * py;
-                        Jy[o + k] = col.v.y + col.o.z * px;
-                        vx += Jx[o + k] * qd[o + k];
-                        vy += Jy[o + k] * qd[o + k];
-                    }
-                }
-                double ax = avp[i].v.x - avp[i].o.z * py, ay = avp[i].v.y + avp[i].o.z * px;
-                double vn = vx * nx + vy * ny, vt = vx * tx + vy * ty;
-                double fn0 = pp.kn * pen - pp.dn * vn;
-                if (fn0 <= 0) continue;
-                double cnn = pp.dn + dt * pp.kn;
-                double ctt = pp.mu * fn0 / std::max(std::abs(vt), pp.v_eps);
-                // D = cnn n n^T + ctt t t^T ; w = F0 - D (v + dt a_vp)
-                double ux = vx + dt * ax, uy = vy + dt * ay;
-                double un = ux * nx + uy * ny, ut = ux * tx + uy * ty;
-                double wx = pp.kn * pen * nx - cnn * un * nx - ctt * ut * tx;
-                double wy = pp.kn * pen * ny - cnn * un * ny - ctt * ut * ty;
-                for (int a = 0; a < nd; ++a) {
-                    if (Jx[a] == 0 && Jy[a] == 0) continue;
-                    rhs[a] += Jx[a] * wx + Jy[a] * wy;
-                    double jan = Jx[a] * nx + Jy[a] * ny, jat = Jx[a] * tx + Jy[a] * ty;
-                    for (int b = 0; b < nd; ++b) {
-                        double jbn = Jx[b] * nx + Jy[b] * ny, jbt = Jx[b] * tx + Jy[b] * ty;
-                        A[a][b] += dt * (cnn * jan * jbn + ctt * jat * jbt);
-                    }
-                }
+                add_contact(i, px, py, pen, -slope * inv, inv, dt, avp, A, rhs);
             }
+            if (!pp.vertex_contacts) continue;
+            // terrain vertices inside the box (sim/GroundVar2D.cpp:440-448 hands Bullet a height field: an edge of the terrain can
+            // enter a box between two of its corners).  Only vertices where the surface is convex can do that.  The vertex is
+            // pushed out through the nearest face: depth = distance to that face, force on the box along the opposite direction.
+            const double ext = std::abs(c) * hx + std::abs(s) * hy;
+            ground.for_vertices(body[i].px - ext - pp.contact_tol, body[i].px + ext + pp.contact_tol, [&](double vx_, double vh, double hp, double hn) {
+                if (!(vh - 0.5 * (hp + hn) > 1e-9)) return;
+                const double rx = vx_ - body[i].px, ry = vh - body[i].py;
+                const double lx = c * rx + s * ry, ly = -s * rx + c * ry;
+                const double dx = hx - std::abs(lx), dy = hy - std::abs(ly);
+                if (dx <= -pp.contact_tol || dy <= -pp.contact_tol) return;
+                if (write_contacts) contact[i] = true;
+                if (dx <= 0 || dy <= 0) return;
+                double nlx = 0, nly = 0, pen;
+                if (dx < dy) { nlx = lx > 0 ? -1.0 : 1.0; pen = dx; } else { nly = ly > 0 ? -1.0 : 1.0; pen = dy; }
+                add_contact(i, vx_, vh, pen, c * nlx - s * nly, s * nlx + c * nly, dt, avp, A, rhs);
+            });
         }
         // joint limits: one-sided implicit spring-damper (limits [1,0] mean "none", sim/World.cpp:28-29)
         for (int j = 1; j < sk.nj; ++j) {

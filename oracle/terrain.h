@@ -332,6 +332,29 @@ struct Ground {
         }
         flip = (seg_id(0) == 0);
     }
+    // (this project's contact model, not a restatement) the terrain vertices with xmin <= x <= xmax, each once: the vertex the two
+    // segments share at their seam is reported from the max segment, as sample() resolves it.  fn(x, h, h_prev, h_next); the
+    // neighbours of a window's end vertices repeat the end height (sample()'s clamp).
+    template <typename F>
+    void for_vertices(double xmin, double xmax, F&& fn) const {
+        const double sp = (double)TerrainGen::kVertSpacing;
+        const double seam = min_seg().get_max_x();
+        for (int si = 0; si < kNumSeg; ++si) {
+            const Seg& sg = seg[seg_id(si)];
+            const int w = (int)sg.data.size();
+            if (w == 0) continue;
+            int k0 = (int)std::ceil((xmin - sg.min_x) / sp - 1e-9), k1 = (int)std::floor((xmax - sg.min_x) / sp + 1e-9);
+            k0 = std::max(k0, 0); k1 = std::min(k1, w - 1);
+            for (int k = k0; k <= k1; ++k) {
+                const double x = sg.min_x + k * sp;
+                if (si == 0 && x >= seam) continue;
+                if (si == 1 && x < seam) continue;
+                const double hp = k > 0 ? (double)sg.data[k - 1] : (si == 1 ? sample(x - sp) : (double)sg.data[k]);
+                const double hn = k < w - 1 ? (double)sg.data[k + 1] : (si == 0 ? sample(x + sp) : (double)sg.data[k]);
+                fn(x, (double)sg.data[k], hp, hn);
+            }
+        }
+    }
     // cGroundVar2D::SampleHeight (sim/GroundVar2D.cpp:103-116)
     double sample(double x, double* slope = nullptr) const {
         const Seg& ms = min_seg();

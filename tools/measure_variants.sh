@@ -34,7 +34,7 @@ for v in "${names[@]}"; do
     if [ "$v" = product ]; then export -n TRL_VARIANT; unset TRL_VARIANT; else export TRL_VARIANT=$v; fi
     timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_ref_golden.py -m gpu -x -q > gpurun_out/variants/$v.parity.txt 2>&1
     echo "$v parity: $(tail -1 gpurun_out/variants/$v.parity.txt)"
-    timeout 300 python bench.py --steps 30 --warmup 5 --cpu-seconds 0.5 > gpurun_out/variants/$v.json 2> gpurun_out/variants/$v.err
+    timeout 300 python bench.py --steps 30 --warmup 5 --cpu-seconds 0.5 --config4 0 > gpurun_out/variants/$v.json 2> gpurun_out/variants/$v.err
 done
 unset TRL_VARIANT
 python - "${names[@]}" <<'P' | tee gpurun_out/variants/summary.txt
