@@ -1,0 +1,495 @@
+// deepterrainrl_b200 -- batched policy decision path (included by trl_step.cu after trl_decide.cuh; same translation unit).
+//
+// All decisions that became due in one env-step are served by ONE pass over the MACE network
+// (data/policies/dog/nets/dog_mace3_deploy.prototxt; cNeuralNet::Eval, learning/NeuralNet.cpp:352-375,977-986,1027-1036), split where
+// the arithmetic changes character:
+//
+//   trl_decide_conv_kernel   the three terrain convolutions: 2.4 of the net's 3.5 MFLOP per decision on 6 K weights.  Parallel over
+//                            decisions (one 4-CTA cluster each, activations in shared memory / DSMEM, trl_decide.cuh's conv
+//                            stage); the flattened conv2 output [32 x 187] of decision idx goes to row idx of a scratch matrix.
+//   trl_decide_fc_kernel     everything behind it as GEMMs over the batch: rows = decisions (chunks of 32), weights streamed ONCE
+//                            per launch instead of once per decision (4.5 MB instead of 16 x 4.5 MB from L2).  One 8-CTA cluster:
+//                              terr_ip0  [32 x 5984] x [5984 x 64]   K split over the CTAs; weight and activation tiles come in
+//                                        through TMA (cp.async.bulk.tensor.2d, 128-byte swizzle, mbarrier ring), partial sums
+//                                        reduced over DSMEM in rank order
+//                              ip0       [32 x 147]  x [147 x 256]   32 output columns per CTA (weights resident in shared memory)
+//                              heads     [32 x 256]  x [256 x 512],  [32 x 128] x [128 x {3,29,29,29}]
+//                            every product on mma.sync.m8n8k4.f64 (DMMA), f64 throughout like the reference's Caffe Net<double>;
+//                            then the scalar decision logic of cDogControllerMACE::UpdateAction / cBaseControllerMACE::
+//                            DecideActionBoltzmann for up to 32 decisions at once, one lane each.
+//
+// Results differ from trl_decide.cuh's single-decision pass only in summation order (<= 1e-13 relative on the net outputs).
+#pragma once
+#include <cooperative_groups.h>
+
+#include "trl_types.h"
+#include "trl_fcmaps.h"
+
+namespace trl {
+
+constexpr int kFcCluster = 8;            // CTAs of the FC-stage cluster
+constexpr int kFcThreads = 512;
+constexpr int kFcRows = 32;              // decisions per chunk (GEMM rows)
+constexpr int kTipIn = kConv2Out * kW2;   // 5984 = terr_ip0 fan-in
+constexpr int kKT = 16;                  // k extent of a TMA tile: 16 doubles = the 128-byte swizzle span
+constexpr int kNumKTiles = kTipIn / kKT;  // 374
+static_assert(kNumKTiles * kKT == kTipIn, "terr_ip0 fan-in must be a whole number of TMA tiles");
+constexpr int kFcStages = 8;
+constexpr int kWTileBytes = kTip0Out * kKT * 8;          // 8 KB  [64 n][16 k]
+constexpr int kATileBytes = kFcRows * kKT * 8;           // 4 KB  [32 m][16 k]
+constexpr int kStageBytes = kWTileBytes + kATileBytes;   // 12 KB, a multiple of 1024 (swizzle atom alignment)
+constexpr int kCatStride = 148;          // doubles per row of concat0 (64 + n_char <= 147, +1 zero pad): 1184 B = 32 mod 128 -> conflict-free fragments
+constexpr int kHStride = 260;            // doubles per row of the ip0 output (256 + 4): 2080 B = 32 mod 128
+constexpr int kHHStride = 132;           // doubles per row of one head's hidden layer (128 + 4)
+constexpr int kYStride = 96;
+// shared memory map of the FC kernel (bytes)
+constexpr int kFcOffPipe = 0;                                              // kFcStages x {W tile, A tile}; later H and HH
+constexpr int kFcOffH = 0;                                                 //   H   [32][260]  (after terr_ip0)
+constexpr int kFcOffHH = kFcOffH + kFcRows * kHStride * 8;                 //   HH  [32][132]  (one head's 128 hidden units)
+constexpr int kFcPipeBytes = (kFcStages * kStageBytes > kFcOffHH + kFcRows * kHHStride * 8) ? kFcStages * kStageBytes
+                                                                                           : kFcOffHH + kFcRows * kHHStride * 8;
+constexpr int kFcOffPart = (kFcPipeBytes + 1023) / 1024 * 1024;           // P   [32][64] partial terr_ip0 sums of this CTA
+constexpr int kFcOffCat = kFcOffPart + kFcRows * kTip0Out * 8;             // CAT [32][148]
+constexpr int kFcOffWip = kFcOffCat + kFcRows * kCatStride * 8;            // ip0 weight slice [32 n][148]
+constexpr int kFcOffY = kFcOffWip + 32 * kCatStride * 8;                   // Y   [32][96] (rank 0)
+constexpr int kFcOffBar = kFcOffY + kFcRows * kYStride * 8;                // mbarriers: full[kFcStages], empty[kFcStages]
+constexpr int kFcSmemBytes = kFcOffBar + 2 * kFcStages * 8 + 64 + 1024;    // + slack for the 1024-byte alignment of the window
+
+// ---- the pieces of PTX the FC kernel needs; the test-only emulator build (g++) gets plain-C++ stand-ins with the same data layout
+__device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, double b) {
+#ifndef TRL_SIMT_EMU
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+#else
+    // lane (g = lane / 4, t = lane % 4) holds A[g][t], B[t][g] and C[g][2t], C[g][2t + 1]
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    double s0 = c0, s1 = c1;
+    for (int k = 0; k < 4; ++k) {
+        const double ak = __shfl_sync(0xffffffffu, a, g * 4 + k);
+        const double b0 = __shfl_sync(0xffffffffu, b, (2 * t) * 4 + k), b1 = __shfl_sync(0xffffffffu, b, (2 * t + 1) * 4 + k);
+        s0 += ak * b0; s1 += ak * b1;
+    }
+    c0 = s0; c1 = s1;
+#endif
+}
+// element (row, k) of a [rows][16] f64 tile written by TMA with CU_TENSOR_MAP_SWIZZLE_128B: 16-byte chunk j of row r sits at chunk j ^ (r % 8)
+__device__ __forceinline__ int swz(int row, int k) { return row * kKT + ((((k >> 1) ^ (row & 7)) << 1) | (k & 1)); }
+
+#ifndef TRL_SIMT_EMU
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(void* bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count)); }
+__device__ __forceinline__ void mbar_expect_tx(void* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(void* bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
+__device__ __forceinline__ void mbar_wait(void* bar, unsigned parity) {
+    asm volatile(
+        "{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, void* bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+                 "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+#endif
+
+// ------------------------------------------------------------------------------------------------ conv stage
+// trl_decide.cuh's conv0 / conv1 / conv2 for the decision at pending index idx; the flattened conv2 output goes to act2[idx][5984]
+__device__ void conv_stage_cluster(cg::cluster_group& cluster, const NetWeights& W, const double* __restrict__ x_in, double* sh, int n_char,
+                                   double* __restrict__ out_row) {
+    const int tid = threadIdx.x;
+    const int rank = (int)cluster.block_rank();
+    const int n_in = 200 + n_char;
+    double* X = sh + kShX;
+    double* A0 = sh + kShA0;
+    double* A1 = sh + kShA1;
+    double* W0s = sh + kShW0;
+    double* W1s = sh + kShW1;
+    double* W2s = sh + kShW2;
+    for (int i = tid; i < n_in; i += kDecideThreads) X[i] = (x_in[i] + W.in_off[i]) * W.in_scale[i];
+    for (int i = tid; i < kConv0Out * kConv0K; i += kDecideThreads) W0s[i] = W.conv0_w[i];
+    for (int i = tid; i < kConv0Out; i += kDecideThreads) W0s[kConv0Out * kConv0K + i] = W.conv0_b[i];
+    for (int i = tid; i < kC1Slice * kConv0Out * kConv1K; i += kDecideThreads) W1s[i] = W.conv1_w[rank * kC1Slice * kConv0Out * kConv1K + i];
+    for (int i = tid; i < kC2Slice * kConv1Out * kConv2K; i += kDecideThreads) W2s[i] = W.conv2_w[rank * kC2Slice * kConv1Out * kConv2K + i];
+    __syncthreads();
+    for (int idx = tid; idx < kConv0Out * kW0; idx += kDecideThreads) {
+        int o = idx / kW0, t = idx - o * kW0;
+        double acc = W0s[kConv0Out * kConv0K + o];
+#pragma unroll
+        for (int k = 0; k < kConv0K; ++k) acc += W0s[o * kConv0K + k] * X[t + k];
+        A0[idx] = acc > 0.0 ? acc : 0.0;
+    }
+    __syncthreads();
+    // conv1: this CTA's output channels, kConvTile adjacent positions per thread (activations and weights of an input channel are
+    // loaded once for tile x K multiply-adds); 4 accumulators by c & 3, k inner -- the summation order of trl_decide.cuh
+    {
+        constexpr int nt = (kW1 + kConvTile - 1) / kConvTile;
+        for (int item = tid; item < kC1Slice * nt; item += kDecideThreads) {
+            const int ol = item / nt, t0 = (item - ol * nt) * kConvTile, o = rank * kC1Slice + ol;
+            const double* w = W1s + ol * kConv0Out * kConv1K;
+            double acc[kConvTile][4];
+#pragma unroll
+            for (int j = 0; j < kConvTile; ++j) { acc[j][0] = W.conv1_b[o]; acc[j][1] = 0.0; acc[j][2] = 0.0; acc[j][3] = 0.0; }
+#pragma unroll
+            for (int c = 0; c < kConv0Out; ++c) {
+                const double* a = A0 + c * kW0;
+                double av[kConvTile + kConv1K - 1];
+#pragma unroll
+                for (int i = 0; i < kConvTile + kConv1K - 1; ++i) av[i] = a[min(t0 + i, kW0 - 1)];
+#pragma unroll
+                for (int k = 0; k < kConv1K; ++k) {
+                    const double wk = w[c * kConv1K + k];
+#pragma unroll
+                    for (int j = 0; j < kConvTile; ++j) acc[j][c & 3] += wk * av[j + k];
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < kConvTile; ++j) {
+                const double v = (acc[j][0] + acc[j][1]) + (acc[j][2] + acc[j][3]);
+                if (t0 + j < kW1) A1[o * kW1 + t0 + j] = v > 0.0 ? v : 0.0;
+            }
+        }
+    }
+    cluster.sync();
+    for (int r = 1; r < kClusterSize; ++r) {
+        int src = (rank + r) % kClusterSize;
+        const double* remote = cluster.map_shared_rank(A1, src);
+        for (int i = tid; i < kC1Slice * kW1; i += kDecideThreads) {
+            int off = src * kC1Slice * kW1 + i;
+            A1[off] = remote[off];
+        }
+    }
+    __syncthreads();
+    {
+        constexpr int nt = (kW2 + kConvTile - 1) / kConvTile;
+        double* out = out_row + (size_t)rank * kC2Slice * kW2;
+        for (int item = tid; item < kC2Slice * nt; item += kDecideThreads) {
+            const int ol = item / nt, t0 = (item - ol * nt) * kConvTile, o = rank * kC2Slice + ol;
+            const double* w = W2s + ol * kConv1Out * kConv2K;
+            double acc[kConvTile][4];
+#pragma unroll
+            for (int j = 0; j < kConvTile; ++j) { acc[j][0] = W.conv2_b[o]; acc[j][1] = 0.0; acc[j][2] = 0.0; acc[j][3] = 0.0; }
+#pragma unroll 8
+            for (int c = 0; c < kConv1Out; ++c) {
+                const double* a = A1 + c * kW1;
+                double av[kConvTile + kConv2K - 1];
+#pragma unroll
+                for (int i = 0; i < kConvTile + kConv2K - 1; ++i) av[i] = a[min(t0 + i, kW1 - 1)];
+#pragma unroll
+                for (int k = 0; k < kConv2K; ++k) {
+                    const double wk = w[c * kConv2K + k];
+#pragma unroll
+                    for (int j = 0; j < kConvTile; ++j) acc[j][c & 3] += wk * av[j + k];
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < kConvTile; ++j) {
+                const double v = (acc[j][0] + acc[j][1]) + (acc[j][2] + acc[j][3]);
+                if (t0 + j < kW2) out[ol * kW2 + t0 + j] = v > 0.0 ? v : 0.0;
+            }
+        }
+    }
+    cluster.sync();   // peers read this CTA's A1 slice until here; the next decision overwrites it
+}
+
+__global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kDecideThreads, TRL_DECIDE_MIN_BLOCKS)
+trl_decide_conv_kernel(Buffers B, NetWeights W, double* __restrict__ act2, int list) {
+    TRL_DYN_SHARED(double, sh);
+    cg::cluster_group cluster = cg::this_cluster();
+    const ModelConst& m = c_model;
+    if (!m.has_net) return;
+    const int cid = blockIdx.x / kClusterSize, ncl = gridDim.x / kClusterSize;
+    const int count = B.pending_count[list];
+    for (int idx = cid; idx < count; idx += ncl) {
+        const int env = B.pending_list[list * B.n + idx];
+        conv_stage_cluster(cluster, W, B.poli_state + (size_t)env * B.S, sh, m.n_char, act2 + (size_t)idx * kTipIn);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ FC stage
+// the scalar decision of one env (cDogControllerMACE::UpdateAction, cBaseControllerMACE::DecideActionBoltzmann, BuildActorAction,
+// ApplyExpNoiseAction: sim/DogController.cpp:847-868, sim/BaseControllerMACE.cpp:254-318,339-396,437-518); Y = this decision's
+// unnormalised net output (unused when the scene has no net)
+__device__ void decide_one(const Buffers& B, const ExpSettings& ex, int env, const double* Y) {
+    const ModelConst& m = c_model;
+    Lane L{nullptr, env, B.n, B.d, B.i};
+    double params[kNumParams];
+    int id, eflags = 4;
+    CounterRng rng = load_rng(L);
+    for (int k = 0; k < m.n_params; ++k) params[k] = L.d(D_PARAMS + k);
+    id = L.i(I_ACTION_ID);
+    const int cmd = L.i(I_CMD);
+    if (cmd >= 0) {
+        if (m.is_mace) eflags |= 3;
+        id = build_base_action(L, rng, cmd, params);
+        L.i(I_CMD) = -1;
+    } else if (m.has_net) {
+        const double base_rand = rng.uniform();
+        if (ex.enable && base_rand < ex.base_rate) {
+            const int a = rng.rand_int(0, m.n_actions);
+            id = build_base_action(L, rng, a, params);
+            eflags = 4 | 3;
+        } else {
+            for (int i = 0; i < m.n_out; ++i) B.net_out[(size_t)env * kMaxNetOut + i] = Y[i];
+            eflags = 0;
+            const int nf = m.n_frags, fs = m.frag;
+            int a_max = 0;
+            for (int i = 1; i < nf; ++i) if (Y[i] > Y[a_max]) a_max = i;
+            int a = a_max;
+            if (ex.enable && ex.temp != 0.0) {   // BoltzmannSelectActor
+                double vals[8], sum = 0.0;
+                for (int i = 0; i < nf; ++i) { vals[i] = exp((Y[i] - Y[a_max]) / ex.temp); sum += vals[i]; }
+                double r = rng.uniform() * sum;
+                for (int i = 0; i < nf; ++i) { r -= vals[i]; if (r <= 0.0) { a = i; break; } }
+            }
+            id = a;
+            for (int k = 0; k < fs; ++k) params[m.opt_idx[k]] = Y[nf + a * fs + k];
+            params[mTransTime] = fabs(params[mTransTime]); params[mCv] = fabs(params[mCv]);
+            if (m.char_type == 2) params[rmCd] = fabs(params[rmCd]);
+            if (ex.enable) {
+                const double rn = rng.uniform();
+                if (rn < ex.rate) {              // ApplyExpNoiseAction
+                    for (int k = 0; k < fs; ++k) params[m.opt_idx[k]] += (ex.noise * rng.normal()) * (1.0 / m.out_scale_actor0[k]);
+                    eflags |= 2;
+                }
+                if (a != a_max) eflags |= 1;
+                if (eflags & 3) eflags |= 4;
+            }
+        }
+    } else {
+        const bool cyclic = m.is_mace ? false : (m.act_cyclic[id] != 0);
+        if (!cyclic) id = build_base_action(L, rng, m.default_action, params);
+    }
+    L.i(I_EXP_FLAGS) = eflags;
+    apply_action(L, id, params, B.com_stash[env], B.com_stash[B.n + env]);
+    store_rng(L, rng);
+}
+
+__global__ void __cluster_dims__(kFcCluster, 1, 1) __launch_bounds__(kFcThreads, 1)
+trl_decide_fc_kernel(Buffers B, NetWeights W, const ExpSettings* __restrict__ ex_dev, const TRL_GRID_CONSTANT FcMaps maps, int* done_count, int list,
+                     int rearm) {
+    TRL_DYN_SHARED(unsigned char, fc_smem_raw);
+    // the swizzled TMA tiles need 1024-byte alignment; the dynamic window starts at the same offset in every CTA of the cluster, so
+    // the rounded address is a valid DSMEM offset as well
+#ifndef TRL_SIMT_EMU
+    unsigned char* fc_smem = fc_smem_raw + ((1024u - (smem_u32(fc_smem_raw) & 1023u)) & 1023u);
+#else
+    unsigned char* fc_smem = fc_smem_raw;      // no hardware swizzle to satisfy; per-CTA host allocations are not equally aligned
+#endif
+    cg::cluster_group cluster = cg::this_cluster();
+    const ModelConst& m = c_model;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t4 = lane & 3;
+    const int rank = (int)cluster.block_rank();
+    const int cid = blockIdx.x / kFcCluster, ncl = gridDim.x / kFcCluster;
+    const int count = B.pending_count[list];
+    const ExpSettings ex = *ex_dev;
+    const int n_char = m.n_char, ncat = kTip0Out + n_char;
+    double* P = (double*)(fc_smem + kFcOffPart);
+    double* CAT = (double*)(fc_smem + kFcOffCat);
+    double* WIP = (double*)(fc_smem + kFcOffWip);
+    double* H = (double*)(fc_smem + kFcOffH);
+    double* HH = (double*)(fc_smem + kFcOffHH);
+    double* Y = (double*)(fc_smem + kFcOffY);
+    unsigned long long* bar_full = (unsigned long long*)(fc_smem + kFcOffBar);
+    unsigned long long* bar_empty = bar_full + kFcStages;
+    const int nchunks = (count + kFcRows - 1) / kFcRows;
+
+    if (m.has_net && cid < nchunks) {
+        // ip0 weight slice of this CTA (32 output columns x ncat, zero-padded to kCatStride): resident for the whole launch
+        for (int i = tid; i < 32 * kCatStride; i += kFcThreads) {
+            const int n = i / kCatStride, k = i - n * kCatStride;
+            WIP[i] = k < ncat ? W.ip0_w[(size_t)(rank * 32 + n) * ncat + k] : 0.0;
+        }
+#ifndef TRL_SIMT_EMU
+        if (tid == 0) {
+            for (int s = 0; s < kFcStages; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], kFcThreads / 32); }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
+#endif
+        __syncthreads();
+    }
+    // k tiles of terr_ip0 this CTA multiplies
+    const int kt0 = (kNumKTiles * rank) / kFcCluster, kt1 = (kNumKTiles * (rank + 1)) / kFcCluster;
+    unsigned pipe_iter = 0;      // tiles issued / consumed so far over all chunks (stage = iter % kFcStages, parity from iter / kFcStages)
+
+    for (int chunk = cid; chunk < nchunks; chunk += ncl) {
+        const int row0 = chunk * kFcRows;
+        const int rows = min(kFcRows, count - row0);
+        if (m.has_net) {
+            // ---------------- terr_ip0: P[32][64] = A[32][k slice] * Wt[k slice][64]; warp w owns C tiles (m tile w / 4, n tiles 2 (w % 4) + {0, 1})
+            const int mt = warp >> 2, nt0 = (warp & 3) * 2;
+            double c00 = 0, c01 = 0, c10 = 0, c11 = 0;
+            const int ntile = kt1 - kt0;
+#ifndef TRL_SIMT_EMU
+            // producer: thread 0 keeps up to kFcStages tiles in flight
+            int issued = 0;
+            auto issue = [&](int j) {
+                const unsigned it = pipe_iter + (unsigned)j;
+                const int s = (int)(it % kFcStages);
+                const unsigned round = it / kFcStages;
+                if (round > 0) mbar_wait(&bar_empty[s], (round - 1) & 1);
+                unsigned char* st = fc_smem + kFcOffPipe + (size_t)s * kStageBytes;
+                mbar_expect_tx(&bar_full[s], kStageBytes);
+                tma_load_2d(st, &maps.w, &bar_full[s], (kt0 + j) * kKT, 0);
+                tma_load_2d(st + kWTileBytes, &maps.a, &bar_full[s], (kt0 + j) * kKT, row0);
+            };
+            if (tid == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // H / HH of the previous chunk live in the same bytes
+                for (; issued < min(kFcStages, ntile); ++issued) issue(issued);
+            }
+#endif
+            for (int j = 0; j < ntile; ++j) {
+                const unsigned it = pipe_iter + (unsigned)j;
+                const int s = (int)(it % kFcStages);
+                double* Wt = (double*)(fc_smem + kFcOffPipe + (size_t)s * kStageBytes);
+                double* At = (double*)(fc_smem + kFcOffPipe + (size_t)s * kStageBytes + kWTileBytes);
+#ifndef TRL_SIMT_EMU
+                mbar_wait(&bar_full[s], (it / kFcStages) & 1);
+#else
+                // emulator: the tile copies TMA would perform, same swizzled layout
+                __syncthreads();
+                for (int i = tid; i < kTip0Out * kKT; i += kFcThreads) {
+                    const int n = i / kKT, k = i - n * kKT;
+                    Wt[swz(n, k)] = maps.w_ptr[(size_t)n * kTipIn + (kt0 + j) * kKT + k];
+                }
+                for (int i = tid; i < kFcRows * kKT; i += kFcThreads) {
+                    const int r = i / kKT, k = i - r * kKT;
+                    At[swz(r, k)] = (row0 + r) < maps.a_rows ? maps.a_ptr[(size_t)(row0 + r) * kTipIn + (kt0 + j) * kKT + k] : 0.0;
+                }
+                __syncthreads();
+#endif
+#pragma unroll
+                for (int ks = 0; ks < kKT / 4; ++ks) {
+                    const double a = At[swz(mt * 8 + g, ks * 4 + t4)];
+                    const double b0 = Wt[swz(nt0 * 8 + g, ks * 4 + t4)];
+                    const double b1 = Wt[swz(nt0 * 8 + 8 + g, ks * 4 + t4)];
+                    dmma_8x8x4(c00, c01, a, b0);
+                    dmma_8x8x4(c10, c11, a, b1);
+                }
+#ifndef TRL_SIMT_EMU
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_empty[s]);
+                if (tid == 0 && issued < ntile) { issue(issued); ++issued; }
+#endif
+            }
+            pipe_iter += (unsigned)ntile;
+            P[(mt * 8 + g) * kTip0Out + nt0 * 8 + 2 * t4] = c00;
+            P[(mt * 8 + g) * kTip0Out + nt0 * 8 + 2 * t4 + 1] = c01;
+            P[(mt * 8 + g) * kTip0Out + nt0 * 8 + 8 + 2 * t4] = c10;
+            P[(mt * 8 + g) * kTip0Out + nt0 * 8 + 8 + 2 * t4 + 1] = c11;
+            cluster.sync();
+            // ---------------- concat0 = [relu(sum of the partials in rank order + bias) | normalised character features]
+            for (int i = tid; i < kFcRows * kTip0Out; i += kFcThreads) {
+                const int r = i / kTip0Out, o = i - r * kTip0Out;
+                double acc = W.tip0_b[o];
+#pragma unroll
+                for (int q = 0; q < kFcCluster; ++q) acc += cluster.map_shared_rank(P, q)[i];
+                CAT[r * kCatStride + o] = acc > 0.0 ? acc : 0.0;
+            }
+            for (int i = tid; i < kFcRows * (kCatStride - kTip0Out); i += kFcThreads) {
+                const int r = i / (kCatStride - kTip0Out), c = i - r * (kCatStride - kTip0Out);
+                double v = 0.0;
+                if (r < rows && c < n_char) {
+                    const int env = B.pending_list[list * B.n + row0 + r];
+                    v = (B.poli_state[(size_t)env * B.S + 200 + c] + W.in_off[200 + c]) * W.in_scale[200 + c];
+                }
+                CAT[r * kCatStride + kTip0Out + c] = v;
+            }
+            cluster.sync();      // CAT complete here; every peer has finished reading this CTA's P
+            // ---------------- ip0: H[:, 32 rank .. 32 rank + 32) = relu(CAT * Wip^T + b); 16 C tiles, one per warp
+            {
+                const int mt2 = warp >> 2, nt2 = warp & 3;
+                double c0 = 0, c1 = 0;
+                const double* arow = CAT + (mt2 * 8 + g) * kCatStride + t4;
+                const double* brow = WIP + (nt2 * 8 + g) * kCatStride + t4;
+#pragma unroll 4
+                for (int ks = 0; ks < kCatStride / 4; ++ks) dmma_8x8x4(c0, c1, arow[ks * 4], brow[ks * 4]);
+                const int col = rank * 32 + nt2 * 8 + 2 * t4;
+                const double v0 = c0 + W.ip0_b[col], v1 = c1 + W.ip0_b[col + 1];
+                // every CTA needs the whole H: write the two values into all eight copies
+#pragma unroll
+                for (int q = 0; q < kFcCluster; ++q) {
+                    double* Hq = cluster.map_shared_rank(H, q);
+                    Hq[(mt2 * 8 + g) * kHStride + col] = v0 > 0.0 ? v0 : 0.0;
+                    Hq[(mt2 * 8 + g) * kHStride + col + 1] = v1 > 0.0 ? v1 : 0.0;
+                }
+            }
+            cluster.sync();
+            // ---------------- head hidden layers: CTA pair (2 hd, 2 hd + 1) owns head hd; this CTA computes 64 of its 128 hidden units.
+            // warp w: n tile w % 8 (of 8), m tiles 2 (w / 8) + {0, 1}; B fragments straight from L2 (each weight is used once per chunk)
+            const int hd = rank >> 1, half = rank & 1;
+            {
+                const int ntl = warp & 7, mt3 = (warp >> 3) * 2;
+                const double* wrow = W.h0_w[hd] + (size_t)(half * 64 + ntl * 8 + g) * kIp0Out + t4;
+                const double* a0 = H + (mt3 * 8 + g) * kHStride + t4;
+                const double* a1 = a0 + 8 * kHStride;
+                double c00h = 0, c01h = 0, c10h = 0, c11h = 0;
+#pragma unroll 8
+                for (int ks = 0; ks < kIp0Out / 4; ++ks) {
+                    const double b = wrow[ks * 4];
+                    dmma_8x8x4(c00h, c01h, a0[ks * 4], b);
+                    dmma_8x8x4(c10h, c11h, a1[ks * 4], b);
+                }
+                const int col = half * 64 + ntl * 8 + 2 * t4;
+                const double b0 = W.h0_b[hd][col], b1 = W.h0_b[hd][col + 1];
+                double* HHo = cluster.map_shared_rank(HH, rank & ~1);      // both halves land in the even CTA of the pair
+                double v;
+                v = c00h + b0; HHo[(mt3 * 8 + g) * kHHStride + col] = v > 0.0 ? v : 0.0;
+                v = c01h + b1; HHo[(mt3 * 8 + g) * kHHStride + col + 1] = v > 0.0 ? v : 0.0;
+                v = c10h + b0; HHo[(mt3 * 8 + 8 + g) * kHHStride + col] = v > 0.0 ? v : 0.0;
+                v = c11h + b1; HHo[(mt3 * 8 + 8 + g) * kHHStride + col + 1] = v > 0.0 ? v : 0.0;
+            }
+            cluster.sync();
+            // ---------------- output layers: the even CTA of a pair multiplies its head's [32 x 128] by [128 x nout] (n padded to 32) and
+            // un-normalises into rank 0's Y
+            if (half == 0) {
+                const int nout = hd == 0 ? m.n_frags : m.frag;
+                const int obase = hd == 0 ? 0 : m.n_frags + (hd - 1) * m.frag;
+                const int mt4 = warp >> 2, nt4 = warp & 3;
+                const int nrow = nt4 * 8 + g;                              // output unit this lane's B fragment belongs to
+                const double* wrow = W.h1_w[hd] + (size_t)min(nrow, nout - 1) * kHeadHidden + t4;
+                const double* arow = HH + (mt4 * 8 + g) * kHHStride + t4;
+                double c0 = 0, c1 = 0;
+#pragma unroll 8
+                for (int ks = 0; ks < kHeadHidden / 4; ++ks) {
+                    const double b = nrow < nout ? wrow[ks * 4] : 0.0;
+                    dmma_8x8x4(c0, c1, arow[ks * 4], b);
+                }
+                double* Y0 = cluster.map_shared_rank(Y, 0);
+                const int o = nt4 * 8 + 2 * t4;
+                if (o < nout) Y0[(mt4 * 8 + g) * kYStride + obase + o] = (c0 + W.h1_b[hd][o]) / W.out_scale[obase + o] - W.out_off[obase + o];
+                if (o + 1 < nout) Y0[(mt4 * 8 + g) * kYStride + obase + o + 1] = (c1 + W.h1_b[hd][o + 1]) / W.out_scale[obase + o + 1] - W.out_off[obase + o + 1];
+            }
+            cluster.sync();
+        }
+        // ---------------- the scalar decisions of this chunk, one lane each
+        if (rank == 0 && tid < rows) decide_one(B, ex, B.pending_list[list * B.n + row0 + tid], Y + tid * kYStride);
+        cluster.sync();      // Y / H / HH / the pipeline buffers are reused by the next chunk
+    }
+    // serial schedule: the last CTA to finish re-arms the list (in the overlapped schedule the catch-up launch, which still needs
+    // the count, does it)
+    if (rearm && threadIdx.x == 0) {
+        __threadfence();
+        int done = atomicAdd(done_count, 1);
+        if (done == (int)gridDim.x - 1) { B.pending_count[list] = 0; *done_count = 0; __threadfence(); }
+    }
+}
+
+
+size_t decide_fc_smem_bytes() { return (size_t)kFcSmemBytes; }
+cudaError_t configure_decide2_kernels() {
+    cudaError_t e = cudaFuncSetAttribute(trl_decide_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decide_smem_bytes());
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(trl_decide_fc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decide_fc_smem_bytes());
+}
+// conv stage for every pending decision (grid of 4-CTA clusters), then the batched FC stage + decisions (fc_clusters 8-CTA clusters)
+void launch_decide2(const Buffers& B, const NetWeights& W, const ExpSettings* ex, const FcMaps& maps, double* act2, int* done_count, int grid,
+                    int fc_clusters, int list, int rearm, cudaStream_t st) {
+    TRL_LAUNCH_CLUSTER(kClusterSize, trl_decide_conv_kernel, grid, kDecideThreads, decide_smem_bytes(), st, B, W, act2, list);
+    TRL_LAUNCH_CLUSTER(kFcCluster, trl_decide_fc_kernel, fc_clusters * kFcCluster, kFcThreads, decide_fc_smem_bytes(), st, B, W, ex, maps, done_count, list,
+                       rearm);
+}
+
+}  // namespace trl

@@ -9,6 +9,7 @@
 
 #include "scene_pack.h"
 #include "trl_types.h"
+#include "trl_fcmaps.h"
 
 struct trl_trainer;
 struct trl_comm;
@@ -23,7 +24,7 @@ struct trl_handle {
     trl::ExpSettings ex;                      // host copy; the kernels read the device copy d_ex
     trl::ExpSettings* d_ex = nullptr;
     trl::Buffers B;
-    trl::NetWeights W;
+    trl::NetWeights W{};
     std::vector<double*> net_blobs;      // 26 + 4 device arrays
     std::vector<int64_t> net_counts;
     int* done_count = nullptr;
@@ -33,6 +34,13 @@ struct trl_handle {
     bool overlap = true;                         // TRL_SERIAL_SCHEDULE=1 turns the overlapped schedule off
     int decide_grid = 288;   // CTAs of the decision launch: a multiple of its cluster size (create_common sizes it from the SM count)
     int num_update_steps = 20;
+    // batched decision path (trl_decide2.cuh): conv2 outputs of the pending decisions, the TMA descriptors over them and over the
+    // terr_ip0 weights (re-encoded whenever the weight pointer changes), number of FC-stage clusters
+    bool decide_v2 = true;                       // TRL_DECIDE_V1=1 selects the one-cluster-per-decision kernel (trl_decide.cuh)
+    double* act2 = nullptr;
+    trl::FcMaps fc_maps;
+    const double* fc_maps_w = nullptr;
+    int fc_clusters = 2;
     int64_t launches = 0;
     std::map<long long, cudaGraphExec_t> graphs;   // keyed by the bit pattern of dt
     bool use_graph = true;

@@ -16,6 +16,7 @@
 #include "scene_pack.h"
 #include "model_io.h"
 #include "trl_types.h"
+#include "trl_fcmaps.h"
 
 namespace trl {
 cudaError_t upload_model(const ModelConst& mc);
@@ -28,6 +29,10 @@ cudaError_t configure_decide_kernel();
 void launch_decide(const Buffers& B, const NetWeights& W, const ExpSettings* ex, int* done_count, int grid, int list, int rearm,
                    cudaStream_t st);
 void launch_stats(const Buffers& B, double* out, cudaStream_t st);
+size_t decide_fc_smem_bytes();
+cudaError_t configure_decide2_kernels();
+void launch_decide2(const Buffers& B, const NetWeights& W, const ExpSettings* ex, const FcMaps& maps, double* act2, int* done_count, int grid,
+                    int fc_clusters, int list, int rearm, cudaStream_t st);
 void launch_terrain(const Buffers& B, double lookahead, cudaStream_t st);
 }  // namespace trl
 namespace trl_cg {
@@ -62,7 +67,13 @@ static const char* kNetLayers[13] = {"terr_conv0", "terr_conv1", "terr_conv2", "
 
 // The kernels read the scene from __constant__ memory, of which there is one copy per process: a handle that is not the
 // current owner re-uploads its model (after draining the owner's work) before it launches anything.
+static int ensure_fc_maps(trl_handle* h);
+static int ensure_model_only(trl_handle* h);
 static int ensure_model(trl_handle* h) {
+    if (ensure_model_only(h)) return 1;
+    return ensure_fc_maps(h);
+}
+static int ensure_model_only(trl_handle* h) {
     // one process drives one GPU: __constant__ scene memory and the streams belong to the device of the handle
     // that was created first; a handle on another device is refused at creation (create_common)
     if (g_model_owner == h) return 0;
@@ -354,6 +365,57 @@ static int check_net_counts(const ModelConst& m, const int64_t* counts, const in
     return 0;
 }
 
+// ---- batched decision path: TMA descriptors over the terr_ip0 weights and the conv2-output scratch (trl_decide2.cuh)
+#ifndef TRL_SIMT_EMU
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn tensor_map_encoder() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+// [rows][5984] f64 row-major, box [box_rows][16 doubles = 128 B], 128-byte swizzle, rows past the end read as zero
+static int encode_rows_map(CUtensorMap* map, const double* base, uint64_t rows, uint32_t box_rows) {
+    EncodeTiledFn enc = tensor_map_encoder();
+    if (!enc) return fail("cuTensorMapEncodeTiled is not available from this driver");
+    if (((uintptr_t)base & 15u) != 0) return fail("TMA needs 16-byte aligned weights");
+    const cuuint64_t dims[2] = {5984, rows};
+    const cuuint64_t strides[1] = {5984 * 8};
+    const cuuint32_t box[2] = {16, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+    return 0;
+}
+#endif
+static int ensure_fc_maps(trl_handle* h) {
+    if (!h->decide_v2 || !h->mc.has_net || !h->act2 || !h->W.tip0_w) return 0;
+    if (h->fc_maps_w == h->W.tip0_w) return 0;
+    h->fc_maps.w_ptr = h->W.tip0_w;
+    h->fc_maps.a_ptr = h->act2;
+    h->fc_maps.a_rows = h->n;
+#ifndef TRL_SIMT_EMU
+    if (encode_rows_map(&h->fc_maps.w, h->W.tip0_w, 64, 64)) return 1;
+    if (encode_rows_map(&h->fc_maps.a, h->act2, (uint64_t)h->n, 32)) return 1;
+#endif
+    h->fc_maps_w = h->W.tip0_w;
+    return 0;
+}
+// the decision launch(es) of one env-step
+static void enqueue_decide(trl_handle* h, int list, int rearm, cudaStream_t st) {
+    if (h->decide_v2)
+        launch_decide2(h->B, h->W, h->d_ex, h->fc_maps, h->act2, h->done_count, h->decide_grid, h->fc_clusters, list, rearm, st);
+    else
+        launch_decide(h->B, h->W, h->d_ex, h->done_count, h->decide_grid, list, rearm, st);
+}
+static int num_decide_launches(const trl_handle* h) { return h->decide_v2 ? 2 : 1; }
+
 static void destroy_graphs(trl_handle* h);
 void trl_drop_graphs(trl_handle* h) { destroy_graphs(h); }
 static void destroy_graphs(trl_handle* h) {
@@ -374,17 +436,31 @@ static void destroy_graphs(trl_handle* h) {
 // S_i and C_i; S_{i+1} needs S_i and C_i.  Two pending lists alternate so that S_i / C_i can append to one while D_{i-1} / C_i
 // read the other.  Every env still advances by exactly one env-step per S/C pair, so results are identical to the serial
 // schedule (tests/test_gpu_scenarios.py::test_overlap_matches_serial).
-static void enqueue_update(trl_handle* h, double dt, bool overlap) {
+// optional recorder of a timeline (trl_update_timeline): an event pair around every launch, on the stream it is launched on
+struct Timeline {
+    std::vector<cudaEvent_t> beg, end;
+    std::vector<int> kind, idx;      // kind: 0 terrain, 1 step S_i, 2 decision D_i, 3 catch-up C_i
+    void open(cudaStream_t st, int k, int i) {
+        cudaEvent_t b, e;
+        cudaEventCreate(&b); cudaEventCreate(&e);
+        beg.push_back(b); end.push_back(e); kind.push_back(k); idx.push_back(i);
+        cudaEventRecord(b, st);
+    }
+    void close(cudaStream_t st) { cudaEventRecord(end.back(), st); }
+};
+static void enqueue_update(trl_handle* h, double dt, bool overlap, Timeline* tl = nullptr) {
     const int ns = h->num_update_steps;
     const double step = dt / ns;
     cudaStream_t A = h->stream, S = h->aux_stream;
-    launch_terrain(h->B, 0.5, A);
+#define TL_OPEN(st, k, i) do { if (tl) tl->open(st, k, i); } while (0)
+#define TL_CLOSE(st) do { if (tl) tl->close(st); } while (0)
+    TL_OPEN(A, 0, 0); launch_terrain(h->B, 0.5, A); TL_CLOSE(A);
     if (!overlap) {
         for (int i = 0; i < ns; ++i) {
-            launch_step(h->B, step, i == 0 ? 2 : 3, 0, A);
-            launch_decide(h->B, h->W, h->d_ex, h->done_count, h->decide_grid, 0, 1, A);
+            TL_OPEN(A, 1, i); launch_step(h->B, step, i == 0 ? 2 : 3, 0, A); TL_CLOSE(A);
+            TL_OPEN(A, 2, i); enqueue_decide(h, 0, 1, A); TL_CLOSE(A);
         }
-        launch_step(h->B, step, 1 | 4, 0, A);
+        TL_OPEN(A, 1, ns); launch_step(h->B, step, 1 | 4, 0, A); TL_CLOSE(A);
         return;
     }
     if ((int)h->fork_events.size() < 2 * ns + 2) {
@@ -394,27 +470,29 @@ static void enqueue_update(trl_handle* h, double dt, bool overlap) {
     }
     cudaEvent_t* ev_s = h->fork_events.data();            // ev_s[i]: S_i done
     cudaEvent_t* ev_c = h->fork_events.data() + ns + 1;   // ev_c[i]: C_i (and everything before it on the side stream) done
-    launch_step(h->B, step, 2, /*app*/ 0, A);
+    TL_OPEN(A, 1, 0); launch_step(h->B, step, 2, /*app*/ 0, A); TL_CLOSE(A);
     cudaEventRecord(ev_s[0], A);
     for (int i = 1; i < ns; ++i) {
         const int app = i & 1, prev = (i - 1) & 1, lists = app | (prev << 1);
         cudaStreamWaitEvent(S, ev_s[i - 1], 0);
-        launch_decide(h->B, h->W, h->d_ex, h->done_count, h->decide_grid, prev, 0, S);
-        trl_cg::launch_step(h->B, step, 1 | 2 | 16, lists, S);
+        TL_OPEN(S, 2, i - 1); enqueue_decide(h, prev, 0, S); TL_CLOSE(S);
+        TL_OPEN(S, 3, i); trl_cg::launch_step(h->B, step, 1 | 2 | 16, lists, S); TL_CLOSE(S);
         cudaEventRecord(ev_c[i], S);
         if (i >= 2) cudaStreamWaitEvent(A, ev_c[i - 1], 0);
-        launch_step(h->B, step, 1 | 2 | 8, lists, A);
+        TL_OPEN(A, 1, i); launch_step(h->B, step, 1 | 2 | 8, lists, A); TL_CLOSE(A);
         cudaEventRecord(ev_s[i], A);
     }
     cudaStreamWaitEvent(S, ev_s[ns - 1], 0);
-    launch_decide(h->B, h->W, h->d_ex, h->done_count, h->decide_grid, (ns - 1) & 1, 1, S);
+    TL_OPEN(S, 2, ns - 1); enqueue_decide(h, (ns - 1) & 1, 1, S); TL_CLOSE(S);
     cudaEventRecord(ev_c[ns], S);
     cudaStreamWaitEvent(A, ev_c[ns], 0);
-    launch_step(h->B, step, 1 | 4, 0, A);
+    TL_OPEN(A, 1, ns); launch_step(h->B, step, 1 | 4, 0, A); TL_CLOSE(A);
+#undef TL_OPEN
+#undef TL_CLOSE
 }
 static int update_launches(const trl_handle* h, bool overlap) {
-    const int ns = h->num_update_steps;
-    return overlap ? 3 * ns + 1 : 2 * ns + 2;    // terrain + S_0..S_{ns-1} + D_0..D_{ns-1} + S_end (+ C_1..C_{ns-1})
+    const int ns = h->num_update_steps, d = num_decide_launches(h);
+    return overlap ? (2 + d) * ns : (1 + d) * ns + 2;    // terrain + S_0..S_{ns-1} + D_0..D_{ns-1} + S_end (+ C_1..C_{ns-1})
 }
 
 extern "C" {
@@ -494,6 +572,11 @@ static trl_handle* create_common(trl_handle* h, int num_envs, int device, int mo
     if (ensure_model(h)) return bail("upload_model failed");
     if (!ck(configure_step_kernels(), "configure_step_kernels")) return bail("");
     if (!ck(configure_decide_kernel(), "configure_decide_kernel")) return bail("");
+    if (!ck(configure_decide2_kernels(), "configure_decide2_kernels")) return bail("");
+    {
+        const char* v1 = std::getenv("TRL_DECIDE_V1");
+        h->decide_v2 = !(v1 && v1[0] == '1');
+    }
     Buffers& B = h->B;
     std::memset(&B, 0, sizeof(B));
     const size_t n = (size_t)num_envs;
@@ -501,7 +584,9 @@ static trl_handle* create_common(trl_handle* h, int num_envs, int device, int mo
     B.S = kNumGroundSamples + 4 * h->mc.nj - 1;
     B.A = 1 + h->mc.n_opt;
     const int A = 1 + h->mc.n_opt;
-    B.tuple_cap = std::max(4096, num_envs);   // >= one tuple per env per outer update (a cycle lasts >> 20 env-steps)
+    // an env finishes at most one cycle per outer update; twice that leaves room for the bursts of a synchronised start while a
+    // fixed-size exchange block (trl_gather_tuples) drains the queue
+    B.tuple_cap = std::max(4096, 2 * num_envs);
     B.dist_cap = std::max(65536, 16 * num_envs);
     bool ok = ck(dalloc(h, &B.d, (size_t)D_NUM_FIELDS * n), "alloc d") && ck(dalloc(h, &B.i, (size_t)I_NUM_FIELDS * n), "alloc i") &&
               ck(dalloc(h, &B.terrain, n * 2 * kTerrainCap), "alloc terrain") && ck(dalloc(h, &B.poli_state, n * B.S), "alloc poli") &&
@@ -513,7 +598,8 @@ static trl_handle* create_common(trl_handle* h, int num_envs, int device, int mo
               ck(dalloc(h, &B.tuple_flags, (size_t)B.tuple_cap), "alloc tf") && ck(dalloc(h, &B.tuple_env, (size_t)B.tuple_cap), "alloc te") &&
               ck(dalloc(h, &B.tuple_count, 1), "alloc tc") && ck(dalloc(h, &B.dist_log, (size_t)B.dist_cap), "alloc dl") &&
               ck(dalloc(h, &B.dist_env, (size_t)B.dist_cap), "alloc de") && ck(dalloc(h, &B.dist_count, 1), "alloc dc") &&
-              ck(dalloc(h, &h->done_count, 1), "alloc done") && ck(dalloc(h, &h->d_ex, 1), "alloc ex");
+              ck(dalloc(h, &h->done_count, 1), "alloc done") && ck(dalloc(h, &h->d_ex, 1), "alloc ex") &&
+              (!h->mc.has_net || ck(dalloc(h, &h->act2, n * (size_t)5984), "alloc act2"));
     if (ok) ok = ck(cudaMemcpy(h->d_ex, &h->ex, sizeof(ExpSettings), cudaMemcpyHostToDevice), "upload ex");
     if (!ok) return bail("");
     if (h->mc.has_net) {
@@ -637,9 +723,9 @@ int trl_env_step(trl_handle* h, double step) {
     if (!h) return fail("trl_env_step: null handle");
     if (ensure_model(h)) return fail("model upload failed");
     launch_step(h->B, step, 2, 0, h->stream);
-    launch_decide(h->B, h->W, h->d_ex, h->done_count, h->decide_grid, 0, 1, h->stream);
+    enqueue_decide(h, 0, 1, h->stream);
     launch_step(h->B, step, 1, 0, h->stream);
-    h->launches += 3;
+    h->launches += 2 + num_decide_launches(h);
     CK(cudaGetLastError());
     return 0;
 }
@@ -1105,7 +1191,7 @@ int trl_debug_time_decide(trl_handle* h, int n_pending, int iters, double* ms_av
         CK(cudaMemcpyAsync(h->B.pending_list, ids.data(), (size_t)n_pending * 4, cudaMemcpyHostToDevice, h->stream));
         CK(cudaMemcpyAsync(h->B.pending_count, &n_pending, 4, cudaMemcpyHostToDevice, h->stream));
         CK(cudaEventRecord(e0, h->stream));
-        launch_decide(h->B, h->W, h->d_ex, h->done_count, h->decide_grid, 0, 1, h->stream);
+        enqueue_decide(h, 0, 1, h->stream);
         CK(cudaEventRecord(e1, h->stream));
         CK(cudaEventSynchronize(e1));
         float ms = 0;
@@ -1201,6 +1287,32 @@ int trl_bench_updates(trl_handle* h, double dt, int k, int flush_l2, double* ms_
 
 // One outer update launched kernel by kernel with an event pair around every launch: returns the summed device time
 // of the step kernel launches and of the decision kernel launches (roofline numerator's denominator).
+// One outer update in the schedule trl_update uses (overlapped unless TRL_SERIAL_SCHEDULE=1), launched eagerly with an event pair
+// around every launch on its own stream: out[4 * k + {0,1,2,3}] = {kind (0 terrain, 1 step, 2 decision, 3 catch-up), index, start
+// ms, end ms} relative to the first launch.  Shows what bounds the update: the step launches or the decision -> catch-up chain.
+int trl_update_timeline(trl_handle* h, double dt, double* out, int cap, int* n_out) {
+    if (!h) return fail("trl_update_timeline: null handle");
+    if (ensure_model(h)) return fail("model upload failed");
+    Timeline tl;
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaStreamSynchronize(h->aux_stream));
+    enqueue_update(h, dt, h->overlap, &tl);
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaStreamSynchronize(h->aux_stream));
+    CK(cudaGetLastError());
+    h->launches += update_launches(h, h->overlap);
+    const int n = (int)tl.beg.size();
+    for (int k = 0; k < n; ++k) {
+        float a = 0, b = 0;
+        cudaEventElapsedTime(&a, tl.beg[0], tl.beg[k]);
+        cudaEventElapsedTime(&b, tl.beg[0], tl.end[k]);
+        if (k < cap) { out[4 * k] = tl.kind[k]; out[4 * k + 1] = tl.idx[k]; out[4 * k + 2] = a; out[4 * k + 3] = b; }
+        cudaEventDestroy(tl.beg[k]); cudaEventDestroy(tl.end[k]);
+    }
+    if (n_out) *n_out = std::min(n, cap);
+    return 0;
+}
+
 static int update_timed_impl(trl_handle* h, double dt, double* step_ms, int* step_launches, double* decide_ms, int* decide_launches,
                              double* per_step, double* per_decide);
 int trl_update_timed(trl_handle* h, double dt, double* step_ms, int* step_launches, double* decide_ms, int* decide_launches) {
@@ -1226,7 +1338,7 @@ static int update_timed_impl(trl_handle* h, double dt, double* step_ms, int* ste
         launch_step(h->B, step, i == 0 ? 2 : 3, 0, h->stream);
         CK(cudaEventRecord(ev[k++], h->stream));
         CK(cudaEventRecord(ev[k++], h->stream));
-        launch_decide(h->B, h->W, h->d_ex, h->done_count, h->decide_grid, 0, 1, h->stream);
+        enqueue_decide(h, 0, 1, h->stream);
         CK(cudaEventRecord(ev[k++], h->stream));
     }
     CK(cudaEventRecord(ev[k++], h->stream));
@@ -1249,7 +1361,7 @@ static int update_timed_impl(trl_handle* h, double dt, double* step_ms, int* ste
     sm += a;
     if (per_step) per_step[ns] = a;
     for (auto& e : ev) cudaEventDestroy(e);
-    h->launches += 2 * ns + 2;
+    h->launches += (1 + num_decide_launches(h)) * ns + 2;
     if (step_ms) *step_ms = sm;
     if (step_launches) *step_launches = ns + 1;
     if (decide_ms) *decide_ms = dm;

@@ -1464,4 +1464,5 @@ void launch_reset(const Buffers& B, const uint64_t* seeds, const int* env_ids, i
 
 #ifndef TRL_CG_VARIANT
 #include "trl_decide.cuh"
+#include "trl_decide2.cuh"
 #endif

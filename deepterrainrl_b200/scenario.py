@@ -107,7 +107,7 @@ EXPORTS = [
     "trl_set_explore", "trl_set_phys_params", "trl_set_weights", "trl_sizes", "trl_num_tuples", "trl_get_tuples",
     "trl_get_tuples_f64", "trl_reset_tuples", "trl_eval_stats", "trl_dist_log", "trl_reset_avg_dist", "trl_get_state", "trl_set_state",
     "trl_get_state_all", "trl_get_ctrl", "trl_get_poli_state", "trl_get_net_out", "trl_get_terrain",
-    "trl_kernel_launches", "trl_last_error", "trl_bench_updates", "trl_update_timed", "trl_device_tuple_block", "trl_snapshot", "trl_snapshot_wait", "trl_update_timed_detail", "trl_debug_time_decide",
+    "trl_kernel_launches", "trl_last_error", "trl_bench_updates", "trl_update_timed", "trl_device_tuple_block", "trl_snapshot", "trl_snapshot_wait", "trl_update_timed_detail", "trl_update_timeline", "trl_debug_time_decide",
     "trl_load_model", "trl_output_model", "trl_write_model", "trl_get_output_offset_scale", "trl_pack_output_offset_scale",
     "trl_set_terrain_lerp", "trl_train_schedule", "trl_trainer_create", "trl_trainer_destroy", "trl_trainer_init_fresh", "trl_trainer_add_from_scene", "trl_trainer_add_tuples", "trl_trainer_add_device", "trl_trainer_train", "trl_train_run", "trl_train_run_timed",
     "trl_trainer_counters", "trl_trainer_num_params", "trl_trainer_launches", "trl_trainer_get", "trl_trainer_set_theta", "trl_trainer_list", "trl_trainer_rows",
@@ -299,6 +299,14 @@ class BatchedScenario:
         ps = np.zeros(num_update_steps + 1); pd = np.zeros(num_update_steps)
         self._ck(self.L.trl_update_timed_detail(self.h, C.c_double(dt), _p(ps), _p(pd)))
         return ps, pd
+
+    def UpdateTimeline(self, dt=1.0 / 30.0):
+        """one update in Update()'s own schedule, every launch timed on its stream: list of (kind, index, start_ms, end_ms);
+        kind 0 terrain, 1 step, 2 decision, 3 catch-up"""
+        out = np.zeros(4 * 128)
+        n = C.c_int(0)
+        self._ck(self.L.trl_update_timeline(self.h, C.c_double(dt), _p(out), 128, C.byref(n)))
+        return [(int(out[4 * k]), int(out[4 * k + 1]), float(out[4 * k + 2]), float(out[4 * k + 3])) for k in range(n.value)]
 
     def UpdateTimed(self, dt=1.0 / 30.0):
         """one outer update with per-launch events: (step_ms, step_launches, decide_ms, decide_launches)."""

@@ -113,6 +113,9 @@ int trl_device_tuple_block(trl_handle* h, void** rows_f64, void** flags_u32, voi
 int trl_bench_updates(trl_handle* h, double dt, int k, int flush_l2, double* ms_total);
 int trl_update_timed(trl_handle* h, double dt, double* step_ms, int* step_launches, double* decide_ms, int* decide_launches);
 int trl_update_timed_detail(trl_handle* h, double dt, double* per_step_ms, double* per_decide_ms);
+/* one update in trl_update's own (overlapped) schedule with an event pair around every launch: out[4k..4k+3] = {kind (0 terrain, 1 step,
+ * 2 decision, 3 catch-up), index, start ms, end ms} */
+int trl_update_timeline(trl_handle* h, double dt, double* out4, int cap, int* n);
 
 int trl_debug_time_decide(trl_handle* h, int n_pending, int iters, double* ms_avg);
 

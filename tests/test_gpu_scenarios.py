@@ -182,7 +182,7 @@ def test_overlap_matches_serial(assets, monkeypatch):
     l0s, l0o = ser.KernelLaunches(), ovl.KernelLaunches()
     for _ in range(45):
         ser.Update(1.0 / 30.0); ovl.Update(1.0 / 30.0)
-    assert ser.KernelLaunches() - l0s == 45 * 42 and ovl.KernelLaunches() - l0o == 45 * 61
+    assert ser.KernelLaunches() - l0s == 45 * 62 and ovl.KernelLaunches() - l0o == 45 * 80   # terrain + 21 steps + 20 x (conv + FC) decision launches (+ 19 catch-ups)
     qa, qda = ser.GetStateAll(); qb, qdb = ovl.GetStateAll()
     np.testing.assert_array_equal(qa, qb)
     np.testing.assert_array_equal(qda, qdb)
