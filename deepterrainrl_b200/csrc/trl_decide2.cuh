@@ -95,62 +95,86 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, v
 #endif
 
 // ------------------------------------------------------------------------------------------------ conv stage
-// trl_decide.cuh's conv0 / conv1 / conv2 for the decision at pending index idx; the flattened conv2 output goes to act2[idx][5984]
-__device__ void conv_stage_cluster(cg::cluster_group& cluster, const NetWeights& W, const double* __restrict__ x_in, double* sh, int n_char,
-                                   double* __restrict__ out_row) {
-    const int tid = threadIdx.x;
-    const int rank = (int)cluster.block_rank();
-    const int n_in = 200 + n_char;
-    double* X = sh + kShX;
-    double* A0 = sh + kShA0;
-    double* A1 = sh + kShA1;
-    double* W0s = sh + kShW0;
-    double* W1s = sh + kShW1;
-    double* W2s = sh + kShW2;
-    for (int i = tid; i < n_in; i += kDecideThreads) X[i] = (x_in[i] + W.in_off[i]) * W.in_scale[i];
-    for (int i = tid; i < kConv0Out * kConv0K; i += kDecideThreads) W0s[i] = W.conv0_w[i];
-    for (int i = tid; i < kConv0Out; i += kDecideThreads) W0s[kConv0Out * kConv0K + i] = W.conv0_b[i];
-    for (int i = tid; i < kC1Slice * kConv0Out * kConv1K; i += kDecideThreads) W1s[i] = W.conv1_w[rank * kC1Slice * kConv0Out * kConv1K + i];
-    for (int i = tid; i < kC2Slice * kConv1Out * kConv2K; i += kDecideThreads) W2s[i] = W.conv2_w[rank * kC2Slice * kConv1Out * kConv2K + i];
-    __syncthreads();
-    for (int idx = tid; idx < kConv0Out * kW0; idx += kDecideThreads) {
-        int o = idx / kW0, t = idx - o * kW0;
-        double acc = W0s[kConv0Out * kConv0K + o];
-#pragma unroll
-        for (int k = 0; k < kConv0K; ++k) acc += W0s[o * kConv0K + k] * X[t + k];
-        A0[idx] = acc > 0.0 ? acc : 0.0;
-    }
-    __syncthreads();
-    // conv1: this CTA's output channels, kConvTile adjacent positions per thread (activations and weights of an input channel are
-    // loaded once for tile x K multiply-adds); 4 accumulators by c & 3, k inner -- the summation order of trl_decide.cuh
-    {
-        constexpr int nt = (kW1 + kConvTile - 1) / kConvTile;
-        for (int item = tid; item < kC1Slice * nt; item += kDecideThreads) {
-            const int ol = item / nt, t0 = (item - ol * nt) * kConvTile, o = rank * kC1Slice + ol;
-            const double* w = W1s + ol * kConv0Out * kConv1K;
-            double acc[kConvTile][4];
-#pragma unroll
-            for (int j = 0; j < kConvTile; ++j) { acc[j][0] = W.conv1_b[o]; acc[j][1] = 0.0; acc[j][2] = 0.0; acc[j][3] = 0.0; }
-#pragma unroll
-            for (int c = 0; c < kConv0Out; ++c) {
-                const double* a = A0 + c * kW0;
-                double av[kConvTile + kConv1K - 1];
-#pragma unroll
-                for (int i = 0; i < kConvTile + kConv1K - 1; ++i) av[i] = a[min(t0 + i, kW0 - 1)];
-#pragma unroll
-                for (int k = 0; k < kConv1K; ++k) {
-                    const double wk = w[c * kConv1K + k];
-#pragma unroll
-                    for (int j = 0; j < kConvTile; ++j) acc[j][c & 3] += wk * av[j + k];
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < kConvTile; ++j) {
-                const double v = (acc[j][0] + acc[j][1]) + (acc[j][2] + acc[j][3]);
-                if (t0 + j < kW1) A1[o * kW1 + t0 + j] = v > 0.0 ? v : 0.0;
-            }
+// The three terrain convolutions of ONE decision on a 4-CTA cluster, every layer as an implicit-im2col GEMM on DMMA:
+//   C[t][o] = sum over (c, k) of act[c][t + k] * w[o][c][k]      rows = output positions, columns = output channels
+// A fragments come straight from the activation rows in shared memory (lane (g, t4) reads act[c][t0 + g + t4]: neighbouring lanes
+// read neighbouring or identical words), B fragments from a padded copy of the weights (row stride = 32 B mod 128 B).  conv1 / conv2
+// have 4 taps = exactly one k-step per input channel.  Each CTA computes conv0 in full and its own 8 output channels of conv1 /
+// conv2; the conv1 slices are exchanged through DSMEM, the conv2 slice goes to row idx of the FC stage's input matrix.
+constexpr int kCvX = 0;                                    // 283 (+pad) normalised input
+constexpr int kCvA0 = 288;                                 // conv0 output [16][193]
+constexpr int kCvA1 = kCvA0 + kConv0Out * kW0 + 8;         // conv1 output [32][190] (own slice computed, rest gathered)
+constexpr int kCvW0 = kCvA1 + kConv1Out * kW1 + 8;         // conv0 weights [16][12]  (8 taps + pad)
+constexpr int kCvW1 = kCvW0 + kConv0Out * 12;              // conv1 weight slice [8][68]   (16 x 4 + pad)
+constexpr int kCvW2 = kCvW1 + kC1Slice * 68;               // conv2 weight slice [8][132]  (32 x 4 + pad)
+constexpr int kConvSmemDoubles = kCvW2 + kC2Slice * 132;
+static_assert(kC1Slice == 8 && kC2Slice == 8, "the DMMA conv stage assumes 8 output channels (one n tile) per CTA");
+
+// 4-tap convolution layer slice: out[o][t] = relu(b[o] + sum_c sum_k act[c][t + k] w[o][c][k]) for this CTA's 8 channels
+template <int CIN, int WIN, int WOUT, int WSTRIDE>
+__device__ __forceinline__ void conv4_dmma(const double* __restrict__ act, const double* __restrict__ ws, const double* __restrict__ bias8,
+                                           double* __restrict__ out, int out_stride) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t4 = lane & 3;
+    constexpr int nmt = (WOUT + 7) / 8, nwarp = kDecideThreads / 32;
+    const double b0 = bias8[2 * t4], b1 = bias8[2 * t4 + 1];
+    const double* brow = ws + g * WSTRIDE + t4;
+    for (int mt = warp; mt < nmt; mt += 2 * nwarp) {
+        // two row tiles per pass share the B fragment
+        const int mt2 = mt + nwarp;
+        const bool two = mt2 < nmt;
+        const double* a0p = act + min(mt * 8 + g, WOUT - 1) + t4;
+        const double* a1p = act + min((two ? mt2 : mt) * 8 + g, WOUT - 1) + t4;
+        double c00 = b0, c01 = b1, c10 = b0, c11 = b1;
+#pragma unroll 8
+        for (int c = 0; c < CIN; ++c) {
+            const double b = brow[4 * c];
+            dmma_8x8x4(c00, c01, a0p[c * WIN], b);
+            dmma_8x8x4(c10, c11, a1p[c * WIN], b);
+        }
+        const int ta = mt * 8 + g, tb = mt2 * 8 + g;
+        if (ta < WOUT) {
+            out[(2 * t4) * out_stride + ta] = c00 > 0.0 ? c00 : 0.0;
+            out[(2 * t4 + 1) * out_stride + ta] = c01 > 0.0 ? c01 : 0.0;
+        }
+        if (two && tb < WOUT) {
+            out[(2 * t4) * out_stride + tb] = c10 > 0.0 ? c10 : 0.0;
+            out[(2 * t4 + 1) * out_stride + tb] = c11 > 0.0 ? c11 : 0.0;
         }
     }
+}
+
+__device__ void conv_stage_cluster(cg::cluster_group& cluster, const NetWeights& W, const double* __restrict__ x_in, double* sh, int n_char,
+                                   double* __restrict__ out_row) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t4 = lane & 3;
+    const int rank = (int)cluster.block_rank();
+    const int n_in = 200 + n_char;
+    double* X = sh + kCvX;
+    double* A0 = sh + kCvA0;
+    double* A1 = sh + kCvA1;
+    double* W0s = sh + kCvW0;
+    double* W1s = sh + kCvW1;
+    double* W2s = sh + kCvW2;
+    for (int i = tid; i < n_in; i += kDecideThreads) X[i] = (x_in[i] + W.in_off[i]) * W.in_scale[i];
+    for (int i = tid; i < kConv0Out * kConv0K; i += kDecideThreads) W0s[(i >> 3) * 12 + (i & 7)] = W.conv0_w[i];
+    for (int i = tid; i < kC1Slice * 64; i += kDecideThreads) W1s[(i >> 6) * 68 + (i & 63)] = W.conv1_w[rank * kC1Slice * 64 + i];
+    for (int i = tid; i < kC2Slice * 128; i += kDecideThreads) W2s[(i >> 7) * 132 + (i & 127)] = W.conv2_w[rank * kC2Slice * 128 + i];
+    __syncthreads();
+    // conv0: 1 -> 16 channels, 8 taps (two k-steps), 25 x 2 C tiles
+    for (int item = warp; item < ((kW0 + 7) / 8) * 2; item += kDecideThreads / 32) {
+        const int mt = item >> 1, nt = item & 1;
+        const double* ap = X + min(mt * 8 + g, kW0 - 1) + t4;
+        const double* bp = W0s + (nt * 8 + g) * 12 + t4;
+        double c0 = W.conv0_b[nt * 8 + 2 * t4], c1 = W.conv0_b[nt * 8 + 2 * t4 + 1];
+        dmma_8x8x4(c0, c1, ap[0], bp[0]);
+        dmma_8x8x4(c0, c1, ap[4], bp[4]);
+        const int t = mt * 8 + g;
+        if (t < kW0) {
+            A0[(nt * 8 + 2 * t4) * kW0 + t] = c0 > 0.0 ? c0 : 0.0;
+            A0[(nt * 8 + 2 * t4 + 1) * kW0 + t] = c1 > 0.0 ? c1 : 0.0;
+        }
+    }
+    __syncthreads();
+    conv4_dmma<kConv0Out, kW0, kW1, 68>(A0, W1s, W.conv1_b + rank * kC1Slice, A1 + rank * kC1Slice * kW1, kW1);
     cluster.sync();
     for (int r = 1; r < kClusterSize; ++r) {
         int src = (rank + r) % kClusterSize;
@@ -161,39 +185,11 @@ __device__ void conv_stage_cluster(cg::cluster_group& cluster, const NetWeights&
         }
     }
     __syncthreads();
-    {
-        constexpr int nt = (kW2 + kConvTile - 1) / kConvTile;
-        double* out = out_row + (size_t)rank * kC2Slice * kW2;
-        for (int item = tid; item < kC2Slice * nt; item += kDecideThreads) {
-            const int ol = item / nt, t0 = (item - ol * nt) * kConvTile, o = rank * kC2Slice + ol;
-            const double* w = W2s + ol * kConv1Out * kConv2K;
-            double acc[kConvTile][4];
-#pragma unroll
-            for (int j = 0; j < kConvTile; ++j) { acc[j][0] = W.conv2_b[o]; acc[j][1] = 0.0; acc[j][2] = 0.0; acc[j][3] = 0.0; }
-#pragma unroll 8
-            for (int c = 0; c < kConv1Out; ++c) {
-                const double* a = A1 + c * kW1;
-                double av[kConvTile + kConv2K - 1];
-#pragma unroll
-                for (int i = 0; i < kConvTile + kConv2K - 1; ++i) av[i] = a[min(t0 + i, kW1 - 1)];
-#pragma unroll
-                for (int k = 0; k < kConv2K; ++k) {
-                    const double wk = w[c * kConv2K + k];
-#pragma unroll
-                    for (int j = 0; j < kConvTile; ++j) acc[j][c & 3] += wk * av[j + k];
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < kConvTile; ++j) {
-                const double v = (acc[j][0] + acc[j][1]) + (acc[j][2] + acc[j][3]);
-                if (t0 + j < kW2) out[ol * kW2 + t0 + j] = v > 0.0 ? v : 0.0;
-            }
-        }
-    }
+    conv4_dmma<kConv1Out, kW1, kW2, 132>(A1, W2s, W.conv2_b + rank * kC2Slice, out_row + (size_t)rank * kC2Slice * kW2, kW2);
     cluster.sync();   // peers read this CTA's A1 slice until here; the next decision overwrites it
 }
 
-__global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kDecideThreads, TRL_DECIDE_MIN_BLOCKS)
+__global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kDecideThreads, 1)
 trl_decide_conv_kernel(Buffers B, NetWeights W, double* __restrict__ act2, int list) {
     TRL_DYN_SHARED(double, sh);
     cg::cluster_group cluster = cg::this_cluster();
@@ -294,6 +290,17 @@ trl_decide_fc_kernel(Buffers B, NetWeights W, const ExpSettings* __restrict__ ex
     unsigned long long* bar_full = (unsigned long long*)(fc_smem + kFcOffBar);
     unsigned long long* bar_empty = bar_full + kFcStages;
     const int nchunks = (count + kFcRows - 1) / kFcRows;
+    int prof_n = 0;
+    auto stamp = [&]() {
+#ifndef TRL_SIMT_EMU
+        if (maps.prof && blockIdx.x == 0 && tid == 0 && prof_n < 16) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            maps.prof[prof_n++] = t;
+        }
+#endif
+    };
+    stamp();     // 0: kernel entry
 
     if (m.has_net && cid < nchunks) {
         // ip0 weight slice of this CTA (32 output columns x ncat, zero-padded to kCatStride): resident for the whole launch
@@ -310,6 +317,7 @@ trl_decide_fc_kernel(Buffers B, NetWeights W, const ExpSettings* __restrict__ ex
 #endif
         __syncthreads();
     }
+    stamp();     // 1: ip0 weights staged, barriers initialised
     // k tiles of terr_ip0 this CTA multiplies
     const int kt0 = (kNumKTiles * rank) / kFcCluster, kt1 = (kNumKTiles * (rank + 1)) / kFcCluster;
     unsigned pipe_iter = 0;      // tiles issued / consumed so far over all chunks (stage = iter % kFcStages, parity from iter / kFcStages)
@@ -379,7 +387,9 @@ trl_decide_fc_kernel(Buffers B, NetWeights W, const ExpSettings* __restrict__ ex
             P[(mt * 8 + g) * kTip0Out + nt0 * 8 + 2 * t4 + 1] = c01;
             P[(mt * 8 + g) * kTip0Out + nt0 * 8 + 8 + 2 * t4] = c10;
             P[(mt * 8 + g) * kTip0Out + nt0 * 8 + 8 + 2 * t4 + 1] = c11;
+            stamp();     // 2: terr_ip0 tiles consumed
             cluster.sync();
+            stamp();     // 3
             // ---------------- concat0 = [relu(sum of the partials in rank order + bias) | normalised character features]
             for (int i = tid; i < kFcRows * kTip0Out; i += kFcThreads) {
                 const int r = i / kTip0Out, o = i - r * kTip0Out;
@@ -397,7 +407,9 @@ trl_decide_fc_kernel(Buffers B, NetWeights W, const ExpSettings* __restrict__ ex
                 }
                 CAT[r * kCatStride + kTip0Out + c] = v;
             }
+            stamp();     // 4: concat0 built
             cluster.sync();      // CAT complete here; every peer has finished reading this CTA's P
+            stamp();     // 5
             // ---------------- ip0: H[:, 32 rank .. 32 rank + 32) = relu(CAT * Wip^T + b); 16 C tiles, one per warp
             {
                 const int mt2 = warp >> 2, nt2 = warp & 3;
@@ -416,7 +428,9 @@ trl_decide_fc_kernel(Buffers B, NetWeights W, const ExpSettings* __restrict__ ex
                     Hq[(mt2 * 8 + g) * kHStride + col + 1] = v1 > 0.0 ? v1 : 0.0;
                 }
             }
+            stamp();     // 6: ip0 done, H scattered
             cluster.sync();
+            stamp();     // 7
             // ---------------- head hidden layers: CTA pair (2 hd, 2 hd + 1) owns head hd; this CTA computes 64 of its 128 hidden units.
             // warp w: n tile w % 8 (of 8), m tiles 2 (w / 8) + {0, 1}; B fragments straight from L2 (each weight is used once per chunk)
             const int hd = rank >> 1, half = rank & 1;
@@ -441,7 +455,9 @@ trl_decide_fc_kernel(Buffers B, NetWeights W, const ExpSettings* __restrict__ ex
                 v = c10h + b0; HHo[(mt3 * 8 + 8 + g) * kHHStride + col] = v > 0.0 ? v : 0.0;
                 v = c11h + b1; HHo[(mt3 * 8 + 8 + g) * kHHStride + col + 1] = v > 0.0 ? v : 0.0;
             }
+            stamp();     // 8: head hidden layers done
             cluster.sync();
+            stamp();     // 9
             // ---------------- output layers: the even CTA of a pair multiplies its head's [32 x 128] by [128 x nout] (n padded to 32) and
             // un-normalises into rank 0's Y
             if (half == 0) {
@@ -462,11 +478,15 @@ trl_decide_fc_kernel(Buffers B, NetWeights W, const ExpSettings* __restrict__ ex
                 if (o < nout) Y0[(mt4 * 8 + g) * kYStride + obase + o] = (c0 + W.h1_b[hd][o]) / W.out_scale[obase + o] - W.out_off[obase + o];
                 if (o + 1 < nout) Y0[(mt4 * 8 + g) * kYStride + obase + o + 1] = (c1 + W.h1_b[hd][o + 1]) / W.out_scale[obase + o + 1] - W.out_off[obase + o + 1];
             }
+            stamp();     // 10: output layers done
             cluster.sync();
+            stamp();     // 11
         }
         // ---------------- the scalar decisions of this chunk, one lane each
         if (rank == 0 && tid < rows) decide_one(B, ex, B.pending_list[list * B.n + row0 + tid], Y + tid * kYStride);
+        stamp();         // 12: decisions applied
         cluster.sync();      // Y / H / HH / the pipeline buffers are reused by the next chunk
+        stamp();         // 13
     }
     // serial schedule: the last CTA to finish re-arms the list (in the overlapped schedule the catch-up launch, which still needs
     // the count, does it)
@@ -480,16 +500,17 @@ trl_decide_fc_kernel(Buffers B, NetWeights W, const ExpSettings* __restrict__ ex
 
 size_t decide_fc_smem_bytes() { return (size_t)kFcSmemBytes; }
 cudaError_t configure_decide2_kernels() {
-    cudaError_t e = cudaFuncSetAttribute(trl_decide_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decide_smem_bytes());
+    cudaError_t e = cudaFuncSetAttribute(trl_decide_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmemDoubles * 8);
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(trl_decide_fc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decide_fc_smem_bytes());
 }
 // conv stage for every pending decision (grid of 4-CTA clusters), then the batched FC stage + decisions (fc_clusters 8-CTA clusters)
 void launch_decide2(const Buffers& B, const NetWeights& W, const ExpSettings* ex, const FcMaps& maps, double* act2, int* done_count, int grid,
-                    int fc_clusters, int list, int rearm, cudaStream_t st) {
-    TRL_LAUNCH_CLUSTER(kClusterSize, trl_decide_conv_kernel, grid, kDecideThreads, decide_smem_bytes(), st, B, W, act2, list);
-    TRL_LAUNCH_CLUSTER(kFcCluster, trl_decide_fc_kernel, fc_clusters * kFcCluster, kFcThreads, decide_fc_smem_bytes(), st, B, W, ex, maps, done_count, list,
-                       rearm);
+                    int fc_clusters, int list, int rearm, cudaStream_t st, int part = 3) {
+    if (part & 1) TRL_LAUNCH_CLUSTER(kClusterSize, trl_decide_conv_kernel, grid, kDecideThreads, (size_t)kConvSmemDoubles * 8, st, B, W, act2, list);
+    if (part & 2)
+        TRL_LAUNCH_CLUSTER(kFcCluster, trl_decide_fc_kernel, fc_clusters * kFcCluster, kFcThreads, decide_fc_smem_bytes(), st, B, W, ex, maps, done_count,
+                           list, rearm);
 }
 
 }  // namespace trl

@@ -17,5 +17,6 @@ struct FcMaps {
     const double* w_ptr;
     const double* a_ptr;
     int a_rows;
+    unsigned long long* prof;    // measurement only (trl_debug_fc_phases): rank 0 / thread 0 of cluster 0 stamps %globaltimer at phase ends
 };
 }  // namespace trl

@@ -29,7 +29,8 @@ struct trl_handle {
     std::vector<int64_t> net_counts;
     int* done_count = nullptr;
     cudaStream_t stream = nullptr;
-    cudaStream_t aux_stream = nullptr;           // high-priority side stream: decisions + catch-up launches (overlapped schedule)
+    cudaStream_t aux_stream = nullptr;           // high-priority side streams: decisions + catch-up launches (overlapped schedule),
+    cudaStream_t aux_stream2 = nullptr;          // alternating by env-step
     std::vector<cudaEvent_t> fork_events;        // dependencies between the two streams inside one update
     bool overlap = true;                         // TRL_SERIAL_SCHEDULE=1 turns the overlapped schedule off
     int decide_grid = 288;   // CTAs of the decision launch: a multiple of its cluster size (create_common sizes it from the SM count)
@@ -37,8 +38,8 @@ struct trl_handle {
     // batched decision path (trl_decide2.cuh): conv2 outputs of the pending decisions, the TMA descriptors over them and over the
     // terr_ip0 weights (re-encoded whenever the weight pointer changes), number of FC-stage clusters
     bool decide_v2 = true;                       // TRL_DECIDE_V1=1 selects the one-cluster-per-decision kernel (trl_decide.cuh)
-    double* act2 = nullptr;
-    trl::FcMaps fc_maps;
+    double* act2[2] = {nullptr, nullptr};        // one scratch matrix per side stream (the decisions of two env-steps can overlap)
+    trl::FcMaps fc_maps[2];
     const double* fc_maps_w = nullptr;
     int fc_clusters = 2;
     int64_t launches = 0;
@@ -53,6 +54,7 @@ struct trl_handle {
     std::vector<int32_t> h_dist_env;
     std::vector<void*> allocs;
     void* flush_buf = nullptr;
+    double* probe_dump = nullptr;        // every blob of one forward pass (trl_probe.cu: trl_get_layer_state)
     // pipelined read-back (trl_snapshot / trl_snapshot_wait)
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t snap_ready = nullptr, snap_copied = nullptr;

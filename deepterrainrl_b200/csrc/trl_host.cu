@@ -32,7 +32,7 @@ void launch_stats(const Buffers& B, double* out, cudaStream_t st);
 size_t decide_fc_smem_bytes();
 cudaError_t configure_decide2_kernels();
 void launch_decide2(const Buffers& B, const NetWeights& W, const ExpSettings* ex, const FcMaps& maps, double* act2, int* done_count, int grid,
-                    int fc_clusters, int list, int rearm, cudaStream_t st);
+                    int fc_clusters, int list, int rearm, cudaStream_t st, int part);
 void launch_terrain(const Buffers& B, double lookahead, cudaStream_t st);
 }  // namespace trl
 namespace trl_cg {
@@ -395,23 +395,26 @@ static int encode_rows_map(CUtensorMap* map, const double* base, uint64_t rows, 
 }
 #endif
 static int ensure_fc_maps(trl_handle* h) {
-    if (!h->decide_v2 || !h->mc.has_net || !h->act2 || !h->W.tip0_w) return 0;
+    if (!h->decide_v2 || !h->mc.has_net || !h->act2[0] || !h->W.tip0_w) return 0;
     if (h->fc_maps_w == h->W.tip0_w) return 0;
-    h->fc_maps.w_ptr = h->W.tip0_w;
-    h->fc_maps.a_ptr = h->act2;
-    h->fc_maps.a_rows = h->n;
+    for (int k = 0; k < 2; ++k) {
+        h->fc_maps[k].w_ptr = h->W.tip0_w;
+        h->fc_maps[k].a_ptr = h->act2[k];
+        h->fc_maps[k].a_rows = h->n;
+        h->fc_maps[k].prof = nullptr;
 #ifndef TRL_SIMT_EMU
-    if (encode_rows_map(&h->fc_maps.w, h->W.tip0_w, 64, 64)) return 1;
-    if (encode_rows_map(&h->fc_maps.a, h->act2, (uint64_t)h->n, 32)) return 1;
+        if (encode_rows_map(&h->fc_maps[k].w, h->W.tip0_w, 64, 64)) return 1;
+        if (encode_rows_map(&h->fc_maps[k].a, h->act2[k], (uint64_t)h->n, 32)) return 1;
 #endif
+    }
     h->fc_maps_w = h->W.tip0_w;
     return 0;
 }
 // the decision launch(es) of one env-step
-static void enqueue_decide(trl_handle* h, int list, int rearm, cudaStream_t st) {
+static void enqueue_decide(trl_handle* h, int list, int rearm, cudaStream_t st, int part = 3, int slot = 0) {
     if (h->decide_v2)
-        launch_decide2(h->B, h->W, h->d_ex, h->fc_maps, h->act2, h->done_count, h->decide_grid, h->fc_clusters, list, rearm, st);
-    else
+        launch_decide2(h->B, h->W, h->d_ex, h->fc_maps[slot], h->act2[slot], h->done_count, h->decide_grid, h->fc_clusters, list, rearm, st, part);
+    else if (part & 1)
         launch_decide(h->B, h->W, h->d_ex, h->done_count, h->decide_grid, list, rearm, st);
 }
 static int num_decide_launches(const trl_handle* h) { return h->decide_v2 ? 2 : 1; }
@@ -428,64 +431,88 @@ static void destroy_graphs(trl_handle* h) {
 // (few) envs that reached a cycle boundary in S_i.
 //
 //   serial schedule      T  S_0  D_0  S_1  D_1 ... S_{ns-1}  D_{ns-1}  S_end
-//   overlapped schedule  main stream   T  S_0 ------ S_1 -------------- S_2 ----- ...  S_{ns-1} ----------- S_end
-//                        side stream          D_0 -> C_1        D_1 -> C_2        ...             D_{ns-1}
+//   overlapped schedule  main stream    T  S_0  S_1  S_2  S_3  S_4 ...  S_{ns-1}  S_end          (back to back)
+//                        side stream 0        D_0 -> C_0 [steps 1, 2]     D_2 -> C_2 [steps 3, 4] ...
+//                        side stream 1             D_1 -> C_1 [steps 2, 3]     D_3 -> C_3 ...
 //
-// In the overlapped schedule S_i (i >= 1) skips the envs that wait for D_{i-1}; the catch-up launch C_i steps exactly
-// those envs once their decision is made (same kernel, one warp per list entry), concurrently with S_i.  D_i needs
-// S_i and C_i; S_{i+1} needs S_i and C_i.  Two pending lists alternate so that S_i / C_i can append to one while D_{i-1} / C_i
-// read the other.  Every env still advances by exactly one env-step per S/C pair, so results are identical to the serial
-// schedule (tests/test_gpu_scenarios.py::test_overlap_matches_serial).
+// In the overlapped schedule the envs that reach a cycle boundary in S_i wait for D_i and are then advanced by the catch-up
+// launch C_i (same kernel, one warp per list entry, registers live across its two env-steps) while S_{i+1} and S_{i+2} skip them;
+// S_{i+3} needs C_i.  Three pending lists rotate (S_i appends to list i % 3, which C_{i-3} re-armed).  Every env still advances
+// by exactly one env-step per launch equivalent, so results are identical to the serial schedule
+// (tests/test_gpu_scenarios.py::test_overlap_matches_serial).  Measured reason (profiles/timeline_r02_*.json): with one step of
+// slack the update was bound by the chain D_i -> C_i (~160 us) rather than by the step launch (~140 us).
 // optional recorder of a timeline (trl_update_timeline): an event pair around every launch, on the stream it is launched on
 struct Timeline {
-    std::vector<cudaEvent_t> beg, end;
-    std::vector<int> kind, idx;      // kind: 0 terrain, 1 step S_i, 2 decision D_i, 3 catch-up C_i
+    std::vector<cudaEvent_t> beg, end, fork;
+    std::vector<int> kind, idx;      // kind: 0 terrain, 1 step S_i, 2 decision D_i (conv stage of the batched path), 3 catch-up C_i, 4 FC stage of D_i
+    std::string err;                 // first CUDA error seen while enqueueing, with the launch it followed
+    void check(const char* where) {
+        const cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess && err.empty())
+            err = std::string(where) + " of launch kind " + std::to_string(kind.empty() ? -1 : kind.back()) + " #" + std::to_string(idx.empty() ? -1 : idx.back()) + ": " + cudaGetErrorString(e);
+    }
     void open(cudaStream_t st, int k, int i) {
+        check("before");
         cudaEvent_t b, e;
         cudaEventCreate(&b); cudaEventCreate(&e);
         beg.push_back(b); end.push_back(e); kind.push_back(k); idx.push_back(i);
         cudaEventRecord(b, st);
+        check("open");
     }
-    void close(cudaStream_t st) { cudaEventRecord(end.back(), st); }
+    void close(cudaStream_t st) { check("launch"); cudaEventRecord(end.back(), st); check("close"); }
 };
 static void enqueue_update(trl_handle* h, double dt, bool overlap, Timeline* tl = nullptr) {
     const int ns = h->num_update_steps;
     const double step = dt / ns;
-    cudaStream_t A = h->stream, S = h->aux_stream;
+    cudaStream_t A = h->stream;
 #define TL_OPEN(st, k, i) do { if (tl) tl->open(st, k, i); } while (0)
 #define TL_CLOSE(st) do { if (tl) tl->close(st); } while (0)
     TL_OPEN(A, 0, 0); launch_terrain(h->B, 0.5, A); TL_CLOSE(A);
     if (!overlap) {
         for (int i = 0; i < ns; ++i) {
             TL_OPEN(A, 1, i); launch_step(h->B, step, i == 0 ? 2 : 3, 0, A); TL_CLOSE(A);
-            TL_OPEN(A, 2, i); enqueue_decide(h, 0, 1, A); TL_CLOSE(A);
+            TL_OPEN(A, 2, i); enqueue_decide(h, 0, 1, A, 1); TL_CLOSE(A); TL_OPEN(A, 4, i); enqueue_decide(h, 0, 1, A, 2); TL_CLOSE(A);
         }
         TL_OPEN(A, 1, ns); launch_step(h->B, step, 1 | 4, 0, A); TL_CLOSE(A);
         return;
     }
-    if ((int)h->fork_events.size() < 2 * ns + 2) {
-        size_t old = h->fork_events.size();
-        h->fork_events.resize(2 * ns + 2);
-        for (size_t i = old; i < h->fork_events.size(); ++i) cudaEventCreateWithFlags(&h->fork_events[i], cudaEventDisableTiming);
+    // Overlapped schedule, two env-steps deep.  Main stream: T S_0 S_1 S_2 ... S_{ns-1} S_end back to back.  The envs that reach a
+    // cycle boundary in S_i (list i % 3) are served on a side stream (two side streams alternate): D_i decides them, the catch-up
+    // launch C_i then advances exactly those envs by TWO env-steps (i + 1 and i + 2; one if the update ends first), while S_{i+1}
+    // and S_{i+2} skip them.  S_{i+3} needs C_i.  The chain D_i -> C_i therefore has two step launches of slack instead of none.
+    std::vector<cudaEvent_t>& fe = tl ? tl->fork : h->fork_events;
+    if ((int)fe.size() < 2 * ns + 2) {
+        size_t old = fe.size();
+        fe.resize(2 * ns + 2);
+        for (size_t i = old; i < fe.size(); ++i) cudaEventCreateWithFlags(&fe[i], cudaEventDisableTiming);
     }
-    cudaEvent_t* ev_s = h->fork_events.data();            // ev_s[i]: S_i done
-    cudaEvent_t* ev_c = h->fork_events.data() + ns + 1;   // ev_c[i]: C_i (and everything before it on the side stream) done
-    TL_OPEN(A, 1, 0); launch_step(h->B, step, 2, /*app*/ 0, A); TL_CLOSE(A);
+    cudaEvent_t* ev_s = fe.data();            // ev_s[i]: S_i done
+    cudaEvent_t* ev_c = fe.data() + ns + 1;   // ev_c[i]: C_i (i < ns - 1) / D_{ns-1} done
+    cudaStream_t side[2] = {h->aux_stream, h->aux_stream2};
+    auto lists_of = [](int app, int prev) { return (app % 3) | ((prev % 3) << 2); };
+    TL_OPEN(A, 1, 0); launch_step(h->B, step, 2, lists_of(0, 0), A); TL_CLOSE(A);
     cudaEventRecord(ev_s[0], A);
     for (int i = 1; i < ns; ++i) {
-        const int app = i & 1, prev = (i - 1) & 1, lists = app | (prev << 1);
-        cudaStreamWaitEvent(S, ev_s[i - 1], 0);
-        TL_OPEN(S, 2, i - 1); enqueue_decide(h, prev, 0, S); TL_CLOSE(S);
-        TL_OPEN(S, 3, i); trl_cg::launch_step(h->B, step, 1 | 2 | 16, lists, S); TL_CLOSE(S);
-        cudaEventRecord(ev_c[i], S);
-        if (i >= 2) cudaStreamWaitEvent(A, ev_c[i - 1], 0);
-        TL_OPEN(A, 1, i); launch_step(h->B, step, 1 | 2 | 8, lists, A); TL_CLOSE(A);
+        // side work for the envs that became due in S_{i-1}
+        const int l = i - 1;
+        cudaStream_t X = side[l & 1];
+        cudaStreamWaitEvent(X, ev_s[l], 0);
+        TL_OPEN(X, 2, l); enqueue_decide(h, l % 3, 0, X, 1, l & 1); TL_CLOSE(X); TL_OPEN(X, 4, l); enqueue_decide(h, l % 3, 0, X, 2, l & 1); TL_CLOSE(X);
+        const int reps = std::min(2, ns - 1 - l);     // equivalents l + 1 (and l + 2) of the main launches; S_end is never caught up
+        TL_OPEN(X, 3, l); trl_cg::launch_step(h->B, step, 1 | 2 | 16 | (reps == 2 ? 32 : 0), lists_of(l + 1, l), X); TL_CLOSE(X);
+        cudaEventRecord(ev_c[l], X);
+        if (i >= 3) cudaStreamWaitEvent(A, ev_c[i - 3], 0);
+        TL_OPEN(A, 1, i); launch_step(h->B, step, 1 | 2 | 8, lists_of(i, i), A); TL_CLOSE(A);
         cudaEventRecord(ev_s[i], A);
     }
-    cudaStreamWaitEvent(S, ev_s[ns - 1], 0);
-    TL_OPEN(S, 2, ns - 1); enqueue_decide(h, (ns - 1) & 1, 1, S); TL_CLOSE(S);
-    cudaEventRecord(ev_c[ns], S);
-    cudaStreamWaitEvent(A, ev_c[ns], 0);
+    {
+        const int l = ns - 1;
+        cudaStream_t X = side[l & 1];
+        cudaStreamWaitEvent(X, ev_s[l], 0);
+        TL_OPEN(X, 2, l); enqueue_decide(h, l % 3, 1, X, 1, l & 1); TL_CLOSE(X); TL_OPEN(X, 4, l); enqueue_decide(h, l % 3, 1, X, 2, l & 1); TL_CLOSE(X);
+        cudaEventRecord(ev_c[l], X);
+    }
+    for (int l = std::max(0, ns - 3); l < ns; ++l) cudaStreamWaitEvent(A, ev_c[l], 0);
     TL_OPEN(A, 1, ns); launch_step(h->B, step, 1 | 4, 0, A); TL_CLOSE(A);
 #undef TL_OPEN
 #undef TL_CLOSE
@@ -561,6 +588,7 @@ static trl_handle* create_common(trl_handle* h, int num_envs, int device, int mo
         int lo = 0, hi = 0;
         cudaDeviceGetStreamPriorityRange(&lo, &hi);   // hi = numerically lowest = greatest priority
         if (cudaStreamCreateWithPriority(&h->aux_stream, cudaStreamNonBlocking, hi) != cudaSuccess) return bail("cudaStreamCreate (side) failed");
+        if (cudaStreamCreateWithPriority(&h->aux_stream2, cudaStreamNonBlocking, hi) != cudaSuccess) return bail("cudaStreamCreate (side 2) failed");
         const char* serial = std::getenv("TRL_SERIAL_SCHEDULE");
         h->overlap = !(serial && serial[0] == '1');
     }
@@ -592,14 +620,14 @@ static trl_handle* create_common(trl_handle* h, int num_envs, int device, int mo
               ck(dalloc(h, &B.terrain, n * 2 * kTerrainCap), "alloc terrain") && ck(dalloc(h, &B.poli_state, n * B.S), "alloc poli") &&
               ck(dalloc(h, &B.net_out, n * kMaxNetOut), "alloc net_out") && ck(dalloc(h, &B.tuple_sbeg, n * B.S), "alloc sbeg") &&
               ck(dalloc(h, &B.tuple_action, n * kNumParams), "alloc action") && ck(dalloc(h, &B.com_stash, 2 * n), "alloc com") &&
-              ck(dalloc(h, &B.pending_list, 2 * n), "alloc pending") && ck(dalloc(h, &B.pending_count, 2), "alloc pc") &&
-              ck(dalloc(h, &B.catchup_done, 1), "alloc cd") &&
+              ck(dalloc(h, &B.pending_list, 3 * n), "alloc pending") && ck(dalloc(h, &B.pending_count, 4), "alloc pc") &&
+              ck(dalloc(h, &B.catchup_done, 4), "alloc cd") &&
               ck(dalloc(h, &B.tuples, (size_t)B.tuple_cap * (1 + B.S + A + B.S)), "alloc tuples") &&
               ck(dalloc(h, &B.tuple_flags, (size_t)B.tuple_cap), "alloc tf") && ck(dalloc(h, &B.tuple_env, (size_t)B.tuple_cap), "alloc te") &&
               ck(dalloc(h, &B.tuple_count, 1), "alloc tc") && ck(dalloc(h, &B.dist_log, (size_t)B.dist_cap), "alloc dl") &&
               ck(dalloc(h, &B.dist_env, (size_t)B.dist_cap), "alloc de") && ck(dalloc(h, &B.dist_count, 1), "alloc dc") &&
               ck(dalloc(h, &h->done_count, 1), "alloc done") && ck(dalloc(h, &h->d_ex, 1), "alloc ex") &&
-              (!h->mc.has_net || ck(dalloc(h, &h->act2, n * (size_t)5984), "alloc act2"));
+              (!h->mc.has_net || (ck(dalloc(h, &h->act2[0], n * (size_t)5984), "alloc act2") && ck(dalloc(h, &h->act2[1], n * (size_t)5984), "alloc act2")));
     if (ok) ok = ck(cudaMemcpy(h->d_ex, &h->ex, sizeof(ExpSettings), cudaMemcpyHostToDevice), "upload ex");
     if (!ok) return bail("");
     if (h->mc.has_net) {
@@ -639,6 +667,7 @@ int trl_destroy(trl_handle* h) {
     if (h->snap_host) cudaFreeHost(h->snap_host);
     for (void* p : h->allocs) cudaFree(p);
     if (h->aux_stream) { cudaStreamSynchronize(h->aux_stream); cudaStreamDestroy(h->aux_stream); }
+    if (h->aux_stream2) { cudaStreamSynchronize(h->aux_stream2); cudaStreamDestroy(h->aux_stream2); }
     for (auto e : h->fork_events) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -655,7 +684,7 @@ int trl_seed_terrain(trl_handle* h, const uint64_t* seeds, int n) {
         cudaError_t e = cudaMemcpyAsync(d_seeds, seeds, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream);
         if (e != cudaSuccess) { cudaFree(d_seeds); return fail(std::string("trl_seed_terrain: ") + cudaGetErrorString(e)); }
     }
-    cudaError_t e = cudaMemsetAsync(h->B.pending_count, 0, 8, h->stream);
+    cudaError_t e = cudaMemsetAsync(h->B.pending_count, 0, 16, h->stream);
     if (e == cudaSuccess) {
         launch_reset(h->B, d_seeds, nullptr, h->n, 1, h->stream);
         h->launches += 1;
@@ -733,6 +762,11 @@ int trl_env_step(trl_handle* h, double step) {
 int trl_sync(trl_handle* h) {
     if (!h) return fail("trl_sync: null handle");
     CK(cudaStreamSynchronize(h->stream));
+    int fault = 0;
+    CK(cudaMemcpy(&fault, h->B.catchup_done + 3, 4, cudaMemcpyDeviceToHost));
+    if (fault)
+        return fail("an env finished a gait cycle inside a catch-up launch (cycle shorter than three env-steps): the overlapped schedule "
+                    "cannot serve it; run with TRL_SERIAL_SCHEDULE=1");
     return 0;
 }
 
@@ -1203,6 +1237,45 @@ int trl_debug_time_decide(trl_handle* h, int n_pending, int iters, double* ms_av
     return 0;
 }
 
+// Phase stamps of the batched decision path's FC kernel for `n_pending` decisions (measurement only): out[k] = nanoseconds from
+// kernel entry to stamp k (see trl_decide2.cuh: stamp()); conv_us / fc_us = event-timed durations of the two launches
+int trl_debug_fc_phases(trl_handle* h, int n_pending, double* out_ns16, double* conv_us, double* fc_us) {
+    if (!h) return fail("trl_debug_fc_phases: null handle");
+    if (!h->decide_v2 || !h->mc.has_net) return fail("trl_debug_fc_phases: the batched decision path is not active");
+    if (ensure_model(h)) return fail("model upload failed");
+    n_pending = std::max(1, std::min(n_pending, h->n));
+    std::vector<int> ids(n_pending);
+    for (int i = 0; i < n_pending; ++i) ids[i] = i;
+    unsigned long long* prof = nullptr;
+    CK(cudaMalloc((void**)&prof, 16 * 8));
+    CK(cudaMemset(prof, 0, 16 * 8));
+    FcMaps maps = h->fc_maps[0];
+    maps.prof = prof;
+    cudaEvent_t e0, e1, e2;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); CK(cudaEventCreate(&e2));
+    for (int it = 0; it < 3; ++it) {      // the last of three runs is reported (weights L2-resident, clocks up)
+        CK(cudaMemcpyAsync(h->B.pending_list, ids.data(), (size_t)n_pending * 4, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->B.pending_count, &n_pending, 4, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaEventRecord(e0, h->stream));
+        launch_decide2(h->B, h->W, h->d_ex, maps, h->act2[0], h->done_count, h->decide_grid, h->fc_clusters, 0, 1, h->stream, 1);
+        CK(cudaEventRecord(e1, h->stream));
+        launch_decide2(h->B, h->W, h->d_ex, maps, h->act2[0], h->done_count, h->decide_grid, h->fc_clusters, 0, 1, h->stream, 2);
+        CK(cudaEventRecord(e2, h->stream));
+        CK(cudaEventSynchronize(e2));
+    }
+    h->launches += 6;
+    float a = 0, b = 0;
+    CK(cudaEventElapsedTime(&a, e0, e1)); CK(cudaEventElapsedTime(&b, e1, e2));
+    if (conv_us) *conv_us = a * 1e3;
+    if (fc_us) *fc_us = b * 1e3;
+    unsigned long long st[16];
+    CK(cudaMemcpy(st, prof, sizeof(st), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < 16; ++k) out_ns16[k] = st[k] ? (double)(st[k] - st[0]) : -1.0;
+    cudaFree(prof);
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+    return 0;
+}
+
 // Pipelined read-back: trl_snapshot() enqueues, behind the work already on the handle's stream, a device-side copy
 // of all pose / velocity planes plus the reduced batch statistics, then moves them to pinned host memory on a second
 // stream; trl_snapshot_wait() blocks on that copy only, so the caller can enqueue the next trl_update() first and
@@ -1296,10 +1369,17 @@ int trl_update_timeline(trl_handle* h, double dt, double* out, int cap, int* n_o
     Timeline tl;
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaStreamSynchronize(h->aux_stream));
+    CK(cudaStreamSynchronize(h->aux_stream2));
+    (void)cudaGetLastError();        // a stale, already reported status of an earlier call must not be charged to this run
     enqueue_update(h, dt, h->overlap, &tl);
+    {
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess && tl.err.empty()) tl.err = std::string("after enqueue: ") + cudaGetErrorString(e);
+        if (!tl.err.empty()) return fail("trl_update_timeline: " + tl.err);
+    }
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaStreamSynchronize(h->aux_stream));
-    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->aux_stream2));
     h->launches += update_launches(h, h->overlap);
     const int n = (int)tl.beg.size();
     for (int k = 0; k < n; ++k) {
@@ -1307,8 +1387,9 @@ int trl_update_timeline(trl_handle* h, double dt, double* out, int cap, int* n_o
         cudaEventElapsedTime(&a, tl.beg[0], tl.beg[k]);
         cudaEventElapsedTime(&b, tl.beg[0], tl.end[k]);
         if (k < cap) { out[4 * k] = tl.kind[k]; out[4 * k + 1] = tl.idx[k]; out[4 * k + 2] = a; out[4 * k + 3] = b; }
-        cudaEventDestroy(tl.beg[k]); cudaEventDestroy(tl.end[k]);
     }
+    for (int k = 0; k < n; ++k) { cudaEventDestroy(tl.beg[k]); cudaEventDestroy(tl.end[k]); }
+    for (auto e : tl.fork) cudaEventDestroy(e);
     if (n_out) *n_out = std::min(n, cap);
     return 0;
 }

@@ -49,7 +49,7 @@ constexpr unsigned kFull = 0xffffffffu;
 #ifndef TRL_STEP_MIN_BLOCKS
 #define TRL_STEP_MIN_BLOCKS 4   // CTAs of 4 warps per SM the register budget is sized for
 #endif
-constexpr int kStepSkipPending = 8, kStepCatchUp = 16;   // flag bits of trl_step_kernel beyond ctrl (1) / phys (2) / end (4)
+constexpr int kStepSkipPending = 8, kStepCatchUp = 16, kStepTwice = 32;   // flag bits of trl_step_kernel beyond ctrl (1) / phys (2) / end (4)
 constexpr double kClearMargin = 0.05;   // >= contact_tol * sqrt(1 + slope^2) for any slope the generators produce
 constexpr int kZeroLane = 31;   // always idle (nj <= 23): its per-link registers are zero, used as the "no source" lane
 constexpr int kTri = kMaxDof * (kMaxDof + 1) / 2;   // 276
@@ -1162,7 +1162,8 @@ __device__ __forceinline__ void catchup_leave(const Buffers& B, int prev) {
     if ((threadIdx.x & 31) == 0) {
         __threadfence();
         const int total = (int)gridDim.x * kWarpsPerBlock;
-        if (atomicAdd(B.catchup_done, 1) == total - 1) { B.pending_count[prev] = 0; *B.catchup_done = 0; __threadfence(); }
+        // one counter per list: the catch-up launches of two consecutive env-steps can be in flight at the same time
+        if (atomicAdd(&B.catchup_done[prev], 1) == total - 1) { B.pending_count[prev] = 0; B.catchup_done[prev] = 0; __threadfence(); }
     }
 }
 
@@ -1181,13 +1182,15 @@ trl_step_kernel(Buffers B, double h, int flags, int lists) {
     }
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // pending-decision lists: envs that reach a cycle boundary in this launch are appended to list `app`; `prev` is the
-    // list the previous env-step filled.  An env's I_PENDING tag is 1 + the list it was last appended to.
-    const int app = lists & 1, prev = (lists >> 1) & 1;
+    // pending-decision lists (three, used round robin by successive env-steps): envs that reach a cycle boundary in this launch are
+    // appended to list `app`; an env's I_PENDING tag is 1 + the list it was last appended to.  The decision of list l is made one
+    // launch later and the env is then caught up over two env-steps by a side launch (trl_host.cu: enqueue_update), so the main
+    // launch of step j skips the envs tagged with the lists of steps j - 1 and j - 2; a tag of list j % 3 is three steps old.
+    const int app = lists & 3, prev = (lists >> 2) & 3;
     int env = blockIdx.x * kWarpsPerBlock + warp;
     if (flags & kStepCatchUp) {
-        // catch-up launch: one warp per entry of the previous step's list, after the decision kernel has served it.
-        // The last CTA to leave re-arms that list (the main launch of the step after next appends to it again).
+        // catch-up launch: one warp per entry of list `prev`, after the decision kernel has served it.
+        // The last CTA to leave re-arms that list (the main launch three steps later appends to it again).
         const int count = B.pending_count[prev];
         if (env >= count) { catchup_leave(B, prev); return; }
         env = B.pending_list[prev * B.n + env];
@@ -1196,12 +1199,12 @@ trl_step_kernel(Buffers B, double h, int flags, int lists) {
     }
     Lane L{nullptr, env, B.n, B.d, B.i};
     if (flags & kStepSkipPending) {
-        // overlapped main launch: envs waiting for the previous step's decision are stepped by the catch-up launch
+        // overlapped main launch: envs waiting for a decision or being caught up are not touched
         const int tag = L.i(I_PENDING);
-        if (tag == 1 + prev) return;
-        if (tag == 1 + app && lane == 0) L.i(I_PENDING) = 0;   // stale tag of two steps ago (already caught up)
+        if (tag != 0 && tag != 1 + app) return;
+        if (tag == 1 + app && lane == 0) L.i(I_PENDING) = 0;   // stale tag of three steps ago (already caught up)
     } else if (!(flags & kStepCatchUp) && (flags & 1) && lane == 0) {
-        L.i(I_PENDING) = 0;    // serial schedule: every decision has been served before this launch
+        L.i(I_PENDING) = 0;    // serial schedule / end of the update: every decision has been served before this launch
     }
     double* xs = s_x + warp * X_END;
     const LinkC lc = load_link(lane);
@@ -1213,6 +1216,12 @@ trl_step_kernel(Buffers B, double h, int flags, int lists) {
     Kin k_ctrl;
     bool have_k = false;       // warp-uniform: the controller half ran and nothing has moved the state since
 #endif
+#ifdef TRL_CG_VARIANT
+    const int reps = (flags & kStepTwice) ? 2 : 1;     // a catch-up launch advances its envs by two env-steps (registers stay live)
+#else
+    constexpr int reps = 1;                            // catch-up launches are the other build of this file (trl_step_cg.cu)
+#endif
+    for (int rep = 0; rep < reps; ++rep) {
     if (flags & 1) {
         // ---------------- controller half of env-step k
         Kin k = kinematics(lc, e TRL_KIN_XS_ARG);
@@ -1348,12 +1357,18 @@ trl_step_kernel(Buffers B, double h, int flags, int lists) {
             if (lane == 0) {
                 B.com_stash[env] = comx; B.com_stash[B.n + env] = comy;
                 L.i(I_FIRST_CYCLE) = 0;
+                if (flags & kStepCatchUp) {
+                    // a gait cycle shorter than three env-steps (the shipped controllers' timed states alone last 150): the side
+                    // launch cannot hand the env to a decision in time -- flag it (trl_sync reports; TRL_SERIAL_SCHEDULE=1 runs it)
+                    B.catchup_done[3] = 1;
+                }
                 L.i(I_PENDING) = 1 + app;
                 int slot = atomicAdd(&B.pending_count[app], 1);
                 B.pending_list[app * B.n + slot] = env;
             }
         }
     }
+    }   // rep
     store_env(L, lc, e, lane);
     if (flags & kStepCatchUp) catchup_leave(B, prev);
 }

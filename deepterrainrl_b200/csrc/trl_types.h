@@ -152,9 +152,9 @@ struct Buffers {
     double* tuple_sbeg;    // [n][S]
     double* tuple_action;  // [n][kNumParams]
     double* com_stash;     // [2][n]   COM at decision time
-    int* pending_list;     // [2][n]  two lists, used alternately by successive env-steps (see trl_host.cu: enqueue_update)
-    int* pending_count;    // [2]
-    int* catchup_done;     // [1]     CTA completion counter of the catch-up launch (re-arms the list it consumed)
+    int* pending_list;     // [3][n]  three lists, used round robin by successive env-steps (see trl_host.cu: enqueue_update)
+    int* pending_count;    // [3]
+    int* catchup_done;     // [4]     [l] CTA completion counter of the catch-up launch of list l (re-arms the list it consumed), [3] fault flag
     // outputs
     double* tuples;        // [tuple_cap][1 + S + A + S]
     uint32_t* tuple_flags; // [tuple_cap]

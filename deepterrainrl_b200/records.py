@@ -3,7 +3,8 @@ tuple stream (one tuple per gait cycle: state at the decision, action taken, rew
 parameters), `RecordActionIDState` (action id + policy state) and the reward per cycle, in the reference's text formats
 (std::to_string -> 6 decimals, ",\\t" separated).  The record lines are byte-identical to the files the reference's compiled
 cScenarioPoliEval writes for the same cycles (tests/test_ref_pinning_cpu.py); `action_table_lines` gives the table of base actions
-that cScenarioPoliEval::InitActionRecord puts in front of the action records (:298-319).  `RecordVel` (:353-367: the
+that cScenarioPoliEval::InitActionRecord puts in front of the action records (:298-319).  `RecordNNActivation` (a named layer's blob of the deploy net after the
+decision, `record_nn_activation` fed from trl_get_layer_state) is written per cycle as well.  `RecordVel` (:353-367: the
 COM's mean forward velocity over the cycle that just ended) does not travel with the tuples; `poll` derives it from the controller
 block after an outer update (a gait cycle is much longer than one update, so at most one cycle ends per call)."""
 import numpy as np
@@ -52,9 +53,11 @@ def _line(head, vec):
 
 class CycleRecorder:
     def __init__(self, env, state_size, action_size, action_file=None, action_id_state_file=None, reward_file=None, vel_file=None,
-                 pack=None):
+                 pack=None, nn_activation_file=None, nn_activation_layer=None):
         self.env, self.S, self.A = env, state_size, action_size
-        self.files = dict(action=action_file, ids=action_id_state_file, reward=reward_file, vel=vel_file)
+        self.nn_layer = nn_activation_layer
+        self.files = dict(action=action_file, ids=action_id_state_file, reward=reward_file, vel=vel_file,
+                          nn=nn_activation_file if nn_activation_layer else None)
         self._last_cycle = 0
         self._acc_dx = self._time = self._prev_time = 0.0
         for f in self.files.values():
@@ -83,6 +86,14 @@ class CycleRecorder:
                     f.write("%f\n" % r[0])
             self.cycles += 1
         return len(sel)
+
+    def record_nn_activation(self, action_id, blob):
+        """cScenarioPoliEval::RecordNNActivation (:271-296): action id + the named layer's blob after the decision that opened the
+        cycle (cNeuralNet::GetLayerState; product side: BatchedScenario.GetLayerState(layer, env) = trl_get_layer_state).  Call once per
+        valid cycle (the warm-up cycle is not recorded), before the cycle's action records; an empty blob writes nothing, as there."""
+        if self.files["nn"] and len(blob) > 0:
+            with open(self.files["nn"], "a") as f:
+                f.write(_line(action_id, blob))
 
     def poll(self, ctrl, dt=1.0 / 30.0, episode_reset=False):
         """cScenarioPoliEval::RecordVel (:353-367).  Call ONCE after every Update(dt) with the env's controller block

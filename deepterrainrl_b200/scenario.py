@@ -72,12 +72,13 @@ def build_library(force=False, verbose=False):
     out = library_path()
     csrc = os.path.join(_PKG, "csrc")
     units = [("trl_step.cu", []), ("trl_step_cg.cu", ["-Xptxas", "-dlcm=cg"]), ("trl_host.cu", []), ("trl_train.cu", []),
-             ("trl_comm.cu", []), ("ref_loader.cpp", [])]
+             ("trl_comm.cu", []), ("trl_probe.cu", []), ("ref_loader.cpp", [])]
     deps = [os.path.join(csrc, f) for f in os.listdir(csrc)]
     deps.append(os.path.join(_ROOT, "include", "terrainrl_b200.h"))
     if not force and os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in deps):
         return out
-    base_objdir = os.path.join(_PKG, "lib", "obj")
+    # objects live outside the tree (they are rebuilt from the sources where they are missing; only the linked libraries travel)
+    base_objdir = os.path.join(os.environ.get("TRL_BUILD_DIR", "/tmp/terrainrl_b200_build"), "obj")
     objdir = os.path.join(base_objdir, "variants", variant) if variant else base_objdir
     os.makedirs(objdir, exist_ok=True)
     os.makedirs(os.path.dirname(out), exist_ok=True)
@@ -106,8 +107,8 @@ EXPORTS = [
     "trl_create_from_pack", "trl_create", "trl_pack_from_args", "trl_destroy", "trl_reset", "trl_seed_terrain", "trl_update", "trl_env_step", "trl_sync",
     "trl_set_explore", "trl_set_phys_params", "trl_set_weights", "trl_sizes", "trl_num_tuples", "trl_get_tuples",
     "trl_get_tuples_f64", "trl_reset_tuples", "trl_eval_stats", "trl_dist_log", "trl_reset_avg_dist", "trl_get_state", "trl_set_state",
-    "trl_get_state_all", "trl_get_ctrl", "trl_get_poli_state", "trl_get_net_out", "trl_get_terrain",
-    "trl_kernel_launches", "trl_last_error", "trl_bench_updates", "trl_update_timed", "trl_device_tuple_block", "trl_snapshot", "trl_snapshot_wait", "trl_update_timed_detail", "trl_update_timeline", "trl_debug_time_decide",
+    "trl_get_state_all", "trl_get_ctrl", "trl_get_poli_state", "trl_get_net_out", "trl_get_layer_state", "trl_get_terrain",
+    "trl_kernel_launches", "trl_last_error", "trl_bench_updates", "trl_update_timed", "trl_device_tuple_block", "trl_snapshot", "trl_snapshot_wait", "trl_update_timed_detail", "trl_update_timeline", "trl_debug_time_decide", "trl_debug_fc_phases",
     "trl_load_model", "trl_output_model", "trl_write_model", "trl_get_output_offset_scale", "trl_pack_output_offset_scale",
     "trl_set_terrain_lerp", "trl_train_schedule", "trl_trainer_create", "trl_trainer_destroy", "trl_trainer_init_fresh", "trl_trainer_add_from_scene", "trl_trainer_add_tuples", "trl_trainer_add_device", "trl_trainer_train", "trl_train_run", "trl_train_run_timed",
     "trl_trainer_counters", "trl_trainer_num_params", "trl_trainer_launches", "trl_trainer_get", "trl_trainer_set_theta", "trl_trainer_list", "trl_trainer_rows",
@@ -269,6 +270,13 @@ class BatchedScenario:
         y = np.zeros(96)
         self._ck(self.L.trl_get_net_out(self.h, env, _p(y)))
         return y[:n]
+
+    def GetLayerState(self, layer_name, env=0):
+        """cNeuralNet::GetLayerState: the named blob of the deploy net for the policy state of env's last decision"""
+        out = np.zeros(8192)
+        n = C.c_int(0)
+        self._ck(self.L.trl_get_layer_state(self.h, int(env), layer_name.encode(), _p(out), out.size, C.byref(n)))
+        return out[:n.value].copy()
 
     def GetTerrain(self, env=0, seg=0, cap=512):
         d = np.zeros(cap, np.float32)

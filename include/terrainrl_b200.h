@@ -91,6 +91,10 @@ int trl_get_state_all(trl_handle* h, double* pose, double* vel);
 int trl_get_ctrl(trl_handle* h, int env, double* out, int cap, int* n);
 int trl_get_poli_state(trl_handle* h, int env, double* out);
 int trl_get_net_out(trl_handle* h, int env, double* out);
+/* cNeuralNet::GetLayerState (learning/NeuralNet.cpp:814-833) for the policy state of env's last decision: the blob `layer_name` of the
+ * deploy net (any top name of data/policies/<char>/nets/<char>_mace3_deploy.prototxt, e.g. "terr_conv1", "relu0", "a1_ip0", "output");
+ * what cScenarioPoliEval::RecordNNActivation writes per cycle (scenarios/ScenarioPoliEval.cpp:271-296).  *n = the blob's size. */
+int trl_get_layer_state(trl_handle* h, int env, const char* layer_name, double* out, int cap, int* n);
 int trl_get_terrain(trl_handle* h, int env, int seg, float* data, int cap, int* n, double* min_x, int* flip);
 
 /* number of engine kernels launched since creation (bench.py's gpu_launches claim) */
@@ -118,6 +122,8 @@ int trl_update_timed_detail(trl_handle* h, double dt, double* per_step_ms, doubl
 int trl_update_timeline(trl_handle* h, double dt, double* out4, int cap, int* n);
 
 int trl_debug_time_decide(trl_handle* h, int n_pending, int iters, double* ms_avg);
+/* measurement only: in-kernel phase stamps (ns from entry, 16 slots) of the batched decision path's FC kernel + event-timed conv / FC launches */
+int trl_debug_fc_phases(trl_handle* h, int n_pending, double* out_ns16, double* conv_us, double* fc_us);
 
 /* ---------------------------------------------------------------------------------------------------------------------
  * MACE trainer on the GPU -- replaces cMACETrainer / cNeuralNetLearner behind cScenarioTrainMACE:

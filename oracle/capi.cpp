@@ -191,6 +191,13 @@ void orc_forward_dynamics(OrcBatch* b, int env, const double* tau, double dt, do
     b->envs[env]->forward_dynamics(tau, dt, qdd, false);
 }
 void orc_net_eval(OrcBatch* b, const double* x, double* y) { b->scene.net.eval(x, y); }
+// cNeuralNet::GetLayerState for the blob `name` after a forward pass on x; returns its size (0: unknown name), copies up to cap values
+int orc_net_layer(OrcBatch* b, const double* x, const char* name, double* out, int cap) {
+    std::vector<double> v;
+    if (!b->scene.net.layer_state(x, name, v)) return 0;
+    for (int i = 0; i < (int)v.size() && i < cap; ++i) out[i] = v[i];
+    return (int)v.size();
+}
 void orc_com(OrcBatch* b, int env, double* com, double* com_vel) {
     Env& e = *b->envs[env];
     e.update_kin();

@@ -7,6 +7,8 @@
 // (niuzhiheng/caffe @ 7b3e6f2, README.md:14-15): parity of this forward pass is pinned only by the shipped
 // weights' behaviour, not by a numeric reference vector ("parity unpinned").
 #pragma once
+#include <map>
+#include <string>
 #include <vector>
 
 #include "pack_reader.h"
@@ -84,6 +86,59 @@ struct Net {
             raw.insert(raw.end(), h1.begin(), h1.end());
         }
         for (int i = 0; i < n_out; ++i) y[i] = raw[i] / out_scale[i] - out_off[i];
+    }
+
+    // cNeuralNet::GetLayerState (learning/NeuralNet.cpp:814-833): the named blob of the deploy net after a forward pass on x.  Every
+    // layer of data/policies/dog/nets/dog_mace3_deploy.prototxt writes its own top blob (the ReLUs are not in place), so the
+    // pre-activation values are blobs of their own.  Returns false for an unknown name.
+    bool layer_state(const double* x, const std::string& name, std::vector<double>& out) const {
+        auto conv = [](const std::vector<double>& in, int cin, int win, const std::vector<double>& w, const std::vector<double>& b, int cout, int k,
+                       std::vector<double>& pre) {
+            const int wout = win - k + 1;
+            pre.assign((size_t)cout * wout, 0.0);
+            for (int o = 0; o < cout; ++o)
+                for (int t = 0; t < wout; ++t) {
+                    double acc = b[o];
+                    for (int c = 0; c < cin; ++c)
+                        for (int kk = 0; kk < k; ++kk) acc += w[((size_t)o * cin + c) * k + kk] * in[(size_t)c * win + t + kk];
+                    pre[(size_t)o * wout + t] = acc;
+                }
+        };
+        auto relu = [](const std::vector<double>& v) { std::vector<double> r(v); for (double& e : r) e = e > 0 ? e : 0; return r; };
+        std::map<std::string, std::vector<double>> blob;
+        std::vector<double> data(n_in);
+        for (int i = 0; i < n_in; ++i) data[i] = (x[i] + in_off[i]) * in_scale[i];
+        blob["data"] = data;
+        blob["data_terrain"].assign(data.begin(), data.begin() + 200);
+        blob["data_char"].assign(data.begin() + 200, data.end());
+        blob["char_flatten0"] = blob["data_char"];
+        conv(blob["data_terrain"], 1, 200, conv0_w, conv0_b, 16, 8, blob["terr_conv0"]);
+        blob["terr_relu0"] = relu(blob["terr_conv0"]);
+        conv(blob["terr_relu0"], 16, 193, conv1_w, conv1_b, 32, 4, blob["terr_conv1"]);
+        blob["terr_relu1"] = relu(blob["terr_conv1"]);
+        conv(blob["terr_relu1"], 32, 190, conv2_w, conv2_b, 32, 4, blob["terr_conv2"]);
+        blob["terr_relu2"] = relu(blob["terr_conv2"]);
+        fc(blob["terr_relu2"], tip0_w, tip0_b, 64, false, blob["terr_ip0"]);
+        blob["terr_relu3"] = relu(blob["terr_ip0"]);
+        std::vector<double> cat = blob["terr_relu3"];
+        cat.insert(cat.end(), blob["data_char"].begin(), blob["data_char"].end());
+        blob["concat0"] = cat;
+        fc(cat, ip0_w, ip0_b, 256, false, blob["ip0"]);
+        blob["relu0"] = relu(blob["ip0"]);
+        const char* heads[4] = {"val", "a0", "a1", "a2"};
+        std::vector<double> outv;
+        for (int k = 0; k < 4; ++k) {
+            const std::string h = heads[k];
+            fc(blob["relu0"], head0_w[k], head0_b[k], 128, false, blob[h + "_ip0"]);
+            blob[h + "_relu0"] = relu(blob[h + "_ip0"]);
+            fc(blob[h + "_relu0"], head1_w[k], head1_b[k], k == 0 ? n_frags : frag, false, blob[h + "_ip1"]);
+            outv.insert(outv.end(), blob[h + "_ip1"].begin(), blob[h + "_ip1"].end());
+        }
+        blob["output"] = outv;
+        auto it = blob.find(name);
+        if (it == blob.end()) return false;
+        out = it->second;
+        return true;
     }
 };
 

@@ -452,6 +452,8 @@ int ref_ctrl_poli_state(RefCtrl* r, double* out, int cap) {
 // cNNController::LoadNet on the stand-in net (sizes installed with ref_ctrl_set_net_output first): runs the reference's own size
 // checks and cBaseControllerMACE::UpdateFragParams (number of actor-critic pairs, fragment size)
 int ref_ctrl_load_net(RefCtrl* r) { return r->ctrl->LoadNet("stand-in") ? 1 : 0; }
+// the blob source behind cNeuralNet::GetLayerState of the stand-in (cScenarioPoliEval::RecordNNActivation)
+void ref_ctrl_set_layer_cb(layer_fn cb) { g_layer_cb = cb; }
 void ref_ctrl_set_net_output(int n_in, const double* y, const double* out_scale, int n_out) {
     g_net_in = n_in; g_net_out = n_out;
     g_net_output.resize(n_out); g_out_scale.resize(n_out);

@@ -40,6 +40,11 @@ static int g_net_in = 0, g_net_out = 0;
 static Eigen::VectorXd g_out_scale;
 static net_fn g_net_cb = nullptr;
 static void* g_net_user = nullptr;
+// cNeuralNet::GetLayerState (learning/NeuralNet.cpp:814-833): the test answers with the named blob of the network it stands in for,
+// for the input of the most recent Eval (Caffe's blobs hold the last forward pass); returns the blob's size, 0 = unknown layer
+typedef int (*layer_fn)(const char* name, const double* x_last, int n_in, double* out, int cap, void* user);
+static layer_fn g_layer_cb = nullptr;
+static std::vector<double> g_last_x;
 
 static std::vector<double> flat(const Eigen::MatrixXd& M) {
     std::vector<double> v((size_t)M.rows() * M.cols());
@@ -86,10 +91,18 @@ void cNeuralNet::Eval(const Eigen::VectorXd& x, Eigen::VectorXd& out_y) const {
     const int no = GetOutputSize();
     std::vector<double> xi(x.size()), y(no);
     for (int i = 0; i < (int)x.size(); ++i) xi[i] = x[i];
+    g_last_x = xi;
     if (g_hooks.eval) g_hooks.eval(id_of(this), xi.data(), 1, y.data(), g_hooks.user);
     else g_net_cb(xi.data(), (int)xi.size(), y.data(), no, g_net_user);
     out_y.resize(no);
     for (int j = 0; j < no; ++j) out_y[j] = y[j];
+}
+void cNeuralNet::GetLayerState(const std::string& layer_name, Eigen::VectorXd& out_state) const {
+    std::vector<double> buf(16384);
+    const int n = g_layer_cb ? g_layer_cb(layer_name.c_str(), g_last_x.data(), (int)g_last_x.size(), buf.data(), (int)buf.size(), g_net_user) : 0;
+    if (n <= 0) { printf("Can't find layer named %s\n", layer_name.c_str()); out_state.resize(0); return; }
+    out_state.resize(n);
+    for (int i = 0; i < n; ++i) out_state[i] = buf[i];
 }
 void cNeuralNet::CopyModel(const cNeuralNet& other) { if (g_hooks.copy) g_hooks.copy(id_of(this), id_of(&other), g_hooks.user); }
 void cNeuralNet::CalcOffsetScale(const Eigen::MatrixXd& X, Eigen::VectorXd& out_offset, Eigen::VectorXd& out_scale) const {

@@ -9,9 +9,10 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "deepterrainrl_b200", "csrc")
-UNITS = ["trl_step.cu", "trl_step_cg.cu", "trl_host.cu", "trl_train.cu", "trl_comm.cu", "ref_loader.cpp"]
+UNITS = ["trl_step.cu", "trl_step_cg.cu", "trl_host.cu", "trl_train.cu", "trl_comm.cu", "trl_probe.cu", "ref_loader.cpp"]
 LOCAL_UNITS = ["simt_runtime.cpp", "selftest.cu"]
 VARIANT_UNITS = ["trl_step.cu", "trl_step_cg.cu"]     # the only units the TRL_* experiment knobs reach
+BUILD_ROOT = os.path.join(os.environ.get("TRL_BUILD_DIR", "/tmp/terrainrl_b200_build"), "simt")     # outside the tree: nothing here travels
 CXXFLAGS = ["-std=c++17", "-O2", "-g1", "-fPIC", "-ffp-contract=off", "-fno-strict-aliasing", "-DTRL_SIMT_EMU=1", "-w",
             "-I", os.path.join(HERE, "include"), "-I", CSRC, "-I", os.path.join(ROOT, "include")]
 
@@ -19,7 +20,7 @@ CXXFLAGS = ["-std=c++17", "-O2", "-g1", "-fPIC", "-ffp-contract=off", "-fno-stri
 def build(defines=(), force=False):
     defines = list(defines)
     tag = hashlib.md5(" ".join(defines).encode()).hexdigest()[:8] if defines else "default"
-    bdir = os.path.join(HERE, "_build", tag)
+    bdir = os.path.join(BUILD_ROOT, tag)
     os.makedirs(bdir, exist_ok=True)
     out = os.path.join(bdir, "libterrainrl_simt.so")
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, f) for f in ["simt_runtime.h"] + LOCAL_UNITS]
@@ -58,7 +59,7 @@ def _build_locked(out, bdir, deps, defines, force):
         return out
     cxx = os.environ.get("CXX", "g++")
     # the knobs only reach the env-step translation units; everything else is compiled once and shared by all variants
-    common_dir = os.path.join(HERE, "_build", "common")
+    common_dir = os.path.join(BUILD_ROOT, "common")
     os.makedirs(common_dir, exist_ok=True)
     with open(os.path.join(common_dir, ".lock"), "w") as clock:
         fcntl.flock(clock, fcntl.LOCK_EX)

@@ -95,15 +95,15 @@ def test_tuple_block_overflow_is_reported(assets):
     """a full tuple block refuses rows: the readers say so (TRL_E_TUPLE_OVERFLOW) and trl_tuples_dropped counts them"""
     import deepterrainrl_b200 as trl
     pack = os.path.join(assets, "dog_slopes_mixed.trlpack")
-    n = 4096                                   # tuple_cap = max(4096, n): every env contributes ~1 tuple per 0.45 s cycle
+    n = 4096                                   # tuple_cap = max(4096, 2 n): every env contributes ~1 tuple per 0.45 s cycle
     sc = trl.ScenarioExpMACE(pack, n)
     sc.EnableExplore(True, 0.2, 0.025, 0.002)
-    for _ in range(45):                        # 1.5 s without a hand-over: ~3 cycles per env > capacity
+    for _ in range(120):                       # 4 s without a hand-over: ~8 cycles per env > capacity
         sc.Update()
     L = sc.L
     cnt = C.c_int(0)
     rc = L.trl_num_tuples(sc.h, C.byref(cnt))
-    assert rc == 2 and cnt.value == 4096 and "overflow" in L.trl_last_error().decode()
+    assert rc == 2 and cnt.value == 8192 and "overflow" in L.trl_last_error().decode()
     with pytest.raises(RuntimeError, match="overflow"):
         sc.GetTuples()
     sc.ResetTupleBuffer()
@@ -112,4 +112,4 @@ def test_tuple_block_overflow_is_reported(assets):
     assert sc.GetNumTuples() == 0
     sc.Update()
     rows, flags, env = sc.GetTuples()          # back to normal
-    assert len(rows) < 4096
+    assert len(rows) < 8192

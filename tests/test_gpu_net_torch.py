@@ -25,3 +25,25 @@ def test_decision_kernel_matches_torch(assets, scene, n_out):
     Yt = torch_net.forward(blobs, io, isc, oo, osc, X)
     err = np.max(np.abs(Yg - Yt) / (1.0 + np.abs(Yt)))
     assert err <= 1e-10, err
+
+
+def test_layer_state_probe_matches_torch(assets):
+    """trl_get_layer_state (cNeuralNet::GetLayerState behind cScenarioPoliEval::RecordNNActivation): every blob of the deploy net for
+    an env's last decision against torch's layers"""
+    import deepterrainrl_b200 as trl
+    import torch_net
+    from pack_scene import read_pack
+    path = os.path.join(assets, "dog_slopes_mixed.trlpack")
+    blobs, io, isc, oo, osc = torch_net.blobs_from_pack(read_pack(path))
+    sc = trl.ScenarioPoliEval(path, 8)
+    for _ in range(30):
+        sc.Update()
+    acts = {}
+    torch_net.forward(blobs, io, isc, oo, osc, sc.GetPoliState(5)[None], acts)
+    assert len(acts) == 28
+    for name, a in acts.items():
+        g = sc.GetLayerState(name, 5)
+        assert g.size == a.size, name
+        assert np.max(np.abs(g - a.ravel()) / (1.0 + np.abs(a.ravel()))) <= 1e-12, name
+    with pytest.raises(RuntimeError, match="Can't find layer"):
+        sc.GetLayerState("no_such_layer", 0)

@@ -93,7 +93,7 @@ def test_update_loop_stats(assets):
     assert gs["episodes"] == os_["episodes"]
     gq, _ = g.GetStateAll()
     oq = np.stack([o.get_state(e)[0] for e in range(n)], axis=1)
-    assert np.max(np.abs(gq[0] - oq[0])) < 1e-3
+    assert np.max(np.abs(gq[0] - oq[0])) < 1e-6      # observed ~1e-11 after 3 s with the policy in the loop; a real divergence is O(1)
 
 
 def test_explore_tuples(assets):

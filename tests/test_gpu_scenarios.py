@@ -233,6 +233,14 @@ def test_baseline_config_sizes(assets):
     st = rap._stats()
     assert st["steps"] == 20 * 20 * 8192 and st["cycles"] >= 8192
     assert np.median(q[0]) > 1.5                                               # the raptor runs forward
+    # ... and against the CPU oracle on a sample of the 8192 environments (same terrain seeds 1 + env)
+    from pyoracle import Oracle
+    sample = np.array([0, 1, 777, 4095, 4096, 6001, 8191])
+    o = Oracle(os.path.join(assets, "raptor_narrow_gaps.trlpack"), len(sample), 0, terrain_seeds=(1 + sample).astype(np.uint64))
+    for _ in range(20):
+        o.update(1.0 / 30.0, 4)
+    oq = np.stack([o.get_state(e)[0] for e in range(len(sample))], axis=1)
+    assert np.max(np.abs(q[:, sample] - oq) / (1.0 + np.abs(oq))) < 1e-8
     del rap, small
     n = 2048
     seeds = (1 + 7919 * (3 * n + np.arange(n))).astype(np.uint64)              # rank 3's shard of the mixed-seed config
@@ -245,3 +253,9 @@ def test_baseline_config_sizes(assets):
     assert st["steps"] == 30 * 20 * n and st["cycles"] >= n
     d, e = goat.GetDistLog()
     assert d.size == st["episodes"]
+    sample = np.array([0, 5, 1023, 2047])
+    o = Oracle(os.path.join(assets, "goat_cliffs.trlpack"), len(sample), 0, terrain_seeds=seeds[sample])
+    for _ in range(30):
+        o.update(1.0 / 30.0, 4)
+    oq = np.stack([o.get_state(e)[0] for e in range(len(sample))], axis=1)
+    assert np.max(np.abs(q[:, sample] - oq) / (1.0 + np.abs(oq))) < 1e-8          # incl. the episode resets of these 30 updates

@@ -516,6 +516,7 @@ def test_scenario_matches_reference_code(assets, tmp_path, scene, mode, n_update
     CFN = C.CFUNCTYPE(C.c_int, C.c_void_p)
     nd = o.ndof
     DT = 1.0 / 30.0
+    NN_LAYER = b"a1_ip0"              # the blob cScenarioPoliEval::RecordNNActivation dumps in the recorded run
     st = dict(h=None, steps=0, worst_tau=0.0, worst_pose=0.0, ended=False, in_update=False, cmp=False, err=None, evals=0)
 
     def ref_state():
@@ -556,6 +557,9 @@ def test_scenario_matches_reference_code(assets, tmp_path, scene, mode, n_update
                 row[1 + o.S] = oc[11]
                 row[2 + o.S:1 + o.S + o.A] = oc[13:12 + o.num_params]
                 if st["cyc"] >= 1:           # cScenarioPoliEval::IsValidCycle: the first cycle is warm-up
+                    blob = np.zeros(8192)
+                    nb = L.orc_net_layer(o.h, _p(np.ascontiguousarray(row[1:1 + o.S])), NN_LAYER, _p(blob), 8192)
+                    rec.record_nn_activation(oc[11], blob[:nb])          # RecordNNActivation comes first in NewCycleUpdate
                     rec.consume(row[None, :], np.zeros(1, np.uint32), np.zeros(1, np.int32))
                 st["cyc"] = cyc
         except BaseException as e:          # an exception cannot cross the C frames: keep it for the main loop
@@ -597,7 +601,22 @@ def test_scenario_matches_reference_code(assets, tmp_path, scene, mode, n_update
     if record:
         from deepterrainrl_b200.records import CycleRecorder
         rec = CycleRecorder(0, o.S, o.A, str(tmp_path / "actions.txt"), str(tmp_path / "ids.txt"), vel_file=str(tmp_path / "vel.txt"),
-                            pack=pack)
+                            pack=pack, nn_activation_file=str(tmp_path / "nn.txt"), nn_activation_layer=NN_LAYER.decode())
+        # cNeuralNet::GetLayerState of the compiled scenario's (stand-in) network: the oracle network's blob for the last Eval input
+        LFN = C.CFUNCTYPE(C.c_int, C.c_char_p, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double), C.c_int, C.c_void_p)
+
+        def layer(name, x, n_in, out, cap, user):
+            xi = np.ctypeslib.as_array(x, (n_in,)).copy()
+            buf = np.zeros(cap)
+            n = L.orc_net_layer(o.h, _p(xi), name, _p(buf), cap)
+            for i in range(min(n, cap)):
+                out[i] = buf[i]
+            return n
+        lcb = LFN(layer)
+        st["lcb"] = lcb
+        ref.ref_ctrl_set_layer_cb(lcb)
+        extra += [b"-record_nn_activation=", b"true", b"-nn_activation_layer=", NN_LAYER, b"-nn_activation_output_file=",
+                  str(tmp_path / "ref_nn.txt").encode()]
         extra += [b"-record_vel=", b"true", b"-vel_output_file=", str(tmp_path / "ref_vel.txt").encode()]
         extra += [b"-record_actions=", b"true", b"-action_output_file=", str(tmp_path / "ref_actions.txt").encode(),
                   b"-record_action_id_state=", b"true", b"-action_id_state_output_file=", str(tmp_path / "ref_ids.txt").encode()]
@@ -664,6 +683,9 @@ def test_scenario_matches_reference_code(assets, tmp_path, scene, mode, n_update
                 assert n_act >= 1 and rec.cycles >= 10 and all(", " in l and ",\t" not in l for l in ref_a[:n_act])
                 assert ref_a == open(tmp_path / "actions.txt").read().splitlines()          # table + records, byte for byte
                 assert open(tmp_path / "ref_ids.txt").read() == open(tmp_path / "ids.txt").read()
+                ref_nn = open(tmp_path / "ref_nn.txt").read()
+                assert ref_nn == open(tmp_path / "nn.txt").read() and ref_nn.count("\n") == rec.cycles     # RecordNNActivation, byte for byte
+                assert all(len(l.split(",\t")) == 1 + 128 for l in ref_nn.splitlines())                      # action id + the 128 units of a1_ip0
                 ref_v = open(tmp_path / "ref_vel.txt").read().splitlines()
                 got_v = open(tmp_path / "vel.txt").read().splitlines()
                 assert len(ref_v) == len(got_v) == rec.cycles

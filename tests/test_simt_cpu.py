@@ -364,3 +364,28 @@ def test_experimental_variant_is_bit_identical(assets, defines, scene, variant_b
     assert np.array_equal(ref, _trajectory(defines, pack, 3, 130, updates=1))
     if "-DTRL_SMEM_XCHG=1" in defines or scene == "dog_slopes_mixed":
         assert np.array_equal(ref, _trajectory(defines, pack, 3, 130, seed=99, updates=1))
+
+
+def test_layer_state_probe_vs_oracle(assets):
+    """trl_get_layer_state (csrc/trl_probe.cu; cNeuralNet::GetLayerState behind RecordNNActivation) on the emulator against the oracle's
+    blobs (oracle/net.h: layer_state, itself checked against torch in tests/test_net_torch_cpu.py) for every top of the deploy net"""
+    import ctypes as C
+    from pyoracle import Oracle
+    import deepterrainrl_b200 as trl
+    pack = os.path.join(assets, "raptor_narrow_gaps.trlpack")
+    names = ["data", "data_terrain", "data_char", "char_flatten0", "terr_conv0", "terr_relu0", "terr_conv1", "terr_relu1", "terr_conv2", "terr_relu2",
+             "terr_ip0", "terr_relu3", "concat0", "ip0", "relu0", "output"] + [h + s for h in ("val", "a0", "a1", "a2") for s in ("_ip0", "_relu0", "_ip1")]
+    with simt_library():
+        sc = trl.ScenarioPoliEval(pack, 3)
+        for _ in range(3):
+            sc.Update()
+        x = sc.GetPoliState(2)
+        o = Oracle(pack, 1, 0)
+        o.L.orc_net_layer.restype = C.c_int
+        for name in names:
+            buf = np.zeros(8192)
+            n = o.L.orc_net_layer(o.h, x.ctypes.data_as(C.c_void_p), name.encode(), buf.ctypes.data_as(C.c_void_p), 8192)
+            g = sc.GetLayerState(name, 2)
+            assert n == g.size > 0, name
+            assert np.max(np.abs(g - buf[:n]) / (1.0 + np.abs(buf[:n]))) <= 1e-13, name
+        sc.close()

@@ -20,7 +20,7 @@ for _ in range(5):
     sc.BenchUpdates(2, 1.0 / 30.0, flush_l2=False)
     runs.append(sc.UpdateTimeline())
 tl = runs[-1]
-names = {0: "T", 1: "S", 2: "D", 3: "C"}
+names = {0: "T", 1: "S", 2: "D", 3: "C", 4: "F"}      # D = decision (conv stage in the batched build), F = its FC stage
 dur = {k: [] for k in names}
 for r in runs[1:]:
     for kind, idx, a, b in r:
@@ -31,7 +31,7 @@ summary = {"envs": n, "build": ("v1 one cluster per decision" if os.environ.get(
            **{f"{names[k]}_us_mean": float(np.mean(v)) * 1e3 for k, v in dur.items() if v},
            **{f"{names[k]}_us_max": float(np.max(v)) * 1e3 for k, v in dur.items() if v}}
 print(json.dumps(summary))
-for kind, idx, a, b in tl[:14]:
+for kind, idx, a, b in tl[:22]:
     print(f"  {names[kind]}{idx:<3d} {a * 1e3:8.1f} -> {b * 1e3:8.1f} us  ({(b - a) * 1e3:6.1f})")
 if out:
     json.dump({"summary": summary, "last": tl}, open(out, "w"))

@@ -20,7 +20,8 @@ def blobs_from_pack(rec):
 
 def forward(blobs, in_off, in_scale, out_off, out_scale, x, activations=None):
     """x: [n, 200 + n_char] raw policy states -> [n, n_out] unnormalised outputs (what cNeuralNet::Eval returns).
-    activations: optional dict that receives every blob of the deploy net (layer name -> [n, ...] array)."""
+    activations: optional dict that receives every blob of the deploy net under its prototxt name (pre-activation blobs and the
+    ReLU layers' own top blobs; [n, ...] arrays) -- what cNeuralNet::GetLayerState returns for that name."""
     t = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64)
     x = t(np.atleast_2d(x))
     n = x.shape[0]
@@ -29,18 +30,24 @@ def forward(blobs, in_off, in_scale, out_off, out_scale, x, activations=None):
     b = lambda name: t(blobs[name][1])
     xn = (x + t(in_off)) * t(in_scale)                                       # NormalizeInput
     terr, char = xn[:, :200].reshape(n, 1, 200), xn[:, 200:]                 # slice0 (axis 1, point 200)
-    a0 = F.relu(F.conv1d(terr, w("terr_conv0", (16, 1, 8)), b("terr_conv0")))
-    a1 = F.relu(F.conv1d(a0, w("terr_conv1", (32, 16, 4)), b("terr_conv1")))
-    a2 = F.relu(F.conv1d(a1, w("terr_conv2", (32, 32, 4)), b("terr_conv2")))
-    tip = F.relu(F.linear(a2.reshape(n, 32 * 187), w("terr_ip0", (64, 32 * 187)), b("terr_ip0")))
-    cat = torch.cat([tip, char], dim=1)                                      # concat0: terrain features first
-    h = F.relu(F.linear(cat, w("ip0", (256, 64 + n_char)), b("ip0")))
-    outs, acts = [], {"terr_conv0": a0, "terr_conv1": a1, "terr_conv2": a2, "terr_ip0": tip, "concat0": cat, "ip0": h}
+    acts = {"data": xn, "data_terrain": terr, "data_char": char, "char_flatten0": char}
+    acts["terr_conv0"] = F.conv1d(terr, w("terr_conv0", (16, 1, 8)), b("terr_conv0"))
+    a0 = acts["terr_relu0"] = F.relu(acts["terr_conv0"])
+    acts["terr_conv1"] = F.conv1d(a0, w("terr_conv1", (32, 16, 4)), b("terr_conv1"))
+    a1 = acts["terr_relu1"] = F.relu(acts["terr_conv1"])
+    acts["terr_conv2"] = F.conv1d(a1, w("terr_conv2", (32, 32, 4)), b("terr_conv2"))
+    a2 = acts["terr_relu2"] = F.relu(acts["terr_conv2"])
+    acts["terr_ip0"] = F.linear(a2.reshape(n, 32 * 187), w("terr_ip0", (64, 32 * 187)), b("terr_ip0"))
+    tip = acts["terr_relu3"] = F.relu(acts["terr_ip0"])
+    cat = acts["concat0"] = torch.cat([tip, char], dim=1)                    # concat0: terrain features first
+    acts["ip0"] = F.linear(cat, w("ip0", (256, 64 + n_char)), b("ip0"))
+    h = acts["relu0"] = F.relu(acts["ip0"])
+    outs = []
     for head in ("val", "a0", "a1", "a2"):
-        hh = F.relu(F.linear(h, w(head + "_ip0", (128, 256)), b(head + "_ip0")))
+        acts[head + "_ip0"] = F.linear(h, w(head + "_ip0", (128, 256)), b(head + "_ip0"))
+        hh = acts[head + "_relu0"] = F.relu(acts[head + "_ip0"])
         nout = blobs[head + "_ip1"][1].size
-        y = F.linear(hh, w(head + "_ip1", (nout, 128)), b(head + "_ip1"))
-        acts[head + "_ip0"] = hh; acts[head + "_ip1"] = y
+        y = acts[head + "_ip1"] = F.linear(hh, w(head + "_ip1", (nout, 128)), b(head + "_ip1"))
         outs.append(y)
     yn = torch.cat(outs, dim=1)                                              # output: val | a0 | a1 | a2
     acts["output"] = yn
