@@ -223,6 +223,9 @@ def run_config4(args, trl, rank, local_rank, world, n, dist, torch):
         if L.trl_comm_unique_id(uid) != 0:
             raise RuntimeError(L.trl_last_error().decode())
         comm = parallel.Comm(sc, 0, 1, backend="nccl", unique_id=bytes(uid))
+    if not args.train_sync:
+        if L.trl_trainer_set_async(tr.h, 1) != 0:
+            raise RuntimeError(L.trl_last_error().decode())
     sp = np.array([0.9, 0.2, 20.0, 0.025, 0.9, 0.002, 2000.0, 2000.0, 0.0])    # cScenarioTrain annealing, shortened to 2000 iterations
     L.trl_train_run_timed.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
     state = C.c_int64(0)
@@ -247,6 +250,8 @@ def run_config4(args, trl, rank, local_rank, world, n, dist, torch):
     roll_ms = sc.BenchUpdates(args.steps, DT, flush_l2=True)
     # exposed device time of one exchange (pack end -> all-gather end on the comm stream), mean over 8 updates
     gm = []
+    if not args.train_sync:
+        L.trl_trainer_set_async(tr.h, 0)
     for _ in range(8):
         sc.Update(DT); comm.GatherTuples(args.block_rows); comm.AddGathered(tr)
         gm.append(comm.LastGatherMs())
@@ -267,6 +272,7 @@ def run_config4(args, trl, rank, local_rank, world, n, dist, torch):
            "block_rows": args.block_rows, "block_bytes_per_rank": 16 + 8 * args.block_rows + 4 * args.block_rows * sc.tuple_width,
            "tuples_last_update_per_rank": [int(x) for x in counts], "tuples_dropped": int(dropped),
            "train_iters_per_update": args.train_iters, "trainer": "replicated on every rank (deterministic; no weight broadcast needed)",
+           "trainer_mode": "synchronous (between the updates)" if args.train_sync else "asynchronous (own stream, overlaps the next update; policy snapshot refreshed between updates)",
            "trainer_iter": c["iter"], "actor_iter": c["actor_iter"], "replay_tuples": c["num"], "replica_spread": spread,
            "gpu_launches": launches, "envs_per_gpu": n, "l2": "flushed between updates (256 MiB memset on the engine stream)",
            "timing": "cudaEvent on the engine stream around K x {update, pack + all-gather, hand-over, trainer iterations}, max over ranks"}
@@ -289,6 +295,9 @@ def main():
                          "trainer iterations (0 = skip)")
     ap.add_argument("--train-iters", type=int, default=4, help="trainer iterations per outer update in the config-4 block")
     ap.add_argument("--block-rows", type=int, default=1024, help="tuple rows per rank and all-gather in the config-4 block")
+    ap.add_argument("--train-sync", type=int, default=0,
+                    help="config-4 block: 1 = the trainer runs between the updates (synchronous); default 0 = the reference's asynchronous "
+                         "trainer semantics: hand-over + training overlap the next update on their own stream")
     ap.add_argument("--presim", type=float, default=4.0,
                     help="seconds of simulated time run (untimed) before warm-up so gait cycles / episodes of the envs "
                          "are desynchronised like in a long evaluation (SURVEY §8d: warm-up 2 s sim)")

@@ -162,7 +162,8 @@ struct trl_comm {
     bool external = false;
     trl_collectives coll{};
     cudaStream_t stream = nullptr;        // collectives run here; ordered against the handle's stream with events
-    cudaEvent_t ev_packed = nullptr, ev_gathered = nullptr, ev_misc = nullptr;
+    cudaEvent_t ev_packed = nullptr, ev_gathered = nullptr, ev_misc = nullptr, ev_consumed = nullptr;
+    bool consumed_pending = false;        // a consumer on another stream has yet to finish reading recv (trl_comm_mark_consumed)
     int block_rows = 0, width = 0;
     size_t block_bytes = 0;
     unsigned char *send = nullptr, *recv = nullptr;
@@ -222,6 +223,7 @@ static int comm_common(trl_handle* h, trl_comm* c) {
     CCK(cudaEventCreate(&c->ev_packed));
     CCK(cudaEventCreate(&c->ev_gathered));
     CCK(cudaEventCreateWithFlags(&c->ev_misc, cudaEventDisableTiming));
+    CCK(cudaEventCreateWithFlags(&c->ev_consumed, cudaEventDisableTiming));
     c->width = 1 + h->B.S + h->B.A + h->B.S;
     c->env_offset = (long long)c->rank * h->n;
     CCK(calloc_dev(c, &c->dropped, 1));
@@ -303,6 +305,7 @@ int trl_comm_destroy(trl_handle* h) {
     if (c->ev_packed) cudaEventDestroy(c->ev_packed);
     if (c->ev_gathered) cudaEventDestroy(c->ev_gathered);
     if (c->ev_misc) cudaEventDestroy(c->ev_misc);
+    if (c->ev_consumed) cudaEventDestroy(c->ev_consumed);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     h->comm = nullptr;
@@ -339,6 +342,7 @@ int trl_gather_tuples(trl_handle* h, int block_rows) {
     CCK(cudaGetLastError());
     CCK(cudaEventRecord(c->ev_packed, h->stream));
     CCK(cudaStreamWaitEvent(c->stream, c->ev_packed, 0));
+    if (c->consumed_pending) { CCK(cudaStreamWaitEvent(c->stream, c->ev_consumed, 0)); c->consumed_pending = false; }
     if (coll_all_gather(c, c->send, c->recv, c->block_bytes)) return 1;
     CCK(cudaEventRecord(c->ev_gathered, c->stream));
     c->gathered = true;
@@ -464,6 +468,21 @@ int trl_comm_view(trl_handle* h, trl_comm_blocks* out) {
     CCK(cudaStreamWaitEvent(h->stream, c->ev_gathered, 0));
     out->recv = c->recv; out->block_bytes = c->block_bytes; out->block_rows = c->block_rows; out->width = c->width;
     out->world = c->world; out->rank = c->rank;
+    return 0;
+}
+int trl_comm_view_on(trl_handle* h, trl_comm_blocks* out, cudaStream_t consumer) {
+    if (!h || !h->comm) return trl_fail("trainer: the scenario has no communicator (trl_comm_init first)");
+    trl_comm* c = h->comm;
+    if (!c->gathered) return trl_fail("trainer: nothing gathered yet (trl_gather_tuples first)");
+    CCK(cudaStreamWaitEvent(consumer, c->ev_gathered, 0));
+    out->recv = c->recv; out->block_bytes = c->block_bytes; out->block_rows = c->block_rows; out->width = c->width;
+    out->world = c->world; out->rank = c->rank;
+    return 0;
+}
+int trl_comm_mark_consumed(trl_handle* h, cudaStream_t consumer) {
+    if (!h || !h->comm) return 0;
+    CCK(cudaEventRecord(h->comm->ev_consumed, consumer));
+    h->comm->consumed_pending = true;
     return 0;
 }
 int trl_comm_broadcast_list(trl_handle* h, double* const* arrays, const size_t* counts, int n, int root) {

@@ -1,5 +1,7 @@
 // deepterrainrl_b200 -- what the trainer (trl_train.cu) needs from the multi-GPU exchange (trl_comm.cu); private to csrc/
 #pragma once
+#include <cuda_runtime.h>
+
 #include <cstddef>
 
 struct trl_handle;
@@ -15,3 +17,7 @@ struct trl_comm_blocks {
 int trl_comm_view(trl_handle* h, trl_comm_blocks* out);
 int trl_comm_broadcast_list(trl_handle* h, double* const* arrays, const size_t* counts, int n, int root);
 int trl_comm_replica_spread(trl_handle* h, const double* theta, size_t n, double* out);
+// the consumer of the gathered blocks runs on `consumer` (not the handle's stream): orders it behind the last all-gather, and makes
+// the next all-gather wait until `mark_consumed` has been recorded on that stream
+int trl_comm_view_on(trl_handle* h, trl_comm_blocks* out, cudaStream_t consumer);
+int trl_comm_mark_consumed(trl_handle* h, cudaStream_t consumer);

@@ -125,7 +125,7 @@ __device__ __forceinline__ void conv4_dmma(const double* __restrict__ act, const
         const double* a0p = act + min(mt * 8 + g, WOUT - 1) + t4;
         const double* a1p = act + min((two ? mt2 : mt) * 8 + g, WOUT - 1) + t4;
         double c00 = b0, c01 = b1, c10 = b0, c11 = b1;
-#pragma unroll 8
+#pragma unroll 4
         for (int c = 0; c < CIN; ++c) {
             const double b = brow[4 * c];
             dmma_8x8x4(c00, c01, a0p[c * WIN], b);
@@ -189,7 +189,8 @@ __device__ void conv_stage_cluster(cg::cluster_group& cluster, const NetWeights&
     cluster.sync();   // peers read this CTA's A1 slice until here; the next decision overwrites it
 }
 
-__global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kDecideThreads, 1)
+// 64 registers: two of these CTAs fit one SM, and one fits beside two resident env-step CTAs (a whole-SM CTA waits for all four to drain)
+__global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kDecideThreads, 2)
 trl_decide_conv_kernel(Buffers B, NetWeights W, double* __restrict__ act2, int list) {
     TRL_DYN_SHARED(double, sh);
     cg::cluster_group cluster = cg::this_cluster();

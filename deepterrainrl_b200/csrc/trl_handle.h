@@ -29,8 +29,9 @@ struct trl_handle {
     std::vector<int64_t> net_counts;
     int* done_count = nullptr;
     cudaStream_t stream = nullptr;
-    cudaStream_t aux_stream = nullptr;           // high-priority side streams: decisions + catch-up launches (overlapped schedule),
-    cudaStream_t aux_stream2 = nullptr;          // alternating by env-step
+    cudaStream_t aux_stream = nullptr;           // = side[0]
+    cudaStream_t side[8] = {nullptr};            // high-priority side streams: decisions + catch-up launches of env-step l run on side[l % lag]
+    int lag = 6;                                 // overlap depth: env-steps a pending env may trail the main launches (TRL_LAG, 1..7)
     std::vector<cudaEvent_t> fork_events;        // dependencies between the two streams inside one update
     bool overlap = true;                         // TRL_SERIAL_SCHEDULE=1 turns the overlapped schedule off
     int decide_grid = 288;   // CTAs of the decision launch: a multiple of its cluster size (create_common sizes it from the SM count)
@@ -38,8 +39,8 @@ struct trl_handle {
     // batched decision path (trl_decide2.cuh): conv2 outputs of the pending decisions, the TMA descriptors over them and over the
     // terr_ip0 weights (re-encoded whenever the weight pointer changes), number of FC-stage clusters
     bool decide_v2 = true;                       // TRL_DECIDE_V1=1 selects the one-cluster-per-decision kernel (trl_decide.cuh)
-    double* act2[2] = {nullptr, nullptr};        // one scratch matrix per side stream (the decisions of two env-steps can overlap)
-    trl::FcMaps fc_maps[2];
+    double* act2[8] = {nullptr};                 // one scratch matrix per side stream (the decisions of several env-steps can overlap)
+    trl::FcMaps fc_maps[8];
     const double* fc_maps_w = nullptr;
     int fc_clusters = 2;
     int64_t launches = 0;

@@ -40,6 +40,7 @@ cudaError_t upload_model(const trl::ModelConst& mc);
 void launch_step(const trl::Buffers& B, double h, int flags, int lists, cudaStream_t st);
 }  // namespace trl_cg
 
+
 using namespace trl;
 
 // both builds of the step kernels keep their own copy of the model constants
@@ -397,7 +398,7 @@ static int encode_rows_map(CUtensorMap* map, const double* base, uint64_t rows, 
 static int ensure_fc_maps(trl_handle* h) {
     if (!h->decide_v2 || !h->mc.has_net || !h->act2[0] || !h->W.tip0_w) return 0;
     if (h->fc_maps_w == h->W.tip0_w) return 0;
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < h->lag; ++k) {
         h->fc_maps[k].w_ptr = h->W.tip0_w;
         h->fc_maps[k].a_ptr = h->act2[k];
         h->fc_maps[k].a_rows = h->n;
@@ -432,15 +433,17 @@ static void destroy_graphs(trl_handle* h) {
 //
 //   serial schedule      T  S_0  D_0  S_1  D_1 ... S_{ns-1}  D_{ns-1}  S_end
 //   overlapped schedule  main stream    T  S_0  S_1  S_2  S_3  S_4 ...  S_{ns-1}  S_end          (back to back)
-//                        side stream 0        D_0 -> C_0 [steps 1, 2]     D_2 -> C_2 [steps 3, 4] ...
+//   (lag = 2 shown)      side stream 0        D_0 -> C_0 [steps 1, 2]     D_2 -> C_2 [steps 3, 4] ...
 //                        side stream 1             D_1 -> C_1 [steps 2, 3]     D_3 -> C_3 ...
 //
-// In the overlapped schedule the envs that reach a cycle boundary in S_i wait for D_i and are then advanced by the catch-up
-// launch C_i (same kernel, one warp per list entry, registers live across its two env-steps) while S_{i+1} and S_{i+2} skip them;
-// S_{i+3} needs C_i.  Three pending lists rotate (S_i appends to list i % 3, which C_{i-3} re-armed).  Every env still advances
-// by exactly one env-step per launch equivalent, so results are identical to the serial schedule
-// (tests/test_gpu_scenarios.py::test_overlap_matches_serial).  Measured reason (profiles/timeline_r02_*.json): with one step of
-// slack the update was bound by the chain D_i -> C_i (~160 us) rather than by the step launch (~140 us).
+// In the overlapped schedule the envs that reach a cycle boundary in S_l wait for D_l and are then advanced by the catch-up
+// launch C_l (same kernel, one warp per list entry, registers live across its `lag` env-steps) while S_{l+1} .. S_{l+lag} skip
+// them; S_{l+lag+1} needs C_l.  lag + 1 pending lists rotate (S_l appends to list l % (lag + 1), which C_{l-lag-1} re-armed); side
+// stream l % lag carries D_l and C_l.  Every env still advances by exactly one env-step per launch equivalent, so results are
+// the same as in the serial schedule up to the rounding of the catch-up build (a second instantiation of the kernel source with the
+// env-step loop: ~1e-12 after 45 updates; tests/test_gpu_scenarios.py::test_overlap_matches_serial).  Why several steps of slack
+// (profiles/timeline_r02_*.txt): a lone warp needs ~110 us per env-step whatever else runs, and the decision kernels wait for SM
+// resources the step launch holds, so the chain D_l -> C_l is ~2.5 step launches long; with one step of slack it bounded the update.
 // optional recorder of a timeline (trl_update_timeline): an event pair around every launch, on the stream it is launched on
 struct Timeline {
     std::vector<cudaEvent_t> beg, end, fork;
@@ -476,10 +479,11 @@ static void enqueue_update(trl_handle* h, double dt, bool overlap, Timeline* tl 
         TL_OPEN(A, 1, ns); launch_step(h->B, step, 1 | 4, 0, A); TL_CLOSE(A);
         return;
     }
-    // Overlapped schedule, two env-steps deep.  Main stream: T S_0 S_1 S_2 ... S_{ns-1} S_end back to back.  The envs that reach a
-    // cycle boundary in S_i (list i % 3) are served on a side stream (two side streams alternate): D_i decides them, the catch-up
-    // launch C_i then advances exactly those envs by TWO env-steps (i + 1 and i + 2; one if the update ends first), while S_{i+1}
-    // and S_{i+2} skip them.  S_{i+3} needs C_i.  The chain D_i -> C_i therefore has two step launches of slack instead of none.
+    // Overlapped schedule, `lag` env-steps deep.  Main stream: T S_0 S_1 S_2 ... S_{ns-1} S_end back to back.  The envs that reach a
+    // cycle boundary in S_l (list l % (lag + 1)) are served on side stream l % lag: D_l decides them, the catch-up launch C_l then
+    // advances exactly those envs by `lag` env-steps (fewer if the update ends first) while S_{l+1} .. S_{l+lag} skip them.
+    // S_{l+lag+1} needs C_l.  The chain D_l -> C_l therefore has `lag` step launches of slack.
+    const int lag = h->lag, nl = lag + 1;
     std::vector<cudaEvent_t>& fe = tl ? tl->fork : h->fork_events;
     if ((int)fe.size() < 2 * ns + 2) {
         size_t old = fe.size();
@@ -487,39 +491,39 @@ static void enqueue_update(trl_handle* h, double dt, bool overlap, Timeline* tl 
         for (size_t i = old; i < fe.size(); ++i) cudaEventCreateWithFlags(&fe[i], cudaEventDisableTiming);
     }
     cudaEvent_t* ev_s = fe.data();            // ev_s[i]: S_i done
-    cudaEvent_t* ev_c = fe.data() + ns + 1;   // ev_c[i]: C_i (i < ns - 1) / D_{ns-1} done
-    cudaStream_t side[2] = {h->aux_stream, h->aux_stream2};
-    auto lists_of = [](int app, int prev) { return (app % 3) | ((prev % 3) << 2); };
-    TL_OPEN(A, 1, 0); launch_step(h->B, step, 2, lists_of(0, 0), A); TL_CLOSE(A);
+    cudaEvent_t* ev_c = fe.data() + ns + 1;   // ev_c[l]: C_l (l < ns - 1) / D_{ns-1} done
+    auto lists_of = [&](int app, int prev, int reps) { return (app % nl) | ((prev % nl) << 3) | (reps << 6); };
+    auto main_step = [&](int flags, int lists, int) { launch_step(h->B, step, flags, lists, A); };
+    TL_OPEN(A, 1, 0); main_step(2, lists_of(0, 0, 0), 1); TL_CLOSE(A);
     cudaEventRecord(ev_s[0], A);
     for (int i = 1; i < ns; ++i) {
         // side work for the envs that became due in S_{i-1}
-        const int l = i - 1;
-        cudaStream_t X = side[l & 1];
+        const int l = i - 1, slot = l % lag;
+        cudaStream_t X = h->side[slot];
         cudaStreamWaitEvent(X, ev_s[l], 0);
-        TL_OPEN(X, 2, l); enqueue_decide(h, l % 3, 0, X, 1, l & 1); TL_CLOSE(X); TL_OPEN(X, 4, l); enqueue_decide(h, l % 3, 0, X, 2, l & 1); TL_CLOSE(X);
-        const int reps = std::min(2, ns - 1 - l);     // equivalents l + 1 (and l + 2) of the main launches; S_end is never caught up
-        TL_OPEN(X, 3, l); trl_cg::launch_step(h->B, step, 1 | 2 | 16 | (reps == 2 ? 32 : 0), lists_of(l + 1, l), X); TL_CLOSE(X);
+        TL_OPEN(X, 2, l); enqueue_decide(h, l % nl, 0, X, 1, slot); TL_CLOSE(X); TL_OPEN(X, 4, l); enqueue_decide(h, l % nl, 0, X, 2, slot); TL_CLOSE(X);
+        const int reps = std::min(lag, ns - 1 - l);     // equivalents l + 1 .. l + reps of the main launches; S_end is never caught up
+        TL_OPEN(X, 3, l); trl_cg::launch_step(h->B, step, 1 | 2 | 16, lists_of(l + 1, l, reps), X); TL_CLOSE(X);
         cudaEventRecord(ev_c[l], X);
-        if (i >= 3) cudaStreamWaitEvent(A, ev_c[i - 3], 0);
-        TL_OPEN(A, 1, i); launch_step(h->B, step, 1 | 2 | 8, lists_of(i, i), A); TL_CLOSE(A);
+        if (i >= nl) cudaStreamWaitEvent(A, ev_c[i - nl], 0);
+        TL_OPEN(A, 1, i); main_step(1 | 2 | 8, lists_of(i, i, 0), i + 1); TL_CLOSE(A);
         cudaEventRecord(ev_s[i], A);
     }
     {
-        const int l = ns - 1;
-        cudaStream_t X = side[l & 1];
+        const int l = ns - 1, slot = l % lag;
+        cudaStream_t X = h->side[slot];
         cudaStreamWaitEvent(X, ev_s[l], 0);
-        TL_OPEN(X, 2, l); enqueue_decide(h, l % 3, 1, X, 1, l & 1); TL_CLOSE(X); TL_OPEN(X, 4, l); enqueue_decide(h, l % 3, 1, X, 2, l & 1); TL_CLOSE(X);
+        TL_OPEN(X, 2, l); enqueue_decide(h, l % nl, 1, X, 1, slot); TL_CLOSE(X); TL_OPEN(X, 4, l); enqueue_decide(h, l % nl, 1, X, 2, slot); TL_CLOSE(X);
         cudaEventRecord(ev_c[l], X);
     }
-    for (int l = std::max(0, ns - 3); l < ns; ++l) cudaStreamWaitEvent(A, ev_c[l], 0);
-    TL_OPEN(A, 1, ns); launch_step(h->B, step, 1 | 4, 0, A); TL_CLOSE(A);
+    for (int l = std::max(0, ns - nl); l < ns; ++l) cudaStreamWaitEvent(A, ev_c[l], 0);     // every side stream joins here
+    TL_OPEN(A, 1, ns); main_step(1 | 4, 0, ns + 1); TL_CLOSE(A);
 #undef TL_OPEN
 #undef TL_CLOSE
 }
 static int update_launches(const trl_handle* h, bool overlap) {
     const int ns = h->num_update_steps, d = num_decide_launches(h);
-    return overlap ? (2 + d) * ns : (1 + d) * ns + 2;    // terrain + S_0..S_{ns-1} + D_0..D_{ns-1} + S_end (+ C_1..C_{ns-1})
+    return overlap ? (2 + d) * ns : (1 + d) * ns + 2;    // terrain + S_0..S_{ns-1} + D_0..D_{ns-1} + S_end (+ C_0..C_{ns-2})
 }
 
 extern "C" {
@@ -587,8 +591,11 @@ static trl_handle* create_common(trl_handle* h, int num_envs, int device, int mo
     {
         int lo = 0, hi = 0;
         cudaDeviceGetStreamPriorityRange(&lo, &hi);   // hi = numerically lowest = greatest priority
-        if (cudaStreamCreateWithPriority(&h->aux_stream, cudaStreamNonBlocking, hi) != cudaSuccess) return bail("cudaStreamCreate (side) failed");
-        if (cudaStreamCreateWithPriority(&h->aux_stream2, cudaStreamNonBlocking, hi) != cudaSuccess) return bail("cudaStreamCreate (side 2) failed");
+        const char* lg = std::getenv("TRL_LAG");
+        if (lg && lg[0]) h->lag = std::min(kMaxLists - 1, std::max(1, std::atoi(lg)));
+        for (int k = 0; k < h->lag; ++k)
+            if (cudaStreamCreateWithPriority(&h->side[k], cudaStreamNonBlocking, hi) != cudaSuccess) return bail("cudaStreamCreate (side) failed");
+        h->aux_stream = h->side[0];
         const char* serial = std::getenv("TRL_SERIAL_SCHEDULE");
         h->overlap = !(serial && serial[0] == '1');
     }
@@ -620,14 +627,14 @@ static trl_handle* create_common(trl_handle* h, int num_envs, int device, int mo
               ck(dalloc(h, &B.terrain, n * 2 * kTerrainCap), "alloc terrain") && ck(dalloc(h, &B.poli_state, n * B.S), "alloc poli") &&
               ck(dalloc(h, &B.net_out, n * kMaxNetOut), "alloc net_out") && ck(dalloc(h, &B.tuple_sbeg, n * B.S), "alloc sbeg") &&
               ck(dalloc(h, &B.tuple_action, n * kNumParams), "alloc action") && ck(dalloc(h, &B.com_stash, 2 * n), "alloc com") &&
-              ck(dalloc(h, &B.pending_list, 3 * n), "alloc pending") && ck(dalloc(h, &B.pending_count, 4), "alloc pc") &&
-              ck(dalloc(h, &B.catchup_done, 4), "alloc cd") &&
+              ck(dalloc(h, &B.pending_list, (size_t)(h->lag + 1) * n), "alloc pending") && ck(dalloc(h, &B.pending_count, kMaxLists), "alloc pc") &&
+              ck(dalloc(h, &B.catchup_done, kMaxLists + 1), "alloc cd") &&
               ck(dalloc(h, &B.tuples, (size_t)B.tuple_cap * (1 + B.S + A + B.S)), "alloc tuples") &&
               ck(dalloc(h, &B.tuple_flags, (size_t)B.tuple_cap), "alloc tf") && ck(dalloc(h, &B.tuple_env, (size_t)B.tuple_cap), "alloc te") &&
               ck(dalloc(h, &B.tuple_count, 1), "alloc tc") && ck(dalloc(h, &B.dist_log, (size_t)B.dist_cap), "alloc dl") &&
               ck(dalloc(h, &B.dist_env, (size_t)B.dist_cap), "alloc de") && ck(dalloc(h, &B.dist_count, 1), "alloc dc") &&
-              ck(dalloc(h, &h->done_count, 1), "alloc done") && ck(dalloc(h, &h->d_ex, 1), "alloc ex") &&
-              (!h->mc.has_net || (ck(dalloc(h, &h->act2[0], n * (size_t)5984), "alloc act2") && ck(dalloc(h, &h->act2[1], n * (size_t)5984), "alloc act2")));
+              ck(dalloc(h, &h->done_count, 1), "alloc done") && ck(dalloc(h, &h->d_ex, 1), "alloc ex");
+    for (int k = 0; ok && h->mc.has_net && k < h->lag; ++k) ok = ck(dalloc(h, &h->act2[k], n * (size_t)5984), "alloc act2");
     if (ok) ok = ck(cudaMemcpy(h->d_ex, &h->ex, sizeof(ExpSettings), cudaMemcpyHostToDevice), "upload ex");
     if (!ok) return bail("");
     if (h->mc.has_net) {
@@ -666,8 +673,8 @@ int trl_destroy(trl_handle* h) {
     if (h->snap_copied) cudaEventDestroy(h->snap_copied);
     if (h->snap_host) cudaFreeHost(h->snap_host);
     for (void* p : h->allocs) cudaFree(p);
-    if (h->aux_stream) { cudaStreamSynchronize(h->aux_stream); cudaStreamDestroy(h->aux_stream); }
-    if (h->aux_stream2) { cudaStreamSynchronize(h->aux_stream2); cudaStreamDestroy(h->aux_stream2); }
+    for (int k = 0; k < 8; ++k)
+        if (h->side[k]) { cudaStreamSynchronize(h->side[k]); cudaStreamDestroy(h->side[k]); }
     for (auto e : h->fork_events) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -684,7 +691,7 @@ int trl_seed_terrain(trl_handle* h, const uint64_t* seeds, int n) {
         cudaError_t e = cudaMemcpyAsync(d_seeds, seeds, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream);
         if (e != cudaSuccess) { cudaFree(d_seeds); return fail(std::string("trl_seed_terrain: ") + cudaGetErrorString(e)); }
     }
-    cudaError_t e = cudaMemsetAsync(h->B.pending_count, 0, 16, h->stream);
+    cudaError_t e = cudaMemsetAsync(h->B.pending_count, 0, kMaxLists * 4, h->stream);
     if (e == cudaSuccess) {
         launch_reset(h->B, d_seeds, nullptr, h->n, 1, h->stream);
         h->launches += 1;
@@ -763,7 +770,7 @@ int trl_sync(trl_handle* h) {
     if (!h) return fail("trl_sync: null handle");
     CK(cudaStreamSynchronize(h->stream));
     int fault = 0;
-    CK(cudaMemcpy(&fault, h->B.catchup_done + 3, 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&fault, h->B.catchup_done + kMaxLists, 4, cudaMemcpyDeviceToHost));
     if (fault)
         return fail("an env finished a gait cycle inside a catch-up launch (cycle shorter than three env-steps): the overlapped schedule "
                     "cannot serve it; run with TRL_SERIAL_SCHEDULE=1");
@@ -1368,8 +1375,7 @@ int trl_update_timeline(trl_handle* h, double dt, double* out, int cap, int* n_o
     if (ensure_model(h)) return fail("model upload failed");
     Timeline tl;
     CK(cudaStreamSynchronize(h->stream));
-    CK(cudaStreamSynchronize(h->aux_stream));
-    CK(cudaStreamSynchronize(h->aux_stream2));
+    for (int k = 0; k < h->lag; ++k) CK(cudaStreamSynchronize(h->side[k]));
     (void)cudaGetLastError();        // a stale, already reported status of an earlier call must not be charged to this run
     enqueue_update(h, dt, h->overlap, &tl);
     {
@@ -1378,8 +1384,7 @@ int trl_update_timeline(trl_handle* h, double dt, double* out, int cap, int* n_o
         if (!tl.err.empty()) return fail("trl_update_timeline: " + tl.err);
     }
     CK(cudaStreamSynchronize(h->stream));
-    CK(cudaStreamSynchronize(h->aux_stream));
-    CK(cudaStreamSynchronize(h->aux_stream2));
+    for (int k = 0; k < h->lag; ++k) CK(cudaStreamSynchronize(h->side[k]));
     h->launches += update_launches(h, h->overlap);
     const int n = (int)tl.beg.size();
     for (int k = 0; k < n; ++k) {

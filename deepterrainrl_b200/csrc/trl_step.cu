@@ -32,7 +32,7 @@
 // every global load bypasses L1.  The cg build serves the catch-up launches of the overlapped schedule: they read env state the
 // decision kernel has just written, while step CTAs running on the same SM may already have pulled the neighbouring envs'
 // words of the same 32-byte sectors into that SM's L1.
-#ifdef TRL_CG_VARIANT
+#if defined(TRL_CG_VARIANT)
 #define TRL_IMPL_NS trl_cg
 #else
 #define TRL_IMPL_NS trl
@@ -49,7 +49,9 @@ constexpr unsigned kFull = 0xffffffffu;
 #ifndef TRL_STEP_MIN_BLOCKS
 #define TRL_STEP_MIN_BLOCKS 4   // CTAs of 4 warps per SM the register budget is sized for
 #endif
-constexpr int kStepSkipPending = 8, kStepCatchUp = 16, kStepTwice = 32;   // flag bits of trl_step_kernel beyond ctrl (1) / phys (2) / end (4)
+constexpr int kStepSkipPending = 8, kStepCatchUp = 16;   // flag bits of trl_step_kernel beyond ctrl (1) / phys (2) / end (4)
+// `lists` packs: bits 0-2 the list new boundary envs are appended to, bits 3-5 the list a catch-up launch serves, bits 6-9 the number
+// of env-steps a catch-up launch advances its envs by
 constexpr double kClearMargin = 0.05;   // >= contact_tol * sqrt(1 + slope^2) for any slope the generators produce
 constexpr int kZeroLane = 31;   // always idle (nj <= 23): its per-link registers are zero, used as the "no source" lane
 constexpr int kTri = kMaxDof * (kMaxDof + 1) / 2;   // 276
@@ -1182,11 +1184,12 @@ trl_step_kernel(Buffers B, double h, int flags, int lists) {
     }
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // pending-decision lists (three, used round robin by successive env-steps): envs that reach a cycle boundary in this launch are
-    // appended to list `app`; an env's I_PENDING tag is 1 + the list it was last appended to.  The decision of list l is made one
-    // launch later and the env is then caught up over two env-steps by a side launch (trl_host.cu: enqueue_update), so the main
-    // launch of step j skips the envs tagged with the lists of steps j - 1 and j - 2; a tag of list j % 3 is three steps old.
-    const int app = lists & 3, prev = (lists >> 2) & 3;
+    // pending-decision lists (lag + 1 of them, used round robin by successive env-steps): envs that reach a cycle boundary in this
+    // launch are appended to list `app`; an env's I_PENDING tag is 1 + the list it was last appended to.  The decision of a list is
+    // made on a side stream and its envs are then caught up over `lag` env-steps by a side launch (trl_host.cu: enqueue_update), so
+    // the main launch of step j skips every tagged env except those of list j % (lag + 1), whose tag is lag + 1 steps old.
+    const int app = lists & 7, prev = (lists >> 3) & 7;
+
     int env = blockIdx.x * kWarpsPerBlock + warp;
     if (flags & kStepCatchUp) {
         // catch-up launch: one warp per entry of list `prev`, after the decision kernel has served it.
@@ -1202,7 +1205,7 @@ trl_step_kernel(Buffers B, double h, int flags, int lists) {
         // overlapped main launch: envs waiting for a decision or being caught up are not touched
         const int tag = L.i(I_PENDING);
         if (tag != 0 && tag != 1 + app) return;
-        if (tag == 1 + app && lane == 0) L.i(I_PENDING) = 0;   // stale tag of three steps ago (already caught up)
+        if (tag == 1 + app && lane == 0) L.i(I_PENDING) = 0;   // stale tag of lag + 1 steps ago (already caught up)
     } else if (!(flags & kStepCatchUp) && (flags & 1) && lane == 0) {
         L.i(I_PENDING) = 0;    // serial schedule / end of the update: every decision has been served before this launch
     }
@@ -1217,7 +1220,7 @@ trl_step_kernel(Buffers B, double h, int flags, int lists) {
     bool have_k = false;       // warp-uniform: the controller half ran and nothing has moved the state since
 #endif
 #ifdef TRL_CG_VARIANT
-    const int reps = (flags & kStepTwice) ? 2 : 1;     // a catch-up launch advances its envs by two env-steps (registers stay live)
+    const int reps = max(1, (lists >> 6) & 15);        // a catch-up launch advances its envs by several env-steps (registers stay live)
 #else
     constexpr int reps = 1;                            // catch-up launches are the other build of this file (trl_step_cg.cu)
 #endif
@@ -1358,9 +1361,9 @@ trl_step_kernel(Buffers B, double h, int flags, int lists) {
                 B.com_stash[env] = comx; B.com_stash[B.n + env] = comy;
                 L.i(I_FIRST_CYCLE) = 0;
                 if (flags & kStepCatchUp) {
-                    // a gait cycle shorter than three env-steps (the shipped controllers' timed states alone last 150): the side
+                    // a gait cycle shorter than the catch-up depth (the shipped controllers' timed states alone last 150 env-steps): the side
                     // launch cannot hand the env to a decision in time -- flag it (trl_sync reports; TRL_SERIAL_SCHEDULE=1 runs it)
-                    B.catchup_done[3] = 1;
+                    B.catchup_done[kMaxLists] = 1;
                 }
                 L.i(I_PENDING) = 1 + app;
                 int slot = atomicAdd(&B.pending_count[app], 1);
@@ -1477,7 +1480,7 @@ void launch_reset(const Buffers& B, const uint64_t* seeds, const int* env_ids, i
 
 }  // namespace TRL_IMPL_NS
 
-#ifndef TRL_CG_VARIANT
+#if !defined(TRL_CG_VARIANT)
 #include "trl_decide.cuh"
 #include "trl_decide2.cuh"
 #endif

@@ -682,6 +682,13 @@ struct trl_trainer {
     uint32_t* stage_flags = nullptr;
     int stage_cap = 0;
     long long gather_cap = 0;          // entries of valid / slot / order (>= stage_cap; grown by trl_trainer_add_gathered)
+    // asynchronous mode (trl_trainer_set_async; the reference's cAsyncMACETrainer): hand-over and training run on their own stream
+    // beside the next update; the scenario evaluates a snapshot of the net that is refreshed between updates
+    cudaStream_t async_stream = nullptr;
+    cudaEvent_t ev_snap = nullptr, ev_trained = nullptr;
+    bool async = false, trained_pending = false, job_pending = false;
+    double* snap = nullptr;            // [P + 2 S + 2 n_out]: theta, in_off, in_scale, out_off, out_scale as the decision kernels see them
+    cudaStream_t work() const { return async ? async_stream : h->stream; }
     int64_t launches = 0;
 };
 
@@ -903,6 +910,10 @@ trl_trainer* trl_trainer_create(trl_handle* h, const double* p) {
 void trl_trainer_orphan(trl_trainer* t) {
     if (!t || !t->h) return;
     cudaStreamSynchronize(t->h->stream);
+    if (t->async_stream) {
+        cudaStreamSynchronize(t->async_stream); cudaStreamDestroy(t->async_stream); cudaEventDestroy(t->ev_snap); cudaEventDestroy(t->ev_trained);
+        t->async_stream = nullptr; t->async = false;
+    }
     if (t->train_graph) { cudaGraphExecDestroy(t->train_graph); t->train_graph = nullptr; }
     for (void* q : t->allocs) cudaFree(q);
     t->allocs.clear();
@@ -910,6 +921,11 @@ void trl_trainer_orphan(trl_trainer* t) {
     t->h = nullptr;
 }
 #define TRL_TRAINER_LIVE(t) do { if (!(t) || !(t)->h) return trl_fail("trainer: the scenario it was attached to has been destroyed"); } while (0)
+static cudaError_t trainer_sync(trl_trainer* t) {
+    cudaError_t e = cudaStreamSynchronize(t->h->stream);
+    if (e == cudaSuccess && t->async_stream) e = cudaStreamSynchronize(t->async_stream);
+    return e;
+}
 
 int trl_trainer_destroy(trl_trainer* t) {
     if (!t) return 0;
@@ -929,6 +945,7 @@ int trl_trainer_destroy(trl_trainer* t) {
     trl_drop_graphs(h);
     h->trainer = nullptr;
     if (t->train_graph) cudaGraphExecDestroy(t->train_graph);
+    if (t->async_stream) { cudaStreamSynchronize(t->async_stream); cudaStreamDestroy(t->async_stream); cudaEventDestroy(t->ev_snap); cudaEventDestroy(t->ev_trained); }
     for (void* q : t->allocs) cudaFree(q);
     delete t;
     return 0;
@@ -973,24 +990,27 @@ int trl_trainer_add_gathered(trl_trainer* t) {
     TRL_TRAINER_LIVE(t);
     trl_handle* h = t->h;
     trl_comm_blocks v;
-    if (trl_comm_view(h, &v)) return 1;
+    cudaStream_t ws = t->work();
+    if (t->async ? trl_comm_view_on(h, &v, ws) : trl_comm_view(h, &v)) return 1;
     if (v.width != t->d.Wd) return trl_fail("trl_trainer_add_gathered: tuple width mismatch");
     if ((long long)v.world * v.block_rows > t->gather_cap) {
         // valid / slot / order are indexed by rank * block_rows + j
         const size_t need = (size_t)v.world * v.block_rows;
         int *nv = nullptr, *ns = nullptr, *no = nullptr;
         TCK(cudaStreamSynchronize(h->stream));
+        TCK(cudaStreamSynchronize(ws));
         TCK(talloc(t, &nv, need)); TCK(talloc(t, &ns, need)); TCK(talloc(t, &no, need));
         t->d.valid = nv; t->d.slot = ns; t->d.order = no;
         t->gather_cap = (long long)need;
     }
     const Dev& d = t->d;
     const GBlocks g{v.recv, v.block_bytes, v.block_rows, v.world};
-    launch_pdl(k_addg_order, dim3(v.block_rows, v.world), dim3(128), 0, h->stream, d, g);
-    launch_pdl(k_addg_assign, dim3(1), dim3(32), 0, h->stream, d, g);
-    launch_pdl(k_addg_copy, dim3(v.block_rows, v.world), dim3(128), 0, h->stream, d, g);
+    launch_pdl(k_addg_order, dim3(v.block_rows, v.world), dim3(128), 0, ws, d, g);
+    launch_pdl(k_addg_assign, dim3(1), dim3(32), 0, ws, d, g);
+    launch_pdl(k_addg_copy, dim3(v.block_rows, v.world), dim3(128), 0, ws, d, g);
     t->launches += 3;
     TCK(cudaGetLastError());
+    if (t->async && trl_comm_mark_consumed(h, ws)) return 1;      // the next all-gather may overwrite the blocks only after this
     return 0;
 }
 
@@ -1019,16 +1039,16 @@ int trl_trainer_train(trl_trainer* t, int iters) {
     if (!t->train_graph) {
         cudaGraph_t graph;
         const int64_t before = t->launches;
-        TCK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-        enqueue_train(t, h->stream);
-        TCK(cudaStreamEndCapture(h->stream, &graph));
+        TCK(cudaStreamBeginCapture(t->work(), cudaStreamCaptureModeThreadLocal));
+        enqueue_train(t, t->work());
+        TCK(cudaStreamEndCapture(t->work(), &graph));
         TCK(cudaGraphInstantiate(&t->train_graph, graph, 0));
         cudaGraphDestroy(graph);
         t->launches = before;
     }
     const int per = 5 + t->d.steps_per_iter * (10 + 5 * 16 + 2 * 26);
     for (int i = 0; i < iters; ++i) {
-        TCK(cudaGraphLaunch(t->train_graph, h->stream));
+        TCK(cudaGraphLaunch(t->train_graph, t->work()));
         t->launches += per;
     }
     return 0;
@@ -1085,6 +1105,75 @@ int trl_trainer_init_fresh(trl_trainer* t, uint64_t seed) {
 // read-back per update); anneal the exploration settings and the curriculum phase from the iteration count }.  sp[9] as in
 // trl_train_schedule.  Everything is enqueued on the scenario's stream; the call returns after the last update is queued
 // (iters_per_update > 0) -- synchronise with trl_sync / trl_trainer_counters.
+// Asynchronous training (the reference's cAsyncMACETrainer / `-trainer_... async` path: exploration keeps running on the net it has
+// while the trainer works, scenarios/ScenarioTrain.cpp:388-408 + learning/AsyncTrainer): the hand-over of gathered tuples and the
+// trainer iterations move to their own low-priority stream and overlap the NEXT outer update; the decision kernels evaluate a snapshot
+// of the net that trl_train_run* refreshes between two updates, once the trainer job enqueued before the previous update is done.
+// Tuples of update u therefore shape the policy from update u + 2 on.  Needs a communicator (trl_comm_init*; a single rank will
+// do): the tuples leave the scenario through the pack kernel of trl_gather_tuples.
+int trl_trainer_set_async(trl_trainer* t, int enable) {
+    TRL_TRAINER_LIVE(t);
+    trl_handle* h = t->h;
+    if ((enable != 0) == t->async) return 0;
+    TCK(trainer_sync(t));
+    const Dev& d = t->d;
+    if (t->train_graph) { cudaGraphExecDestroy(t->train_graph); t->train_graph = nullptr; }      // it was captured on the other stream
+    NetWeights& W = h->W;
+    if (enable) {
+        if (!h->comm) return trl_fail("trl_trainer_set_async: asynchronous training needs a communicator (trl_comm_init first)");
+        if (!t->async_stream) {
+            int lo = 0, hi = 0;
+            cudaDeviceGetStreamPriorityRange(&lo, &hi);
+            TCK(cudaStreamCreateWithPriority(&t->async_stream, cudaStreamNonBlocking, lo));
+            TCK(cudaEventCreateWithFlags(&t->ev_snap, cudaEventDisableTiming));
+            TCK(cudaEventCreateWithFlags(&t->ev_trained, cudaEventDisableTiming));
+            TCK(talloc(t, &t->snap, (size_t)d.P + 2 * (size_t)d.S + 2 * (size_t)d.n_out));
+        }
+        double* sn = t->snap;
+        TCK(cudaMemcpy(sn, d.theta, (size_t)d.P * 8, cudaMemcpyDeviceToDevice));
+        TCK(cudaMemcpy(sn + d.P, d.in_off, (size_t)d.S * 8, cudaMemcpyDeviceToDevice));
+        TCK(cudaMemcpy(sn + d.P + d.S, d.in_scale, (size_t)d.S * 8, cudaMemcpyDeviceToDevice));
+        TCK(cudaMemcpy(sn + d.P + 2 * d.S, d.out_off, (size_t)d.n_out * 8, cudaMemcpyDeviceToDevice));
+        TCK(cudaMemcpy(sn + d.P + 2 * d.S + d.n_out, d.out_scale, (size_t)d.n_out * 8, cudaMemcpyDeviceToDevice));
+    }
+    // bind the decision kernels to the snapshot (async) or straight to the trainer's arrays (synchronous: SyncNet as a pointer binding)
+    const double* th = enable ? t->snap : d.theta;
+    auto blob = [&](int b) { return th + d.off[b]; };
+    W.conv0_w = blob(0); W.conv0_b = blob(1); W.conv1_w = blob(2); W.conv1_b = blob(3); W.conv2_w = blob(4); W.conv2_b = blob(5);
+    W.tip0_w = blob(6); W.tip0_b = blob(7); W.ip0_w = blob(8); W.ip0_b = blob(9);
+    for (int k = 0; k < 4; ++k) { W.h0_w[k] = blob(10 + 4 * k); W.h0_b[k] = blob(11 + 4 * k); W.h1_w[k] = blob(12 + 4 * k); W.h1_b[k] = blob(13 + 4 * k); }
+    W.in_off = enable ? t->snap + d.P : d.in_off;
+    W.in_scale = enable ? t->snap + d.P + d.S : d.in_scale;
+    W.out_off = enable ? t->snap + d.P + 2 * d.S : d.out_off;
+    W.out_scale = enable ? t->snap + d.P + 2 * d.S + d.n_out : d.out_scale;
+    trl_drop_graphs(h);
+    t->async = enable != 0;
+    t->trained_pending = t->job_pending = false;
+    return 0;
+}
+// between two updates, on the scenario's stream: wait for the trainer job that was enqueued before the previous update, refresh the
+// snapshot the decision kernels read, then hand the trainer its next job (the tuples gathered after the previous update)
+static int async_turnover(trl_trainer* t, int iters) {
+    trl_handle* h = t->h;
+    const Dev& d = t->d;
+    cudaStream_t A = h->stream, T = t->async_stream;
+    if (t->trained_pending) { TCK(cudaStreamWaitEvent(A, t->ev_trained, 0)); t->trained_pending = false; }
+    double* sn = t->snap;
+    TCK(cudaMemcpyAsync(sn, d.theta, (size_t)d.P * 8, cudaMemcpyDeviceToDevice, A));
+    TCK(cudaMemcpyAsync(sn + d.P, d.in_off, (size_t)d.S * 8, cudaMemcpyDeviceToDevice, A));
+    TCK(cudaMemcpyAsync(sn + d.P + d.S, d.in_scale, (size_t)d.S * 8, cudaMemcpyDeviceToDevice, A));
+    TCK(cudaEventRecord(t->ev_snap, A));
+    if (t->job_pending) {
+        TCK(cudaStreamWaitEvent(T, t->ev_snap, 0));           // the trainer must not move theta under the copy
+        if (trl_trainer_add_gathered(t)) return 1;            // (on T, behind the all-gather)
+        if (iters > 0 && trl_trainer_train(t, iters)) return 1;
+        TCK(cudaEventRecord(t->ev_trained, T));
+        t->trained_pending = true;
+        t->job_pending = false;
+    }
+    return 0;
+}
+
 static int train_run_impl(trl_trainer* t, const double* sp, int num_updates, int iters_per_update, int tuple_buffer_size, double time_step,
                           int block_rows, long long* iters_state, void* flush_buf = nullptr, size_t flush_bytes = 0) {
     trl_handle* h = t->h;
@@ -1104,6 +1193,15 @@ static int train_run_impl(trl_trainer* t, const double* sp, int num_updates, int
         if (trl_set_explore(h, 1, s[0], s[1], s[2])) return 1;
         if (s[3] != last_phase) { if (trl_set_terrain_lerp(h, s[3])) return 1; last_phase = s[3]; }
         if (flush_buf) TCK(cudaMemsetAsync(flush_buf, u & 0xff, flush_bytes, h->stream));     // measurement: evict L2 between updates
+        if (t->async) {
+            if (iters_per_update <= 0) return trl_fail("asynchronous training needs a fixed number of trainer iterations per update");
+            if (async_turnover(t, iters_per_update)) return 1;
+            if (trl_update(h, time_step)) return 1;
+            if (trl_gather_tuples(h, block_rows)) return 1;
+            t->job_pending = true;
+            iters_req += iters_per_update;
+            continue;
+        }
         if (trl_update(h, time_step)) return 1;
         if (h->comm) {
             // N GPUs: the tuples of every rank reach every rank's trainer (one all-gather), scenarios/ScenarioTrain.cpp:388-395
@@ -1121,6 +1219,11 @@ static int train_run_impl(trl_trainer* t, const double* sp, int num_updates, int
         }
         if (k > 0 && trl_trainer_train(t, k)) return 1;
         iters_req += k;
+    }
+    if (t->async) {
+        // the trainer job of the last update, and the end of the stream of work: the caller's trl_sync must cover the trainer too
+        if (async_turnover(t, iters_per_update)) return 1;
+        if (t->trained_pending) { TCK(cudaStreamWaitEvent(h->stream, t->ev_trained, 0)); t->trained_pending = false; }
     }
     if (iters_state) *iters_state = iters_req;
     return 0;
@@ -1160,7 +1263,7 @@ int trl_train_run_timed(trl_trainer* t, const double* sp, int num_updates, int i
 int trl_trainer_counters(trl_trainer* t, int64_t* c, double* l) {
     TRL_TRAINER_LIVE(t);
     Counters hc;
-    TCK(cudaStreamSynchronize(t->h->stream));
+    TCK(trainer_sync(t));
     TCK(cudaMemcpy(&hc, t->d.c, sizeof(hc), cudaMemcpyDeviceToHost));
     if (c) {
         c[0] = hc.iter; c[1] = hc.actor_iter; c[2] = hc.stage; c[3] = hc.num; c[4] = hc.head; c[5] = hc.total;
@@ -1179,7 +1282,7 @@ int trl_trainer_get(trl_trainer* t, int what, double* out) {
     const double* src[8] = {d.theta, d.target, d.history, d.in_off, d.in_scale, d.out_off, d.out_scale, d.grad};
     const size_t cnt[8] = {(size_t)d.P, (size_t)d.P, (size_t)d.P, (size_t)d.S, (size_t)d.S, (size_t)d.n_out, (size_t)d.n_out, (size_t)d.P};
     if (what < 0 || what > 7) return trl_fail("trl_trainer_get: bad selector");
-    TCK(cudaStreamSynchronize(t->h->stream));
+    TCK(trainer_sync(t));
     TCK(cudaMemcpy(out, src[what], cnt[what] * 8, cudaMemcpyDeviceToHost));
     return 0;
 }
@@ -1194,7 +1297,7 @@ int trl_trainer_set_theta(trl_trainer* t, const double* theta) {
 // replay rows (float, [n][1 + S + A + S]) and flags of the given slots
 int trl_trainer_rows(trl_trainer* t, const int32_t* ids, int n, float* rows, int32_t* flags) {
     TRL_TRAINER_LIVE(t);
-    TCK(cudaStreamSynchronize(t->h->stream));
+    TCK(trainer_sync(t));
     for (int i = 0; i < n; ++i) {
         if (ids[i] < 0 || ids[i] >= t->d.cap) return trl_fail("trl_trainer_rows: slot out of range");
         TCK(cudaMemcpy(rows + (size_t)i * t->d.Wd, t->d.mem + (size_t)ids[i] * t->d.Wd, (size_t)t->d.Wd * 4, cudaMemcpyDeviceToHost));
@@ -1206,7 +1309,7 @@ int trl_trainer_rows(trl_trainer* t, const int32_t* ids, int n, float* rows, int
 int trl_trainer_list(trl_trainer* t, int which, int32_t* out, int cap, int* len) {
     TRL_TRAINER_LIVE(t);
     Counters hc;
-    TCK(cudaStreamSynchronize(t->h->stream));
+    TCK(trainer_sync(t));
     TCK(cudaMemcpy(&hc, t->d.c, sizeof(hc), cudaMemcpyDeviceToHost));
     const int* src = which == 0 ? t->d.critic_list : (which == 1 ? t->d.actor_list : (which == 2 ? t->d.actor_batch : t->d.ids));
     const int n = which == 0 ? hc.critic_count : (which == 1 ? hc.actor_count : (which == 2 ? hc.actor_batch_count : trl_train::kB));

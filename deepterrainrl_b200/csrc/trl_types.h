@@ -33,6 +33,7 @@ constexpr int kMaxActions = 16;
 constexpr int kMaxCtrlSets = 8;
 constexpr int kMaxNetOut = 96;
 constexpr int kWarp = 32;
+constexpr int kMaxLists = 8;       // pending-decision lists (overlap depth + 1 <= 8)
 
 // ---- f64 SoA planes -------------------------------------------------------------------------------------------
 enum DField : int {
@@ -152,9 +153,9 @@ struct Buffers {
     double* tuple_sbeg;    // [n][S]
     double* tuple_action;  // [n][kNumParams]
     double* com_stash;     // [2][n]   COM at decision time
-    int* pending_list;     // [3][n]  three lists, used round robin by successive env-steps (see trl_host.cu: enqueue_update)
-    int* pending_count;    // [3]
-    int* catchup_done;     // [4]     [l] CTA completion counter of the catch-up launch of list l (re-arms the list it consumed), [3] fault flag
+    int* pending_list;     // [lists][n]  used round robin by successive env-steps (see trl_host.cu: enqueue_update)
+    int* pending_count;    // [kMaxLists]
+    int* catchup_done;     // [kMaxLists + 1]  [l] CTA completion counter of the catch-up launch of list l (re-arms the list it consumed), [kMaxLists] fault flag
     // outputs
     double* tuples;        // [tuple_cap][1 + S + A + S]
     uint32_t* tuple_flags; // [tuple_cap]

@@ -114,7 +114,7 @@ EXPORTS = [
     "trl_trainer_counters", "trl_trainer_num_params", "trl_trainer_launches", "trl_trainer_get", "trl_trainer_set_theta", "trl_trainer_list", "trl_trainer_rows",
     "trl_tuples_dropped", "trl_comm_unique_id", "trl_comm_init", "trl_comm_init_external", "trl_comm_destroy", "trl_comm_info", "trl_comm_set_env_offset",
     "trl_gather_tuples", "trl_gathered_blocks", "trl_gathered_fetch", "trl_gather_last_ms", "trl_trainer_add_gathered", "trl_trainer_broadcast",
-    "trl_comm_broadcast_weights", "trl_comm_eval_stats", "trl_trainer_replica_spread",
+    "trl_comm_broadcast_weights", "trl_comm_eval_stats", "trl_trainer_replica_spread", "trl_trainer_set_async",
 ]
 
 

@@ -178,6 +178,11 @@ int trl_train_run(trl_trainer* t, const double* sp9, int num_updates, int iters_
  * memset before every update, as trl_bench_updates does); *iters_state carries the annealing position across calls (start at 0) */
 int trl_train_run_timed(trl_trainer* t, const double* sp9, int num_updates, int iters_per_update, int block_rows, double time_step,
                         int flush_l2, int64_t* iters_state, double* ms);
+/* asynchronous training (the reference's asynchronous trainer: exploration keeps running on the net it has while the trainer works):
+ * hand-over + trainer iterations run on their own stream beside the NEXT update inside trl_train_run / trl_train_run_timed; the
+ * decision kernels read a snapshot of the net refreshed between updates (tuples of update u shape the policy from update u + 2 on).
+ * Needs a communicator (a single rank will do) and a fixed iters_per_update. */
+int trl_trainer_set_async(trl_trainer* t, int enable);
 int trl_trainer_counters(trl_trainer* t, int64_t* counters9, double* losses2);
 int trl_trainer_num_params(trl_trainer* t);
 int64_t trl_trainer_launches(trl_trainer* t);

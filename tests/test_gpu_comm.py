@@ -113,3 +113,29 @@ def test_tuple_block_overflow_is_reported(assets):
     sc.Update()
     rows, flags, env = sc.GetTuples()          # back to normal
     assert len(rows) < 8192
+
+
+def test_asynchronous_trainer_is_reproducible(assets):
+    """trl_trainer_set_async: hand-over + training overlap the next update on their own stream; two runs give bit-identical weights
+    (every dependency between the streams is an event, nothing is timing dependent), all tuples arrive, iterations are counted"""
+    import deepterrainrl_b200 as trl
+    from deepterrainrl_b200 import parallel
+    pack = os.path.join(assets, "dog_slopes_mixed.trlpack")
+    sp = np.array([0.5, 0.2, 20.0, 0.025, 0.3, 0.002, 200.0, 200.0, 0.0])
+    out = []
+    for run in range(2):
+        sc = trl.ScenarioExpMACE(pack, 512, rng_seed=31)
+        tr = trl.MACETrainer(sc, replay_mem_size=8192, num_init_samples=256, freeze_target_iters=5, seed=9)
+        comm = parallel.Comm(sc, 0, 1, backend="nccl", unique_id=_uid(sc.L))
+        L = sc.L
+        L.trl_train_run_timed.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
+        assert L.trl_trainer_set_async(tr.h, 1) == 0, L.trl_last_error().decode()
+        state, ms = C.c_int64(0), C.c_double(0)
+        assert L.trl_train_run_timed(tr.h, sp.ctypes.data_as(C.c_void_p), 90, 2, 256, C.c_double(1.0 / 30.0), 0, C.byref(state), C.byref(ms)) == 0, \
+            L.trl_last_error().decode()
+        c = tr.counters()
+        assert state.value == 180 and 100 < c["iter"] <= 180 and c["total"] > 2000 and sc.GetNumTuples() == 0
+        out.append((tr.get("theta"), c))
+        comm.close(); tr.close(); sc.close()
+    assert out[0][1] == out[1][1]
+    np.testing.assert_array_equal(out[0][0], out[1][0])

@@ -389,3 +389,48 @@ def test_layer_state_probe_vs_oracle(assets):
             assert n == g.size > 0, name
             assert np.max(np.abs(g - buf[:n]) / (1.0 + np.abs(buf[:n]))) <= 1e-13, name
         sc.close()
+
+
+def _loopback_comm(sc):
+    """a single-rank communicator whose collectives are memory copies (trl_comm_init_external)"""
+    from deepterrainrl_b200.parallel import _Collectives
+
+    def all_gather(ctx, send, recv, nbytes, stream):
+        C.memmove(recv, send, nbytes)
+        return 0
+    fns = (_Collectives.AG(all_gather), _Collectives.BC(lambda ctx, buf, nbytes, root, stream: 0), _Collectives.AR(lambda ctx, buf, count, stream: 0))
+    coll = _Collectives(None, *fns)
+    assert sc.L.trl_comm_init_external(sc.h, C.byref(coll), 0, 1) == 0, sc.L.trl_last_error().decode()
+    return coll, fns
+
+
+def test_asynchronous_trainer_loop(assets):
+    """trl_trainer_set_async + trl_train_run_timed (the reference's asynchronous trainer semantics): hand-over and training on their
+    own stream, policy snapshot refreshed between updates: the mechanics on the emulator -- one trainer job per update, the last one
+    flushed, mode switch back (tuple flow and reproducibility of the overlapped run: tests/test_gpu_comm.py on the GPU)."""
+    import deepterrainrl_b200 as trl
+    pack = os.path.join(assets, "dog_slopes_mixed.trlpack")
+    sp = np.array([0.5, 0.2, 20.0, 0.025, 0.3, 0.002, 12.0, 8.0, 0.0])
+    with simt_library() as L:
+        L.trl_train_run_timed.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
+        sc = trl.ScenarioExpMACE(pack, 6, rng_seed=31)
+        tr = trl.MACETrainer(sc, replay_mem_size=320, num_init_samples=16, freeze_target_iters=3, seed=9)
+        # a critic batch needs 32 tuples: seed the replay memory so that the short rollout below trains from its first job on
+        rng = np.random.default_rng(1)
+        rows = rng.normal(size=(48, tr.W)) * 0.1
+        rows[:, 1 + tr.S] = rng.integers(0, 3, 48)
+        tr.AddTuples(rows, np.zeros(48, np.uint32))
+        keep = _loopback_comm(sc)
+        assert L.trl_trainer_set_async(tr.h, 1) == 0, L.trl_last_error().decode()
+        theta0 = tr.get("theta")
+        state, ms = C.c_int64(0), C.c_double(0)
+        updates, iters = 8, 1
+        assert L.trl_train_run_timed(tr.h, sp.ctypes.data_as(C.c_void_p), updates, iters, 32, C.c_double(1.0 / 30.0), 0, C.byref(state),
+                                     C.byref(ms)) == 0, L.trl_last_error().decode()
+        c = tr.counters()
+        assert state.value == updates * iters and c["iter"] == updates * iters             # one trainer job per update, the last one flushed
+        assert c["total"] >= 48 and c["stage"] == 1 and sc.GetNumTuples() == 0               # (tuple flow itself: tests/test_gpu_comm.py, test_distributed_cpu.py)
+        assert np.max(np.abs(tr.get("theta") - theta0)) > 0
+        assert L.trl_trainer_set_async(tr.h, 0) == 0                                        # back to the pointer binding
+        sc.Update(); sc.Sync()
+        tr.close(); sc.close(); del keep
