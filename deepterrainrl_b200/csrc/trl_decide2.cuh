@@ -144,7 +144,8 @@ __device__ __forceinline__ void conv4_dmma(const double* __restrict__ act, const
 }
 
 __device__ void conv_stage_cluster(cg::cluster_group& cluster, const NetWeights& W, const double* __restrict__ x_in, double* sh, int n_char,
-                                   double* __restrict__ out_row) {
+                                   double* __restrict__ out_row, bool normalised = false, double* __restrict__ a0_out = nullptr,
+                                   double* __restrict__ a1_out = nullptr) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t4 = lane & 3;
     const int rank = (int)cluster.block_rank();
     const int n_in = 200 + n_char;
@@ -154,7 +155,7 @@ __device__ void conv_stage_cluster(cg::cluster_group& cluster, const NetWeights&
     double* W0s = sh + kCvW0;
     double* W1s = sh + kCvW1;
     double* W2s = sh + kCvW2;
-    for (int i = tid; i < n_in; i += kDecideThreads) X[i] = (x_in[i] + W.in_off[i]) * W.in_scale[i];
+    for (int i = tid; i < n_in; i += kDecideThreads) X[i] = normalised ? x_in[i] : (x_in[i] + W.in_off[i]) * W.in_scale[i];
     for (int i = tid; i < kConv0Out * kConv0K; i += kDecideThreads) W0s[(i >> 3) * 12 + (i & 7)] = W.conv0_w[i];
     for (int i = tid; i < kC1Slice * 64; i += kDecideThreads) W1s[(i >> 6) * 68 + (i & 63)] = W.conv1_w[rank * kC1Slice * 64 + i];
     for (int i = tid; i < kC2Slice * 128; i += kDecideThreads) W2s[(i >> 7) * 132 + (i & 127)] = W.conv2_w[rank * kC2Slice * 128 + i];
@@ -174,8 +175,10 @@ __device__ void conv_stage_cluster(cg::cluster_group& cluster, const NetWeights&
         }
     }
     __syncthreads();
+    if (a0_out && rank == 0) for (int i = tid; i < kConv0Out * kW0; i += kDecideThreads) a0_out[i] = A0[i];
     conv4_dmma<kConv0Out, kW0, kW1, 68>(A0, W1s, W.conv1_b + rank * kC1Slice, A1 + rank * kC1Slice * kW1, kW1);
     cluster.sync();
+    if (a1_out) for (int i = tid; i < kC1Slice * kW1; i += kDecideThreads) a1_out[rank * kC1Slice * kW1 + i] = A1[rank * kC1Slice * kW1 + i];
     for (int r = 1; r < kClusterSize; ++r) {
         int src = (rank + r) % kClusterSize;
         const double* remote = cluster.map_shared_rank(A1, src);
@@ -202,6 +205,18 @@ trl_decide_conv_kernel(Buffers B, NetWeights W, double* __restrict__ act2, int l
         const int env = B.pending_list[list * B.n + idx];
         conv_stage_cluster(cluster, W, B.poli_state + (size_t)env * B.S, sh, m.n_char, act2 + (size_t)idx * kTipIn);
     }
+}
+
+// the conv stage over the rows of a trainer minibatch (one cluster per row)
+__global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kDecideThreads, 2)
+trl_fwd_conv_train_kernel(NetWeights W, FwdTrain f, double* __restrict__ act2) {
+    TRL_DYN_SHARED(double, sh);
+    cg::cluster_group cluster = cg::this_cluster();
+    if (f.gate && *f.gate == 0) return;
+    const int cid = blockIdx.x / kClusterSize, ncl = gridDim.x / kClusterSize;
+    for (int r = cid; r < f.rows; r += ncl)
+        conv_stage_cluster(cluster, W, f.xn + (size_t)r * f.S, sh, f.S - 200, act2 + (size_t)r * kTipIn, true,
+                           f.a0 ? f.a0 + (size_t)r * kConv0Out * kW0 : nullptr, f.a1 ? f.a1 + (size_t)r * kConv1Out * kW1 : nullptr);
 }
 
 // ------------------------------------------------------------------------------------------------ FC stage
@@ -263,9 +278,9 @@ __device__ void decide_one(const Buffers& B, const ExpSettings& ex, int env, con
     store_rng(L, rng);
 }
 
-__global__ void __cluster_dims__(kFcCluster, 1, 1) __launch_bounds__(kFcThreads, 1)
-trl_decide_fc_kernel(Buffers B, NetWeights W, const ExpSettings* __restrict__ ex_dev, const TRL_GRID_CONSTANT FcMaps maps, int* done_count, int list,
-                     int rearm) {
+template <bool kTrain>
+__device__ __forceinline__ void fc_stage(const Buffers& B, const NetWeights& W, const ExpSettings* __restrict__ ex_dev, const FcMaps& maps, const FwdTrain& ft,
+                                         int* done_count, int list, int rearm) {
     TRL_DYN_SHARED(unsigned char, fc_smem_raw);
     // the swizzled TMA tiles need 1024-byte alignment; the dynamic window starts at the same offset in every CTA of the cluster, so
     // the rounded address is a valid DSMEM offset as well
@@ -279,9 +294,13 @@ trl_decide_fc_kernel(Buffers B, NetWeights W, const ExpSettings* __restrict__ ex
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t4 = lane & 3;
     const int rank = (int)cluster.block_rank();
     const int cid = blockIdx.x / kFcCluster, ncl = gridDim.x / kFcCluster;
-    const int count = B.pending_count[list];
-    const ExpSettings ex = *ex_dev;
-    const int n_char = m.n_char, ncat = kTip0Out + n_char;
+    if (kTrain && ft.gate && *ft.gate == 0) return;
+    const int count = kTrain ? ft.rows : B.pending_count[list];
+    ExpSettings ex{};
+    if (!kTrain) ex = *ex_dev;
+    const int n_char = kTrain ? ft.S - 200 : m.n_char, ncat = kTip0Out + n_char;
+    const bool has_net = kTrain || m.has_net;
+    const int n_frags = kTrain ? ft.n_frags : m.n_frags, frag = kTrain ? ft.frag : m.frag;
     double* P = (double*)(fc_smem + kFcOffPart);
     double* CAT = (double*)(fc_smem + kFcOffCat);
     double* WIP = (double*)(fc_smem + kFcOffWip);
@@ -303,7 +322,7 @@ trl_decide_fc_kernel(Buffers B, NetWeights W, const ExpSettings* __restrict__ ex
     };
     stamp();     // 0: kernel entry
 
-    if (m.has_net && cid < nchunks) {
+    if (has_net && cid < nchunks) {
         // ip0 weight slice of this CTA (32 output columns x ncat, zero-padded to kCatStride): resident for the whole launch
         for (int i = tid; i < 32 * kCatStride; i += kFcThreads) {
             const int n = i / kCatStride, k = i - n * kCatStride;
@@ -326,7 +345,7 @@ trl_decide_fc_kernel(Buffers B, NetWeights W, const ExpSettings* __restrict__ ex
     for (int chunk = cid; chunk < nchunks; chunk += ncl) {
         const int row0 = chunk * kFcRows;
         const int rows = min(kFcRows, count - row0);
-        if (m.has_net) {
+        if (has_net) {
             // ---------------- terr_ip0: P[32][64] = A[32][k slice] * Wt[k slice][64]; warp w owns C tiles (m tile w / 4, n tiles 2 (w % 4) + {0, 1})
             const int mt = warp >> 2, nt0 = (warp & 3) * 2;
             double c00 = 0, c01 = 0, c10 = 0, c11 = 0;
@@ -403,13 +422,20 @@ trl_decide_fc_kernel(Buffers B, NetWeights W, const ExpSettings* __restrict__ ex
                 const int r = i / (kCatStride - kTip0Out), c = i - r * (kCatStride - kTip0Out);
                 double v = 0.0;
                 if (r < rows && c < n_char) {
-                    const int env = B.pending_list[list * B.n + row0 + r];
-                    v = (B.poli_state[(size_t)env * B.S + 200 + c] + W.in_off[200 + c]) * W.in_scale[200 + c];
+                    if (kTrain) v = ft.xn[(size_t)(row0 + r) * ft.S + 200 + c];
+                    else {
+                        const int env = B.pending_list[list * B.n + row0 + r];
+                        v = (B.poli_state[(size_t)env * B.S + 200 + c] + W.in_off[200 + c]) * W.in_scale[200 + c];
+                    }
                 }
                 CAT[r * kCatStride + kTip0Out + c] = v;
             }
             stamp();     // 4: concat0 built
             cluster.sync();      // CAT complete here; every peer has finished reading this CTA's P
+            if (kTrain && rank == 0) {
+                for (int i = tid; i < rows * ncat; i += kFcThreads) { const int r = i / ncat, c = i - r * ncat; ft.catb[(size_t)(row0 + r) * ft.cat + c] = CAT[r * kCatStride + c]; }
+                for (int i = tid; i < rows * kTip0Out; i += kFcThreads) { const int r = i / kTip0Out, c = i - r * kTip0Out; ft.t[(size_t)(row0 + r) * kTip0Out + c] = CAT[r * kCatStride + c]; }
+            }
             stamp();     // 5
             // ---------------- ip0: H[:, 32 rank .. 32 rank + 32) = relu(CAT * Wip^T + b); 16 C tiles, one per warp
             {
@@ -431,6 +457,8 @@ trl_decide_fc_kernel(Buffers B, NetWeights W, const ExpSettings* __restrict__ ex
             }
             stamp();     // 6: ip0 done, H scattered
             cluster.sync();
+            if (kTrain && rank == 1)
+                for (int i = tid; i < rows * kIp0Out; i += kFcThreads) { const int r = i / kIp0Out, c = i - r * kIp0Out; ft.h[(size_t)(row0 + r) * kIp0Out + c] = H[r * kHStride + c]; }
             stamp();     // 7
             // ---------------- head hidden layers: CTA pair (2 hd, 2 hd + 1) owns head hd; this CTA computes 64 of its 128 hidden units.
             // warp w: n tile w % 8 (of 8), m tiles 2 (w / 8) + {0, 1}; B fragments straight from L2 (each weight is used once per chunk)
@@ -458,12 +486,17 @@ trl_decide_fc_kernel(Buffers B, NetWeights W, const ExpSettings* __restrict__ ex
             }
             stamp();     // 8: head hidden layers done
             cluster.sync();
+            if (kTrain && half == 0 && ft.hh)
+                for (int i = tid; i < rows * kHeadHidden; i += kFcThreads) {
+                    const int r = i / kHeadHidden, c = i - r * kHeadHidden;
+                    ft.hh[((size_t)hd * ft.rows + row0 + r) * kHeadHidden + c] = HH[r * kHHStride + c];
+                }
             stamp();     // 9
             // ---------------- output layers: the even CTA of a pair multiplies its head's [32 x 128] by [128 x nout] (n padded to 32) and
             // un-normalises into rank 0's Y
             if (half == 0) {
-                const int nout = hd == 0 ? m.n_frags : m.frag;
-                const int obase = hd == 0 ? 0 : m.n_frags + (hd - 1) * m.frag;
+                const int nout = hd == 0 ? n_frags : frag;
+                const int obase = hd == 0 ? 0 : n_frags + (hd - 1) * frag;
                 const int mt4 = warp >> 2, nt4 = warp & 3;
                 const int nrow = nt4 * 8 + g;                              // output unit this lane's B fragment belongs to
                 const double* wrow = W.h1_w[hd] + (size_t)min(nrow, nout - 1) * kHeadHidden + t4;
@@ -474,34 +507,55 @@ trl_decide_fc_kernel(Buffers B, NetWeights W, const ExpSettings* __restrict__ ex
                     const double b = nrow < nout ? wrow[ks * 4] : 0.0;
                     dmma_8x8x4(c0, c1, arow[ks * 4], b);
                 }
-                double* Y0 = cluster.map_shared_rank(Y, 0);
-                const int o = nt4 * 8 + 2 * t4;
-                if (o < nout) Y0[(mt4 * 8 + g) * kYStride + obase + o] = (c0 + W.h1_b[hd][o]) / W.out_scale[obase + o] - W.out_off[obase + o];
-                if (o + 1 < nout) Y0[(mt4 * 8 + g) * kYStride + obase + o + 1] = (c1 + W.h1_b[hd][o + 1]) / W.out_scale[obase + o + 1] - W.out_off[obase + o + 1];
+                const int o = nt4 * 8 + 2 * t4, yrow = mt4 * 8 + g;
+                if (kTrain) {
+                    // the trainer works on the net's own (normalised) outputs
+                    if (yrow < rows && o < nout) ft.y[(size_t)(row0 + yrow) * ft.n_out + obase + o] = c0 + W.h1_b[hd][o];
+                    if (yrow < rows && o + 1 < nout) ft.y[(size_t)(row0 + yrow) * ft.n_out + obase + o + 1] = c1 + W.h1_b[hd][o + 1];
+                } else {
+                    double* Y0 = cluster.map_shared_rank(Y, 0);
+                    if (o < nout) Y0[yrow * kYStride + obase + o] = (c0 + W.h1_b[hd][o]) / W.out_scale[obase + o] - W.out_off[obase + o];
+                    if (o + 1 < nout) Y0[yrow * kYStride + obase + o + 1] = (c1 + W.h1_b[hd][o + 1]) / W.out_scale[obase + o + 1] - W.out_off[obase + o + 1];
+                }
             }
             stamp();     // 10: output layers done
             cluster.sync();
             stamp();     // 11
         }
         // ---------------- the scalar decisions of this chunk, one lane each
-        if (rank == 0 && tid < rows) decide_one(B, ex, B.pending_list[list * B.n + row0 + tid], Y + tid * kYStride);
+        if (!kTrain && rank == 0 && tid < rows) decide_one(B, ex, B.pending_list[list * B.n + row0 + tid], Y + tid * kYStride);
         stamp();         // 12: decisions applied
         cluster.sync();      // Y / H / HH / the pipeline buffers are reused by the next chunk
         stamp();         // 13
     }
     // serial schedule: the last CTA to finish re-arms the list (in the overlapped schedule the catch-up launch, which still needs
     // the count, does it)
-    if (rearm && threadIdx.x == 0) {
+    if (!kTrain && rearm && threadIdx.x == 0) {
         __threadfence();
         int done = atomicAdd(done_count, 1);
         if (done == (int)gridDim.x - 1) { B.pending_count[list] = 0; *done_count = 0; __threadfence(); }
     }
 }
 
+__global__ void __cluster_dims__(kFcCluster, 1, 1) __launch_bounds__(kFcThreads, 1)
+trl_decide_fc_kernel(Buffers B, NetWeights W, const ExpSettings* __restrict__ ex_dev, const TRL_GRID_CONSTANT FcMaps maps, int* done_count, int list,
+                     int rearm) {
+    const FwdTrain none{};
+    fc_stage<false>(B, W, ex_dev, maps, none, done_count, list, rearm);
+}
+// the FC stage over a trainer minibatch: activations and raw outputs to global memory, no decisions
+__global__ void __cluster_dims__(kFcCluster, 1, 1) __launch_bounds__(kFcThreads, 1)
+trl_fwd_fc_train_kernel(NetWeights W, const TRL_GRID_CONSTANT FcMaps maps, FwdTrain f) {
+    Buffers none{};
+    fc_stage<true>(none, W, nullptr, maps, f, nullptr, 0, 0);
+}
+
 
 size_t decide_fc_smem_bytes() { return (size_t)kFcSmemBytes; }
 cudaError_t configure_decide2_kernels() {
     cudaError_t e = cudaFuncSetAttribute(trl_decide_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmemDoubles * 8);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(trl_fwd_conv_train_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmemDoubles * 8);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(trl_fwd_fc_train_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decide_fc_smem_bytes());
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(trl_decide_fc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decide_fc_smem_bytes());
 }
@@ -512,6 +566,13 @@ void launch_decide2(const Buffers& B, const NetWeights& W, const ExpSettings* ex
     if (part & 2)
         TRL_LAUNCH_CLUSTER(kFcCluster, trl_decide_fc_kernel, fc_clusters * kFcCluster, kFcThreads, decide_fc_smem_bytes(), st, B, W, ex, maps, done_count,
                            list, rearm);
+}
+
+// the forward pass of a trainer minibatch through the same two kernels (trl_train.cu: enqueue_forward); act2 = [rows][5984] scratch the
+// FC stage's TMA descriptor `maps.a` covers
+void launch_forward_train(const NetWeights& W, const FcMaps& maps, const FwdTrain& f, double* act2, cudaStream_t st) {
+    TRL_LAUNCH_CLUSTER(kClusterSize, trl_fwd_conv_train_kernel, kClusterSize * f.rows, kDecideThreads, (size_t)kConvSmemDoubles * 8, st, W, f, act2);
+    TRL_LAUNCH_CLUSTER(kFcCluster, trl_fwd_fc_train_kernel, kFcCluster, kFcThreads, decide_fc_smem_bytes(), st, W, maps, f);
 }
 
 }  // namespace trl

@@ -19,4 +19,14 @@ struct FcMaps {
     int a_rows;
     unsigned long long* prof;    // measurement only (trl_debug_fc_phases): rank 0 / thread 0 of cluster 0 stamps %globaltimer at phase ends
 };
+
+// the same two kernels as the forward pass of a TRAINER batch (trl_train.cu): rows = the minibatch, inputs already normalised, every
+// activation the backward pass needs written out, raw (normalised) outputs, no decisions.  All-null in the decision path.
+struct FwdTrain {
+    const double* xn;                 // [rows][S] normalised net inputs
+    int rows, S, cat, n_out, n_frags, frag;
+    const int* gate;                  // device word: the launch is a no-op while it is 0 (the trainer's on-device control flow)
+    double *a0, *a1;                  // post-ReLU conv0 / conv1 activations [rows][16 * 193], [rows][32 * 190] (null: not kept)
+    double *t, *catb, *h, *hh, *y;    // [rows][64], [rows][cat], [rows][256], [4][rows][128] (null: not kept), raw outputs [rows][n_out]
+};
 }  // namespace trl

@@ -68,4 +68,5 @@ struct trl_handle {
 int trl_fail(const std::string& msg);                 // records the message for trl_last_error(), returns 1
 void trl_drop_graphs(trl_handle* h);
 extern "C" void trl_trainer_orphan(trl_trainer* t);              // trl_destroy with a trainer still attached (trl_train.cu)
+int trl_make_fc_maps(trl::FcMaps* out, const double* tip0_w, const double* act2, int rows);   // trl_host.cu
 int trl_reupload_model(trl_handle* h);                // after editing h->mc: refresh the __constant__ copies                  // captured graphs bake kernel arguments (weight pointers) in

@@ -395,6 +395,16 @@ static int encode_rows_map(CUtensorMap* map, const double* base, uint64_t rows, 
     return 0;
 }
 #endif
+// TMA descriptors for a forward pass through the batched kernels outside the decision path (the trainer's minibatch)
+int trl_make_fc_maps(trl::FcMaps* out, const double* tip0_w, const double* act2, int rows) {
+    std::memset(out, 0, sizeof(*out));
+    out->w_ptr = tip0_w; out->a_ptr = act2; out->a_rows = rows; out->prof = nullptr;
+#ifndef TRL_SIMT_EMU
+    if (encode_rows_map(&out->w, tip0_w, 64, 64)) return 1;
+    if (encode_rows_map(&out->a, act2, (uint64_t)rows, 32)) return 1;
+#endif
+    return 0;
+}
 static int ensure_fc_maps(trl_handle* h) {
     if (!h->decide_v2 || !h->mc.has_net || !h->act2[0] || !h->W.tip0_w) return 0;
     if (h->fc_maps_w == h->W.tip0_w) return 0;

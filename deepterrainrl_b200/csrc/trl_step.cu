@@ -60,7 +60,7 @@ constexpr int X_M = 0;
 // Experiments (profiles/step_kernel_r01_source_phases.md: shuffles are 27 % of the kernel's instructions).  Each knob moves one
 // family of lane-to-lane exchanges from warp shuffles (2 SHFL + register moves per double) to per-warp shared memory (128-bit
 // stores / loads); values and operation order are untouched, so every variant is bit-identical to the default build
-// (tests/test_simt_cpu.py checks that on the CPU emulator).  Default build: all off, SASS unchanged.  -DTRL_SMEM_XCHG=1: all on.
+// (tests/test_simt_cpu.py checks that on the CPU emulator).  Default build: the LDL^T exchange on, the others off (measured).  -DTRL_SMEM_XCHG=1: all on.
 #ifndef TRL_SMEM_XCHG
 #define TRL_SMEM_XCHG 0
 #endif
@@ -68,7 +68,8 @@ constexpr int X_M = 0;
 #define TRL_ACCUM_SMEM TRL_SMEM_XCHG     // child -> parent hand-off of the inward rounds (9 doubles x 9 rounds x 5 sub-steps)
 #endif
 #ifndef TRL_LDLT_SMEM
-#define TRL_LDLT_SMEM TRL_SMEM_XCHG      // pivot column of the register LDL^T + fused forward substitution (253 + 23 doubles)
+#define TRL_LDLT_SMEM 1                  // ON by default since round 2 (B200 A/B, profiles/step_kernel_variants_r02_ab2.txt: +2.8 % env-steps/s;
+                                         // spill stores 404 -> 228 B).  pivot column of the register LDL^T + fused forward substitution (253 + 23 doubles)
 #endif
 #ifndef TRL_KIN_SMEM
 #define TRL_KIN_SMEM TRL_SMEM_XCHG       // pointer-jumping prefix sums of the kinematics (26 doubles x 6 per env-step)

@@ -28,6 +28,9 @@
 #include "trl_handle.h"
 #include "trl_comm.h"
 
+namespace trl {
+void launch_forward_train(const NetWeights& W, const FcMaps& maps, const FwdTrain& f, double* act2, cudaStream_t st);
+}
 namespace trl_train {
 using namespace trl;
 
@@ -678,6 +681,10 @@ struct trl_trainer {
     Dev d;
     std::vector<void*> allocs;
     cudaGraphExec_t train_graph = nullptr;
+    // forward passes run through the batched decision kernels (trl_decide2.cuh): per net the weight views and TMA descriptors
+    trl::NetWeights nw[2];             // 0 current net, 1 target net
+    trl::FcMaps fmaps[2];
+    bool batched_fwd = true;           // TRL_TRAIN_FWD_V1=1: the per-layer kernels below
     double* stage_rows = nullptr;      // device staging for tuples handed in from the host
     uint32_t* stage_flags = nullptr;
     int stage_cap = 0;
@@ -711,11 +718,25 @@ cudaError_t talloc(trl_trainer* t, Tp** p, size_t count) {
 struct NetRef { const double* theta; const double *in_off, *in_scale; };
 
 // forward pass of the kB rows named by d.ids (replay columns starting at col0) through `net`; activations stay in d.*
-int enqueue_forward(trl_trainer* t, int pred, int col0, const NetRef& net, cudaStream_t st) {
+int enqueue_forward(trl_trainer* t, int pred, int col0, const NetRef& net, cudaStream_t st, bool keep_act = true) {
     const Dev& d = t->d;
     const double* th = net.theta;
     auto blob = [&](int b) { return th + d.off[b]; };
     launch_pdl(k_gather_norm, dim3(kB), dim3(128), 0, st, d, pred, col0, net.in_off, net.in_scale);
+    if (t->batched_fwd) {
+        // conv stage (one 4-CTA cluster per row, DMMA) + FC stage (one 8-CTA cluster, TMA-fed terr_ip0, DMMA): 2 launches instead of
+        // 15.  Plain stream order on both sides (no programmatic attribute): the pass starts after k_gather_norm has finished and the
+        // next kernel's griddepcontrol.wait covers it.
+        const int which = th == d.target ? 1 : 0;
+        FwdTrain f{};
+        f.xn = d.xn; f.rows = kB; f.S = d.S; f.cat = d.cat; f.n_out = d.n_out; f.n_frags = d.n_frags; f.frag = d.frag;
+        f.gate = pred == P_CRITIC ? &d.c->critic_ok : pred == P_CAND ? &d.c->cand_count : pred == P_ACTOR ? &d.c->actor_ok : nullptr;
+        f.a0 = keep_act ? d.a0 : nullptr; f.a1 = keep_act ? d.a1 : nullptr; f.hh = keep_act ? d.hh : nullptr;
+        f.t = d.t; f.catb = d.catb; f.h = d.h; f.y = d.y;
+        launch_forward_train(t->nw[which], t->fmaps[which], f, d.a2, st);
+        t->launches += 3;
+        return 0;
+    }
     launch_pdl(k_conv_fwd, dim3(dim3(C0 / kConvOut, kB)), dim3(224), (size_t)kTerr * 8, st, d, pred, d.xn, d.S, 1, kTerr, blob(0), blob(1), C0, K0, d.a0);
     launch_pdl(k_conv_fwd, dim3(dim3(C1 / kConvOut, kB)), dim3(224), (size_t)C0 * W0 * 8, st, d, pred, d.a0, C0 * W0, C0, W0, blob(2), blob(3), C1, K1, d.a1);
     launch_pdl(k_conv_fwd, dim3(dim3(C2 / kConvOut, kB)), dim3(224), (size_t)C1 * W1 * 8, st, d, pred, d.a1, C1 * W1, C1, W1, blob(4), blob(5), C2, K2, d.a2);
@@ -776,16 +797,16 @@ int enqueue_train(trl_trainer* t, cudaStream_t st) {
     for (int s = 0; s < d.steps_per_iter; ++s) {
         // ---- critic: BuildProblem + UpdateNet (learning/NeuralNetTrainer.cpp:414-456, MACETrainer.cpp:222-247)
         launch_pdl(k_sample_critic, dim3(1), dim3(32), 0, st, d);
-        enqueue_forward(t, P_CRITIC, col_end, tar, st);
+        enqueue_forward(t, P_CRITIC, col_end, tar, st, false);
         launch_pdl(k_vals, dim3(1), dim3(32), 0, st, d, P_CRITIC, 1, d.v1);
         enqueue_forward(t, P_CRITIC, col_beg, cur, st);
         launch_pdl(k_labels, dim3(1), dim3(256), 0, st, d, P_CRITIC, 0);
         enqueue_backward_update(t, P_CRITIC, st);
         // ---- actor: UpdateActorBatchBuffer + UpdateActor (learning/MACETrainer.cpp:541-626)
         launch_pdl(k_sample_actor, dim3(1), dim3(32), 0, st, d);
-        enqueue_forward(t, P_CAND, col_beg, tar, st);
+        enqueue_forward(t, P_CAND, col_beg, tar, st, false);
         launch_pdl(k_vals, dim3(1), dim3(32), 0, st, d, P_CAND, 0, d.v0);
-        enqueue_forward(t, P_CAND, col_end, tar, st);
+        enqueue_forward(t, P_CAND, col_end, tar, st, false);
         launch_pdl(k_vals, dim3(1), dim3(32), 0, st, d, P_CAND, 1, d.v1);
         launch_pdl(k_actor_select, dim3(1), dim3(32), 0, st, d);
         enqueue_forward(t, P_ACTOR, col_beg, cur, st);
@@ -891,6 +912,24 @@ trl_trainer* trl_trainer_create(trl_handle* h, const double* p) {
         for (void* q : t->allocs) cudaFree(q);
         delete t;
         return nullptr;
+    }
+    {
+        const char* v1 = std::getenv("TRL_TRAIN_FWD_V1");
+        t->batched_fwd = !(v1 && v1[0] == '1');
+        const double* bases[2] = {d.theta, d.target};
+        for (int k = 0; k < 2 && t->batched_fwd; ++k) {
+            NetWeights& W = t->nw[k];
+            auto bl = [&](int b) { return (const double*)(bases[k] + d.off[b]); };
+            W.conv0_w = bl(0); W.conv0_b = bl(1); W.conv1_w = bl(2); W.conv1_b = bl(3); W.conv2_w = bl(4); W.conv2_b = bl(5);
+            W.tip0_w = bl(6); W.tip0_b = bl(7); W.ip0_w = bl(8); W.ip0_b = bl(9);
+            for (int q = 0; q < 4; ++q) { W.h0_w[q] = bl(10 + 4 * q); W.h0_b[q] = bl(11 + 4 * q); W.h1_w[q] = bl(12 + 4 * q); W.h1_b[q] = bl(13 + 4 * q); }
+            W.in_off = W.in_scale = W.out_off = W.out_scale = nullptr;          // the minibatch arrives normalised; outputs stay normalised
+            if (trl_make_fc_maps(&t->fmaps[k], W.tip0_w, d.a2, kB)) {
+                for (void* q : t->allocs) cudaFree(q);
+                delete t;
+                return nullptr;
+            }
+        }
     }
     // cNeuralNetLearner::SyncNet as a binding: the decision kernel reads the trainer's weights from now on
     NetWeights& Wt = h->W;
@@ -1046,7 +1085,7 @@ int trl_trainer_train(trl_trainer* t, int iters) {
         cudaGraphDestroy(graph);
         t->launches = before;
     }
-    const int per = 5 + t->d.steps_per_iter * (10 + 5 * 16 + 2 * 26);
+    const int per = 5 + t->d.steps_per_iter * (10 + 5 * (t->batched_fwd ? 3 : 16) + 2 * 26);
     for (int i = 0; i < iters; ++i) {
         TCK(cudaGraphLaunch(t->train_graph, t->work()));
         t->launches += per;
@@ -1124,7 +1163,9 @@ int trl_trainer_set_async(trl_trainer* t, int enable) {
         if (!t->async_stream) {
             int lo = 0, hi = 0;
             cudaDeviceGetStreamPriorityRange(&lo, &hi);
-            TCK(cudaStreamCreateWithPriority(&t->async_stream, cudaStreamNonBlocking, lo));
+            // highest priority: the trainer's ~140 launches per iteration are a few CTAs each; behind the step launch's CTAs every
+            // one of them would wait for a free slot
+            TCK(cudaStreamCreateWithPriority(&t->async_stream, cudaStreamNonBlocking, hi));
             TCK(cudaEventCreateWithFlags(&t->ev_snap, cudaEventDisableTiming));
             TCK(cudaEventCreateWithFlags(&t->ev_trained, cudaEventDisableTiming));
             TCK(talloc(t, &t->snap, (size_t)d.P + 2 * (size_t)d.S + 2 * (size_t)d.n_out));

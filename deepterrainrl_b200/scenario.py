@@ -22,11 +22,11 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 # the product library (lib/variants/<name>/).  Unset = the product build.  There is still no CPU path behind any of them.
 VARIANTS = {
     "accum_smem": ["-DTRL_ACCUM_SMEM=1"],
-    "ldlt_smem": ["-DTRL_LDLT_SMEM=1"],
+    "ldlt_regs": ["-DTRL_LDLT_SMEM=0"],          # the round-1 default: pivot column exchanged by shuffles
     "kin_smem": ["-DTRL_KIN_SMEM=1"],
     "outward_smem": ["-DTRL_OUTWARD_SMEM=1"],
     "contact_smem": ["-DTRL_CONTACT_SMEM=1"],
-    "accum_ldlt": ["-DTRL_ACCUM_SMEM=1", "-DTRL_LDLT_SMEM=1"],                                  # the two largest families, 23 KB smem / CTA
+    "accum_ldlt": ["-DTRL_ACCUM_SMEM=1"],                                  # the two largest families, 23 KB smem / CTA
     "xchg_no_contact": ["-DTRL_ACCUM_SMEM=1", "-DTRL_LDLT_SMEM=1", "-DTRL_KIN_SMEM=1", "-DTRL_OUTWARD_SMEM=1"],   # 36 KB
     "smem_xchg": ["-DTRL_SMEM_XCHG=1"],
     "smem_xchg_3cta": ["-DTRL_SMEM_XCHG=1", "-DTRL_STEP_MIN_BLOCKS=3"],
