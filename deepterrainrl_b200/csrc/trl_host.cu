@@ -303,7 +303,10 @@ static int fill_model(trl_handle* h, uint64_t rng_seed) {
         lerp -= i0;
         for (int i = 0; i < kTerrainParams; ++i) m.terrain_params[i] = (1 - lerp) * tp[i0 * kTerrainParams + i] + lerp * tp[i1 * kTerrainParams + i];
     }
-    m.phys = PhysParams{2.0e5, 2.0e3, 0.81, 0.01, 0.00025, 2.0e4, 20.0};
+    {
+        const char* vc = std::getenv("TRL_VERTEX_CONTACTS");
+        m.phys = PhysParams{2.0e5, 2.0e3, 0.81, 0.01, 0.00025, 2.0e4, 20.0, (vc && vc[0] == '1') ? 1 : 0};
+    }
     h->ex = ExpSettings{h->mode == TRL_MODE_EXPLORE ? 1 : 0, mf[4], mf[5], mf[6], m.exp_noise};   // uploaded by create_common
     if (m.has_net) {
         const auto& nd = s.i32("net_dims");
@@ -968,7 +971,7 @@ int trl_train_schedule(const double* sp, int iters, double* out) {
 int trl_set_phys_params(trl_handle* h, const double* p) {
     if (!h) return fail("trl_set_phys_params: null handle");
     CK(cudaStreamSynchronize(h->stream));
-    h->mc.phys = PhysParams{p[0], p[1], p[2], p[3], p[4], p[5], p[6]};
+    h->mc.phys = PhysParams{p[0], p[1], p[2], p[3], p[4], p[5], p[6], h->mc.phys.vertex_contacts};
     g_model_owner = nullptr;
     if (ensure_model(h)) return fail("model upload failed");
     return 0;

@@ -845,6 +845,9 @@ __device__ double controller_torque(Lane& L, const LinkC& lc, const EnvRegs& e, 
 // Updates e (q, qd, root translation) in place and returns the contact bitmask (same value in every lane).
 __device__ int physics_substep(const LinkC& lc, EnvRegs& e, const GroundView& g, const double* s_clx, const double* s_cly,
                                const int* s_cbody, int lane, double dt, double clear_y TRL_PHYS_XS_DECL TRL_REUSE_KIN_DECL) {
+    // per-body box tables (link frame): centre offset, axis rotation, half sizes -- staged by the kernel next to the corner tables
+    const double *s_bax = s_clx + 4 * kMaxJoints, *s_bay = s_bax + kMaxJoints, *s_bc = s_bay + kMaxJoints, *s_bs = s_bc + kMaxJoints,
+                 *s_hx = s_bs + kMaxJoints, *s_hy = s_hx + kMaxJoints;
     const ModelConst& m = c_model;
     const PhysParams& pp = m.phys;
     const int md = m.max_depth;
@@ -881,10 +884,82 @@ __device__ int physics_substep(const LinkC& lc, EnvRegs& e, const GroundView& g,
     kin2[lane] = make_double2(k.w, k.vx); kin3[lane] = k.vy;
     __syncwarp();
 #endif
-    for (int base = 0; base < nc; base += kWarp) {
+    // one compliant contact at the point (rpx, rpy) rel. O of a body moving with (bw, bvx, bvy): penetration `pen` along the unit
+    // direction (nx, ny) the force pushes the body in; implicit in the point velocity (adds dt X^T D X to the body's articulated
+    // inertia and X^T w to its bias force, D = cnn n n^T + ctt t t^T)
+    auto contact_force = [&](double rpx, double rpy, double pen, double nx, double ny, double bw, double bvx, double bvy, double* add) {
+        const double tx = ny, ty = -nx;
+        const double pvx = bvx - bw * rpy, pvy = bvy + bw * rpx;
+        const double vn = pvx * nx + pvy * ny, vt = pvx * tx + pvy * ty;
+        const double fn0 = pp.kn * pen - pp.dn * vn;
+        if (fn0 > 0.0) {
+            const double cnn = pp.dn + dt * pp.kn;
+            const double ctt = pp.mu * fn0 / fmax(fabs(vt), pp.v_eps);
+            const double fwx = pp.kn * pen * nx - cnn * vn * nx - ctt * vt * tx;
+            const double fwy = pp.kn * pen * ny - cnn * vn * ny - ctt * vt * ty;
+            const double dxx = dt * (cnn * nx * nx + ctt * tx * tx), dxy = dt * (cnn * nx * ny + ctt * tx * ty),
+                         dyy = dt * (cnn * ny * ny + ctt * ty * ty);
+            const double kx = -rpy, ky = rpx;
+            const double dkx = dxx * kx + dxy * ky, dky = dxy * kx + dyy * ky;
+            add[0] = kx * dkx + ky * dky; add[1] = dkx; add[2] = dky; add[3] = dxx; add[4] = dxy; add[5] = dyy;
+            add[6] = -(rpx * fwy - rpy * fwx); add[7] = -fwx; add[8] = -fwy;
+        }
+    };
+    // rounds 0 .. nc/32: box corners against the height field.  rounds after that (pp.vertex_contacts): the terrain vertices inside a
+    // box -- lane (body, slot) looks at the slot-th vertex under the body's x extent (a box spans at most 4 vertices); where the surface
+    // is convex and the vertex lies inside, it is pushed out through the nearest face (sim/GroundVar2D.cpp:440-448 hands Bullet a
+    // height field: an edge of the terrain can enter a box between two of its corners)
+    const int nrounds = (nc + kWarp - 1) / kWarp;
+    for (int round = 0; round < (pp.vertex_contacts ? 2 * nrounds : nrounds); ++round) {
+        const bool vtx = round >= nrounds;
+        const int base = (vtx ? round - nrounds : round) * kWarp;
         const int ci = base + lane;
         const bool valid = ci < nc;
         const int b = valid ? s_cbody[ci] : 0;
+        if (vtx) {
+            const double bcw = shf(k.cw, b), bsw = shf(k.sw, b), brx = shf(k.rx, b), bry = shf(k.ry, b);
+            const double bax = s_bax[b], bay = s_bay[b], bc = s_bc[b], bs = s_bs[b], hxb = s_hx[b], hyb = s_hy[b];
+            const double C = bcw * bc - bsw * bs, S = bsw * bc + bcw * bs;                      // box axes in the world
+            const double cxr = brx + bcw * bax - bsw * bay, cyr = bry + bsw * bax + bcw * bay;   // box centre rel. O
+            const bool cand = valid && (e.oy + cyr - (fabs(S) * hxb + fabs(C) * hyb) <= clear_y);
+            if (!__any_sync(kFull, cand)) continue;
+            const double bw = shf(k.w, b), bvx = shf(k.vx, b), bvy = shf(k.vy, b);
+            double add[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+            bool touching = false;
+            if (cand) {
+                const double extx = fabs(C) * hxb + fabs(S) * hyb, cxw = e.ox + cxr;
+                double xv, hv, hp, hn;
+                if (g.vertex_slot(cxw - extx - pp.contact_tol, cxw + extx + pp.contact_tol, ci & 3, &xv, &hv, &hp, &hn) && hv - 0.5 * (hp + hn) > 1e-9) {
+                    const double rx = xv - cxw, ry = hv - (e.oy + cyr);
+                    const double lx = C * rx + S * ry, ly = -S * rx + C * ry;
+                    const double dx = hxb - fabs(lx), dy = hyb - fabs(ly);
+                    if (dx > -pp.contact_tol && dy > -pp.contact_tol) {
+                        touching = true;
+                        if (dx > 0.0 && dy > 0.0) {
+                            double nlx = 0.0, nly = 0.0, pen;
+                            if (dx < dy) { nlx = lx > 0.0 ? -1.0 : 1.0; pen = dx; } else { nly = ly > 0.0 ? -1.0 : 1.0; pen = dy; }
+                            contact_force(xv - e.ox, hv - e.oy, pen, C * nlx - S * nly, S * nlx + C * nly, bw, bvx, bvy, add);
+                        }
+                    }
+                }
+            }
+            const unsigned tmask = __ballot_sync(kFull, touching);
+            unsigned fmask = __ballot_sync(kFull, add[3] != 0.0 || add[5] != 0.0);
+            const int cb = lc.act ? m.corner_base[lane] : -1;
+            const bool mine = cb >= base && cb < base + kWarp;
+            while (fmask) {
+                const int src = __ffs(fmask) - 1;
+                fmask &= fmask - 1;
+                const bool to_me = mine && (src >= cb - base) && (src < cb - base + 4);
+#pragma unroll
+                for (int v = 0; v < 9; ++v) {
+                    double t = shf(add[v], src);
+                    if (to_me) ia[v] += t;
+                }
+            }
+            if (mine && ((tmask >> (cb - base)) & 0xfu)) contact |= 1 << lane;
+            continue;
+        }
         const double lx = valid ? s_clx[ci] : 0.0, ly = valid ? s_cly[ci] : 0.0;
 #if TRL_CONTACT_SMEM
         const double2 k0_ = kin0[b], k1_ = kin1[b];
@@ -912,24 +987,7 @@ __device__ int physics_substep(const LinkC& lc, EnvRegs& e, const GroundView& g,
             const double pen = (hgt - (e.oy + rpy)) * inv;
             if (pen > -pp.contact_tol) {
                 touching = true;
-                if (pen > 0.0) {
-                    const double nx = -slope * inv, ny = inv, tx = inv, ty = slope * inv;
-                    const double pvx = bvx - bw * rpy, pvy = bvy + bw * rpx;
-                    const double vn = pvx * nx + pvy * ny, vt = pvx * tx + pvy * ty;
-                    const double fn0 = pp.kn * pen - pp.dn * vn;
-                    if (fn0 > 0.0) {
-                        const double cnn = pp.dn + dt * pp.kn;
-                        const double ctt = pp.mu * fn0 / fmax(fabs(vt), pp.v_eps);
-                        const double fwx = pp.kn * pen * nx - cnn * vn * nx - ctt * vt * tx;
-                        const double fwy = pp.kn * pen * ny - cnn * vn * ny - ctt * vt * ty;
-                        const double dxx = dt * (cnn * nx * nx + ctt * tx * tx), dxy = dt * (cnn * nx * ny + ctt * tx * ty),
-                                     dyy = dt * (cnn * ny * ny + ctt * ty * ty);
-                        const double kx = -rpy, ky = rpx;
-                        const double dkx = dxx * kx + dxy * ky, dky = dxy * kx + dyy * ky;
-                        add[0] = kx * dkx + ky * dky; add[1] = dkx; add[2] = dky; add[3] = dxx; add[4] = dxy; add[5] = dyy;
-                        add[6] = -(rpx * fwy - rpy * fwx); add[7] = -fwx; add[8] = -fwy;
-                    }
-                }
+                if (pen > 0.0) contact_force(rpx, rpy, pen, -slope * inv, inv, bw, bvx, bvy, add);
             }
         }
         // hand the (few) force-producing corners to the lanes that own their bodies, in corner order (deterministic)
@@ -1172,7 +1230,7 @@ __device__ __forceinline__ void catchup_leave(const Buffers& B, int prev) {
 
 __global__ void __launch_bounds__(kBlockThreads, TRL_STEP_MIN_BLOCKS)
 trl_step_kernel(Buffers B, double h, int flags, int lists) {
-    __shared__ double s_clx[4 * kMaxJoints], s_cly[4 * kMaxJoints];
+    __shared__ double s_clx[4 * kMaxJoints + 6 * kMaxJoints], s_cly[4 * kMaxJoints];     // s_clx also carries the six per-body box tables
     __shared__ int s_cbody[4 * kMaxJoints];
 #if TRL_SMEM_ALIGNED
     __shared__ __align__(16) double s_x[kWarpsPerBlock * X_END];
@@ -1182,6 +1240,11 @@ trl_step_kernel(Buffers B, double h, int flags, int lists) {
     const ModelConst& m = c_model;
     for (int t = threadIdx.x; t < m.n_corners; t += kBlockThreads) {
         s_clx[t] = m.corner_lx[t]; s_cly[t] = m.corner_ly[t]; s_cbody[t] = m.corner_body[t];
+    }
+    for (int t = threadIdx.x; t < m.nj; t += kBlockThreads) {
+        double* tb = s_clx + 4 * kMaxJoints;
+        tb[t] = m.body_ax[t]; tb[kMaxJoints + t] = m.body_ay[t]; tb[2 * kMaxJoints + t] = m.body_cos[t]; tb[3 * kMaxJoints + t] = m.body_sin[t];
+        tb[4 * kMaxJoints + t] = m.half_x[t]; tb[5 * kMaxJoints + t] = m.half_y[t];
     }
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

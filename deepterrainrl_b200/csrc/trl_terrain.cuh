@@ -338,6 +338,40 @@ struct GroundView {
         return a + lerp * (b - a);
     }
 
+    // The slot-th terrain vertex with xmin <= x <= xmax (this project's contact model; oracle/terrain.h: Ground::for_vertices): the
+    // min segment's vertices first (without its last one, which the max segment repeats at the seam), then the max segment's.
+    // Returns the vertex (x, h) and its two neighbours' heights; the window's end vertices repeat their own height.
+    __device__ bool vertex_slot(double xmin, double xmax, int slot, double* xv, double* hv, double* hp, double* hn) const {
+        const double sp = TRL_VERT_SPACING_D;
+        const int ia = seg_id(0), ib = seg_id(1);
+        const int wa = n[ia] < kTerrainCap ? n[ia] : kTerrainCap, wb = n[ib] < kTerrainCap ? n[ib] : kTerrainCap;
+        int a0 = 0, a1 = -1, b0 = 0, b1 = -1;
+        if (wa > 0) {
+            a0 = max((int)ceil((xmin - min_x[ia]) / sp - 1e-9), 0);
+            a1 = min((int)floor((xmax - min_x[ia]) / sp + 1e-9), wa - 2);        // x < seam: the last vertex belongs to the max segment
+        }
+        if (wb > 0) {
+            b0 = max((int)ceil((xmin - min_x[ib]) / sp - 1e-9), 0);
+            b1 = min((int)floor((xmax - min_x[ib]) / sp + 1e-9), wb - 1);
+        }
+        const int na = max(a1 - a0 + 1, 0);
+        if (slot < na) {
+            const int kk = a0 + slot;
+            const float* d = data + ia * kTerrainCap;
+            *xv = min_x[ia] + kk * sp; *hv = (double)d[kk];
+            *hp = kk > 0 ? (double)d[kk - 1] : (double)d[kk];
+            *hn = (double)d[kk + 1];
+            return true;
+        }
+        const int kk = b0 + (slot - na);
+        if (kk > b1) return false;
+        const float* d = data + ib * kTerrainCap;
+        *xv = min_x[ib] + kk * sp; *hv = (double)d[kk];
+        *hp = kk > 0 ? (double)d[kk - 1] : sample(*xv - sp);
+        *hn = kk < wb - 1 ? (double)d[kk + 1] : (double)d[kk];
+        return true;
+    }
+
     // Upper bound of sample(x) over x in [x0, x1]: max of the vertices either segment can interpolate between for that
     // window (clamped sampling maps x outside a segment to its end vertex, which the clamped index range includes).
     // Warp-cooperative; every lane returns the same value.

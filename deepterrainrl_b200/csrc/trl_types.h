@@ -64,6 +64,7 @@ enum IField : int {
 
 struct PhysParams {
     double kn, dn, mu, v_eps, contact_tol, k_lim, d_lim;
+    int vertex_contacts;      // terrain vertices inside body boxes produce contacts too (opt-in: TRL_VERTEX_CONTACTS=1)
 };
 
 // Model / scene constants, uploaded once into __constant__ memory (uniform across lanes -> constant-cache broadcast).

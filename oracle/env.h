@@ -52,7 +52,7 @@ struct PhysParams {
     double contact_tol = 0.00025;  // 0.001 Bullet units / world_scale 4 (sim/ContactManager.cpp:74)
     double k_lim = 2.0e4;   // joint-limit stiffness [N m/rad]
     double d_lim = 20.0;    // joint-limit damping [N m s/rad]
-    int vertex_contacts = std::getenv("ORC_VTX") ? std::atoi(std::getenv("ORC_VTX")) : 0;   // terrain vertices inside boxes (experiment switch)
+    int vertex_contacts = std::getenv("ORC_VTX") ? std::atoi(std::getenv("ORC_VTX")) : 0;   // terrain vertices inside body boxes produce contacts too (opt-in: ORC_VTX=1)
 };
 
 // dog / goat joint indices (sim/SimDog.h:11-36)

@@ -35,9 +35,9 @@ def _gather_worker(rank, world, port, pack, out_dir):
     comm = parallel.Comm(sc, rank, world, backend="external")
     sc.EnableExplore(True, 0.3, 0.025, 0.02)
     got_rows, got_flags, got_env, local_rows, counts_log = [], [], [], [], []
-    for k in range(80):
+    for k in range(48):
         sc.Update(1.0 / 30.0)
-        if k % 20 == 19:
+        if k % 12 == 11:
             loc, lf, le = sc.GetTuples()                 # what this rank is about to contribute, ordered as in its block
             local_rows.append(loc)
             # a block of 4 rows: more tuples than one gather carries -> the remainder must stay queued, not be lost
@@ -72,7 +72,7 @@ def test_gloo_world2_native_tuple_gather(assets, tmp_path):
     for r, loc in enumerate((g0["local"], g1["local"])):
         assert by_rank[r].shape == loc.shape
         np.testing.assert_array_equal(by_rank[r], loc.astype(np.float32))   # order inside a rank is preserved by the queue
-    assert int(g0["steps"]) == int(g1["steps"]) == 2 * 6 * 80 * 20
+    assert int(g0["steps"]) == int(g1["steps"]) == 2 * 6 * 48 * 20
     assert int(g0["cycles"]) == int(g0["local_cycles"]) + int(g1["local_cycles"])
     assert int(g0["dropped"]) == 0
 
@@ -88,12 +88,17 @@ def _train_worker(rank, world, port, pack, out_dir):
     assert comm.ReplicaSpread(tr) > 0
     comm.BroadcastTrainer(tr, root=0)                   # ... is brought back by cNeuralNetLearner::SyncNet across ranks
     assert comm.ReplicaSpread(tr) == 0.0
+    # a critic batch needs 32 tuples: the same synthetic tuples on both ranks, then the gathered rollout tuples on top
+    rng = np.random.default_rng(4)
+    rows = rng.normal(size=(40, tr.W)) * 0.1
+    rows[:, 1 + tr.S] = rng.integers(0, 3, 40)
+    tr.AddTuples(rows, np.zeros(40, np.uint32))
     sc.EnableExplore(True, 0.1, 0.025, 0.0)
-    for k in range(74):
+    for k in range(34):
         sc.Update(1.0 / 30.0)
         comm.GatherTuples(block_rows=64)
         comm.AddGathered(tr)
-        if k >= 70:
+        if k >= 32:
             tr.Train(1)                                 # the first call initialises the input offset / scale
     c = tr.counters()
     spread = comm.ReplicaSpread(tr)
@@ -111,7 +116,7 @@ def test_gloo_world2_emulated_engines_replicated_trainers(assets, tmp_path):
     port = 29500 + ((os.getpid() + 517) % 1000)
     mp.spawn(_train_worker, args=(2, port, pack, str(tmp_path)), nprocs=2, join=True)
     e0 = np.load(tmp_path / "e0.npz"); e1 = np.load(tmp_path / "e1.npz")
-    assert int(e0["total"]) == int(e1["total"]) >= 32 and int(e0["num"]) == int(e1["num"]) == int(e0["total"])
+    assert int(e0["total"]) == int(e1["total"]) > 40 and int(e0["num"]) == int(e1["num"]) == int(e0["total"])      # 40 seeded + gathered
     assert int(e0["iters"]) == int(e1["iters"]) >= 2, (int(e0["total"]), int(e0["critic"]), int(e0["stage"]))
     assert int(e0["local_cycles"]) > 0 and int(e1["local_cycles"]) > 0
     np.testing.assert_array_equal(e0["theta"], e1["theta"])          # bit-identical replicas

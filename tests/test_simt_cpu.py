@@ -424,7 +424,7 @@ def test_asynchronous_trainer_loop(assets):
         assert L.trl_trainer_set_async(tr.h, 1) == 0, L.trl_last_error().decode()
         theta0 = tr.get("theta")
         state, ms = C.c_int64(0), C.c_double(0)
-        updates, iters = 8, 1
+        updates, iters = 4, 1
         assert L.trl_train_run_timed(tr.h, sp.ctypes.data_as(C.c_void_p), updates, iters, 32, C.c_double(1.0 / 30.0), 0, C.byref(state),
                                      C.byref(ms)) == 0, L.trl_last_error().decode()
         c = tr.counters()
@@ -434,3 +434,28 @@ def test_asynchronous_trainer_loop(assets):
         assert L.trl_trainer_set_async(tr.h, 0) == 0                                        # back to the pointer binding
         sc.Update(); sc.Sync()
         tr.close(); sc.close(); del keep
+
+
+def test_vertex_contacts_opt_in_vs_oracle(assets, monkeypatch):
+    """The opt-in contact model (terrain vertices inside body boxes) in the kernel sources against the oracle's: goat /
+    cliffs, where step edges do enter boxes -- the trajectories differ from the default model's and agree with each other."""
+    from pyoracle import Oracle
+    import deepterrainrl_b200 as trl
+    pack = os.path.join(assets, "goat_cliffs.trlpack")
+    n, updates = 3, 26
+    base = Oracle(pack, n, 0)
+    for _ in range(updates):
+        base.update(1.0 / 30.0, 1)
+    monkeypatch.setenv("ORC_VTX", "1")
+    monkeypatch.setenv("TRL_VERTEX_CONTACTS", "1")
+    o = Oracle(pack, n, 0)                           # the switch is read when a scene is loaded
+    with simt_library():
+        g = trl.ScenarioPoliEval(pack, n)
+        for _ in range(updates):
+            g.Update(1.0 / 30.0); o.update(1.0 / 30.0, 1)
+        gq, _ = g.GetStateAll()
+        g.close()
+    oq = np.stack([o.get_state(e)[0] for e in range(n)], axis=1)
+    bq = np.stack([base.get_state(e)[0] for e in range(n)], axis=1)
+    assert np.max(np.abs(gq - oq) / (1.0 + np.abs(oq))) < 1e-8
+    assert np.max(np.abs(bq - oq)) > 1e-6            # the opt-in model did change the motion
