@@ -33,7 +33,9 @@ DT = 1.0 / 30.0
 # per env-step the persistent state must be read and written once (q, qd, held torque, 64-scalar
 # controller block = 133 scalars each way) plus <= 42 terrain vertices read: (133 * 2) * 8 B + 42 * 4 B for f64 state
 ALGO_BYTES_PER_ENV_STEP = 133 * 2 * 8 + 42 * 4
-FP64_INST_PER_LAUNCH_ENV = 138.0e3     # ncu smsp__sass_thread_inst_executed_op_fp64 of one 4096-env step launch / 4096 (dog)
+# ncu (profiles/ncu_step_kernel_r02.csv, dog / slopes_mixed, one 4096-env step launch): DFMA + DADD + DMUL thread-instructions per cycle
+# (445.6 + 341.0 + 110.4) x 309,825 elapsed cycles = 278 M per launch
+FP64_INST_PER_LAUNCH_ENV = 278.0e6 / 4096
 
 
 def measured_peaks():
@@ -144,6 +146,18 @@ def granted_cores():
         n = max(1, min(n, int(quota + 0.5)))
     info["used"] = n
     return n, info
+
+
+def ncu_metric(name):
+    """one metric of the committed `ncu --set full` summary of the step kernel (profiles/ncu_step_kernel_r02.csv), or None"""
+    try:
+        for line in open(os.path.join(ROOT, "profiles", "ncu_step_kernel_r02.csv")):
+            f = line.strip().split(",")
+            if len(f) == 3 and f[0] == name:
+                return float(f[2])
+    except (OSError, ValueError):
+        pass
+    return None
 
 
 def cpu_reference(num_envs, seconds_target, threads, min_updates=1):
@@ -393,6 +407,12 @@ def main():
     env_steps_per_launch = ENV_STEPS_PER_UPDATE / step_l
     achieved = ALGO_BYTES_PER_ENV_STEP * n * env_steps_per_launch / launch_s / 1e9
     stats = sc._stats()
+    if world > 1:
+        # cOptScenarioPoliEval::OutputResults' merge of the per-scene results, over the ranks: one all-reduce through the C ABI
+        from deepterrainrl_b200 import parallel
+        ev_comm = parallel.Comm(sc, rank, world, backend="nccl")
+        stats = ev_comm.EvalStats()
+        ev_comm.close()
 
     # ---- BASELINE configs[3] in the same run: exploration on, ONE all-gather of the tuple blocks per outer update through the
     # C ABI (trl_gather_tuples), every rank's trainer fed with all ranks' tuples, trainer iterations between the updates
@@ -430,7 +450,8 @@ def main():
                      "algorithmic_bytes_per_env_step": ALGO_BYTES_PER_ENV_STEP, "env_steps_per_launch": env_steps_per_launch,
                      "step_kernel_share_of_update": step_ms / (step_ms + dec_ms),
                      "note": "path is FP64-latency bound, not HBM bound (SURVEY §8d): see DESIGN.md"},
-        "sim": {"episodes": stats["episodes"], "cycles": stats["cycles"], "avg_dist_m": stats["avg_dist"]},
+        "sim": {"episodes": stats["episodes"], "cycles": stats["cycles"], "avg_dist_m": stats["avg_dist"],
+                "merged_over_ranks": world > 1},
     }
     if cpu_val is not None:
         line["cpu_baseline"] = {"value": cpu_val, "unit": "env-steps/s", "cores": cores, "kind": "port", "per_thread": cpu_val / cores,
@@ -448,7 +469,10 @@ def main():
         fp64_peak = 148 * 64 * sm_mhz * 1e6
         fp64_ach = FP64_INST_PER_LAUNCH_ENV * n / launch_s
         line["roofline"]["fp64_pipe"] = {"achieved_ginst_s": fp64_ach / 1e9, "peak_ginst_s": fp64_peak / 1e9, "frac": fp64_ach / fp64_peak,
-                                         "thread_inst_per_launch_env": FP64_INST_PER_LAUNCH_ENV, "peak": "148 SMs x 64 FP64 lanes x measured SM clock"}
+                                         "thread_inst_per_launch_env": FP64_INST_PER_LAUNCH_ENV, "peak": "148 SMs x 64 FP64 lanes x measured SM clock",
+                                         "what": "DFMA + DADD + DMUL thread-instructions (ncu) of the step kernel per launch / live launch time",
+                                         "ncu_pipe_fp64_cycles_active_pct": ncu_metric("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
+                                         "ncu_issue_active_pct": ncu_metric("smsp__issue_active.avg.pct_of_peak_sustained_active")}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

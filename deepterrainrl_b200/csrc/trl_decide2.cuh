@@ -34,10 +34,14 @@ constexpr int kTipIn = kConv2Out * kW2;   // 5984 = terr_ip0 fan-in
 constexpr int kKT = 16;                  // k extent of a TMA tile: 16 doubles = the 128-byte swizzle span
 constexpr int kNumKTiles = kTipIn / kKT;  // 374
 static_assert(kNumKTiles * kKT == kTipIn, "terr_ip0 fan-in must be a whole number of TMA tiles");
-constexpr int kFcStages = 8;
+// A pipeline stage carries kTilesPerStage k-tiles: the per-stage cost of the ring (full / empty barrier round trip of the whole CTA,
+// ~0.3 us measured, tools/microbench/tma_stream.cu + profiles/decide_fc_phases_r02.txt) is paid half as often as with one tile per stage
+constexpr int kTilesPerStage = 2;
+constexpr int kFcStages = 4;
 constexpr int kWTileBytes = kTip0Out * kKT * 8;          // 8 KB  [64 n][16 k]
 constexpr int kATileBytes = kFcRows * kKT * 8;           // 4 KB  [32 m][16 k]
-constexpr int kStageBytes = kWTileBytes + kATileBytes;   // 12 KB, a multiple of 1024 (swizzle atom alignment)
+constexpr int kTileBytes = kWTileBytes + kATileBytes;    // 12 KB, a multiple of 1024 (swizzle atom alignment)
+constexpr int kStageBytes = kTilesPerStage * kTileBytes;
 constexpr int kCatStride = 148;          // doubles per row of concat0 (64 + n_char <= 147, +1 zero pad): 1184 B = 32 mod 128 -> conflict-free fragments
 constexpr int kHStride = 260;            // doubles per row of the ip0 output (256 + 4): 2080 B = 32 mod 128
 constexpr int kHHStride = 132;           // doubles per row of one head's hidden layer (128 + 4)
@@ -349,60 +353,72 @@ __device__ __forceinline__ void fc_stage(const Buffers& B, const NetWeights& W, 
             // ---------------- terr_ip0: P[32][64] = A[32][k slice] * Wt[k slice][64]; warp w owns C tiles (m tile w / 4, n tiles 2 (w % 4) + {0, 1})
             const int mt = warp >> 2, nt0 = (warp & 3) * 2;
             double c00 = 0, c01 = 0, c10 = 0, c11 = 0;
-            const int ntile = kt1 - kt0;
+            const int ntile = kt1 - kt0, nload = (ntile + kTilesPerStage - 1) / kTilesPerStage;
 #ifndef TRL_SIMT_EMU
             // producer: thread 0 keeps up to kFcStages tiles in flight
             int issued = 0;
-            auto issue = [&](int j) {
+            auto issue = [&](int j) {          // stage-load j: k-tiles kt0 + 2 j, kt0 + 2 j + 1 (the last one may hold a single tile)
                 const unsigned it = pipe_iter + (unsigned)j;
                 const int s = (int)(it % kFcStages);
                 const unsigned round = it / kFcStages;
                 if (round > 0) mbar_wait(&bar_empty[s], (round - 1) & 1);
                 unsigned char* st = fc_smem + kFcOffPipe + (size_t)s * kStageBytes;
-                mbar_expect_tx(&bar_full[s], kStageBytes);
-                tma_load_2d(st, &maps.w, &bar_full[s], (kt0 + j) * kKT, 0);
-                tma_load_2d(st + kWTileBytes, &maps.a, &bar_full[s], (kt0 + j) * kKT, row0);
+                const int nt = min(kTilesPerStage, ntile - j * kTilesPerStage);
+                mbar_expect_tx(&bar_full[s], nt * kTileBytes);
+                for (int q = 0; q < nt; ++q) {
+                    const int kt = kt0 + j * kTilesPerStage + q;
+                    tma_load_2d(st + q * kTileBytes, &maps.w, &bar_full[s], kt * kKT, 0);
+                    tma_load_2d(st + q * kTileBytes + kWTileBytes, &maps.a, &bar_full[s], kt * kKT, row0);
+                }
             };
             if (tid == 0) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // H / HH of the previous chunk live in the same bytes
-                for (; issued < min(kFcStages, ntile); ++issued) issue(issued);
+                for (; issued < min(kFcStages, nload); ++issued) issue(issued);
             }
 #endif
-            for (int j = 0; j < ntile; ++j) {
+            for (int j = 0; j < nload; ++j) {
                 const unsigned it = pipe_iter + (unsigned)j;
                 const int s = (int)(it % kFcStages);
-                double* Wt = (double*)(fc_smem + kFcOffPipe + (size_t)s * kStageBytes);
-                double* At = (double*)(fc_smem + kFcOffPipe + (size_t)s * kStageBytes + kWTileBytes);
+                const int nt = min(kTilesPerStage, ntile - j * kTilesPerStage);
 #ifndef TRL_SIMT_EMU
                 mbar_wait(&bar_full[s], (it / kFcStages) & 1);
 #else
                 // emulator: the tile copies TMA would perform, same swizzled layout
                 __syncthreads();
-                for (int i = tid; i < kTip0Out * kKT; i += kFcThreads) {
-                    const int n = i / kKT, k = i - n * kKT;
-                    Wt[swz(n, k)] = maps.w_ptr[(size_t)n * kTipIn + (kt0 + j) * kKT + k];
-                }
-                for (int i = tid; i < kFcRows * kKT; i += kFcThreads) {
-                    const int r = i / kKT, k = i - r * kKT;
-                    At[swz(r, k)] = (row0 + r) < maps.a_rows ? maps.a_ptr[(size_t)(row0 + r) * kTipIn + (kt0 + j) * kKT + k] : 0.0;
+                for (int q = 0; q < nt; ++q) {
+                    double* Wq = (double*)(fc_smem + kFcOffPipe + (size_t)s * kStageBytes + (size_t)q * kTileBytes);
+                    double* Aq = (double*)(fc_smem + kFcOffPipe + (size_t)s * kStageBytes + (size_t)q * kTileBytes + kWTileBytes);
+                    const int kt = kt0 + j * kTilesPerStage + q;
+                    for (int i = tid; i < kTip0Out * kKT; i += kFcThreads) {
+                        const int n = i / kKT, k = i - n * kKT;
+                        Wq[swz(n, k)] = maps.w_ptr[(size_t)n * kTipIn + kt * kKT + k];
+                    }
+                    for (int i = tid; i < kFcRows * kKT; i += kFcThreads) {
+                        const int r = i / kKT, k = i - r * kKT;
+                        Aq[swz(r, k)] = (row0 + r) < maps.a_rows ? maps.a_ptr[(size_t)(row0 + r) * kTipIn + kt * kKT + k] : 0.0;
+                    }
                 }
                 __syncthreads();
 #endif
+                for (int q = 0; q < nt; ++q) {
+                    const double* Wt = (const double*)(fc_smem + kFcOffPipe + (size_t)s * kStageBytes + (size_t)q * kTileBytes);
+                    const double* At = (const double*)(fc_smem + kFcOffPipe + (size_t)s * kStageBytes + (size_t)q * kTileBytes + kWTileBytes);
 #pragma unroll
-                for (int ks = 0; ks < kKT / 4; ++ks) {
-                    const double a = At[swz(mt * 8 + g, ks * 4 + t4)];
-                    const double b0 = Wt[swz(nt0 * 8 + g, ks * 4 + t4)];
-                    const double b1 = Wt[swz(nt0 * 8 + 8 + g, ks * 4 + t4)];
-                    dmma_8x8x4(c00, c01, a, b0);
-                    dmma_8x8x4(c10, c11, a, b1);
+                    for (int ks = 0; ks < kKT / 4; ++ks) {
+                        const double a = At[swz(mt * 8 + g, ks * 4 + t4)];
+                        const double b0 = Wt[swz(nt0 * 8 + g, ks * 4 + t4)];
+                        const double b1 = Wt[swz(nt0 * 8 + 8 + g, ks * 4 + t4)];
+                        dmma_8x8x4(c00, c01, a, b0);
+                        dmma_8x8x4(c10, c11, a, b1);
+                    }
                 }
 #ifndef TRL_SIMT_EMU
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bar_empty[s]);
-                if (tid == 0 && issued < ntile) { issue(issued); ++issued; }
+                if (tid == 0 && issued < nload) { issue(issued); ++issued; }
 #endif
             }
-            pipe_iter += (unsigned)ntile;
+            pipe_iter += (unsigned)nload;
             P[(mt * 8 + g) * kTip0Out + nt0 * 8 + 2 * t4] = c00;
             P[(mt * 8 + g) * kTip0Out + nt0 * 8 + 2 * t4 + 1] = c01;
             P[(mt * 8 + g) * kTip0Out + nt0 * 8 + 8 + 2 * t4] = c10;
