@@ -364,6 +364,7 @@ def main():
     barrier()
     t_beg = time.perf_counter()
     ms = sc.BenchUpdates(args.steps, DT, flush_l2=True)
+    span_ms = sc.BenchLastSpan()
     t_end = time.perf_counter()
     barrier()
     clocks = sampler.stop(t_beg, t_end) if rank == 0 else None
@@ -437,8 +438,9 @@ def main():
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "envs_per_gpu": n,
                    "env_steps_per_step": ENV_STEPS_PER_UPDATE * n, "sim_substeps": 5, "parallelism": f"env-shard x{world}",
-                   "l2": "flushed between steps (256 MiB memset on the engine stream)",
-                   "timing": "cudaEvent on the engine stream around K graph-launched updates",
+                   "l2": "flushed before every step (256 MiB memset on the engine stream, between the per-step event pairs: the flush itself is not timed)",
+                   "timing": "one cudaEvent pair per graph-launched update on the engine stream, K pairs summed; span_ms_incl_flush = first start to last end with the flushes in it",
+                   "span_ms_incl_flush": span_ms, "env_groups": int(os.environ.get("TRL_GROUPS", "0")) or "library default",
                    "presim_s": args.presim, "build": os.environ.get("TRL_VARIANT") or "product"},
         "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": d2h,
                 "note": "poli_eval is closed-loop: no per-step host inputs exist; each step reads the counters and all poses/velocities back to host arrays (pinned staging, read-back of step k overlapped with step k+1)"},

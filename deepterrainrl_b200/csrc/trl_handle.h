@@ -31,6 +31,8 @@ struct trl_handle {
     cudaStream_t stream = nullptr;
     cudaStream_t aux_stream = nullptr;           // = side[0]
     cudaStream_t side[8] = {nullptr};            // high-priority side streams: decisions + catch-up launches of env-step l run on side[l % lag]
+    int groups = 2;                              // env groups of the main step launches (TRL_GROUPS, 1..kMaxGroups; reduced when a group would be empty): see enqueue_update
+    cudaStream_t group_stream[7] = {nullptr};    // streams of groups 1 .. groups-1 (group 0 runs on `stream`)
     int lag = 6;                                 // overlap depth: env-steps a pending env may trail the main launches (TRL_LAG, 1..7)
     std::vector<cudaEvent_t> fork_events;        // dependencies between the two streams inside one update
     bool overlap = true;                         // TRL_SERIAL_SCHEDULE=1 turns the overlapped schedule off
@@ -55,6 +57,7 @@ struct trl_handle {
     std::vector<int32_t> h_dist_env;
     std::vector<void*> allocs;
     void* flush_buf = nullptr;
+    double bench_span_ms = 0.0;          // trl_bench_updates: first update's start to last update's end, flushes included
     double* probe_dump = nullptr;        // every blob of one forward pass (trl_probe.cu: trl_get_layer_state)
     // pipelined read-back (trl_snapshot / trl_snapshot_wait)
     cudaStream_t copy_stream = nullptr;

@@ -22,7 +22,7 @@ namespace trl {
 cudaError_t upload_model(const ModelConst& mc);
 size_t step_smem_bytes();
 cudaError_t configure_step_kernels();
-void launch_step(const Buffers& B, double h, int flags, int lists, cudaStream_t st);
+void launch_step(const Buffers& B, double h, int flags, int lists, cudaStream_t st, int group = 0, int n_groups = 1);
 void launch_reset(const Buffers& B, const uint64_t* seeds, const int* env_ids, int count, int reseed, cudaStream_t st);
 size_t decide_smem_bytes();
 cudaError_t configure_decide_kernel();
@@ -37,7 +37,7 @@ void launch_terrain(const Buffers& B, double lookahead, cudaStream_t st);
 }  // namespace trl
 namespace trl_cg {
 cudaError_t upload_model(const trl::ModelConst& mc);
-void launch_step(const trl::Buffers& B, double h, int flags, int lists, cudaStream_t st);
+void launch_step(const trl::Buffers& B, double h, int flags, int lists, cudaStream_t st, int group = 0, int n_groups = 1);
 }  // namespace trl_cg
 
 
@@ -497,46 +497,62 @@ static void enqueue_update(trl_handle* h, double dt, bool overlap, Timeline* tl 
     // advances exactly those envs by `lag` env-steps (fewer if the update ends first) while S_{l+1} .. S_{l+lag} skip them.
     // S_{l+lag+1} needs C_l.  The chain D_l -> C_l therefore has `lag` step launches of slack.
     const int lag = h->lag, nl = lag + 1;
+    // Env groups: the main launch of an env-step is split into G launches over contiguous env ranges, group g on its own stream
+    // (group 0 on the engine stream).  The groups only meet where the side work does (D_l needs S_l of every group, S_{l+lag+1} of every
+    // group needs C_l), so group g's S_{i+1} starts as soon as ITS S_i has drained and its CTAs fill the SM slots the tail of the other
+    // groups' launches would leave idle (4096 warps over 2368 resident-warp slots = 1.73 waves per monolithic launch).
+    const int G = std::max(1, std::min(h->groups, kMaxGroups));
     std::vector<cudaEvent_t>& fe = tl ? tl->fork : h->fork_events;
-    if ((int)fe.size() < 2 * ns + 2) {
+    const size_t need = (size_t)(ns + 1) * G + ns + 2;
+    if (fe.size() < need) {
         size_t old = fe.size();
-        fe.resize(2 * ns + 2);
+        fe.resize(need);
         for (size_t i = old; i < fe.size(); ++i) cudaEventCreateWithFlags(&fe[i], cudaEventDisableTiming);
     }
-    cudaEvent_t* ev_s = fe.data();            // ev_s[i]: S_i done
-    cudaEvent_t* ev_c = fe.data() + ns + 1;   // ev_c[l]: C_l (l < ns - 1) / D_{ns-1} done
+    cudaEvent_t* ev_s = fe.data();                    // ev_s[i * G + g]: S_i of group g done
+    cudaEvent_t* ev_c = fe.data() + (ns + 1) * G;     // ev_c[l]: C_l (l < ns - 1) / D_{ns-1} done
+    cudaEvent_t ev_t = fe[need - 1];                  // terrain look-ahead done
     auto lists_of = [&](int app, int prev, int reps) { return (app % nl) | ((prev % nl) << 3) | (reps << 6); };
-    auto main_step = [&](int flags, int lists, int) { launch_step(h->B, step, flags, lists, A); };
-    TL_OPEN(A, 1, 0); main_step(2, lists_of(0, 0, 0), 1); TL_CLOSE(A);
-    cudaEventRecord(ev_s[0], A);
+    auto stream_of = [&](int g) { return g == 0 ? A : h->group_stream[g - 1]; };
+    if (G > 1) { cudaEventRecord(ev_t, A); for (int g = 1; g < G; ++g) cudaStreamWaitEvent(stream_of(g), ev_t, 0); }
+    for (int g = 0; g < G; ++g) {
+        cudaStream_t M = stream_of(g);
+        TL_OPEN(M, 1, 0); launch_step(h->B, step, 2, lists_of(0, 0, 0), M, g, G); TL_CLOSE(M);
+        cudaEventRecord(ev_s[g], M);
+    }
     for (int i = 1; i < ns; ++i) {
         // side work for the envs that became due in S_{i-1}
         const int l = i - 1, slot = l % lag;
         cudaStream_t X = h->side[slot];
-        cudaStreamWaitEvent(X, ev_s[l], 0);
+        for (int g = 0; g < G; ++g) cudaStreamWaitEvent(X, ev_s[l * G + g], 0);
         TL_OPEN(X, 2, l); enqueue_decide(h, l % nl, 0, X, 1, slot); TL_CLOSE(X); TL_OPEN(X, 4, l); enqueue_decide(h, l % nl, 0, X, 2, slot); TL_CLOSE(X);
         const int reps = std::min(lag, ns - 1 - l);     // equivalents l + 1 .. l + reps of the main launches; S_end is never caught up
         TL_OPEN(X, 3, l); trl_cg::launch_step(h->B, step, 1 | 2 | 16, lists_of(l + 1, l, reps), X); TL_CLOSE(X);
         cudaEventRecord(ev_c[l], X);
-        if (i >= nl) cudaStreamWaitEvent(A, ev_c[i - nl], 0);
-        TL_OPEN(A, 1, i); main_step(1 | 2 | 8, lists_of(i, i, 0), i + 1); TL_CLOSE(A);
-        cudaEventRecord(ev_s[i], A);
+        for (int g = 0; g < G; ++g) {
+            cudaStream_t M = stream_of(g);
+            if (i >= nl) cudaStreamWaitEvent(M, ev_c[i - nl], 0);
+            TL_OPEN(M, 1, i); launch_step(h->B, step, 1 | 2 | 8, lists_of(i, i, 0), M, g, G); TL_CLOSE(M);
+            cudaEventRecord(ev_s[i * G + g], M);
+        }
     }
     {
         const int l = ns - 1, slot = l % lag;
         cudaStream_t X = h->side[slot];
-        cudaStreamWaitEvent(X, ev_s[l], 0);
+        for (int g = 0; g < G; ++g) cudaStreamWaitEvent(X, ev_s[l * G + g], 0);
         TL_OPEN(X, 2, l); enqueue_decide(h, l % nl, 1, X, 1, slot); TL_CLOSE(X); TL_OPEN(X, 4, l); enqueue_decide(h, l % nl, 1, X, 2, slot); TL_CLOSE(X);
         cudaEventRecord(ev_c[l], X);
     }
     for (int l = std::max(0, ns - nl); l < ns; ++l) cudaStreamWaitEvent(A, ev_c[l], 0);     // every side stream joins here
-    TL_OPEN(A, 1, ns); main_step(1 | 4, 0, ns + 1); TL_CLOSE(A);
+    for (int g = 1; g < G; ++g) cudaStreamWaitEvent(A, ev_s[(ns - 1) * G + g], 0);          // and every group stream
+    TL_OPEN(A, 1, ns); launch_step(h->B, step, 1 | 4, 0, A); TL_CLOSE(A);
 #undef TL_OPEN
 #undef TL_CLOSE
 }
 static int update_launches(const trl_handle* h, bool overlap) {
     const int ns = h->num_update_steps, d = num_decide_launches(h);
-    return overlap ? (2 + d) * ns : (1 + d) * ns + 2;    // terrain + S_0..S_{ns-1} + D_0..D_{ns-1} + S_end (+ C_0..C_{ns-2})
+    const int G = std::max(1, std::min(h->groups, kMaxGroups));
+    return overlap ? (1 + G + d) * ns : (1 + d) * ns + 2;    // G x S_0..S_{ns-1} + D_0..D_{ns-1} + S_end + C_0..C_{ns-2} (the terrain look-ahead is not counted)
 }
 
 extern "C" {
@@ -609,6 +625,11 @@ static trl_handle* create_common(trl_handle* h, int num_envs, int device, int mo
         for (int k = 0; k < h->lag; ++k)
             if (cudaStreamCreateWithPriority(&h->side[k], cudaStreamNonBlocking, hi) != cudaSuccess) return bail("cudaStreamCreate (side) failed");
         h->aux_stream = h->side[0];
+        const char* gr = std::getenv("TRL_GROUPS");
+        if (gr && gr[0]) h->groups = std::min(kMaxGroups, std::max(1, std::atoi(gr)));     // default 2: profiles/step_groups_r02_ab.txt
+        while (h->groups > 1 && group_chunk(num_envs, h->groups) * (h->groups - 1) >= num_envs) --h->groups;   // no empty group
+        for (int g = 1; g < h->groups; ++g)
+            if (cudaStreamCreateWithFlags(&h->group_stream[g - 1], cudaStreamNonBlocking) != cudaSuccess) return bail("cudaStreamCreate (group) failed");
         const char* serial = std::getenv("TRL_SERIAL_SCHEDULE");
         h->overlap = !(serial && serial[0] == '1');
     }
@@ -688,6 +709,8 @@ int trl_destroy(trl_handle* h) {
     for (void* p : h->allocs) cudaFree(p);
     for (int k = 0; k < 8; ++k)
         if (h->side[k]) { cudaStreamSynchronize(h->side[k]); cudaStreamDestroy(h->side[k]); }
+    for (int g = 0; g < kMaxGroups - 1; ++g)
+        if (h->group_stream[g]) { cudaStreamSynchronize(h->group_stream[g]); cudaStreamDestroy(h->group_stream[g]); }
     for (auto e : h->fork_events) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -1361,20 +1384,38 @@ int trl_bench_updates(trl_handle* h, double dt, int k, int flush_l2, double* ms_
     if (ensure_model(h)) return fail("model upload failed");
     const size_t flush_bytes = (size_t)256 << 20;
     if (flush_l2 && !h->flush_buf) { CK(cudaMalloc(&h->flush_buf, flush_bytes)); h->allocs.push_back(h->flush_buf); }
-    cudaEvent_t e0, e1;
-    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    // One event pair per update; the L2 flush (a measurement device, not part of the path) sits BETWEEN the pairs, so the reported
+    // time is the sum of the K updates' own device time, every one of them starting from a cold L2.
+    std::vector<cudaEvent_t> ev(2 * (size_t)std::max(k, 0));
+    for (auto& e : ev) CK(cudaEventCreate(&e));
     CK(cudaStreamSynchronize(h->stream));
-    CK(cudaEventRecord(e0, h->stream));
     for (int i = 0; i < k; ++i) {
         if (flush_l2) CK(cudaMemsetAsync(h->flush_buf, i & 0xff, flush_bytes, h->stream));
+        CK(cudaEventRecord(ev[2 * i], h->stream));
         if (trl_update(h, dt)) return 1;
+        CK(cudaEventRecord(ev[2 * i + 1], h->stream));
     }
-    CK(cudaEventRecord(e1, h->stream));
-    CK(cudaEventSynchronize(e1));
-    float ms = 0.f;
-    CK(cudaEventElapsedTime(&ms, e0, e1));
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    CK(cudaStreamSynchronize(h->stream));
+    double ms = 0.0;
+    for (int i = 0; i < k; ++i) {
+        float t = 0.f;
+        CK(cudaEventElapsedTime(&t, ev[2 * i], ev[2 * i + 1]));
+        ms += t;
+    }
+    if (k > 0) {
+        float t = 0.f;
+        CK(cudaEventElapsedTime(&t, ev[0], ev[2 * k - 1]));      // first update's start to last update's end, flushes included
+        h->bench_span_ms = t;
+    }
+    for (auto& e : ev) cudaEventDestroy(e);
     if (ms_total) *ms_total = ms;
+    return 0;
+}
+
+// the span of the last trl_bench_updates call from the first update's start to the last update's end, L2 flushes included
+int trl_bench_last_span(trl_handle* h, double* ms) {
+    if (!h || !ms) return fail("trl_bench_last_span: null argument");
+    *ms = h->bench_span_ms;
     return 0;
 }
 

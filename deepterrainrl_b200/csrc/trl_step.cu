@@ -25,6 +25,8 @@
 // The decision itself (MACE forward pass + action decode) runs in trl_decide.cuh between two launches of this kernel.
 #include <cuda_runtime.h>
 
+#include <algorithm>
+
 #include "trl_terrain.cuh"
 #include "trl_types.h"
 
@@ -377,6 +379,33 @@ __device__ void store_rng(Lane& L, const CounterRng& r) {
 
 // ================================================================================================ warp context
 // Per-lane constants of link `lane` and the env state held in registers.
+#ifndef TRL_LINK_SMEM
+#define TRL_LINK_SMEM 0     // 1: the per-lane link constants live in shared memory (one table per CTA) instead of ~28 registers per thread
+#endif
+#if TRL_LINK_SMEM
+enum { LF_AX, LF_AY, LF_MASS, LF_BAX, LF_BAY, LF_IZZ, LF_LIM_LO, LF_LIM_HI, LF_NUM };
+enum { LI_PARENT, LI_DEPTH, LI_ACC_ROUND, LI_ANC1, LI_ANC2, LI_ANC4, LI_ANC8, LI_NUM };
+// a field of the table as a value: every read is one conflict-free LDS (tables are [field][lane])
+template <int F> struct LkD { const double* p; __device__ __forceinline__ operator double() const { return p[F * kWarp]; } };
+template <int F> struct LkI { const int* p; __device__ __forceinline__ operator int() const { return p[F * kWarp]; } };
+struct LkU { const unsigned long long* p; __device__ __forceinline__ operator unsigned long long() const { return *p; } };
+struct LinkTables {
+    double d[LF_NUM * kWarp];
+    unsigned long long u[kWarp];
+    int i[LI_NUM * kWarp];
+};
+struct LinkC {
+    int act;            // lane < nj
+    LkI<LI_PARENT> parent; LkI<LI_DEPTH> depth; LkI<LI_ACC_ROUND> acc_round;
+    LkU acc_src;
+    LkI<LI_ANC1> anc1; LkI<LI_ANC2> anc2; LkI<LI_ANC4> anc4; LkI<LI_ANC8> anc8;
+    LkD<LF_AX> ax; LkD<LF_AY> ay;
+    LkD<LF_MASS> mass; LkD<LF_BAX> bax; LkD<LF_BAY> bay; LkD<LF_IZZ> izz_c;
+    LkD<LF_LIM_LO> lim_lo; LkD<LF_LIM_HI> lim_hi;
+};
+#define TRL_LINK_TABLES_DECL __shared__ LinkTables s_link; LinkTables* const link_tabs = &s_link;
+#else
+struct LinkTables;
 struct LinkC {
     int act;            // lane < nj
     int parent, depth;
@@ -385,9 +414,10 @@ struct LinkC {
     int anc1, anc2, anc4, anc8;   // 2^k-th ancestors (31 = none: the idle zero lane) for the pointer-jumping prefix sums
     double ax, ay;      // attach point in the parent's joint frame
     double mass, bax, bay, izz_c;
-    int has_lim;
     double lim_lo, lim_hi;
 };
+#define TRL_LINK_TABLES_DECL LinkTables* const link_tabs = nullptr;
+#endif
 struct Kin {            // world-axes kinematics of link `lane` about O (the root joint position)
     double phi, cw, sw, rx, ry, w, vx, vy;   // joint frame rotation, joint origin, spatial velocity (w, vO)
     double cx, cy;                           // body COM
@@ -398,9 +428,15 @@ struct EnvRegs {
     double tau;              // held joint torque of link j
 };
 
-__device__ __forceinline__ LinkC load_link(int lane) {
+// the link constants of lane `lane` as plain values (constant memory -> registers)
+struct LinkVals {
+    int act, parent, depth, acc_round, anc1, anc2, anc4, anc8;
+    unsigned long long acc_src;
+    double ax, ay, mass, bax, bay, izz_c, lim_lo, lim_hi;
+};
+__device__ __forceinline__ LinkVals link_values(int lane) {
     const ModelConst& m = c_model;
-    LinkC c;
+    LinkVals c;
     c.act = lane < m.nj;
     int j = c.act ? lane : 0;
     c.parent = (c.act && j > 0) ? m.parent[j] : 0;
@@ -417,9 +453,45 @@ __device__ __forceinline__ LinkC load_link(int lane) {
     c.mass = c.act ? m.mass[j] : 0.0;
     c.bax = m.body_ax[j]; c.bay = m.body_ay[j];
     c.izz_c = c.act ? m.izz_c[j] : 0.0;
-    c.has_lim = c.act ? m.has_limit[j] : 0;
-    c.lim_lo = c.has_lim ? m.lim_lo[j] : -INFINITY;    // no limit: never violated, so the limit force needs no branch
-    c.lim_hi = c.has_lim ? m.lim_hi[j] : INFINITY;
+    const int has_lim = c.act ? m.has_limit[j] : 0;
+    c.lim_lo = has_lim ? m.lim_lo[j] : -INFINITY;    // no limit: never violated, so the limit force needs no branch
+    c.lim_hi = has_lim ? m.lim_hi[j] : INFINITY;
+    return c;
+}
+// TRL_LINK_SMEM: the first warp of the CTA fills the table (the caller's __syncthreads() publishes it)
+__device__ __forceinline__ void stage_link_tables(LinkTables* t) {
+#if TRL_LINK_SMEM
+    if (threadIdx.x < kWarp) {
+        const int lane = threadIdx.x;
+        const LinkVals v = link_values(lane);
+        t->d[LF_AX * kWarp + lane] = v.ax; t->d[LF_AY * kWarp + lane] = v.ay; t->d[LF_MASS * kWarp + lane] = v.mass;
+        t->d[LF_BAX * kWarp + lane] = v.bax; t->d[LF_BAY * kWarp + lane] = v.bay; t->d[LF_IZZ * kWarp + lane] = v.izz_c;
+        t->d[LF_LIM_LO * kWarp + lane] = v.lim_lo; t->d[LF_LIM_HI * kWarp + lane] = v.lim_hi;
+        t->u[lane] = v.acc_src;
+        t->i[LI_PARENT * kWarp + lane] = v.parent; t->i[LI_DEPTH * kWarp + lane] = v.depth; t->i[LI_ACC_ROUND * kWarp + lane] = v.acc_round;
+        t->i[LI_ANC1 * kWarp + lane] = v.anc1; t->i[LI_ANC2 * kWarp + lane] = v.anc2; t->i[LI_ANC4 * kWarp + lane] = v.anc4;
+        t->i[LI_ANC8 * kWarp + lane] = v.anc8;
+    }
+#else
+    (void)t;
+#endif
+}
+__device__ __forceinline__ LinkC load_link(int lane, const LinkTables* t) {
+    LinkC c;
+#if TRL_LINK_SMEM
+    c.act = lane < c_model.nj;
+    const double* d = t->d + lane;
+    const int* i = t->i + lane;
+    c.parent.p = i; c.depth.p = i; c.acc_round.p = i; c.anc1.p = i; c.anc2.p = i; c.anc4.p = i; c.anc8.p = i;
+    c.acc_src.p = t->u + lane;
+    c.ax.p = d; c.ay.p = d; c.mass.p = d; c.bax.p = d; c.bay.p = d; c.izz_c.p = d; c.lim_lo.p = d; c.lim_hi.p = d;
+#else
+    (void)t;
+    const LinkVals v = link_values(lane);
+    c.act = v.act; c.parent = v.parent; c.depth = v.depth; c.acc_round = v.acc_round; c.acc_src = v.acc_src;
+    c.anc1 = v.anc1; c.anc2 = v.anc2; c.anc4 = v.anc4; c.anc8 = v.anc8;
+    c.ax = v.ax; c.ay = v.ay; c.mass = v.mass; c.bax = v.bax; c.bay = v.bay; c.izz_c = v.izz_c; c.lim_lo = v.lim_lo; c.lim_hi = v.lim_hi;
+#endif
     return c;
 }
 
@@ -433,7 +505,7 @@ __device__ __forceinline__ LinkC load_link(int lane) {
 #define TRL_TREE_PREFIX2(a, b)                                                                  \
     do {                                                                                        \
         _Pragma("unroll") for (int r_ = 0; r_ < 4; ++r_) {                                      \
-            int an_ = (r_ == 0) ? c.anc1 : ((r_ == 1) ? c.anc2 : ((r_ == 2) ? c.anc4 : c.anc8)); \
+            int an_ = (r_ == 0) ? (int)c.anc1 : ((r_ == 1) ? (int)c.anc2 : ((r_ == 2) ? (int)c.anc4 : (int)c.anc8)); \
             double2* buf_ = trl_as2<double2>(xs + X_PFX + (r_ & 1) * 2 * kWarp);      \
             buf_[lane] = make_double2((a), (b));                                                \
             __syncwarp();                                                                       \
@@ -445,7 +517,7 @@ __device__ __forceinline__ LinkC load_link(int lane) {
 #define TRL_TREE_PREFIX2(a, b)                                                                  \
     do {                                                                                        \
         _Pragma("unroll") for (int r_ = 0; r_ < 4; ++r_) {                                      \
-            int an_ = (r_ == 0) ? c.anc1 : ((r_ == 1) ? c.anc2 : ((r_ == 2) ? c.anc4 : c.anc8)); \
+            int an_ = (r_ == 0) ? (int)c.anc1 : ((r_ == 1) ? (int)c.anc2 : ((r_ == 2) ? (int)c.anc4 : (int)c.anc8)); \
             double ta_ = shf((a), an_), tb_ = shf((b), an_);                                    \
             (a) += ta_; (b) += tb_;                                                             \
         }                                                                                       \
@@ -1246,6 +1318,8 @@ trl_step_kernel(Buffers B, double h, int flags, int lists) {
         tb[t] = m.body_ax[t]; tb[kMaxJoints + t] = m.body_ay[t]; tb[2 * kMaxJoints + t] = m.body_cos[t]; tb[3 * kMaxJoints + t] = m.body_sin[t];
         tb[4 * kMaxJoints + t] = m.half_x[t]; tb[5 * kMaxJoints + t] = m.half_y[t];
     }
+    TRL_LINK_TABLES_DECL
+    stage_link_tables(link_tabs);
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // pending-decision lists (lag + 1 of them, used round robin by successive env-steps): envs that reach a cycle boundary in this
@@ -1255,13 +1329,24 @@ trl_step_kernel(Buffers B, double h, int flags, int lists) {
     const int app = lists & 7, prev = (lists >> 3) & 7;
 
     int env = blockIdx.x * kWarpsPerBlock + warp;
+    int env_end = B.n;
+    {
+        // env groups (trl_host.cu: enqueue_update): a main launch covers group g of G contiguous env ranges, each on its own stream,
+        // so that the tail of one group's launch is filled by the next group's CTAs instead of leaving SM slots idle
+        const int G = (lists >> 14) & 15;
+        if (G > 1) {
+            const int chunk = group_chunk(B.n, G);
+            env += ((lists >> 10) & 15) * chunk;
+            env_end = min(B.n, (((lists >> 10) & 15) + 1) * chunk);
+        }
+    }
     if (flags & kStepCatchUp) {
         // catch-up launch: one warp per entry of list `prev`, after the decision kernel has served it.
         // The last CTA to leave re-arms that list (the main launch three steps later appends to it again).
         const int count = B.pending_count[prev];
         if (env >= count) { catchup_leave(B, prev); return; }
         env = B.pending_list[prev * B.n + env];
-    } else if (env >= B.n) {
+    } else if (env >= env_end) {
         return;
     }
     Lane L{nullptr, env, B.n, B.d, B.i};
@@ -1274,7 +1359,7 @@ trl_step_kernel(Buffers B, double h, int flags, int lists) {
         L.i(I_PENDING) = 0;    // serial schedule / end of the update: every decision has been served before this launch
     }
     double* xs = s_x + warp * X_END;
-    const LinkC lc = load_link(lane);
+    const LinkC lc = load_link(lane, link_tabs);
     EnvRegs e;
     load_env(L, lc, e, lane);
     int contact = L.i(I_CONTACT);
@@ -1443,6 +1528,11 @@ trl_step_kernel(Buffers B, double h, int flags, int lists) {
 // Initial reset of every env (trl_create / trl_reset): seeds the terrain RNG and runs the episode reset.
 __global__ void __launch_bounds__(kBlockThreads)
 trl_reset_kernel(Buffers B, const uint64_t* terrain_seeds, const int* env_ids, int count, int reseed) {
+    TRL_LINK_TABLES_DECL
+#if TRL_LINK_SMEM
+    stage_link_tables(link_tabs);
+    __syncthreads();
+#endif
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int idx = blockIdx.x * kWarpsPerBlock + warp;
     if (idx >= count) return;
@@ -1461,7 +1551,7 @@ trl_reset_kernel(Buffers B, const uint64_t* terrain_seeds, const int* env_ids, i
         L.d(D_CUR_CYCLE_T) = 0.0; L.d(D_CUR_STUMBLE) = 0.0; L.d(D_PREV_COM_X) = 0.0; L.d(D_PREV_COM_Y) = 0.0;
     }
     __syncwarp();
-    const LinkC lc = load_link(lane);
+    const LinkC lc = load_link(lane, link_tabs);
     EnvRegs e;
 #if TRL_KIN_SMEM
     __shared__ __align__(16) double s_pfx[kWarpsPerBlock * 3 * 2 * kWarp];
@@ -1533,8 +1623,15 @@ cudaError_t configure_step_kernels() {
     return cudaSuccess;
 #endif
 }
-void launch_step(const Buffers& B, double h, int flags, int lists, cudaStream_t st) {
-    int blocks = (B.n + kWarpsPerBlock - 1) / kWarpsPerBlock;
+void launch_step(const Buffers& B, double h, int flags, int lists, cudaStream_t st, int group, int n_groups) {
+    int envs = B.n;
+    if (n_groups > 1) {
+        const int chunk = group_chunk(B.n, n_groups);
+        envs = std::max(0, std::min(B.n, (group + 1) * chunk) - group * chunk);
+        lists |= (group << 10) | (n_groups << 14);
+        if (envs == 0) return;
+    }
+    int blocks = (envs + kWarpsPerBlock - 1) / kWarpsPerBlock;
     TRL_LAUNCH(trl_step_kernel, blocks, kBlockThreads, 0, st, B, h, flags, lists);
 }
 void launch_reset(const Buffers& B, const uint64_t* seeds, const int* env_ids, int count, int reseed, cudaStream_t st) {

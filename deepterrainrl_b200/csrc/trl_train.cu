@@ -553,62 +553,81 @@ __global__ void k_labels(Dev d, int pred, int mode) {
 }
 
 // ================================================================================================ backward
-// dw[o][i] = sum_n dy[n][o] x[n][i], db[o] = sum_n dy[n][o].  grid (nout, ceil(nin / 256))
-__global__ void k_fc_bwd_w(Dev d, int pred, const double* dy, int ldy, const double* x, int ldx, int nin, double* dw, double* db) {
-    pdl_sync();
-    if (!pred_on(d, pred)) return;
+// The four backward kernels are written as bodies over explicit block / thread coordinates: the per-layer kernels below call one
+// body each, k_bwd_multi (further down) runs several independent bodies in ONE launch (blocks of 256 threads).
+// dw[o][i] = sum_n dy[n][o] x[n][i], db[o] = sum_n dy[n][o].  grid (nout, ceil(nin / nthreads))
+__device__ __forceinline__ void fc_bwd_w_body(int bx, int by, int tid, int nthreads, const double* dy, int ldy, const double* x, int ldx, int nin,
+                                              double* dw, double* db) {
     __shared__ double dys[kB];
-    const int o = blockIdx.x;
-    if (threadIdx.x < kB) dys[threadIdx.x] = dy[(size_t)threadIdx.x * ldy + o];
+    const int o = bx;
+    if (tid < kB) dys[tid] = dy[(size_t)tid * ldy + o];
     __syncthreads();
-    const int i = blockIdx.y * blockDim.x + threadIdx.x;
+    const int i = by * nthreads + tid;
     if (i < nin) {
         double s = 0;
 #pragma unroll
         for (int n = 0; n < kB; ++n) s += dys[n] * x[(size_t)n * ldx + i];
         dw[(size_t)o * nin + i] = s;
     }
-    if (blockIdx.y == 0 && threadIdx.x == 0) {
+    if (by == 0 && tid == 0) {
         double s = 0;
         for (int n = 0; n < kB; ++n) s += dys[n];
         db[o] = s;
     }
 }
+__global__ void k_fc_bwd_w(Dev d, int pred, const double* dy, int ldy, const double* x, int ldx, int nin, double* dw, double* db) {
+    pdl_sync();
+    if (!pred_on(d, pred)) return;
+    fc_bwd_w_body(blockIdx.x, blockIdx.y, threadIdx.x, blockDim.x, dy, ldy, x, ldx, nin, dw, db);
+}
 // dx[n][i] (=|+=) mask(act[n][i]) * sum_o dy[n][o] w[o][i] for i < ncols.  grid (ceil(ncols / 32), kB), block (32, 8): the
-// output neurons are split over threadIdx.y and reduced through shared memory in a fixed order.
+// output neurons are split over ty and reduced through shared memory in a fixed order.  `heads` > 1: the sum over several
+// (dy, w) pairs with strides dy_stride / w_stride, accumulated head after head exactly like `heads` launches with accumulate = 1.
+__device__ __forceinline__ void fc_bwd_x_body(int bx, int by, int tx, int ty, const double* dy, int ldy, int nout, const double* w, int nin, int ncols,
+                                              const double* act, int lda, double* dx, int ldx, int accumulate, int heads, size_t dy_stride,
+                                              const double* const* w_heads) {
+    __shared__ double dys[H];
+    __shared__ double part[8][33];
+    const int n = by;
+    const int i = bx * 32 + tx;
+    double acc = 0;
+    for (int hd = 0; hd < heads; ++hd) {
+        const double* dyh = dy + (size_t)hd * dy_stride;
+        const double* wh = w_heads ? w_heads[hd] : w;
+        if (hd > 0) __syncthreads();                       // dys / part of the previous head have been consumed
+        for (int o = ty * 32 + tx; o < nout; o += 256) dys[o] = dyh[(size_t)n * ldy + o];
+        __syncthreads();
+        double s = 0;
+        if (i < ncols)
+            for (int o = ty; o < nout; o += 8) s += dys[o] * wh[(size_t)o * nin + i];
+        part[ty][tx] = s;
+        __syncthreads();
+        if (ty == 0 && i < ncols) {
+            double tot = 0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) tot += part[q][tx];
+            if (act && !(act[(size_t)n * lda + i] > 0)) tot = 0;
+            if (hd == 0) acc = tot; else acc += tot;
+        }
+    }
+    if (ty == 0 && i < ncols) {
+        if (accumulate) dx[(size_t)n * ldx + i] += acc; else dx[(size_t)n * ldx + i] = acc;
+    }
+}
 __global__ void k_fc_bwd_x(Dev d, int pred, const double* dy, int ldy, int nout, const double* w, int nin, int ncols, const double* act,
                            int lda, double* dx, int ldx, int accumulate) {
     pdl_sync();
     if (!pred_on(d, pred)) return;
-    __shared__ double dys[H];
-    __shared__ double part[8][33];
-    const int n = blockIdx.y, tx = threadIdx.x, ty = threadIdx.y;
-    for (int o = ty * 32 + tx; o < nout; o += 256) dys[o] = dy[(size_t)n * ldy + o];
-    __syncthreads();
-    const int i = blockIdx.x * 32 + tx;
-    double s = 0;
-    if (i < ncols)
-        for (int o = ty; o < nout; o += 8) s += dys[o] * w[(size_t)o * nin + i];
-    part[ty][tx] = s;
-    __syncthreads();
-    if (ty == 0 && i < ncols) {
-        double tot = 0;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) tot += part[q][tx];
-        if (act && !(act[(size_t)n * lda + i] > 0)) tot = 0;
-        if (accumulate) dx[(size_t)n * ldx + i] += tot; else dx[(size_t)n * ldx + i] = tot;
-    }
+    fc_bwd_x_body(blockIdx.x, blockIdx.y, threadIdx.x, threadIdx.y, dy, ldy, nout, w, nin, ncols, act, lda, dx, ldx, accumulate, 1, 0, nullptr);
 }
 // dw[o][c][kk] = sum_{n,t} dy[n][o][t] x[n][c][t + kk]; db[o] = sum dy[n][o][t].  grid (cin, cout)
-__global__ void k_conv_bwd_w(Dev d, int pred, const double* dy, int cout, int k, const double* x, int ldn, int cin, int win, double* dw,
-                             double* db) {
-    pdl_sync();
-    if (!pred_on(d, pred)) return;
-    const int c = blockIdx.x, o = blockIdx.y, wout = win - k + 1;
+__device__ __forceinline__ void conv_bwd_w_body(int bx, int by, int tid, int nthreads, const double* dy, int cout, int k, const double* x, int ldn,
+                                                int cin, int win, double* dw, double* db) {
+    const int c = bx, o = by, wout = win - k + 1;
     double acc[K0 + 1];
 #pragma unroll
     for (int kk = 0; kk <= K0; ++kk) acc[kk] = 0.0;
-    for (int idx = threadIdx.x; idx < kB * wout; idx += blockDim.x) {
+    for (int idx = tid; idx < kB * wout; idx += nthreads) {
         const int n = idx / wout, t = idx - n * wout;
         const double g = dy[((size_t)n * cout + o) * wout + t];
         const double* xr = x + (size_t)n * ldn + (size_t)c * win + t;
@@ -621,26 +640,30 @@ __global__ void k_conv_bwd_w(Dev d, int pred, const double* dy, int cout, int k,
 #pragma unroll
     for (int kk = 0; kk <= K0; ++kk) {
         double v = warp_sum(acc[kk]);
-        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][kk] = v;
+        if ((tid & 31) == 0) red[tid >> 5][kk] = v;
     }
     __syncthreads();
-    if (threadIdx.x <= K0) {
+    if (tid <= K0) {
         double s = 0;
-        for (int wq = 0; wq < (int)(blockDim.x >> 5); ++wq) s += red[wq][threadIdx.x];
-        if (threadIdx.x < k) dw[((size_t)o * cin + c) * k + threadIdx.x] = s;
-        else if (threadIdx.x == K0 && c == 0) db[o] = s;
+        for (int wq = 0; wq < (nthreads >> 5); ++wq) s += red[wq][tid];
+        if (tid < k) dw[((size_t)o * cin + c) * k + tid] = s;
+        else if (tid == K0 && c == 0) db[o] = s;
     }
 }
-// dx[n][c][s] = mask * sum_{o,kk} dy[n][o][s - kk] w[o][c][kk].  grid (cin, kB), one thread per input position
-__global__ void k_conv_bwd_x(Dev d, int pred, const double* dy, int cout, int k, const double* w, int cin, int win, const double* act,
-                             double* dx) {
+__global__ void k_conv_bwd_w(Dev d, int pred, const double* dy, int cout, int k, const double* x, int ldn, int cin, int win, double* dw,
+                             double* db) {
     pdl_sync();
     if (!pred_on(d, pred)) return;
+    conv_bwd_w_body(blockIdx.x, blockIdx.y, threadIdx.x, blockDim.x, dy, cout, k, x, ldn, cin, win, dw, db);
+}
+// dx[n][c][s] = mask * sum_{o,kk} dy[n][o][s - kk] w[o][c][kk].  grid (cin, kB), one thread per input position
+__device__ __forceinline__ void conv_bwd_x_body(int bx, int by, int tid, int nthreads, const double* dy, int cout, int k, const double* w, int cin,
+                                                int win, const double* act, double* dx) {
     __shared__ double ws[C2 * K2];            // cout * k <= 128
-    const int c = blockIdx.x, n = blockIdx.y, wout = win - k + 1;
-    for (int i = threadIdx.x; i < cout * k; i += blockDim.x) { int o = i / k, kk = i - o * k; ws[i] = w[((size_t)o * cin + c) * k + kk]; }
+    const int c = bx, n = by, wout = win - k + 1;
+    for (int i = tid; i < cout * k; i += nthreads) { int o = i / k, kk = i - o * k; ws[i] = w[((size_t)o * cin + c) * k + kk]; }
     __syncthreads();
-    const int s = threadIdx.x;
+    const int s = tid;
     if (s >= win) return;
     double acc = 0;
     for (int o = 0; o < cout; ++o) {
@@ -652,6 +675,40 @@ __global__ void k_conv_bwd_x(Dev d, int pred, const double* dy, int cout, int k,
     }
     const size_t idx = ((size_t)n * cin + c) * win + s;
     dx[idx] = (act[idx] > 0) ? acc : 0;
+}
+__global__ void k_conv_bwd_x(Dev d, int pred, const double* dy, int cout, int k, const double* w, int cin, int win, const double* act,
+                             double* dx) {
+    pdl_sync();
+    if (!pred_on(d, pred)) return;
+    conv_bwd_x_body(blockIdx.x, blockIdx.y, threadIdx.x, blockDim.x, dy, cout, k, w, cin, win, act, dx);
+}
+// Several independent backward bodies in one launch (fewer, fatter launches: the per-layer launches of a batch-32 step are bound
+// by launch latency, profiles/launches_trainer_r01_summary.csv).  Blocks of 256 threads; job q owns `blocks` consecutive blocks,
+// laid out as a gx x gy grid of that body.  Per-element arithmetic and summation order are those of the per-layer kernels.
+enum JobKind { J_FC_BWD_W = 0, J_FC_BWD_X, J_FC_BWD_X_HEADS, J_CONV_BWD_W, J_CONV_BWD_X };
+struct Job {
+    int kind, blocks, gx;
+    const double *dy, *a, *act;          // a: x (bwd_w) or w (bwd_x)
+    double *o0, *o1;                     // dw / dx, db
+    int i0, i1, i2, i3, i4, i5, i6;
+    const double* wh[4];                 // J_FC_BWD_X_HEADS: the four heads' weights
+};
+constexpr int kMaxJobs = 8;
+struct JobList { int n; Job j[kMaxJobs]; };
+__global__ void __launch_bounds__(256) k_bwd_multi(Dev d, int pred, JobList jl) {
+    pdl_sync();
+    if (!pred_on(d, pred)) return;
+    int b = blockIdx.x, q = 0;
+    while (q < jl.n - 1 && b >= jl.j[q].blocks) { b -= jl.j[q].blocks; ++q; }
+    const Job& J = jl.j[q];
+    const int bx = b % J.gx, by = b / J.gx, tid = threadIdx.x;
+    switch (J.kind) {
+        case J_FC_BWD_W: fc_bwd_w_body(bx, by, tid, 256, J.dy, J.i0, J.a, J.i1, J.i2, J.o0, J.o1); break;                       // ldy, ldx, nin
+        case J_FC_BWD_X: fc_bwd_x_body(bx, by, tid & 31, tid >> 5, J.dy, J.i0, J.i1, J.a, J.i2, J.i3, J.act, J.i4, J.o0, J.i5, J.i6, 1, 0, nullptr); break;
+        case J_FC_BWD_X_HEADS: fc_bwd_x_body(bx, by, tid & 31, tid >> 5, J.dy, J.i0, J.i1, nullptr, J.i2, J.i3, J.act, J.i4, J.o0, J.i5, 0, 4, (size_t)J.i6, J.wh); break;
+        case J_CONV_BWD_W: conv_bwd_w_body(bx, by, tid, 256, J.dy, J.i0, J.i1, J.a, J.i2, J.i3, J.i4, J.o0, J.o1); break;      // cout, k, ldn, cin, win
+        default: conv_bwd_x_body(bx, by, tid, 256, J.dy, J.i0, J.i1, J.a, J.i2, J.i3, J.act, J.o0); break;                      // cout, k, cin, win
+    }
 }
 // Caffe SGDSolver: Regularize (L2) + ComputeUpdateValue + Net::Update, one pass over all 26 blobs
 __global__ void k_sgd(Dev d, int pred) {
@@ -685,6 +742,7 @@ struct trl_trainer {
     trl::NetWeights nw[2];             // 0 current net, 1 target net
     trl::FcMaps fmaps[2];
     bool batched_fwd = true;           // TRL_TRAIN_FWD_V1=1: the per-layer kernels below
+    bool fused_bwd = true;             // TRL_TRAIN_BWD_V1=1: one launch per backward kernel (26 per pass instead of 8)
     double* stage_rows = nullptr;      // device staging for tuples handed in from the host
     uint32_t* stage_flags = nullptr;
     int stage_cap = 0;
@@ -756,10 +814,66 @@ int enqueue_forward(trl_trainer* t, int pred, int col0, const NetRef& net, cudaS
     return 0;
 }
 // backward of the current net from d.dy (activations of the last forward) into d.grad, then the SGD step
+static JobList job_list(std::initializer_list<Job> jobs) {
+    JobList jl{};
+    for (const Job& j : jobs) jl.j[jl.n++] = j;
+    return jl;
+}
+static int job_blocks(const JobList& jl) { int b = 0; for (int q = 0; q < jl.n; ++q) b += jl.j[q].blocks; return b; }
+static Job job_fc_w(const double* dy, int ldy, const double* x, int ldx, int nin, int nout, double* dw, double* db) {
+    Job j{}; j.kind = J_FC_BWD_W; j.gx = nout; j.blocks = nout * ((nin + 255) / 256);
+    j.dy = dy; j.a = x; j.o0 = dw; j.o1 = db; j.i0 = ldy; j.i1 = ldx; j.i2 = nin;
+    return j;
+}
+static Job job_fc_x(const double* dy, int ldy, int nout, const double* w, int nin, int ncols, const double* act, int lda, double* dx, int ldx, int accumulate) {
+    Job j{}; j.kind = J_FC_BWD_X; j.gx = (ncols + 31) / 32; j.blocks = j.gx * kB;
+    j.dy = dy; j.a = w; j.act = act; j.o0 = dx; j.i0 = ldy; j.i1 = nout; j.i2 = nin; j.i3 = ncols; j.i4 = lda; j.i5 = ldx; j.i6 = accumulate;
+    return j;
+}
+static Job job_conv_w(const double* dy, int cout, int k, const double* x, int ldn, int cin, int win, double* dw, double* db) {
+    Job j{}; j.kind = J_CONV_BWD_W; j.gx = cin; j.blocks = cin * cout;
+    j.dy = dy; j.a = x; j.o0 = dw; j.o1 = db; j.i0 = cout; j.i1 = k; j.i2 = ldn; j.i3 = cin; j.i4 = win;
+    return j;
+}
+static Job job_conv_x(const double* dy, int cout, int k, const double* w, int cin, int win, const double* act, double* dx) {
+    Job j{}; j.kind = J_CONV_BWD_X; j.gx = cin; j.blocks = cin * kB;
+    j.dy = dy; j.a = w; j.act = act; j.o0 = dx; j.i0 = cout; j.i1 = k; j.i2 = cin; j.i3 = win;
+    return j;
+}
 int enqueue_backward_update(trl_trainer* t, int pred, cudaStream_t st) {
     const Dev& d = t->d;
     auto W = [&](int b) { return d.theta + d.off[b]; };
     auto G = [&](int b) { return d.grad + d.off[b]; };
+    const int nflat = C2 * W2;
+    if (t->fused_bwd) {
+        // 8 launches: independent bodies of one level share a launch; the four heads run side by side (dhh holds one block per head)
+        auto multi = [&](const JobList& jl) { launch_pdl(k_bwd_multi, dim3(job_blocks(jl)), dim3(256), 0, st, d, pred, jl); };
+        JobList l1{}, l2{};
+        int col = 0;
+        Job hx{}; hx.kind = J_FC_BWD_X_HEADS; hx.gx = H / 32; hx.blocks = hx.gx * kB;
+        hx.dy = d.dhh; hx.act = d.h; hx.o0 = d.dh; hx.i0 = HH; hx.i1 = HH; hx.i2 = H; hx.i3 = H; hx.i4 = H; hx.i5 = H; hx.i6 = kB * HH;
+        for (int hd = 0; hd < 4; ++hd) {
+            const int nout = hd == 0 ? d.n_frags : d.frag;
+            double* hh = d.hh + (size_t)hd * kB * HH;
+            double* dhh = d.dhh + (size_t)hd * kB * HH;
+            l1.j[l1.n++] = job_fc_w(d.dy + col, d.n_out, hh, HH, HH, nout, G(12 + 4 * hd), G(13 + 4 * hd));
+            l1.j[l1.n++] = job_fc_x(d.dy + col, d.n_out, nout, W(12 + 4 * hd), HH, HH, hh, HH, dhh, HH, 0);
+            l2.j[l2.n++] = job_fc_w(dhh, HH, d.h, H, H, HH, G(10 + 4 * hd), G(11 + 4 * hd));
+            hx.wh[hd] = W(10 + 4 * hd);
+            col += nout;
+        }
+        l2.j[l2.n++] = hx;
+        multi(l1);
+        multi(l2);
+        multi(job_list({job_fc_w(d.dh, H, d.catb, d.cat, d.cat, H, G(8), G(9)), job_fc_x(d.dh, H, H, W(8), d.cat, T, d.t, T, d.dt, T, 0)}));
+        multi(job_list({job_fc_w(d.dt, T, d.a2, nflat, nflat, T, G(6), G(7)), job_fc_x(d.dt, T, T, W(6), nflat, nflat, d.a2, nflat, d.da2, nflat, 0)}));
+        multi(job_list({job_conv_w(d.da2, C2, K2, d.a1, C1 * W1, C1, W1, G(4), G(5)), job_conv_x(d.da2, C2, K2, W(4), C1, W1, d.a1, d.da1)}));
+        multi(job_list({job_conv_w(d.da1, C1, K1, d.a0, C0 * W0, C0, W0, G(2), G(3)), job_conv_x(d.da1, C1, K1, W(2), C0, W0, d.a0, d.da0)}));
+        multi(job_list({job_conv_w(d.da0, C0, K0, d.xn, d.S, 1, kTerr, G(0), G(1))}));
+        launch_pdl(k_sgd, dim3(296), dim3(256), 0, st, d, pred);
+        t->launches += 8;
+        return 0;
+    }
     int col = 0;
     for (int hd = 0; hd < 4; ++hd) {
         const int nout = hd == 0 ? d.n_frags : d.frag;
@@ -772,7 +886,6 @@ int enqueue_backward_update(trl_trainer* t, int pred, cudaStream_t st) {
     }
     launch_pdl(k_fc_bwd_w, dim3(dim3(H, 1)), dim3(256), 0, st, d, pred, d.dh, H, d.catb, d.cat, d.cat, G(8), G(9));
     launch_pdl(k_fc_bwd_x, dim3(dim3(T / 32, kB)), dim3(dim3(32, 8)), 0, st, d, pred, d.dh, H, H, W(8), d.cat, T, d.t, T, d.dt, T, 0);          // only the terr_ip0 columns
-    const int nflat = C2 * W2;
     launch_pdl(k_fc_bwd_w, dim3(dim3(T, (nflat + 255) / 256)), dim3(256), 0, st, d, pred, d.dt, T, d.a2, nflat, nflat, G(6), G(7));
     launch_pdl(k_fc_bwd_x, dim3(dim3((nflat + 31) / 32, kB)), dim3(dim3(32, 8)), 0, st, d, pred, d.dt, T, T, W(6), nflat, nflat, d.a2, nflat, d.da2, nflat, 0);
     launch_pdl(k_conv_bwd_w, dim3(dim3(C1, C2)), dim3(256), 0, st, d, pred, d.da2, C2, K2, d.a1, C1 * W1, C1, W1, G(4), G(5));
@@ -891,7 +1004,7 @@ trl_trainer* trl_trainer_create(trl_handle* h, const double* p) {
     A(talloc(t, &d.xn, (size_t)kB * d.S)); A(talloc(t, &d.a0, (size_t)kB * C0 * W0)); A(talloc(t, &d.a1, (size_t)kB * C1 * W1));
     A(talloc(t, &d.a2, (size_t)kB * C2 * W2)); A(talloc(t, &d.t, (size_t)kB * T)); A(talloc(t, &d.catb, (size_t)kB * d.cat));
     A(talloc(t, &d.h, (size_t)kB * H)); A(talloc(t, &d.hh, (size_t)4 * kB * HH)); A(talloc(t, &d.y, (size_t)kB * d.n_out));
-    A(talloc(t, &d.v0, kB)); A(talloc(t, &d.v1, kB)); A(talloc(t, &d.dy, (size_t)kB * d.n_out)); A(talloc(t, &d.dhh, (size_t)kB * HH));
+    A(talloc(t, &d.v0, kB)); A(talloc(t, &d.v1, kB)); A(talloc(t, &d.dy, (size_t)kB * d.n_out)); A(talloc(t, &d.dhh, (size_t)4 * kB * HH));
     A(talloc(t, &d.dh, (size_t)kB * H)); A(talloc(t, &d.dt, (size_t)kB * T)); A(talloc(t, &d.da2, (size_t)kB * C2 * W2));
     A(talloc(t, &d.da1, (size_t)kB * C1 * W1)); A(talloc(t, &d.da0, (size_t)kB * C0 * W0)); A(talloc(t, &d.mean, d.S)); A(talloc(t, &d.part, (size_t)kSplit * kB * T));
     t->stage_cap = add_cap;
@@ -916,6 +1029,8 @@ trl_trainer* trl_trainer_create(trl_handle* h, const double* p) {
     {
         const char* v1 = std::getenv("TRL_TRAIN_FWD_V1");
         t->batched_fwd = !(v1 && v1[0] == '1');
+        const char* b1 = std::getenv("TRL_TRAIN_BWD_V1");
+        t->fused_bwd = !(b1 && b1[0] == '1');
         const double* bases[2] = {d.theta, d.target};
         for (int k = 0; k < 2 && t->batched_fwd; ++k) {
             NetWeights& W = t->nw[k];
@@ -1085,7 +1200,7 @@ int trl_trainer_train(trl_trainer* t, int iters) {
         cudaGraphDestroy(graph);
         t->launches = before;
     }
-    const int per = 5 + t->d.steps_per_iter * (10 + 5 * (t->batched_fwd ? 3 : 16) + 2 * 26);
+    const int per = 5 + t->d.steps_per_iter * (10 + 5 * (t->batched_fwd ? 3 : 16) + 2 * (t->fused_bwd ? 8 : 26));
     for (int i = 0; i < iters; ++i) {
         TCK(cudaGraphLaunch(t->train_graph, t->work()));
         t->launches += per;

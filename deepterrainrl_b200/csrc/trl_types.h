@@ -21,6 +21,12 @@
 #define TRL_DYN_SHARED(type, name) extern __shared__ type name[]
 #endif
 
+#if defined(__CUDACC__) && !defined(TRL_SIMT_EMU)
+#define TRL_HD __host__ __device__
+#else
+#define TRL_HD
+#endif
+
 namespace trl {
 
 constexpr int kMaxJoints = 21;      // dog / goat: 21 joints, raptor: 19
@@ -33,6 +39,9 @@ constexpr int kMaxActions = 16;
 constexpr int kMaxCtrlSets = 8;
 constexpr int kMaxNetOut = 96;
 constexpr int kWarp = 32;
+constexpr int kMaxGroups = 8;      // env groups a main step launch can be split into (one stream each)
+// envs per group when a main launch is split into n_groups launches: a multiple of 16 envs (= one 128-byte line of an f64 plane)
+TRL_HD inline int group_chunk(int n, int n_groups) { return ((n + 16 * n_groups - 1) / (16 * n_groups)) * 16; }
 constexpr int kMaxLists = 8;       // pending-decision lists (overlap depth + 1 <= 8)
 
 // ---- f64 SoA planes -------------------------------------------------------------------------------------------

@@ -31,6 +31,9 @@ VARIANTS = {
     "smem_xchg": ["-DTRL_SMEM_XCHG=1"],
     "smem_xchg_3cta": ["-DTRL_SMEM_XCHG=1", "-DTRL_STEP_MIN_BLOCKS=3"],
     "noinline_cold": ["-DTRL_NOINLINE_COLD=1"],
+    "regs96": ["-DTRL_STEP_MIN_BLOCKS=5"],       # 5 CTAs (20 warps) per SM at 96 registers, more spills; only makes sense with env groups
+    "regs80": ["-DTRL_STEP_MIN_BLOCKS=6"],
+    "link_smem": ["-DTRL_LINK_SMEM=1"],          # per-lane link constants in shared memory instead of ~28 registers (180 B instead of 216 B spilled)
     "reuse_kin": ["-DTRL_REUSE_KIN=1"],
     "smem_xchg_reuse_kin": ["-DTRL_SMEM_XCHG=1", "-DTRL_REUSE_KIN=1"],
     # decision kernel: register-tiled conv1 / conv2 (the untiled loops are shared-memory-bandwidth bound)
@@ -72,7 +75,7 @@ def build_library(force=False, verbose=False):
     out = library_path()
     csrc = os.path.join(_PKG, "csrc")
     units = [("trl_step.cu", []), ("trl_step_cg.cu", ["-Xptxas", "-dlcm=cg"]), ("trl_host.cu", []), ("trl_train.cu", []),
-             ("trl_comm.cu", []), ("trl_probe.cu", []), ("ref_loader.cpp", [])]
+             ("trl_comm.cu", []), ("trl_probe.cu", []), ("trl_tc_policy.cu", []), ("ref_loader.cpp", [])]
     deps = [os.path.join(csrc, f) for f in os.listdir(csrc)]
     deps.append(os.path.join(_ROOT, "include", "terrainrl_b200.h"))
     if not force and os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in deps):
@@ -115,6 +118,7 @@ EXPORTS = [
     "trl_tuples_dropped", "trl_comm_unique_id", "trl_comm_init", "trl_comm_init_external", "trl_comm_destroy", "trl_comm_info", "trl_comm_set_env_offset",
     "trl_gather_tuples", "trl_gathered_blocks", "trl_gathered_fetch", "trl_gather_last_ms", "trl_trainer_add_gathered", "trl_trainer_broadcast",
     "trl_comm_broadcast_weights", "trl_comm_eval_stats", "trl_trainer_replica_spread", "trl_trainer_set_async",
+    "trl_tc_split", "trl_tc_fc", "trl_tc_last_error", "trl_bench_last_span",
 ]
 
 
@@ -298,9 +302,15 @@ class BatchedScenario:
         return int(self.L.trl_kernel_launches(self.h))
 
     def BenchUpdates(self, k, dt=1.0 / 30.0, flush_l2=True):
-        """k outer updates, device-timed on the library's stream; returns elapsed milliseconds."""
+        """k outer updates, device-timed on the library's stream with one event pair per update (the optional L2 flush sits between the
+        pairs); returns the summed milliseconds.  BenchLastSpan() = first start to last end, flushes included."""
         ms = C.c_double(0)
         self._ck(self.L.trl_bench_updates(self.h, C.c_double(dt), int(k), int(bool(flush_l2)), C.byref(ms)))
+        return ms.value
+
+    def BenchLastSpan(self):
+        ms = C.c_double(0)
+        self._ck(self.L.trl_bench_last_span(self.h, C.byref(ms)))
         return ms.value
 
     def UpdateTimedDetail(self, dt=1.0 / 30.0, num_update_steps=20):

@@ -112,9 +112,12 @@ int trl_snapshot_wait(trl_handle* h, double* pose, double* vel, int64_t* cycles,
 int trl_device_tuple_block(trl_handle* h, void** rows_f64, void** flags_u32, void** env_i32, void** count_i32,
                            int* cap, int* width);
 
-/* measurement helpers: K outer updates timed with CUDA events on the handle's stream (optional L2 flush between
- * updates); one update with an event pair around every kernel launch (per-kernel device time for the roofline). */
+/* measurement helpers: K outer updates timed with CUDA events on the handle's stream, one event pair per update, *ms_total = the sum
+ * (flush_l2: a 256 MiB memset between the pairs evicts L2 before every update; it is a measurement device and is not timed --
+ * trl_bench_last_span returns the span from the first update's start to the last update's end with the flushes in it);
+ * one update with an event pair around every kernel launch (per-kernel device time for the roofline). */
 int trl_bench_updates(trl_handle* h, double dt, int k, int flush_l2, double* ms_total);
+int trl_bench_last_span(trl_handle* h, double* ms);
 int trl_update_timed(trl_handle* h, double dt, double* step_ms, int* step_launches, double* decide_ms, int* decide_launches);
 int trl_update_timed_detail(trl_handle* h, double dt, double* per_step_ms, double* per_decide_ms);
 /* one update in trl_update's own (overlapped) schedule with an event pair around every launch: out[4k..4k+3] = {kind (0 terrain, 1 step,
@@ -242,6 +245,16 @@ int trl_comm_eval_stats(trl_handle* h, int64_t* cycles, int64_t* episodes, doubl
 int trl_trainer_replica_spread(trl_trainer* t, double* max_abs_diff);
 
 const char* trl_last_error(void);
+
+/* ---- EXPERIMENT (not on the decision path, which stays f64): the policy's wide inner product terr_ip0 (5984 -> 64; cNeuralNet::Eval,
+ * learning/NeuralNet.cpp:352-375) as a TMA-fed tcgen05.mma GEMM over a batch of decisions in split precision (csrc/trl_tc_policy.cu);
+ * tools/tc_policy_probe.py measures what the narrow arithmetic does to real decisions.  kind: 0 = bf16 parts, 1 = tf32 parts.
+ * trl_tc_split: x[rows][K] f64 -> planes[parts][rows][K]; trl_tc_fc: out[M][64] (FP32) = sum over the part pairs in `pairs` (bit 3 i + j)
+ * of A_i[M][K] B_j[64][K]^T; all pointers are device pointers, stream is a cudaStream_t, *err_flag is set if a barrier wait gave up. */
+int trl_tc_split(const double* x, long long rows, int K, int kind, int parts, void* planes, void* stream);
+int trl_tc_fc(const void* a_planes, const void* b_planes, int M, int K, int kind, int parts, int pairs, int ksplit, float* out, int* err_flag,
+              void* stream);
+const char* trl_tc_last_error(void);
 
 #ifdef __cplusplus
 }

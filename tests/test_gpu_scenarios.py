@@ -182,7 +182,7 @@ def test_overlap_matches_serial(assets, monkeypatch):
     l0s, l0o = ser.KernelLaunches(), ovl.KernelLaunches()
     for _ in range(45):
         ser.Update(1.0 / 30.0); ovl.Update(1.0 / 30.0)
-    assert ser.KernelLaunches() - l0s == 45 * 62 and ovl.KernelLaunches() - l0o == 45 * 80   # terrain + 21 steps + 20 x (conv + FC) decision launches (+ 19 catch-ups)
+    assert ser.KernelLaunches() - l0s == 45 * 62 and ovl.KernelLaunches() - l0o == 45 * 100   # terrain + 21 steps + 20 x (conv + FC) decision launches; overlapped: 2 env groups x 20 step launches + S_end + 40 decision launches + 19 catch-ups
     # The catch-up launches are a second instantiation of the step kernel's source (csrc/trl_step_cg.cu: L1-bypassing loads, the
     # loop over the env-steps a pending env trails by): same operations in the same order, but the compiler's multiply-add
     # contraction may differ, so the two schedules agree to rounding amplified over 45 updates (observed 2.5e-12), not bit for bit.
@@ -200,6 +200,39 @@ def test_overlap_matches_serial(assets, monkeypatch):
     np.testing.assert_array_equal(ea[ka], eb[kb])
     np.testing.assert_array_equal(fa[ka], fb[kb])
     np.testing.assert_allclose(ra[ka], rb[kb], rtol=0, atol=1e-7)
+
+
+def test_env_groups_match_monolithic_launch(assets, monkeypatch):
+    """TRL_GROUPS=G: every main step launch is split into G launches over contiguous env ranges on G streams that only meet at the
+    decision / catch-up launches.  Same kernels, same per-env arithmetic: states, counters and tuples are bit-identical."""
+    import deepterrainrl_b200 as trl
+    pack = os.path.join(assets, "dog_slopes_mixed.trlpack")
+    n = 1000
+    scs = []
+    for G in ("1", "3", "8"):
+        monkeypatch.setenv("TRL_GROUPS", G)
+        scs.append(trl.ScenarioExpMACE(pack, n, rng_seed=7))
+    monkeypatch.delenv("TRL_GROUPS")
+    for sc in scs:
+        sc.EnableExplore(True, 0.2, 0.025, 0.01)
+    l0 = [sc.KernelLaunches() for sc in scs]
+    for _ in range(45):
+        for sc in scs:
+            sc.Update(1.0 / 30.0)
+    assert [sc.KernelLaunches() - a for sc, a in zip(scs, l0)] == [45 * 80, 45 * 120, 45 * 220]
+    ref = scs[0]
+    ra, fa, ea = ref.GetTuples(f64=True)
+    ka = np.lexsort(np.column_stack([ea, fa, ra]).T[::-1])
+    assert ra.shape[0] > n
+    for sc in scs[1:]:
+        for a, b in zip(ref.GetStateAll(), sc.GetStateAll()):
+            np.testing.assert_array_equal(a, b)
+        assert ref._stats() == sc._stats()
+        rb, fb, eb = sc.GetTuples(f64=True)
+        kb = np.lexsort(np.column_stack([eb, fb, rb]).T[::-1])
+        np.testing.assert_array_equal(ea[ka], eb[kb])
+        np.testing.assert_array_equal(fa[ka], fb[kb])
+        np.testing.assert_array_equal(ra[ka], rb[kb])
 
 
 def test_two_scenes_interleaved(assets):

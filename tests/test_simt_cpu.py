@@ -219,7 +219,53 @@ def test_serial_schedule_single_env_reset_and_two_scenes(assets, monkeypatch):
             sc.close()
 
 
-def test_trainer_kernels_vs_oracle(assets):
+def test_env_groups_match_the_monolithic_launch(assets, monkeypatch):
+    """TRL_GROUPS=G splits every main step launch into G launches over contiguous env ranges on G streams (they only meet at the
+    decision / catch-up launches): states, counters and tuples are bit-identical to the one-launch schedule; a group count that
+    would leave a group empty is reduced."""
+    import deepterrainrl_b200 as trl
+    dog = os.path.join(assets, "dog_slopes_mixed.trlpack")
+    with simt_library():
+        n = 20           # G = 2 -> chunk 16: groups [0,16) [16,20)
+        scs = []
+        for G in ("1", "2"):
+            monkeypatch.setenv("TRL_GROUPS", G)
+            scs.append(trl.ScenarioExpMACE(dog, n, rng_seed=7))
+        monkeypatch.setenv("TRL_GROUPS", "8")
+        tiny = trl.ScenarioExpMACE(dog, 5, rng_seed=7)     # 8 groups of >= 16 envs cannot be filled from 5 envs
+        monkeypatch.delenv("TRL_GROUPS")
+        lt = tiny.KernelLaunches()
+        tiny.Update(1.0 / 30.0)
+        assert tiny.KernelLaunches() - lt == 80
+        tiny.close()
+        for sc in scs:
+            sc.EnableExplore(True, 0.2, 0.025, 0.01)
+        l0 = [sc.KernelLaunches() for sc in scs]
+        nu = 0
+        while nu < 40 and (nu < 12 or scs[0].GetNumTuples() < n // 2):     # until the first gait cycles have ended (tuples exist)
+            for sc in scs:
+                sc.Update(1.0 / 30.0)
+            nu += 1
+        got = [sc.KernelLaunches() - a for sc, a in zip(scs, l0)]
+        assert got == [nu * 80, nu * 100], got
+        ref = scs[0]
+        ra, fa, ea = ref.GetTuples(f64=True)
+        ka = np.lexsort(np.column_stack([ea, fa, ra]).T[::-1])
+        assert ra.shape[0] >= n // 2
+        for sc in scs[1:]:
+            for a, b in zip(ref.GetStateAll(), sc.GetStateAll()):
+                np.testing.assert_array_equal(a, b)
+            assert ref._stats() == sc._stats()
+            rb, fb, eb = sc.GetTuples(f64=True)
+            kb = np.lexsort(np.column_stack([eb, fb, rb]).T[::-1])
+            np.testing.assert_array_equal(ea[ka], eb[kb])
+            np.testing.assert_array_equal(fa[ka], fb[kb])
+            np.testing.assert_array_equal(ra[ka], rb[kb])
+        for sc in scs:
+            sc.close()
+
+
+def test_trainer_kernels_vs_oracle(assets, monkeypatch):
     from pyoracle import OracleTrainer
     from test_gpu_trainer import _synthetic_tuples
     import deepterrainrl_b200 as trl
@@ -228,12 +274,22 @@ def test_trainer_kernels_vs_oracle(assets):
     with simt_library():
         sc = trl.ScenarioExpMACE(pack, 4)
         g = trl.MACETrainer(sc, replay_mem_size=160, **kw)
+        # the same trainer with one launch per backward kernel (26 per pass) instead of the 8 multi-body launches: bit-identical weights
+        monkeypatch.setenv("TRL_TRAIN_BWD_V1", "1")
+        sc1 = trl.ScenarioExpMACE(pack, 4)
+        g1 = trl.MACETrainer(sc1, replay_mem_size=160, **kw)
+        monkeypatch.delenv("TRL_TRAIN_BWD_V1")
         o = OracleTrainer(pack, replay_cap=160, **kw)
         rows, flags = _synthetic_tuples(128, g.S, g.A, o.get("in_off"), o.get("in_scale"), 3)
         g.AddTuples(rows, flags)
+        g1.AddTuples(rows, flags)
         o.add_tuples(rows, flags)
         for it in range(2):   # the second iteration includes an actor step
+            l0, l1 = g.KernelLaunches(), g1.KernelLaunches()
             g.Train(1)
+            g1.Train(1)
+            assert (g.KernelLaunches() - l0, g1.KernelLaunches() - l1) == (46, 82)
+            np.testing.assert_array_equal(g.get("theta"), g1.get("theta"))
             o.train()
             cg, co = g.counters(), o.counters()
             for k in ("iter", "actor_iter", "stage", "num", "head", "total", "critic", "actor", "actor_batch"):
@@ -247,6 +303,7 @@ def test_trainer_kernels_vs_oracle(assets):
         with pytest.raises(RuntimeError, match="has been destroyed"):
             g.Train(1)
         g.close()
+        g1.close(); sc1.close()
 
 
 def test_trainer_kernels_have_no_schedule_dependent_results(assets):
@@ -330,6 +387,7 @@ VARIANTS = [
     ["-DTRL_SMEM_XCHG=1", "-DTRL_REUSE_KIN=1"],
     ["-DTRL_DECIDE_TILE=1", "-DTRL_CONV_TILE=2"],
     ["-DTRL_DECIDE_TILE=1", "-DTRL_CONV_TILE=4"],
+    ["-DTRL_LINK_SMEM=1"],
 ]
 
 

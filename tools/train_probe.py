@@ -33,9 +33,11 @@ st.exp.Sync()
 dr = time.perf_counter() - t1
 st.exp.ResetTupleBuffer()
 # trainer alone
+lt0 = st.trainer.KernelLaunches()
 t2 = time.perf_counter()
 st.trainer.Train(updates * k)
 st.exp.Sync()
+lt1 = st.trainer.KernelLaunches()
 dtr = time.perf_counter() - t2
 print(json.dumps({"envs": n, "updates": updates, "iters_per_update": k,
                   "train_loop_env_steps_per_s": n * 20 * updates / dt, "rollout_only_env_steps_per_s": n * 20 * updates / dr,
@@ -43,4 +45,4 @@ print(json.dumps({"envs": n, "updates": updates, "iters_per_update": k,
                   "trainer_ms_per_iter": 1e3 * dtr / (updates * k), "trainer_iters": c1["iter"] - c0["iter"],
                   "actor_iters": c1["actor_iter"] - c0["actor_iter"], "tuples_per_update": (c1["total"] - c0["total"]) / updates,
                   "critic_loss": c1["critic_loss"], "actor_loss": c1["actor_loss"],
-                  "trainer_kernel_launches_per_iter": 142}))
+                  "trainer_kernel_launches_per_iter": (lt1 - lt0) / (updates * k)}))
