@@ -588,7 +588,7 @@ void launch_decide2(const Buffers& B, const NetWeights& W, const ExpSettings* ex
 // FC stage's TMA descriptor `maps.a` covers
 void launch_forward_train(const NetWeights& W, const FcMaps& maps, const FwdTrain& f, double* act2, cudaStream_t st) {
     TRL_LAUNCH_CLUSTER(kClusterSize, trl_fwd_conv_train_kernel, kClusterSize * f.rows, kDecideThreads, (size_t)kConvSmemDoubles * 8, st, W, f, act2);
-    TRL_LAUNCH_CLUSTER(kFcCluster, trl_fwd_fc_train_kernel, kFcCluster, kFcThreads, decide_fc_smem_bytes(), st, W, maps, f);
+    TRL_LAUNCH_CLUSTER(kFcCluster, trl_fwd_fc_train_kernel, kFcCluster * ((f.rows + kFcRows - 1) / kFcRows), kFcThreads, decide_fc_smem_bytes(), st, W, maps, f);   // one cluster per chunk of 32 rows
 }
 
 }  // namespace trl

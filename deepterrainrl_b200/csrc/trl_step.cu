@@ -218,13 +218,23 @@ struct CounterRng {
 };
 
 // ------------------------------------------------------------------------------------------------ global accessors
+#ifndef TRL_FIELD_SMEM
+#define TRL_FIELD_SMEM 0    // 1: the step kernel stages every per-env field of its env in shared memory (one batch of independent loads at
+#endif                      //    the start, one batch of stores at the end) instead of ~50 dependent L2 round trips spread over the launch
 struct Lane {
     double* sm;          // unused by the warp kernel (kept for the decision kernel's scalar helpers)
     int env, n;
     double* D;
     int* I;
+#if TRL_FIELD_SMEM
+    double* sd;          // staged copy of the env's f64 fields [D_NUM_FIELDS] (null: read / write the planes directly)
+    int* si;             // staged copy of the env's i32 fields [I_NUM_FIELDS]
+    __device__ __forceinline__ double& d(int f) { return sd ? sd[f] : D[(size_t)f * n + env]; }
+    __device__ __forceinline__ int& i(int f) { return si ? si[f] : I[(size_t)f * n + env]; }
+#else
     __device__ __forceinline__ double& d(int f) { return D[(size_t)f * n + env]; }
     __device__ __forceinline__ int& i(int f) { return I[(size_t)f * n + env]; }
+#endif
 };
 
 __device__ __forceinline__ bool has_fallen(Lane& L, double root_theta) {
@@ -380,7 +390,8 @@ __device__ void store_rng(Lane& L, const CounterRng& r) {
 // ================================================================================================ warp context
 // Per-lane constants of link `lane` and the env state held in registers.
 #ifndef TRL_LINK_SMEM
-#define TRL_LINK_SMEM 0     // 1: the per-lane link constants live in shared memory (one table per CTA) instead of ~28 registers per thread
+#define TRL_LINK_SMEM 1     // 1: the per-lane link constants live in shared memory (one table per CTA) instead of ~28 registers per thread
+                            //    (the register build spills them and reloads them inside the ABA rounds; + 1.5 % measured, profiles/step_groups_r02_ab.txt)
 #endif
 #if TRL_LINK_SMEM
 enum { LF_AX, LF_AY, LF_MASS, LF_BAX, LF_BAY, LF_IZZ, LF_LIM_LO, LF_LIM_HI, LF_NUM };
@@ -1319,6 +1330,11 @@ trl_step_kernel(Buffers B, double h, int flags, int lists) {
         tb[4 * kMaxJoints + t] = m.half_x[t]; tb[5 * kMaxJoints + t] = m.half_y[t];
     }
     TRL_LINK_TABLES_DECL
+#if TRL_FIELD_SMEM
+    static_assert(I_NUM_FIELDS <= kWarp, "one lane per i32 field");
+    __shared__ double s_fd[kWarpsPerBlock * D_NUM_FIELDS];
+    __shared__ int s_fi[kWarpsPerBlock * I_NUM_FIELDS];
+#endif
     stage_link_tables(link_tabs);
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1350,10 +1366,25 @@ trl_step_kernel(Buffers B, double h, int flags, int lists) {
         return;
     }
     Lane L{nullptr, env, B.n, B.d, B.i};
+    int tag = 0;
     if (flags & kStepSkipPending) {
         // overlapped main launch: envs waiting for a decision or being caught up are not touched
-        const int tag = L.i(I_PENDING);
+        tag = L.i(I_PENDING);
         if (tag != 0 && tag != 1 + app) return;
+    }
+#if TRL_FIELD_SMEM
+    // every field of this env in one batch of independent loads (the planes are B.n apart: a field costs an L2 round trip wherever it
+    // is first touched); the env is private to this warp for the whole launch, so the copy is written back in one batch at the end
+    {
+        double* sd = s_fd + warp * D_NUM_FIELDS;
+        int* si = s_fi + warp * I_NUM_FIELDS;
+        for (int f = lane; f < D_NUM_FIELDS; f += kWarp) sd[f] = L.D[(size_t)f * L.n + env];
+        if (lane < I_NUM_FIELDS) si[lane] = L.I[(size_t)lane * L.n + env];
+        __syncwarp();
+        L.sd = sd; L.si = si;
+    }
+#endif
+    if (flags & kStepSkipPending) {
         if (tag == 1 + app && lane == 0) L.i(I_PENDING) = 0;   // stale tag of lag + 1 steps ago (already caught up)
     } else if (!(flags & kStepCatchUp) && (flags & 1) && lane == 0) {
         L.i(I_PENDING) = 0;    // serial schedule / end of the update: every decision has been served before this launch
@@ -1522,6 +1553,11 @@ trl_step_kernel(Buffers B, double h, int flags, int lists) {
     }
     }   // rep
     store_env(L, lc, e, lane);
+#if TRL_FIELD_SMEM
+    __syncwarp();
+    for (int f = lane; f < D_NUM_FIELDS; f += kWarp) L.D[(size_t)f * L.n + env] = L.sd[f];
+    if (lane < I_NUM_FIELDS) L.I[(size_t)lane * L.n + env] = L.si[lane];
+#endif
     if (flags & kStepCatchUp) catchup_leave(B, prev);
 }
 

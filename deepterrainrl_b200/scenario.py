@@ -33,7 +33,8 @@ VARIANTS = {
     "noinline_cold": ["-DTRL_NOINLINE_COLD=1"],
     "regs96": ["-DTRL_STEP_MIN_BLOCKS=5"],       # 5 CTAs (20 warps) per SM at 96 registers, more spills; only makes sense with env groups
     "regs80": ["-DTRL_STEP_MIN_BLOCKS=6"],
-    "link_smem": ["-DTRL_LINK_SMEM=1"],          # per-lane link constants in shared memory instead of ~28 registers (180 B instead of 216 B spilled)
+    "field_smem": ["-DTRL_FIELD_SMEM=1"],        # every per-env field staged in shared memory for the launch (one load batch, one store batch): + 0.4 %, not adopted
+    "link_regs": ["-DTRL_LINK_SMEM=0"],          # the round-1 layout: per-lane link constants in registers (the default keeps them in shared memory)          # per-lane link constants in shared memory instead of ~28 registers (180 B instead of 216 B spilled)
     "reuse_kin": ["-DTRL_REUSE_KIN=1"],
     "smem_xchg_reuse_kin": ["-DTRL_SMEM_XCHG=1", "-DTRL_REUSE_KIN=1"],
     # decision kernel: register-tiled conv1 / conv2 (the untiled loops are shared-memory-bandwidth bound)

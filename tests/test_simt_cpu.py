@@ -288,7 +288,7 @@ def test_trainer_kernels_vs_oracle(assets, monkeypatch):
             l0, l1 = g.KernelLaunches(), g1.KernelLaunches()
             g.Train(1)
             g1.Train(1)
-            assert (g.KernelLaunches() - l0, g1.KernelLaunches() - l1) == (46, 82)
+            assert (g.KernelLaunches() - l0, g1.KernelLaunches() - l1) == (43, 79)
             np.testing.assert_array_equal(g.get("theta"), g1.get("theta"))
             o.train()
             cg, co = g.counters(), o.counters()
@@ -387,7 +387,8 @@ VARIANTS = [
     ["-DTRL_SMEM_XCHG=1", "-DTRL_REUSE_KIN=1"],
     ["-DTRL_DECIDE_TILE=1", "-DTRL_CONV_TILE=2"],
     ["-DTRL_DECIDE_TILE=1", "-DTRL_CONV_TILE=4"],
-    ["-DTRL_LINK_SMEM=1"],
+    ["-DTRL_LINK_SMEM=0"],
+    ["-DTRL_FIELD_SMEM=1"],
 ]
 
 
