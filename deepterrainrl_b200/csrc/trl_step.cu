@@ -44,8 +44,25 @@ namespace TRL_IMPL_NS {
 using namespace trl;
 
 __constant__ ModelConst c_model;
+// Lane-indexed tables (one entry per link / corner) are read from a global-memory mirror of the same struct: the constant cache
+// serves one address per access, so `c_model.kp[lane]` costs one replay per distinct lane, while the mirror is one coalesced,
+// L1-cached read-only load.  Warp-uniform reads stay in constant memory.
+#ifndef TRL_TABLE_MIRROR
+#define TRL_TABLE_MIRROR 1      // + 4.5 % on a B200 (profiles/step_groups_r02_ab.txt); 0 = the round-1 reads from constant memory
+#endif
+#if TRL_TABLE_MIRROR
+__device__ ModelConst g_model;
+#define LT(field, idx) __ldg(&g_model.field[(idx)])
+#define LT2(field, i, j) __ldg(&g_model.field[(i)][(j)])
+#else
+#define LT(field, idx) c_model.field[(idx)]
+#define LT2(field, i, j) c_model.field[(i)][(j)]
+#endif
 
-constexpr int kWarpsPerBlock = 4;
+#ifndef TRL_WARPS_PER_BLOCK
+#define TRL_WARPS_PER_BLOCK 4
+#endif
+constexpr int kWarpsPerBlock = TRL_WARPS_PER_BLOCK;   // one env per warp; 16 resident warps per SM at 128 registers whatever the CTA size
 constexpr int kBlockThreads = kWarpsPerBlock * kWarp;
 constexpr unsigned kFull = 0xffffffffu;
 #ifndef TRL_STEP_MIN_BLOCKS
@@ -450,23 +467,23 @@ __device__ __forceinline__ LinkVals link_values(int lane) {
     LinkVals c;
     c.act = lane < m.nj;
     int j = c.act ? lane : 0;
-    c.parent = (c.act && j > 0) ? m.parent[j] : 0;
-    c.depth = c.act ? m.depth[j] : -1;
-    c.acc_round = c.act ? m.acc_round[j] : -1;
-    c.acc_src = c.act ? m.acc_src[j] : ~0ull;
-    c.anc1 = c.act ? m.anc_pow[j][0] : -1; c.anc2 = c.act ? m.anc_pow[j][1] : -1;
-    c.anc4 = c.act ? m.anc_pow[j][2] : -1; c.anc8 = c.act ? m.anc_pow[j][3] : -1;
+    c.parent = (c.act && j > 0) ? LT(parent, j) : 0;
+    c.depth = c.act ? LT(depth, j) : -1;
+    c.acc_round = c.act ? LT(acc_round, j) : -1;
+    c.acc_src = c.act ? LT(acc_src, j) : ~0ull;
+    c.anc1 = c.act ? LT2(anc_pow, j, 0) : -1; c.anc2 = c.act ? LT2(anc_pow, j, 1) : -1;
+    c.anc4 = c.act ? LT2(anc_pow, j, 2) : -1; c.anc8 = c.act ? LT2(anc_pow, j, 3) : -1;
     if (c.anc1 < 0) c.anc1 = kZeroLane;
     if (c.anc2 < 0) c.anc2 = kZeroLane;
     if (c.anc4 < 0) c.anc4 = kZeroLane;
     if (c.anc8 < 0) c.anc8 = kZeroLane;
-    c.ax = m.attach_x[j]; c.ay = m.attach_y[j];
-    c.mass = c.act ? m.mass[j] : 0.0;
-    c.bax = m.body_ax[j]; c.bay = m.body_ay[j];
-    c.izz_c = c.act ? m.izz_c[j] : 0.0;
-    const int has_lim = c.act ? m.has_limit[j] : 0;
-    c.lim_lo = has_lim ? m.lim_lo[j] : -INFINITY;    // no limit: never violated, so the limit force needs no branch
-    c.lim_hi = has_lim ? m.lim_hi[j] : INFINITY;
+    c.ax = LT(attach_x, j); c.ay = LT(attach_y, j);
+    c.mass = c.act ? LT(mass, j) : 0.0;
+    c.bax = LT(body_ax, j); c.bay = LT(body_ay, j);
+    c.izz_c = c.act ? LT(izz_c, j) : 0.0;
+    const int has_lim = c.act ? LT(has_limit, j) : 0;
+    c.lim_lo = has_lim ? LT(lim_lo, j) : -INFINITY;    // no limit: never violated, so the limit force needs no branch
+    c.lim_hi = has_lim ? LT(lim_hi, j) : INFINITY;
     return c;
 }
 // TRL_LINK_SMEM: the first warp of the CTA fills the table (the caller's __syncthreads() publishes it)
@@ -705,18 +722,18 @@ __device__ double controller_torque(Lane& L, const LinkC& lc, const EnvRegs& e, 
     double tau0 = 0.0, rhs_link = 0.0, kd_link = 0.0, kd_eff = 0.0;
     if (lc.act && lane > 0) {
         double theta = e.q;
-        if (m.world_pd[lane]) {
+        if (LT(world_pd, lane)) {
             // child body's world rotation, wrapped (cPDController::CalcTheta, sim/PDController.cpp:181-198)
-            double c = k.cw * m.body_cos[lane] - k.sw * m.body_sin[lane];
-            double s = k.sw * m.body_cos[lane] + k.cw * m.body_sin[lane];
+            double c = k.cw * LT(body_cos, lane) - k.sw * LT(body_sin, lane);
+            double s = k.sw * LT(body_cos, lane) + k.cw * LT(body_sin, lane);
             double a = acos(fmin(1.0, fmax(-1.0, c)));
             theta = (s >= 0) ? a : -a;
         }
         const bool pd_on = !(active_vf && lane == st_hip);
-        kd_link = m.kd[lane];
+        kd_link = LT(kd, lane);
         kd_eff = pd_on ? kd_link : 0.0;
-        double perr = L.d(D_PD_TARGET + lane) - theta, verr = m.target_vel[lane] - e.qd;
-        tau0 = pd_on ? (m.kp[lane] * (perr - h * e.qd) + kd_link * verr) : 0.0;
+        double perr = L.d(D_PD_TARGET + lane) - theta, verr = LT(target_vel, lane) - e.qd;
+        tau0 = pd_on ? (LT(kp, lane) * (perr - h * e.qd) + kd_link * verr) : 0.0;
         rhs_link = tau0 - Cj;
     }
     // dof-lane view: lane d holds row d of (M + h Kd) and rhs_d
@@ -810,9 +827,9 @@ __device__ double controller_torque(Lane& L, const LinkC& lc, const EnvRegs& e, 
     // foot bottom-centre positions (GetEndEffectorContactPos), relative to O
     double ex[2], ey[2];
     {
-        double bc = k.cw * m.body_cos[lc.act ? lane : 0] - k.sw * m.body_sin[lc.act ? lane : 0];
-        double bs = k.sw * m.body_cos[lc.act ? lane : 0] + k.cw * m.body_sin[lc.act ? lane : 0];
-        double ly = -m.half_y[lc.act ? lane : 0];
+        double bc = k.cw * LT(body_cos, lc.act ? lane : 0) - k.sw * LT(body_sin, lc.act ? lane : 0);
+        double bs = k.sw * LT(body_cos, lc.act ? lane : 0) + k.cw * LT(body_sin, lc.act ? lane : 0);
+        double ly = -LT(half_y, lc.act ? lane : 0);
         double px = k.cx - bs * ly, py = k.cy + bc * ly;
         ex[0] = shf(px, eff0); ey[0] = shf(py, eff0);
         ex[1] = shf(px, eff1); ey[1] = shf(py, eff1);
@@ -916,7 +933,7 @@ __device__ double controller_torque(Lane& L, const LinkC& lc, const EnvRegs& e, 
 
     // ---- cJoint::ApplyTorque clamp (sim/Joint.cpp:171-201,257-264)
     if (lc.act && lane > 0) {
-        double lim = m.torque_lim[lane];
+        double lim = LT(torque_lim, lane);
         if (fabs(tau) > lim) tau *= lim / fabs(tau);
     } else tau = 0.0;
     (void)nj;
@@ -1028,7 +1045,7 @@ __device__ int physics_substep(const LinkC& lc, EnvRegs& e, const GroundView& g,
             }
             const unsigned tmask = __ballot_sync(kFull, touching);
             unsigned fmask = __ballot_sync(kFull, add[3] != 0.0 || add[5] != 0.0);
-            const int cb = lc.act ? m.corner_base[lane] : -1;
+            const int cb = lc.act ? LT(corner_base, lane) : -1;
             const bool mine = cb >= base && cb < base + kWarp;
             while (fmask) {
                 const int src = __ffs(fmask) - 1;
@@ -1076,7 +1093,7 @@ __device__ int physics_substep(const LinkC& lc, EnvRegs& e, const GroundView& g,
         // hand the (few) force-producing corners to the lanes that own their bodies, in corner order (deterministic)
         const unsigned tmask = __ballot_sync(kFull, touching);
         unsigned fmask = __ballot_sync(kFull, add[3] != 0.0 || add[5] != 0.0);
-        const int cb = lc.act ? m.corner_base[lane] : -1;
+        const int cb = lc.act ? LT(corner_base, lane) : -1;
         const bool mine = cb >= base && cb < base + kWarp;
 #if TRL_CONTACT_SMEM
         if (fmask) {
@@ -1322,12 +1339,12 @@ trl_step_kernel(Buffers B, double h, int flags, int lists) {
 #endif
     const ModelConst& m = c_model;
     for (int t = threadIdx.x; t < m.n_corners; t += kBlockThreads) {
-        s_clx[t] = m.corner_lx[t]; s_cly[t] = m.corner_ly[t]; s_cbody[t] = m.corner_body[t];
+        s_clx[t] = LT(corner_lx, t); s_cly[t] = LT(corner_ly, t); s_cbody[t] = LT(corner_body, t);
     }
     for (int t = threadIdx.x; t < m.nj; t += kBlockThreads) {
         double* tb = s_clx + 4 * kMaxJoints;
-        tb[t] = m.body_ax[t]; tb[kMaxJoints + t] = m.body_ay[t]; tb[2 * kMaxJoints + t] = m.body_cos[t]; tb[3 * kMaxJoints + t] = m.body_sin[t];
-        tb[4 * kMaxJoints + t] = m.half_x[t]; tb[5 * kMaxJoints + t] = m.half_y[t];
+        tb[t] = LT(body_ax, t); tb[kMaxJoints + t] = LT(body_ay, t); tb[2 * kMaxJoints + t] = LT(body_cos, t); tb[3 * kMaxJoints + t] = LT(body_sin, t);
+        tb[4 * kMaxJoints + t] = LT(half_x, t); tb[5 * kMaxJoints + t] = LT(half_y, t);
     }
     TRL_LINK_TABLES_DECL
 #if TRL_FIELD_SMEM
@@ -1648,7 +1665,13 @@ __global__ void trl_stats_kernel(Buffers B, double* out) {
 void launch_stats(const Buffers& B, double* out, cudaStream_t st) { TRL_LAUNCH(trl_stats_kernel, 1, 1024, 0, st, B, out); }
 
 // ---- host-side launch helpers (called from trl_host.cu)
-cudaError_t upload_model(const ModelConst& mc) { return cudaMemcpyToSymbol(c_model, &mc, sizeof(ModelConst)); }
+cudaError_t upload_model(const ModelConst& mc) {
+    cudaError_t e = cudaMemcpyToSymbol(c_model, &mc, sizeof(ModelConst));
+#if TRL_TABLE_MIRROR
+    if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_model, &mc, sizeof(ModelConst));
+#endif
+    return e;
+}
 size_t step_smem_bytes() { return 0; }
 cudaError_t configure_step_kernels() {
 #if TRL_SMEM_ALIGNED && !defined(TRL_SIMT_EMU)

@@ -294,17 +294,22 @@ struct GroundView {
     int flip;
     uint32_t rng_state;
 
+    // n[] / min_x[] are only ever indexed with constants (through these selects): a run-time index would force the whole view into
+    // local memory, and every height sample of the contact pass would pay two local-memory loads for it
+    __device__ __forceinline__ int nn(int id) const { return id ? n[1] : n[0]; }
+    __device__ __forceinline__ double mnx(int id) const { return id ? min_x[1] : min_x[0]; }
+
     __device__ __forceinline__ int seg_id(int s) const { return flip ? (s == 0 ? 1 : 0) : s; }
     __device__ __forceinline__ double seg_max_x(int id) const {
-        return n[id] == 0 ? -INFINITY : __dadd_rn(min_x[id], __dmul_rn((double)(n[id] - 1), TRL_VERT_SPACING_D));
+        return nn(id) == 0 ? -INFINITY : __dadd_rn(mnx(id), __dmul_rn((double)(nn(id) - 1), TRL_VERT_SPACING_D));
     }
-    __device__ __forceinline__ double seg_min_x(int id) const { return n[id] == 0 ? INFINITY : min_x[id]; }
+    __device__ __forceinline__ double seg_min_x(int id) const { return nn(id) == 0 ? INFINITY : mnx(id); }
 
     // tSegment::SampleHeight (clamped grid coordinate, lerp of the two neighbouring float vertices)
     __device__ double sample_seg(int id, double x, double* slope) const {
         const float* d = data + id * kTerrainCap;
-        int w = n[id] < kTerrainCap ? n[id] : kTerrainCap;
-        double coord = (x - min_x[id]) / TRL_VERT_SPACING_D;
+        int w = nn(id) < kTerrainCap ? nn(id) : kTerrainCap;
+        double coord = (x - mnx(id)) / TRL_VERT_SPACING_D;
         coord = fmin(fmax(coord, 0.0), (double)(w - 1));
         int i = (int)coord;
         int j = min(w - 1, i + 1);
@@ -327,8 +332,8 @@ struct GroundView {
         const int ms = seg_id(0);
         const int id = (x >= seg_max_x(ms)) ? seg_id(1) : ms;
         const float* d = data + id * kTerrainCap;
-        const int w = n[id] < kTerrainCap ? n[id] : kTerrainCap;
-        double coord = (x - min_x[id]) * inv_sp;
+        const int w = nn(id) < kTerrainCap ? nn(id) : kTerrainCap;
+        double coord = (x - mnx(id)) * inv_sp;
         coord = fmin(fmax(coord, 0.0), (double)(w - 1));
         const int i = (int)coord;
         const int j = min(w - 1, i + 1);
@@ -344,21 +349,21 @@ struct GroundView {
     __device__ bool vertex_slot(double xmin, double xmax, int slot, double* xv, double* hv, double* hp, double* hn) const {
         const double sp = TRL_VERT_SPACING_D;
         const int ia = seg_id(0), ib = seg_id(1);
-        const int wa = n[ia] < kTerrainCap ? n[ia] : kTerrainCap, wb = n[ib] < kTerrainCap ? n[ib] : kTerrainCap;
+        const int wa = nn(ia) < kTerrainCap ? nn(ia) : kTerrainCap, wb = nn(ib) < kTerrainCap ? nn(ib) : kTerrainCap;
         int a0 = 0, a1 = -1, b0 = 0, b1 = -1;
         if (wa > 0) {
-            a0 = max((int)ceil((xmin - min_x[ia]) / sp - 1e-9), 0);
-            a1 = min((int)floor((xmax - min_x[ia]) / sp + 1e-9), wa - 2);        // x < seam: the last vertex belongs to the max segment
+            a0 = max((int)ceil((xmin - mnx(ia)) / sp - 1e-9), 0);
+            a1 = min((int)floor((xmax - mnx(ia)) / sp + 1e-9), wa - 2);        // x < seam: the last vertex belongs to the max segment
         }
         if (wb > 0) {
-            b0 = max((int)ceil((xmin - min_x[ib]) / sp - 1e-9), 0);
-            b1 = min((int)floor((xmax - min_x[ib]) / sp + 1e-9), wb - 1);
+            b0 = max((int)ceil((xmin - mnx(ib)) / sp - 1e-9), 0);
+            b1 = min((int)floor((xmax - mnx(ib)) / sp + 1e-9), wb - 1);
         }
         const int na = max(a1 - a0 + 1, 0);
         if (slot < na) {
             const int kk = a0 + slot;
             const float* d = data + ia * kTerrainCap;
-            *xv = min_x[ia] + kk * sp; *hv = (double)d[kk];
+            *xv = mnx(ia) + kk * sp; *hv = (double)d[kk];
             *hp = kk > 0 ? (double)d[kk - 1] : (double)d[kk];
             *hn = (double)d[kk + 1];
             return true;
@@ -366,7 +371,7 @@ struct GroundView {
         const int kk = b0 + (slot - na);
         if (kk > b1) return false;
         const float* d = data + ib * kTerrainCap;
-        *xv = min_x[ib] + kk * sp; *hv = (double)d[kk];
+        *xv = mnx(ib) + kk * sp; *hv = (double)d[kk];
         *hp = kk > 0 ? (double)d[kk - 1] : sample(*xv - sp);
         *hn = kk < wb - 1 ? (double)d[kk + 1] : (double)d[kk];
         return true;
@@ -379,11 +384,11 @@ struct GroundView {
         float mx = -INFINITY;
 #pragma unroll
         for (int id = 0; id < 2; ++id) {
-            const int w = n[id] < kTerrainCap ? n[id] : kTerrainCap;
+            const int w = nn(id) < kTerrainCap ? nn(id) : kTerrainCap;
             if (w <= 0) continue;
             const float* d = data + id * kTerrainCap;
-            const double c0 = fmin(fmax((x0 - min_x[id]) / TRL_VERT_SPACING_D, 0.0), (double)(w - 1));
-            const double c1 = fmin(fmax((x1 - min_x[id]) / TRL_VERT_SPACING_D, 0.0), (double)(w - 1));
+            const double c0 = fmin(fmax((x0 - mnx(id)) / TRL_VERT_SPACING_D, 0.0), (double)(w - 1));
+            const double c1 = fmin(fmax((x1 - mnx(id)) / TRL_VERT_SPACING_D, 0.0), (double)(w - 1));
             const int i0 = (int)c0, i1 = min(w - 1, (int)c1 + 1);
             for (int i = i0 + lane; i <= i1; i += 32) mx = fmaxf(mx, d[i]);
         }
@@ -409,8 +414,9 @@ struct GroundView {
         if (nv > 0) end_h = align_min ? d[0] : d[nv - 1];
         float h_off = __double2float_rn(__dsub_rn(fix_y, (double)end_h));
         for (int i = 0; i < nv; ++i) d[i] = __fadd_rn(d[i], h_off);
-        n[id] = nv;
-        min_x[id] = align_min ? bmin : __dsub_rn(bmax, __dmul_rn((double)(nv - 1), TRL_VERT_SPACING_D));
+        if (id) n[1] = nv; else n[0] = nv;
+        const double mn_ = align_min ? bmin : __dsub_rn(bmax, __dmul_rn((double)(nv - 1), TRL_VERT_SPACING_D));
+        if (id) min_x[1] = mn_; else min_x[0] = mn_;
         rng_state = rng.x;
     }
     __device__ void init_segments(double bmin, double bmax, int type, const double* params, double seg_width) {
@@ -433,7 +439,7 @@ struct GroundView {
         if (bmax <= mn || bmin >= mx) { init_segments(bmin, bmax, type, params, seg_width); return true; }
         if (bmax >= mx) {
             const float* dm = data + smax * kTerrainCap;
-            double end_h = (double)dm[n[smax] - 1];
+            double end_h = (double)dm[nn(smax) - 1];
             build_segment(smin, mx, __dadd_rn(mx, seg_width), true, end_h, type, params, seg_width);
         } else {
             const float* dm = data + smin * kTerrainCap;

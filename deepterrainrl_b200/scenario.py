@@ -34,6 +34,10 @@ VARIANTS = {
     "regs96": ["-DTRL_STEP_MIN_BLOCKS=5"],       # 5 CTAs (20 warps) per SM at 96 registers, more spills; only makes sense with env groups
     "regs80": ["-DTRL_STEP_MIN_BLOCKS=6"],
     "field_smem": ["-DTRL_FIELD_SMEM=1"],        # every per-env field staged in shared memory for the launch (one load batch, one store batch): + 0.4 %, not adopted
+    "cta1": ["-DTRL_WARPS_PER_BLOCK=1", "-DTRL_STEP_MIN_BLOCKS=16"],     # CTA size of the step kernel: 1 / 2 / 8 warps (default 4), 16 warps per SM in all
+    "cta2": ["-DTRL_WARPS_PER_BLOCK=2", "-DTRL_STEP_MIN_BLOCKS=8"],
+    "cta8": ["-DTRL_WARPS_PER_BLOCK=8", "-DTRL_STEP_MIN_BLOCKS=2"],
+    "table_const": ["-DTRL_TABLE_MIRROR=0"],     # lane-indexed model tables from constant memory (divergent LDC, the round-1 reads); the default reads a global-memory mirror
     "link_regs": ["-DTRL_LINK_SMEM=0"],          # the round-1 layout: per-lane link constants in registers (the default keeps them in shared memory)          # per-lane link constants in shared memory instead of ~28 registers (180 B instead of 216 B spilled)
     "reuse_kin": ["-DTRL_REUSE_KIN=1"],
     "smem_xchg_reuse_kin": ["-DTRL_SMEM_XCHG=1", "-DTRL_REUSE_KIN=1"],

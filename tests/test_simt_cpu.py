@@ -389,6 +389,7 @@ VARIANTS = [
     ["-DTRL_DECIDE_TILE=1", "-DTRL_CONV_TILE=4"],
     ["-DTRL_LINK_SMEM=0"],
     ["-DTRL_FIELD_SMEM=1"],
+    ["-DTRL_TABLE_MIRROR=0"],
 ]
 
 
