@@ -1138,20 +1138,33 @@ __device__ int physics_substep(const LinkC& lc, EnvRegs& e, const GroundView& g,
     // ---- pass 2: articulated inertias / bias forces inward (level-synchronous)
     const double s1 = k.ry, s2 = -k.rx;
     double U0 = 0.0, U1 = 0.0, U2 = 0.0, dinv = 0.0, uu = 0.0;
+    // one-sided implicit spring-damper at the joint limits (branch-free: the range of a free joint is infinite).  It depends on
+    // the joint's own state only, so it is evaluated once per sub-step, not once per elimination round
+#ifndef TRL_HOIST_LIMITS
+#define TRL_HOIST_LIMITS 1
+#endif
+#if TRL_HOIST_LIMITS
+    const double viol = fmax(e.q - lc.lim_hi, 0.0) + fmin(e.q - lc.lim_lo, 0.0);
+    const double cl = (viol != 0.0) ? pp.d_lim + dt * pp.k_lim : 0.0;
+    const double lim_f = pp.k_lim * viol + cl * e.qd;
+    const int my_round = lc.acc_round;
+#else
+#define my_round lc.acc_round
+#endif
     for (int r = 0; r < m.acc_rounds; ++r) {
-        if (lc.acc_round == r) {
+        if (my_round == r) {
             U0 = ia[0] + ia[1] * s1 + ia[2] * s2;
             U1 = ia[1] + ia[3] * s1 + ia[4] * s2;
             U2 = ia[2] + ia[4] * s1 + ia[5] * s2;
             double Dj = U0 + s1 * U1 + s2 * U2;
             uu = e.tau - (ia[6] + s1 * ia[7] + s2 * ia[8]);
-            {
-                // one-sided implicit spring-damper at the joint limits (branch-free: the range of a free joint is infinite)
-                const double viol = fmax(e.q - lc.lim_hi, 0.0) + fmin(e.q - lc.lim_lo, 0.0);
-                const double cl = (viol != 0.0) ? pp.d_lim + dt * pp.k_lim : 0.0;
-                uu -= pp.k_lim * viol + cl * e.qd;
-                Dj += dt * cl;
-            }
+#if !TRL_HOIST_LIMITS
+            const double viol = fmax(e.q - lc.lim_hi, 0.0) + fmin(e.q - lc.lim_lo, 0.0);
+            const double cl = (viol != 0.0) ? pp.d_lim + dt * pp.k_lim : 0.0;
+            const double lim_f = pp.k_lim * viol + cl * e.qd;
+#endif
+            uu -= lim_f;
+            Dj += dt * cl;
             dinv = 1.0 / Dj;
             // Ia = IA - U U^T / D ;  pa = pA + Ia c + U u / D
             double n0 = ia[0] - U0 * U0 * dinv, n1 = ia[1] - U0 * U1 * dinv, n2 = ia[2] - U0 * U2 * dinv;
@@ -1192,6 +1205,13 @@ __device__ int physics_substep(const LinkC& lc, EnvRegs& e, const GroundView& g,
     // pass 3: accelerations outward; each link lane integrates its own joint (semi-implicit Euler)
     double aw = a0, alx = a1, aly = a2;
     const double thd0 = shf(e.qd, 0);
+#if TRL_HOIST_LIMITS
+    const int my_depth = lc.depth, my_parent = lc.parent;
+#else
+#undef my_round
+#define my_depth lc.depth
+#define my_parent lc.parent
+#endif
     for (int l = 1; l <= md; ++l) {
 #if TRL_OUTWARD_SMEM
         // every lane publishes its current (aw, ax, ay); a link of depth l reads its parent's, which is final since level l-1.
@@ -1200,12 +1220,12 @@ __device__ int physics_substep(const LinkC& lc, EnvRegs& e, const GroundView& g,
         double* o1 = xs + X_OUT + (l & 1) * kOutBuf + 2 * kWarp;
         o2[lane] = make_double2(aw, alx); o1[lane] = aly;
         __syncwarp();
-        const double2 pp_ = o2[lc.parent];
-        const double paw = pp_.x, pax = pp_.y, pay = o1[lc.parent];
+        const double2 pp_ = o2[my_parent];
+        const double paw = pp_.x, pax = pp_.y, pay = o1[my_parent];
 #else
-        double paw = shf(aw, lc.parent), pax = shf(alx, lc.parent), pay = shf(aly, lc.parent);
+        double paw = shf(aw, my_parent), pax = shf(alx, my_parent), pay = shf(aly, my_parent);
 #endif
-        if (lc.depth == l) {
+        if (my_depth == l) {
             double bx = pax + cvx, by = pay + cvy;
             double qdd = (uu - (U0 * paw + U1 * bx + U2 * by)) * dinv;
             aw = paw + qdd; alx = bx + s1 * qdd; aly = by + s2 * qdd;
@@ -1220,6 +1240,10 @@ __device__ int physics_substep(const LinkC& lc, EnvRegs& e, const GroundView& g,
         e.ox += dt * e.oxd; e.oy += dt * e.oyd;
         if (lane == 0) { e.qd += dt * a0; e.q += dt * e.qd; }
     }
+#if !TRL_HOIST_LIMITS
+#undef my_depth
+#undef my_parent
+#endif
     return contact;
 }
 

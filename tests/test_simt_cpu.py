@@ -390,6 +390,7 @@ VARIANTS = [
     ["-DTRL_LINK_SMEM=0"],
     ["-DTRL_FIELD_SMEM=1"],
     ["-DTRL_TABLE_MIRROR=0"],
+    ["-DTRL_HOIST_LIMITS=0"],
 ]
 
 
