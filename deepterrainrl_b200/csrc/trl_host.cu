@@ -626,7 +626,7 @@ static trl_handle* create_common(trl_handle* h, int num_envs, int device, int mo
             if (cudaStreamCreateWithPriority(&h->side[k], cudaStreamNonBlocking, hi) != cudaSuccess) return bail("cudaStreamCreate (side) failed");
         h->aux_stream = h->side[0];
         const char* gr = std::getenv("TRL_GROUPS");
-        if (gr && gr[0]) h->groups = std::min(kMaxGroups, std::max(1, std::atoi(gr)));     // default 2: profiles/step_groups_r02_ab.txt
+        if (gr && gr[0]) h->groups = std::min(kMaxGroups, std::max(1, std::atoi(gr)));     // default 2: profiles/step_kernel_r02_session2_ab.txt
         while (h->groups > 1 && group_chunk(num_envs, h->groups) * (h->groups - 1) >= num_envs) --h->groups;   // no empty group
         for (int g = 1; g < h->groups; ++g)
             if (cudaStreamCreateWithFlags(&h->group_stream[g - 1], cudaStreamNonBlocking) != cudaSuccess) return bail("cudaStreamCreate (group) failed");

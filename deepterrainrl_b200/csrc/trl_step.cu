@@ -48,7 +48,7 @@ __constant__ ModelConst c_model;
 // serves one address per access, so `c_model.kp[lane]` costs one replay per distinct lane, while the mirror is one coalesced,
 // L1-cached read-only load.  Warp-uniform reads stay in constant memory.
 #ifndef TRL_TABLE_MIRROR
-#define TRL_TABLE_MIRROR 1      // + 4.5 % on a B200 (profiles/step_groups_r02_ab.txt); 0 = the round-1 reads from constant memory
+#define TRL_TABLE_MIRROR 1      // + 4.5 % on a B200 (profiles/step_kernel_r02_session2_ab.txt); 0 = the round-1 reads from constant memory
 #endif
 #if TRL_TABLE_MIRROR
 __device__ ModelConst g_model;
@@ -408,7 +408,7 @@ __device__ void store_rng(Lane& L, const CounterRng& r) {
 // Per-lane constants of link `lane` and the env state held in registers.
 #ifndef TRL_LINK_SMEM
 #define TRL_LINK_SMEM 1     // 1: the per-lane link constants live in shared memory (one table per CTA) instead of ~28 registers per thread
-                            //    (the register build spills them and reloads them inside the ABA rounds; + 1.5 % measured, profiles/step_groups_r02_ab.txt)
+                            //    (the register build spills them and reloads them inside the ABA rounds; + 1.5 % measured, profiles/step_kernel_r02_session2_ab.txt)
 #endif
 #if TRL_LINK_SMEM
 enum { LF_AX, LF_AY, LF_MASS, LF_BAX, LF_BAY, LF_IZZ, LF_LIM_LO, LF_LIM_HI, LF_NUM };
@@ -595,7 +595,7 @@ __device__ __forceinline__ Kin kinematics(const LinkC& c, const EnvRegs& e TRL_K
 // `xs` (the warp's shared-memory block) must be in scope.
 #define TRL_ACCUM_ROUND(r, NV, vals)                                                        \
     do {                                                                                    \
-        const int src_ = (int)(lc.acc_src >> (5 * (r))) & 31;                               \
+        const int src_ = (int)(acc_src_v >> (5 * (r))) & 31;                                \
         double2* mine_ = trl_as2<double2>(xs + X_ACC + lane * kAccStride);        \
         _Pragma("unroll") for (int v_ = 0; v_ + 1 < (NV); v_ += 2) mine_[v_ / 2] = make_double2((vals)[v_], (vals)[v_ + 1]); \
         if ((NV) & 1) xs[X_ACC + lane * kAccStride + (NV) - 1] = (vals)[(NV) - 1];         \
@@ -611,7 +611,7 @@ __device__ __forceinline__ Kin kinematics(const LinkC& c, const EnvRegs& e TRL_K
 #else
 #define TRL_ACCUM_ROUND(r, NV, vals)                                                        \
     do {                                                                                    \
-        const int src_ = (int)(lc.acc_src >> (5 * (r))) & 31;                               \
+        const int src_ = (int)(acc_src_v >> (5 * (r))) & 31;                                \
         _Pragma("unroll") for (int v_ = 0; v_ < (NV); ++v_) (vals)[v_] += shf((vals)[v_], src_); \
     } while (0)
 #endif
@@ -635,9 +635,10 @@ __device__ double controller_torque(Lane& L, const LinkC& lc, const EnvRegs& e, 
         alx = -m.gx + c0 * cjx - s0 * cjy;
         aly = -m.gy + s0 * cjx + c0 * cjy;
     }
+    const int ctl_parent = lc.parent, ctl_depth = lc.depth;
     for (int l = 1; l <= md; ++l) {
-        double pax = shf(alx, lc.parent), pay = shf(aly, lc.parent);
-        if (lc.depth == l) {
+        double pax = shf(alx, ctl_parent), pay = shf(aly, ctl_parent);
+        if (ctl_depth == l) {
             alx = pax + e.qd * (k.w * k.rx + k.vy);   // a_j = a_parent + v_j x (S_j qd_j)
             aly = pay + e.qd * (k.w * k.ry - k.vx);
         }
@@ -652,7 +653,10 @@ __device__ double controller_torque(Lane& L, const LinkC& lc, const EnvRegs& e, 
         vals[6] = lc.mass * aly + k.w * hlx;
         if (!lc.act) { vals[4] = vals[5] = vals[6] = 0.0; }
     }
-    for (int r = 0; r < m.acc_rounds; ++r) TRL_ACCUM_ROUND(r, 7, vals);
+    {
+        const unsigned long long acc_src_v = lc.acc_src;       // one read of the schedule word, not one per round
+        for (int r = 0; r < m.acc_rounds; ++r) TRL_ACCUM_ROUND(r, 7, vals);
+    }
     const double s1 = k.ry, s2 = -k.rx;                       // S_j = (1, s1, s2)
     // bias force C (per link lane; the root's three entries live in lane 0)
     const double Cj = vals[4] + s1 * vals[5] + s2 * vals[6];
@@ -1143,6 +1147,7 @@ __device__ int physics_substep(const LinkC& lc, EnvRegs& e, const GroundView& g,
 #ifndef TRL_HOIST_LIMITS
 #define TRL_HOIST_LIMITS 1
 #endif
+    const unsigned long long acc_src_v = lc.acc_src;
 #if TRL_HOIST_LIMITS
     const double viol = fmax(e.q - lc.lim_hi, 0.0) + fmin(e.q - lc.lim_lo, 0.0);
     const double cl = (viol != 0.0) ? pp.d_lim + dt * pp.k_lim : 0.0;

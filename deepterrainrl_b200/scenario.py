@@ -39,6 +39,7 @@ VARIANTS = {
     "cta8": ["-DTRL_WARPS_PER_BLOCK=8", "-DTRL_STEP_MIN_BLOCKS=2"],
     "table_const": ["-DTRL_TABLE_MIRROR=0"],     # lane-indexed model tables from constant memory (divergent LDC, the round-1 reads); the default reads a global-memory mirror
     "no_hoist": ["-DTRL_HOIST_LIMITS=0"],        # joint-limit terms and link indices re-evaluated in every ABA round (the code before the hoist)
+    "contact_outward_smem": ["-DTRL_CONTACT_SMEM=1", "-DTRL_OUTWARD_SMEM=1"],
     "link_regs": ["-DTRL_LINK_SMEM=0"],          # the round-1 layout: per-lane link constants in registers (the default keeps them in shared memory)          # per-lane link constants in shared memory instead of ~28 registers (180 B instead of 216 B spilled)
     "reuse_kin": ["-DTRL_REUSE_KIN=1"],
     "smem_xchg_reuse_kin": ["-DTRL_SMEM_XCHG=1", "-DTRL_REUSE_KIN=1"],
