@@ -33,9 +33,10 @@ DT = 1.0 / 30.0
 # per env-step the persistent state must be read and written once (q, qd, held torque, 64-scalar
 # controller block = 133 scalars each way) plus <= 42 terrain vertices read: (133 * 2) * 8 B + 42 * 4 B for f64 state
 ALGO_BYTES_PER_ENV_STEP = 133 * 2 * 8 + 42 * 4
-# ncu (profiles/ncu_step_kernel_r02.csv, dog / slopes_mixed, one 4096-env step launch): DFMA + DADD + DMUL thread-instructions per cycle
-# (445.6 + 341.0 + 110.4) x 309,825 elapsed cycles = 278 M per launch
-FP64_INST_PER_LAUNCH_ENV = 278.0e6 / 4096
+# ncu (profiles/ncu_step_kernel_r02.csv, dog / slopes_mixed, one 4096-env step launch of the shipped build): DFMA + DADD + DMUL
+# thread-instructions per cycle (465.8 + 357.8 + 115.7) x 295,256 elapsed cycles = 277 M per launch (the arithmetic has not changed
+# since the first round-2 capture: 278 M)
+FP64_INST_PER_LAUNCH_ENV = 277.3e6 / 4096
 
 
 def measured_peaks():
@@ -228,7 +229,7 @@ def run_config4(args, trl, rank, local_rank, world, n, dist, torch):
     from deepterrainrl_b200 import parallel
     seeds = parallel.shard_seeds(rank, n)
     sc = trl.ScenarioExpMACE(PACK, n, device=local_rank, terrain_seeds=seeds, rng_seed=100 + rank)
-    tr = trl.MACETrainer(sc, replay_mem_size=200000, num_init_samples=4000 * world, freeze_target_iters=50, seed=9)
+    tr = trl.MACETrainer(sc, replay_mem_size=args.replay_size, num_init_samples=4000 * world, freeze_target_iters=50, seed=9)
     L = sc.L
     if world > 1:
         comm = parallel.Comm(sc, rank, world, backend="nccl")          # the library's own NCCL communicator; id shipped over torch.distributed
@@ -287,7 +288,7 @@ def run_config4(args, trl, rank, local_rank, world, n, dist, torch):
            "tuples_last_update_per_rank": [int(x) for x in counts], "tuples_dropped": int(dropped),
            "train_iters_per_update": args.train_iters, "trainer": "replicated on every rank (deterministic; no weight broadcast needed)",
            "trainer_mode": "synchronous (between the updates)" if args.train_sync else "asynchronous (own stream, overlaps the next update; policy snapshot refreshed between updates)",
-           "trainer_iter": c["iter"], "actor_iter": c["actor_iter"], "replay_tuples": c["num"], "replica_spread": spread,
+           "trainer_iter": c["iter"], "actor_iter": c["actor_iter"], "replay_tuples": c["num"], "replay_capacity": args.replay_size, "replica_spread": spread,
            "gpu_launches": launches, "envs_per_gpu": n, "l2": "flushed between updates (256 MiB memset on the engine stream)",
            "timing": "cudaEvent on the engine stream around K x {update, pack + all-gather, hand-over, trainer iterations}, max over ranks"}
     tr.close(); comm.close(); sc.close()
@@ -309,6 +310,8 @@ def main():
                          "trainer iterations (0 = skip)")
     ap.add_argument("--train-iters", type=int, default=4, help="trainer iterations per outer update in the config-4 block")
     ap.add_argument("--block-rows", type=int, default=1024, help="tuple rows per rank and all-gather in the config-4 block")
+    ap.add_argument("--replay-size", type=int, default=200000,
+                    help="replay memory of the config-4 trainer (tuples); a small value puts the run into the wrapped-ring steady state of a long training run")
     ap.add_argument("--train-sync", type=int, default=0,
                     help="config-4 block: 1 = the trainer runs between the updates (synchronous); default 0 = the reference's asynchronous "
                          "trainer semantics: hand-over + training overlap the next update on their own stream")

@@ -180,19 +180,155 @@ __device__ int assign_slot(const Dev& d, Counters& c, uint32_t flags) {
     }
     return t;
 }
+// One batch of up to 32 incoming tuples in arrival order, one per lane (lane order = arrival order): `take` = the lane's tuple gets a
+// replay slot, `flags` its tuple flags.  Returns the lane's slot (-1 if not taken).  Counters live in lane 0's `c` (a register copy of
+// *d.c); every lane's copy is refreshed at the end.  Fast path -- every slot of the batch is fresh (never written: the ring has not
+// wrapped onto it): head / list positions are prefix sums over the batch, all stores in parallel, the result is what the sequential
+// loop produces.  Otherwise lane 0 runs the sequential cNeuralNetTrainer::AddTuple + cMACETrainer::UpdateBuffers (assign_slot) tuple
+// by tuple.  The loads a tuple needs (its slot's list positions) are issued for the whole batch at once instead of one dependent
+// L2 round trip after the other: the single-thread loop took ~1.5 us per tuple, 3 ms per update with 8 ranks' tuples.
+__device__ int assign_batch(const Dev& d, Counters& c, bool take, uint32_t flags) {
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned tmask = __ballot_sync(0xffffffffu, take);
+    if (tmask == 0) return -1;
+    const int pre = __popc(tmask & ((1u << lane) - 1u));
+    const int nt = __popc(tmask);
+    const int t = (int)(((long long)c.head + pre) % d.cap);
+    const int pa = take ? d.pos_actor[t] : -1, pc = take ? d.pos_critic[t] : -1;
+    const bool fresh = __all_sync(0xffffffffu, !take || (pa < 0 && pc < 0)) && nt <= d.cap;
+    int slot = -1;
+    if (fresh) {
+        const bool ea = take && (flags & 4u) != 0, ec = take && !ea;       // eFlagExpActor -> actor buffer, else critic buffer
+        const unsigned am = __ballot_sync(0xffffffffu, ea), cm = __ballot_sync(0xffffffffu, ec);
+        if (ea) { const int q = c.actor_count + __popc(am & ((1u << lane) - 1u)); d.pos_actor[t] = q; d.actor_list[q] = t; }
+        if (ec) { const int q = c.critic_count + __popc(cm & ((1u << lane) - 1u)); d.pos_critic[t] = q; d.critic_list[q] = t; }
+        c.actor_count += __popc(am); c.critic_count += __popc(cm);
+        c.head = (int)(((long long)c.head + nt) % d.cap);
+        c.num = min(d.cap, c.num + nt);
+        c.total += nt;
+        if (take) slot = t;
+    } else if (d.cap >= 64) {
+        // The ring has wrapped onto used slots (the steady state of a long run): the reference's sequential order matters -- a slot
+        // moves between the critic and the actor list by swap-remove + append, and leaves the pending actor batch.  Lane 0 walks the
+        // batch in arrival order on shared-memory copies of everything the walk can touch: the list positions of the batch's own
+        // slots, a 64-entry window around either list's tail (all reads are tail reads), the pending actor batch.  Stores that fall
+        // outside go to memory directly (nothing in the batch reads them back); the copies are written back at the end.
+        __shared__ int w_list[2][64], w_pos[2][32], w_ab[4 * kB], w_slot[32], w_hit[32];
+        __shared__ uint32_t w_flags[32];
+        const int head0 = c.head;
+        const int base0 = max(0, c.critic_count - 32), base1 = max(0, c.actor_count - 32);
+        for (int k = lane; k < 64; k += 32) {
+            w_list[0][k] = base0 + k < d.cap ? d.critic_list[base0 + k] : -1;
+            w_list[1][k] = base1 + k < d.cap ? d.actor_list[base1 + k] : -1;
+        }
+        w_hit[lane] = 0;
+        __syncwarp();
+        for (int k = lane; k < 4 * kB; k += 32) {
+            const int v = k < c.actor_batch_count ? d.actor_batch[k] : -1;
+            w_ab[k] = v;
+            if (v >= 0) {                                  // which of the batch's slots sit in the pending actor batch (rare): only those scan it
+                int bl = v - head0;
+                if (bl < 0) bl += d.cap;
+                if (bl < nt) w_hit[bl] = 1;
+            }
+        }
+        if (take) { w_pos[0][pre] = pc; w_pos[1][pre] = pa; w_flags[pre] = flags; }
+        __syncwarp();
+        if (lane == 0) {
+            int cnt[2] = {c.critic_count, c.actor_count};
+            const int wbase[2] = {base0, base1};
+            int* lists[2] = {d.critic_list, d.actor_list};
+            int* poss[2] = {d.pos_critic, d.pos_actor};
+            int abc = c.actor_batch_count;
+            for (int bi = 0; bi < nt; ++bi) {
+                int tq = head0 + bi;                                           // head0 < cap, bi < 32 <= cap
+                if (tq >= d.cap) tq -= d.cap;
+                const int nl = (w_flags[bi] & 4u) ? 1 : 0, ol = 1 - nl;       // eFlagExpActor -> actor list (1), else critic list (0)
+                if (w_pos[nl][bi] < 0) {                                       // append to the list it belongs to now
+                    const int k = cnt[nl] - wbase[nl];
+                    w_pos[nl][bi] = cnt[nl];
+                    if (k >= 0 && k < 64) w_list[nl][k] = tq; else lists[nl][cnt[nl]] = tq;
+                    ++cnt[nl];
+                }
+                const int pq = w_pos[ol][bi];
+                if (pq >= 0) {                                                 // list_remove from the other one (swap with its tail)
+                    const int kl = cnt[ol] - 1 - wbase[ol];
+                    const int last = (kl >= 0 && kl < 64) ? w_list[ol][kl] : lists[ol][cnt[ol] - 1];
+                    const int kp = pq - wbase[ol];
+                    if (kp >= 0 && kp < 64) w_list[ol][kp] = last; else lists[ol][pq] = last;
+                    int bl = last - head0;
+                    if (bl < 0) bl += d.cap;
+                    if (bl < nt) w_pos[ol][bl] = pq; else poss[ol][last] = pq;
+                    w_pos[ol][bi] = -1;
+                    --cnt[ol];
+                }
+                if (w_hit[bi]) {
+                    for (int k = 0; k < abc;) {                                // the overwritten slot leaves the pending actor batch
+                        if (w_ab[k] == tq) w_ab[k] = w_ab[--abc];
+                        else ++k;
+                    }
+                }
+                w_slot[bi] = tq;
+            }
+            c.critic_count = cnt[0]; c.actor_count = cnt[1]; c.actor_batch_count = abc;
+            c.head = head0 + nt >= d.cap ? head0 + nt - d.cap : head0 + nt;
+            c.num = min(d.cap, c.num + nt);
+            c.total += nt;
+        }
+        __syncwarp();
+        for (int k = lane; k < 64; k += 32) {
+            if (base0 + k < d.cap) d.critic_list[base0 + k] = w_list[0][k];
+            if (base1 + k < d.cap) d.actor_list[base1 + k] = w_list[1][k];
+        }
+        for (int k = lane; k < 4 * kB; k += 32) if (w_ab[k] >= 0 || k < 4 * kB) d.actor_batch[k] = w_ab[k];
+        if (take) { d.pos_critic[t] = w_pos[0][pre]; d.pos_actor[t] = w_pos[1][pre]; slot = w_slot[pre]; }
+        c.head = __shfl_sync(0xffffffffu, c.head, 0); c.num = __shfl_sync(0xffffffffu, c.num, 0);
+        c.total = __shfl_sync(0xffffffffu, c.total, 0);
+        c.actor_count = __shfl_sync(0xffffffffu, c.actor_count, 0); c.critic_count = __shfl_sync(0xffffffffu, c.critic_count, 0);
+        c.actor_batch_count = __shfl_sync(0xffffffffu, c.actor_batch_count, 0);
+        __syncwarp();
+    } else {
+        // tiny replay memories (tests): the sequential loop against memory
+        __syncwarp();
+        for (int q = 0; q < 32; ++q) {
+            if (!((tmask >> q) & 1u)) continue;
+            const uint32_t fq = __shfl_sync(0xffffffffu, flags, q);
+            int tq = 0;
+            if (lane == 0) tq = assign_slot(d, c, fq);
+            tq = __shfl_sync(0xffffffffu, tq, 0);
+            if ((int)lane == q) slot = tq;
+        }
+        c.head = __shfl_sync(0xffffffffu, c.head, 0); c.num = __shfl_sync(0xffffffffu, c.num, 0);
+        c.total = __shfl_sync(0xffffffffu, c.total, 0);
+        c.actor_count = __shfl_sync(0xffffffffu, c.actor_count, 0); c.critic_count = __shfl_sync(0xffffffffu, c.critic_count, 0);
+        c.actor_batch_count = __shfl_sync(0xffffffffu, c.actor_batch_count, 0);
+        __syncwarp();
+    }
+    return slot;
+}
 // cNeuralNetTrainer::AddTuple slot assignment + cMACETrainer::UpdateBuffers, in arrival order (one thread: O(1) per tuple)
 __global__ void k_add_assign(Dev d, const uint32_t* src_flags, const int* count_ptr, int count_val, int max_count, int* reset_count, int use_order) {
     pdl_sync();
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (blockIdx.x != 0 || threadIdx.x >= 32) return;
+    const int lane = threadIdx.x;
     const int count = count_ptr ? min(*count_ptr, max_count) : count_val;
-    Counters& c = *d.c;
-    for (int r = 0; r < count; ++r) {
-        const int i = use_order ? d.order[r] : r;
-        if (!d.valid[i]) { d.slot[i] = -1; continue; }
-        d.slot[i] = assign_slot(d, c, src_flags[i]);
+    Counters c = *d.c;                                     // register copy, written back once
+    for (int base = 0; base < count; base += 32) {
+        const int r = base + lane;
+        const bool in = r < count;
+        const int i = in ? (use_order ? d.order[r] : r) : 0;
+        const bool take = in && d.valid[i] != 0;
+        const uint32_t f = take ? src_flags[i] : 0u;
+        const int t = assign_batch(d, c, take, f);
+        if (in) d.slot[i] = t;
     }
-    c.add_count = count;                                   // k_add_copy must not re-read a counter that is reset here
-    if (reset_count) *reset_count = 0;                     // cScenarioExp::ResetTupleBuffer
+    if (lane == 0) {
+        Counters& g = *d.c;
+        g.head = c.head; g.num = c.num; g.total = c.total; g.actor_count = c.actor_count; g.critic_count = c.critic_count;
+        g.actor_batch_count = c.actor_batch_count;
+        g.add_count = count;                               // k_add_copy must not re-read a counter that is reset here
+        if (reset_count) *reset_count = 0;                 // cScenarioExp::ResetTupleBuffer
+    }
 }
 __global__ void k_add_copy(Dev d, const double* rows, const uint32_t* src_flags) {
     pdl_sync();
@@ -241,20 +377,30 @@ __global__ void k_addg_order(Dev d, GBlocks g) {
 }
 __global__ void k_addg_assign(Dev d, GBlocks g) {
     pdl_sync();
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    Counters& c = *d.c;
+    if (blockIdx.x != 0 || threadIdx.x >= 32) return;
+    const int lane = threadIdx.x;
+    Counters c = *d.c;
     int total = 0;
     for (int r = 0; r < g.world; ++r) {
         const int count = min(max(gb_hdr(g, r)[0], 0), g.R);
         const uint32_t* flags = gb_flags(g, r);
-        for (int k = 0; k < count; ++k) {
-            const int j = d.order[r * g.R + k];
-            const uint32_t f = flags[j];
-            d.slot[r * g.R + j] = (f & 0x80000000u) ? -1 : assign_slot(d, c, f);
+        for (int base = 0; base < count; base += 32) {
+            const int k = base + lane;
+            const bool in = k < count;
+            const int j = in ? d.order[r * g.R + k] : 0;
+            const uint32_t f = in ? flags[j] : 0x80000000u;
+            const bool take = in && !(f & 0x80000000u);
+            const int t = assign_batch(d, c, take, f);
+            if (in) d.slot[r * g.R + j] = t;
         }
         total += count;
     }
-    c.add_count = total;
+    if (lane == 0) {
+        Counters& gc = *d.c;
+        gc.head = c.head; gc.num = c.num; gc.total = c.total; gc.actor_count = c.actor_count; gc.critic_count = c.critic_count;
+        gc.actor_batch_count = c.actor_batch_count;
+        gc.add_count = total;
+    }
 }
 __global__ void k_addg_copy(Dev d, GBlocks g) {
     pdl_sync();

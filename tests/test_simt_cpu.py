@@ -298,6 +298,31 @@ def test_trainer_kernels_vs_oracle(assets, monkeypatch):
             tg, to = g.get("theta"), o.get("theta")
             assert np.max(np.abs(tg - to)) <= 1e-12 * max(1.0, np.max(np.abs(to))), it
         assert co["actor_iter"] >= 1
+        # a second batch wraps the 160-slot ring onto used slots: the warp-cooperative slot assignment must fall back to the reference's
+        # sequential order (buffers move between the critic and the actor list, the pending actor batch loses overwritten slots)
+        rows2, flags2 = _synthetic_tuples(100, g.S, g.A, o.get("in_off"), o.get("in_scale"), 4)
+        g.AddTuples(rows2, flags2)
+        o.add_tuples(rows2, flags2)
+        cg, co2 = g.counters(), o.counters()
+        for k in ("num", "head", "total", "critic", "actor", "actor_batch"):
+            assert cg[k] == co2[k], k
+        for which in ("critic", "actor", "actor_batch"):
+            np.testing.assert_array_equal(g.lists(which), o.lists(which))
+        # ... and a small ring that wraps several times with mixed flags (list tails inside and outside the batch's own slots)
+        kw2 = dict(kw, num_init_samples=10 ** 6)
+        sc2 = trl.ScenarioExpMACE(pack, 4)
+        g2 = trl.MACETrainer(sc2, replay_mem_size=96, **kw2)
+        o2 = OracleTrainer(pack, replay_cap=96, **kw2)
+        for rnd in range(7):
+            rw, fl = _synthetic_tuples(37 + 11 * rnd, g.S, g.A, o.get("in_off"), o.get("in_scale"), 10 + rnd)
+            g2.AddTuples(rw, fl)
+            o2.add_tuples(rw, fl)
+            c1, c2 = g2.counters(), o2.counters()
+            for k in ("num", "head", "total", "critic", "actor", "actor_batch"):
+                assert c1[k] == c2[k], (rnd, k)
+            for which in ("critic", "actor"):
+                np.testing.assert_array_equal(g2.lists(which), o2.lists(which))
+        g2.close(); sc2.close()
         # destroying the scenario first leaves the trainer an inert shell: calls fail with a message, destroy is harmless
         sc.close()
         with pytest.raises(RuntimeError, match="has been destroyed"):
