@@ -44,6 +44,13 @@ namespace TRL_IMPL_NS {
 using namespace trl;
 
 __constant__ ModelConst c_model;
+// character-type branches: a run-time constant of the scene (the raptor's controller differs from the dog's / goat's); an experiment
+// build can fix it at compile time (-DTRL_FIXED_CHAR=0 dog / goat, 2 raptor) to see what the unused branches cost
+#ifdef TRL_FIXED_CHAR
+#define TRL_IS_RAPTOR(mc) (TRL_FIXED_CHAR == 2)
+#else
+#define TRL_IS_RAPTOR(mc) ((mc).char_type == 2)
+#endif
 // Lane-indexed tables (one entry per link / corner) are read from a global-memory mirror of the same struct: the constant cache
 // serves one address per access, so `c_model.kp[lane]` costs one replay per distinct lane, while the mirror is one coalesced,
 // L1-cached read-only load.  Warp-uniform reads stay in constant memory.
@@ -263,7 +270,7 @@ __device__ __forceinline__ bool has_fallen(Lane& L, double root_theta) {
 __device__ void set_state_params(Lane& L, int state) {
     const ModelConst& m = c_model;
     int base = D_PARAMS + m.misc_max + state * m.sp_max;
-    if (m.char_type == 2) {
+    if (TRL_IS_RAPTOR(m)) {
         const int st = L.i(I_STANCE) == 0 ? rRightHip : rLeftHip, sw = L.i(I_STANCE) == 0 ? rLeftHip : rRightHip;
         L.d(D_PD_TARGET + st) = L.d(base + rpStanceHip); L.d(D_PD_TARGET + st + 1) = L.d(base + rpStanceKnee);
         L.d(D_PD_TARGET + st + 2) = L.d(base + rpStanceAnkle);
@@ -291,7 +298,7 @@ __device__ double calc_reward(Lane& L, bool fallen) {
         vel_r = exp(-0.5 * err * err);
         double avg_st = L.d(D_PREV_STUMBLE) / ct;
         stum_r = 1.0 / (1.0 + 10.0 * avg_st);
-        if (c_model.char_type == 2 && avg_vel < 0.0) { vel_r = 0.0; stum_r = 0.0; }   // sim/RaptorController.cpp:583-587
+        if (TRL_IS_RAPTOR(c_model) && avg_vel < 0.0) { vel_r = 0.0; stum_r = 0.0; }   // sim/RaptorController.cpp:583-587
     }
     return 0.8 * vel_r + 0.2 * stum_r;
 }
@@ -339,7 +346,7 @@ __device__ int build_base_action(Lane& L, CounterRng& rng, int a, double* params
     double blend = m.act_blend[a];
     for (int k = 0; k < m.n_params; ++k) {
         double p0 = m.ctrl_params[i0][k], p1 = m.ctrl_params[i1][k];
-        if (k == mTransTime || k == mCv || (m.char_type == 2 && k == rmCd)) { p0 = fabs(p0); p1 = fabs(p1); }
+        if (k == mTransTime || k == mCv || (TRL_IS_RAPTOR(m) && k == rmCd)) { p0 = fabs(p0); p1 = fabs(p1); }
         params[k] = (1.0 - blend) * p0 + blend * p1;
     }
     int id = a;
@@ -366,7 +373,7 @@ __device__ void apply_action(Lane& L, int id, const double* params, double comx,
     for (int k = 0; k < c_model.n_params; ++k) L.d(D_PARAMS + k) = params[k];
     L.d(D_PARAMS + mTransTime) = fabs(params[mTransTime]);
     L.d(D_PARAMS + mCv) = fabs(params[mCv]);
-    if (c_model.char_type == 2) L.d(D_PARAMS + rmCd) = fabs(params[rmCd]);
+    if (TRL_IS_RAPTOR(c_model)) L.d(D_PARAMS + rmCd) = fabs(params[rmCd]);
     L.i(I_ACTION_ID) = id;
     L.d(D_PREV_CYCLE_T) = L.d(D_CUR_CYCLE_T); L.d(D_CUR_CYCLE_T) = 0.0;
     L.d(D_PREV_STUMBLE) = L.d(D_CUR_STUMBLE); L.d(D_CUR_STUMBLE) = 0.0;
@@ -694,7 +701,7 @@ __device__ double controller_torque(Lane& L, const LinkC& lc, const EnvRegs& e, 
 
     // ---- ApplyFeedback (sim/DogController.cpp:903-945) / ApplySwingFeedback (sim/RaptorController.cpp:907-931)
     const int state = L.i(I_STATE);
-    const bool raptor = m.char_type == 2;
+    const bool raptor = TRL_IS_RAPTOR(m);
     const int stance = raptor ? L.i(I_STANCE) : 0;
     const int st_hip = stance == 0 ? rRightHip : rLeftHip, sw_hip = stance == 0 ? rLeftHip : rRightHip, st_toe = st_hip + 3;
     // cRaptorController::IsActiveVFEffector(stance toe): stance foot on the ground during Contact / Down
@@ -1267,7 +1274,7 @@ __device__ void build_poli_state(const LinkC& lc, const EnvRegs& e, const Kin& k
         // raptor: when the left leg is the stance leg the two legs' entries are swapped
         // (cRaptorController::FlipPoliPoseStance, sim/RaptorController.cpp:1414-1432,1469-1487)
         int slot = lane;
-        if (m.char_type == 2 && stance != 0 && lane >= rRightHip) slot = lane < rLeftHip ? lane + 4 : lane - 4;
+        if (TRL_IS_RAPTOR(m) && stance != 0 && lane >= rRightHip) slot = lane < rLeftHip ? lane + 4 : lane - 4;
         if (lane > 0) {
             out[kNumGroundSamples + 1 + 2 * (slot - 1)] = k.cx;       // body COM relative to the root joint position
             out[kNumGroundSamples + 1 + 2 * (slot - 1) + 1] = k.cy;
@@ -1554,7 +1561,7 @@ trl_step_kernel(Buffers B, double h, int flags, int lists) {
             double phase = L.d(D_PHASE) + h / L.d(D_PARAMS + mTransTime);
             bool advance = first != 0;
             int ns2;
-            if (m.char_type == 2) {
+            if (TRL_IS_RAPTOR(m)) {
                 // cRaptorController::UpdateState (sim/RaptorController.cpp:804-849): Contact, Down, Passing are timed,
                 // Up ends when the swing toe touches down; the stance flips at the end of every cycle but the first
                 const int sw_toe = (L.i(I_STANCE) == 0 ? rLeftHip : rRightHip) + 3;
@@ -1571,7 +1578,7 @@ trl_step_kernel(Buffers B, double h, int flags, int lists) {
             if (advance) {
                 if ((ns2 < 0) || first) {
                     end_step = 1;
-                    if (m.char_type == 2 && !first) L.i(I_STANCE) = 1 - L.i(I_STANCE);   // FlipStance
+                    if (TRL_IS_RAPTOR(m) && !first) L.i(I_STANCE) = 1 - L.i(I_STANCE);   // FlipStance
                 } else { L.i(I_STATE) = ns2; L.d(D_PHASE) = 0.0; set_state_params(L, ns2); }
             }
         }
@@ -1580,7 +1587,7 @@ trl_step_kernel(Buffers B, double h, int flags, int lists) {
         if (end_step) {
             // cycle boundary: build the policy state and hand the env to the decision kernel
             Kin k = kinematics(lc, e TRL_KIN_XS_ARG);
-            build_poli_state(lc, e, k, B, g, env, lane, m.char_type == 2 ? L.i(I_STANCE) : 0);
+            build_poli_state(lc, e, k, B, g, env, lane, TRL_IS_RAPTOR(m) ? L.i(I_STANCE) : 0);
             double comx = e.ox + warp_sum_all(lc.mass * k.cx) / m.total_mass;
             double comy = e.oy + warp_sum_all(lc.mass * k.cy) / m.total_mass;
             if (lane == 0) {
