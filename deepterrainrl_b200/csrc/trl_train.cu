@@ -58,7 +58,7 @@ struct Dev {
     float* mem;
     int *flags, *pos_critic, *pos_actor, *critic_list, *actor_list, *actor_batch;
     Counters* c;
-    int *valid, *slot, *order, *ids, *cand;
+    int *valid, *slot, *order, *ids, *ids2, *cand;      // ids: the critic's / the actor's batch; ids2: the actor candidates (padded)
     double *xn, *a0, *a1, *a2, *t, *catb, *h, *hh, *y;           // activations of the most recent forward pass (kB rows)
     double *v0, *v1;
     double *dy, *dhh, *dh, *dt, *da2, *da1, *da0;
@@ -497,7 +497,7 @@ __global__ void k_sample_actor(Dev d) {
         if (!contains) d.cand[nc++] = t;
     }
     c.cand_count = nc;
-    for (int i = 0; i < kB; ++i) d.ids[i] = nc > 0 ? d.cand[i < nc ? i : 0] : 0;    // pad the batch with the first candidate
+    for (int i = 0; i < kB; ++i) d.ids2[i] = nc > 0 ? d.cand[i < nc ? i : 0] : 0;   // pad the batch with the first candidate
 }
 // UpdateActorBatchBuffer's test (learning/MACETrainer.cpp:556-573) + the batch for cMACETrainer::StepActor
 __global__ void k_actor_select(Dev d) {
@@ -537,12 +537,14 @@ __global__ void k_target_update(Dev d) {
 
 // ================================================================================================ forward
 // rows ids[0..kB) of the replay memory, columns [col0, col0 + S), normalised like cNeuralNet::NormalizeInput
-// (a launch of 2 kB blocks stacks a second block of rows under the first: the same ids, columns starting at col1)
-__global__ void k_gather_norm(Dev d, int pred, int col0, int col1, const double* in_off, const double* in_scale) {
+// (a launch of 2 kB or 3 kB blocks stacks further blocks of kB rows under the first: block b takes the columns starting at
+// col0 / col1 / col2 and, where bit b of ids2_mask is set, the candidate ids d.ids2 instead of d.ids)
+__global__ void k_gather_norm(Dev d, int pred, int col0, int col1, int col2, int ids2_mask, const double* in_off, const double* in_scale) {
     pdl_sync();
     if (!pred_on(d, pred)) return;
-    const int n = blockIdx.x;
-    const float* r = d.mem + (size_t)d.ids[n % kB] * d.Wd + (n < kB ? col0 : col1);
+    const int n = blockIdx.x, b = n / kB;
+    const int* ids = ((ids2_mask >> b) & 1) ? d.ids2 : d.ids;
+    const float* r = d.mem + (size_t)ids[n % kB] * d.Wd + (b == 0 ? col0 : (b == 1 ? col1 : col2));
     for (int i = threadIdx.x; i < d.S; i += blockDim.x) d.xn[(size_t)n * d.S + i] = ((double)r[i] + in_off[i]) * in_scale[i];
 }
 // Convolution (cross-correlation, stride 1) + ReLU.  grid (cout / kConvOut, kB): the block stages all input channels of its
@@ -654,7 +656,7 @@ __global__ void k_concat(Dev d, int pred) {
 // ================================================================================================ labels + loss
 // max over the critic outputs of the un-normalised target-net output (GetMaxFragValAux) -> v0 (state begin) or the Bellman
 // value r (1 - gamma) + gamma max V'(s') -> v1 (CalcNewCumulativeRewardBatch, learning/MACETrainer.cpp:472-513)
-__global__ void k_vals(Dev d, int pred, int with_reward, double* out, int row0) {
+__global__ void k_vals(Dev d, int pred, int with_reward, double* out, int row0, int use_ids2) {
     pdl_sync();
     if (!pred_on(d, pred)) return;
     const int n = threadIdx.x;
@@ -662,7 +664,7 @@ __global__ void k_vals(Dev d, int pred, int with_reward, double* out, int row0) 
     double m = -INFINITY;
     for (int f = 0; f < d.n_frags; ++f) m = fmax(m, d.y[(size_t)(row0 + n) * d.n_out + f] / d.t_out_scale[f] - d.t_out_off[f]);
     if (with_reward) {
-        const int t = d.ids[n];
+        const int t = use_ids2 ? d.ids2[n] : d.ids[n];
         const double r = (double)d.mem[(size_t)t * d.Wd] * (1.0 - d.discount);
         m = (d.flags[t] & 1) ? r : r + d.discount * m;       // eFlagFail
     }
@@ -923,13 +925,15 @@ cudaError_t talloc(trl_trainer* t, Tp** p, size_t count) {
 struct NetRef { const double* theta; const double *in_off, *in_scale; };
 
 // forward pass of the kB rows named by d.ids (replay columns starting at col0) through `net`; activations stay in d.*
-// (col1 >= 0, batched path only: a second block of kB rows with the columns starting at col1 rides along, rows kB .. 2 kB - 1)
-int enqueue_forward(trl_trainer* t, int pred, int col0, const NetRef& net, cudaStream_t st, bool keep_act = true, int col1 = -1) {
+// (col1 / col2 >= 0, batched path only: further blocks of kB rows with the columns starting there ride along; bit b of ids2_mask:
+// block b is taken from the candidate ids)
+int enqueue_forward(trl_trainer* t, int pred, int col0, const NetRef& net, cudaStream_t st, bool keep_act = true, int col1 = -1, int col2 = -1,
+                    int ids2_mask = 0) {
     const Dev& d = t->d;
     const double* th = net.theta;
     auto blob = [&](int b) { return th + d.off[b]; };
-    const int rows = col1 >= 0 ? 2 * kB : kB;
-    launch_pdl(k_gather_norm, dim3(rows), dim3(128), 0, st, d, pred, col0, col1, net.in_off, net.in_scale);
+    const int rows = kB * (1 + (col1 >= 0 ? 1 : 0) + (col2 >= 0 ? 1 : 0));
+    launch_pdl(k_gather_norm, dim3(rows), dim3(128), 0, st, d, pred, col0, col1, col2, ids2_mask, net.in_off, net.in_scale);
     if (t->batched_fwd) {
         // conv stage (one 4-CTA cluster per row, DMMA) + FC stage (one 8-CTA cluster, TMA-fed terr_ip0, DMMA): 2 launches instead of
         // 15.  Plain stream order on both sides (no programmatic attribute): the pass starts after k_gather_norm has finished and the
@@ -1057,25 +1061,30 @@ int enqueue_train(trl_trainer* t, cudaStream_t st) {
     launch_pdl(k_stage_commit, dim3(1), dim3(1), 0, st, d);
     t->launches += 4;
     for (int s = 0; s < d.steps_per_iter; ++s) {
-        // ---- critic: BuildProblem + UpdateNet (learning/NeuralNetTrainer.cpp:414-456, MACETrainer.cpp:222-247)
+        // ---- both batches are drawn up front (the draws of k_sample_actor follow those of k_sample_critic in the RNG stream as before;
+        // nothing between them consumes a draw or touches what they read), so that everything the frozen TARGET net has to evaluate
+        // -- the critic's s', the actor candidates' s and s' -- goes through it in ONE pass of 3 kB rows (three FC clusters side by side)
         launch_pdl(k_sample_critic, dim3(1), dim3(32), 0, st, d);
-        enqueue_forward(t, P_CRITIC, col_end, tar, st, false);
-        launch_pdl(k_vals, dim3(1), dim3(32), 0, st, d, P_CRITIC, 1, d.v1, 0);
+        launch_pdl(k_sample_actor, dim3(1), dim3(32), 0, st, d);
+        if (t->batched_fwd) {
+            enqueue_forward(t, P_ALWAYS, col_end, tar, st, false, col_beg, col_end, 0x6);
+        } else {
+            enqueue_forward(t, P_CRITIC, col_end, tar, st, false);
+        }
+        // ---- critic: BuildProblem + UpdateNet (learning/NeuralNetTrainer.cpp:414-456, MACETrainer.cpp:222-247)
+        launch_pdl(k_vals, dim3(1), dim3(32), 0, st, d, P_CRITIC, 1, d.v1, 0, 0);
         enqueue_forward(t, P_CRITIC, col_beg, cur, st);
         launch_pdl(k_labels, dim3(1), dim3(256), 0, st, d, P_CRITIC, 0);
         enqueue_backward_update(t, P_CRITIC, st);
         // ---- actor: UpdateActorBatchBuffer + UpdateActor (learning/MACETrainer.cpp:541-626)
-        launch_pdl(k_sample_actor, dim3(1), dim3(32), 0, st, d);
         if (t->batched_fwd) {
-            // the candidates' s and s' go through the target net in ONE pass of 2 kB rows (two FC clusters side by side)
-            enqueue_forward(t, P_CAND, col_beg, tar, st, false, col_end);
-            launch_pdl(k_vals, dim3(1), dim3(32), 0, st, d, P_CAND, 0, d.v0, 0);
-            launch_pdl(k_vals, dim3(1), dim3(32), 0, st, d, P_CAND, 1, d.v1, kB);
+            launch_pdl(k_vals, dim3(1), dim3(32), 0, st, d, P_CAND, 0, d.v0, kB, 1);
+            launch_pdl(k_vals, dim3(1), dim3(32), 0, st, d, P_CAND, 1, d.v1, 2 * kB, 1);
         } else {
-            enqueue_forward(t, P_CAND, col_beg, tar, st, false);
-            launch_pdl(k_vals, dim3(1), dim3(32), 0, st, d, P_CAND, 0, d.v0, 0);
-            enqueue_forward(t, P_CAND, col_end, tar, st, false);
-            launch_pdl(k_vals, dim3(1), dim3(32), 0, st, d, P_CAND, 1, d.v1, 0);
+            enqueue_forward(t, P_CAND, col_beg, tar, st, false, -1, -1, 0x1);
+            launch_pdl(k_vals, dim3(1), dim3(32), 0, st, d, P_CAND, 0, d.v0, 0, 1);
+            enqueue_forward(t, P_CAND, col_end, tar, st, false, -1, -1, 0x1);
+            launch_pdl(k_vals, dim3(1), dim3(32), 0, st, d, P_CAND, 1, d.v1, 0, 1);
         }
         launch_pdl(k_actor_select, dim3(1), dim3(32), 0, st, d);
         enqueue_forward(t, P_ACTOR, col_beg, cur, st);
@@ -1156,11 +1165,11 @@ trl_trainer* trl_trainer_create(trl_handle* h, const double* p) {
     A(talloc(t, &d.pos_critic, d.cap)); A(talloc(t, &d.pos_actor, d.cap)); A(talloc(t, &d.critic_list, d.cap)); A(talloc(t, &d.actor_list, d.cap));
     A(talloc(t, &d.actor_batch, 4 * kB)); A(talloc(t, &d.c, 1));
     const int add_cap = std::max(h->B.tuple_cap, 4096);
-    A(talloc(t, &d.valid, add_cap)); A(talloc(t, &d.slot, add_cap)); A(talloc(t, &d.order, add_cap)); A(talloc(t, &d.ids, kB)); A(talloc(t, &d.cand, kB));
-    // xn, a2, t, catb, h, y hold 2 kB rows: the candidates' double pass (s and s' through the target net in one launch)
-    A(talloc(t, &d.xn, (size_t)2 * kB * d.S)); A(talloc(t, &d.a0, (size_t)kB * C0 * W0)); A(talloc(t, &d.a1, (size_t)kB * C1 * W1));
-    A(talloc(t, &d.a2, (size_t)2 * kB * C2 * W2)); A(talloc(t, &d.t, (size_t)2 * kB * T)); A(talloc(t, &d.catb, (size_t)2 * kB * d.cat));
-    A(talloc(t, &d.h, (size_t)2 * kB * H)); A(talloc(t, &d.hh, (size_t)4 * kB * HH)); A(talloc(t, &d.y, (size_t)2 * kB * d.n_out));
+    A(talloc(t, &d.valid, add_cap)); A(talloc(t, &d.slot, add_cap)); A(talloc(t, &d.order, add_cap)); A(talloc(t, &d.ids, kB)); A(talloc(t, &d.ids2, kB)); A(talloc(t, &d.cand, kB));
+    // xn, a2, t, catb, h, y hold 3 kB rows: the target net's triple pass (critic s', candidates' s and s' in one launch)
+    A(talloc(t, &d.xn, (size_t)3 * kB * d.S)); A(talloc(t, &d.a0, (size_t)kB * C0 * W0)); A(talloc(t, &d.a1, (size_t)kB * C1 * W1));
+    A(talloc(t, &d.a2, (size_t)3 * kB * C2 * W2)); A(talloc(t, &d.t, (size_t)3 * kB * T)); A(talloc(t, &d.catb, (size_t)3 * kB * d.cat));
+    A(talloc(t, &d.h, (size_t)3 * kB * H)); A(talloc(t, &d.hh, (size_t)4 * kB * HH)); A(talloc(t, &d.y, (size_t)3 * kB * d.n_out));
     A(talloc(t, &d.v0, kB)); A(talloc(t, &d.v1, kB)); A(talloc(t, &d.dy, (size_t)kB * d.n_out)); A(talloc(t, &d.dhh, (size_t)4 * kB * HH));
     A(talloc(t, &d.dh, (size_t)kB * H)); A(talloc(t, &d.dt, (size_t)kB * T)); A(talloc(t, &d.da2, (size_t)kB * C2 * W2));
     A(talloc(t, &d.da1, (size_t)kB * C1 * W1)); A(talloc(t, &d.da0, (size_t)kB * C0 * W0)); A(talloc(t, &d.mean, d.S)); A(talloc(t, &d.part, (size_t)kSplit * kB * T));
@@ -1196,7 +1205,7 @@ trl_trainer* trl_trainer_create(trl_handle* h, const double* p) {
             W.tip0_w = bl(6); W.tip0_b = bl(7); W.ip0_w = bl(8); W.ip0_b = bl(9);
             for (int q = 0; q < 4; ++q) { W.h0_w[q] = bl(10 + 4 * q); W.h0_b[q] = bl(11 + 4 * q); W.h1_w[q] = bl(12 + 4 * q); W.h1_b[q] = bl(13 + 4 * q); }
             W.in_off = W.in_scale = W.out_off = W.out_scale = nullptr;          // the minibatch arrives normalised; outputs stay normalised
-            if (trl_make_fc_maps(&t->fmaps[k], W.tip0_w, d.a2, 2 * kB)) {
+            if (trl_make_fc_maps(&t->fmaps[k], W.tip0_w, d.a2, 3 * kB)) {
                 for (void* q : t->allocs) cudaFree(q);
                 delete t;
                 return nullptr;
@@ -1357,7 +1366,7 @@ int trl_trainer_train(trl_trainer* t, int iters) {
         cudaGraphDestroy(graph);
         t->launches = before;
     }
-    const int per = 5 + t->d.steps_per_iter * (10 + (t->batched_fwd ? 4 * 3 : 5 * 16) + 2 * (t->fused_bwd ? 8 : 26));
+    const int per = 5 + t->d.steps_per_iter * (10 + (t->batched_fwd ? 3 * 3 : 5 * 16) + 2 * (t->fused_bwd ? 8 : 26));
     for (int i = 0; i < iters; ++i) {
         TCK(cudaGraphLaunch(t->train_graph, t->work()));
         t->launches += per;

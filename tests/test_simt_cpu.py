@@ -288,7 +288,7 @@ def test_trainer_kernels_vs_oracle(assets, monkeypatch):
             l0, l1 = g.KernelLaunches(), g1.KernelLaunches()
             g.Train(1)
             g1.Train(1)
-            assert (g.KernelLaunches() - l0, g1.KernelLaunches() - l1) == (43, 79)
+            assert (g.KernelLaunches() - l0, g1.KernelLaunches() - l1) == (40, 76)
             np.testing.assert_array_equal(g.get("theta"), g1.get("theta"))
             o.train()
             cg, co = g.counters(), o.counters()
