@@ -226,7 +226,7 @@ def test_env_groups_match_the_monolithic_launch(assets, monkeypatch):
     import deepterrainrl_b200 as trl
     dog = os.path.join(assets, "dog_slopes_mixed.trlpack")
     with simt_library():
-        n = 20           # G = 2 -> chunk 16: groups [0,16) [16,20)
+        n = 18           # G = 2 -> chunk 16: groups [0,16) [16,18)
         scs = []
         for G in ("1", "2"):
             monkeypatch.setenv("TRL_GROUPS", G)
@@ -242,7 +242,7 @@ def test_env_groups_match_the_monolithic_launch(assets, monkeypatch):
             sc.EnableExplore(True, 0.2, 0.025, 0.01)
         l0 = [sc.KernelLaunches() for sc in scs]
         nu = 0
-        while nu < 40 and (nu < 12 or scs[0].GetNumTuples() < n // 2):     # until the first gait cycles have ended (tuples exist)
+        while nu < 40 and (nu < 12 or scs[0].GetNumTuples() < 4):          # until the first gait cycles have ended (tuples exist)
             for sc in scs:
                 sc.Update(1.0 / 30.0)
             nu += 1
@@ -251,7 +251,7 @@ def test_env_groups_match_the_monolithic_launch(assets, monkeypatch):
         ref = scs[0]
         ra, fa, ea = ref.GetTuples(f64=True)
         ka = np.lexsort(np.column_stack([ea, fa, ra]).T[::-1])
-        assert ra.shape[0] >= n // 2
+        assert ra.shape[0] >= 4
         for sc in scs[1:]:
             for a, b in zip(ref.GetStateAll(), sc.GetStateAll()):
                 np.testing.assert_array_equal(a, b)
