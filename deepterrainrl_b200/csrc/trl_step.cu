@@ -540,7 +540,7 @@ __device__ __forceinline__ LinkC load_link(int lane, const LinkTables* t) {
 #define TRL_TREE_PREFIX2(a, b)                                                                  \
     do {                                                                                        \
         _Pragma("unroll") for (int r_ = 0; r_ < 4; ++r_) {                                      \
-            int an_ = (r_ == 0) ? (int)c.anc1 : ((r_ == 1) ? (int)c.anc2 : ((r_ == 2) ? (int)c.anc4 : (int)c.anc8)); \
+            const int an_ = (r_ == 0) ? kin_anc1 : ((r_ == 1) ? kin_anc2 : ((r_ == 2) ? kin_anc4 : kin_anc8));                 \
             double2* buf_ = trl_as2<double2>(xs + X_PFX + (r_ & 1) * 2 * kWarp);      \
             buf_[lane] = make_double2((a), (b));                                                \
             __syncwarp();                                                                       \
@@ -552,7 +552,7 @@ __device__ __forceinline__ LinkC load_link(int lane, const LinkTables* t) {
 #define TRL_TREE_PREFIX2(a, b)                                                                  \
     do {                                                                                        \
         _Pragma("unroll") for (int r_ = 0; r_ < 4; ++r_) {                                      \
-            int an_ = (r_ == 0) ? (int)c.anc1 : ((r_ == 1) ? (int)c.anc2 : ((r_ == 2) ? (int)c.anc4 : (int)c.anc8)); \
+            const int an_ = (r_ == 0) ? kin_anc1 : ((r_ == 1) ? kin_anc2 : ((r_ == 2) ? kin_anc4 : kin_anc8));                 \
             double ta_ = shf((a), an_), tb_ = shf((b), an_);                                    \
             (a) += ta_; (b) += tb_;                                                             \
         }                                                                                       \
@@ -563,6 +563,8 @@ __device__ __forceinline__ LinkC load_link(int lane, const LinkTables* t) {
 // outward kinematics: world rotation, joint origin (rel. O) and spatial velocity of every link
 __device__ __forceinline__ Kin kinematics(const LinkC& c, const EnvRegs& e TRL_KIN_XS_DECL) {
     Kin k;
+    // the link's table entries are read once per call (they live in shared memory; a read cannot move across the shuffles below)
+    const int kin_anc1 = c.anc1, kin_anc2 = c.anc2, kin_anc4 = c.anc4, kin_anc8 = c.anc8, kin_parent = c.parent, kin_depth = c.depth;
     double phi = e.q, w = e.qd;
     TRL_TREE_PREFIX2(phi, w);
     k.phi = phi; k.w = w;
@@ -574,22 +576,23 @@ __device__ __forceinline__ Kin kinematics(const LinkC& c, const EnvRegs& e TRL_K
         double2* buf = trl_as2<double2>(xs + X_PFX + 2 * 2 * kWarp);
         buf[lane] = make_double2(k.cw, k.sw);
         __syncwarp();
-        const double2 t = buf[c.parent];
+        const double2 t = buf[kin_parent];
         pcw = t.x; psw = t.y;
     }
 #else
-    double pcw = shf(k.cw, c.parent), psw = shf(k.sw, c.parent);
+    double pcw = shf(k.cw, kin_parent), psw = shf(k.sw, kin_parent);
 #endif
     double rx = 0.0, ry = 0.0;
-    if (c.depth > 0) { rx = pcw * c.ax - psw * c.ay; ry = psw * c.ax + pcw * c.ay; }
+    if (kin_depth > 0) { const double ax = c.ax, ay = c.ay; rx = pcw * ax - psw * ay; ry = psw * ax + pcw * ay; }
     TRL_TREE_PREFIX2(rx, ry);
     // v_j = v_root + sum over the chain of S_a qd_a,  S_a = (1, r_ay, -r_ax)
-    double vx = (c.depth > 0) ? e.qd * ry : e.oxd, vy = (c.depth > 0) ? -e.qd * rx : e.oyd;
-    if (c.depth < 0) { vx = 0.0; vy = 0.0; }
+    double vx = (kin_depth > 0) ? e.qd * ry : e.oxd, vy = (kin_depth > 0) ? -e.qd * rx : e.oyd;
+    if (kin_depth < 0) { vx = 0.0; vy = 0.0; }
     TRL_TREE_PREFIX2(vx, vy);
     k.rx = rx; k.ry = ry; k.vx = vx; k.vy = vy;
-    k.cx = rx + k.cw * c.bax - k.sw * c.bay;
-    k.cy = ry + k.sw * c.bax + k.cw * c.bay;
+    const double bax = c.bax, bay = c.bay;
+    k.cx = rx + k.cw * bax - k.sw * bay;
+    k.cy = ry + k.sw * bax + k.cw * bay;
     return k;
 }
 
@@ -627,12 +630,13 @@ __device__ __forceinline__ Kin kinematics(const LinkC& c, const EnvRegs& e TRL_K
 // Returns the clamped joint torque of link `lane` (0 for the root and idle lanes).
 __device__ double controller_torque(Lane& L, const LinkC& lc, const EnvRegs& e, const Kin& k, double* xs, int lane,
                                     double h, int contact) {
+    const double lk_mass = lc.mass;      // read once (shared-memory table; a read cannot move across the shuffles below)
     const ModelConst& m = c_model;
     const int nj = m.nj, nd = m.ndof, md = m.max_depth;
     double* M = xs + X_M;
 
     // ---- body inertia about O in world axes, RNEA accelerations with qdd = 0 and the reference's Cj
-    const double hx = lc.mass * k.cx, hy = lc.mass * k.cy, Io = lc.izz_c + lc.mass * (k.cx * k.cx + k.cy * k.cy);
+    const double hx = lk_mass * k.cx, hy = lk_mass * k.cy, Io = lc.izz_c + lk_mass * (k.cx * k.cx + k.cy * k.cy);
     double alx, aly;
     {
         // root: a0 = -g + R0 * cj, cj from cRBDUtil::BuildCjPlanar with c = s = cos(theta_dot) (sim/RBDUtil.cpp:821-822)
@@ -653,11 +657,11 @@ __device__ double controller_torque(Lane& L, const LinkC& lc, const EnvRegs& e, 
     // vals: composite inertia (Io, hx, hy, m) and subtree force (n, fx, fy)
     double vals[7];
     {
-        double hlx = -hy * k.w + lc.mass * k.vx, hly = hx * k.w + lc.mass * k.vy;
-        vals[0] = Io; vals[1] = hx; vals[2] = hy; vals[3] = lc.mass;
+        double hlx = -hy * k.w + lk_mass * k.vx, hly = hx * k.w + lk_mass * k.vy;
+        vals[0] = Io; vals[1] = hx; vals[2] = hy; vals[3] = lk_mass;
         vals[4] = (-hy * alx + hx * aly) + (k.vx * hly - k.vy * hlx);
-        vals[5] = lc.mass * alx - k.w * hly;
-        vals[6] = lc.mass * aly + k.w * hlx;
+        vals[5] = lk_mass * alx - k.w * hly;
+        vals[6] = lk_mass * aly + k.w * hlx;
         if (!lc.act) { vals[4] = vals[5] = vals[6] = 0.0; }
     }
     {
@@ -707,10 +711,10 @@ __device__ double controller_torque(Lane& L, const LinkC& lc, const EnvRegs& e, 
     // cRaptorController::IsActiveVFEffector(stance toe): stance foot on the ground during Contact / Down
     const bool active_vf = raptor && (state == rsContact || state == rsDown) && ((contact >> st_toe) & 1);
     {
-        double bvx = lc.mass * (k.vx - k.w * k.cy);
+        double bvx = lk_mass * (k.vx - k.w * k.cy);
         double comvx = warp_sum_all(bvx) / m.total_mass;
         if (raptor) {
-            double comx = warp_sum_all(lc.mass * k.cx) / m.total_mass;
+            double comx = warp_sum_all(lk_mass * k.cx) / m.total_mass;
             double toe_x = shf(k.cx, st_toe);
             if (lane == 0) {
                 bool first_half = state == rsContact || state == rsDown;
@@ -956,6 +960,7 @@ __device__ double controller_torque(Lane& L, const LinkC& lc, const EnvRegs& e, 
 // Updates e (q, qd, root translation) in place and returns the contact bitmask (same value in every lane).
 __device__ int physics_substep(const LinkC& lc, EnvRegs& e, const GroundView& g, const double* s_clx, const double* s_cly,
                                const int* s_cbody, int lane, double dt, double clear_y TRL_PHYS_XS_DECL TRL_REUSE_KIN_DECL) {
+    const double lk_mass = lc.mass;      // read once (shared-memory table; a read cannot move across the shuffles below)
     // per-body box tables (link frame): centre offset, axis rotation, half sizes -- staged by the kernel next to the corner tables
     const double *s_bax = s_clx + 4 * kMaxJoints, *s_bay = s_bax + kMaxJoints, *s_bc = s_bay + kMaxJoints, *s_bs = s_bc + kMaxJoints,
                  *s_hx = s_bs + kMaxJoints, *s_hy = s_hx + kMaxJoints;
@@ -970,14 +975,14 @@ __device__ int physics_substep(const LinkC& lc, EnvRegs& e, const GroundView& g,
 #endif
 
     // rigid inertia about O, bias force incl. gravity as an external force
-    const double hx = lc.mass * k.cx, hy = lc.mass * k.cy, Io = lc.izz_c + lc.mass * (k.cx * k.cx + k.cy * k.cy);
+    const double hx = lk_mass * k.cx, hy = lk_mass * k.cy, Io = lc.izz_c + lk_mass * (k.cx * k.cx + k.cy * k.cy);
     double ia[9];   // articulated inertia (a, bx, by, cxx, cxy, cyy) and bias force (n, fx, fy)
     {
-        double hlx = -hy * k.w + lc.mass * k.vx, hly = hx * k.w + lc.mass * k.vy;
-        ia[0] = Io; ia[1] = -hy; ia[2] = hx; ia[3] = lc.mass; ia[4] = 0.0; ia[5] = lc.mass;
+        double hlx = -hy * k.w + lk_mass * k.vx, hly = hx * k.w + lk_mass * k.vy;
+        ia[0] = Io; ia[1] = -hy; ia[2] = hx; ia[3] = lk_mass; ia[4] = 0.0; ia[5] = lk_mass;
         ia[6] = (k.vx * hly - k.vy * hlx) - (hx * m.gy - hy * m.gx);
-        ia[7] = -k.w * hly - lc.mass * m.gx;
-        ia[8] = k.w * hlx - lc.mass * m.gy;
+        ia[7] = -k.w * hly - lk_mass * m.gx;
+        ia[8] = k.w * hlx - lk_mass * m.gy;
         if (!lc.act) { ia[6] = ia[7] = ia[8] = 0.0; }
     }
     const double cvx = e.qd * (k.w * k.rx + k.vy), cvy = e.qd * (k.w * k.ry - k.vx);   // c_j = v_j x (S_j qd_j)
