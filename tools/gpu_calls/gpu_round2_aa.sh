@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, call AA: tuple intake with a wrapped replay ring (the steady state of a long run), 1 GPU; trainer / comm tests
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out/r2aa
 O=gpurun_out/r2aa
 timeout 600 python -m pytest tests/test_gpu_trainer.py tests/test_gpu_comm.py -m gpu -x -q > $O/pytest.txt 2>&1; echo "tests rc=$? $(tail -1 $O/pytest.txt)"

@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, call AB: shipped build after the trainer's merged target pass -- full GPU tier, smoke, trainer probe, bench
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out/r2ab
 O=gpurun_out/r2ab
 timeout 1200 python -m pytest tests -m gpu -x -q > $O/pytest_gpu.txt 2>&1; echo "pytest gpu rc=$? $(tail -1 $O/pytest_gpu.txt)"

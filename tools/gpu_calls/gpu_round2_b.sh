@@ -1,6 +1,6 @@
 #!/bin/bash
 # round-2 GPU call B: the batched decision path (TMA + DMMA) on hardware -- smoke under a timeout first, then tests, timelines, A/B
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out/r2b
 O=gpurun_out/r2b
 (cd tools/microbench && ./fp64_pipes) > $O/fp64_pipes.txt 2>&1; tail -6 $O/fp64_pipes.txt

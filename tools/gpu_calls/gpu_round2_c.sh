@@ -1,6 +1,6 @@
 #!/bin/bash
 # round-2 GPU call C: where does the batched decision path spend its time?  timelines + ncu of its two kernels
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out/r2c
 O=gpurun_out/r2c
 timeout 300 python tools/timeline_probe.py 4096 $O/timeline_v2.json > $O/timeline_v2.txt 2>&1; head -24 $O/timeline_v2.txt

@@ -1,5 +1,5 @@
 #!/bin/bash
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out/r2d
 O=gpurun_out/r2d
 timeout 300 python tools/fc_phase_probe.py > $O/fc_phases.txt 2>&1; cat $O/fc_phases.txt | tail -6

@@ -1,5 +1,5 @@
 #!/bin/bash
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out/r2e
 O=gpurun_out/r2e
 (cd tools/microbench && timeout 120 ./tma_stream) > $O/tma_stream.txt 2>&1; cat $O/tma_stream.txt

@@ -1,6 +1,6 @@
 #!/bin/bash
 # round-2 GPU call F (--gpus 2): the native exchange over NCCL between two ranks
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out/r2f
 O=gpurun_out/r2f
 N=${1:-2}

@@ -1,6 +1,6 @@
 #!/bin/bash
 # round-2 GPU call K: ncu evidence for the shipped build -- launch list of the bench command, full reports of the step / conv / FC kernels
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out/r2k
 O=gpurun_out/r2k
 # launch list of the same command the driver runs (graph launches expand to kernel launches under ncu)

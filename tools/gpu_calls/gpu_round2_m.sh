@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, call M: tcgen05 split-precision probe, env-group A/B of the step launches, group parity test
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out/r2m
 O=gpurun_out/r2m
 nvidia-smi --query-gpu=name,clocks.max.sm --format=csv,noheader

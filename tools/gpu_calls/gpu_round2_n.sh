@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, call N: tcgen05 split-precision probe; register-budget variants x env groups
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out/r2n
 O=gpurun_out/r2n
 timeout 700 python tools/tc_policy_probe.py --decisions 1000000 > $O/tc_policy.json 2> $O/tc_policy.err; echo "tc probe rc=$?"; tail -3 $O/tc_policy.err; cut -c1-3000 $O/tc_policy.json

@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, call O: full GPU test tier, trainer A/B (fused backward), bench with config 4, link_smem A/B, ncu evidence of the shipped build
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out/r2o
 O=gpurun_out/r2o
 timeout 1200 python -m pytest tests -m gpu -x -q > $O/pytest_gpu.txt 2>&1; echo "pytest gpu rc=$? $(tail -1 $O/pytest_gpu.txt)"

@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, call P: trainer with the merged candidate pass, shared-memory staging variants of the step kernel (A/B, two rounds)
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out/r2p
 O=gpurun_out/r2p
 timeout 600 python -m pytest tests/test_gpu_trainer.py tests/test_gpu_comm.py -m gpu -x -q > $O/pytest_trainer.txt 2>&1; echo "trainer tests rc=$? $(tail -1 $O/pytest_trainer.txt)"

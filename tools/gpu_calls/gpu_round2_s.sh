@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, call S: ground view in registers (product) -- parity, bench x2, fresh ncu capture of the step kernel for the next round of source-level analysis
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out/r2s
 O=gpurun_out/r2s
 timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_scenarios.py tests/test_gpu_ref_golden.py -m gpu -x -q > $O/pytest.txt 2>&1; echo "parity tests rc=$? $(tail -1 $O/pytest.txt)"

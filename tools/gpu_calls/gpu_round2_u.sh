@@ -1,9 +1,9 @@
 #!/bin/bash
-# round 2, call Q: CTA size of the step kernel (1 / 2 / 4 / 8 warps per CTA, 16 resident warps per SM in all)
-cd "$(dirname "$0")/.."
-mkdir -p gpurun_out/r2q
-O=gpurun_out/r2q
-for v in product cta2 cta1 cta8 product cta2 cta1 cta8; do
+# round 2, call U: shared-memory exchange variants re-measured on the round-2 final kernel
+cd "$(dirname "$0")/../.."
+mkdir -p gpurun_out/r2u
+O=gpurun_out/r2u
+for v in product accum_smem kin_smem outward_smem contact_smem smem_xchg product accum_smem smem_xchg; do
   if [ $v = product ]; then unset TRL_VARIANT; else export TRL_VARIANT=$v; fi
   timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -x -q > $O/parity_$v.txt 2>&1; echo "$v parity: $(tail -1 $O/parity_$v.txt)"
   timeout 300 python bench.py --steps 30 --warmup 5 --cpu-seconds 0 --config4 0 > $O/bench_$v.json 2> $O/bench_$v.err

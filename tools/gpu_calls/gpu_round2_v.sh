@@ -1,9 +1,9 @@
 #!/bin/bash
-# round 2, call T: joint-limit terms hoisted out of the ABA rounds (product) vs re-evaluated per round (no_hoist)
-cd "$(dirname "$0")/.."
-mkdir -p gpurun_out/r2t
-O=gpurun_out/r2t
-for v in product no_hoist product no_hoist; do
+# round 2, call V: reuse_kin and the two small shared-memory exchanges re-measured on the round-2 final kernel
+cd "$(dirname "$0")/../.."
+mkdir -p gpurun_out/r2v
+O=gpurun_out/r2v
+for v in product reuse_kin contact_smem contact_outward_smem product reuse_kin contact_smem contact_outward_smem; do
   if [ $v = product ]; then unset TRL_VARIANT; else export TRL_VARIANT=$v; fi
   timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -x -q > $O/parity_$v.txt 2>&1; echo "$v parity: $(tail -1 $O/parity_$v.txt)"
   timeout 300 python bench.py --steps 30 --warmup 5 --cpu-seconds 0 --config4 0 > $O/bench_$v.json 2> $O/bench_$v.err

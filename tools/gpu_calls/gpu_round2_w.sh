@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, call W: the shipped build -- full GPU test tier, bench (+ reference arm), side scenes, trainer probe, ncu evidence
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out/r2w
 O=gpurun_out/r2w
 timeout 1200 python -m pytest tests -m gpu -x -q > $O/pytest_gpu.txt 2>&1; echo "pytest gpu rc=$? $(tail -1 $O/pytest_gpu.txt)"
