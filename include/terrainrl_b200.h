@@ -12,6 +12,7 @@
  */
 #ifndef TERRAINRL_B200_H
 #define TERRAINRL_B200_H
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus

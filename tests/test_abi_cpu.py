@@ -31,6 +31,16 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(trl.scenario.EXPORTS)
 
 
+def test_public_header_is_self_contained_c99(tmp_path):
+    """include/terrainrl_b200.h is what a maintainer's cgo / ctypes / C++ binding includes first: it must compile on its own as C99 and as C++"""
+    import subprocess
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "terrainrl_b200.h"\nint main(void) { return 0; }\n')
+    inc = os.path.join(ROOT, "include")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", inc, "-fsyntax-only", str(src)], check=True)
+    subprocess.run(["g++", "-std=c++17", "-Wall", "-Werror", "-I", inc, "-fsyntax-only", "-x", "c++", str(src)], check=True)
+
+
 def test_null_handles_are_refused_with_a_message():
     """The reference asserts on misuse (scenarios/ScenarioTrain.cpp:282); across the ABI that is a non-zero return + trl_last_error."""
     import ctypes as C
